@@ -1,0 +1,254 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) on CPU.
+
+Run in the build container only:   python tests/golden/make_golden.py
+The fixtures are committed; the GPU box never needs /root/reference.
+
+For each of the five target models (CL/StandardRec, NRMS, NAML, LSTUR[con|ini], NPA) at a small
+shape the script stores: config, reference-initialised state_dict, a dense reference-format batch
+(with padded history slots, ragged title lengths and one fully padded history), and the reference's
+outputs: scores, user embeddings, trainer losses (MSE∘ReLU, BCE-with-logits, InfoNCE, total) and the
+gradient of the total loss w.r.t. every parameter.  Layer-level fixtures (additive / personalised /
+multi-head attention, GRU) and metric / loss known-answer values are stored too.
+"""
+import json
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+from _refshim import DotMap, load_reference  # noqa: E402
+
+load_reference()
+from xnrs.models import make_model  # noqa: E402
+from xnrs.models.components import layers  # noqa: E402
+import xnrs.training as T  # noqa: E402
+import xnrs.utils as U  # noqa: E402
+from xnrs.evaluation import metrics as M  # noqa: E402
+
+torch.set_num_threads(4)
+
+BASE = dict(scoring='dot', text_features=['title_emb'], catg_features=[], user_features=[], add_features=[],
+            title_emb_dim=16, total_emb_dim=16, d_backbone=32, n_heads=4, hist_len=4, st_hist_len=4, seq_len=5,
+            p_dropout=0., bias=False, n_categories=6, n_subcategories=9, n_users=11, cat_emb_dim=8, sub_emb_dim=8,
+            user_emb_dim=8, n_negatives=2, batch_size=4, contrastive_temperature=0.08, contrastive_lambda=0.1,
+            device='cpu')
+
+MODELS = {
+    'cl': dict(model='standard'),
+    'nrms': dict(model='NRMS', bias=False),
+    'naml': dict(model='NAML', text_features=['title_emb', 'abstract_emb'],
+                 catg_features=['category_index', 'subcategory_index']),
+    'lstur_con': dict(model='LSTUR', total_emb_dim=24, long_term_method='embedding', long_short_term_method='con',
+                      p_user_dropout=0.0, catg_features=['category_index'], user_features=['user_index']),
+    'lstur_ini': dict(model='LSTUR', total_emb_dim=24, long_term_method='embedding', long_short_term_method='ini',
+                      p_user_dropout=0.0, catg_features=['category_index'], user_features=['user_index']),
+    'npa': dict(model='NPA', user_features=['user_index']),
+}
+
+
+def make_batch(cfg, g, lstur=False):
+    B, H, N, S, D = cfg.batch_size, cfg.hist_len, cfg.n_negatives + 1, cfg.seq_len, cfg.d_backbone
+
+    def text(n, hist):
+        x = torch.randn(B, n, S, D, generator=g)
+        ln = torch.randint(1, S + 1, (B, n), generator=g)
+        if hist:
+            nh = torch.tensor([H, 2, 1, 3][:B])         # valid history items, front aligned
+            if not lstur:
+                nh[2] = 0                               # one user with a fully padded history
+            ln = ln * (torch.arange(n)[None, :] < nh[:, None])
+        m = (torch.arange(S)[None, None, :] < ln[:, :, None]).float().unsqueeze(-1)
+        return x * m, m                                 # padded tokens are zero rows (dataset.py:82-85)
+
+    hist, cand = {}, {}
+    for feat in cfg.text_features:
+        hist[feat], cand[feat] = text(H, True), text(N, False)
+    hm = hist['title_emb'][1].sum(2).clamp(0, 1).squeeze(-1)
+    for feat, hi in (('category_index', cfg.n_categories), ('subcategory_index', cfg.n_subcategories)):
+        if feat in cfg.catg_features:
+            hist[feat] = (torch.randint(1, hi + 1, (B, H), generator=g) * hm).int()     # pad label 0
+            cand[feat] = torch.randint(1, hi + 1, (B, N), generator=g).int()
+    other = {}
+    if 'user_index' in cfg.user_features:
+        other['user_index'] = torch.randint(1, cfg.n_users + 1, (B, 1), generator=g).int()
+    t = torch.zeros(B, N, 1)
+    t[:, 0] = 1
+    return {'user_features': {'history': hist, 'other': other}, 'candidate_features': cand, 'targets': t,
+            'main_theme': ['sport', 'news', 'sport', 'life'][:B]}
+
+
+def flat(prefix, obj, out):
+    if isinstance(obj, dict):
+        for k, v in obj.items():
+            flat(f'{prefix}/{k}', v, out)
+    elif isinstance(obj, (tuple, list)) and len(obj) == 2 and isinstance(obj[0], torch.Tensor):
+        out[prefix + '/x'], out[prefix + '/m'] = obj[0].numpy(), obj[1].numpy()
+    elif isinstance(obj, torch.Tensor):
+        out[prefix] = obj.numpy()
+
+
+def model_fixture(name, over, seed):
+    cfg = DotMap(dict(BASE, **over))
+    torch.manual_seed(seed)
+    model = make_model(cfg)
+    # default init leaves dummy_param at 0 and heads tiny; perturb so every path carries signal
+    with torch.no_grad():
+        for p in model.parameters():
+            if p.numel() > 1:
+                p.mul_(2.0)
+    model.eval()
+    g = torch.Generator().manual_seed(seed + 100)
+    batch = make_batch(cfg, g, lstur=name.startswith('lstur'))
+    out = {'cfg': np.array(json.dumps(dict(cfg)))}
+    for k, v in model.state_dict().items():
+        out['sd/' + k] = v.numpy().copy()
+    flat('batch', {k: v for k, v in batch.items() if k != 'main_theme'}, out)
+    out['batch/main_theme'] = np.array(batch['main_theme'])
+
+    scores = model(batch)
+    out['ref/scores'] = scores.detach().numpy()
+    fake = types.SimpleNamespace(temperature=cfg.contrastive_temperature)
+    labels = torch.tensor([{'sport': 0, 'news': 1, 'life': 2}[t] for t in batch['main_theme']])
+    l_rec = torch.nn.functional.mse_loss(torch.relu(scores), batch['targets'])
+    out['ref/loss_mse'] = l_rec.detach().numpy()
+    out['ref/loss_bce'] = torch.nn.functional.binary_cross_entropy_with_logits(scores, batch['targets']).detach().numpy()
+    if hasattr(model, 'get_user_embeddings'):
+        ue = model.get_user_embeddings(batch)
+        out['ref/user_emb'] = ue.detach().numpy()
+        l_cl = T.ContrastiveRankingTrainer._compute_contrastive_loss(fake, ue, labels)
+        total = l_rec + cfg.contrastive_lambda * l_cl
+        out['ref/loss_cl'] = l_cl.detach().numpy()
+    else:                                   # NPA: no CL hook exists -> MSE trainer
+        total = l_rec
+    out['ref/loss_total'] = total.detach().numpy()
+    model.zero_grad()
+    total.backward()
+    for k, p in model.named_parameters():
+        out['grad/' + k] = (p.grad if p.grad is not None else torch.zeros_like(p)).numpy().copy()
+    np.savez_compressed(os.path.join(HERE, f'model_{name}.npz'), **out)
+    print(name, 'loss', float(total), 'params', sum(p.numel() for p in model.parameters()))
+
+
+def layer_fixtures():
+    g = torch.Generator().manual_seed(7)
+    out = {}
+    R, L, F = 6, 7, 24
+    x = torch.randn(R, L, F, generator=g)
+    ln = torch.tensor([7, 3, 1, 0, 5, 7])
+    m = (torch.arange(L)[None, :] < ln[:, None]).float().unsqueeze(-1)
+    out['x'], out['m'] = x.numpy(), m.numpy()
+
+    torch.manual_seed(11)
+    aa = layers.AdditiveAttention(F, 256)
+    for k, v in aa.state_dict().items():
+        out['aa/' + k] = v.numpy().copy()
+    o, a = aa(x, m, return_weights=True)
+    out['aa/out'], out['aa/a'] = o.detach().numpy(), a.detach().numpy()
+    out['aa/out_nomask'] = aa(x).detach().numpy()
+
+    mha = layers.MultiHeadAttention(4, F).eval()
+    for k, v in mha.state_dict().items():
+        out['mha/' + k] = v.numpy().copy()
+    out['mha/out'] = mha(x, m).detach().numpy()
+    xp = x.clone()
+    xp[0, 6] += 1.0                                   # perturb a key that is *valid* in row 0
+    xq = x.clone()
+    xq[1, 5] += 1.0                                   # perturb a PADDED key of row 1: valid rows still change
+    out['mha/out_perturb_padkey'] = mha(xq, m).detach().numpy()
+
+    pa = layers.PersonalizedAttention(F, 128, 8)
+    q = torch.randn(R, 1, 8, generator=g)
+    for k, v in pa.state_dict().items():
+        out['pa/' + k] = v.numpy().copy()
+    out['pa/q'] = q.numpy()
+    out['pa/out'] = pa(q, x, m).detach().numpy()
+
+    out['mm/out'] = layers.MaskedMean()(x, m).detach().numpy()
+
+    gru = torch.nn.GRU(F, 10, batch_first=True)
+    for k, v in gru.state_dict().items():
+        out['gru/' + k] = v.numpy().copy()
+    lens = torch.tensor([7, 3, 1, 2, 5, 7])
+    h0 = torch.randn(1, R, 10, generator=g)
+    pk = torch.nn.utils.rnn.pack_padded_sequence(x, lens, batch_first=True, enforce_sorted=False)
+    out['gru/lens'] = lens.numpy()
+    out['gru/h0'] = h0[0].numpy()
+    out['gru/h_zero'] = gru(pk)[1][0].detach().numpy()
+    out['gru/h_init'] = gru(pk, h0)[1][0].detach().numpy()
+    np.savez_compressed(os.path.join(HERE, 'layers.npz'), **out)
+
+
+def loss_metric_fixtures():
+    out = {}
+    g = torch.Generator().manual_seed(123)
+    e = torch.randn(6, 8, generator=g)
+    lab = torch.tensor([0, 1, 0, 2, 1, 0])
+    fake = types.SimpleNamespace(temperature=0.08)
+    out['cl/e'], out['cl/labels'] = e.numpy(), lab.numpy()
+    out['cl/loss'] = T.ContrastiveRankingTrainer._compute_contrastive_loss(fake, e, lab).numpy()
+    e2 = torch.randn(40, 16, generator=g)
+    lab2 = torch.randint(0, 6, (40,), generator=g)
+    lab2[7] = 17                                        # an anchor without positives
+    out['cl2/e'], out['cl2/labels'] = e2.numpy(), lab2.numpy()
+    out['cl2/loss'] = T.ContrastiveRankingTrainer._compute_contrastive_loss(fake, e2, lab2).numpy()
+
+    p = torch.tensor([[.5], [-.2]])
+    n = torch.tensor([[.1, -.3, .2, 0.], [.4, .1, -.5, .3]])
+    out['nll/p'], out['nll/n'] = p.numpy(), n.numpy()
+    out['nll/mean'] = U.ranking_loss(p, n).numpy()
+    out['nll/none'] = U.ranking_loss(p, n, reduction='none').numpy()
+
+    # metrics: tie-free random impressions through the reference functions unchanged
+    rng = np.random.default_rng(5)
+    ys, yt, vals = [], [], []
+    for i in range(64):
+        n_pos, n_neg = int(rng.integers(1, 4)), int(rng.integers(1, 70))
+        t = np.array([1.] * n_pos + [0.] * n_neg, dtype=np.float32)
+        s = rng.permutation(n_pos + n_neg).astype(np.float32) / 7.0          # distinct scores
+        ys.append(s)
+        yt.append(t)
+        vals.append([M.auc_score(t, s), M.rr_score(t, s), M.ndcg_score(t, s, 5), M.ndcg_score(t, s, 10),
+                     M.ctr_score(t, s, 1), M.ctr_score(t, s, 10)])
+    out['met/offsets'] = np.cumsum([0] + [len(s) for s in ys]).astype(np.int64)
+    out['met/scores'], out['met/targets'] = np.concatenate(ys), np.concatenate(yt)
+    out['met/values'] = np.array(vals, dtype=np.float64)
+
+    # tied (post-ReLU style) scores: reference functions with argsort forced to kind='stable'
+    # (the documented canonical tie policy); AUC is the stock sklearn call.
+    real_argsort = np.argsort
+    ys, yt, vals = [], [], []
+    for i in range(64):
+        n_pos, n_neg = int(rng.integers(1, 4)), int(rng.integers(1, 40))
+        t = np.array([1.] * n_pos + [0.] * n_neg, dtype=np.float32)
+        s = np.maximum(rng.normal(size=n_pos + n_neg).astype(np.float32), 0).round(1)
+        M.np.argsort = lambda a, *aa, **kw: real_argsort(a, kind='stable')
+        try:
+            row = [M.auc_score(t, s), M.rr_score(t, s), M.ndcg_score(t, s, 5), M.ndcg_score(t, s, 10),
+                   M.ctr_score(t, s, 1), M.ctr_score(t, s, 10)]
+        finally:
+            M.np.argsort = real_argsort
+        ys.append(s)
+        yt.append(t)
+        vals.append(row)
+    out['mett/offsets'] = np.cumsum([0] + [len(s) for s in ys]).astype(np.int64)
+    out['mett/scores'], out['mett/targets'] = np.concatenate(ys), np.concatenate(yt)
+    out['mett/values'] = np.array(vals, dtype=np.float64)
+
+    t = np.array([1, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 1], dtype=np.float32)
+    s = np.array([.9, .8, .1, .4, .3, .05, .7, .2, .6, 0, .55, .35], dtype=np.float32)
+    out['kat/t'], out['kat/s'] = t, s
+    out['kat/values'] = np.array([M.auc_score(t, s), M.rr_score(t, s), M.ndcg_score(t, s, 5),
+                                  M.ndcg_score(t, s, 10), M.ctr_score(t, s, 1), M.ctr_score(t, s, 10)])
+    np.savez_compressed(os.path.join(HERE, 'loss_metrics.npz'), **out)
+
+
+if __name__ == '__main__':
+    for i, (name, over) in enumerate(MODELS.items()):
+        model_fixture(name, over, seed=20 + i)
+    layer_fixtures()
+    loss_metric_fixtures()
+    print('golden fixtures written to', HERE)

@@ -1,0 +1,167 @@
+/*
+ * xnrs_b200 — C ABI of the B200 (sm_100a) kernels behind the xnrs bi-encoder hot path.
+ *
+ * The reference (tan9zj/xnrs) has no FFI: its hot path is PyTorch eager code.  This header is the
+ * drop-in boundary a maintainer binds instead (ctypes stub in INTEGRATION.md): every entry point
+ * takes plain device pointers, sizes and a CUDA stream, returns 0 on success and a negative code on
+ * error (message via xnrs_last_error()).  No torch types, no hidden streams, no host sync, no CPU
+ * fallback.  All tensors are dense row-major fp32 unless stated; index tensors are int32.
+ * Each group cites the reference lines (relative to the reference repo) it replaces.
+ */
+#ifndef XNRS_B200_H
+#define XNRS_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *xnrs_stream_t; /* cudaStream_t */
+
+enum { XNRS_OK = 0, XNRS_ERR_ARG = -1, XNRS_ERR_CUDA = -2, XNRS_ERR_UNSUPPORTED = -3 };
+enum { XNRS_ACT_NONE = 0, XNRS_ACT_RELU = 1, XNRS_ACT_TANH = 2, XNRS_ACT_RELU_MASK = 3 };
+/* arithmetic of the GEMM-shaped ops: exact fp32 FMA, 3xTF32 split (fp32-accurate, tensor cores),
+ * single-pass TF32, or BF16 operands with fp32 accumulation */
+enum { XNRS_PREC_FP32 = 0, XNRS_PREC_TF32X3 = 1, XNRS_PREC_TF32 = 2, XNRS_PREC_BF16 = 3 };
+enum { XNRS_LOSS_MSE_RELU = 0, XNRS_LOSS_BCE_LOGITS = 1, XNRS_LOSS_NLL = 2 };
+
+int xnrs_version(void);
+const char *xnrs_last_error(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+long long xnrs_launch_count(void);
+/* 1 when the running device is compute capability 10.x */
+int xnrs_device_is_sm100(void);
+
+/* ---- row G: gather (xnrs/data/dataset.py:63-65,77-85,97-109; news_encoding.py:45-47) ---------- */
+/* news ids (R) -> flat token-row ids (R*S) and token mask (R*S, 1.0 where token != 0) */
+int xnrs_expand_titles(const int *title_tokens, long long n_news, int S, const int *news_ids, long long R,
+                       int *token_rows, float *mask, xnrs_stream_t st);
+/* out[r,:] = table[rows[r],:]  (bit-exact copy; D % 4 == 0) */
+int xnrs_gather_rows(const float *table, long long V, int D, const int *rows, long long R, float *out,
+                     long long ld_out, xnrs_stream_t st);
+/* dtable[rows[r],:] += dout[r,:]  (nn.Embedding backward: lstur.py:94-98, npa.py:12-15, naml.py:34-47);
+ * rows equal to skip_row (padding_idx, or -1 for none) receive nothing */
+int xnrs_scatter_add_rows(float *dtable, long long V, int D, const int *rows, long long R, const float *dout,
+                          long long ld_dout, int skip_row, xnrs_stream_t st);
+
+/* ---- GEMM (every nn.Linear / matmul on the path: layers.py:60,94-95,128-130,154; news_encoding.py:55-56)
+ * C[M,N] (=|+=) act( opA(A)[M,K] * opB(B)[K,N] + bias[N] ).  transA=0: A stored MxK (lda), 1: KxM.
+ * transB=0: B stored KxN (ldb), 1: NxK (an nn.Linear weight).  a_rows / b_rows (nullable) gather the
+ * STORED rows of A / B through an index (the fused table gather of row G).  act RELU_MASK multiplies by
+ * (aux > 0) (ReLU backward), aux has C's layout.  split_k > 1 accumulates partial sums atomically
+ * (requires accumulate semantics: C must hold the initial value; bias added once; act must be NONE). */
+int xnrs_gemm(int transA, int transB, long long M, long long N, long long K, const float *A, long long lda,
+              const int *a_rows, const float *B, long long ldb, const int *b_rows, float *C, long long ldc,
+              const float *bias, int act, const float *aux, int accumulate, int split_k, int precision,
+              xnrs_stream_t st);
+/* out[N] += column sums of X[M,N] (bias gradients) */
+int xnrs_colsum(const float *X, long long M, long long N, long long ldx, float *out, xnrs_stream_t st);
+/* y = a*x + b*y elementwise; a_dev (nullable) is a device scalar multiplied into a */
+int xnrs_axpby(long long n, float a, const float *a_dev, const float *x, float b, float *y, xnrs_stream_t st);
+int xnrs_relu(long long n, const float *x, float *y, xnrs_stream_t st);
+int xnrs_relu_bwd(long long n, const float *y, const float *dy, float *dx, xnrs_stream_t st);
+/* out (cols,rows) = in (rows,cols)^T */
+int xnrs_transpose(const float *in, long long rows, long long cols, float *out, xnrs_stream_t st);
+/* inverted dropout y = x * keep / (1-p)  (nn.Dropout: lstur.py:112,135; layers.py:148 lives inside xnrs_mha_*).
+ * keep (nullable, n floats 0/1) is an explicit mask, else a counter-based generator seeded by `seed` */
+int xnrs_dropout(long long n, const float *x, const float *keep, float p, unsigned long long seed, float *y,
+                 xnrs_stream_t st);
+
+/* ---- row A: additive-attention pooling (layers.py:47-69) -------------------------------------
+ * hid = tanh(fc1 x) (R*L, A) comes from xnrs_gemm(act=TANH).  x rows are x[r*L+l] or, with x_rows,
+ * table rows x[x_rows[r*L+l]].  mask nullable (R*L).  attn (R*L) and pooled (R,F) are outputs. */
+int xnrs_addpool_fwd(const float *x, const int *x_rows, const float *mask, const float *hid, const float *w2,
+                     const float *b2, long long R, int L, int F, int A, float *attn, float *pooled,
+                     xnrs_stream_t st);
+/* d_hid (R*L,A) = grad wrt the fc1 pre-activation; d_w2 (A), d_b2 (1) accumulate; d_x (nullable, R*L,F)
+ * receives a_s * d_pooled (the fc1 path is added by the caller's GEMM); d_attn (nullable) is an
+ * incoming gradient on the returned weights */
+int xnrs_addpool_bwd(const float *x, const int *x_rows, const float *mask, const float *hid, const float *w2,
+                     const float *attn, const float *d_pooled, const float *d_attn, long long R, int L, int F,
+                     int A, float *d_hid, float *d_w2, float *d_b2, float *d_x, xnrs_stream_t st);
+/* ---- row P: personalised attention (layers.py:88-101): logit = <tanh(x_fc x), q_fc(q)> ---------
+ * hid (R*L,A) = tanh(x_fc x); qh (Rq,A) = q_fc(q); title r uses query row r / rows_per_query */
+int xnrs_perspool_fwd(const float *x, const int *x_rows, const float *mask, const float *hid, const float *qh,
+                      long long R, int L, int F, int A, int rows_per_query, float *attn, float *pooled,
+                      xnrs_stream_t st);
+int xnrs_perspool_bwd(const float *x, const int *x_rows, const float *mask, const float *hid, const float *qh,
+                      const float *attn, const float *d_pooled, long long R, int L, int F, int A,
+                      int rows_per_query, float *d_hid, float *d_qh, float *d_x, xnrs_stream_t st);
+/* masked mean pooling (layers.py:25-37) */
+int xnrs_meanpool_fwd(const float *x, const float *mask, long long R, int L, int F, float *pooled,
+                      xnrs_stream_t st);
+/* collapsed mask: clamp(sum_l m, 0, 1) (xnrs/utils.py:74-75) */
+int xnrs_collapse_mask(const float *mask, long long R, int L, float *out, xnrs_stream_t st);
+
+/* ---- row M: multi-head self-attention core (layers.py:133-151) -------------------------------
+ * q,k,v,o: (R,L,h*dk) with row stride ld.  QUERY-axis mask (R*L, nullable): masked query rows attend
+ * uniformly, keys are never masked.  Dropout on the normalised weights: keep (nullable, R*h*L*L 0/1)
+ * is an explicit keep mask; else if p_drop > 0 a Philox stream (seed, per (r,head,i,j) counter) is used.
+ * lse (R*h*L) is saved for the backward. */
+int xnrs_mha_fwd(const float *q, const float *k, const float *v, long long ld, const float *mask, long long R,
+                 int L, int h, int dk, const float *keep, float p_drop, unsigned long long seed, float *o,
+                 float *lse, xnrs_stream_t st);
+int xnrs_mha_bwd(const float *q, const float *k, const float *v, const float *o, const float *d_o, long long ld,
+                 const float *mask, const float *lse, long long R, int L, int h, int dk, const float *keep,
+                 float p_drop, unsigned long long seed, float *dq, float *dk_, float *dv, xnrs_stream_t st);
+
+/* ---- row U-lstur: GRU over the front-aligned history, final state at the true length
+ * (lstur.py:139-153, torch.nn.GRU gate order r,z,n).  gi = x W_ih^T + b_ih (B*L,3Hd) from xnrs_gemm;
+ * w_hh_t is W_hh transposed (Hd,3Hd).  lengths (B) int32.  Saves hs (B,L,Hd) = the state BEFORE each
+ * step and gates (B,L,4Hd) = r,z,n,gh_n. */
+int xnrs_gru_fwd(const float *gi, const float *w_hh_t, const float *b_hh, const float *h0, const int *lengths,
+                 long long B, int L, int Hd, float *hs, float *gates, float *h_out, xnrs_stream_t st);
+/* d_gi (B*L,3Hd), d_gh (B*L,3Hd) and d_h0 (B,Hd) out; w_hh is the untransposed (3Hd,Hd) weight */
+int xnrs_gru_bwd(const float *d_h_out, const float *w_hh, const int *lengths, const float *hs,
+                 const float *gates, long long B, int L, int Hd, float *d_gi, float *d_gh, float *d_h0,
+                 xnrs_stream_t st);
+int xnrs_lengths_from_mask(const float *mask, long long B, int L, int *lengths, xnrs_stream_t st);
+
+/* ---- rows S + L-*: dot scoring (scoring.py:12-23) fused with the trainer losses
+ * (training.py:336-337, 378-392; utils.py:117-131).  u (B,T), c (B,N,T), targets/weights (B*N).
+ * Outputs: scores (B*N raw dot products), preds (B*N activated: relu for MSE, raw otherwise),
+ * loss (1, overwritten), and — when d_u/d_c are non-null — gradients of the loss (times grad_scale).
+ * With u == NULL, c holds (B,N) scores computed upstream and d_c (B,N) receives d loss / d score. */
+int xnrs_score_loss(const float *u, const float *c, const float *targets, const float *weights, int kind,
+                    long long B, int N, int T, float grad_scale, float *scores, float *preds, float *loss,
+                    float *d_u, float *d_c, xnrs_stream_t st);
+/* standalone scorer and its backward: s[b,n] = <c[b,n], u[b]> */
+int xnrs_dot_score(const float *u, const float *c, long long B, int N, int T, float *scores, xnrs_stream_t st);
+int xnrs_dot_score_bwd(const float *u, const float *c, const float *d_s, long long B, int N, int T, float *d_u,
+                       float *d_c, xnrs_stream_t st);
+
+/* ---- row L-cl: supervised InfoNCE (training.py:433-472) ----------------------------------------
+ * anchors = rows [row0, row0+Ba) of the Bk gathered embeddings emb (Bk,E); labels (Bk).
+ * stage 1 writes normalised embeddings ehat (Bk,E) and inv_norm (Bk); the caller forms
+ * sim = ehat[row0:row0+Ba] ehat^T with xnrs_gemm; stage 2 turns sim (Ba,Bk) into the un-normalised
+ * gradient G in place and accumulates stats[0] += sum of anchor terms, stats[1] += anchors with positives.
+ * stage 3 (after an optional all-reduce of stats) writes loss = stats[0]/(stats[1]+1e-8).
+ * stage 4 maps d_ehat (Bk,E) (= G ehat_k on anchor rows + G^T ehat_a, from xnrs_gemm) to d_emb. */
+int xnrs_infonce_normalize(const float *emb, long long Bk, int E, float *ehat, float *inv_norm, xnrs_stream_t st);
+int xnrs_infonce_rows(float *sim, const int *labels, long long Ba, long long Bk, long long row0,
+                      float temperature, float *stats, xnrs_stream_t st);
+int xnrs_infonce_finalize(const float *stats, float *loss, xnrs_stream_t st);
+int xnrs_infonce_normalize_bwd(const float *d_ehat, const float *ehat, const float *inv_norm, const float *stats,
+                               float grad_scale, long long Bk, int E, float *d_emb, xnrs_stream_t st);
+
+/* ---- rows E + Me: per-impression scoring and ranking metrics (training.py:194-227; metrics.py:7-44)
+ * CSR impressions: candidates of impression i are cand_ids[offsets[i]:offsets[i+1]].  score =
+ * act(<user[i], news_vecs[cand]>) (act: 0 raw, 1 relu, 2 sigmoid), then nan_to_num(nan 0, +inf 1, -inf 0).
+ * If user == NULL, `scores_io` already holds the scores.  metrics_out (n_imp,6) doubles:
+ * auc, rr, ndcg@5, ndcg@10, ctr@1, ctr@10.  Tie order: descending score, then descending index. */
+int xnrs_eval_impressions(const float *user, const float *news_vecs, int T, const int *cand_ids,
+                          const long long *offsets, const float *targets, long long n_imp, int act,
+                          float *scores_io, double *metrics_out, xnrs_stream_t st);
+/* sums[0..5] += column sums over impressions with a finite auc, sums[6] += their count */
+int xnrs_metric_sums(const double *metrics, long long n_imp, double *sums, xnrs_stream_t st);
+
+/* ---- row Opt: Adam, torch defaults (training.py:39), one launch over a flat parameter buffer ---- */
+/* bias corrections come from the host `step` (>= 1) or, when bc_dev is non-null, from the device pair
+ * {1/(1-b1^t), 1/sqrt(1-b2^t)} that xnrs_adam_tick maintains (CUDA-graph replay keeps counting) */
+int xnrs_adam_step(float *p, const float *g, float *m, float *v, long long n, float lr, float beta1, float beta2,
+                   float eps, int step, const float *bc_dev, float grad_scale, xnrs_stream_t st);
+int xnrs_adam_tick(int *step_dev, float beta1, float beta2, float *bc_dev, xnrs_stream_t st);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XNRS_B200_H */

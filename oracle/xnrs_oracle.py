@@ -363,6 +363,8 @@ def contrastive_loss(emb: Tensor, labels: Tensor, temperature: float) -> Tensor:
 def theme_labels(themes) -> Tensor:
     """training.py:414-417 maps theme strings to indices through a python set (arbitrary but
     consistent numbering); the loss only uses label *equality*, so any consistent numbering works."""
+    if isinstance(themes, torch.Tensor):
+        return themes.long()
     order = {}
     return torch.tensor([order.setdefault(t, len(order)) for t in themes], dtype=torch.long)
 

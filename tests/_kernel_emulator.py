@@ -1,0 +1,327 @@
+"""CPU stand-in for the C-ABI entry points — TEST INFRASTRUCTURE for the `-m "not gpu"` suite only.
+
+It lets the *host logic* (argument marshalling, autograd glue, module wiring, state_dict layout, the
+trainer hooks, the data-parallel plumbing over gloo) be exercised in a container without a GPU, by
+replacing ``xnrs_b200.kernels.call`` with an executable specification of every entry point's contract
+written in plain torch.  It is never imported by the package, bench.py or the GPU tests: the product has
+no CPU path, and `tests/test_gpu_*.py` run the real kernels through the real ``call``.
+"""
+import math
+
+import torch
+
+from xnrs_b200 import kernels as K
+
+
+def _rows(x, rows):
+    return x if rows is None else x[rows.long()]
+
+
+def _kf(keep, p, shape):
+    if keep is not None:
+        return keep.reshape(shape)
+    if p > 0:
+        raise NotImplementedError('emulator only supports explicit keep masks')
+    return torch.ones(shape)
+
+
+def call(name, *a):
+    fn = globals().get('_' + name)
+    if fn is None:
+        raise NotImplementedError(name)
+    fn(*[x.t if isinstance(x, K._Strided) else x for x in a])
+
+
+def _xnrs_expand_titles(title_tokens, n_news, S, news_ids, R, rows, mask):
+    tok = title_tokens[news_ids.long()].reshape(-1)
+    rows.copy_(tok)
+    if mask is not None:
+        mask.copy_((tok != 0).float())
+
+
+def _xnrs_gather_rows(table, V, D, rows, R, out, ld):
+    out.copy_(table[rows.long()])
+
+
+def _xnrs_scatter_add_rows(dtable, V, D, rows, R, dout, ld, skip):
+    keep = rows != skip
+    dtable.index_add_(0, rows[keep].long(), dout[keep])
+
+
+def _xnrs_gemm(ta, tb, M, N, K_, A, lda, a_rows, B, ldb, b_rows, C, ldc, bias, act, aux, accumulate, split_k, prec):
+    a = _rows(A, a_rows)
+    b = _rows(B, b_rows)
+    a = a.T if ta else a
+    b = b.T if tb else b
+    y = a @ b
+    assert y.shape == (M, N) and a.shape[1] == K_
+    if bias is not None:
+        y = y + bias
+    if act == K.ACT_RELU:
+        y = torch.relu(y)
+    elif act == K.ACT_TANH:
+        y = torch.tanh(y)
+    elif act == K.ACT_RELU_MASK:
+        y = y * (aux > 0)
+    if accumulate:
+        C.add_(y)
+    else:
+        C.copy_(y)
+
+
+def _xnrs_colsum(X, M, N, ldx, out):
+    out.add_(X.sum(0))
+
+
+def _xnrs_axpby(n, a, a_dev, x, b, y):
+    aa = a * (float(a_dev) if a_dev is not None else 1.0)
+    y.copy_(aa * x + (b * y if b != 0 else 0))
+
+
+def _xnrs_relu(n, x, y):
+    y.copy_(torch.relu(x))
+
+
+def _xnrs_relu_bwd(n, y, dy, dx):
+    dx.copy_(dy * (y > 0))
+
+
+def _xnrs_transpose(inp, rows, cols, out):
+    out.copy_(inp.reshape(rows, cols).T)
+
+
+def _xnrs_dropout(n, x, keep, p, seed, y):
+    y.copy_(x * _kf(keep, p, x.shape) / (1 - p))
+
+
+def _pool(x, x_rows, mask, logits, R, L, F_):
+    xr = _rows(x, x_rows).reshape(R, L, F_)
+    e = torch.exp(logits.reshape(R, L))
+    if mask is not None:
+        e = e * mask.reshape(R, L)
+    a = e / (e.sum(1, keepdim=True) + 1e-8)
+    return a, (a.unsqueeze(-1) * xr).sum(1), xr
+
+
+def _xnrs_addpool_fwd(x, x_rows, mask, hid, w2, b2, R, L, F_, A, attn, pooled):
+    a, p, _ = _pool(x, x_rows, mask, hid @ w2 + b2, R, L, F_)
+    attn.copy_(a)
+    pooled.copy_(p)
+
+
+def _pool_bwd(xr, attn, d_pooled, d_attn, R, L):
+    da = (xr * d_pooled.unsqueeze(1)).sum(-1)
+    if d_attn is not None:
+        da = da + d_attn.reshape(R, L)
+    a = attn.reshape(R, L)
+    return a * (da - (a * da).sum(1, keepdim=True))
+
+
+def _xnrs_addpool_bwd(x, x_rows, mask, hid, w2, attn, d_pooled, d_attn, R, L, F_, A, d_hid, d_w2, d_b2, d_x):
+    xr = _rows(x, x_rows).reshape(R, L, F_)
+    dl = _pool_bwd(xr, attn, d_pooled, d_attn, R, L).reshape(-1)
+    d_hid.copy_(dl[:, None] * w2[None, :] * (1 - hid * hid))
+    d_w2.add_((dl[:, None] * hid).sum(0))
+    d_b2.add_(dl.sum())
+    if d_x is not None:
+        d_x.copy_((attn.reshape(R, L, 1) * d_pooled.unsqueeze(1)).reshape(R * L, F_))
+
+
+def _xnrs_perspool_fwd(x, x_rows, mask, hid, qh, R, L, F_, A, rpq, attn, pooled):
+    q = qh.repeat_interleave(rpq, 0).repeat_interleave(L, 0)
+    a, p, _ = _pool(x, x_rows, mask, (hid * q).sum(-1), R, L, F_)
+    attn.copy_(a)
+    pooled.copy_(p)
+
+
+def _xnrs_perspool_bwd(x, x_rows, mask, hid, qh, attn, d_pooled, R, L, F_, A, rpq, d_hid, d_qh, d_x):
+    xr = _rows(x, x_rows).reshape(R, L, F_)
+    dl = _pool_bwd(xr, attn, d_pooled, None, R, L).reshape(-1)
+    q = qh.repeat_interleave(rpq, 0).repeat_interleave(L, 0)
+    d_hid.copy_(dl[:, None] * q * (1 - hid * hid))
+    contrib = (dl[:, None] * hid).reshape(R // rpq, rpq * L, A).sum(1)
+    d_qh.add_(contrib)
+    if d_x is not None:
+        d_x.copy_((attn.reshape(R, L, 1) * d_pooled.unsqueeze(1)).reshape(R * L, F_))
+
+
+def _xnrs_meanpool_fwd(x, mask, R, L, F_, pooled):
+    m = mask.reshape(R, L, 1)
+    pooled.copy_((x.reshape(R, L, F_) * m).sum(1) / (m.sum(1) + 1e-8))
+
+
+def _xnrs_collapse_mask(mask, R, L, out):
+    out.copy_(mask.reshape(R, L).sum(1).clamp(0, 1))
+
+
+def _att(q, k, v, mask, R, L, h, dk, keep, p):
+    qh, kh, vh = (t.reshape(R, L, h, dk).transpose(1, 2) for t in (q, k, v))
+    s = qh @ kh.transpose(-1, -2) / math.sqrt(dk)
+    if mask is not None:
+        s = s.masked_fill(mask.reshape(R, 1, L, 1) == 0, -1e9)
+    pr = torch.softmax(s, -1)
+    return pr * _kf(keep, p, pr.shape) / (1 - p), vh
+
+
+def _xnrs_mha_fwd(q, k, v, ld, mask, R, L, h, dk, keep, p, seed, o, lse):
+    pr, vh = _att(q, k, v, mask, R, L, h, dk, keep, p)
+    o.copy_((pr @ vh).transpose(1, 2).reshape(R * L, h * dk))
+
+
+def _xnrs_mha_bwd(q, k, v, o, d_o, ld, mask, lse, R, L, h, dk, keep, p, seed, dq, dk_, dv):
+    qq, kk, vv = (t.detach().clone().requires_grad_(True) for t in (q, k, v))
+    with torch.enable_grad():
+        pr, vh = _att(qq, kk, vv, mask, R, L, h, dk, keep, p)
+        out = (pr @ vh).transpose(1, 2).reshape(R * L, h * dk)
+        g = torch.autograd.grad(out, (qq, kk, vv), d_o)
+    dq.copy_(g[0])
+    dk_.copy_(g[1])
+    dv.copy_(g[2])
+
+
+def _gru(gi, w_hh, b_hh, h0, lengths, B, L, Hd):
+    h = torch.zeros(B, Hd) if h0 is None else h0
+    hs, gates = [], []
+    g3 = gi.reshape(B, L, 3 * Hd)
+    for t in range(L):
+        gh = h @ w_hh.T + b_hh
+        r = torch.sigmoid(g3[:, t, :Hd] + gh[:, :Hd])
+        z = torch.sigmoid(g3[:, t, Hd:2 * Hd] + gh[:, Hd:2 * Hd])
+        n = torch.tanh(g3[:, t, 2 * Hd:] + r * gh[:, 2 * Hd:])
+        live = (lengths > t).float().unsqueeze(1)
+        hs.append(h)
+        gates.append(torch.cat([r, z, n, gh[:, 2 * Hd:]], 1))
+        h = live * ((1 - z) * n + z * h) + (1 - live) * h
+    return h, torch.stack(hs, 1), torch.stack(gates, 1)
+
+
+def _xnrs_gru_fwd(gi, w_hh_t, b_hh, h0, lengths, B, L, Hd, hs, gates, h_out):
+    h, s, g = _gru(gi, w_hh_t.T, b_hh, h0, lengths, B, L, Hd)
+    h_out.copy_(h)
+    hs.copy_(s.reshape(B * L, Hd))
+    gates.copy_(g)
+
+
+def _xnrs_gru_bwd(d_h_out, w_hh, lengths, hs, gates, B, L, Hd, d_gi, d_gh, d_h0):
+    dh = d_h_out.clone()
+    g4 = gates.reshape(B, L, 4 * Hd)
+    hp = hs.reshape(B, L, Hd)
+    dgi, dgh = torch.zeros(B, L, 3 * Hd), torch.zeros(B, L, 3 * Hd)
+    for t in range(L - 1, -1, -1):
+        r, z, n, ghn = g4[:, t, :Hd], g4[:, t, Hd:2 * Hd], g4[:, t, 2 * Hd:3 * Hd], g4[:, t, 3 * Hd:]
+        live = (lengths > t).float().unsqueeze(1)
+        dn = dh * (1 - z) * (1 - n * n)
+        gz = dh * (hp[:, t] - n) * z * (1 - z)
+        gr = dn * ghn * r * (1 - r)
+        dgi[:, t] = live * torch.cat([gr, gz, dn], 1)
+        dgh[:, t] = live * torch.cat([gr, gz, dn * r], 1)
+        dh = live * (dh * z + dgh[:, t] @ w_hh) + (1 - live) * dh
+    d_gi.copy_(dgi.reshape(B * L, -1))
+    d_gh.copy_(dgh.reshape(B * L, -1))
+    if d_h0 is not None:
+        d_h0.copy_(dh)
+
+
+def _xnrs_lengths_from_mask(mask, B, L, lengths):
+    lengths.copy_(mask.reshape(B, L).sum(1).round().int())
+
+
+def _xnrs_score_loss(u, c, targets, weights, kind, B, N, T, gscale, scores, preds, loss, d_u, d_c):
+    cc = c.detach().clone().requires_grad_(True)
+    uu = None if u is None else u.detach().clone().requires_grad_(True)
+    with torch.enable_grad():
+        s = cc if u is None else (cc * uu.unsqueeze(1)).sum(-1)
+        w = 1.0 if weights is None else weights.reshape(B, N)
+        if kind == K.LOSS_MSE_RELU:
+            p = torch.relu(s)
+            l = (((p - targets.reshape(B, N)) ** 2) * w).mean()
+        elif kind == K.LOSS_BCE_LOGITS:
+            p = s
+            t = targets.reshape(B, N)
+            l = ((torch.clamp(s, min=0) - s * t + torch.log1p(torch.exp(-s.abs()))) * w).mean()
+        else:
+            p = s
+            e = torch.exp(s)
+            l = (-torch.log(e[:, 0] / e.sum(1))).mean()
+        if d_c is not None:
+            gr = torch.autograd.grad(l, (cc,) if u is None else (cc, uu))
+            d_c.copy_(gr[0] * gscale)
+            if u is not None:
+                d_u.copy_(gr[1] * gscale)
+    scores.copy_(s.detach())
+    if preds is not None:
+        preds.copy_(p.detach())
+    loss.copy_(l.detach().reshape(1))
+
+
+def _xnrs_dot_score(u, c, B, N, T, scores):
+    scores.copy_((c * u.unsqueeze(1)).sum(-1))
+
+
+def _xnrs_dot_score_bwd(u, c, d_s, B, N, T, d_u, d_c):
+    d_u.copy_((d_s.unsqueeze(-1) * c).sum(1))
+    d_c.copy_(d_s.unsqueeze(-1) * u.unsqueeze(1))
+
+
+def _xnrs_infonce_normalize(emb, Bk, E, ehat, inv_norm):
+    inv = 1.0 / emb.norm(dim=1).clamp_min(1e-12)
+    ehat.copy_(emb * inv[:, None])
+    inv_norm.copy_(inv)
+
+
+def _xnrs_infonce_rows(sim, labels, Ba, Bk, row0, temperature, stats):
+    ex = torch.exp(sim / temperature)
+    gi = torch.arange(Ba) + row0
+    off = torch.arange(Bk)[None, :] != gi[:, None]
+    pos = (labels[gi][:, None] == labels[None, :]) & off
+    num, den = (ex * pos).sum(1), (ex * off).sum(1)
+    has = pos.any(1)
+    stats[0] += (-torch.log(num[has] / (den[has] + 1e-12))).sum()
+    stats[1] += has.sum()
+    G = ex / temperature * (off / (den[:, None] + 1e-12) - pos / num.clamp_min(1e-38)[:, None])
+    sim.copy_(G * has[:, None])
+
+
+def _xnrs_infonce_finalize(stats, loss):
+    loss.copy_((stats[0] / (stats[1] + 1e-8)).reshape(1))
+
+
+def _xnrs_infonce_normalize_bwd(d_ehat, ehat, inv_norm, stats, gscale, Bk, E, d_emb):
+    sc = gscale / (stats[1] + 1e-8)
+    d_emb.copy_(sc * inv_norm[:, None] * (d_ehat - ehat * (ehat * d_ehat).sum(1, keepdim=True)))
+
+
+def _xnrs_adam_step(p, g, m, v, n, lr, b1, b2, eps, step, bc_dev, gscale):
+    gg = g * gscale
+    m.mul_(b1).add_(gg, alpha=1 - b1)
+    v.mul_(b2).addcmul_(gg, gg, value=1 - b2)
+    if bc_dev is not None:
+        i1, i2 = float(bc_dev[0]), float(bc_dev[1])
+    else:
+        i1, i2 = 1 / (1 - b1 ** step), 1 / math.sqrt(1 - b2 ** step)
+    p.sub_(lr * i1 * m / (v.sqrt() * i2 + eps))
+
+
+def _xnrs_adam_tick(step_dev, b1, b2, bc):
+    step_dev += 1
+    t = int(step_dev)
+    bc[0], bc[1] = 1 / (1 - b1 ** t), 1 / math.sqrt(1 - b2 ** t)
+
+
+def _xnrs_eval_impressions(user, news_vecs, T, cand_ids, offsets, targets, n_imp, act, scores, metrics):
+    from oracle import xnrs_oracle as O
+    for i in range(n_imp):
+        a, b = int(offsets[i]), int(offsets[i + 1])
+        if user is not None:
+            s = news_vecs[cand_ids[a:b].long()] @ user[i]
+            s = torch.relu(s) if act == 1 else (torch.sigmoid(s) if act == 2 else s)
+            scores[a:b] = s
+        r = O.impression_metrics(targets[a:b].numpy(), scores[a:b].numpy())
+        metrics[i] = torch.tensor([r['auc'], r['rr'], r['ndcg@5'], r['ndcg@10'], r['ctr@1'], r['ctr@10']],
+                                  dtype=torch.float64)
+
+
+def _xnrs_metric_sums(metrics, n_imp, sums):
+    ok = torch.isfinite(metrics).all(1)
+    sums[:6] += metrics[ok].sum(0)
+    sums[6] += ok.sum()

@@ -136,7 +136,7 @@ def model_fixture(name, over, seed):
 def layer_fixtures():
     g = torch.Generator().manual_seed(7)
     out = {}
-    R, L, F = 6, 7, 24
+    R, L, F = 6, 7, 32
     x = torch.randn(R, L, F, generator=g)
     ln = torch.tensor([7, 3, 1, 0, 5, 7])
     m = (torch.arange(L)[None, :] < ln[:, None]).float().unsqueeze(-1)

@@ -1,0 +1,405 @@
+"""Kernel-level parity on a real B200: every C-ABI entry point against the CPU oracle on the same seeded inputs
+(fp32, 1e-4 relative to the tensor scale; index / copy work bit-exact)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from _common import assert_close, load_npz
+from oracle import xnrs_oracle as O
+from xnrs_b200 import kernels as K
+from xnrs_b200.models import components as C
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+TOL = 1e-4
+
+
+def g(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def cu(t):
+    return t.to(DEV).contiguous()
+
+
+def test_library_reports_sm100_and_counts_launches():
+    from xnrs_b200 import _lib
+    assert _lib.lib().xnrs_device_is_sm100() == 1
+    n0 = K.launch_count()
+    K.gemm(cu(torch.randn(8, 8)), cu(torch.randn(8, 8)))
+    assert K.launch_count() == n0 + 1
+
+
+@pytest.mark.parametrize('ta,tb', [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize('M,N,K_', [(77, 130, 45), (256, 256, 768), (1, 5, 3), (300, 64, 1000)])
+def test_gemm_layouts(ta, tb, M, N, K_):
+    a = torch.randn((K_, M) if ta else (M, K_), generator=g(1))
+    b = torch.randn((N, K_) if tb else (K_, N), generator=g(2))
+    bias = torch.randn(N, generator=g(3))
+    want = (a.T if ta else a) @ (b.T if tb else b) + bias
+    got = K.gemm(cu(a), cu(b), trans_a=bool(ta), trans_b=bool(tb), bias=cu(bias))
+    assert_close(got, want, 2e-5, 'gemm')
+
+
+def test_gemm_epilogues_strides_splitk_and_gather():
+    M, N, K_ = 200, 96, 333
+    a, b = torch.randn(M, K_, generator=g(1)), torch.randn(N, K_, generator=g(2))
+    bias, aux = torch.randn(N, generator=g(3)), torch.randn(M, N, generator=g(4))
+    base = a @ b.T + bias
+    assert_close(K.gemm(cu(a), cu(b), trans_b=True, bias=cu(bias), act=K.ACT_RELU), torch.relu(base), 2e-5, 'relu')
+    assert_close(K.gemm(cu(a), cu(b), trans_b=True, bias=cu(bias), act=K.ACT_TANH), torch.tanh(base), 2e-5, 'tanh')
+    assert_close(K.gemm(cu(a), cu(b), trans_b=True, bias=cu(bias), act=K.ACT_RELU_MASK, aux=cu(aux)),
+                 base * (aux > 0), 2e-5, 'relu mask')
+    out = cu(aux.clone())
+    K.gemm(cu(a), cu(b), trans_b=True, bias=cu(bias), out=out, accumulate=True)
+    assert_close(out, aux + base, 2e-5, 'accumulate')
+    # strided output (a column block of a wider buffer) and an unaligned leading dimension on A
+    wide = torch.zeros(M, N + 40, device=DEV)
+    a_pad = cu(torch.cat([a, torch.zeros(M, 3)], 1))
+    K.gemm(a_pad[:, :K_], cu(b), trans_b=True, out=wide[:, 8:8 + N])
+    assert_close(wide[:, 8:8 + N], a @ b.T, 2e-5, 'strided')
+    assert float(wide[:, :8].abs().max()) == 0 and float(wide[:, 8 + N:].abs().max()) == 0
+    # split-K (weight-gradient shape: tiny output, long K) with and without accumulation
+    Kl = 20000
+    x, dy = torch.randn(Kl, 64, generator=g(5)), torch.randn(Kl, 48, generator=g(6))
+    want = dy.T @ x
+    assert_close(K.gemm(cu(dy), cu(x), trans_a=True, split_k=16), want, 5e-5, 'split-k')
+    assert_close(K.gemm(cu(dy), cu(x), trans_a=True), want, 5e-5, 'auto split-k')
+    acc = cu(torch.ones(48, 64))
+    K.gemm(cu(dy), cu(x), trans_a=True, out=acc, accumulate=True, split_k=7)
+    assert_close(acc, want + 1, 5e-5, 'split-k accumulate')
+    # fused row gather on A (forward) and on B (weight gradient)
+    table = torch.randn(500, K_, generator=g(7))
+    rows = torch.randint(0, 500, (M,), generator=g(8)).int()
+    assert_close(K.gemm(cu(table), cu(b), trans_b=True, a_rows=cu(rows)), table[rows.long()] @ b.T, 2e-5, 'a_rows')
+    d = torch.randn(M, 40, generator=g(9))
+    assert_close(K.gemm(cu(d), cu(table), trans_a=True, b_rows=cu(rows)), d.T @ table[rows.long()], 5e-5, 'b_rows')
+
+
+def test_gather_is_bit_exact_and_matches_dataset_semantics():
+    table = torch.randn(1000, 768, generator=g(0))
+    table[0] = 0
+    titles = torch.randint(1, 1000, (300, 30), generator=g(1)).int()
+    titles[0] = 0
+    titles[5, 7:] = 0
+    ids = torch.randint(0, 300, (16, 55), generator=g(2)).int()
+    ids[3, 10:] = 0
+    from xnrs_b200.data import TitleStore
+    x, m = TitleStore(cu(table), cu(titles)).dense(cu(ids))
+    wx, wm = O.gather_titles(table, titles, ids)
+    assert torch.equal(x.cpu(), wx) and torch.equal(m.cpu(), wm)
+
+
+def _aa_params(F_, A, seed, scale=1.0):
+    gg = g(seed)
+    return {'p.fc1.weight': torch.randn(A, F_, generator=gg) * scale / math.sqrt(F_),
+            'p.fc1.bias': torch.randn(A, generator=gg) * 0.1,
+            'p.fc2.weight': torch.randn(1, A, generator=gg) / math.sqrt(A), 'p.fc2.bias': torch.randn(1, generator=gg)}
+
+
+@pytest.mark.parametrize('R,L,F_,use_mask', [(37, 30, 768, True), (64, 50, 256, True), (50, 4, 256, False)])
+def test_additive_pool_forward_backward(R, L, F_, use_mask):
+    P = _aa_params(F_, 256, 3)
+    x = torch.randn(R, L, F_, generator=g(4))
+    ln = torch.randint(0, L + 1, (R,), generator=g(5))
+    ln[0], ln[1] = 0, L                                     # fully masked and full rows
+    m = (torch.arange(L)[None, :] < ln[:, None]).float().unsqueeze(-1) if use_mask else None
+    xo = x.clone().requires_grad_(True)
+    Po = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    wo, wa = O.additive_attention(xo, m, Po, 'p', return_weights=True)
+    gout = torch.randn(R, 1, F_, generator=g(6))
+    (wo * gout).sum().backward()
+
+    mod = C.AdditiveAttention(F_, 256).to(DEV)
+    mod.load_state_dict({k[2:]: v for k, v in P.items()})
+    xg = cu(x).requires_grad_(True)
+    go, ga = mod(xg, None if m is None else cu(m), return_weights=True)
+    assert_close(go, wo, TOL, 'pooled')
+    assert_close(ga, wa, TOL, 'weights')
+    if use_mask:
+        assert float(go[0].abs().max()) == 0.0             # fully masked -> exactly zero
+    (go * cu(gout)).sum().backward()
+    assert_close(xg.grad, xo.grad, TOL, 'dx')
+    for k in P:
+        want = Po[k].grad
+        assert_close(dict(mod.named_parameters())[k[2:]].grad, want, TOL, 'grad ' + k,
+                     atol=1e-5 * float(Po['p.fc1.weight'].grad.abs().max()))
+
+
+def test_personalized_pool_forward_backward():
+    R, L, F_, Q, A = 40, 30, 768, 64, 128
+    gg = g(11)
+    P = {'p.x_fc.weight': torch.randn(A, F_, generator=gg) / math.sqrt(F_), 'p.x_fc.bias': torch.randn(A, generator=gg) * .1,
+         'p.q_fc.weight': torch.randn(A, Q, generator=gg) / math.sqrt(Q), 'p.q_fc.bias': torch.randn(A, generator=gg) * .1}
+    x, q = torch.randn(R, L, F_, generator=gg), torch.randn(R, 1, Q, generator=gg) * 0.3
+    ln = torch.randint(0, L + 1, (R,), generator=gg)
+    m = (torch.arange(L)[None, :] < ln[:, None]).float().unsqueeze(-1)
+    Po = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    xo, qo = x.clone().requires_grad_(True), q.clone().requires_grad_(True)
+    wo = O.personalized_attention(qo, xo, m, Po, 'p')
+    gout = torch.randn(R, 1, F_, generator=gg)
+    (wo * gout).sum().backward()
+    mod = C.PersonalizedAttention(F_, A, Q).to(DEV)
+    mod.load_state_dict({k[2:]: v for k, v in P.items()})
+    xg, qg = cu(x).requires_grad_(True), cu(q).requires_grad_(True)
+    go = mod(qg, xg, cu(m))
+    assert_close(go, wo, TOL, 'pooled')
+    (go * cu(gout)).sum().backward()
+    assert_close(xg.grad, xo.grad, TOL, 'dx')
+    assert_close(qg.grad, qo.grad, TOL, 'dq')
+    for k in P:
+        assert_close(dict(mod.named_parameters())[k[2:]].grad, Po[k].grad, TOL, 'grad ' + k)
+
+
+@pytest.mark.parametrize('R,L,D,h,p', [(9, 30, 768, 16, 0.0), (7, 50, 768, 16, 0.1), (33, 50, 256, 16, 0.0),
+                                        (5, 25, 256, 16, 0.1), (4, 7, 32, 4, 0.0)])
+def test_multi_head_attention_forward_backward(R, L, D, h, p):
+    gg = g(21)
+    P = {}
+    for n in ('q_linear', 'k_linear', 'v_linear', 'out'):
+        P[f'a.{n}.weight'] = torch.randn(D, D, generator=gg) / math.sqrt(D)
+        P[f'a.{n}.bias'] = torch.randn(D, generator=gg) * 0.1
+    x = torch.randn(R, L, D, generator=gg)
+    ln = torch.randint(1, L + 1, (R,), generator=gg)
+    ln[0] = L
+    m = (torch.arange(L)[None, :] < ln[:, None]).float().unsqueeze(-1)
+    keep = (torch.rand(R, h, L, L, generator=gg) >= p).float() if p > 0 else None
+    Po = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    xo = x.clone().requires_grad_(True)
+    wo = O.multi_head_attention(xo, m, Po, 'a', h, keep, p)
+    gout = torch.randn(R, L, D, generator=gg)
+    (wo * gout).sum().backward()
+    mod = C.MultiHeadAttention(h, D, dropout=p).to(DEV).eval()
+    mod.load_state_dict({k[2:]: v for k, v in P.items()})
+    mod.keep_mask = None if keep is None else cu(keep)
+    xg = cu(x).requires_grad_(True)
+    go = mod(xg, cu(m))
+    assert_close(go, wo, TOL, 'mha out')
+    (go * cu(gout)).sum().backward()
+    assert_close(xg.grad, xo.grad, TOL, 'dx')
+    for k in P:
+        assert_close(dict(mod.named_parameters())[k[2:]].grad, Po[k].grad, TOL, 'grad ' + k)
+
+
+def test_mha_seeded_dropout_is_reproducible_and_unbiased():
+    R, L, D, h = 64, 30, 256, 16
+    mod = C.MultiHeadAttention(h, D, dropout=0.1).to(DEV).train()
+    x, m = cu(torch.randn(R, L, D, generator=g(1))), torch.ones(R, L, 1, device=DEV)
+    torch.manual_seed(5)
+    a = mod(x, m)
+    torch.manual_seed(5)
+    b = mod(x, m)
+    assert torch.equal(a, b)
+    mod.eval()
+    c = mod(x, m)
+    assert 1e-3 < float((a - c).abs().mean()) < 1.0         # dropout changes the output, mean stays close
+    assert abs(float(a.mean() - c.mean())) < 0.05 * float(c.abs().mean()) + 1e-3
+
+
+@pytest.mark.parametrize('B,L,I,Hd,with_h0', [(9, 25, 272, 136, False), (6, 7, 24, 10, True), (130, 50, 272, 272, True)])
+def test_gru_forward_backward(B, L, I, Hd, with_h0):
+    gg = g(31)
+    P = {'g.weight_ih_l0': torch.randn(3 * Hd, I, generator=gg) / math.sqrt(I),
+         'g.weight_hh_l0': torch.randn(3 * Hd, Hd, generator=gg) / math.sqrt(Hd),
+         'g.bias_ih_l0': torch.randn(3 * Hd, generator=gg) * .1, 'g.bias_hh_l0': torch.randn(3 * Hd, generator=gg) * .1}
+    x = torch.randn(B, L, I, generator=gg)
+    lens = torch.randint(1, L + 1, (B,), generator=gg)
+    lens[0] = L
+    h0 = torch.randn(B, Hd, generator=gg) if with_h0 else None
+    Po = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    xo = x.clone().requires_grad_(True)
+    h0o = None if h0 is None else h0.clone().requires_grad_(True)
+    wo = O.gru_last_hidden(xo, lens, Po, 'g', h0o)
+    gout = torch.randn(B, Hd, generator=gg)
+    (wo * gout).sum().backward()
+    Pg = {k: cu(v).requires_grad_(True) for k, v in P.items()}
+    xg = cu(x).requires_grad_(True)
+    h0g = None if h0 is None else cu(h0).requires_grad_(True)
+    go = K.GruLastFn.apply(xg, cu(lens.int()), Pg['g.weight_ih_l0'], Pg['g.weight_hh_l0'], Pg['g.bias_ih_l0'],
+                           Pg['g.bias_hh_l0'], h0g)
+    assert_close(go, wo, TOL, 'gru h')
+    (go * cu(gout)).sum().backward()
+    assert_close(xg.grad, xo.grad, TOL, 'dx')
+    if h0 is not None:
+        assert_close(h0g.grad, h0o.grad, TOL, 'dh0')
+    for k in P:
+        assert_close(Pg[k].grad, Po[k].grad, TOL, 'grad ' + k)
+
+
+@pytest.mark.parametrize('kind', [K.LOSS_MSE_RELU, K.LOSS_BCE_LOGITS, K.LOSS_NLL])
+@pytest.mark.parametrize('B,N,T', [(64, 5, 256), (3, 300, 272)])
+def test_score_loss_fused(kind, B, N, T):
+    gg = g(41)
+    u, c = torch.randn(B, T, generator=gg) * 0.2, torch.randn(B, N, T, generator=gg) * 0.2
+    t = torch.zeros(B, N)
+    t[:, 0] = 1
+    w = torch.rand(B, N, generator=gg) + 0.5 if kind != K.LOSS_NLL else None
+    uo, co = u.clone().requires_grad_(True), c.clone().requires_grad_(True)
+    s = O.dot_scoring(uo.unsqueeze(1), co)
+    if kind == K.LOSS_MSE_RELU:
+        want, _ = O.mse_relu_loss(s, t.unsqueeze(-1), w.unsqueeze(-1))
+    elif kind == K.LOSS_BCE_LOGITS:
+        want = O.bce_logits_loss(s, t.unsqueeze(-1), w.unsqueeze(-1))
+    else:
+        want = O.ranking_nll(s[:, :1, 0], s[:, 1:, 0])
+    want.backward()
+    ug, cg = cu(u).requires_grad_(True), cu(c).requires_grad_(True)
+    loss, preds, scores = K.ScoreLossFn.apply(ug, cg, cu(t).reshape(-1), None if w is None else cu(w).reshape(-1), kind)
+    assert_close(loss, want, TOL, 'loss')
+    assert_close(scores, s.squeeze(-1), TOL, 'scores')
+    (loss * 3.0).backward()
+    assert_close(ug.grad, 3 * uo.grad, TOL, 'du')
+    assert_close(cg.grad, 3 * co.grad, TOL, 'dc')
+    # standalone scorer
+    ug2, cg2 = cu(u).requires_grad_(True), cu(c).requires_grad_(True)
+    s2 = C.DotScoring()(ug2.unsqueeze(1), cg2)
+    assert_close(s2, s, TOL, 'dot scoring')
+    s2.sum().backward()
+    assert_close(cg2.grad, u.unsqueeze(1).expand_as(c), TOL, 'dot dc')
+
+
+@pytest.mark.parametrize('B,E', [(6, 8), (40, 16), (512, 256), (1024, 256)])
+def test_infonce(B, E):
+    gg = g(51)
+    e = torch.randn(B, E, generator=gg)
+    lab = torch.randint(0, 6, (B,), generator=gg)
+    if B > 8:
+        lab[7] = 99                                         # an anchor without positives is skipped
+    eo = e.clone().requires_grad_(True)
+    want = O.contrastive_loss(eo, lab, 0.08)
+    want.backward()
+    eg = cu(e).requires_grad_(True)
+    got = K.InfoNCEFn.apply(eg, cu(lab.int()), 0.08)
+    assert_close(got, want, TOL, 'infonce')
+    got.backward()
+    assert_close(eg.grad, eo.grad, 2e-4, 'd emb')
+
+
+def test_infonce_known_answers_from_reference():
+    fx = load_npz('loss_metrics')
+    for tag in ('cl', 'cl2'):
+        got = K.InfoNCEFn.apply(cu(torch.tensor(fx[tag + '/e'])), cu(torch.tensor(fx[tag + '/labels']).int()), 0.08)
+        assert_close(got, fx[tag + '/loss'], TOL, tag)
+    all_diff = K.InfoNCEFn.apply(cu(torch.randn(5, 8)), cu(torch.arange(5).int()), 0.08)
+    assert float(all_diff) == 0.0                           # no anchor has a positive -> 0 / (0 + 1e-8)
+
+
+@pytest.mark.parametrize('tag', ['met', 'mett', 'kat'])
+def test_ranking_metrics_against_reference_values(tag):
+    fx = load_npz('loss_metrics')
+    if tag == 'kat':
+        s, t, off, want = fx['kat/s'], fx['kat/t'], np.array([0, len(fx['kat/s'])]), fx['kat/values'][None]
+    else:
+        s, t, off, want = fx[tag + '/scores'], fx[tag + '/targets'], fx[tag + '/offsets'], fx[tag + '/values']
+    sc = cu(torch.tensor(s))
+    _, m = K.eval_impressions(None, None, None, cu(torch.tensor(off)), cu(torch.tensor(t)), act=0, scores=sc)
+    np.testing.assert_allclose(m.cpu().numpy(), want, rtol=0, atol=1e-6)
+
+
+def test_eval_impressions_scoring_ties_nan_and_long_segments():
+    gg = g(61)
+    T, n_news = 256, 5000
+    vecs, users = torch.randn(n_news, T, generator=gg) * 0.1, torch.randn(40, T, generator=gg) * 0.1
+    sizes = torch.randint(5, 74, (40,), generator=gg)
+    sizes[3], sizes[4] = 3000, 2                             # longer than the shared-memory staging; tiny
+    off = torch.cat([torch.zeros(1, dtype=torch.long), sizes.cumsum(0)])
+    cand = torch.randint(0, n_news, (int(off[-1]),), generator=gg).int()
+    tg = torch.zeros(int(off[-1]))
+    for i in range(40):
+        tg[off[i]:off[i] + 1 + i % 3] = 1
+    tg[off[4]:off[5]] = torch.tensor([1., 0.])
+    scores, m = K.eval_impressions(cu(users), cu(vecs), cu(cand), cu(off), cu(tg), act=1)
+    want_s = torch.cat([torch.relu(vecs[cand[off[i]:off[i + 1]].long()] @ users[i]) for i in range(40)])
+    assert_close(scores, want_s, TOL, 'scores')
+    sc = scores.cpu().numpy()                                # rank the GPU's own scores: ties (relu zeros) are exact
+    for i in range(40):
+        r = O.impression_metrics(tg[off[i]:off[i + 1]].numpy(), sc[off[i]:off[i + 1]])
+        want = [r['auc'], r['rr'], r['ndcg@5'], r['ndcg@10'], r['ctr@1'], r['ctr@10']]
+        np.testing.assert_allclose(m[i].cpu().numpy(), want, rtol=0, atol=1e-9, err_msg=f'impression {i}')
+    # nan_to_num(nan 0, +inf 1, -inf 0) (training.py:211) and single-class impressions
+    s = cu(torch.tensor([float('nan'), float('inf'), -float('inf'), 0.5, 0.2, 0.7]))
+    t = cu(torch.tensor([1., 0, 0, 1, 1, 1]))
+    _, m2 = K.eval_impressions(None, None, None, cu(torch.tensor([0, 4, 6])), t, act=0, scores=s.clone())
+    r = O.impression_metrics([1, 0, 0, 1], np.array([np.nan, np.inf, -np.inf, 0.5], dtype=np.float32))
+    np.testing.assert_allclose(m2[0].cpu().numpy(), [r['auc'], r['rr'], r['ndcg@5'], r['ndcg@10'], r['ctr@1'], r['ctr@10']],
+                               atol=1e-9)
+    assert math.isnan(float(m2[1, 0]))                       # only positives: AUC undefined
+    sums = K.metric_sums(m2).cpu().numpy()
+    assert sums[6] == 1 and abs(sums[1] - float(m2[0, 1])) < 1e-12
+
+
+def test_adam_matches_oracle_and_device_counter():
+    gg = g(71)
+    p, m, v = torch.randn(1000, generator=gg), torch.zeros(1000), torch.zeros(1000)
+    pg, mg, vg = cu(p), cu(m), cu(v)
+    p2, m2, v2 = cu(p), cu(m), cu(v)
+    step_dev, bc = torch.zeros(1, dtype=torch.int32, device=DEV), torch.zeros(2, device=DEV)
+    for step in range(1, 5):
+        gr = torch.randn(1000, generator=gg)
+        O.adam_step(p, gr, m, v, step, 1e-3)
+        K.adam_step(pg, cu(gr), mg, vg, 1e-3, step=step)
+        K.call('xnrs_adam_tick', step_dev, 0.9, 0.999, bc)
+        K.adam_step(p2, cu(gr), m2, v2, 1e-3, step=0, bc_dev=bc)
+    assert_close(pg, p, 1e-6, 'adam')
+    assert_close(p2, p, 1e-6, 'adam (device step counter)')
+
+
+def test_embedding_dropout_lengths_and_collapse():
+    gg = g(81)
+    w = torch.randn(50, 16, generator=gg)
+    idx = torch.randint(0, 50, (7, 3), generator=gg)
+    idx[0, 0] = 0
+    wg = cu(w).requires_grad_(True)
+    out = K.EmbeddingFn.apply(wg, cu(idx), 0)
+    assert torch.equal(out.cpu(), w[idx.reshape(-1)])
+    out.sum().backward()
+    want = torch.zeros(50, 16).index_add_(0, idx.reshape(-1), torch.ones(21, 16))
+    want[0] = 0                                              # padding_idx receives no gradient
+    assert_close(wg.grad, want, 1e-6, 'embedding grad')
+    x = cu(torch.randn(1000, generator=gg))
+    keep = cu((torch.rand(1000, generator=gg) > 0.07).float())
+    assert_close(K.DropoutFn.apply(x, keep, 0.07, 0), x * keep / 0.93, 1e-6, 'dropout')
+    y = K.DropoutFn.apply(x, None, 0.5, 123)
+    frac = float((y == 0).float().mean())
+    assert 0.4 < frac < 0.6 and torch.equal(y, K.DropoutFn.apply(x, None, 0.5, 123))
+    m = cu((torch.rand(9, 25, generator=gg) > 0.5).float())
+    lengths = torch.empty(9, dtype=torch.int32, device=DEV)
+    K.call('xnrs_lengths_from_mask', m.reshape(-1), 9, 25, lengths)
+    assert torch.equal(lengths.cpu(), m.cpu().sum(1).int())
+    assert torch.equal(K.collapse_mask(m.reshape(-1), 9, 25).cpu(), m.cpu().sum(1).clamp(0, 1))
+
+
+def test_layer_goldens_from_reference():
+    fx = load_npz('layers')
+    x, m = cu(torch.tensor(fx['x'])), cu(torch.tensor(fx['m']))
+
+    def load(mod, tag):
+        mod.load_state_dict({k[len(tag) + 1:]: torch.tensor(v) for k, v in fx.items()
+                             if k.startswith(tag + '/') and (k.endswith('weight') or k.endswith('bias'))})
+        return mod.to(DEV).eval()
+
+    aa = load(C.AdditiveAttention(32, 256), 'aa')
+    o, a = aa(x, m, return_weights=True)
+    assert_close(o, fx['aa/out'], TOL, 'aa')
+    assert_close(a, fx['aa/a'], TOL, 'aa weights')
+    assert_close(aa(x), fx['aa/out_nomask'], TOL, 'aa nomask')
+    mha = load(C.MultiHeadAttention(4, 32), 'mha')
+    assert_close(mha(x, m), fx['mha/out'], TOL, 'mha')
+    xq = x.clone()
+    xq[1, 5] += 1.0
+    assert_close(mha(xq, m), fx['mha/out_perturb_padkey'], TOL, 'mha padded key')
+    pa = load(C.PersonalizedAttention(32, 128, 8), 'pa')
+    assert_close(pa(cu(torch.tensor(fx['pa/q'])), x, m), fx['pa/out'], TOL, 'pa')
+    assert_close(C.MaskedMean()(x, m), fx['mm/out'], TOL, 'masked mean')
+    gw = {k[4:]: cu(torch.tensor(v)) for k, v in fx.items() if k.startswith('gru/') and '_l0' in k}
+    lens = cu(torch.tensor(fx['gru/lens']).int())
+    args = (gw['weight_ih_l0'], gw['weight_hh_l0'], gw['bias_ih_l0'], gw['bias_hh_l0'])
+    assert_close(K.GruLastFn.apply(x, lens, *args, None), fx['gru/h_zero'], TOL, 'gru')
+    assert_close(K.GruLastFn.apply(x, lens, *args, cu(torch.tensor(fx['gru/h0']))), fx['gru/h_init'], TOL, 'gru h0')
+
+
+def test_cpu_tensors_are_rejected():
+    with pytest.raises(RuntimeError, match='CUDA'):
+        K.gemm(torch.randn(4, 4), torch.randn(4, 4))

@@ -1,0 +1,252 @@
+// Rows A / P: additive and personalised attention pooling (layers.py:47-69, 88-101), forward and
+// backward, plus masked-mean pooling and the collapsed title mask.
+//
+// The hidden layer hid = tanh(fc1 x) is produced by the GEMM; these kernels fuse everything after it:
+// logit = <hid, w> (+b), exp, multiplicative mask, normalisation by (sum + 1e-8) and the weighted sum
+// over the (optionally table-gathered) rows of x.  One CTA walks titles grid-stride; rows whose
+// weight is exactly 0 (padding) are never read.  HBM-bound: per title it reads L*A (hid) + L*F (x).
+#include "common.cuh"
+
+namespace xnrs {
+
+constexpr int POOL_THREADS = 256;
+
+template <bool kPers>
+__global__ void __launch_bounds__(POOL_THREADS)
+pool_fwd_kernel(const float *__restrict__ x, const int *__restrict__ x_rows, const float *__restrict__ mask,
+                const float *__restrict__ hid, const float *__restrict__ w2, const float *__restrict__ b2,
+                const float *__restrict__ qh, int rows_per_query, long long R, int L, int F, int A,
+                float *__restrict__ attn, float *__restrict__ pooled) {
+    extern __shared__ float sm[];
+    float *e = sm;                               // [L]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int F4 = F >> 2;
+    const float4 *x4 = reinterpret_cast<const float4 *>(x);
+    for (long long r = blockIdx.x; r < R; r += gridDim.x) {
+        const float *wv = kPers ? qh + (r / rows_per_query) * A : w2;
+        const float bias = kPers ? 0.f : b2[0];
+        for (int l = warp; l < L; l += nwarps) {
+            const float mval = mask ? mask[r * L + l] : 1.f;
+            float acc = 0.f;
+            if (mval != 0.f) {
+                const float *hrow = hid + (r * L + l) * A;
+                for (int j = lane; j < A; j += 32) acc = fmaf(hrow[j], wv[j], acc);
+                acc = warp_sum(acc);
+            }
+            if (lane == 0) e[l] = (mval != 0.f) ? expf(acc + bias) * mval : 0.f;
+        }
+        __syncthreads();
+        float tot = 0.f;
+        for (int l = 0; l < L; ++l) tot += e[l];
+        const float denom = tot + 1e-8f;
+        for (int l = tid; l < L; l += blockDim.x) attn[r * L + l] = e[l] / denom;
+        for (int c = tid; c < F4; c += blockDim.x) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int l = 0; l < L; ++l) {
+                const float a = e[l] / denom;
+                if (a == 0.f) continue;
+                const long long row = x_rows ? (long long)x_rows[r * L + l] : r * L + l;
+                const float4 v = ldg_stream(x4 + row * F4 + c);
+                acc.x = fmaf(a, v.x, acc.x); acc.y = fmaf(a, v.y, acc.y);
+                acc.z = fmaf(a, v.z, acc.z); acc.w = fmaf(a, v.w, acc.w);
+            }
+            reinterpret_cast<float4 *>(pooled)[r * F4 + c] = acc;
+        }
+        __syncthreads();
+    }
+}
+
+// backward.  With a = E/(T+eps), E = exp(logit)*m:  dlogit_l = a_l * (da_l - sum_j a_j da_j).
+template <bool kPers>
+__global__ void __launch_bounds__(POOL_THREADS)
+pool_bwd_kernel(const float *__restrict__ x, const int *__restrict__ x_rows, const float *__restrict__ hid,
+                const float *__restrict__ w2, const float *__restrict__ qh, int rows_per_query,
+                const float *__restrict__ attn, const float *__restrict__ d_pooled, const float *__restrict__ d_attn,
+                long long R, int L, int F, int A, float *__restrict__ d_hid, float *__restrict__ d_w2,
+                float *__restrict__ d_b2, float *__restrict__ d_qh, float *__restrict__ d_x) {
+    extern __shared__ float sm[];
+    float *da = sm;            // [L]  da_l, then dlogit_l
+    float *al = sm + L;        // [L]  a_l
+    float *dw = sm + 2 * L;    // [A]  per-CTA accumulator for d_w2 (additive only)
+    __shared__ float db_acc;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int F4 = F >> 2;
+    const float4 *x4 = reinterpret_cast<const float4 *>(x);
+    if (!kPers) {
+        for (int j = tid; j < A; j += blockDim.x) dw[j] = 0.f;
+        if (tid == 0) db_acc = 0.f;
+    }
+    __syncthreads();
+    for (long long r = blockIdx.x; r < R; r += gridDim.x) {
+        const float4 *dp4 = reinterpret_cast<const float4 *>(d_pooled) + r * F4;
+        for (int l = warp; l < L; l += nwarps) {
+            const float a = attn[r * L + l];
+            float acc = 0.f;
+            if (a != 0.f) {
+                const long long row = x_rows ? (long long)x_rows[r * L + l] : r * L + l;
+                for (int c = lane; c < F4; c += 32) {
+                    const float4 v = ldg_stream(x4 + row * F4 + c);
+                    const float4 g = dp4[c];
+                    acc = fmaf(v.x, g.x, acc); acc = fmaf(v.y, g.y, acc);
+                    acc = fmaf(v.z, g.z, acc); acc = fmaf(v.w, g.w, acc);
+                }
+                acc = warp_sum(acc);
+                if (d_attn) acc += d_attn[r * L + l];
+            }
+            if (lane == 0) { da[l] = acc; al[l] = a; }
+        }
+        __syncthreads();
+        float dot = 0.f;
+        for (int l = 0; l < L; ++l) dot = fmaf(al[l], da[l], dot);
+        __syncthreads();
+        for (int l = tid; l < L; l += blockDim.x) da[l] = al[l] * (da[l] - dot);     // dlogit
+        __syncthreads();
+        const float *wv = kPers ? qh + (r / rows_per_query) * A : w2;
+        for (int j = tid; j < A; j += blockDim.x) {
+            const float w = wv[j];
+            float gw = 0.f;
+            for (int l = 0; l < L; ++l) {
+                const float dl = da[l];
+                const long long idx = (r * L + l) * A + j;
+                if (dl != 0.f) {
+                    const float h = hid[idx];
+                    gw = fmaf(dl, h, gw);
+                    d_hid[idx] = dl * w * (1.f - h * h);
+                } else {
+                    d_hid[idx] = 0.f;
+                }
+            }
+            if (kPers) atomicAdd(d_qh + (r / rows_per_query) * A + j, gw);
+            else dw[j] += gw;
+        }
+        if (!kPers && tid == 0) {
+            float s = 0.f;
+            for (int l = 0; l < L; ++l) s += da[l];
+            db_acc += s;
+        }
+        if (d_x) {
+            for (int i = tid; i < L * F4; i += blockDim.x) {
+                const int l = i / F4, c = i - l * F4;
+                const float a = al[l];
+                const float4 g = dp4[c];
+                reinterpret_cast<float4 *>(d_x)[(r * L + l) * F4 + c] = make_float4(a * g.x, a * g.y, a * g.z, a * g.w);
+            }
+        }
+        __syncthreads();
+    }
+    if (!kPers) {
+        for (int j = tid; j < A; j += blockDim.x) atomicAdd(d_w2 + j, dw[j]);
+        if (tid == 0) atomicAdd(d_b2, db_acc);
+    }
+}
+
+__global__ void meanpool_fwd_kernel(const float *__restrict__ x, const float *__restrict__ mask, long long R, int L,
+                                    int F, float *__restrict__ pooled) {
+    for (long long r = blockIdx.x; r < R; r += gridDim.x) {
+        float tot = 0.f;
+        for (int l = 0; l < L; ++l) tot += mask[r * L + l];
+        const float denom = tot + 1e-8f;
+        for (int f = threadIdx.x; f < F; f += blockDim.x) {
+            float acc = 0.f;
+            for (int l = 0; l < L; ++l) acc = fmaf(x[(r * L + l) * F + f], mask[r * L + l], acc);
+            pooled[r * F + f] = acc / denom;
+        }
+    }
+}
+
+__global__ void collapse_mask_kernel(const float *__restrict__ mask, long long R, int L, float *__restrict__ out) {
+    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < R; r += (long long)gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int l = 0; l < L; ++l) s += mask[r * L + l];
+        out[r] = fminf(fmaxf(s, 0.f), 1.f);
+    }
+}
+
+static unsigned pool_grid(long long R) {
+    long long cap = 8LL * num_sms();
+    return (unsigned)(R < cap ? (R < 1 ? 1 : R) : cap);
+}
+
+static int check_pool(long long R, int L, int F, int A, const float *x) {
+    if (R < 0 || L <= 0 || F <= 0 || A <= 0) return fail(XNRS_ERR_ARG, "%s: bad sizes", "pool");
+    if (F % 4 != 0) return fail(XNRS_ERR_ARG, "%s: F must be a multiple of 4", "pool");
+    if ((uintptr_t)x & 15) return fail(XNRS_ERR_ARG, "%s: x must be 16-byte aligned", "pool");
+    return XNRS_OK;
+}
+
+}  // namespace xnrs
+
+using namespace xnrs;
+
+extern "C" int xnrs_addpool_fwd(const float *x, const int *x_rows, const float *mask, const float *hid,
+                                const float *w2, const float *b2, long long R, int L, int F, int A, float *attn,
+                                float *pooled, xnrs_stream_t st) {
+    if (int e = check_pool(R, L, F, A, x)) return e;
+    if (R == 0) return XNRS_OK;
+    XNRS_REQUIRE(x && hid && w2 && b2 && attn && pooled, "null pointer");
+    pool_fwd_kernel<false><<<pool_grid(R), POOL_THREADS, L * sizeof(float), STREAM(st)>>>(
+        x, x_rows, mask, hid, w2, b2, nullptr, 1, R, L, F, A, attn, pooled);
+    XNRS_LAUNCHED();
+    return XNRS_OK;
+}
+
+extern "C" int xnrs_addpool_bwd(const float *x, const int *x_rows, const float *mask, const float *hid,
+                                const float *w2, const float *attn, const float *d_pooled, const float *d_attn,
+                                long long R, int L, int F, int A, float *d_hid, float *d_w2, float *d_b2, float *d_x,
+                                xnrs_stream_t st) {
+    (void)mask;   // the mask is already folded into attn (masked rows have weight exactly 0)
+    if (int e = check_pool(R, L, F, A, x)) return e;
+    if (R == 0) return XNRS_OK;
+    XNRS_REQUIRE(x && hid && w2 && attn && d_pooled && d_hid && d_w2 && d_b2, "null pointer");
+    XNRS_REQUIRE(!(d_x && x_rows), "d_x is only defined for dense x");
+    pool_bwd_kernel<false><<<pool_grid(R), POOL_THREADS, (2 * L + A) * sizeof(float), STREAM(st)>>>(
+        x, x_rows, hid, w2, nullptr, 1, attn, d_pooled, d_attn, R, L, F, A, d_hid, d_w2, d_b2, nullptr, d_x);
+    XNRS_LAUNCHED();
+    return XNRS_OK;
+}
+
+extern "C" int xnrs_perspool_fwd(const float *x, const int *x_rows, const float *mask, const float *hid,
+                                 const float *qh, long long R, int L, int F, int A, int rows_per_query, float *attn,
+                                 float *pooled, xnrs_stream_t st) {
+    if (int e = check_pool(R, L, F, A, x)) return e;
+    if (R == 0) return XNRS_OK;
+    XNRS_REQUIRE(x && hid && qh && attn && pooled && rows_per_query > 0, "null pointer");
+    pool_fwd_kernel<true><<<pool_grid(R), POOL_THREADS, L * sizeof(float), STREAM(st)>>>(
+        x, x_rows, mask, hid, nullptr, nullptr, qh, rows_per_query, R, L, F, A, attn, pooled);
+    XNRS_LAUNCHED();
+    return XNRS_OK;
+}
+
+extern "C" int xnrs_perspool_bwd(const float *x, const int *x_rows, const float *mask, const float *hid,
+                                 const float *qh, const float *attn, const float *d_pooled, long long R, int L, int F,
+                                 int A, int rows_per_query, float *d_hid, float *d_qh, float *d_x, xnrs_stream_t st) {
+    (void)mask;
+    if (int e = check_pool(R, L, F, A, x)) return e;
+    if (R == 0) return XNRS_OK;
+    XNRS_REQUIRE(x && hid && qh && attn && d_pooled && d_hid && d_qh && rows_per_query > 0, "null pointer");
+    XNRS_REQUIRE(!(d_x && x_rows), "d_x is only defined for dense x");
+    pool_bwd_kernel<true><<<pool_grid(R), POOL_THREADS, (2 * L + A) * sizeof(float), STREAM(st)>>>(
+        x, x_rows, hid, nullptr, qh, rows_per_query, attn, d_pooled, nullptr, R, L, F, A, d_hid, nullptr, nullptr,
+        d_qh, d_x);
+    XNRS_LAUNCHED();
+    return XNRS_OK;
+}
+
+extern "C" int xnrs_meanpool_fwd(const float *x, const float *mask, long long R, int L, int F, float *pooled,
+                                 xnrs_stream_t st) {
+    XNRS_REQUIRE(R >= 0 && L > 0 && F > 0, "bad sizes");
+    if (R == 0) return XNRS_OK;
+    XNRS_REQUIRE(x && mask && pooled, "null pointer");
+    meanpool_fwd_kernel<<<pool_grid(R), 128, 0, STREAM(st)>>>(x, mask, R, L, F, pooled);
+    XNRS_LAUNCHED();
+    return XNRS_OK;
+}
+
+extern "C" int xnrs_collapse_mask(const float *mask, long long R, int L, float *out, xnrs_stream_t st) {
+    XNRS_REQUIRE(R >= 0 && L > 0, "bad sizes");
+    if (R == 0) return XNRS_OK;
+    XNRS_REQUIRE(mask && out, "null pointer");
+    collapse_mask_kernel<<<(unsigned)cdiv(R, 256), 256, 0, STREAM(st)>>>(mask, R, L, out);
+    XNRS_LAUNCHED();
+    return XNRS_OK;
+}

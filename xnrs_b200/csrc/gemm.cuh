@@ -1,0 +1,20 @@
+// GEMM argument block shared by the SIMT (exact fp32) and tcgen05 (tensor-core) implementations.
+#pragma once
+#include "common.cuh"
+
+namespace xnrs {
+
+struct GemmArgs {
+    long long M, N, K;
+    const float *A; long long lda; const int *a_rows; int transA;
+    const float *B; long long ldb; const int *b_rows; int transB;
+    float *C; long long ldc;
+    const float *bias; int act; const float *aux; int accumulate;
+    int split_k; long long k_per_split;
+};
+
+int gemm_simt(const GemmArgs &a, cudaStream_t st);
+// gemm_tc.cu: returns 1 if the problem was taken by the tcgen05 path (*status holds the result), 0 if not
+int gemm_tensorcore(const GemmArgs &a, int precision, cudaStream_t st, int *status);
+
+}  // namespace xnrs

@@ -1,0 +1,162 @@
+// Rows E + Me: per-impression candidate scoring and ranking metrics over CSR impressions
+// (training.py:194-227; evaluation/metrics.py:7-44).  One CTA per impression:
+//   1. score_c = act(<user_i, news_vecs[cand_c]>)  (a warp per candidate, float4 loads), nan_to_num;
+//   2. a segmented enumeration (rank) sort inside the CTA: rank_c = #{c' : s_c' > s_c or (s_c' == s_c
+//      and c' > c)} — i.e. descending score, ties by descending index == np.argsort(kind='stable')[::-1];
+//      impressions are short (mean ~37 candidates) so the O(n^2/threads) rank sort beats a bitonic network;
+//   3. AUC (Mann-Whitney, ties 1/2), reciprocal rank, nDCG@5/10, CTR@1/10 in float64 like numpy.
+#include "common.cuh"
+
+namespace xnrs {
+
+constexpr int MT = 128;          // threads per impression
+constexpr int MCAP = 2048;       // candidates staged in shared memory; longer impressions read global memory
+
+__device__ __forceinline__ float nan_to_num_f(float s) {
+    if (isnan(s)) return 0.f;
+    if (isinf(s)) return s > 0.f ? 1.f : 0.f;
+    return s;
+}
+
+__device__ __forceinline__ double block_sum_d(double v, double *red) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    v = warp_sum_d(v);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    double t = (lane < nw) ? red[lane] : 0.0;
+    return warp_sum_d(t);
+}
+
+__global__ void __launch_bounds__(MT)
+eval_impressions_kernel(const float *__restrict__ user, const float *__restrict__ news_vecs, int T,
+                        const int *__restrict__ cand_ids, const long long *__restrict__ offsets,
+                        const float *__restrict__ targets, long long n_imp, int act, float *__restrict__ scores_io,
+                        double *__restrict__ metrics_out) {
+    __shared__ float s_sc[MCAP];
+    __shared__ float s_tg[MCAP];
+    __shared__ double red[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    for (long long imp = blockIdx.x; imp < n_imp; imp += gridDim.x) {
+        const long long beg = offsets[imp];
+        const int n = (int)(offsets[imp + 1] - beg);
+        float *gs = scores_io + beg;
+        const float *gt = targets + beg;
+        if (user) {
+            const int T4 = T >> 2;
+            const float4 *u4 = reinterpret_cast<const float4 *>(user) + imp * T4;
+            for (int c = warp; c < n; c += nw) {
+                const float4 *v4 = reinterpret_cast<const float4 *>(news_vecs) + (long long)cand_ids[beg + c] * T4;
+                float acc = 0.f;
+                for (int i = lane; i < T4; i += 32) {
+                    const float4 a = v4[i], b = u4[i];
+                    acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc);
+                    acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+                }
+                acc = warp_sum(acc);
+                if (lane == 0) {
+                    if (act == 1) acc = fmaxf(acc, 0.f);
+                    else if (act == 2) acc = 1.f / (1.f + expf(-acc));
+                    gs[c] = acc;
+                }
+            }
+            __syncthreads();
+        }
+        const bool in_smem = n <= MCAP;
+        if (in_smem) {
+            for (int c = tid; c < n; c += blockDim.x) { s_sc[c] = nan_to_num_f(gs[c]); s_tg[c] = gt[c]; }
+            __syncthreads();
+        }
+        auto SC = [&](int c) -> float { return in_smem ? s_sc[c] : nan_to_num_f(gs[c]); };
+        auto TG = [&](int c) -> float { return in_smem ? s_tg[c] : gt[c]; };
+
+        double dcg5 = 0, dcg10 = 0, idcg5 = 0, idcg10 = 0, ctr1 = 0, ctr10 = 0, rr = 0, auc_num = 0, npos = 0, nneg = 0;
+        for (int c = tid; c < n; c += blockDim.x) {
+            const float sc = SC(c), tc = TG(c);
+            int rank = 0, trank = 0;
+            double wins = 0.0;
+            const bool pos = tc > 0.5f;
+            for (int j = 0; j < n; ++j) {
+                const float sj = SC(j), tj = TG(j);
+                rank += (sj > sc) || (sj == sc && j > c);
+                trank += (tj > tc) || (tj == tc && j > c);
+                if (pos && !(tj > 0.5f)) wins += (sc > sj) ? 1.0 : (sc == sj ? 0.5 : 0.0);
+            }
+            const double gain = exp2((double)tc) - 1.0;
+            if (rank < 5) dcg5 += gain / log2((double)rank + 2.0);
+            if (rank < 10) dcg10 += gain / log2((double)rank + 2.0);
+            if (trank < 5) idcg5 += gain / log2((double)trank + 2.0);
+            if (trank < 10) idcg10 += gain / log2((double)trank + 2.0);
+            if (rank < 1) ctr1 += tc;
+            if (rank < 10) ctr10 += tc;
+            rr = fmax(rr, (double)tc / ((double)rank + 1.0));
+            auc_num += wins;
+            if (pos) npos += 1.0; else nneg += 1.0;
+        }
+        dcg5 = block_sum_d(dcg5, red); dcg10 = block_sum_d(dcg10, red);
+        idcg5 = block_sum_d(idcg5, red); idcg10 = block_sum_d(idcg10, red);
+        ctr1 = block_sum_d(ctr1, red); ctr10 = block_sum_d(ctr10, red);
+        auc_num = block_sum_d(auc_num, red); npos = block_sum_d(npos, red); nneg = block_sum_d(nneg, red);
+        // max-reduce rr
+        for (int o = 16; o > 0; o >>= 1) rr = fmax(rr, __shfl_xor_sync(0xffffffffu, rr, o));
+        __syncthreads();
+        if (lane == 0) red[warp] = rr;
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < nw; ++w) rr = fmax(rr, red[w]);
+            double *m = metrics_out + imp * 6;
+            m[0] = (npos > 0 && nneg > 0) ? auc_num / (npos * nneg) : nan("");
+            m[1] = rr;
+            m[2] = dcg5 / idcg5;
+            m[3] = dcg10 / idcg10;
+            m[4] = n > 0 ? ctr1 / 1.0 : nan("");
+            m[5] = n > 0 ? ctr10 / (double)min(n, 10) : nan("");
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void metric_sums_kernel(const double *__restrict__ metrics, long long n_imp, double *__restrict__ sums) {
+    __shared__ double red[32];
+    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_imp; i += (long long)gridDim.x * blockDim.x) {
+        const double *m = metrics + i * 6;
+        bool ok = true;
+        for (int k = 0; k < 6; ++k) ok = ok && isfinite(m[k]);
+        if (!ok) continue;
+        for (int k = 0; k < 6; ++k) acc[k] += m[k];
+        acc[6] += 1.0;
+    }
+    for (int k = 0; k < 7; ++k) {
+        double v = block_sum_d(acc[k], red);
+        if (threadIdx.x == 0) atomicAdd(sums + k, v);
+    }
+}
+
+}  // namespace xnrs
+
+using namespace xnrs;
+
+extern "C" int xnrs_eval_impressions(const float *user, const float *news_vecs, int T, const int *cand_ids,
+                                     const long long *offsets, const float *targets, long long n_imp, int act,
+                                     float *scores_io, double *metrics_out, xnrs_stream_t st) {
+    XNRS_REQUIRE(n_imp >= 0 && act >= 0 && act <= 2, "bad arguments");
+    if (n_imp == 0) return XNRS_OK;
+    XNRS_REQUIRE(offsets && targets && scores_io && metrics_out, "null pointer");
+    if (user) XNRS_REQUIRE(news_vecs && cand_ids && T > 0 && T % 4 == 0, "scoring needs news_vecs, cand_ids, T % 4 == 0");
+    long long cap = 16LL * num_sms();
+    eval_impressions_kernel<<<(unsigned)(n_imp < cap ? n_imp : cap), MT, 0, STREAM(st)>>>(
+        user, news_vecs, T, cand_ids, offsets, targets, n_imp, act, scores_io, metrics_out);
+    XNRS_LAUNCHED();
+    return XNRS_OK;
+}
+
+extern "C" int xnrs_metric_sums(const double *metrics, long long n_imp, double *sums, xnrs_stream_t st) {
+    XNRS_REQUIRE(n_imp >= 0, "bad sizes");
+    if (n_imp == 0) return XNRS_OK;
+    XNRS_REQUIRE(metrics && sums, "null pointer");
+    long long blocks = cdiv(n_imp, 256), cap = 2LL * num_sms();
+    metric_sums_kernel<<<(unsigned)(blocks > cap ? cap : blocks), 256, 0, STREAM(st)>>>(metrics, n_imp, sums);
+    XNRS_LAUNCHED();
+    return XNRS_OK;
+}

@@ -1,0 +1,66 @@
+"""Device-resident form of the reference's per-sample host gather (row G).
+
+The reference looks every news id up in a python dict of precomputed (S, D) token-embedding blocks and
+concatenates them on the host (xnrs/data/dataset.py:63-65,77-85,97-109), then ships ~4.6 MB per impression
+over PCIe inside TextEncoder.forward (news_encoding.py:45-47).  Here the frozen token table and the
+catalogue's token ids live in HBM; a batch carries int32 news ids and the encoders gather rows inside
+their kernels.  News id 0 / token id 0 are the pad article / pad token (zero row, zero mask), which
+reproduces the zero-embedding, zero-mask history padding of dataset.py:82-85.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from . import kernels as K
+
+
+class TitleStore:
+    """frozen token table (V, D) fp32 + catalogue token ids (N_news, S) int32, both on one CUDA device."""
+
+    def __init__(self, token_table: torch.Tensor, title_tokens: torch.Tensor):
+        if token_table.dtype != torch.float32 or token_table.dim() != 2 or token_table.shape[1] % 4:
+            raise ValueError('token_table must be fp32 (V, D) with D % 4 == 0')
+        if title_tokens.dim() != 2:
+            raise ValueError('title_tokens must be (N_news, S)')
+        self.token_table = token_table.contiguous()
+        self.title_tokens = title_tokens.to(torch.int32).contiguous()
+        if self.token_table.device != self.title_tokens.device:
+            raise ValueError('token_table and title_tokens must share a device')
+
+    @property
+    def device(self):
+        return self.token_table.device
+
+    @property
+    def seq_len(self) -> int:
+        return self.title_tokens.shape[1]
+
+    @property
+    def dim(self) -> int:
+        return self.token_table.shape[1]
+
+    def to(self, device):
+        return TitleStore(self.token_table.to(device), self.title_tokens.to(device))
+
+    def index(self, news_ids: torch.Tensor) -> 'IndexedTitles':
+        return IndexedTitles(self, news_ids)
+
+    def dense(self, news_ids: torch.Tensor):
+        """materialise the reference-format pair (x (..,S,D), m (..,S,1)) — for parity tests and explain-style
+        callers that need the dense tensors; the encoders never call this."""
+        rows, mask = K.expand_titles(self.title_tokens, news_ids.to(self.device))
+        x = K.gather_rows(self.token_table, rows)
+        shape = tuple(news_ids.shape)
+        return x.view(*shape, self.seq_len, self.dim), mask.view(*shape, self.seq_len, 1)
+
+
+@dataclass
+class IndexedTitles:
+    """what a batch carries instead of (x, m): int32 news ids (b, n) into a TitleStore."""
+    store: TitleStore
+    news_ids: torch.Tensor
+
+    def to(self, device):
+        return IndexedTitles(self.store, self.news_ids.to(device, non_blocking=True))

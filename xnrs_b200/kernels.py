@@ -1,0 +1,524 @@
+"""torch-tensor front end of the C ABI (include/xnrs_b200.h) and the autograd glue around it.
+
+PyTorch is plumbing here: it owns device memory, the current CUDA stream and the autograd tape.
+Every FLOP of the hot path runs in the kernels of xnrs_b200/csrc through ``call``; nothing in this
+file computes with torch ops, and nothing falls back to the CPU — non-CUDA inputs raise.
+"""
+from __future__ import annotations
+
+import contextlib
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+ACT_NONE, ACT_RELU, ACT_TANH, ACT_RELU_MASK = 0, 1, 2, 3
+LOSS_MSE_RELU, LOSS_BCE_LOGITS, LOSS_NLL = 0, 1, 2
+PRECISIONS = {'fp32': 0, 'tf32x3': 1, 'tf32': 2, 'bf16': 3}
+_precision = 0
+
+
+def set_precision(name: str) -> None:
+    """arithmetic of the GEMM-shaped ops: 'fp32' (exact FMA), 'tf32x3' (fp32-accurate tensor cores),
+    'tf32' or 'bf16' (2e-2 tolerance class)."""
+    global _precision
+    _precision = PRECISIONS[name]
+
+
+def get_precision() -> str:
+    return {v: k for k, v in PRECISIONS.items()}[_precision]
+
+
+@contextlib.contextmanager
+def precision(name: str):
+    global _precision
+    old = _precision
+    set_precision(name)
+    try:
+        yield
+    finally:
+        _precision = old
+
+
+class _Strided:
+    """marks a 2-D operand that may be a row-strided view (unit column stride, explicit leading dimension)"""
+    __slots__ = ('t',)
+
+    def __init__(self, t: torch.Tensor):
+        if t.dim() != 2 or t.stride(1) != 1 or t.dtype != torch.float32:
+            raise RuntimeError('gemm operands must be fp32 2-D with unit column stride')
+        self.t = t
+
+
+def _arg(a):
+    if isinstance(a, _Strided):
+        if not a.t.is_cuda:
+            raise RuntimeError('xnrs_b200 kernels need CUDA tensors (there is no CPU path)')
+        return a.t.data_ptr()
+    if isinstance(a, torch.Tensor):
+        if not a.is_cuda:
+            raise RuntimeError('xnrs_b200 kernels need CUDA tensors (there is no CPU path)')
+        if not a.is_contiguous():
+            raise RuntimeError('xnrs_b200 kernels need contiguous tensors')
+        return a.data_ptr()
+    return a
+
+
+def call(name: str, *args) -> None:
+    """invoke one C-ABI entry point on the current torch stream; raise on a non-zero status."""
+    fn = getattr(_lib.lib(), name)
+    rc = fn(*[_arg(a) for a in args], torch.cuda.current_stream().cuda_stream)
+    if rc != 0:
+        raise RuntimeError(f'{name} failed ({rc}): {_lib.last_error()}')
+
+
+def _mat(t: torch.Tensor) -> _Strided:
+    return _Strided(t)
+
+
+def launch_count() -> int:
+    return int(_lib.lib().xnrs_launch_count())
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise RuntimeError(f'expected float32, got {t.dtype}')
+    return t.contiguous()
+
+
+def _i32(t: torch.Tensor) -> torch.Tensor:
+    return t.to(torch.int32).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# raw ops (no autograd)
+# ------------------------------------------------------------------------------------------------
+
+def gemm(a, b, *, trans_a=False, trans_b=False, bias=None, act=ACT_NONE, aux=None, out=None, accumulate=False,
+         a_rows=None, b_rows=None, split_k=0):
+    """out (M,N) (=|+=) act(op(a) @ op(b) + bias).  `a`/`b` are 2-D row-major; with a_rows/b_rows they are
+    tables whose stored rows are gathered through the index."""
+    rows_a = a_rows.numel() if a_rows is not None else a.shape[0]
+    rows_b = b_rows.numel() if b_rows is not None else b.shape[0]
+    M, K = (a.shape[1], rows_a) if trans_a else (rows_a, a.shape[1])
+    N, Kb = (rows_b, b.shape[1]) if trans_b else (b.shape[1], rows_b)
+    if K != Kb:
+        raise RuntimeError(f'gemm: inner dimensions differ ({K} vs {Kb})')
+    if out is None:
+        out = torch.empty((M, N), device=a.device, dtype=torch.float32)
+        accumulate = False
+    call('xnrs_gemm', int(trans_a), int(trans_b), M, N, K, _mat(a), a.stride(0), a_rows, _mat(b), b.stride(0), b_rows,
+         _mat(out), out.stride(0), bias, act, aux, int(accumulate), split_k, _precision)
+    return out
+
+
+def colsum_into(x2d: torch.Tensor, out: torch.Tensor) -> None:
+    call('xnrs_colsum', x2d, x2d.shape[0], x2d.shape[1], x2d.stride(0), out)
+
+
+def colsum(x2d: torch.Tensor) -> torch.Tensor:
+    out = torch.zeros(x2d.shape[1], device=x2d.device, dtype=torch.float32)
+    colsum_into(x2d, out)
+    return out
+
+
+def expand_titles(title_tokens: torch.Tensor, news_ids: torch.Tensor):
+    """news ids (any shape) -> (token rows (R*S,) int32, mask (R*S,) fp32)"""
+    n_news, S = title_tokens.shape
+    ids = _i32(news_ids).reshape(-1)
+    rows = torch.empty(ids.numel() * S, device=ids.device, dtype=torch.int32)
+    mask = torch.empty(ids.numel() * S, device=ids.device, dtype=torch.float32)
+    call('xnrs_expand_titles', title_tokens, n_news, S, ids, ids.numel(), rows, mask)
+    return rows, mask
+
+
+def gather_rows(table: torch.Tensor, rows: torch.Tensor) -> torch.Tensor:
+    rows = _i32(rows).reshape(-1)
+    out = torch.empty((rows.numel(), table.shape[1]), device=table.device, dtype=torch.float32)
+    call('xnrs_gather_rows', table, table.shape[0], table.shape[1], rows, rows.numel(), out, out.stride(0))
+    return out
+
+
+def collapse_mask(mask: torch.Tensor, R: int, L: int) -> torch.Tensor:
+    out = torch.empty(R, device=mask.device, dtype=torch.float32)
+    call('xnrs_collapse_mask', mask, R, L, out)
+    return out
+
+
+def adam_step(p, g, m, v, lr, beta1=0.9, beta2=0.999, eps=1e-8, step=1, bc_dev=None, grad_scale=1.0):
+    call('xnrs_adam_step', p, g, m, v, p.numel(), lr, beta1, beta2, eps, step, bc_dev, grad_scale)
+
+
+def eval_impressions(user, news_vecs, cand_ids, offsets, targets, act=1, scores=None):
+    """-> (scores (n_cand,), metrics (n_imp,6) float64: auc, rr, ndcg@5, ndcg@10, ctr@1, ctr@10)"""
+    n_imp = offsets.numel() - 1
+    dev = targets.device
+    if scores is None:
+        scores = torch.empty(targets.numel(), device=dev, dtype=torch.float32)
+    metrics = torch.empty((n_imp, 6), device=dev, dtype=torch.float64)
+    T = news_vecs.shape[1] if news_vecs is not None else 0
+    call('xnrs_eval_impressions', user, news_vecs, T, cand_ids, offsets, targets, n_imp, act, scores, metrics)
+    return scores, metrics
+
+
+def metric_sums(metrics: torch.Tensor) -> torch.Tensor:
+    sums = torch.zeros(7, device=metrics.device, dtype=torch.float64)
+    call('xnrs_metric_sums', metrics, metrics.shape[0], sums)
+    return sums
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd functions.  Convention: `x` is either a dense (rows, F) matrix or — with `rows` — a frozen
+# table whose rows are gathered on the fly (row G fused into the consumer).
+# ------------------------------------------------------------------------------------------------
+
+def _need(ctx, i):
+    return ctx.needs_input_grad[i]
+
+
+class LinearFn(torch.autograd.Function):
+    """y = x W^T + b (nn.Linear), optional fused table gather on x."""
+
+    @staticmethod
+    def forward(ctx, x, rows, weight, bias):
+        y = gemm(x, weight, trans_b=True, bias=bias, a_rows=rows)
+        ctx.save_for_backward(x, rows, weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, rows, weight = ctx.saved_tensors
+        dy = _f32(dy)
+        dx = dw = db = None
+        if _need(ctx, 0):
+            if rows is not None:
+                raise RuntimeError('no gradient flows into a gathered (frozen) table')
+            dx = gemm(dy, weight)
+        if _need(ctx, 2):
+            dw = gemm(dy, x, trans_a=True, b_rows=rows)
+        if ctx.has_bias and _need(ctx, 3):
+            db = colsum(dy)
+        return dx, None, dw, db
+
+
+class Mlp2Fn(torch.autograd.Function):
+    """the encoder head Linear -> ReLU -> Linear (news_encoding.py:27-31,55-56; user_encoding.py:29-33)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        h = gemm(x, w1, trans_b=True, bias=b1, act=ACT_RELU)
+        y = gemm(h, w2, trans_b=True, bias=b2)
+        ctx.save_for_backward(x, w1, w2, h)
+        ctx.bias = b1 is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w1, w2, h = ctx.saved_tensors
+        dy = _f32(dy)
+        dw2 = gemm(dy, h, trans_a=True)
+        dh = gemm(dy, w2, act=ACT_RELU_MASK, aux=h)
+        dw1 = gemm(dh, x, trans_a=True)
+        db1 = colsum(dh) if ctx.bias else None
+        db2 = colsum(dy) if ctx.bias else None
+        dx = gemm(dh, w1) if _need(ctx, 0) else None
+        return dx, dw1, db1, dw2, db2
+
+
+class AdditivePoolFn(torch.autograd.Function):
+    """layers.AdditiveAttention (layers.py:47-69) over R groups of L rows: -> pooled (R,F), attn (R,L)."""
+
+    @staticmethod
+    def forward(ctx, x, rows, mask, w1, b1, w2, b2, R, L):
+        F_, A = x.shape[1], w1.shape[0]
+        hid = gemm(x, w1, trans_b=True, bias=b1, act=ACT_TANH, a_rows=rows)
+        attn = torch.empty((R, L), device=x.device, dtype=torch.float32)
+        pooled = torch.empty((R, F_), device=x.device, dtype=torch.float32)
+        call('xnrs_addpool_fwd', x, rows, mask, hid, w2, b2, R, L, F_, A, attn, pooled)
+        ctx.save_for_backward(x, rows, w1, w2, hid, attn)
+        ctx.dims = (R, L, F_, A)
+        return pooled, attn
+
+    @staticmethod
+    def backward(ctx, d_pooled, d_attn):
+        x, rows, w1, w2, hid, attn = ctx.saved_tensors
+        R, L, F_, A = ctx.dims
+        dev = x.device
+        d_pooled = _f32(d_pooled)
+        d_attn = None if d_attn is None else _f32(d_attn)
+        d_hid = torch.empty_like(hid)
+        d_w2 = torch.zeros_like(w2)
+        d_b2 = torch.zeros(1, device=dev, dtype=torch.float32)
+        need_dx = _need(ctx, 0)
+        if need_dx and rows is not None:
+            raise RuntimeError('no gradient flows into a gathered (frozen) table')
+        d_x = torch.empty_like(x) if need_dx else None
+        call('xnrs_addpool_bwd', x, rows, None, hid, w2, attn, d_pooled, d_attn, R, L, F_, A, d_hid, d_w2, d_b2, d_x)
+        d_w1 = gemm(d_hid, x, trans_a=True, b_rows=rows)
+        d_b1 = colsum(d_hid)
+        if need_dx:
+            gemm(d_hid, w1, out=d_x, accumulate=True)
+        return d_x, None, None, d_w1, d_b1, d_w2, d_b2, None, None
+
+
+class PersonalizedPoolFn(torch.autograd.Function):
+    """layers.PersonalizedAttention (layers.py:88-101); group r uses query row r // rows_per_query."""
+
+    @staticmethod
+    def forward(ctx, q, x, rows, mask, xw, xb, qw, qb, R, L, rows_per_query):
+        F_, A = x.shape[1], xw.shape[0]
+        hid = gemm(x, xw, trans_b=True, bias=xb, act=ACT_TANH, a_rows=rows)
+        qh = gemm(q, qw, trans_b=True, bias=qb)
+        attn = torch.empty((R, L), device=x.device, dtype=torch.float32)
+        pooled = torch.empty((R, F_), device=x.device, dtype=torch.float32)
+        call('xnrs_perspool_fwd', x, rows, mask, hid, qh, R, L, F_, A, rows_per_query, attn, pooled)
+        ctx.save_for_backward(q, x, rows, xw, qw, hid, qh, attn)
+        ctx.dims = (R, L, F_, A, rows_per_query)
+        return pooled
+
+    @staticmethod
+    def backward(ctx, d_pooled):
+        q, x, rows, xw, qw, hid, qh, attn = ctx.saved_tensors
+        R, L, F_, A, rpq = ctx.dims
+        d_pooled = _f32(d_pooled)
+        d_hid = torch.empty_like(hid)
+        d_qh = torch.zeros_like(qh)
+        need_dx = _need(ctx, 1)
+        if need_dx and rows is not None:
+            raise RuntimeError('no gradient flows into a gathered (frozen) table')
+        d_x = torch.empty_like(x) if need_dx else None
+        call('xnrs_perspool_bwd', x, rows, None, hid, qh, attn, d_pooled, R, L, F_, A, rpq, d_hid, d_qh, d_x)
+        d_xw = gemm(d_hid, x, trans_a=True, b_rows=rows)
+        d_xb = colsum(d_hid)
+        if need_dx:
+            gemm(d_hid, xw, out=d_x, accumulate=True)
+        d_qw = gemm(d_qh, q, trans_a=True)
+        d_qb = colsum(d_qh)
+        d_q = gemm(d_qh, qw) if _need(ctx, 0) else None
+        return d_q, d_x, None, None, d_xw, d_xb, d_qw, d_qb, None, None, None
+
+
+class MultiHeadAttentionFn(torch.autograd.Function):
+    """layers.MultiHeadAttention (layers.py:121-156) over R sequences of L rows."""
+
+    @staticmethod
+    def forward(ctx, x, rows, mask, wq, bq, wk, bk, wv, bv, wo, bo, R, L, n_heads, keep, p_drop, seed):
+        D = wq.shape[0]
+        dk = D // n_heads
+        q = gemm(x, wq, trans_b=True, bias=bq, a_rows=rows)
+        k = gemm(x, wk, trans_b=True, bias=bk, a_rows=rows)
+        v = gemm(x, wv, trans_b=True, bias=bv, a_rows=rows)
+        o = torch.empty_like(q)
+        lse = torch.empty((R, n_heads, L), device=x.device, dtype=torch.float32)
+        call('xnrs_mha_fwd', q, k, v, D, mask, R, L, n_heads, dk, keep, p_drop, seed, o, lse)
+        y = gemm(o, wo, trans_b=True, bias=bo)
+        ctx.save_for_backward(x, rows, mask, wq, wk, wv, wo, q, k, v, o, lse, keep)
+        ctx.cfg = (R, L, n_heads, dk, D, p_drop, seed)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, rows, mask, wq, wk, wv, wo, q, k, v, o, lse, keep = ctx.saved_tensors
+        R, L, h, dk, D, p_drop, seed = ctx.cfg
+        dy = _f32(dy)
+        d_wo = gemm(dy, o, trans_a=True)
+        d_bo = colsum(dy)
+        d_o = gemm(dy, wo)
+        dq, dk_, dv = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
+        call('xnrs_mha_bwd', q, k, v, o, d_o, D, mask, lse, R, L, h, dk, keep, p_drop, seed, dq, dk_, dv)
+        d_wq = gemm(dq, x, trans_a=True, b_rows=rows)
+        d_wk = gemm(dk_, x, trans_a=True, b_rows=rows)
+        d_wv = gemm(dv, x, trans_a=True, b_rows=rows)
+        d_bq, d_bk, d_bv = colsum(dq), colsum(dk_), colsum(dv)
+        d_x = None
+        if _need(ctx, 0):
+            if rows is not None:
+                raise RuntimeError('no gradient flows into a gathered (frozen) table')
+            d_x = gemm(dq, wq)
+            gemm(dk_, wk, out=d_x, accumulate=True)
+            gemm(dv, wv, out=d_x, accumulate=True)
+        return (d_x, None, None, d_wq, d_bq, d_wk, d_bk, d_wv, d_bv, d_wo, d_bo,
+                None, None, None, None, None, None)
+
+
+class EmbeddingFn(torch.autograd.Function):
+    """nn.Embedding lookup with a dense weight gradient (lstur.py:94-98,180-183; npa.py:12-15; naml.py:34-47)."""
+
+    @staticmethod
+    def forward(ctx, weight, idx, padding_idx):
+        idx = _i32(idx).reshape(-1)
+        ctx.save_for_backward(idx)
+        ctx.shape, ctx.pad = weight.shape, -1 if padding_idx is None else int(padding_idx)
+        return gather_rows(weight, idx)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (idx,) = ctx.saved_tensors
+        dy = _f32(dy)
+        dw = torch.zeros(ctx.shape, device=dy.device, dtype=torch.float32)
+        call('xnrs_scatter_add_rows', dw, ctx.shape[0], ctx.shape[1], idx, idx.numel(), dy, dy.stride(0), ctx.pad)
+        return dw, None, None
+
+
+class GruLastFn(torch.autograd.Function):
+    """final GRU state at each sequence's true length (lstur.py:139-153): x (B,L,I), lengths (B,) int32."""
+
+    @staticmethod
+    def forward(ctx, x, lengths, w_ih, w_hh, b_ih, b_hh, h0):
+        B, L, I = x.shape
+        Hd = w_hh.shape[1]
+        x2 = x.reshape(B * L, I)
+        gi = gemm(x2, w_ih, trans_b=True, bias=b_ih)
+        w_hh_t = torch.empty((Hd, 3 * Hd), device=x.device, dtype=torch.float32)
+        call('xnrs_transpose', w_hh, 3 * Hd, Hd, w_hh_t)
+        hs = torch.empty((B * L, Hd), device=x.device, dtype=torch.float32)      # state BEFORE step t
+        gates = torch.empty((B, L, 4 * Hd), device=x.device, dtype=torch.float32)
+        h_out = torch.empty((B, Hd), device=x.device, dtype=torch.float32)
+        call('xnrs_gru_fwd', gi, w_hh_t, b_hh, h0, lengths, B, L, Hd, hs, gates, h_out)
+        ctx.save_for_backward(x2, lengths, w_ih, w_hh, hs, gates)
+        ctx.dims = (B, L, I, Hd)
+        ctx.has_h0 = h0 is not None
+        return h_out
+
+    @staticmethod
+    def backward(ctx, d_h):
+        x2, lengths, w_ih, w_hh, hs, gates = ctx.saved_tensors
+        B, L, I, Hd = ctx.dims
+        d_h = _f32(d_h)
+        d_gi = torch.empty((B * L, 3 * Hd), device=d_h.device, dtype=torch.float32)
+        d_gh = torch.empty((B * L, 3 * Hd), device=d_h.device, dtype=torch.float32)
+        d_h0 = torch.empty((B, Hd), device=d_h.device, dtype=torch.float32)
+        call('xnrs_gru_bwd', d_h, w_hh, lengths, hs, gates, B, L, Hd, d_gi, d_gh, d_h0)
+        d_wih = gemm(d_gi, x2, trans_a=True)
+        d_bih = colsum(d_gi)
+        d_whh = gemm(d_gh, hs, trans_a=True)
+        d_bhh = colsum(d_gh)
+        d_x = gemm(d_gi, w_ih).reshape(B, L, I) if _need(ctx, 0) else None
+        return d_x, None, d_wih, d_whh, d_bih, d_bhh, (d_h0 if ctx.has_h0 else None)
+
+
+class DropoutFn(torch.autograd.Function):
+    """inverted dropout with an explicit keep mask or a seeded counter-based generator."""
+
+    @staticmethod
+    def forward(ctx, x, keep, p, seed):
+        y = torch.empty_like(x)
+        call('xnrs_dropout', x.numel(), x, keep, p, seed, y)
+        ctx.save_for_backward(keep)
+        ctx.cfg = (p, seed)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (keep,) = ctx.saved_tensors
+        dy = _f32(dy)
+        dx = torch.empty_like(dy)
+        call('xnrs_dropout', dy.numel(), dy, keep, ctx.cfg[0], ctx.cfg[1], dx)
+        return dx, None, None, None
+
+
+class DotScoreFn(torch.autograd.Function):
+    """scoring.DotScoring (scoring.py:12-23): u (B,T), c (B,N,T) -> (B,N)."""
+
+    @staticmethod
+    def forward(ctx, u, c):
+        B, N, T = c.shape
+        s = torch.empty((B, N), device=c.device, dtype=torch.float32)
+        call('xnrs_dot_score', u, c, B, N, T, s)
+        ctx.save_for_backward(u, c)
+        return s
+
+    @staticmethod
+    def backward(ctx, ds):
+        u, c = ctx.saved_tensors
+        B, N, T = c.shape
+        ds = _f32(ds)
+        du, dc = torch.empty_like(u), torch.empty_like(c)
+        call('xnrs_dot_score_bwd', u, c, ds, B, N, T, du, dc)
+        return du, dc
+
+
+class ScoreLossFn(torch.autograd.Function):
+    """dot scoring fused with a trainer loss; value and both gradients in one pass -> (loss, preds, scores)."""
+
+    @staticmethod
+    def forward(ctx, u, c, targets, weights, kind):
+        """u (B,T), c (B,N,T)  — or u None and c (B,N) = scores computed upstream."""
+        B, N = c.shape[0], c.shape[1]
+        T = c.shape[2] if u is not None else 0
+        dev = c.device
+        scores = torch.empty((B, N), device=dev, dtype=torch.float32)
+        preds = torch.empty((B, N), device=dev, dtype=torch.float32)
+        loss = torch.empty(1, device=dev, dtype=torch.float32)
+        need = (u is not None and u.requires_grad) or c.requires_grad
+        du = torch.empty_like(u) if (need and u is not None) else None
+        dc = torch.empty_like(c) if need else None
+        call('xnrs_score_loss', u, c, targets, weights, kind, B, N, T, 1.0, scores, preds, loss, du, dc)
+        ctx.save_for_backward(du, dc)
+        ctx.mark_non_differentiable(preds, scores)
+        return loss.reshape(()), preds, scores
+
+    @staticmethod
+    def backward(ctx, g, _gp, _gs):
+        du, dc = ctx.saved_tensors
+        g = _f32(g).reshape(1)
+        gu = None
+        if du is not None:
+            gu = torch.empty_like(du)
+            call('xnrs_axpby', du.numel(), 1.0, g, du, 0.0, gu)
+        gc = torch.empty_like(dc)
+        call('xnrs_axpby', dc.numel(), 1.0, g, dc, 0.0, gc)
+        return gu, gc, None, None, None
+
+
+class ReluFn(torch.autograd.Function):
+    """the trainer's output activation (training.py:392)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _f32(x)
+        y = torch.empty_like(x)
+        call('xnrs_relu', x.numel(), x, y)
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        dy = _f32(dy)
+        dx = torch.empty_like(dy)
+        call('xnrs_relu_bwd', dy.numel(), y, dy, dx)
+        return dx
+
+
+class InfoNCEFn(torch.autograd.Function):
+    """ContrastiveRankingTrainer._compute_contrastive_loss (training.py:433-472), single device."""
+
+    @staticmethod
+    def forward(ctx, emb, labels, temperature):
+        B, E = emb.shape
+        dev = emb.device
+        ehat = torch.empty_like(emb)
+        inv_norm = torch.empty(B, device=dev, dtype=torch.float32)
+        call('xnrs_infonce_normalize', emb, B, E, ehat, inv_norm)
+        sim = gemm(ehat, ehat, trans_b=True)
+        stats = torch.zeros(2, device=dev, dtype=torch.float32)
+        call('xnrs_infonce_rows', sim, labels, B, B, 0, temperature, stats)
+        loss = torch.empty(1, device=dev, dtype=torch.float32)
+        call('xnrs_infonce_finalize', stats, loss)
+        ctx.save_for_backward(ehat, inv_norm, sim, stats)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        ehat, inv_norm, G, stats = ctx.saved_tensors
+        B, E = ehat.shape
+        d_ehat = gemm(G, ehat)                                   # anchor side:  G  ehat
+        gemm(G, ehat, trans_a=True, out=d_ehat, accumulate=True)  # key side:     G^T ehat
+        d_scaled = torch.empty_like(ehat)
+        call('xnrs_infonce_normalize_bwd', d_ehat, ehat, inv_norm, stats, 1.0, B, E, d_scaled)
+        d_emb = torch.empty_like(ehat)
+        call('xnrs_axpby', d_emb.numel(), 1.0, _f32(g).reshape(1), d_scaled, 0.0, d_emb)
+        return d_emb, None, None

@@ -1,0 +1,265 @@
+"""Building blocks with the reference's interfaces (xnrs/models/components/{layers,news_encoding,
+user_encoding,scoring,parent}.py) whose forward/backward run in the xnrs_b200 CUDA kernels.
+
+The nn.Linear / nn.Sequential / nn.Embedding / nn.GRU children are used purely as *parameter containers*
+so that ``state_dict()`` keys and shapes equal the reference's; their own forward methods
+are never called.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from .. import kernels as K
+from ..data import IndexedTitles
+
+
+def _dev(module: nn.Module) -> torch.device:
+    return next(module.parameters()).device
+
+
+def _flat_rows(x: torch.Tensor):
+    """(R, L, F) dense -> ((R*L, F) contiguous, R, L)"""
+    R, L, F_ = x.shape
+    return K._f32(x).reshape(R * L, F_), R, L
+
+
+def _flat_mask(m: Optional[torch.Tensor], n: int):
+    if m is None:
+        return None
+    m = K._f32(m).reshape(-1)
+    if m.numel() != n:
+        raise RuntimeError(f'mask has {m.numel()} entries, expected {n}')
+    return m
+
+
+def _seed() -> int:
+    return int(torch.randint(0, 2 ** 62, (1,)).item())
+
+
+class MaskedMean(nn.Module):
+    """layers.MaskedMean (layers.py:19-37); forward only (its users are outside the five target models)."""
+
+    def forward(self, x: torch.Tensor, m: torch.Tensor):
+        x2, R, L = _flat_rows(x)
+        out = torch.empty((R, x.shape[2]), device=x.device, dtype=torch.float32)
+        K.call('xnrs_meanpool_fwd', x2, _flat_mask(m, R * L), R, L, x.shape[2], out)
+        return out.unsqueeze(1)
+
+
+class AdditiveAttention(nn.Module):
+    """layers.AdditiveAttention (layers.py:40-69): same constructor, parameters and forward contract."""
+
+    def __init__(self, in_features, hidden_features):
+        super().__init__()
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.fc2 = nn.Linear(hidden_features, 1)
+
+    def pool(self, x2: torch.Tensor, rows, mask, R: int, L: int):
+        """(R*L, F) rows (or table + row index) -> pooled (R, F), weights (R, L)"""
+        return K.AdditivePoolFn.apply(x2, rows, mask, self.fc1.weight, self.fc1.bias,
+                                      self.fc2.weight.reshape(-1), self.fc2.bias, R, L)
+
+    def forward(self, x: torch.Tensor, m: torch.Tensor = None, return_weights: bool = False):
+        x2, R, L = _flat_rows(x)
+        pooled, attn = self.pool(x2, None, _flat_mask(m, R * L), R, L)
+        pooled = pooled.unsqueeze(1)
+        return (pooled, attn.unsqueeze(-1)) if return_weights else pooled
+
+
+class PersonalizedAttention(nn.Module):
+    """layers.PersonalizedAttention (layers.py:72-102)."""
+
+    def __init__(self, in_features, hidden_features, query_features):
+        super().__init__()
+        self.x_fc = nn.Linear(in_features, hidden_features)
+        self.q_fc = nn.Linear(query_features, hidden_features)
+
+    def pool(self, q2, x2, rows, mask, R: int, L: int, rows_per_query: int = 1):
+        return K.PersonalizedPoolFn.apply(q2, x2, rows, mask, self.x_fc.weight, self.x_fc.bias,
+                                          self.q_fc.weight, self.q_fc.bias, R, L, rows_per_query)
+
+    def forward(self, q: torch.Tensor, x: torch.Tensor, m: torch.Tensor = None):
+        x2, R, L = _flat_rows(x)
+        q2 = K._f32(q).reshape(R, -1)
+        return self.pool(q2, x2, None, _flat_mask(m, R * L), R, L).unsqueeze(1)
+
+
+class MultiHeadAttention(nn.Module):
+    """layers.MultiHeadAttention (layers.py:105-156), including its query-axis mask and p=0.1 dropout default.
+
+    Train-mode dropout uses a counter-based generator seeded from torch's RNG (bit parity with torch's
+    Philox stream is not a goal — SURVEY §7 hard part 3); ``keep_mask`` (R,h,L,L) overrides it for tests."""
+
+    def __init__(self, n_heads, d_model, dropout=0.1, scaled=True):
+        super().__init__()
+        if not scaled:
+            raise NotImplementedError('the reference only ever uses scaled=True')
+        self.scaled = scaled
+        self.d_model = d_model
+        self.d_k = d_model // n_heads
+        self.h = n_heads
+        self.q_linear = nn.Linear(d_model, d_model)
+        self.v_linear = nn.Linear(d_model, d_model)
+        self.k_linear = nn.Linear(d_model, d_model)
+        self.dropout = nn.Dropout(dropout)
+        self.out = nn.Linear(d_model, d_model)
+        self.keep_mask: Optional[torch.Tensor] = None
+
+    def attend(self, x2: torch.Tensor, rows, mask, R: int, L: int) -> torch.Tensor:
+        p = float(self.dropout.p) if (self.training or self.keep_mask is not None) else 0.0
+        keep = None if self.keep_mask is None else K._f32(self.keep_mask).reshape(-1)
+        seed = _seed() if (p > 0 and keep is None) else 0
+        return K.MultiHeadAttentionFn.apply(
+            x2, rows, mask, self.q_linear.weight, self.q_linear.bias, self.k_linear.weight, self.k_linear.bias,
+            self.v_linear.weight, self.v_linear.bias, self.out.weight, self.out.bias, R, L, self.h, keep, p, seed)
+
+    def forward(self, x: torch.Tensor, m: torch.Tensor):
+        x2, R, L = _flat_rows(x)
+        return self.attend(x2, None, _flat_mask(m, R * L), R, L).view(R, L, self.d_model)
+
+
+def _apply_head(head: nn.Sequential, x2: torch.Tensor) -> torch.Tensor:
+    if not isinstance(head[1], nn.ReLU):
+        raise NotImplementedError('only the reference default activation nn.ReLU() is implemented')
+    return K.Mlp2Fn.apply(x2, head[0].weight, head[0].bias, head[2].weight, head[2].bias)
+
+
+def _input_dropout(module: nn.Module, x: torch.Tensor) -> torch.Tensor:
+    p = float(module.dropout.p)
+    if p > 0 and module.training:
+        return K.DropoutFn.apply(K._f32(x), None, p, _seed())
+    return x
+
+
+class TextEncoder(nn.Module):
+    """news_encoding.TextEncoder (news_encoding.py:8-60).
+
+    ``forward`` accepts the reference's dense ``(x[b,n,s,d], m[b,n,s,1])`` pair (tuple or list) or an
+    ``IndexedTitles`` (int32 news ids into a device-resident TitleStore); in the indexed case the token
+    rows are gathered inside the kernels and the dense (b,n,s,d) tensor never exists."""
+
+    def __init__(self, pooler: nn.Module, p_dropout: float, out_features: int, in_features: Optional[int] = 768,
+                 head: bool = True, activation: nn.Module = nn.ReLU(), att: Optional[nn.Module] = None,
+                 bias: bool = True):
+        super().__init__()
+        self.dummy_param = nn.Parameter(torch.zeros(1))
+        self.dropout = nn.Dropout(p=p_dropout)
+        self.att = att
+        self.pooler = pooler
+        if head:
+            assert in_features is not None, 'in_features is required if head is True'
+            self.head = nn.Sequential(nn.Linear(in_features, out_features, bias=bias), activation,
+                                      nn.Linear(out_features, out_features, bias=bias))
+        self.out_dim = out_features
+
+    def _encode(self, x2, rows, mask, R: int, S: int):
+        if self.att is not None:
+            x2, rows = self.att.attend(x2, rows, mask, R, S), None
+        pooled, _ = self.pooler.pool(x2, rows, mask, R, S)
+        return _apply_head(self.head, pooled) if hasattr(self, 'head') else pooled
+
+    def forward(self, inpt):
+        device = _dev(self)
+        if isinstance(inpt, IndexedTitles):
+            store = inpt.store
+            ids = inpt.news_ids.to(device)
+            b, n = ids.shape
+            S = store.seq_len
+            rows, mask = K.expand_titles(store.title_tokens, ids)
+            if self.dropout.p > 0 and self.training:
+                raise NotImplementedError('input dropout on gathered titles (every shipped config has p_dropout 0)')
+            e = self._encode(store.token_table, rows, mask, b * n, S)
+        else:
+            x, m = inpt
+            x, m = x.to(device), m.to(device)
+            b, n, S, d = x.shape
+            x = _input_dropout(self, x)
+            mask = _flat_mask(m, b * n * S)
+            e = self._encode(K._f32(x).reshape(b * n * S, d), None, mask, b * n, S)
+        cm = K.collapse_mask(mask, b * n, S)
+        return e.view(b, n, self.out_dim), cm.view(b, n, 1)
+
+
+class UserEncoder(nn.Module):
+    """user_encoding.UserEncoder (user_encoding.py:6-81); ``out_dim`` is accepted and ignored like the reference."""
+
+    def __init__(self, pooler: nn.Module, p_dropout: float, emb_dim: Optional[int] = None,
+                 out_dim: Optional[int] = None, att: Optional[nn.Module] = None, head: bool = False,
+                 activation: nn.Module = nn.ReLU(), bias: bool = True):
+        super().__init__()
+        self.dummy_param = nn.Parameter(torch.zeros(1))
+        self.dropout = nn.Dropout(p=p_dropout)
+        self.att = att
+        self.pooler = pooler
+        if head:
+            assert emb_dim is not None
+            self.head = nn.Sequential(nn.Linear(emb_dim, emb_dim, bias=bias), activation,
+                                      nn.Linear(emb_dim, emb_dim, bias=bias))
+
+    def forward(self, inpt, add_features: Optional[dict] = None, return_weights: bool = False):
+        x, m = inpt
+        device = _dev(self)
+        x, m = x.to(device), m.to(device)
+        x = _input_dropout(self, x)
+        x2, R, L = _flat_rows(x)
+        mask = _flat_mask(m, R * L)
+        if self.att is not None:
+            x2 = self.att.attend(x2, None, mask, R, L)
+        a = None
+        if isinstance(self.pooler, MaskedMean):
+            pooled = self.pooler(x2.view(R, L, -1), mask.view(R, L, 1)).squeeze(1)
+        else:
+            pooled, a = self.pooler.pool(x2, None, mask, R, L)
+        if hasattr(self, 'head'):
+            pooled = _apply_head(self.head, pooled)
+        u = pooled.unsqueeze(1)
+        return (u, a.unsqueeze(-1)) if return_weights else u
+
+
+class DotScoring(nn.Module):
+    """scoring.DotScoring (scoring.py:6-23): u (B,1,D), c (B,N,D) -> (B,N,1)."""
+
+    def __init__(self, normalize: bool = False):
+        super().__init__()
+        if normalize:
+            raise NotImplementedError('normalize=True is never enabled by the reference factory')
+        self.normalize = normalize
+
+    def forward(self, u: torch.Tensor, c: torch.Tensor):
+        B, N, T = c.shape
+        return K.DotScoreFn.apply(K._f32(u).reshape(B, T), K._f32(c)).unsqueeze(-1)
+
+
+class ParentRec(nn.Module):
+    """parent.ParentRec (parent.py:8-81): news_encoder x2 -> user_encoder -> rec_model."""
+
+    def __init__(self, news_encoder: nn.Module, user_encoder: nn.Module, rec_model: nn.Module,
+                 text_feature: str = 'title_emb'):
+        super().__init__()
+        self.news_encoder = news_encoder
+        self.user_encoder = user_encoder
+        self.rec_model = rec_model
+        self.text_feature = text_feature
+
+    def _forward(self, history, candidates, add_user_feats=None, return_embeddings: bool = False):
+        h, hm = self.news_encoder(history)
+        c, _ = self.news_encoder(candidates)
+        u = self.user_encoder((h, hm), add_user_feats)
+        r = self.rec_model(u, c)
+        return (r, u, c) if return_embeddings else r
+
+    def forward(self, batch: dict, return_embeddings: bool = False):
+        return self._forward(history=batch['user_features']['history'][self.text_feature],
+                             candidates=batch['candidate_features'][self.text_feature],
+                             add_user_feats=batch['user_features'].get('other'),
+                             return_embeddings=return_embeddings)
+
+    def get_user_embeddings(self, batch: dict) -> torch.Tensor:
+        history = batch['user_features']['history'][self.text_feature]
+        if isinstance(history, list) and len(history) == 2:
+            history = tuple(history)
+        news_emb, news_mask = self.news_encoder(history)
+        return self.user_encoder((news_emb, news_mask)).squeeze(1)

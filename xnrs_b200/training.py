@@ -1,0 +1,223 @@
+"""Trainer loss hooks of the reference (xnrs/training.py) on top of the fused kernels.
+
+Kept: the hook names and semantics — ``_init_loss`` / ``self.L``, ``forward(batch)``, ``_train_step``,
+``_test_step``, ``_compute_contrastive_loss`` — and Adam with torch defaults.  Dropped (host orchestration,
+out of scope): dataloaders, epoch loops, wandb, checkpoint / CSV export.
+
+Differences that are deliberate and documented in DESIGN.md:
+  * the user embedding for the contrastive term is taken from the SAME forward pass as the scores
+    (``share_user_forward=True``); the reference runs the history side twice (training.py:409), which
+    gives identical values whenever dropout is off (every config except NRMS' attention dropout);
+  * all parameters live in one flat buffer so Adam is one kernel launch and data-parallel training
+    all-reduces one bucket.
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import kernels as K
+from .models.components import DotScoring
+from .models.zoo import Cfg
+
+
+def batch_to_device(batch: dict, device) -> None:
+    """xnrs/utils.py:88-93 (tensors and nested dicts; (x, m) tuples are moved by the encoders themselves)."""
+    for k, v in batch.items():
+        if isinstance(v, torch.Tensor):
+            batch[k] = v.to(device, non_blocking=True)
+        elif isinstance(v, dict):
+            batch_to_device(v, device)
+
+
+def theme_labels(themes, device) -> torch.Tensor:
+    """training.py:414-417 — theme strings -> int labels (only label equality matters). Accepts int tensors too."""
+    if isinstance(themes, torch.Tensor):
+        return themes.to(device=device, dtype=torch.int32).contiguous()
+    order: Dict[str, int] = {}
+    return torch.tensor([order.setdefault(t, len(order)) for t in themes], dtype=torch.int32, device=device)
+
+
+class FlatAdam:
+    """torch.optim.Adam(lr, defaults) (training.py:39) over ONE flat parameter / gradient buffer.
+
+    Every parameter becomes a view into ``flat_p`` and owns a persistent ``.grad`` view into ``flat_g``
+    (autograd accumulates into it in place), so the update is a single xnrs_adam_step launch and a
+    data-parallel job all-reduces a single bucket."""
+
+    def __init__(self, params: Iterable[nn.Parameter], lr: float, betas=(0.9, 0.999), eps: float = 1e-8,
+                 graph_safe: bool = False):
+        self.params: List[nn.Parameter] = [p for p in params if p.requires_grad]
+        dev = self.params[0].device
+        sizes = [((p.numel() + 3) // 4) * 4 for p in self.params]          # keep every view 16-byte aligned
+        total = sum(sizes)
+        self.flat_p = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.flat_g = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.m = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.v = torch.zeros(total, device=dev, dtype=torch.float32)
+        off = 0
+        for p, n in zip(self.params, sizes):
+            view = self.flat_p[off:off + p.numel()].view_as(p)
+            view.copy_(p.data)
+            p.data = view
+            p.grad = self.flat_g[off:off + p.numel()].view_as(p)
+            off += n
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.step_count = 0
+        self.graph_safe = graph_safe
+        if graph_safe:      # step counter and bias corrections live on the device so a CUDA graph replays them
+            self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
+            self.bc_dev = torch.zeros(2, device=dev, dtype=torch.float32)
+
+    def zero_grad(self) -> None:
+        self.flat_g.zero_()
+
+    def step(self, grad_scale: float = 1.0) -> None:
+        self.step_count += 1
+        bc = None
+        if self.graph_safe:
+            K.call('xnrs_adam_tick', self.step_dev, self.betas[0], self.betas[1], self.bc_dev)
+            bc = self.bc_dev
+        K.adam_step(self.flat_p, self.flat_g, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps,
+                    self.step_count, bc, grad_scale)
+
+
+class RankingTrainer:
+    """common part of the reference's BaseTrainer / RankingTrainer (training.py:24-44, 191-243)."""
+
+    loss_kind = K.LOSS_MSE_RELU
+    eval_act = 1            # activation applied to raw scores before the ranking metrics (relu)
+
+    def __init__(self, cfg, model: nn.Module, trainset=None, testset=None, graph_safe: bool = False):
+        self.cfg = cfg if isinstance(cfg, Cfg) else Cfg(cfg)
+        self.model = model
+        self.device = torch.device(self.cfg.get('device', 'cuda:0'))
+        self.model.to(self.device)
+        self.optimizer = FlatAdam(self.model.parameters(), lr=float(self.cfg.get('lr', 1e-4)), graph_safe=graph_safe)
+        self._init_loss()
+        self.current_train_step = 0
+
+    # -- loss hooks ---------------------------------------------------------------------------------
+    def _init_loss(self):
+        kind = self.loss_kind
+
+        def loss(scores: torch.Tensor, target: torch.Tensor, weight: Optional[torch.Tensor] = None):
+            """self.L(s, t[, w]) of the reference on RAW scores (B,N,1): the activation is fused in."""
+            B, N = scores.shape[0], scores.shape[1]
+            l, _, _ = K.ScoreLossFn.apply(None, K._f32(scores).reshape(B, N), _flat(target), _flat(weight), kind)
+            return l
+        self.L = loss
+
+    def raw_scores(self, batch) -> torch.Tensor:
+        batch_to_device(batch, self.device)
+        return self.model.forward(batch)
+
+    def forward(self, batch) -> torch.Tensor:
+        """scores with the trainer's output activation (training.py:388-392 applies relu)."""
+        s = self.raw_scores(batch)
+        return K.ReluFn.apply(s) if self.loss_kind == K.LOSS_MSE_RELU else s
+
+    def _embeddings(self, batch):
+        """(u (B,T), c (B,N,T)) from ONE forward pass; None if the model cannot return embeddings (NPA)."""
+        batch_to_device(batch, self.device)
+        try:
+            r, u, c = self.model(batch, return_embeddings=True)
+        except TypeError:
+            return None
+        if not isinstance(getattr(self.model, 'rec_model', None), DotScoring):
+            return None
+        B, N, T = c.shape
+        return K._f32(u).reshape(B, T), K._f32(c)
+
+    def rec_loss(self, batch):
+        """-> (loss_rec, preds (B,N,1), user_emb (B,T) or None): scorer and loss fused when the model exposes u, c."""
+        t = _flat(batch['targets'].to(self.device))
+        w = _flat(batch['weights'].to(self.device)) if 'weights' in batch else None
+        uc = self._embeddings(batch)
+        if uc is not None:
+            u, c = uc
+            loss, preds, _ = K.ScoreLossFn.apply(u, c, t, w, self.loss_kind)
+            return loss, preds.unsqueeze(-1), u
+        s = self.model.forward(batch)
+        B, N = s.shape[0], s.shape[1]
+        loss, preds, _ = K.ScoreLossFn.apply(None, K._f32(s).reshape(B, N), t, w, self.loss_kind)
+        return loss, preds.unsqueeze(-1), None
+
+    def _train_step(self, batch: dict) -> dict:
+        """BaseTrainer._train_step (training.py:97-112)."""
+        self.optimizer.zero_grad()
+        loss, preds, _ = self.rec_loss(batch)
+        loss.backward()
+        self.optimizer.step()
+        self.current_train_step += 1
+        return {'loss': loss.detach(), 'logits': preds}
+
+    @torch.no_grad()
+    def _test_step(self, batch: dict) -> dict:
+        """RankingTrainer._test_step (training.py:194-243) for one impression (B=1, all candidates)."""
+        t = batch['targets'].to(self.device)
+        loss, preds, _ = self.rec_loss(batch)
+        raw = self.raw_scores(batch) if self.eval_act == 2 else None
+        scores = K._f32(preds).reshape(-1) if raw is None else K._f32(raw).reshape(-1)
+        n = scores.numel()
+        offsets = torch.tensor([0, n], device=self.device, dtype=torch.int64)
+        scores = scores.clone()
+        _, m = K.eval_impressions(None, None, None, offsets, _flat(t), act=0 if raw is None else 2, scores=scores)
+        m = m[0].tolist()
+        return {'auc': m[0], 'rr': m[1], 'ndcg@5': m[2], 'ndcg@10': m[3], 'ctr@1': m[4], 'ctr@10': m[5],
+                'scores': scores, 'targets': t.reshape(-1), 'loss': loss}
+
+
+def _flat(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    return None if t is None else K._f32(t).reshape(-1)
+
+
+class MSERankingTrainer(RankingTrainer):
+    """training.py:376-392 — MSE(relu(score), target)."""
+    loss_kind = K.LOSS_MSE_RELU
+    eval_act = 1
+
+
+class BCELogitsRankingTrainer(RankingTrainer):
+    """training.py:334-373 — BCE with logits; evaluation ranks sigmoid(score)."""
+    loss_kind = K.LOSS_BCE_LOGITS
+    eval_act = 2
+
+
+class ContrastiveRankingTrainer(MSERankingTrainer):
+    """training.py:395-472 — MSE(relu(score), target) + lambda * supervised InfoNCE(user embeddings, theme)."""
+
+    def __init__(self, cfg, model, trainset=None, testset=None, share_user_forward: bool = True,
+                 graph_safe: bool = False):
+        super().__init__(cfg, model, trainset, testset, graph_safe=graph_safe)
+        self.share_user_forward = share_user_forward
+
+    def _init_loss(self):
+        super()._init_loss()
+        self.temperature = float(self.cfg.get('contrastive_temperature', 0.1))
+        self.lambda_cl = float(self.cfg.get('contrastive_lambda', 0.1))
+
+    def _compute_contrastive_loss(self, embeddings: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        if embeddings.dim() > 2:
+            embeddings = embeddings.reshape(embeddings.shape[0], -1)       # NAML's (B,1,D), training.py:443-444
+        return K.InfoNCEFn.apply(K._f32(embeddings), labels.to(torch.int32).contiguous(), self.temperature)
+
+    def losses(self, batch: dict):
+        """-> (total, loss_rec, loss_cl, preds)"""
+        loss_rec, preds, u = self.rec_loss(batch)
+        if u is None or not self.share_user_forward:
+            u = self.model.get_user_embeddings(batch)
+        labels = theme_labels(batch['main_theme'], self.device)
+        loss_cl = self._compute_contrastive_loss(u, labels)
+        total = loss_rec + self.lambda_cl * loss_cl          # two device scalars (training.py:422)
+        return total, loss_rec, loss_cl, preds
+
+    def _train_step(self, batch: dict) -> dict:
+        self.optimizer.zero_grad()
+        total, loss_rec, loss_cl, preds = self.losses(batch)
+        total.backward()
+        self.optimizer.step()
+        self.current_train_step += 1
+        return {'loss': total.detach(), 'loss_rec': loss_rec.detach(), 'loss_cl': loss_cl.detach(), 'logits': preds}

@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""Headline benchmark: CL bi-encoder (config/mind_small_CL.yml, `model: standard`) TRAINING throughput in
+impressions/s on synthetic MIND-shaped data (BASELINE.json configs[1]; north-star shapes S=30, H=50, 1:4).
+
+One "step" = one full ContrastiveRankingTrainer step over one batch of impressions: index gather from the
+device-resident token table, title + user encoders, fused dot-score + MSE(ReLU), supervised InfoNCE,
+backward through everything, Adam.  Contract: see the task statement (`value` = inputs resident in HBM,
+`e2e` = host index buffers + H2D + D2H loss read inside the timed region, `roofline` for the dominant
+kernel timed live with CUDA events, `cpu_baseline` = the CPU oracle on a bounded sample).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B] [--precision fp32]
+N>1 is launched by torchrun (one rank per GPU, NCCL); rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+CL_CFG = dict(model='standard', scoring='dot', text_features=['title_emb'], catg_features=[], title_emb_dim=256,
+              total_emb_dim=256, d_backbone=768, p_dropout=0., bias=False, n_negatives=4, lr=1e-4,
+              contrastive_temperature=0.08, contrastive_lambda=0.01)          # config/mind_small_CL.yml
+SEQ_LEN, HIST_LEN, N_NEWS, VOCAB = 30, 50, 65_238, 100_000                     # SURVEY §8(d) north-star shapes
+METRIC, UNIT = 'train impressions/s', 'impressions/s'
+
+
+def workload_name(batch):
+    return (f'CL bi-encoder (mind_small_CL.yml, model=standard) train step fwd+loss(MSE.ReLU + 0.01*InfoNCE)+bwd+Adam; '
+            f'synthetic MIND-shaped: S={SEQ_LEN} tokens, H={HIST_LEN} history, 1:4 negatives, D=768, '
+            f'{N_NEWS} news, {VOCAB}-row token table; {batch} impressions/GPU/step')
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))), 'measured'
+    except Exception:
+        return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, 'fallback'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '100', '-i', str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=lambda: self.rows.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(',')]
+            if len(f) < 6 or not f[0].isdigit():
+                continue
+            sm.append(int(f[0]))
+            mx.append(int(f[1]))
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': max(mx), 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def oracle_step_fn(batch_size, threads):
+    """the CPU path: the oracle's restatement of ContrastiveRankingTrainer._train_step (two history forwards like
+    the reference, training.py:402-431) + autograd + Adam, on dense host batches built from the same ids."""
+    from oracle import xnrs_oracle as O
+    from xnrs_b200 import synthetic as syn
+    from xnrs_b200.models import make_model
+    torch.set_num_threads(threads)
+    cat = syn.make_catalogue(N_NEWS, SEQ_LEN, VOCAB, 768, seed=0)
+    torch.manual_seed(0)
+    P = {k: v.detach().clone().requires_grad_(True) for k, v in make_model(CL_CFG).state_dict().items()}
+    state = {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in P.items()}
+    batches = [syn.dense_batch(cat, syn.make_train_batch(N_NEWS, batch_size, HIST_LEN, seed=100 + i)) for i in range(2)]
+    counter = [0]
+
+    def step():
+        b = batches[counter[0] % len(batches)]
+        counter[0] += 1
+        for v in P.values():
+            v.grad = None
+        scores = O.parent_forward(P, b)
+        u = O.parent_user_embeddings(P, b)
+        loss, _, _ = O.contrastive_train_loss(scores, b['targets'], u, b['main_theme'].long(),
+                                              CL_CFG['contrastive_temperature'], CL_CFG['contrastive_lambda'])
+        loss.backward()
+        with torch.no_grad():
+            for k, v in P.items():
+                if v.grad is not None:
+                    O.adam_step(v, v.grad, state[k][0], state[k][1], counter[0], CL_CFG['lr'])
+        return float(loss.detach())
+    return step
+
+
+def time_cpu(batch_size, steps, warmup, threads):
+    step = oracle_step_fn(batch_size, threads)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return batch_size * steps / dt, dt / steps
+
+
+def run_reference(args):
+    """--impl reference: the reference algorithm's CPU path (oracle port; the Python reference cannot travel to the
+    GPU box) with all host threads, same metric/config, each step a bounded sample of the workload."""
+    if int(os.environ.get('RANK', '0')) != 0:
+        return
+    threads = os.cpu_count() or 1
+    bs = args.ref_batch
+    value, per_step = time_cpu(bs, args.steps, args.warmup, threads)
+    sample = f'{bs} impressions/step x {args.steps} steps (bounded sample of the {args.batch}/GPU workload)'
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': per_step * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': workload_name(args.batch), 'reference_sample': sample},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=1024, help='impressions per GPU per step')
+    ap.add_argument('--ref-batch', type=int, default=64, help='impressions per CPU step (reference arm / cpu_baseline)')
+    ap.add_argument('--precision', default='fp32', choices=['fp32', 'tf32x3', 'tf32', 'bf16'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch.distributed as dist
+    from xnrs_b200 import kernels as K
+    from xnrs_b200 import synthetic as syn
+    from xnrs_b200.data import TitleStore
+    from xnrs_b200.distributed import DataParallelTrainer
+    from xnrs_b200.models import make_model
+    from xnrs_b200.training import ContrastiveRankingTrainer
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    if world != args.gpus and rank == 0:
+        print(f'warning: --gpus {args.gpus} but WORLD_SIZE {world}', file=sys.stderr)
+    K.set_precision(args.precision)
+    B = args.batch
+
+    cat = syn.make_catalogue(N_NEWS, SEQ_LEN, VOCAB, 768, seed=0)
+    store = TitleStore(cat.token_table.to(dev), cat.title_tokens.to(dev))
+    torch.manual_seed(0)
+    trainer = ContrastiveRankingTrainer(dict(CL_CFG, device=str(dev)), make_model(CL_CFG))
+    trainer.model.train()
+    dp = DataParallelTrainer(trainer)
+
+    n_batches = 8           # distinct batches cycled through; weak scaling: every rank draws its own B impressions
+    raws = [syn.make_train_batch(N_NEWS, B, HIST_LEN, seed=1000 + 97 * rank + i) for i in range(n_batches)]
+    pinned = [{k: v.pin_memory() for k, v in r.items()} for r in raws]
+    resident = [syn.index_batch(store, cat, r, dev) for r in raws]
+    h2d_bytes = sum(v.numel() * v.element_size() for v in raws[0].values())
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        dp.train_step(resident[i % n_batches])
+
+    # ---- timed region 1: inputs resident in HBM; every kernel call bracketed by CUDA events on its stream ----
+    records = []
+
+    def hook(name, args_):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        records.append((name, args_, s, e))
+        return s, e
+
+    K.set_event_hook(hook)
+    sync_all()
+    n0 = K.launch_count()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        t0.record()
+        for i in range(args.steps):
+            dp.train_step(resident[i % n_batches])
+        t1.record()
+        sync_all()
+    K.set_event_hook(None)
+    launches = K.launch_count() - n0
+    ms = torch.tensor([t0.elapsed_time(t1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms)
+    value = B * world * args.steps / (ms_total * 1e-3)
+
+    # dominant kernel: aggregate event time per entry point; GEMM FLOPs are 2*M*N*K per launch
+    agg = {}
+    for name, a, s, e in records:
+        d = agg.setdefault(name, [0.0, 0, 0.0])
+        d[0] += s.elapsed_time(e)
+        d[1] += 1
+        if name == 'xnrs_gemm':
+            d[2] += 2.0 * a[2] * a[3] * a[4]
+    top = max(agg.items(), key=lambda kv: kv[1][0])
+    pk, pk_kind = peaks()
+    gemm_ms, gemm_n, gemm_flop = agg.get('xnrs_gemm', [0.0, 0, 0.0])
+    kernel_ms_total = sum(v[0] for v in agg.values())
+    roofline = {
+        'kernel': 'gemm_simt_kernel (xnrs_gemm: fc1 / head / weight-gradient GEMMs)' if args.precision == 'fp32'
+                  else 'xnrs_gemm (tcgen05 path where taken)',
+        'bound': 'tensor', 'achieved': gemm_flop / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None,
+        'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
+        'frac': (gemm_flop / (gemm_ms * 1e-3) / 1e12 / pk['bf16_tflops_sustained']) if gemm_ms else None,
+        'traffic': None, 'peak_source': f'{pk_kind} (sustained bf16 GEMM; kernel timed inside a long step)',
+        'launches_timed': gemm_n, 'avg_launch_ms': gemm_ms / max(gemm_n, 1),
+        'share_of_step_kernel_time': gemm_ms / kernel_ms_total if kernel_ms_total else None,
+        'top_entry_point_by_time': top[0],
+        'per_entry_point_ms_per_step': {k: round(v[0] / args.steps, 4) for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])},
+    }
+
+    # ---- timed region 2: end to end through the public trainer API with HOST (pinned) index buffers ----
+    def e2e_step(i):
+        out = dp.train_step(syn.index_batch(store, cat, pinned[i % n_batches], dev))
+        return float(out['loss'])            # device -> host read of the step's loss (4 bytes, synchronises)
+
+    e2e_step(0)
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wall0 = time.perf_counter()
+    e0.record()
+    last = 0.0
+    for i in range(args.steps):
+        last = e2e_step(i)
+    e1.record()
+    sync_all()
+    wall = time.perf_counter() - wall0
+    ems = torch.tensor([max(e0.elapsed_time(e1), wall * 1e3)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+    e2e_value = B * world * args.steps / (float(ems) * 1e-3)
+
+    out = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': {'fp32': 'f32', 'tf32x3': 'f32 (3xTF32)', 'tf32': 'tf32', 'bf16': 'bf16'}[args.precision],
+        'data': 'synthetic',
+        'config': {'workload': workload_name(B), 'global_batch': B * world, 'parallelism': f'dp{world}',
+                   'l2': 'inputs larger than L2: 307 MB token table, ~5 GB of gathered rows per step, 8 batches cycled',
+                   'precision': args.precision, 'final_loss': last},
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4,
+                'note': 'host input = int32 news ids / targets / labels (the index fast path of the drop-in API)'},
+        'gpu_launches': launches, 'roofline': roofline, 'clocks': clocks.summary(),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, per = time_cpu(args.ref_batch, 3, 1, threads)
+        out['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                               'sample': f'{args.ref_batch} impressions/step x 3 steps after 1 warm-up, oracle '
+                                         f'(torch CPU fp32, autograd + Adam), same shapes'}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

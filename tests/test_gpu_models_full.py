@@ -1,0 +1,94 @@
+"""Full-width parity on the GPU: the five models at the reference layer widths (D=768, E=256, A=256, 16 heads) on both
+shape sets (north-star S=30/H=50 and reference S=50/H=25), fed through the INDEX fast path (device-resident token
+table + int32 news ids), against the CPU oracle on the dense batch built from the same ids."""
+import pytest
+import torch
+
+from _common import assert_close
+from oracle import xnrs_oracle as O
+from xnrs_b200 import synthetic as syn
+from xnrs_b200.data import TitleStore
+from xnrs_b200.models import make_model
+from xnrs_b200.training import ContrastiveRankingTrainer, MSERankingTrainer
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+N_NEWS, VOCAB, N_USERS = 400, 3000, 1000
+
+BASE = dict(scoring='dot', text_features=['title_emb'], catg_features=[], title_emb_dim=256, total_emb_dim=256,
+            d_backbone=768, n_heads=16, p_dropout=0., bias=False, n_categories=19, n_subcategories=264,
+            n_users=N_USERS, cat_emb_dim=16, sub_emb_dim=16, user_emb_dim=64, contrastive_temperature=0.08,
+            contrastive_lambda=0.1, lr=1e-4, device=DEV)
+MODELS = {
+    'cl': dict(model='standard', contrastive_lambda=0.01),
+    'nrms': dict(model='NRMS'),
+    'naml': dict(model='NAML', text_features=['title_emb', 'abstract_emb'],
+                 catg_features=['category_index', 'subcategory_index']),
+    'lstur': dict(model='LSTUR', total_emb_dim=272, long_term_method='embedding', long_short_term_method='con',
+                  p_user_dropout=0.0, catg_features=['category_index']),
+    'npa': dict(model='NPA'),
+}
+
+
+def oracle_forward(name, P, batch, cfg):
+    if name in ('cl', 'nrms'):
+        nh = cfg['n_heads'] if name == 'nrms' else 0
+        r, u, _ = O.parent_forward(P, batch, nh, return_embeddings=True)
+        return r, u.squeeze(1)
+    if name == 'naml':
+        r, u, _ = O.naml_forward(P, batch, return_embeddings=True)
+        return r, u.squeeze(1)
+    if name == 'lstur':
+        r, u, _ = O.lstur_forward(P, batch, 'con', cfg['st_hist_len'], return_embeddings=True)
+        return r, u.squeeze(1)
+    return O.npa_forward(P, batch), None
+
+
+@pytest.mark.parametrize('S,H', [(30, 50), (50, 25)])
+@pytest.mark.parametrize('name', list(MODELS))
+def test_index_path_matches_oracle(name, S, H):
+    cfg = dict(BASE, **MODELS[name], seq_len=S, hist_len=H, st_hist_len=H)
+    B = 5
+    cat = syn.make_catalogue(N_NEWS, S, VOCAB, 768, seed=3, with_abstract=(name == 'naml'))
+    raw = syn.make_train_batch(N_NEWS, B, H, n_users=N_USERS, seed=4)
+    raw['hist_ids'][1, 3:] = 0                      # a short history
+    torch.manual_seed(1)
+    model = make_model(cfg)
+    with torch.no_grad():                           # default init keeps scores tiny; widen the dynamic range
+        for p in model.parameters():
+            if p.dim() > 1:
+                p.mul_(1.5)
+    P = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in model.state_dict().items()}
+    trainer = (MSERankingTrainer if name == 'npa' else ContrastiveRankingTrainer)(cfg, model)
+    model.eval()
+    store = TitleStore(cat.token_table.to(DEV), cat.title_tokens.to(DEV))
+    astore = TitleStore(store.token_table, cat.abstract_tokens.to(DEV)) if name == 'naml' else None
+    batch = syn.index_batch(store, cat, raw, DEV, abstract_store=astore)
+    dense = syn.dense_batch(cat, raw, with_abstract=(name == 'naml'))
+
+    want_scores, want_u = oracle_forward(name, P, dense, cfg)
+    trainer.optimizer.zero_grad()
+    if name == 'npa':
+        total, preds, _ = trainer.rec_loss(batch)
+        want_total, _ = O.mse_relu_loss(want_scores, dense['targets'])
+    else:
+        total, l_rec, l_cl, preds = trainer.losses(batch)
+        want_total, want_rec, want_cl = O.contrastive_train_loss(
+            want_scores, dense['targets'], want_u, dense['main_theme'].long(), cfg['contrastive_temperature'],
+            cfg['contrastive_lambda'])
+        assert_close(l_cl, want_cl, 1e-4, 'InfoNCE')
+    assert_close(preds, torch.relu(want_scores), 1e-4, 'relu(scores)')
+    assert_close(total, want_total, 1e-4, 'loss')
+    total.backward()
+    want_total.backward()
+    gmax = max(float(v.grad.abs().max()) for v in P.values() if v.grad is not None)
+    for k, p in model.named_parameters():
+        want = P[k].grad if P[k].grad is not None else torch.zeros_like(P[k])
+        assert_close(p.grad, want, 2e-4, 'grad ' + k, atol=2e-6 * gmax)
+
+    # the dense reference-format batch (moved to the device by the encoders themselves) gives the same scores
+    with torch.no_grad():
+        dense_scores = model(dense)
+        index_scores = model(batch)
+    assert_close(dense_scores, index_scores, 1e-6, 'dense vs index path')
+    assert_close(index_scores, want_scores, 1e-4, 'scores')

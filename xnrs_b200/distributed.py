@@ -1,0 +1,106 @@
+"""Data-parallel plumbing (one process per GPU, torch.distributed over NCCL/NVLink; gloo in the CPU tests).
+
+The reference is single-process; what shards naturally is the impression batch (§8(e)):
+  * every rank runs the same step on B/world impressions with replicated tables and parameters;
+  * the supervised InfoNCE term couples users across the batch, so user embeddings and labels are
+    all-gathered and every rank evaluates the GLOBAL-batch loss for its own anchors (reference semantics at
+    the global batch size); the backward all-reduces the (B,E) embedding gradient;
+  * all parameter gradients live in FlatAdam's single flat buffer: ONE all-reduce per step, averaged by
+    folding 1/world into the Adam kernel's grad_scale.
+No collective is issued on the data path itself (gathers/encoders/scorer are rank-local).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import kernels as K
+
+
+def world() -> int:
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def rank() -> int:
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
+def shard_range(n: int, r: int, w: int):
+    """contiguous balanced slice [lo, hi) of n units for rank r of w"""
+    base, rem = divmod(n, w)
+    lo = r * base + min(r, rem)
+    return lo, lo + base + (1 if r < rem else 0)
+
+
+class DistInfoNCEFn(torch.autograd.Function):
+    """global-batch supervised InfoNCE (training.py:433-472) with rank-local anchors."""
+
+    @staticmethod
+    def forward(ctx, emb, labels, temperature):
+        w, r = world(), rank()
+        Ba, E = emb.shape
+        dev = emb.device
+        emb_all = torch.empty((w * Ba, E), device=dev, dtype=torch.float32)
+        lab_all = torch.empty(w * Ba, device=dev, dtype=torch.int32)
+        dist.all_gather_into_tensor(emb_all, emb.contiguous())
+        dist.all_gather_into_tensor(lab_all, labels.to(torch.int32).contiguous())
+        Bk, row0 = w * Ba, r * Ba
+        ehat = torch.empty_like(emb_all)
+        inv_norm = torch.empty(Bk, device=dev, dtype=torch.float32)
+        K.call('xnrs_infonce_normalize', emb_all, Bk, E, ehat, inv_norm)
+        ehat_a = ehat[row0:row0 + Ba]
+        sim = K.gemm(ehat_a, ehat, trans_b=True)
+        stats = torch.zeros(2, device=dev, dtype=torch.float32)
+        K.call('xnrs_infonce_rows', sim, lab_all, Ba, Bk, row0, temperature, stats)
+        dist.all_reduce(stats)
+        loss = torch.empty(1, device=dev, dtype=torch.float32)
+        K.call('xnrs_infonce_finalize', stats, loss)
+        ctx.save_for_backward(ehat, inv_norm, sim, stats)
+        ctx.dims = (Ba, Bk, E, row0, w)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        ehat, inv_norm, G, stats = ctx.saved_tensors
+        Ba, Bk, E, row0, w = ctx.dims
+        ehat_a = ehat[row0:row0 + Ba]
+        d_ehat = K.gemm(G, ehat_a, trans_a=True)                              # key side, all Bk rows
+        K.gemm(G, ehat, out=d_ehat[row0:row0 + Ba], accumulate=True)          # anchor side, local rows
+        dist.all_reduce(d_ehat)
+        d_all = torch.empty_like(ehat)
+        K.call('xnrs_infonce_normalize_bwd', d_ehat, ehat, inv_norm, stats, 1.0, Bk, E, d_all)
+        # parameter gradients are averaged over ranks afterwards; this term is already the gradient of the
+        # GLOBAL loss, so pre-multiply by world to survive the averaging
+        d_emb = torch.empty((Ba, E), device=ehat.device, dtype=torch.float32)
+        K.call('xnrs_axpby', Ba * E, float(w), K._f32(g).reshape(1), d_all[row0:row0 + Ba].contiguous(), 0.0, d_emb)
+        return d_emb, None, None
+
+
+class DataParallelTrainer:
+    """wraps a ContrastiveRankingTrainer / MSERankingTrainer for one-process-per-GPU data parallelism."""
+
+    def __init__(self, trainer):
+        self.trainer = trainer
+        self.world, self.rank = world(), rank()
+        if self.world > 1:
+            dist.broadcast(trainer.optimizer.flat_p, src=0)                  # identical replicas
+            if hasattr(trainer, '_compute_contrastive_loss'):
+                temp = trainer.temperature
+                trainer._compute_contrastive_loss = (
+                    lambda e, l: DistInfoNCEFn.apply(K._f32(e.reshape(e.shape[0], -1)), l, temp))
+
+    def train_step(self, batch: dict) -> dict:
+        tr = self.trainer
+        tr.optimizer.zero_grad()
+        if hasattr(tr, 'losses'):
+            total, loss_rec, loss_cl, preds = tr.losses(batch)
+            out = {'loss': total.detach(), 'loss_rec': loss_rec.detach(), 'loss_cl': loss_cl.detach(), 'logits': preds}
+        else:
+            total, preds, _ = tr.rec_loss(batch)
+            out = {'loss': total.detach(), 'logits': preds}
+        total.backward()
+        if self.world > 1:
+            dist.all_reduce(tr.optimizer.flat_g)                             # the one gradient bucket
+        tr.optimizer.step(grad_scale=1.0 / self.world)
+        tr.current_train_step += 1
+        return out

@@ -65,10 +65,25 @@ def _arg(a):
     return a
 
 
+_event_hook = None
+
+
+def set_event_hook(hook) -> None:
+    """bench.py timing: ``hook(name, scalar_args) -> (start_event, end_event)`` brackets each entry point with CUDA
+    events recorded on the stream the kernel is launched on (torch's current stream)."""
+    global _event_hook
+    _event_hook = hook
+
+
 def call(name: str, *args) -> None:
     """invoke one C-ABI entry point on the current torch stream; raise on a non-zero status."""
     fn = getattr(_lib.lib(), name)
+    ev = _event_hook(name, tuple(a for a in args if isinstance(a, (int, float)))) if _event_hook else None
+    if ev:
+        ev[0].record()
     rc = fn(*[_arg(a) for a in args], torch.cuda.current_stream().cuda_stream)
+    if ev:
+        ev[1].record()
     if rc != 0:
         raise RuntimeError(f'{name} failed ({rc}): {_lib.last_error()}')
 

@@ -119,7 +119,7 @@ def test_additive_pool_forward_backward(R, L, F_, use_mask):
     assert_close(go, wo, TOL, 'pooled')
     assert_close(ga, wa, TOL, 'weights')
     if use_mask:
-        assert float(go[0].abs().max()) == 0.0             # fully masked -> exactly zero
+        assert float(go[0].detach().abs().max()) == 0.0    # fully masked -> exactly zero
     (go * cu(gout)).sum().backward()
     assert_close(xg.grad, xo.grad, TOL, 'dx')
     for k in P:
@@ -179,8 +179,9 @@ def test_multi_head_attention_forward_backward(R, L, D, h, p):
     assert_close(go, wo, TOL, 'mha out')
     (go * cu(gout)).sum().backward()
     assert_close(xg.grad, xo.grad, TOL, 'dx')
-    for k in P:
-        assert_close(dict(mod.named_parameters())[k[2:]].grad, Po[k].grad, TOL, 'grad ' + k)
+    gmax = max(float(v.grad.abs().max()) for v in Po.values())
+    for k in P:     # d/d k_linear.bias is analytically 0 (a key bias shifts every score of a row equally): noise only
+        assert_close(dict(mod.named_parameters())[k[2:]].grad, Po[k].grad, TOL, 'grad ' + k, atol=1e-5 * gmax)
 
 
 def test_mha_seeded_dropout_is_reproducible_and_unbiased():

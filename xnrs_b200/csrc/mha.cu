@@ -121,7 +121,7 @@ __global__ void mha_bwd_kernel(const float *__restrict__ q, const float *__restr
     if (w >= R * h) return;
     const long long r = w / h;
     const int head = (int)(w - r * h);
-    float *Ks = smem + (size_t)warp * (4 * L * DK + 3 * L);
+    float *Ks = smem + (size_t)warp * (size_t)((4 * L * DK + 3 * L + 3) & ~3);     // 16-byte aligned per-warp slab
     float *Vs = Ks + L * DK, *Qs = Vs + L * DK, *Gs = Qs + L * DK;     // Gs = d_o
     float *Ls = Gs + L * DK, *Ds = Ls + L, *Ms = Ds + L;               // lse, D_i, masked flag
     stage<DK>(Ks, k, r, L, ld, head, lane);
@@ -224,7 +224,7 @@ static int launch_bwd(const float *q, const float *k, const float *v, const floa
                       const float *mask, const float *lse, long long R, int L, int h, const float *keep, float p_drop,
                       unsigned long long seed, float *dq, float *dk_, float *dv, cudaStream_t st) {
     const int wpb = 2;
-    size_t smem = (size_t)wpb * (4 * L * DK + 3 * L) * sizeof(float);
+    size_t smem = (size_t)wpb * (size_t)((4 * L * DK + 3 * L + 3) & ~3) * sizeof(float);
     if (smem > 220 * 1024) return fail(XNRS_ERR_UNSUPPORTED, "%s: sequence too long for shared memory", "xnrs_mha_bwd");
     cudaFuncSetAttribute(mha_bwd_kernel<DK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     mha_bwd_kernel<DK><<<(unsigned)cdiv(R * h, wpb), wpb * 32, smem, st>>>(q, k, v, o, d_o, ld, mask, lse, R, L, h,

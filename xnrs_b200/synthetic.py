@@ -100,12 +100,14 @@ def index_batch(store, cat: Catalogue, raw: Dict[str, torch.Tensor], device, abs
     if abstract_store is not None:
         hist['abstract_emb'] = abstract_store.index(hist_ids)
         cand['abstract_emb'] = abstract_store.index(cand_ids)
-    if cat.category.device != hist_ids.device:
-        cat.category, cat.subcategory = cat.category.to(device), cat.subcategory.to(device)
-    hist['category_index'] = cat.category[hist_ids.long()]
-    cand['category_index'] = cat.category[cand_ids.long()]
-    hist['subcategory_index'] = cat.subcategory[hist_ids.long()]
-    cand['subcategory_index'] = cat.subcategory[cand_ids.long()]
+    key = ('_dev', str(device))
+    if getattr(cat, '_dev_cache', None) is None or cat._dev_cache[0] != key:
+        cat._dev_cache = (key, cat.category.to(device), cat.subcategory.to(device))
+    _, category, subcategory = cat._dev_cache
+    hist['category_index'] = category[hist_ids.long()]
+    cand['category_index'] = category[cand_ids.long()]
+    hist['subcategory_index'] = subcategory[hist_ids.long()]
+    cand['subcategory_index'] = subcategory[cand_ids.long()]
     return {'user_features': {'history': hist, 'other': {'user_index': raw['user_index'].to(device, non_blocking=True)}},
             'candidate_features': cand, 'targets': raw['targets'].to(device, non_blocking=True),
             'main_theme': raw['main_theme'].to(device, non_blocking=True)}

@@ -154,7 +154,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=1024, help='impressions per GPU per step')
     ap.add_argument('--ref-batch', type=int, default=64, help='impressions per CPU step (reference arm / cpu_baseline)')
-    ap.add_argument('--precision', default='fp32', choices=['fp32', 'tf32x3', 'tf32', 'bf16'])
+    ap.add_argument('--precision', default='tf32x3', choices=['fp32', 'tf32x3', 'tf32', 'bf16'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -230,13 +230,18 @@ def main():
     value = B * world * args.steps / (ms_total * 1e-3)
 
     # dominant kernel: aggregate event time per entry point; GEMM FLOPs are 2*M*N*K per launch
-    agg = {}
+    agg, shapes = {}, {}
     for name, a, s, e in records:
         d = agg.setdefault(name, [0.0, 0, 0.0])
-        d[0] += s.elapsed_time(e)
+        dt = s.elapsed_time(e)
+        d[0] += dt
         d[1] += 1
         if name == 'xnrs_gemm':
             d[2] += 2.0 * a[2] * a[3] * a[4]
+            sh = shapes.setdefault(f'{"T" if a[0] else "N"}{"T" if a[1] else "N"} M={a[2]} N={a[3]} K={a[4]}', [0.0, 0, 0.0])
+            sh[0] += dt
+            sh[1] += 1
+            sh[2] += 2.0 * a[2] * a[3] * a[4]
     top = max(agg.items(), key=lambda kv: kv[1][0])
     pk, pk_kind = peaks()
     gemm_ms, gemm_n, gemm_flop = agg.get('xnrs_gemm', [0.0, 0, 0.0])
@@ -251,6 +256,8 @@ def main():
         'launches_timed': gemm_n, 'avg_launch_ms': gemm_ms / max(gemm_n, 1),
         'share_of_step_kernel_time': gemm_ms / kernel_ms_total if kernel_ms_total else None,
         'top_entry_point_by_time': top[0],
+        'gemm_shapes_ms_per_step': {k: f'{v[0] / args.steps:.3f} ms, {v[2] / (v[0] * 1e-3) / 1e12:.1f} TF/s, {v[1] // args.steps}x'
+                                    for k, v in sorted(shapes.items(), key=lambda kv: -kv[1][0])[:8]},
         'per_entry_point_ms_per_step': {k: round(v[0] / args.steps, 4) for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])},
     }
 

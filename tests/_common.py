@@ -64,6 +64,8 @@ def assert_close(a, b, tol=1e-4, what='', atol=0.0):
     assert np.shape(a) == np.shape(b), f'{what}: shape {np.shape(a)} vs {np.shape(b)}'
     assert np.all(np.isfinite(a)), f'{what}: non-finite values'
     e = rel_err(a, b)
+    if os.environ.get('XNRS_SHOW_ERR'):
+        print(f'[err] {what}: {e:.3e} (tol {tol:.1e})')
     if atol and a.size and float(np.max(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)))) <= atol:
         return
     assert e <= tol, f'{what}: relative error {e:.3e} > {tol:.1e}'

@@ -404,3 +404,54 @@ def test_layer_goldens_from_reference():
 def test_cpu_tensors_are_rejected():
     with pytest.raises(RuntimeError, match='CUDA'):
         K.gemm(torch.randn(4, 4), torch.randn(4, 4))
+
+
+@pytest.mark.parametrize('prec,tol', [('tf32x3', 5e-5), ('tf32', 3e-3)])
+@pytest.mark.parametrize('ta,tb', [(0, 1), (1, 0), (0, 0), (1, 1)])
+@pytest.mark.parametrize('M,N,K_', [(256, 256, 768), (1000, 200, 333 * 4), (128, 64, 32), (4097, 768, 768)])
+def test_tensor_core_gemm(prec, tol, ta, tb, M, N, K_):
+    """the tcgen05/TMA path of xnrs_gemm (all four operand-major combinations, ragged tiles) against fp32 matmul"""
+    a = torch.randn((K_, M) if ta else (M, K_), generator=g(1)) / math.sqrt(K_)      # O(1) outputs
+    b = torch.randn((N, K_) if tb else (K_, N), generator=g(2))
+    bias = torch.randn(N, generator=g(3))
+    want = (a.double().T if ta else a.double()) @ (b.double().T if tb else b.double()) + bias.double()
+    with K.precision(prec):
+        got = K.gemm(cu(a), cu(b), trans_a=bool(ta), trans_b=bool(tb), bias=cu(bias))
+        assert_close(got, want.float(), tol, f'tc gemm {prec}')
+        assert_close(K.gemm(cu(a), cu(b), trans_a=bool(ta), trans_b=bool(tb), bias=cu(bias), act=K.ACT_TANH),
+                     torch.tanh(want).float(), tol, 'tanh epilogue')
+        acc = cu(torch.ones(M, N))
+        K.gemm(cu(a), cu(b), trans_a=bool(ta), trans_b=bool(tb), out=acc, accumulate=True)
+        assert_close(acc, (want - bias.double() + 1).float(), tol, 'accumulate')
+
+
+@pytest.mark.parametrize('prec,tol', [('tf32x3', 3e-5), ('tf32', 3e-3)])
+def test_tensor_core_gemm_split_k_weight_gradient_shape(prec, tol):
+    Kl = 40000
+    x, dy = torch.randn(Kl, 768, generator=g(5)), torch.randn(Kl, 256, generator=g(6))
+    want = (dy.double().T @ x.double()).float()
+    with K.precision(prec):
+        assert_close(K.gemm(cu(dy), cu(x), trans_a=True), want, tol, 'auto split-k')
+        acc = cu(torch.ones(256, 768))
+        K.gemm(cu(dy), cu(x), trans_a=True, out=acc, accumulate=True, split_k=5)
+        assert_close(acc, want + 1, tol, 'split-k accumulate')
+
+
+@pytest.mark.parametrize('prec,tol', [('tf32x3', 5e-5), ('tf32', 3e-3)])
+def test_tensor_core_gemm_tma_gather(prec, tol):
+    """table rows gathered by TMA gather4 straight into the swizzled MMA tiles: forward (rows of A) and
+    weight-gradient (rows of B along K) forms, ragged sizes"""
+    V, D, A_ = 5000, 768, 256
+    table = torch.randn(V, D, generator=g(1)) / math.sqrt(D)
+    for R in (1650, 4097):
+        rows = torch.randint(0, V, (R,), generator=g(2)).int()
+        w = torch.randn(A_, D, generator=g(3))
+        bias = torch.randn(A_, generator=g(4))
+        want = torch.tanh(table[rows.long()].double() @ w.double().T + bias.double()).float()
+        d = torch.randn(R, A_, generator=g(5))
+        want_dw = (d.double().T @ table[rows.long()].double()).float()
+        with K.precision(prec):
+            got = K.gemm(cu(table), cu(w), trans_b=True, bias=cu(bias), act=K.ACT_TANH, a_rows=cu(rows))
+            assert_close(got, want, tol, 'gathered forward')
+            got_dw = K.gemm(cu(d), cu(table), trans_a=True, b_rows=cu(rows))
+            assert_close(got_dw, want_dw, tol, 'gathered weight gradient')

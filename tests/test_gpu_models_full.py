@@ -44,9 +44,12 @@ def oracle_forward(name, P, batch, cfg):
     return O.npa_forward(P, batch), None
 
 
+@pytest.mark.parametrize('prec', ['fp32', 'tf32x3'])
 @pytest.mark.parametrize('S,H', [(30, 50), (50, 25)])
 @pytest.mark.parametrize('name', list(MODELS))
-def test_index_path_matches_oracle(name, S, H):
+def test_index_path_matches_oracle(name, S, H, prec, monkeypatch):
+    from xnrs_b200 import kernels as K
+    monkeypatch.setattr(K, '_precision', K.PRECISIONS[prec])
     cfg = dict(BASE, **MODELS[name], seq_len=S, hist_len=H, st_hist_len=H)
     B = 5
     cat = syn.make_catalogue(N_NEWS, S, VOCAB, 768, seed=3, with_abstract=(name == 'naml'))
@@ -77,7 +80,8 @@ def test_index_path_matches_oracle(name, S, H):
             want_scores, dense['targets'], want_u, dense['main_theme'].long(), cfg['contrastive_temperature'],
             cfg['contrastive_lambda'])
         assert_close(l_cl, want_cl, 1e-4, 'InfoNCE')
-    assert_close(preds, torch.relu(want_scores), 1e-4, 'relu(scores)')
+    # relative to the scale of the raw scores (after the ReLU the surviving values can be arbitrarily small)
+    assert_close(preds, torch.relu(want_scores), 1e-4, 'relu(scores)', atol=1e-4 * float(want_scores.abs().max()))
     assert_close(total, want_total, 1e-4, 'loss')
     total.backward()
     want_total.backward()

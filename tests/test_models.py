@@ -18,11 +18,14 @@ from xnrs_b200.training import BCELogitsRankingTrainer, ContrastiveRankingTraine
 TOL = 1e-4          # north-star fp32 tolerance (relative to the tensor's scale)
 
 
-@pytest.fixture(params=['emulated', pytest.param('cuda', marks=pytest.mark.gpu)])
+@pytest.fixture(params=['emulated', pytest.param('cuda', marks=pytest.mark.gpu),
+                        pytest.param('cuda-tf32x3', marks=pytest.mark.gpu)])
 def device(request, monkeypatch):
+    """'cuda' = exact-fp32 SIMT GEMMs; 'cuda-tf32x3' = the tcgen05 3xTF32 tensor-core GEMMs (same 1e-4 bar)"""
     if request.param == 'emulated':
         monkeypatch.setattr(K, 'call', EMU.call)
         return 'cpu'
+    monkeypatch.setattr(K, '_precision', K.PRECISIONS['tf32x3' if request.param.endswith('tf32x3') else 'fp32'])
     return 'cuda'
 
 

@@ -1,7 +1,498 @@
-// tcgen05 (5th-gen tensor core) GEMM path.  Placeholder dispatcher until the TMA/TMEM kernel lands:
-// reports "not taken" so xnrs_gemm falls through to the exact-fp32 SIMT kernel (still CUDA, never CPU).
+// tcgen05 (5th-gen tensor core) GEMM for sm_100a: TMA-fed, TMEM accumulators, warp-specialised, persistent.
+//
+//   C[M,N] (=|+=) act( opA(A)[M,K] * opB(B)[K,N] + bias )     A, B, C fp32 in global memory
+//
+// Arithmetic modes (include/xnrs_b200.h XNRS_PREC_*):
+//   TF32X3  fp32-accurate: every fp32 operand tile is split IN SHARED MEMORY into hi = rna_tf32(x) and
+//           lo = x - hi by dedicated splitter warps, and the issuer runs 3 MMAs per k-step
+//           (hi*hi + lo*hi + hi*lo; the dropped lo*lo term is ~2^-22 relative).  L2 traffic stays 1x.
+//   TF32    single pass on the raw fp32 tiles (tensor core reads the top 19 bits).
+//
+// CTA = 3 warpgroups: {warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc)} | warps 4-7 splitters | warps 8-11
+// epilogue; setmaxnreg moves registers from the first two warpgroups to the epilogue (a full 128-column row per thread)
+// Tile 128 x 128 x 32 (UMMA M=128, N=128, K=8 per instruction, 128-byte swizzled rows), 3 (x3) or 6 (x1)
+// smem stages, 2 TMEM accumulator stages (x2 accumulators: main + correction = all 512 columns) so the epilogue of
+// tile i overlaps the main loop of tile i+1.
+// Both operand majors are supported through the UMMA descriptors (K-major: nn.Linear forward;
+// MN-major: weight-gradient and input-gradient GEMMs), so no transposed copies are ever made.
+#include <cuda.h>
+
 #include "gemm.cuh"
 
 namespace xnrs {
-int gemm_tensorcore(const GemmArgs &, int, cudaStream_t, int *) { return 0; }
+
+constexpr int TBM = 128, TBN = 128, TBK = 32;
+constexpr int TILE_BYTES = TBM * TBK * 4;             // 16 KB per operand tile
+constexpr int SMEM_DATA = 192 * 1024;
+constexpr int TC_THREADS = 384;          // 3 warpgroups: {TMA, MMA, -, -} | 4 splitter warps | 4 epilogue warps
+constexpr int ACC_STAGES = 2;
+constexpr int MAX_STAGES = 6;
+constexpr long long KCHUNK = 2048;   // longest K run accumulated inside the tensor core: its fp32 accumulation truncates, so the
+                                     // error grows ~linearly with K; longer reductions are split and summed with IEEE fp32 atomics
+
+struct TcArgs {
+    long long M, N, K;
+    float *C; long long ldc;
+    const float *bias; int act; const float *aux; int accumulate;
+    int split_k; long long k_per_split;
+    int a_mn, b_mn;         // 1: operand stored [K, MN] (MN contiguous); 0: stored [MN, K] (K contiguous)
+    const int *a_gather;    // K-major A: stored rows gathered through this index (table gather fused by TMA gather4)
+    const int *b_gather;    // MN-major B: stored rows (= K index) gathered through this index
+    int passes;             // 3 (TF32X3) or 1 (TF32)
+    int stages;
+    long long tiles_m, tiles_n;
+};
+
+// ---- PTX wrappers --------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug traps (CUDA error) after ~2 s instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    if (mbar_try(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+// Blackwell TMA gather: four independent rows (same column window) land as four consecutive smem rows
+__device__ __forceinline__ void tma_gather4(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int4 rows) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(rows.x), "r"(rows.y), "r"(rows.z), "r"(rows.w)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t *r = reinterpret_cast<uint32_t *>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64))
+// MN-major 32-bit (tf32) operands must use the 32-byte-atom variant SWIZZLE_128B_BASE32B=1 (Swizzle<2,5,2>, 4 k-rows
+// per 512-byte atom) — "for mn-major tf32 operands, SW128_32B is the only available smem layout" (CUTLASS sm100 builder).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | ((uint64_t)layout << 61);
+}
+
+struct StageRing {
+    int stage = 0;
+    uint32_t phase = 0;
+    __device__ __forceinline__ void advance(int n) {
+        if (++stage == n) { stage = 0; phase ^= 1; }
+    }
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcArgs p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], split_bar[MAX_STAGES], empty_bar[MAX_STAGES];
+    __shared__ __align__(8) uint64_t tfull_bar[ACC_STAGES], tempty_bar[ACC_STAGES];
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int stages = p.stages, passes = p.passes;
+    const int stage_bytes = (passes == 3 ? 4 : 2) * TILE_BYTES;
+    auto tileA = [&](int s) { return smem + (size_t)s * stage_bytes; };
+    auto tileB = [&](int s) { return smem + (size_t)s * stage_bytes + TILE_BYTES; };
+    auto tileAlo = [&](int s) { return smem + (size_t)s * stage_bytes + 2 * TILE_BYTES; };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&split_bar[s], 128);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < ACC_STAGES; ++a) {
+            mbar_init(&tfull_bar[a], 1);
+            mbar_init(&tempty_bar[a], 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {        // TMEM: 2 accumulator stages x 128 fp32 columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
+                     "r"(ACC_STAGES * 2 * TBN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    const long long tiles_mn = p.tiles_m * p.tiles_n;
+    const long long total = tiles_mn * p.split_k;
+
+    if (warp == 0) {
+        // ===================== TMA producer (lane 0 drives; all 32 lanes issue the gather4 rows) =====================
+        StageRing r;
+        for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+            const long long split = t / tiles_mn, mn = t - split * tiles_mn;
+            const int m0 = (int)((mn / p.tiles_n) * TBM), n0 = (int)((mn % p.tiles_n) * TBN);
+            const long long kbeg = split * p.k_per_split, kend = min(p.K, kbeg + p.k_per_split);
+            int4 arow = make_int4(0, 0, 0, 0);
+            if (p.a_gather) {       // rows m0+4*lane .. +3 of this tile, fixed for the whole K loop; rows past M re-read
+                const long long m = m0 + 4 * lane, last = p.M - 1;      // the last valid row (their results are dropped)
+                arow.x = p.a_gather[min(m, last)];
+                arow.y = p.a_gather[min(m + 1, last)];
+                arow.z = p.a_gather[min(m + 2, last)];
+                arow.w = p.a_gather[min(m + 3, last)];
+            }
+            for (long long k0 = kbeg; k0 < kend; k0 += TBK) {
+                if (lane == 0) {
+                    mbar_wait(&empty_bar[r.stage], r.phase ^ 1);
+                    mbar_expect_tx(&full_bar[r.stage], 2 * TILE_BYTES);
+                }
+                __syncwarp();
+                if (p.a_gather) {
+                    tma_gather4(tileA(r.stage) + lane * 512, &mapA, &full_bar[r.stage], (int)k0, arow);
+                } else if (lane == 0) {
+                    if (!p.a_mn) {
+                        tma_load_2d(tileA(r.stage), &mapA, &full_bar[r.stage], (int)k0, m0);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            tma_load_2d(tileA(r.stage) + c * 4096, &mapA, &full_bar[r.stage], m0 + 32 * c, (int)k0);
+                    }
+                }
+                if (p.b_gather) {   // chunk c = lane/8 (32 N-columns), k-rows k0+4j .. +3 with j = lane%8
+                    const int c = lane >> 3, j = lane & 7;
+                    const long long k = k0 + 4 * j;
+                    // rows past K re-read the last valid row: the A tile is zero-filled there, so they contribute 0
+                    const long long last = p.K - 1;
+                    int4 brow;
+                    brow.x = p.b_gather[min(k, last)];
+                    brow.y = p.b_gather[min(k + 1, last)];
+                    brow.z = p.b_gather[min(k + 2, last)];
+                    brow.w = p.b_gather[min(k + 3, last)];
+                    tma_gather4(tileB(r.stage) + c * 4096 + j * 512, &mapB, &full_bar[r.stage], n0 + 32 * c, brow);
+                } else if (lane == 0) {
+                    if (!p.b_mn) {
+                        tma_load_2d(tileB(r.stage), &mapB, &full_bar[r.stage], (int)k0, n0);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            tma_load_2d(tileB(r.stage) + c * 4096, &mapB, &full_bar[r.stage], n0 + 32 * c, (int)k0);
+                    }
+                }
+                r.advance(stages);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A/B=TF32 [7,10)=[10,13)=2,
+            // a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29)
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
+                                   ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+            const uint32_t a_lbo = p.a_mn ? 4096 : 16, b_lbo = p.b_mn ? 4096 : 16;
+            const uint32_t a_kadv = p.a_mn ? 1024 : 32, b_kadv = p.b_mn ? 1024 : 32;   // bytes per K=8 step
+            const uint32_t a_sbo = p.a_mn ? 512 : 1024, b_sbo = p.b_mn ? 512 : 1024;   // 4- vs 8-row swizzle atoms
+            const uint32_t a_lay = p.a_mn ? 1 : 2, b_lay = p.b_mn ? 1 : 2;
+            StageRing r, acc;
+            for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+                const long long split = t / tiles_mn;
+                const long long kbeg = split * p.k_per_split, kend = min(p.K, kbeg + p.k_per_split);
+                mbar_wait(&tempty_bar[acc.stage], acc.phase ^ 1);
+                tc_fence_after();
+                // two accumulators per tile: hi*hi in the first, the 2^-11-smaller correction terms in the second.  The
+                // tensor core truncates on every accumulate, so keeping the main sum at one add per k-step (instead of
+                // three) cuts the rounding error 3x; the epilogue adds the two with one IEEE fp32 add.
+                const uint32_t d_tmem = tmem_base + acc.stage * 2 * TBN, d_corr = d_tmem + TBN;
+                uint32_t first = 1;
+                for (long long k0 = kbeg; k0 < kend; k0 += TBK) {
+                    mbar_wait(passes == 3 ? &split_bar[r.stage] : &full_bar[r.stage], r.phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(tileA(r.stage)), sb = smem_u32(tileB(r.stage));
+#pragma unroll
+                    for (int k = 0; k < TBK / 8; ++k) {
+                        const uint64_t da = umma_desc(sa + k * a_kadv, a_lbo, a_sbo, a_lay);
+                        const uint64_t db = umma_desc(sb + k * b_kadv, b_lbo, b_sbo, b_lay);
+                        tc_mma_tf32(d_tmem, da, db, idesc, first ? 0u : 1u);
+                        if (passes == 3) {
+                            const uint64_t dal = umma_desc(sa + 2 * TILE_BYTES + k * a_kadv, a_lbo, a_sbo, a_lay);
+                            const uint64_t dbl = umma_desc(sb + 2 * TILE_BYTES + k * b_kadv, b_lbo, b_sbo, b_lay);
+                            tc_mma_tf32(d_corr, dal, db, idesc, first ? 0u : 1u);
+                            tc_mma_tf32(d_corr, da, dbl, idesc, 1u);
+                        }
+                        first = 0;
+                    }
+                    tc_commit(&empty_bar[r.stage]);          // frees the smem stage when the MMAs retire
+                    r.advance(stages);
+                }
+                tc_commit(&tfull_bar[acc.stage]);             // accumulator ready for the epilogue
+                acc.advance(ACC_STAGES);
+            }
+        }
+    } else if (warp < 4) {
+        // idle warps of warpgroup 0
+    } else if (warp < 8) {
+        // ===================== splitters: hi = rna_tf32(x), lo = x - hi, in place in shared memory ================
+        if (passes == 3) {
+            const int tid = threadIdx.x - 128;         // 0..127
+            StageRing r;
+            for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+                const long long split = t / tiles_mn;
+                const long long kbeg = split * p.k_per_split, kend = min(p.K, kbeg + p.k_per_split);
+                for (long long k0 = kbeg; k0 < kend; k0 += TBK) {
+                    mbar_wait(&full_bar[r.stage], r.phase);
+                    float4 *hi = reinterpret_cast<float4 *>(tileA(r.stage));      // A and B tiles are contiguous
+                    float4 *lo = reinterpret_cast<float4 *>(tileAlo(r.stage));
+#pragma unroll 4
+                    for (int i = tid; i < 2 * TILE_BYTES / 16; i += 128) {
+                        float4 v = hi[i], h, l;
+                        uint32_t t0, t1, t2, t3;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t0) : "f"(v.x));
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t1) : "f"(v.y));
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t2) : "f"(v.z));
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t3) : "f"(v.w));
+                        h = make_float4(__uint_as_float(t0), __uint_as_float(t1), __uint_as_float(t2), __uint_as_float(t3));
+                        l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                        hi[i] = h;
+                        lo[i] = l;
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (MMA)
+                    mbar_arrive(&split_bar[r.stage]);
+                    r.advance(stages);
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue: TMEM -> registers -> bias/act -> global =====================
+        const int q = warp & 3;                         // TMEM lane quarter this warp may access
+        const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+        StageRing acc;
+        for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+            const long long split = t / tiles_mn, mn = t - split * tiles_mn;
+            const long long m0 = (mn / p.tiles_n) * TBM, n0 = (mn % p.tiles_n) * TBN;
+            const long long row = m0 + 32 * q + lane;
+            mbar_wait(&tfull_bar[acc.stage], acc.phase);
+            tc_fence_after();
+            float *crow = p.C + row * p.ldc;
+            const float *arow = p.aux ? p.aux + row * p.ldc : nullptr;
+#pragma unroll 1
+            for (int c = 0; c < TBN / 32; ++c) {
+                float r[32];
+                const uint32_t taddr = tmem_base + acc.stage * 2 * TBN + c * 32 + ((uint32_t)(32 * q) << 16);
+                tc_ld32(taddr, r);
+                if (passes == 3) {
+                    float corr[32];
+                    tc_ld32(taddr + TBN, corr);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] += corr[j];
+                }
+                if (row >= p.M) continue;
+#pragma unroll
+                for (int j0 = 0; j0 < 32; j0 += 4) {
+                    const long long col = n0 + c * 32 + j0;
+                    if (col >= p.N) break;
+                    float x[4] = {r[j0], r[j0 + 1], r[j0 + 2], r[j0 + 3]};
+                    const int nv = (int)min((long long)4, p.N - col);
+                    if (p.split_k > 1) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            if (e < nv) {
+                                if (split == 0 && p.bias) x[e] += p.bias[col + e];
+                                atomicAdd(crow + col + e, x[e]);
+                            }
+                        }
+                        continue;
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        if (e < nv) {
+                            if (p.bias) x[e] += p.bias[col + e];
+                            if (p.act == XNRS_ACT_RELU) x[e] = fmaxf(x[e], 0.f);
+                            else if (p.act == XNRS_ACT_TANH) x[e] = tanhf(x[e]);
+                            else if (p.act == XNRS_ACT_RELU_MASK) x[e] = (arow[col + e] > 0.f) ? x[e] : 0.f;
+                        }
+                    }
+                    if (vec_ok && nv == 4) {
+                        float4 *dst = reinterpret_cast<float4 *>(crow + col);
+                        if (p.accumulate) {
+                            const float4 o = *dst;
+                            x[0] += o.x; x[1] += o.y; x[2] += o.z; x[3] += o.w;
+                        }
+                        *dst = make_float4(x[0], x[1], x[2], x[3]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (e < nv) crow[col + e] = p.accumulate ? crow[col + e] + x[e] : x[e];
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[acc.stage]);
+            acc.advance(ACC_STAGES);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ACC_STAGES * 2 * TBN));
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D fp32 tensor map: inner (contiguous) extent `inner`, `outer` rows of stride ld floats, box {32, box_outer}
+static bool make_map(CUtensorMap *map, const float *base, long long inner, long long outer, long long ld, int box_outer,
+                     bool mn_major) {
+    if (outer <= 0) outer = 1;
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint32_t box[2] = {32, (cuuint32_t)box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int gemm_tensorcore(const GemmArgs &a, int precision, cudaStream_t st, int *status) {
+    // shapes / layouts the TMA path cannot take fall through to the exact-fp32 SIMT kernel
+    if (a.a_rows && a.transA) return 0;          // gather is fused for K-major A (forward) ...
+    if (a.b_rows && a.transB) return 0;          // ... and MN-major B (weight gradient); other combinations: SIMT
+    if (a.M < 128 || a.N < 32 || a.K < 32) return 0;
+    if (a.lda % 4 || a.ldb % 4) return 0;
+    if (((uintptr_t)a.A & 15) || ((uintptr_t)a.B & 15)) return 0;
+    if (a.M > 2000000000LL || a.N > 2000000000LL || a.K > 2000000000LL) return 0;
+    static int is_sm100 = -1;
+    if (is_sm100 < 0) is_sm100 = xnrs_device_is_sm100();
+    if (!is_sm100) return 0;
+
+    TcArgs p;
+    p.M = a.M; p.N = a.N; p.K = a.K;
+    p.C = a.C; p.ldc = a.ldc; p.bias = a.bias; p.act = a.act; p.aux = a.aux; p.accumulate = a.accumulate;
+    p.a_mn = a.transA ? 1 : 0;      // transA: A stored [K, M]
+    p.b_mn = a.transB ? 0 : 1;      // transB: B stored [N, K] (K-major); else stored [K, N]
+    p.a_gather = a.a_rows; p.b_gather = a.b_rows;
+    p.passes = (precision == XNRS_PREC_TF32X3) ? 3 : 1;
+    p.stages = p.passes == 3 ? 3 : 6;
+    p.tiles_m = cdiv(a.M, TBM);
+    p.tiles_n = cdiv(a.N, TBN);
+    long long tiles = p.tiles_m * p.tiles_n;
+    int split = a.split_k;
+    if (split <= 0) {
+        long long want = num_sms();
+        long long s = tiles >= want ? 1 : want / tiles;
+        long long maxs = cdiv(a.K, 512);
+        if (s > maxs) s = maxs;
+        if (s < 1) s = 1;
+        if (a.act != XNRS_ACT_NONE) s = 1;
+        split = (int)s;
+    }
+    if (a.act == XNRS_ACT_NONE && cdiv(a.K, split) > KCHUNK) split = (int)cdiv(a.K, KCHUNK);
+    if (split > 1 && a.act != XNRS_ACT_NONE) {
+        *status = fail(XNRS_ERR_ARG, "%s: split_k with activation", "xnrs_gemm");
+        return 1;
+    }
+    p.split_k = split;
+    p.k_per_split = cdiv(cdiv(a.K, split), TBK) * TBK;
+
+    CUtensorMap mapA, mapB;
+    // gathered operands: the map spans the whole table (row count unknown to the GEMM: use the int32 range) and the box
+    // is one row high — tile::gather4 fetches four such rows per instruction
+    const long long table_rows = 0x7fffffffLL;
+    bool ok = p.a_mn ? make_map(&mapA, a.A, a.M, a.K, a.lda, 32, true)
+                     : make_map(&mapA, a.A, a.K, a.a_rows ? table_rows : a.M, a.lda, a.a_rows ? 1 : TBM, false);
+    ok = ok && (p.b_mn ? make_map(&mapB, a.B, a.N, a.b_rows ? table_rows : a.K, a.ldb, a.b_rows ? 1 : 32, true)
+                       : make_map(&mapB, a.B, a.K, a.N, a.ldb, TBN, false));
+    if (!ok) return 0;
+
+    if (split > 1 && !a.accumulate) {
+        if (cudaMemset2DAsync(a.C, a.ldc * sizeof(float), 0, a.N * sizeof(float), a.M, st) != cudaSuccess) {
+            *status = fail(XNRS_ERR_CUDA, "%s: memset2d failed", "xnrs_gemm");
+            return 1;
+        }
+    }
+    static bool attr_set = false;
+    const int smem_bytes = SMEM_DATA + 1024;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) {
+            cudaGetLastError();
+            return 0;
+        }
+        attr_set = true;
+    }
+    long long total = tiles * split;
+    unsigned grid = (unsigned)(total < num_sms() ? total : num_sms());
+    gemm_tc_kernel<<<grid, TC_THREADS, smem_bytes, st>>>(mapA, mapB, p);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        snprintf(g_err, sizeof(g_err), "xnrs_gemm (tcgen05): CUDA error: %s", cudaGetErrorString(e));
+        *status = XNRS_ERR_CUDA;
+        return 1;
+    }
+    *status = XNRS_OK;
+    return 1;
+}
+
 }  // namespace xnrs

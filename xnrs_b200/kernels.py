@@ -192,6 +192,19 @@ def _need(ctx, i):
     return ctx.needs_input_grad[i]
 
 
+GATHER_IN_TMA = bool(int(__import__('os').environ.get('XNRS_TMA_GATHER', '0')))
+
+
+def _resolve_rows(x, rows):
+    """how the fused table gather (row G) reaches the GEMMs.  The exact-fp32 SIMT GEMM gathers rows inside its tile
+    loads.  The tcgen05 GEMM can gather with TMA tile::gather4 (XNRS_TMA_GATHER=1), but 128-byte gather4 rows
+    issue ~4x slower than tiled TMA boxes (measured 92 vs 156 TFLOP/s), so by default the tensor-core modes copy the
+    gathered rows once (one coalesced pass, bit exact) and every consumer of the step reads the dense copy."""
+    if rows is not None and _precision != 0 and not GATHER_IN_TMA:
+        return gather_rows(x, rows), None
+    return x, rows
+
+
 class LinearFn(torch.autograd.Function):
     """y = x W^T + b (nn.Linear), optional fused table gather on x."""
 
@@ -248,6 +261,7 @@ class AdditivePoolFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, rows, mask, w1, b1, w2, b2, R, L):
         F_, A = x.shape[1], w1.shape[0]
+        x, rows = _resolve_rows(x, rows)
         hid = gemm(x, w1, trans_b=True, bias=b1, act=ACT_TANH, a_rows=rows)
         attn = torch.empty((R, L), device=x.device, dtype=torch.float32)
         pooled = torch.empty((R, F_), device=x.device, dtype=torch.float32)
@@ -284,6 +298,7 @@ class PersonalizedPoolFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, x, rows, mask, xw, xb, qw, qb, R, L, rows_per_query):
         F_, A = x.shape[1], xw.shape[0]
+        x, rows = _resolve_rows(x, rows)
         hid = gemm(x, xw, trans_b=True, bias=xb, act=ACT_TANH, a_rows=rows)
         qh = gemm(q, qw, trans_b=True, bias=qb)
         attn = torch.empty((R, L), device=x.device, dtype=torch.float32)
@@ -322,6 +337,7 @@ class MultiHeadAttentionFn(torch.autograd.Function):
     def forward(ctx, x, rows, mask, wq, bq, wk, bk, wv, bv, wo, bo, R, L, n_heads, keep, p_drop, seed):
         D = wq.shape[0]
         dk = D // n_heads
+        x, rows = _resolve_rows(x, rows)
         q = gemm(x, wq, trans_b=True, bias=bq, a_rows=rows)
         k = gemm(x, wk, trans_b=True, bias=bk, a_rows=rows)
         v = gemm(x, wv, trans_b=True, bias=bv, a_rows=rows)

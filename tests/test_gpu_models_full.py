@@ -94,5 +94,6 @@ def test_index_path_matches_oracle(name, S, H, prec, monkeypatch):
     with torch.no_grad():
         dense_scores = model(dense)
         index_scores = model(batch)
-    assert_close(dense_scores, index_scores, 1e-6, 'dense vs index path')
+    # same kernels, different row sets (title dedup changes tile / split-K composition): fp32 summation-order noise only
+    assert_close(dense_scores, index_scores, 1e-5, 'dense vs index path')
     assert_close(index_scores, want_scores, 1e-4, 'scores')

@@ -139,7 +139,14 @@ class TextEncoder(nn.Module):
 
     ``forward`` accepts the reference's dense ``(x[b,n,s,d], m[b,n,s,1])`` pair (tuple or list) or an
     ``IndexedTitles`` (int32 news ids into a device-resident TitleStore); in the indexed case the token
-    rows are gathered inside the kernels and the dense (b,n,s,d) tensor never exists."""
+    rows are gathered inside the kernels and the dense (b,n,s,d) tensor never exists.
+
+    ``dedup_titles``: every title is encoded independently of its batch position (news_encoding.py:48-57), so with
+    ids the encoder runs ONCE per distinct article of the batch and the vectors are gathered back to the (b,n)
+    slots; the backward pass sums the slot gradients per article (scatter-add) before the encoder's backward.
+    Same values and gradients (up to fp32 summation order), ~6x fewer titles on MIND-shaped (Zipf) batches."""
+
+    dedup_titles = True
 
     def __init__(self, pooler: nn.Module, p_dropout: float, out_features: int, in_features: Optional[int] = 768,
                  head: bool = True, activation: nn.Module = nn.ReLU(), att: Optional[nn.Module] = None,
@@ -168,9 +175,17 @@ class TextEncoder(nn.Module):
             ids = inpt.news_ids.to(device)
             b, n = ids.shape
             S = store.seq_len
-            rows, mask = K.expand_titles(store.title_tokens, ids)
             if self.dropout.p > 0 and self.training:
                 raise NotImplementedError('input dropout on gathered titles (every shipped config has p_dropout 0)')
+            if self.dedup_titles and b * n >= 64:
+                uniq, inv = torch.unique(ids.reshape(-1), return_inverse=True)      # id plumbing (one host sync)
+                nu = uniq.numel()
+                rows, mask = K.expand_titles(store.title_tokens, uniq)
+                e_u = self._encode(store.token_table, rows, mask, nu, S)
+                e = K.EmbeddingFn.apply(e_u, inv, None)                            # gather back; bwd = scatter-add
+                cm = K.collapse_mask(mask, nu, S)[inv]
+                return e.view(b, n, self.out_dim), cm.view(b, n, 1)
+            rows, mask = K.expand_titles(store.title_tokens, ids)
             e = self._encode(store.token_table, rows, mask, b * n, S)
         else:
             x, m = inpt

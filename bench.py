@@ -27,11 +27,28 @@ import torch  # noqa: E402
 CL_CFG = dict(model='standard', scoring='dot', text_features=['title_emb'], catg_features=[], title_emb_dim=256,
               total_emb_dim=256, d_backbone=768, p_dropout=0., bias=False, n_negatives=4, lr=1e-4,
               contrastive_temperature=0.08, contrastive_lambda=0.01)          # config/mind_small_CL.yml
+# the other BASELINE.json configs (secondary lines: `--model nrms|naml|lstur|npa`), hyper-parameters from config/mind_small_*.yml
+_COMMON = dict(scoring='dot', title_emb_dim=256, d_backbone=768, p_dropout=0., bias=False, n_negatives=4, lr=1e-4,
+               n_categories=19, n_subcategories=300, n_users=703_789, cat_emb_dim=16, sub_emb_dim=16, n_heads=16,
+               contrastive_temperature=0.08, contrastive_lambda=0.1)
+MODEL_CFGS = {
+    'cl': CL_CFG,
+    'nrms': dict(_COMMON, model='NRMS', text_features=['title_emb'], catg_features=[], total_emb_dim=256),
+    'naml': dict(_COMMON, model='NAML', text_features=['title_emb', 'abstract_emb'], total_emb_dim=256,
+                 catg_features=['category_index', 'subcategory_index']),
+    'lstur': dict(_COMMON, model='LSTUR', text_features=['title_emb'], catg_features=['category_index'], total_emb_dim=272,
+                  long_term_method='embedding', long_short_term_method='con', p_user_dropout=0.07, st_hist_len=50),
+    'npa': dict(_COMMON, model='NPA', text_features=['title_emb'], catg_features=[], total_emb_dim=256, user_emb_dim=64),
+}
 SEQ_LEN, HIST_LEN, N_NEWS, VOCAB = 30, 50, 65_238, 100_000                     # SURVEY §8(d) north-star shapes
 METRIC, UNIT = 'train impressions/s', 'impressions/s'
 
 
-def workload_name(batch):
+def workload_name(batch, model='cl'):
+    if model != 'cl':
+        return (f'{model.upper()} (config/mind_small_{model.upper()}.yml) train step fwd+loss+bwd+Adam; synthetic MIND-shaped: '
+                f'S={SEQ_LEN}, H={HIST_LEN}, 1:4 negatives, D=768, {N_NEWS} news, {VOCAB}-row token table; '
+                f'{batch} impressions/GPU/step')
     return (f'CL bi-encoder (mind_small_CL.yml, model=standard) train step fwd+loss(MSE.ReLU + 0.01*InfoNCE)+bwd+Adam; '
             f'synthetic MIND-shaped: S={SEQ_LEN} tokens, H={HIST_LEN} history, 1:4 negatives, D=768, '
             f'{N_NEWS} news, {VOCAB}-row token table; {batch} impressions/GPU/step')
@@ -248,6 +265,7 @@ def main():
     ap.add_argument('--precision', default='tf32x3', choices=['fp32', 'tf32x3', 'tf32', 'bf16'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--workload', default='train', choices=['train', 'eval'])
+    ap.add_argument('--model', default='cl', choices=list(MODEL_CFGS), help='cl is the headline (BASELINE configs[1])')
     ap.add_argument('--no-dedup', action='store_true', help='encode every (impression, slot) title, not each distinct article once')
     ap.add_argument('--eval-impressions', type=int, default=376_471)
     args = ap.parse_args()
@@ -279,17 +297,21 @@ def main():
     from xnrs_b200.models.components import TextEncoder
     TextEncoder.dedup_titles = not args.no_dedup
 
-    cat = syn.make_catalogue(N_NEWS, SEQ_LEN, VOCAB, 768, seed=0)
+    cfg = MODEL_CFGS[args.model]
+    cat = syn.make_catalogue(N_NEWS, SEQ_LEN, VOCAB, 768, seed=0, with_abstract=(args.model == 'naml'))
     store = TitleStore(cat.token_table.to(dev), cat.title_tokens.to(dev))
+    astore = TitleStore(store.token_table, cat.abstract_tokens.to(dev)) if args.model == 'naml' else None
     torch.manual_seed(0)
-    trainer = ContrastiveRankingTrainer(dict(CL_CFG, device=str(dev)), make_model(CL_CFG))
+    from xnrs_b200.training import MSERankingTrainer
+    trainer_cls = MSERankingTrainer if args.model == 'npa' else ContrastiveRankingTrainer     # NPA has no CL hook
+    trainer = trainer_cls(dict(cfg, device=str(dev)), make_model(cfg))
     trainer.model.train()
     dp = DataParallelTrainer(trainer)
 
     n_batches = 8           # distinct batches cycled through; weak scaling: every rank draws its own B impressions
     raws = [syn.make_train_batch(N_NEWS, B, HIST_LEN, seed=1000 + 97 * rank + i) for i in range(n_batches)]
     pinned = [{k: v.pin_memory() for k, v in r.items()} for r in raws]
-    resident = [syn.index_batch(store, cat, r, dev) for r in raws]
+    resident = [syn.index_batch(store, cat, r, dev, abstract_store=astore) for r in raws]
     h2d_bytes = sum(v.numel() * v.element_size() for v in raws[0].values())
 
     def sync_all():
@@ -366,7 +388,7 @@ def main():
 
     # ---- timed region 2: end to end through the public trainer API with HOST (pinned) index buffers ----
     def e2e_step(i):
-        out = dp.train_step(syn.index_batch(store, cat, pinned[i % n_batches], dev))
+        out = dp.train_step(syn.index_batch(store, cat, pinned[i % n_batches], dev, abstract_store=astore))
         return float(out['loss'])            # device -> host read of the step's loss (4 bytes, synchronises)
 
     e2e_step(0)
@@ -390,7 +412,7 @@ def main():
         'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': {'fp32': 'f32', 'tf32x3': 'f32 (3xTF32)', 'tf32': 'tf32', 'bf16': 'bf16'}[args.precision],
         'data': 'synthetic',
-        'config': {'workload': workload_name(B), 'global_batch': B * world, 'parallelism': f'dp{world}',
+        'config': {'workload': workload_name(B, args.model), 'global_batch': B * world, 'parallelism': f'dp{world}',
                    'l2': 'inputs larger than L2: 307 MB token table, ~5 GB of gathered rows per step, 8 batches cycled',
                    'precision': args.precision, 'final_loss': last,
                    'dedup_titles': not args.no_dedup},
@@ -398,7 +420,7 @@ def main():
                 'note': 'host input = int32 news ids / targets / labels (the index fast path of the drop-in API)'},
         'gpu_launches': launches, 'roofline': roofline, 'clocks': clocks.summary(),
     }
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.model == 'cl':
         threads = os.cpu_count() or 1
         v, per = time_cpu(args.ref_batch, 3, 1, threads)
         out['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',

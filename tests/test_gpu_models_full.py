@@ -97,3 +97,29 @@ def test_index_path_matches_oracle(name, S, H, prec, monkeypatch):
     # same kernels, different row sets (title dedup changes tile / split-K composition): fp32 summation-order noise only
     assert_close(dense_scores, index_scores, 1e-5, 'dense vs index path')
     assert_close(index_scores, want_scores, 1e-4, 'scores')
+
+
+@pytest.mark.parametrize('name', ['cl', 'nrms', 'naml'])
+def test_title_dedup_gives_the_same_loss_and_gradients(name, monkeypatch):
+    """encoding each distinct article of the batch once (default) == encoding every (impression, slot) title"""
+    from xnrs_b200.models.components import TextEncoder
+    cfg = dict(BASE, **MODELS[name], seq_len=30, hist_len=50, st_hist_len=50)
+    cat = syn.make_catalogue(60, 30, VOCAB, 768, seed=3, with_abstract=(name == 'naml'))     # tiny catalogue: many repeats
+    raw = syn.make_train_batch(60, 6, 50, n_users=N_USERS, seed=4)
+    store = TitleStore(cat.token_table.to(DEV), cat.title_tokens.to(DEV))
+    astore = TitleStore(store.token_table, cat.abstract_tokens.to(DEV)) if name == 'naml' else None
+    results = []
+    for dedup in (True, False):
+        monkeypatch.setattr(TextEncoder, 'dedup_titles', dedup)
+        torch.manual_seed(1)
+        model = make_model(cfg)
+        trainer = ContrastiveRankingTrainer(cfg, model)
+        model.eval()
+        trainer.optimizer.zero_grad()
+        total, _, _, preds = trainer.losses(syn.index_batch(store, cat, raw, DEV, abstract_store=astore))
+        total.backward()
+        results.append((total.detach().clone(), preds.detach().clone(), trainer.optimizer.flat_g.clone()))
+    (l0, p0, g0), (l1, p1, g1) = results
+    assert_close(l0, l1, 1e-6, 'loss')
+    assert_close(p0, p1, 1e-5, 'predictions', atol=1e-6)
+    assert_close(g0, g1, 1e-5, 'flat gradient')

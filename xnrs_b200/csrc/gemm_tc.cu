@@ -17,15 +17,15 @@
 // MN-major: weight-gradient and input-gradient GEMMs), so no transposed copies are ever made.
 #include <cuda.h>
 
+#define XNRS_SPLIT_TRUNC 1
+
 #include "gemm.cuh"
 
 namespace xnrs {
 
-constexpr int TBM = 128, TBN = 128, TBK = 32;
-constexpr int TILE_BYTES = TBM * TBK * 4;             // 16 KB per operand tile
+constexpr int TBM = 128, TBK = 32;
 constexpr int SMEM_DATA = 192 * 1024;
 constexpr int TC_THREADS = 384;          // 3 warpgroups: {TMA, MMA, -, -} | 4 splitter warps | 4 epilogue warps
-constexpr int ACC_STAGES = 2;
 constexpr int MAX_STAGES = 6;
 constexpr long long KCHUNK = 2048;   // longest K run accumulated inside the tensor core: its fp32 accumulation truncates, so the
                                      // error grows ~linearly with K; longer reductions are split and summed with IEEE fp32 atomics
@@ -128,20 +128,25 @@ struct StageRing {
     }
 };
 
+// BN = 128 or 256 output columns per tile.  With SS-mode MMAs the operand fetch (A 4 KB + B BN*32 B per K=8 step) runs at
+// the full 128 B/clk shared-memory bandwidth for BN=128; BN=256 halves the A bytes per FLOP (ncu: L1/shared was the bound).
+template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcArgs p) {
+    constexpr int TILE_A = TBM * TBK * 4, TILE_B = BN * TBK * 4, HALF = TILE_A + TILE_B;   // [A hi][B hi] | [A lo][B lo]
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], split_bar[MAX_STAGES], empty_bar[MAX_STAGES];
-    __shared__ __align__(8) uint64_t tfull_bar[ACC_STAGES], tempty_bar[ACC_STAGES];
+    __shared__ __align__(8) uint64_t tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_smem;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int stages = p.stages, passes = p.passes;
-    const int stage_bytes = (passes == 3 ? 4 : 2) * TILE_BYTES;
+    const int stage_bytes = (passes == 3 ? 2 : 1) * HALF;
+    const int acc_cols = (passes == 3 ? 2 : 1) * BN;         // main (+ correction) accumulator columns per tile
+    const int acc_stages = 512 / acc_cols >= 2 ? 2 : 1;      // TMEM has 512 columns
     auto tileA = [&](int s) { return smem + (size_t)s * stage_bytes; };
-    auto tileB = [&](int s) { return smem + (size_t)s * stage_bytes + TILE_BYTES; };
-    auto tileAlo = [&](int s) { return smem + (size_t)s * stage_bytes + 2 * TILE_BYTES; };
+    auto tileB = [&](int s) { return smem + (size_t)s * stage_bytes + TILE_A; };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
@@ -149,15 +154,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             mbar_init(&split_bar[s], 128);
             mbar_init(&empty_bar[s], 1);
         }
-        for (int a = 0; a < ACC_STAGES; ++a) {
+        for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
             mbar_init(&tempty_bar[a], 128);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {        // TMEM: 2 accumulator stages x 128 fp32 columns
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
-                     "r"(ACC_STAGES * 2 * TBN));
+    if (warp == 1) {        // all 512 TMEM columns (1 CTA per SM)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     tc_fence_before();
@@ -173,7 +177,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         StageRing r;
         for (long long t = blockIdx.x; t < total; t += gridDim.x) {
             const long long split = t / tiles_mn, mn = t - split * tiles_mn;
-            const int m0 = (int)((mn / p.tiles_n) * TBM), n0 = (int)((mn % p.tiles_n) * TBN);
+            const int m0 = (int)((mn / p.tiles_n) * TBM), n0 = (int)((mn % p.tiles_n) * BN);
             const long long kbeg = split * p.k_per_split, kend = min(p.K, kbeg + p.k_per_split);
             int4 arow = make_int4(0, 0, 0, 0);
             if (p.a_gather) {       // rows m0+4*lane .. +3 of this tile, fixed for the whole K loop; rows past M re-read
@@ -186,7 +190,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             for (long long k0 = kbeg; k0 < kend; k0 += TBK) {
                 if (lane == 0) {
                     mbar_wait(&empty_bar[r.stage], r.phase ^ 1);
-                    mbar_expect_tx(&full_bar[r.stage], 2 * TILE_BYTES);
+                    mbar_expect_tx(&full_bar[r.stage], HALF);
                 }
                 __syncwarp();
                 if (p.a_gather) {
@@ -200,23 +204,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                             tma_load_2d(tileA(r.stage) + c * 4096, &mapA, &full_bar[r.stage], m0 + 32 * c, (int)k0);
                     }
                 }
-                if (p.b_gather) {   // chunk c = lane/8 (32 N-columns), k-rows k0+4j .. +3 with j = lane%8
-                    const int c = lane >> 3, j = lane & 7;
-                    const long long k = k0 + 4 * j;
+                if (p.b_gather) {   // chunk c (32 N-columns) x k-row group j: k-rows k0+4j .. +3
+                    const int j = lane & 7;
+                    const long long k = k0 + 4 * j, last = p.K - 1;
                     // rows past K re-read the last valid row: the A tile is zero-filled there, so they contribute 0
-                    const long long last = p.K - 1;
                     int4 brow;
                     brow.x = p.b_gather[min(k, last)];
                     brow.y = p.b_gather[min(k + 1, last)];
                     brow.z = p.b_gather[min(k + 2, last)];
                     brow.w = p.b_gather[min(k + 3, last)];
-                    tma_gather4(tileB(r.stage) + c * 4096 + j * 512, &mapB, &full_bar[r.stage], n0 + 32 * c, brow);
+#pragma unroll
+                    for (int c = lane >> 3; c < BN / 32; c += 4)
+                        tma_gather4(tileB(r.stage) + c * 4096 + j * 512, &mapB, &full_bar[r.stage], n0 + 32 * c, brow);
                 } else if (lane == 0) {
                     if (!p.b_mn) {
                         tma_load_2d(tileB(r.stage), &mapB, &full_bar[r.stage], (int)k0, n0);
                     } else {
 #pragma unroll
-                        for (int c = 0; c < 4; ++c)
+                        for (int c = 0; c < BN / 32; ++c)
                             tma_load_2d(tileB(r.stage) + c * 4096, &mapB, &full_bar[r.stage], n0 + 32 * c, (int)k0);
                     }
                 }
@@ -229,7 +234,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A/B=TF32 [7,10)=[10,13)=2,
             // a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29)
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
-                                   ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+                                   ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
             const uint32_t a_lbo = p.a_mn ? 4096 : 16, b_lbo = p.b_mn ? 4096 : 16;
             const uint32_t a_kadv = p.a_mn ? 1024 : 32, b_kadv = p.b_mn ? 1024 : 32;   // bytes per K=8 step
             const uint32_t a_sbo = p.a_mn ? 512 : 1024, b_sbo = p.b_mn ? 512 : 1024;   // 4- vs 8-row swizzle atoms
@@ -243,7 +248,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 // two accumulators per tile: hi*hi in the first, the 2^-11-smaller correction terms in the second.  The
                 // tensor core truncates on every accumulate, so keeping the main sum at one add per k-step (instead of
                 // three) cuts the rounding error 3x; the epilogue adds the two with one IEEE fp32 add.
-                const uint32_t d_tmem = tmem_base + acc.stage * 2 * TBN, d_corr = d_tmem + TBN;
+                const uint32_t d_tmem = tmem_base + acc.stage * acc_cols, d_corr = d_tmem + BN;
                 uint32_t first = 1;
                 for (long long k0 = kbeg; k0 < kend; k0 += TBK) {
                     mbar_wait(passes == 3 ? &split_bar[r.stage] : &full_bar[r.stage], r.phase);
@@ -255,8 +260,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         const uint64_t db = umma_desc(sb + k * b_kadv, b_lbo, b_sbo, b_lay);
                         tc_mma_tf32(d_tmem, da, db, idesc, first ? 0u : 1u);
                         if (passes == 3) {
-                            const uint64_t dal = umma_desc(sa + 2 * TILE_BYTES + k * a_kadv, a_lbo, a_sbo, a_lay);
-                            const uint64_t dbl = umma_desc(sb + 2 * TILE_BYTES + k * b_kadv, b_lbo, b_sbo, b_lay);
+                            const uint64_t dal = umma_desc(sa + HALF + k * a_kadv, a_lbo, a_sbo, a_lay);
+                            const uint64_t dbl = umma_desc(sb + HALF + k * b_kadv, b_lbo, b_sbo, b_lay);
                             tc_mma_tf32(d_corr, dal, db, idesc, first ? 0u : 1u);
                             tc_mma_tf32(d_corr, da, dbl, idesc, 1u);
                         }
@@ -266,13 +271,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     r.advance(stages);
                 }
                 tc_commit(&tfull_bar[acc.stage]);             // accumulator ready for the epilogue
-                acc.advance(ACC_STAGES);
+                acc.advance(acc_stages);
             }
         }
     } else if (warp < 4) {
         // idle warps of warpgroup 0
     } else if (warp < 8) {
-        // ===================== splitters: hi = rna_tf32(x), lo = x - hi, in place in shared memory ================
+        // ===================== splitters: lo = x - hi for every element of the stage, in shared memory ================
+        // XNRS_SPLIT_TRUNC: hi is what the tensor core itself reads from the raw fp32 word (the top 19 bits), so only lo is
+        // written (one shared-memory store less per element); otherwise hi = rna_tf32(x) is written back as well
         if (passes == 3) {
             const int tid = threadIdx.x - 128;         // 0..127
             StageRing r;
@@ -282,18 +289,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 for (long long k0 = kbeg; k0 < kend; k0 += TBK) {
                     mbar_wait(&full_bar[r.stage], r.phase);
                     float4 *hi = reinterpret_cast<float4 *>(tileA(r.stage));      // A and B tiles are contiguous
-                    float4 *lo = reinterpret_cast<float4 *>(tileAlo(r.stage));
+                    float4 *lo = reinterpret_cast<float4 *>(tileA(r.stage) + HALF);
 #pragma unroll 4
-                    for (int i = tid; i < 2 * TILE_BYTES / 16; i += 128) {
+                    for (int i = tid; i < HALF / 16; i += 128) {
                         float4 v = hi[i], h, l;
+#ifdef XNRS_SPLIT_TRUNC
+                        h = make_float4(__uint_as_float(__float_as_uint(v.x) & 0xffffe000u), __uint_as_float(__float_as_uint(v.y) & 0xffffe000u),
+                                        __uint_as_float(__float_as_uint(v.z) & 0xffffe000u), __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
+#else
                         uint32_t t0, t1, t2, t3;
                         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t0) : "f"(v.x));
                         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t1) : "f"(v.y));
                         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t2) : "f"(v.z));
                         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t3) : "f"(v.w));
                         h = make_float4(__uint_as_float(t0), __uint_as_float(t1), __uint_as_float(t2), __uint_as_float(t3));
-                        l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
                         hi[i] = h;
+#endif
+                        l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
                         lo[i] = l;
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (MMA)
@@ -309,20 +321,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         StageRing acc;
         for (long long t = blockIdx.x; t < total; t += gridDim.x) {
             const long long split = t / tiles_mn, mn = t - split * tiles_mn;
-            const long long m0 = (mn / p.tiles_n) * TBM, n0 = (mn % p.tiles_n) * TBN;
+            const long long m0 = (mn / p.tiles_n) * TBM, n0 = (mn % p.tiles_n) * BN;
             const long long row = m0 + 32 * q + lane;
             mbar_wait(&tfull_bar[acc.stage], acc.phase);
             tc_fence_after();
             float *crow = p.C + row * p.ldc;
             const float *arow = p.aux ? p.aux + row * p.ldc : nullptr;
 #pragma unroll 1
-            for (int c = 0; c < TBN / 32; ++c) {
+            for (int c = 0; c < BN / 32; ++c) {
                 float r[32];
-                const uint32_t taddr = tmem_base + acc.stage * 2 * TBN + c * 32 + ((uint32_t)(32 * q) << 16);
+                const uint32_t taddr = tmem_base + acc.stage * acc_cols + c * 32 + ((uint32_t)(32 * q) << 16);
                 tc_ld32(taddr, r);
                 if (passes == 3) {
                     float corr[32];
-                    tc_ld32(taddr + TBN, corr);
+                    tc_ld32(taddr + BN, corr);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) r[j] += corr[j];
                 }
@@ -368,7 +380,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             }
             tc_fence_before();
             mbar_arrive(&tempty_bar[acc.stage]);
-            acc.advance(ACC_STAGES);
+            acc.advance(acc_stages);
         }
     }
 
@@ -376,7 +388,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ACC_STAGES * 2 * TBN));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
 }
 
@@ -434,9 +446,14 @@ int gemm_tensorcore(const GemmArgs &a, int precision, cudaStream_t st, int *stat
     p.b_mn = a.transB ? 0 : 1;      // transB: B stored [N, K] (K-major); else stored [K, N]
     p.a_gather = a.a_rows; p.b_gather = a.b_rows;
     p.passes = (precision == XNRS_PREC_TF32X3) ? 3 : 1;
-    p.stages = p.passes == 3 ? 3 : 6;
+    // 3xTF32 keeps BN=128: its stage is 2x larger (hi+lo), and 3 smem stages + 2 TMEM stages beat the wider tile
+    // (measured: 156 vs 142 TFLOP/s); single-pass TF32 takes BN=256 (398 vs 340 TFLOP/s)
+    const int BN = (p.passes == 1 && a.N > 128 && cdiv(a.M, TBM) * cdiv(a.N, 256) >= num_sms()) ? 256 : 128;
+    const int half = TBM * TBK * 4 + BN * TBK * 4;
+    p.stages = SMEM_DATA / (half * (p.passes == 3 ? 2 : 1));
+    if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
     p.tiles_m = cdiv(a.M, TBM);
-    p.tiles_n = cdiv(a.N, TBN);
+    p.tiles_n = cdiv(a.N, BN);
     long long tiles = p.tiles_m * p.tiles_n;
     int split = a.split_k;
     if (split <= 0) {
@@ -463,7 +480,7 @@ int gemm_tensorcore(const GemmArgs &a, int precision, cudaStream_t st, int *stat
     bool ok = p.a_mn ? make_map(&mapA, a.A, a.M, a.K, a.lda, 32, true)
                      : make_map(&mapA, a.A, a.K, a.a_rows ? table_rows : a.M, a.lda, a.a_rows ? 1 : TBM, false);
     ok = ok && (p.b_mn ? make_map(&mapB, a.B, a.N, a.b_rows ? table_rows : a.K, a.ldb, a.b_rows ? 1 : 32, true)
-                       : make_map(&mapB, a.B, a.K, a.N, a.ldb, TBN, false));
+                       : make_map(&mapB, a.B, a.K, a.N, a.ldb, BN, false));
     if (!ok) return 0;
 
     if (split > 1 && !a.accumulate) {
@@ -475,7 +492,8 @@ int gemm_tensorcore(const GemmArgs &a, int precision, cudaStream_t st, int *stat
     static bool attr_set = false;
     const int smem_bytes = SMEM_DATA + 1024;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) {
+        if (cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess ||
+            cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) {
             cudaGetLastError();
             return 0;
         }
@@ -483,7 +501,8 @@ int gemm_tensorcore(const GemmArgs &a, int precision, cudaStream_t st, int *stat
     }
     long long total = tiles * split;
     unsigned grid = (unsigned)(total < num_sms() ? total : num_sms());
-    gemm_tc_kernel<<<grid, TC_THREADS, smem_bytes, st>>>(mapA, mapB, p);
+    if (BN == 256) gemm_tc_kernel<256><<<grid, TC_THREADS, smem_bytes, st>>>(mapA, mapB, p);
+    else gemm_tc_kernel<128><<<grid, TC_THREADS, smem_bytes, st>>>(mapA, mapB, p);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {

@@ -16,7 +16,7 @@ def test_header_prototypes_parse():
         assert must in protos
     # every prototype ends with the stream argument (no hidden streams), except the three queries
     for name, (_, args) in protos.items():
-        if name not in ('xnrs_version', 'xnrs_last_error', 'xnrs_launch_count', 'xnrs_device_is_sm100'):
+        if name not in ('xnrs_version', 'xnrs_last_error', 'xnrs_launch_count', 'xnrs_device_is_sm100', 'xnrs_set_option'):
             assert args and args[-1] is ctypes.c_void_p, name
 
 

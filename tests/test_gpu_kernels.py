@@ -455,3 +455,23 @@ def test_tensor_core_gemm_tma_gather(prec, tol):
             assert_close(got, want, tol, 'gathered forward')
             got_dw = K.gemm(cu(d), cu(table), trans_a=True, b_rows=cu(rows))
             assert_close(got_dw, want_dw, tol, 'gathered weight gradient')
+
+
+@pytest.mark.parametrize('prec,tol', [('tf32x3', 5e-5), ('tf32', 3e-3)])
+@pytest.mark.parametrize('ta,tb', [(0, 1), (1, 0), (0, 0), (1, 1)])
+def test_tensor_core_gemm_cta_pair_kernel(prec, tol, ta, tb):
+    """the cta_group::2 (CTA-pair, 256x256 tile) variant of the tcgen05 GEMM — opt-in, kept correct for round 2"""
+    from xnrs_b200 import _lib
+    lib = _lib.lib()
+    assert lib.xnrs_set_option(b'gemm_2cta', 1) == 0
+    try:
+        for M, N, K_ in [(1000, 200, 1332), (4097, 768, 768)]:
+            a = torch.randn((K_, M) if ta else (M, K_), generator=g(1)) / math.sqrt(K_)
+            b = torch.randn((N, K_) if tb else (K_, N), generator=g(2))
+            bias = torch.randn(N, generator=g(3))
+            want = (a.double().T if ta else a.double()) @ (b.double().T if tb else b.double()) + bias.double()
+            with K.precision(prec):
+                got = K.gemm(cu(a), cu(b), trans_a=bool(ta), trans_b=bool(tb), bias=cu(bias), act=K.ACT_RELU)
+            assert_close(got, torch.relu(want).float(), tol, f'2-CTA gemm {prec}')
+    finally:
+        lib.xnrs_set_option(b'gemm_2cta', 0)

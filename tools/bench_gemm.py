@@ -26,12 +26,14 @@ def timeit(fn, n=10):
     return s.elapsed_time(e) / n
 
 
-for name, M, N, Kd, ta, tb in SHAPES:
+ONLY = os.environ.get('SHAPE_IDX')
+PRECS = os.environ.get('PRECS', 'fp32,tf32x3,tf32').split(',')
+for name, M, N, Kd, ta, tb in (SHAPES if ONLY is None else [SHAPES[int(ONLY)]]):
     a = torch.randn((Kd, M) if ta else (M, Kd), device='cuda')
     b = torch.randn((N, Kd) if tb else (Kd, N), device='cuda')
     out = torch.empty(M, N, device='cuda')
     row = {'shape': name}
-    for prec in ('fp32', 'tf32x3', 'tf32'):
+    for prec in PRECS:
         with K.precision(prec):
             ms = timeit(lambda: K.gemm(a, b, trans_a=ta, trans_b=tb, out=out))
         row[prec] = f'{ms:.3f} ms {2.0 * M * N * Kd / ms / 1e9:.1f} TF/s'

@@ -16,6 +16,8 @@
 // Both operand majors are supported through the UMMA descriptors (K-major: nn.Linear forward;
 // MN-major: weight-gradient and input-gradient GEMMs), so no transposed copies are ever made.
 #include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
 
 #define XNRS_SPLIT_TRUNC 1
 
@@ -392,6 +394,299 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
 }
 
+// =====================================================================================================================
+// 2-CTA variant (cta_group::2): a CTA pair on one TPC computes a 256 x 256 tile.  Each CTA stages its own 128 A rows and
+// HALF of B (128 of the 256 N rows); the leader CTA issues UMMA M=256,N=256 that reads both CTAs' shared memory, and each
+// CTA's TMEM receives its 128 rows of D.  Operand bytes fetched from shared memory per FLOP are half of the 1-CTA
+// 128x128 kernel, whose profile showed shared-memory bandwidth as the bound.
+// Barriers: full/empty/tfull are per CTA (empty and tfull are armed by MULTICAST tcgen05.commit from the leader);
+// ready (operands split and visible) and tempty (accumulator drained) live in the LEADER and collect remote arrivals.
+// =====================================================================================================================
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_saddr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_saddr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_cluster(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
+#ifdef XNRS_EXP_CTA_WAIT
+    mbar_wait(bar, parity);
+    asm volatile("fence.acq_rel.cluster;" ::: "memory");
+    return;
+#endif
+    if (mbar_try_cluster(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_cluster(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void tc2_commit_mc(uint64_t *bar) {      // arrive on the same barrier offset in BOTH CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc2_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+
+constexpr int T2N = 256;       // tile columns of the pair
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcArgs p) {
+    constexpr int TILE = TBM * TBK * 4, HALF = 2 * TILE;          // per CTA: [A hi][B-half hi] | [A lo][B-half lo]
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], ready_bar[MAX_STAGES], empty_bar[MAX_STAGES];
+    __shared__ __align__(8) uint64_t tfull_bar[2], tempty_bar[2];
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_rank();
+    const int stages = p.stages, passes = p.passes;
+    const int stage_bytes = (passes == 3 ? 2 : 1) * HALF;
+    const int acc_cols = (passes == 3 ? 2 : 1) * T2N;
+    const int acc_stages = 512 / acc_cols;
+    auto tileA = [&](int s) { return smem + (size_t)s * stage_bytes; };
+    auto tileB = [&](int s) { return smem + (size_t)s * stage_bytes + TILE; };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&ready_bar[s], passes == 3 ? 256 : 2);      // used in the leader only
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull_bar[a], 1);
+            mbar_init(&tempty_bar[a], 256);                        // used in the leader only
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    const long long tiles_mn = p.tiles_m * p.tiles_n;
+    const long long total = tiles_mn * p.split_k;
+    const long long pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+    if (warp == 0) {
+        // ===================== TMA producer: this CTA's 128 A rows and its half of B =====================
+        if (lane == 0) {
+            StageRing r;
+            for (long long t = pair; t < total; t += npairs) {
+                const long long split = t / tiles_mn, mn = t - split * tiles_mn;
+                const int m0 = (int)((mn / p.tiles_n) * 256 + 128 * rank), n0 = (int)((mn % p.tiles_n) * T2N + 128 * rank);
+                const long long kbeg = split * p.k_per_split, kend = min(p.K, kbeg + p.k_per_split);
+                for (long long k0 = kbeg; k0 < kend; k0 += TBK) {
+                    mbar_wait(&empty_bar[r.stage], r.phase ^ 1);
+                    mbar_expect_tx(&full_bar[r.stage], HALF);
+                    if (!p.a_mn) {
+                        tma_load_2d(tileA(r.stage), &mapA, &full_bar[r.stage], (int)k0, m0);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            tma_load_2d(tileA(r.stage) + c * 4096, &mapA, &full_bar[r.stage], m0 + 32 * c, (int)k0);
+                    }
+                    if (!p.b_mn) {
+                        tma_load_2d(tileB(r.stage), &mapB, &full_bar[r.stage], (int)k0, n0);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            tma_load_2d(tileB(r.stage) + c * 4096, &mapB, &full_bar[r.stage], n0 + 32 * c, (int)k0);
+                    }
+                    r.advance(stages);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer: one thread of the LEADER CTA =====================
+        if (rank == 0 && lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
+                                   ((uint32_t)(T2N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+            const uint32_t a_lbo = p.a_mn ? 4096 : 16, b_lbo = p.b_mn ? 4096 : 16;
+            const uint32_t a_kadv = p.a_mn ? 1024 : 32, b_kadv = p.b_mn ? 1024 : 32;
+            const uint32_t a_sbo = p.a_mn ? 512 : 1024, b_sbo = p.b_mn ? 512 : 1024;
+            const uint32_t a_lay = p.a_mn ? 1 : 2, b_lay = p.b_mn ? 1 : 2;
+            StageRing r, acc;
+            for (long long t = pair; t < total; t += npairs) {
+                const long long split = t / tiles_mn;
+                const long long kbeg = split * p.k_per_split, kend = min(p.K, kbeg + p.k_per_split);
+                mbar_wait_cluster(&tempty_bar[acc.stage], acc.phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc.stage * acc_cols, d_corr = d_tmem + T2N;
+                uint32_t first = 1;
+                for (long long k0 = kbeg; k0 < kend; k0 += TBK) {
+                    mbar_wait_cluster(&ready_bar[r.stage], r.phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(tileA(r.stage)), sb = smem_u32(tileB(r.stage));
+#pragma unroll
+                    for (int k = 0; k < TBK / 8; ++k) {
+                        const uint64_t da = umma_desc(sa + k * a_kadv, a_lbo, a_sbo, a_lay);
+                        const uint64_t db = umma_desc(sb + k * b_kadv, b_lbo, b_sbo, b_lay);
+                        tc2_mma_tf32(d_tmem, da, db, idesc, first ? 0u : 1u);
+                        if (passes == 3) {
+                            const uint64_t dal = umma_desc(sa + HALF + k * a_kadv, a_lbo, a_sbo, a_lay);
+                            const uint64_t dbl = umma_desc(sb + HALF + k * b_kadv, b_lbo, b_sbo, b_lay);
+                            tc2_mma_tf32(d_corr, dal, db, idesc, first ? 0u : 1u);
+                            tc2_mma_tf32(d_corr, da, dbl, idesc, 1u);
+                        }
+                        first = 0;
+                    }
+                    tc2_commit_mc(&empty_bar[r.stage]);       // both CTAs' producers may refill this stage
+                    r.advance(stages);
+                }
+                tc2_commit_mc(&tfull_bar[acc.stage]);          // both CTAs' epilogues may read their accumulator half
+                acc.advance(acc_stages);
+            }
+        }
+    } else if (warp == 2) {
+        // ===================== relay (single-pass mode): "my operands have landed" -> leader =====================
+        if (passes != 3 && lane == 0) {
+            StageRing r;
+            for (long long t = pair; t < total; t += npairs) {
+                const long long split = t / tiles_mn;
+                const long long kbeg = split * p.k_per_split, kend = min(p.K, kbeg + p.k_per_split);
+                for (long long k0 = kbeg; k0 < kend; k0 += TBK) {
+                    mbar_wait(&full_bar[r.stage], r.phase);
+                    mbar_arrive_cluster(map_to_cta(smem_u32(&ready_bar[r.stage]), 0));
+                    r.advance(stages);
+                }
+            }
+        }
+    } else if (warp < 4) {
+        // idle
+    } else if (warp < 8) {
+        // ===================== splitters (3xTF32): lo = x - trunc_tf32(x) for this CTA's tiles =====================
+        if (passes == 3) {
+            const int tid = threadIdx.x - 128;
+            StageRing r;
+            for (long long t = pair; t < total; t += npairs) {
+                const long long split = t / tiles_mn;
+                const long long kbeg = split * p.k_per_split, kend = min(p.K, kbeg + p.k_per_split);
+                for (long long k0 = kbeg; k0 < kend; k0 += TBK) {
+                    mbar_wait(&full_bar[r.stage], r.phase);
+                    const float4 *hi = reinterpret_cast<const float4 *>(tileA(r.stage));
+                    float4 *lo = reinterpret_cast<float4 *>(tileA(r.stage) + HALF);
+#pragma unroll 4
+                    for (int i = tid; i < HALF / 16; i += 128) {
+                        const float4 v = hi[i];
+                        lo[i] = make_float4(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u),
+                                            v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u),
+                                            v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u),
+                                            v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_arrive_cluster(map_to_cta(smem_u32(&ready_bar[r.stage]), 0));
+                    r.advance(stages);
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue: this CTA's 128 rows of the pair's tile =====================
+        const int q = warp & 3;
+        const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+        StageRing acc;
+        for (long long t = pair; t < total; t += npairs) {
+            const long long split = t / tiles_mn, mn = t - split * tiles_mn;
+            const long long m0 = (mn / p.tiles_n) * 256 + 128 * rank, n0 = (mn % p.tiles_n) * T2N;
+            const long long row = m0 + 32 * q + lane;
+            mbar_wait(&tfull_bar[acc.stage], acc.phase);
+            tc_fence_after();
+            float *crow = p.C + row * p.ldc;
+            const float *arow = p.aux ? p.aux + row * p.ldc : nullptr;
+#pragma unroll 1
+            for (int c = 0; c < T2N / 32; ++c) {
+                float r[32];
+                const uint32_t taddr = tmem_base + acc.stage * acc_cols + c * 32 + ((uint32_t)(32 * q) << 16);
+                tc_ld32(taddr, r);
+                if (passes == 3) {
+                    float corr[32];
+                    tc_ld32(taddr + T2N, corr);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] += corr[j];
+                }
+                if (row >= p.M) continue;
+#pragma unroll
+                for (int j0 = 0; j0 < 32; j0 += 4) {
+                    const long long col = n0 + c * 32 + j0;
+                    if (col >= p.N) break;
+                    float x[4] = {r[j0], r[j0 + 1], r[j0 + 2], r[j0 + 3]};
+                    const int nv = (int)min((long long)4, p.N - col);
+                    if (p.split_k > 1) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            if (e < nv) {
+                                if (split == 0 && p.bias) x[e] += p.bias[col + e];
+                                atomicAdd(crow + col + e, x[e]);
+                            }
+                        }
+                        continue;
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        if (e < nv) {
+                            if (p.bias) x[e] += p.bias[col + e];
+                            if (p.act == XNRS_ACT_RELU) x[e] = fmaxf(x[e], 0.f);
+                            else if (p.act == XNRS_ACT_TANH) x[e] = tanhf(x[e]);
+                            else if (p.act == XNRS_ACT_RELU_MASK) x[e] = (arow[col + e] > 0.f) ? x[e] : 0.f;
+                        }
+                    }
+                    if (vec_ok && nv == 4) {
+                        float4 *dst = reinterpret_cast<float4 *>(crow + col);
+                        if (p.accumulate) {
+                            const float4 o = *dst;
+                            x[0] += o.x; x[1] += o.y; x[2] += o.z; x[3] += o.w;
+                        }
+                        *dst = make_float4(x[0], x[1], x[2], x[3]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (e < nv) crow[col + e] = p.accumulate ? crow[col + e] + x[e] : x[e];
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive_cluster(map_to_cta(smem_u32(&tempty_bar[acc.stage]), 0));
+            acc.advance(acc_stages);
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();         // neither CTA may exit (or free TMEM) while its peer can still touch its smem / barriers
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -427,6 +722,8 @@ static bool make_map(CUtensorMap *map, const float *base, long long inner, long 
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+int g_opt_2cta = -1;
+
 int gemm_tensorcore(const GemmArgs &a, int precision, cudaStream_t st, int *status) {
     // shapes / layouts the TMA path cannot take fall through to the exact-fp32 SIMT kernel
     if (a.a_rows && a.transA) return 0;          // gather is fused for K-major A (forward) ...
@@ -448,16 +745,24 @@ int gemm_tensorcore(const GemmArgs &a, int precision, cudaStream_t st, int *stat
     p.passes = (precision == XNRS_PREC_TF32X3) ? 3 : 1;
     // 3xTF32 keeps BN=128: its stage is 2x larger (hi+lo), and 3 smem stages + 2 TMEM stages beat the wider tile
     // (measured: 156 vs 142 TFLOP/s); single-pass TF32 takes BN=256 (398 vs 340 TFLOP/s)
-    const int BN = (p.passes == 1 && a.N > 128 && cdiv(a.M, TBM) * cdiv(a.N, 256) >= num_sms()) ? 256 : 128;
+    // CTA-pair kernel (256x256 tiles, cta_group::2): wide outputs with enough rows and no fused gather
+    // Off by default: measured on B200 it is correct (tests) and lifts the tensor pipe from 47 % to 50 % active in 3xTF32,
+    // but its cross-CTA ready/empty handshake makes the short K loop latency-bound (168 vs 179 TFLOP/s) — round-2 work.
+    if (g_opt_2cta < 0) {
+        const char *e = getenv("XNRS_GEMM_2CTA");
+        g_opt_2cta = e ? atoi(e) : 0;
+    }
+    const bool use2 = g_opt_2cta && a.N > 128 && a.M >= 256 && !a.a_rows && !a.b_rows && (num_sms() % 2 == 0);
+    const int BN = use2 ? 128 : ((p.passes == 1 && a.N > 128 && cdiv(a.M, TBM) * cdiv(a.N, 256) >= num_sms()) ? 256 : 128);
     const int half = TBM * TBK * 4 + BN * TBK * 4;
     p.stages = SMEM_DATA / (half * (p.passes == 3 ? 2 : 1));
     if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
-    p.tiles_m = cdiv(a.M, TBM);
-    p.tiles_n = cdiv(a.N, BN);
+    p.tiles_m = cdiv(a.M, use2 ? 256 : TBM);
+    p.tiles_n = cdiv(a.N, use2 ? 256 : BN);
     long long tiles = p.tiles_m * p.tiles_n;
     int split = a.split_k;
     if (split <= 0) {
-        long long want = num_sms();
+        long long want = use2 ? num_sms() / 2 : num_sms();
         long long s = tiles >= want ? 1 : want / tiles;
         long long maxs = cdiv(a.K, 512);
         if (s > maxs) s = maxs;
@@ -493,7 +798,8 @@ int gemm_tensorcore(const GemmArgs &a, int precision, cudaStream_t st, int *stat
     const int smem_bytes = SMEM_DATA + 1024;
     if (!attr_set) {
         if (cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess ||
-            cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) {
+            cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess ||
+            cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) {
             cudaGetLastError();
             return 0;
         }
@@ -501,7 +807,10 @@ int gemm_tensorcore(const GemmArgs &a, int precision, cudaStream_t st, int *stat
     }
     long long total = tiles * split;
     unsigned grid = (unsigned)(total < num_sms() ? total : num_sms());
-    if (BN == 256) gemm_tc_kernel<256><<<grid, TC_THREADS, smem_bytes, st>>>(mapA, mapB, p);
+    if (use2) {
+        const long long pairs = total < num_sms() / 2 ? total : num_sms() / 2;
+        gemm_tc2_kernel<<<(unsigned)(2 * pairs), TC_THREADS, smem_bytes, st>>>(mapA, mapB, p);
+    } else if (BN == 256) gemm_tc_kernel<256><<<grid, TC_THREADS, smem_bytes, st>>>(mapA, mapB, p);
     else gemm_tc_kernel<128><<<grid, TC_THREADS, smem_bytes, st>>>(mapA, mapB, p);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
@@ -515,3 +824,11 @@ int gemm_tensorcore(const GemmArgs &a, int precision, cudaStream_t st, int *stat
 }
 
 }  // namespace xnrs
+
+extern "C" int xnrs_set_option(const char *name, int value) {
+    if (name && !strcmp(name, "gemm_2cta")) {
+        xnrs::g_opt_2cta = value ? 1 : 0;
+        return XNRS_OK;
+    }
+    return xnrs::fail(XNRS_ERR_ARG, "%s: unknown option", "xnrs_set_option");
+}

@@ -266,6 +266,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--workload', default='train', choices=['train', 'eval'])
     ap.add_argument('--model', default='cl', choices=list(MODEL_CFGS), help='cl is the headline (BASELINE configs[1])')
+    ap.add_argument('--no-skip-padding', action='store_true', help='run pad tokens through the encoder like the reference does')
     ap.add_argument('--no-dedup', action='store_true', help='encode every (impression, slot) title, not each distinct article once')
     ap.add_argument('--eval-impressions', type=int, default=376_471)
     args = ap.parse_args()
@@ -296,6 +297,7 @@ def main():
     B = args.batch
     from xnrs_b200.models.components import TextEncoder
     TextEncoder.dedup_titles = not args.no_dedup
+    TextEncoder.skip_padding = not args.no_skip_padding
 
     cfg = MODEL_CFGS[args.model]
     cat = syn.make_catalogue(N_NEWS, SEQ_LEN, VOCAB, 768, seed=0, with_abstract=(args.model == 'naml'))
@@ -415,7 +417,7 @@ def main():
         'config': {'workload': workload_name(B, args.model), 'global_batch': B * world, 'parallelism': f'dp{world}',
                    'l2': 'inputs larger than L2: 307 MB token table, ~5 GB of gathered rows per step, 8 batches cycled',
                    'precision': args.precision, 'final_loss': last,
-                   'dedup_titles': not args.no_dedup},
+                   'dedup_titles': not args.no_dedup, 'skip_padding': not args.no_skip_padding},
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4,
                 'note': 'host input = int32 news ids / targets / labels (the index fast path of the drop-in API)'},
         'gpu_launches': launches, 'roofline': roofline, 'clocks': clocks.summary(),

@@ -71,22 +71,24 @@ int xnrs_dropout(long long n, const float *x, const float *keep, float p, unsign
 /* ---- row A: additive-attention pooling (layers.py:47-69) -------------------------------------
  * hid = tanh(fc1 x) (R*L, A) comes from xnrs_gemm(act=TANH).  x rows are x[r*L+l] or, with x_rows,
  * table rows x[x_rows[r*L+l]].  mask nullable (R*L).  attn (R*L) and pooled (R,F) are outputs. */
+/* seg (nullable, R+1 ints): ragged groups — group r owns rows [seg[r], seg[r+1]) of x/hid/attn (padding tokens are
+ * never materialised) and L is the longest group; with seg == NULL every group has exactly L rows */
 int xnrs_addpool_fwd(const float *x, const int *x_rows, const float *mask, const float *hid, const float *w2,
-                     const float *b2, long long R, int L, int F, int A, float *attn, float *pooled,
+                     const float *b2, const int *seg, long long R, int L, int F, int A, float *attn, float *pooled,
                      xnrs_stream_t st);
 /* d_hid (R*L,A) = grad wrt the fc1 pre-activation; d_w2 (A), d_b2 (1) accumulate; d_x (nullable, R*L,F)
  * receives a_s * d_pooled (the fc1 path is added by the caller's GEMM); d_attn (nullable) is an
  * incoming gradient on the returned weights */
 int xnrs_addpool_bwd(const float *x, const int *x_rows, const float *mask, const float *hid, const float *w2,
-                     const float *attn, const float *d_pooled, const float *d_attn, long long R, int L, int F,
-                     int A, float *d_hid, float *d_w2, float *d_b2, float *d_x, xnrs_stream_t st);
+                     const float *attn, const float *d_pooled, const float *d_attn, const int *seg, long long R, int L,
+                     int F, int A, float *d_hid, float *d_w2, float *d_b2, float *d_x, xnrs_stream_t st);
 /* ---- row P: personalised attention (layers.py:88-101): logit = <tanh(x_fc x), q_fc(q)> ---------
  * hid (R*L,A) = tanh(x_fc x); qh (Rq,A) = q_fc(q); title r uses query row r / rows_per_query */
 int xnrs_perspool_fwd(const float *x, const int *x_rows, const float *mask, const float *hid, const float *qh,
-                      long long R, int L, int F, int A, int rows_per_query, float *attn, float *pooled,
+                      const int *seg, long long R, int L, int F, int A, int rows_per_query, float *attn, float *pooled,
                       xnrs_stream_t st);
 int xnrs_perspool_bwd(const float *x, const int *x_rows, const float *mask, const float *hid, const float *qh,
-                      const float *attn, const float *d_pooled, long long R, int L, int F, int A,
+                      const float *attn, const float *d_pooled, const int *seg, long long R, int L, int F, int A,
                       int rows_per_query, float *d_hid, float *d_qh, float *d_x, xnrs_stream_t st);
 /* masked mean pooling (layers.py:25-37) */
 int xnrs_meanpool_fwd(const float *x, const float *mask, long long R, int L, int F, float *pooled,

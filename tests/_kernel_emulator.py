@@ -94,55 +94,70 @@ def _xnrs_dropout(n, x, keep, p, seed, y):
     y.copy_(x * _kf(keep, p, x.shape) / (1 - p))
 
 
-def _pool(x, x_rows, mask, logits, R, L, F_):
-    xr = _rows(x, x_rows).reshape(R, L, F_)
-    e = torch.exp(logits.reshape(R, L))
-    if mask is not None:
-        e = e * mask.reshape(R, L)
-    a = e / (e.sum(1, keepdim=True) + 1e-8)
-    return a, (a.unsqueeze(-1) * xr).sum(1), xr
+def _groups(R, L, seg):
+    return [(r * L, L) for r in range(R)] if seg is None else [(int(seg[r]), int(seg[r + 1] - seg[r])) for r in range(R)]
 
 
-def _xnrs_addpool_fwd(x, x_rows, mask, hid, w2, b2, R, L, F_, A, attn, pooled):
-    a, p, _ = _pool(x, x_rows, mask, hid @ w2 + b2, R, L, F_)
-    attn.copy_(a)
-    pooled.copy_(p)
+def _pool_fwd(x, x_rows, mask, logits, seg, R, L, attn, pooled):
+    xr = _rows(x, x_rows)
+    af, lg = attn.reshape(-1), logits.reshape(-1)
+    for r, (b, n) in enumerate(_groups(R, L, seg)):
+        e = torch.exp(lg[b:b + n])
+        if mask is not None:
+            e = e * mask.reshape(-1)[b:b + n]
+        a = e / (e.sum() + 1e-8)
+        af[b:b + n] = a
+        pooled[r] = (a[:, None] * xr[b:b + n]).sum(0)
 
 
-def _pool_bwd(xr, attn, d_pooled, d_attn, R, L):
-    da = (xr * d_pooled.unsqueeze(1)).sum(-1)
-    if d_attn is not None:
-        da = da + d_attn.reshape(R, L)
-    a = attn.reshape(R, L)
-    return a * (da - (a * da).sum(1, keepdim=True))
+def _pool_dlogit(x, x_rows, attn, d_pooled, d_attn, seg, R, L):
+    xr = _rows(x, x_rows)
+    af = attn.reshape(-1)
+    dl = torch.zeros_like(af)
+    for r, (b, n) in enumerate(_groups(R, L, seg)):
+        da = xr[b:b + n] @ d_pooled[r]
+        if d_attn is not None:
+            da = da + d_attn.reshape(-1)[b:b + n]
+        a = af[b:b + n]
+        dl[b:b + n] = a * (da - (a * da).sum())
+    return dl
 
 
-def _xnrs_addpool_bwd(x, x_rows, mask, hid, w2, attn, d_pooled, d_attn, R, L, F_, A, d_hid, d_w2, d_b2, d_x):
-    xr = _rows(x, x_rows).reshape(R, L, F_)
-    dl = _pool_bwd(xr, attn, d_pooled, d_attn, R, L).reshape(-1)
+def _pool_dx(attn, d_pooled, seg, R, L, d_x):
+    af = attn.reshape(-1)
+    for r, (b, n) in enumerate(_groups(R, L, seg)):
+        d_x[b:b + n] = af[b:b + n, None] * d_pooled[r][None, :]
+
+
+def _xnrs_addpool_fwd(x, x_rows, mask, hid, w2, b2, seg, R, L, F_, A, attn, pooled):
+    _pool_fwd(x, x_rows, mask, hid @ w2 + b2, seg, R, L, attn, pooled)
+
+
+def _xnrs_addpool_bwd(x, x_rows, mask, hid, w2, attn, d_pooled, d_attn, seg, R, L, F_, A, d_hid, d_w2, d_b2, d_x):
+    dl = _pool_dlogit(x, x_rows, attn, d_pooled, d_attn, seg, R, L)
     d_hid.copy_(dl[:, None] * w2[None, :] * (1 - hid * hid))
     d_w2.add_((dl[:, None] * hid).sum(0))
     d_b2.add_(dl.sum())
     if d_x is not None:
-        d_x.copy_((attn.reshape(R, L, 1) * d_pooled.unsqueeze(1)).reshape(R * L, F_))
+        _pool_dx(attn, d_pooled, seg, R, L, d_x)
 
 
-def _xnrs_perspool_fwd(x, x_rows, mask, hid, qh, R, L, F_, A, rpq, attn, pooled):
-    q = qh.repeat_interleave(rpq, 0).repeat_interleave(L, 0)
-    a, p, _ = _pool(x, x_rows, mask, (hid * q).sum(-1), R, L, F_)
-    attn.copy_(a)
-    pooled.copy_(p)
+def _qrows(qh, seg, R, L, rpq):
+    return torch.cat([qh[r // rpq][None, :].expand(n, -1) for r, (b, n) in enumerate(_groups(R, L, seg))]) \
+        if R else qh[:0]
 
 
-def _xnrs_perspool_bwd(x, x_rows, mask, hid, qh, attn, d_pooled, R, L, F_, A, rpq, d_hid, d_qh, d_x):
-    xr = _rows(x, x_rows).reshape(R, L, F_)
-    dl = _pool_bwd(xr, attn, d_pooled, None, R, L).reshape(-1)
-    q = qh.repeat_interleave(rpq, 0).repeat_interleave(L, 0)
-    d_hid.copy_(dl[:, None] * q * (1 - hid * hid))
-    contrib = (dl[:, None] * hid).reshape(R // rpq, rpq * L, A).sum(1)
-    d_qh.add_(contrib)
+def _xnrs_perspool_fwd(x, x_rows, mask, hid, qh, seg, R, L, F_, A, rpq, attn, pooled):
+    _pool_fwd(x, x_rows, mask, (hid * _qrows(qh, seg, R, L, rpq)).sum(-1), seg, R, L, attn, pooled)
+
+
+def _xnrs_perspool_bwd(x, x_rows, mask, hid, qh, attn, d_pooled, seg, R, L, F_, A, rpq, d_hid, d_qh, d_x):
+    dl = _pool_dlogit(x, x_rows, attn, d_pooled, None, seg, R, L)
+    d_hid.copy_(dl[:, None] * _qrows(qh, seg, R, L, rpq) * (1 - hid * hid))
+    for r, (b, n) in enumerate(_groups(R, L, seg)):
+        d_qh[r // rpq] += (dl[b:b + n, None] * hid[b:b + n]).sum(0)
     if d_x is not None:
-        d_x.copy_((attn.reshape(R, L, 1) * d_pooled.unsqueeze(1)).reshape(R * L, F_))
+        _pool_dx(attn, d_pooled, seg, R, L, d_x)
 
 
 def _xnrs_meanpool_fwd(x, mask, R, L, F_, pooled):

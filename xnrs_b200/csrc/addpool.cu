@@ -15,21 +15,25 @@ template <bool kPers>
 __global__ void __launch_bounds__(POOL_THREADS)
 pool_fwd_kernel(const float *__restrict__ x, const int *__restrict__ x_rows, const float *__restrict__ mask,
                 const float *__restrict__ hid, const float *__restrict__ w2, const float *__restrict__ b2,
-                const float *__restrict__ qh, int rows_per_query, long long R, int L, int F, int A,
-                float *__restrict__ attn, float *__restrict__ pooled) {
+                const float *__restrict__ qh, int rows_per_query, const int *__restrict__ seg, long long R, int L, int F,
+                int A, float *__restrict__ attn, float *__restrict__ pooled) {
     extern __shared__ float sm[];
     float *e = sm;                               // [L]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int F4 = F >> 2;
     const float4 *x4 = reinterpret_cast<const float4 *>(x);
+    const int Lmax = L;
     for (long long r = blockIdx.x; r < R; r += gridDim.x) {
+        // ragged groups: rows [seg[r], seg[r+1]) (padding tokens were never materialised); else fixed L rows per group
+        const long long base = seg ? (long long)seg[r] : r * (long long)Lmax;
+        const int L = seg ? seg[r + 1] - seg[r] : Lmax;
         const float *wv = kPers ? qh + (r / rows_per_query) * A : w2;
         const float bias = kPers ? 0.f : b2[0];
         for (int l = warp; l < L; l += nwarps) {
-            const float mval = mask ? mask[r * L + l] : 1.f;
+            const float mval = mask ? mask[base + l] : 1.f;
             float acc = 0.f;
             if (mval != 0.f) {
-                const float *hrow = hid + (r * L + l) * A;
+                const float *hrow = hid + (base + l) * A;
                 for (int j = lane; j < A; j += 32) acc = fmaf(hrow[j], wv[j], acc);
                 acc = warp_sum(acc);
             }
@@ -39,13 +43,13 @@ pool_fwd_kernel(const float *__restrict__ x, const int *__restrict__ x_rows, con
         float tot = 0.f;
         for (int l = 0; l < L; ++l) tot += e[l];
         const float denom = tot + 1e-8f;
-        for (int l = tid; l < L; l += blockDim.x) attn[r * L + l] = e[l] / denom;
+        for (int l = tid; l < L; l += blockDim.x) attn[base + l] = e[l] / denom;
         for (int c = tid; c < F4; c += blockDim.x) {
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int l = 0; l < L; ++l) {
                 const float a = e[l] / denom;
                 if (a == 0.f) continue;
-                const long long row = x_rows ? (long long)x_rows[r * L + l] : r * L + l;
+                const long long row = x_rows ? (long long)x_rows[base + l] : base + l;
                 const float4 v = ldg_stream(x4 + row * F4 + c);
                 acc.x = fmaf(a, v.x, acc.x); acc.y = fmaf(a, v.y, acc.y);
                 acc.z = fmaf(a, v.z, acc.z); acc.w = fmaf(a, v.w, acc.w);
@@ -62,10 +66,10 @@ __global__ void __launch_bounds__(POOL_THREADS)
 pool_bwd_kernel(const float *__restrict__ x, const int *__restrict__ x_rows, const float *__restrict__ hid,
                 const float *__restrict__ w2, const float *__restrict__ qh, int rows_per_query,
                 const float *__restrict__ attn, const float *__restrict__ d_pooled, const float *__restrict__ d_attn,
-                long long R, int L, int F, int A, float *__restrict__ d_hid, float *__restrict__ d_w2,
+                const int *__restrict__ seg, long long R, int L, int F, int A, float *__restrict__ d_hid, float *__restrict__ d_w2,
                 float *__restrict__ d_b2, float *__restrict__ d_qh, float *__restrict__ d_x) {
     extern __shared__ float sm[];
-    float *da = sm;            // [L]  da_l, then dlogit_l
+    float *da = sm;            // [L]  da_l, then dlogit_l            (L here = the maximum group length)
     float *al = sm + L;        // [L]  a_l
     float *dw = sm + 2 * L;    // [A]  per-CTA accumulator for d_w2 (additive only)
     __shared__ float db_acc;
@@ -77,13 +81,16 @@ pool_bwd_kernel(const float *__restrict__ x, const int *__restrict__ x_rows, con
         if (tid == 0) db_acc = 0.f;
     }
     __syncthreads();
+    const int Lmax = L;
     for (long long r = blockIdx.x; r < R; r += gridDim.x) {
+        const long long base = seg ? (long long)seg[r] : r * (long long)Lmax;
+        const int L = seg ? seg[r + 1] - seg[r] : Lmax;
         const float4 *dp4 = reinterpret_cast<const float4 *>(d_pooled) + r * F4;
         for (int l = warp; l < L; l += nwarps) {
-            const float a = attn[r * L + l];
+            const float a = attn[base + l];
             float acc = 0.f;
             if (a != 0.f) {
-                const long long row = x_rows ? (long long)x_rows[r * L + l] : r * L + l;
+                const long long row = x_rows ? (long long)x_rows[base + l] : base + l;
                 for (int c = lane; c < F4; c += 32) {
                     const float4 v = ldg_stream(x4 + row * F4 + c);
                     const float4 g = dp4[c];
@@ -91,7 +98,7 @@ pool_bwd_kernel(const float *__restrict__ x, const int *__restrict__ x_rows, con
                     acc = fmaf(v.z, g.z, acc); acc = fmaf(v.w, g.w, acc);
                 }
                 acc = warp_sum(acc);
-                if (d_attn) acc += d_attn[r * L + l];
+                if (d_attn) acc += d_attn[base + l];
             }
             if (lane == 0) { da[l] = acc; al[l] = a; }
         }
@@ -107,7 +114,7 @@ pool_bwd_kernel(const float *__restrict__ x, const int *__restrict__ x_rows, con
             float gw = 0.f;
             for (int l = 0; l < L; ++l) {
                 const float dl = da[l];
-                const long long idx = (r * L + l) * A + j;
+                const long long idx = (base + l) * A + j;
                 if (dl != 0.f) {
                     const float h = hid[idx];
                     gw = fmaf(dl, h, gw);
@@ -129,7 +136,7 @@ pool_bwd_kernel(const float *__restrict__ x, const int *__restrict__ x_rows, con
                 const int l = i / F4, c = i - l * F4;
                 const float a = al[l];
                 const float4 g = dp4[c];
-                reinterpret_cast<float4 *>(d_x)[(r * L + l) * F4 + c] = make_float4(a * g.x, a * g.y, a * g.z, a * g.w);
+                reinterpret_cast<float4 *>(d_x)[(base + l) * F4 + c] = make_float4(a * g.x, a * g.y, a * g.z, a * g.w);
             }
         }
         __syncthreads();
@@ -179,54 +186,55 @@ static int check_pool(long long R, int L, int F, int A, const float *x) {
 using namespace xnrs;
 
 extern "C" int xnrs_addpool_fwd(const float *x, const int *x_rows, const float *mask, const float *hid,
-                                const float *w2, const float *b2, long long R, int L, int F, int A, float *attn,
-                                float *pooled, xnrs_stream_t st) {
+                                const float *w2, const float *b2, const int *seg, long long R, int L, int F, int A,
+                                float *attn, float *pooled, xnrs_stream_t st) {
     if (int e = check_pool(R, L, F, A, x)) return e;
     if (R == 0) return XNRS_OK;
     XNRS_REQUIRE(x && hid && w2 && b2 && attn && pooled, "null pointer");
     pool_fwd_kernel<false><<<pool_grid(R), POOL_THREADS, L * sizeof(float), STREAM(st)>>>(
-        x, x_rows, mask, hid, w2, b2, nullptr, 1, R, L, F, A, attn, pooled);
+        x, x_rows, mask, hid, w2, b2, nullptr, 1, seg, R, L, F, A, attn, pooled);
     XNRS_LAUNCHED();
     return XNRS_OK;
 }
 
 extern "C" int xnrs_addpool_bwd(const float *x, const int *x_rows, const float *mask, const float *hid,
                                 const float *w2, const float *attn, const float *d_pooled, const float *d_attn,
-                                long long R, int L, int F, int A, float *d_hid, float *d_w2, float *d_b2, float *d_x,
-                                xnrs_stream_t st) {
+                                const int *seg, long long R, int L, int F, int A, float *d_hid, float *d_w2, float *d_b2,
+                                float *d_x, xnrs_stream_t st) {
     (void)mask;   // the mask is already folded into attn (masked rows have weight exactly 0)
     if (int e = check_pool(R, L, F, A, x)) return e;
     if (R == 0) return XNRS_OK;
     XNRS_REQUIRE(x && hid && w2 && attn && d_pooled && d_hid && d_w2 && d_b2, "null pointer");
     XNRS_REQUIRE(!(d_x && x_rows), "d_x is only defined for dense x");
     pool_bwd_kernel<false><<<pool_grid(R), POOL_THREADS, (2 * L + A) * sizeof(float), STREAM(st)>>>(
-        x, x_rows, hid, w2, nullptr, 1, attn, d_pooled, d_attn, R, L, F, A, d_hid, d_w2, d_b2, nullptr, d_x);
+        x, x_rows, hid, w2, nullptr, 1, attn, d_pooled, d_attn, seg, R, L, F, A, d_hid, d_w2, d_b2, nullptr, d_x);
     XNRS_LAUNCHED();
     return XNRS_OK;
 }
 
 extern "C" int xnrs_perspool_fwd(const float *x, const int *x_rows, const float *mask, const float *hid,
-                                 const float *qh, long long R, int L, int F, int A, int rows_per_query, float *attn,
-                                 float *pooled, xnrs_stream_t st) {
+                                 const float *qh, const int *seg, long long R, int L, int F, int A, int rows_per_query,
+                                 float *attn, float *pooled, xnrs_stream_t st) {
     if (int e = check_pool(R, L, F, A, x)) return e;
     if (R == 0) return XNRS_OK;
     XNRS_REQUIRE(x && hid && qh && attn && pooled && rows_per_query > 0, "null pointer");
     pool_fwd_kernel<true><<<pool_grid(R), POOL_THREADS, L * sizeof(float), STREAM(st)>>>(
-        x, x_rows, mask, hid, nullptr, nullptr, qh, rows_per_query, R, L, F, A, attn, pooled);
+        x, x_rows, mask, hid, nullptr, nullptr, qh, rows_per_query, seg, R, L, F, A, attn, pooled);
     XNRS_LAUNCHED();
     return XNRS_OK;
 }
 
 extern "C" int xnrs_perspool_bwd(const float *x, const int *x_rows, const float *mask, const float *hid,
-                                 const float *qh, const float *attn, const float *d_pooled, long long R, int L, int F,
-                                 int A, int rows_per_query, float *d_hid, float *d_qh, float *d_x, xnrs_stream_t st) {
+                                 const float *qh, const float *attn, const float *d_pooled, const int *seg, long long R,
+                                 int L, int F, int A, int rows_per_query, float *d_hid, float *d_qh, float *d_x,
+                                 xnrs_stream_t st) {
     (void)mask;
     if (int e = check_pool(R, L, F, A, x)) return e;
     if (R == 0) return XNRS_OK;
     XNRS_REQUIRE(x && hid && qh && attn && d_pooled && d_hid && d_qh && rows_per_query > 0, "null pointer");
     XNRS_REQUIRE(!(d_x && x_rows), "d_x is only defined for dense x");
     pool_bwd_kernel<true><<<pool_grid(R), POOL_THREADS, (2 * L + A) * sizeof(float), STREAM(st)>>>(
-        x, x_rows, hid, nullptr, qh, rows_per_query, attn, d_pooled, nullptr, R, L, F, A, d_hid, nullptr, nullptr,
+        x, x_rows, hid, nullptr, qh, rows_per_query, attn, d_pooled, nullptr, seg, R, L, F, A, d_hid, nullptr, nullptr,
         d_qh, d_x);
     XNRS_LAUNCHED();
     return XNRS_OK;

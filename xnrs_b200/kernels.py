@@ -259,20 +259,21 @@ class AdditivePoolFn(torch.autograd.Function):
     """layers.AdditiveAttention (layers.py:47-69) over R groups of L rows: -> pooled (R,F), attn (R,L)."""
 
     @staticmethod
-    def forward(ctx, x, rows, mask, w1, b1, w2, b2, R, L):
+    def forward(ctx, x, rows, mask, w1, b1, w2, b2, R, L, seg=None):
+        """seg (R+1 int32, optional): ragged groups — group r owns rows [seg[r], seg[r+1]); L = longest group"""
         F_, A = x.shape[1], w1.shape[0]
         x, rows = _resolve_rows(x, rows)
         hid = gemm(x, w1, trans_b=True, bias=b1, act=ACT_TANH, a_rows=rows)
-        attn = torch.empty((R, L), device=x.device, dtype=torch.float32)
+        attn = torch.empty((R, L) if seg is None else (hid.shape[0],), device=x.device, dtype=torch.float32)
         pooled = torch.empty((R, F_), device=x.device, dtype=torch.float32)
-        call('xnrs_addpool_fwd', x, rows, mask, hid, w2, b2, R, L, F_, A, attn, pooled)
-        ctx.save_for_backward(x, rows, w1, w2, hid, attn)
+        call('xnrs_addpool_fwd', x, rows, mask, hid, w2, b2, seg, R, L, F_, A, attn, pooled)
+        ctx.save_for_backward(x, rows, w1, w2, hid, attn, seg)
         ctx.dims = (R, L, F_, A)
         return pooled, attn
 
     @staticmethod
     def backward(ctx, d_pooled, d_attn):
-        x, rows, w1, w2, hid, attn = ctx.saved_tensors
+        x, rows, w1, w2, hid, attn, seg = ctx.saved_tensors
         R, L, F_, A = ctx.dims
         dev = x.device
         d_pooled = _f32(d_pooled)
@@ -284,33 +285,33 @@ class AdditivePoolFn(torch.autograd.Function):
         if need_dx and rows is not None:
             raise RuntimeError('no gradient flows into a gathered (frozen) table')
         d_x = torch.empty_like(x) if need_dx else None
-        call('xnrs_addpool_bwd', x, rows, None, hid, w2, attn, d_pooled, d_attn, R, L, F_, A, d_hid, d_w2, d_b2, d_x)
+        call('xnrs_addpool_bwd', x, rows, None, hid, w2, attn, d_pooled, d_attn, seg, R, L, F_, A, d_hid, d_w2, d_b2, d_x)
         d_w1 = gemm(d_hid, x, trans_a=True, b_rows=rows)
         d_b1 = colsum(d_hid)
         if need_dx:
             gemm(d_hid, w1, out=d_x, accumulate=True)
-        return d_x, None, None, d_w1, d_b1, d_w2, d_b2, None, None
+        return d_x, None, None, d_w1, d_b1, d_w2, d_b2, None, None, None
 
 
 class PersonalizedPoolFn(torch.autograd.Function):
     """layers.PersonalizedAttention (layers.py:88-101); group r uses query row r // rows_per_query."""
 
     @staticmethod
-    def forward(ctx, q, x, rows, mask, xw, xb, qw, qb, R, L, rows_per_query):
+    def forward(ctx, q, x, rows, mask, xw, xb, qw, qb, R, L, rows_per_query, seg=None):
         F_, A = x.shape[1], xw.shape[0]
         x, rows = _resolve_rows(x, rows)
         hid = gemm(x, xw, trans_b=True, bias=xb, act=ACT_TANH, a_rows=rows)
         qh = gemm(q, qw, trans_b=True, bias=qb)
-        attn = torch.empty((R, L), device=x.device, dtype=torch.float32)
+        attn = torch.empty((R, L) if seg is None else (hid.shape[0],), device=x.device, dtype=torch.float32)
         pooled = torch.empty((R, F_), device=x.device, dtype=torch.float32)
-        call('xnrs_perspool_fwd', x, rows, mask, hid, qh, R, L, F_, A, rows_per_query, attn, pooled)
-        ctx.save_for_backward(q, x, rows, xw, qw, hid, qh, attn)
+        call('xnrs_perspool_fwd', x, rows, mask, hid, qh, seg, R, L, F_, A, rows_per_query, attn, pooled)
+        ctx.save_for_backward(q, x, rows, xw, qw, hid, qh, attn, seg)
         ctx.dims = (R, L, F_, A, rows_per_query)
         return pooled
 
     @staticmethod
     def backward(ctx, d_pooled):
-        q, x, rows, xw, qw, hid, qh, attn = ctx.saved_tensors
+        q, x, rows, xw, qw, hid, qh, attn, seg = ctx.saved_tensors
         R, L, F_, A, rpq = ctx.dims
         d_pooled = _f32(d_pooled)
         d_hid = torch.empty_like(hid)
@@ -319,7 +320,7 @@ class PersonalizedPoolFn(torch.autograd.Function):
         if need_dx and rows is not None:
             raise RuntimeError('no gradient flows into a gathered (frozen) table')
         d_x = torch.empty_like(x) if need_dx else None
-        call('xnrs_perspool_bwd', x, rows, None, hid, qh, attn, d_pooled, R, L, F_, A, rpq, d_hid, d_qh, d_x)
+        call('xnrs_perspool_bwd', x, rows, None, hid, qh, attn, d_pooled, seg, R, L, F_, A, rpq, d_hid, d_qh, d_x)
         d_xw = gemm(d_hid, x, trans_a=True, b_rows=rows)
         d_xb = colsum(d_hid)
         if need_dx:
@@ -327,7 +328,7 @@ class PersonalizedPoolFn(torch.autograd.Function):
         d_qw = gemm(d_qh, q, trans_a=True)
         d_qb = colsum(d_qh)
         d_q = gemm(d_qh, qw) if _need(ctx, 0) else None
-        return d_q, d_x, None, None, d_xw, d_xb, d_qw, d_qb, None, None, None
+        return d_q, d_x, None, None, d_xw, d_xb, d_qw, d_qb, None, None, None, None
 
 
 class MultiHeadAttentionFn(torch.autograd.Function):

@@ -57,10 +57,10 @@ class AdditiveAttention(nn.Module):
         self.fc1 = nn.Linear(in_features, hidden_features)
         self.fc2 = nn.Linear(hidden_features, 1)
 
-    def pool(self, x2: torch.Tensor, rows, mask, R: int, L: int):
-        """(R*L, F) rows (or table + row index) -> pooled (R, F), weights (R, L)"""
+    def pool(self, x2: torch.Tensor, rows, mask, R: int, L: int, seg=None):
+        """(R*L, F) rows (or table + row index) -> pooled (R, F), weights (R, L); seg: ragged group offsets (R+1)"""
         return K.AdditivePoolFn.apply(x2, rows, mask, self.fc1.weight, self.fc1.bias,
-                                      self.fc2.weight.reshape(-1), self.fc2.bias, R, L)
+                                      self.fc2.weight.reshape(-1), self.fc2.bias, R, L, seg)
 
     def forward(self, x: torch.Tensor, m: torch.Tensor = None, return_weights: bool = False):
         x2, R, L = _flat_rows(x)
@@ -77,9 +77,9 @@ class PersonalizedAttention(nn.Module):
         self.x_fc = nn.Linear(in_features, hidden_features)
         self.q_fc = nn.Linear(query_features, hidden_features)
 
-    def pool(self, q2, x2, rows, mask, R: int, L: int, rows_per_query: int = 1):
+    def pool(self, q2, x2, rows, mask, R: int, L: int, rows_per_query: int = 1, seg=None):
         return K.PersonalizedPoolFn.apply(q2, x2, rows, mask, self.x_fc.weight, self.x_fc.bias,
-                                          self.q_fc.weight, self.q_fc.bias, R, L, rows_per_query)
+                                          self.q_fc.weight, self.q_fc.bias, R, L, rows_per_query, seg)
 
     def forward(self, q: torch.Tensor, x: torch.Tensor, m: torch.Tensor = None):
         x2, R, L = _flat_rows(x)
@@ -121,6 +121,17 @@ class MultiHeadAttention(nn.Module):
         return self.attend(x2, None, _flat_mask(m, R * L), R, L).view(R, L, self.d_model)
 
 
+def ragged_token_rows(title_tokens: torch.Tensor, news_ids: torch.Tensor):
+    """index plumbing for the padding-free path: -> (token rows of the real tokens (total,) int32,
+    group offsets (n+1,) int32, collapsed title mask (n,) fp32).  One host sync (the compacted size)."""
+    tok = title_tokens[news_ids.long()]
+    valid = tok != 0
+    lens = valid.sum(1, dtype=torch.int32)
+    seg = torch.zeros(lens.numel() + 1, device=tok.device, dtype=torch.int32)
+    torch.cumsum(lens, 0, out=seg[1:])
+    return tok[valid].contiguous(), seg, (lens > 0).to(torch.float32)
+
+
 def _apply_head(head: nn.Sequential, x2: torch.Tensor) -> torch.Tensor:
     if not isinstance(head[1], nn.ReLU):
         raise NotImplementedError('only the reference default activation nn.ReLU() is implemented')
@@ -144,9 +155,14 @@ class TextEncoder(nn.Module):
     ``dedup_titles``: every title is encoded independently of its batch position (news_encoding.py:48-57), so with
     ids the encoder runs ONCE per distinct article of the batch and the vectors are gathered back to the (b,n)
     slots; the backward pass sums the slot gradients per article (scatter-add) before the encoder's backward.
-    Same values and gradients (up to fp32 summation order), ~6x fewer titles on MIND-shaped (Zipf) batches."""
+    Same values and gradients (up to fp32 summation order), ~6x fewer titles on MIND-shaped (Zipf) batches.
+
+    ``skip_padding``: pad tokens have mask 0, i.e. pooling weight exactly 0 (layers.py:62-64), so without self-attention
+    they cannot influence anything: only real tokens are gathered and the pooler works on ragged groups.  (With
+    self-attention padded tokens ARE attended to as keys — layers.py:142-144 — so NRMS keeps the fixed-length path.)"""
 
     dedup_titles = True
+    skip_padding = True
 
     def __init__(self, pooler: nn.Module, p_dropout: float, out_features: int, in_features: Optional[int] = 768,
                  head: bool = True, activation: nn.Module = nn.ReLU(), att: Optional[nn.Module] = None,
@@ -162,10 +178,10 @@ class TextEncoder(nn.Module):
                                       nn.Linear(out_features, out_features, bias=bias))
         self.out_dim = out_features
 
-    def _encode(self, x2, rows, mask, R: int, S: int):
+    def _encode(self, x2, rows, mask, R: int, S: int, seg=None):
         if self.att is not None:
             x2, rows = self.att.attend(x2, rows, mask, R, S), None
-        pooled, _ = self.pooler.pool(x2, rows, mask, R, S)
+        pooled, _ = self.pooler.pool(x2, rows, mask, R, S, seg)
         return _apply_head(self.head, pooled) if hasattr(self, 'head') else pooled
 
     def forward(self, inpt):
@@ -177,16 +193,21 @@ class TextEncoder(nn.Module):
             S = store.seq_len
             if self.dropout.p > 0 and self.training:
                 raise NotImplementedError('input dropout on gathered titles (every shipped config has p_dropout 0)')
+            uniq, inv = ids.reshape(-1), None
             if self.dedup_titles and b * n >= 64:
-                uniq, inv = torch.unique(ids.reshape(-1), return_inverse=True)      # id plumbing (one host sync)
-                nu = uniq.numel()
+                uniq, inv = torch.unique(uniq, return_inverse=True)                 # id plumbing (one host sync)
+            nu = uniq.numel()
+            if self.skip_padding and self.att is None and hasattr(self.pooler, 'fc1'):
+                rows, seg, cm_u = ragged_token_rows(store.title_tokens, uniq)
+                e_u = self._encode(store.token_table, rows, None, nu, S, seg)
+            else:
                 rows, mask = K.expand_titles(store.title_tokens, uniq)
                 e_u = self._encode(store.token_table, rows, mask, nu, S)
-                e = K.EmbeddingFn.apply(e_u, inv, None)                            # gather back; bwd = scatter-add
-                cm = K.collapse_mask(mask, nu, S)[inv]
-                return e.view(b, n, self.out_dim), cm.view(b, n, 1)
-            rows, mask = K.expand_titles(store.title_tokens, ids)
-            e = self._encode(store.token_table, rows, mask, b * n, S)
+                cm_u = K.collapse_mask(mask, nu, S)
+            if inv is None:
+                return e_u.view(b, n, self.out_dim), cm_u.view(b, n, 1)
+            e = K.EmbeddingFn.apply(e_u, inv, None)                                # gather back; bwd = scatter-add
+            return e.view(b, n, self.out_dim), cm_u[inv].view(b, n, 1)
         else:
             x, m = inpt
             x, m = x.to(device), m.to(device)

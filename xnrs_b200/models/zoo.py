@@ -290,8 +290,15 @@ class NPA(nn.Module):
             ids = feats.news_ids.to(device)
             b, n = ids.shape
             s = feats.store.seq_len
-            rows, mask = K.expand_titles(feats.store.title_tokens, ids)
+            from .components import TextEncoder, ragged_token_rows
             x2 = feats.store.token_table
+            if TextEncoder.skip_padding:            # only real tokens reach the GEMM / pooler (ragged groups)
+                rows, seg, cm = ragged_token_rows(feats.store.title_tokens, ids.reshape(-1))
+                pooled = self.title_pooler.pool(ue2, x2, rows, None, b * n, s, rows_per_query=n, seg=seg)
+                hd = self.news_head
+                e = K.Mlp2Fn.apply(pooled, hd[0].weight, hd[0].bias, hd[2].weight, hd[2].bias)
+                return e.view(b, n, -1), cm, (b, n, s)
+            rows, mask = K.expand_titles(feats.store.title_tokens, ids)
         else:
             x, m = feats
             x, m = x.to(device), m.to(device)
@@ -308,7 +315,7 @@ class NPA(nn.Module):
         device = _dev(self)
         ue2 = _embed(self.user_embedder, uid.to(device)).reshape(uid.shape[0], -1)      # (B, du)
         h, hmask, (b, nh, s) = self._titles(hist_title_features, ue2)
-        hm = K.collapse_mask(hmask, b * nh, s)
+        hm = hmask if hmask.numel() == b * nh else K.collapse_mask(hmask, b * nh, s)     # ragged path returns it collapsed
         u = self.user_encoder.pool(ue2, h.reshape(b * nh, -1), None, hm, b, nh).unsqueeze(1)
         c, _, _ = self._titles(cand_title_features, ue2)
         return self.rec_model(u, c)

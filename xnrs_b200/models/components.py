@@ -269,6 +269,29 @@ class DotScoring(nn.Module):
         return K.DotScoreFn.apply(K._f32(u).reshape(B, T), K._f32(c)).unsqueeze(-1)
 
 
+def merge_sides(history, candidates):
+    """history and candidate titles go through the SAME encoder (parent.py:31-32): with index batches they are encoded in
+    one call (one de-duplication, half the launches).  Returns (merged IndexedTitles, n_hist) or None."""
+    if (isinstance(history, IndexedTitles) and isinstance(candidates, IndexedTitles)
+            and history.store is candidates.store and history.news_ids.shape[0] == candidates.news_ids.shape[0]):
+        dev = history.store.device
+        ids = torch.cat([history.news_ids.to(dev), candidates.news_ids.to(dev)], dim=1)
+        return IndexedTitles(history.store, ids), history.news_ids.shape[1]
+    return None
+
+
+def encode_both_sides(encoder, history, candidates):
+    """-> (h (b,nh,E), hm (b,nh,1), c (b,nc,E))"""
+    merged = merge_sides(history, candidates)
+    if merged is None:
+        h, hm = encoder(history)
+        c, _ = encoder(candidates)
+        return h, hm, c
+    e, m = encoder(merged[0])
+    nh = merged[1]
+    return e[:, :nh], m[:, :nh], e[:, nh:]
+
+
 class ParentRec(nn.Module):
     """parent.ParentRec (parent.py:8-81): news_encoder x2 -> user_encoder -> rec_model."""
 
@@ -281,8 +304,7 @@ class ParentRec(nn.Module):
         self.text_feature = text_feature
 
     def _forward(self, history, candidates, add_user_feats=None, return_embeddings: bool = False):
-        h, hm = self.news_encoder(history)
-        c, _ = self.news_encoder(candidates)
+        h, hm, c = encode_both_sides(self.news_encoder, history, candidates)
         u = self.user_encoder((h, hm), add_user_feats)
         r = self.rec_model(u, c)
         return (r, u, c) if return_embeddings else r

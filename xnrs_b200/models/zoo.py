@@ -12,7 +12,7 @@ import torch.nn as nn
 
 from .. import kernels as K
 from .components import (AdditiveAttention, DotScoring, MultiHeadAttention, ParentRec, PersonalizedAttention,
-                         TextEncoder, UserEncoder, _dev, _flat_mask)
+                         TextEncoder, UserEncoder, _dev, _flat_mask, merge_sides)
 
 
 class _Missing:
@@ -147,8 +147,15 @@ class NAML(nn.Module):
 
     def _forward(self, hist_title_features, hist_abstract_features, hist_ctg, hist_subctg,
                  cand_title_features, cand_abstract_features, cand_ctg, cand_subctg, return_embeddings=False):
-        h, hm = self._news(hist_title_features, hist_abstract_features, hist_ctg, hist_subctg)
-        c, _ = self._news(cand_title_features, cand_abstract_features, cand_ctg, cand_subctg)
+        mt, ma = merge_sides(hist_title_features, cand_title_features), merge_sides(hist_abstract_features, cand_abstract_features)
+        if mt is not None and ma is not None:       # index batches: both sides in one pass through the shared encoders
+            dev = _dev(self)
+            e, m = self._news(mt[0], ma[0], torch.cat([hist_ctg.to(dev), cand_ctg.to(dev)], 1),
+                              torch.cat([hist_subctg.to(dev), cand_subctg.to(dev)], 1))
+            h, hm, c = e[:, :mt[1]], m[:, :mt[1]], e[:, mt[1]:]
+        else:
+            h, hm = self._news(hist_title_features, hist_abstract_features, hist_ctg, hist_subctg)
+            c, _ = self._news(cand_title_features, cand_abstract_features, cand_ctg, cand_subctg)
         u = self._user(h, hm)
         r = self.rec_model(u, c)
         return (r, u, c) if return_embeddings else r
@@ -255,8 +262,15 @@ class LSTUR(nn.Module):
     def forward(self, batch: dict, return_embeddings: bool = False):
         hs, cs = self._subcats(batch)
         hf, cf = batch['user_features']['history'], batch['candidate_features']
-        h, hm = self.news_encoder(hf['title_emb'], hf['category_index'], hs)
-        c, _ = self.news_encoder(cf['title_emb'], cf['category_index'], cs)
+        mt = merge_sides(hf['title_emb'], cf['title_emb'])
+        if mt is not None:
+            dev = _dev(self)
+            sub = None if hs is None else torch.cat([hs.to(dev), cs.to(dev)], 1)
+            e, m = self.news_encoder(mt[0], torch.cat([hf['category_index'].to(dev), cf['category_index'].to(dev)], 1), sub)
+            h, hm, c = e[:, :mt[1]], m[:, :mt[1]], e[:, mt[1]:]
+        else:
+            h, hm = self.news_encoder(hf['title_emb'], hf['category_index'], hs)
+            c, _ = self.news_encoder(cf['title_emb'], cf['category_index'], cs)
         u = self.user_encoder((h, hm), batch['user_features']['other']['user_index'])
         r = self.rec_model(u, c)
         return (r, u, c) if return_embeddings else r

@@ -373,15 +373,32 @@ def main():
     pk, pk_kind = peaks()
     gemm_ms, gemm_n, gemm_flop = agg.get('xnrs_gemm', [0.0, 0, 0.0])
     kernel_ms_total = sum(v[0] for v in agg.values())
+    # dominant kernel = the GEMM launch class (layout, N, K; M varies with the batch's distinct-token count) with the most time
+    classes = {}
+    for name, a, s_, e_ in records:
+        if name == 'xnrs_gemm':
+            c = classes.setdefault((a[0], a[1], a[3], a[4]) if not a[0] else (a[0], a[1], a[2], a[3]), [0.0, 0, 0.0, 0])
+            c[0] += s_.elapsed_time(e_)
+            c[1] += 1
+            c[2] += 2.0 * a[2] * a[3] * a[4]
+            c[3] += a[4] if a[0] else a[2]
+    (d_ta, d_tb, d_1, d_2), (d_ms, d_n, d_flop, d_rows) = max(classes.items(), key=lambda kv: kv[1][0])
+    d_name = (f'gemm_tc_kernel<128> {"TN" if d_ta else "NT"} '
+              + (f'M={d_1} N={d_2} K~{d_rows // max(d_n, 1)} (fc1 weight gradient)' if d_ta
+                 else f'M~{d_rows // max(d_n, 1)} N={d_1} K={d_2} (title fc1 forward, tanh epilogue)'))
+    d_tflops = d_flop / (d_ms * 1e-3) / 1e12 if d_ms else None
     roofline = {
-        'kernel': 'gemm_simt_kernel (xnrs_gemm: fc1 / head / weight-gradient GEMMs)' if args.precision == 'fp32'
-                  else 'xnrs_gemm (tcgen05 path where taken)',
-        'bound': 'tensor', 'achieved': gemm_flop / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None,
-        'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
-        'frac': (gemm_flop / (gemm_ms * 1e-3) / 1e12 / pk['bf16_tflops_sustained']) if gemm_ms else None,
-        'traffic': None, 'peak_source': f'{pk_kind} (sustained bf16 GEMM; kernel timed inside a long step)',
-        'launches_timed': gemm_n, 'avg_launch_ms': gemm_ms / max(gemm_n, 1),
-        'share_of_step_kernel_time': gemm_ms / kernel_ms_total if kernel_ms_total else None,
+        'kernel': d_name if args.precision != 'fp32' else 'gemm_simt_kernel ' + d_name,
+        'bound': 'tensor', 'achieved': d_tflops, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
+        'frac': d_tflops / pk['bf16_tflops_sustained'] if d_tflops else None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of ONE such launch (ncu --set full, profiles/README.md): 472.7 MB read
+        # + 129.1 MB written at M=150 k rows = 4013 B/row, i.e. exactly the algorithmic A row (3072 B) + C row (1024 B)
+        'traffic': 4013.0 * (d_rows / max(d_n, 1)) if (not d_ta and args.precision != 'fp32') else None,
+        'peak_source': f'{pk_kind} (sustained bf16 GEMM; kernel timed inside a long step). The kernel computes in TF32 '
+                       f'(3 MMAs per product in the fp32-accurate 3xTF32 mode): its own ceiling is 1/6 of this bf16 peak',
+        'launches_timed': d_n, 'avg_launch_ms': d_ms / max(d_n, 1),
+        'all_gemm_tflops': gemm_flop / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None,
+        'gemm_share_of_step_kernel_time': gemm_ms / kernel_ms_total if kernel_ms_total else None,
         'top_entry_point_by_time': top[0], 'ms_per_step_with_event_hooks': ms_hooked / args.steps,
         'gemm_shapes_ms_per_step': {k: f'{v[0] / args.steps:.3f} ms, {v[2] / (v[0] * 1e-3) / 1e12:.1f} TF/s, {v[1] // args.steps}x'
                                     for k, v in sorted(shapes.items(), key=lambda kv: -kv[1][0])[:8]},

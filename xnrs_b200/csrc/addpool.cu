@@ -147,6 +147,84 @@ pool_bwd_kernel(const float *__restrict__ x, const int *__restrict__ x_rows, con
     }
 }
 
+// ---- warp-per-group forward (used when there are thousands of groups): no block barriers, one warp owns a title from
+// logits to pooled vector (measured 0.26 vs 0.33 ms at title level; the same idea was slower for the backward pass).
+// Valid for F <= 1024 and A <= 256 (register-resident per-lane slices); other shapes take the CTA-per-group kernels above.
+constexpr int WPB = 8;            // warps per CTA
+constexpr int FQ = 8;             // float4 accumulators per lane: F <= 32 * 4 * FQ = 1024
+constexpr int AQ = 8;             // hidden units per lane: A <= 32 * AQ = 256
+
+template <bool kPers>
+__global__ void __launch_bounds__(WPB * 32)
+pool_fwd_warp_kernel(const float *__restrict__ x, const int *__restrict__ x_rows, const float *__restrict__ mask,
+                     const float *__restrict__ hid, const float *__restrict__ w2, const float *__restrict__ b2,
+                     const float *__restrict__ qh, int rows_per_query, const int *__restrict__ seg, long long R, int Lmax,
+                     int F, int A, float *__restrict__ attn, float *__restrict__ pooled) {
+    extern __shared__ float sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *e = sm + warp * Lmax;
+    const int F4 = F >> 2;
+    const float4 *x4 = reinterpret_cast<const float4 *>(x);
+    const long long wid = (long long)blockIdx.x * WPB + warp, nw = (long long)gridDim.x * WPB;
+    float wreg[AQ];
+    if (!kPers) {
+#pragma unroll
+        for (int i = 0; i < AQ; ++i) wreg[i] = (lane + 32 * i < A) ? w2[lane + 32 * i] : 0.f;
+    }
+    for (long long r = wid; r < R; r += nw) {
+        const long long base = seg ? (long long)seg[r] : r * (long long)Lmax;
+        const int L = seg ? seg[r + 1] - seg[r] : Lmax;
+        if (kPers) {
+            const float *wv = qh + (r / rows_per_query) * A;
+#pragma unroll
+            for (int i = 0; i < AQ; ++i) wreg[i] = (lane + 32 * i < A) ? wv[lane + 32 * i] : 0.f;
+        }
+        const float bias = kPers ? 0.f : b2[0];
+        float tot = 0.f;
+        for (int l = 0; l < L; ++l) {
+            const float mval = mask ? mask[base + l] : 1.f;
+            float ev = 0.f;
+            if (mval != 0.f) {
+                const float *hrow = hid + (base + l) * A;
+                float acc = 0.f;
+#pragma unroll
+                for (int i = 0; i < AQ; ++i)
+                    if (lane + 32 * i < A) acc = fmaf(hrow[lane + 32 * i], wreg[i], acc);
+                acc = warp_sum(acc);
+                ev = expf(acc + bias) * mval;
+            }
+            if (lane == 0) e[l] = ev;
+            tot += ev;
+        }
+        __syncwarp();
+        const float denom = tot + 1e-8f;
+        for (int l = lane; l < L; l += 32) attn[base + l] = e[l] / denom;
+        float4 acc[FQ];
+#pragma unroll
+        for (int c = 0; c < FQ; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int l = 0; l < L; ++l) {
+            const float a = e[l] / denom;
+            if (a == 0.f) continue;
+            const long long row = x_rows ? (long long)x_rows[base + l] : base + l;
+#pragma unroll
+            for (int c = 0; c < FQ; ++c) {
+                const int col = lane + 32 * c;
+                if (col < F4) {
+                    const float4 v = ldg_stream(x4 + row * F4 + col);
+                    acc[c].x = fmaf(a, v.x, acc[c].x); acc[c].y = fmaf(a, v.y, acc[c].y);
+                    acc[c].z = fmaf(a, v.z, acc[c].z); acc[c].w = fmaf(a, v.w, acc[c].w);
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < FQ; ++c) {
+            const int col = lane + 32 * c;
+            if (col < F4) reinterpret_cast<float4 *>(pooled)[r * F4 + col] = acc[c];
+        }
+        __syncwarp();
+    }
+}
+
 __global__ void meanpool_fwd_kernel(const float *__restrict__ x, const float *__restrict__ mask, long long R, int L,
                                     int F, float *__restrict__ pooled) {
     for (long long r = blockIdx.x; r < R; r += gridDim.x) {
@@ -174,6 +252,14 @@ static unsigned pool_grid(long long R) {
     return (unsigned)(R < cap ? (R < 1 ? 1 : R) : cap);
 }
 
+// a warp per group needs many groups to fill the machine (title level: thousands); few long groups (user level: one per
+// impression) keep a whole CTA per group
+static bool warp_path(long long R, int L, int F, int A) { return R >= 4096 && F <= 32 * 4 * FQ && A <= 32 * AQ && L <= 1024; }
+static unsigned warp_grid(long long R) {
+    long long blocks = cdiv(R, WPB), cap = 8LL * num_sms();
+    return (unsigned)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
 static int check_pool(long long R, int L, int F, int A, const float *x) {
     if (R < 0 || L <= 0 || F <= 0 || A <= 0) return fail(XNRS_ERR_ARG, "%s: bad sizes", "pool");
     if (F % 4 != 0) return fail(XNRS_ERR_ARG, "%s: F must be a multiple of 4", "pool");
@@ -191,8 +277,12 @@ extern "C" int xnrs_addpool_fwd(const float *x, const int *x_rows, const float *
     if (int e = check_pool(R, L, F, A, x)) return e;
     if (R == 0) return XNRS_OK;
     XNRS_REQUIRE(x && hid && w2 && b2 && attn && pooled, "null pointer");
-    pool_fwd_kernel<false><<<pool_grid(R), POOL_THREADS, L * sizeof(float), STREAM(st)>>>(
-        x, x_rows, mask, hid, w2, b2, nullptr, 1, seg, R, L, F, A, attn, pooled);
+    if (warp_path(R, L, F, A))
+        pool_fwd_warp_kernel<false><<<warp_grid(R), WPB * 32, WPB * L * sizeof(float), STREAM(st)>>>(
+            x, x_rows, mask, hid, w2, b2, nullptr, 1, seg, R, L, F, A, attn, pooled);
+    else
+        pool_fwd_kernel<false><<<pool_grid(R), POOL_THREADS, L * sizeof(float), STREAM(st)>>>(
+            x, x_rows, mask, hid, w2, b2, nullptr, 1, seg, R, L, F, A, attn, pooled);
     XNRS_LAUNCHED();
     return XNRS_OK;
 }
@@ -207,7 +297,7 @@ extern "C" int xnrs_addpool_bwd(const float *x, const int *x_rows, const float *
     XNRS_REQUIRE(x && hid && w2 && attn && d_pooled && d_hid && d_w2 && d_b2, "null pointer");
     XNRS_REQUIRE(!(d_x && x_rows), "d_x is only defined for dense x");
     pool_bwd_kernel<false><<<pool_grid(R), POOL_THREADS, (2 * L + A) * sizeof(float), STREAM(st)>>>(
-        x, x_rows, hid, w2, nullptr, 1, attn, d_pooled, d_attn, seg, R, L, F, A, d_hid, d_w2, d_b2, nullptr, d_x);
+            x, x_rows, hid, w2, nullptr, 1, attn, d_pooled, d_attn, seg, R, L, F, A, d_hid, d_w2, d_b2, nullptr, d_x);
     XNRS_LAUNCHED();
     return XNRS_OK;
 }
@@ -218,8 +308,12 @@ extern "C" int xnrs_perspool_fwd(const float *x, const int *x_rows, const float 
     if (int e = check_pool(R, L, F, A, x)) return e;
     if (R == 0) return XNRS_OK;
     XNRS_REQUIRE(x && hid && qh && attn && pooled && rows_per_query > 0, "null pointer");
-    pool_fwd_kernel<true><<<pool_grid(R), POOL_THREADS, L * sizeof(float), STREAM(st)>>>(
-        x, x_rows, mask, hid, nullptr, nullptr, qh, rows_per_query, seg, R, L, F, A, attn, pooled);
+    if (warp_path(R, L, F, A))
+        pool_fwd_warp_kernel<true><<<warp_grid(R), WPB * 32, WPB * L * sizeof(float), STREAM(st)>>>(
+            x, x_rows, mask, hid, nullptr, nullptr, qh, rows_per_query, seg, R, L, F, A, attn, pooled);
+    else
+        pool_fwd_kernel<true><<<pool_grid(R), POOL_THREADS, L * sizeof(float), STREAM(st)>>>(
+            x, x_rows, mask, hid, nullptr, nullptr, qh, rows_per_query, seg, R, L, F, A, attn, pooled);
     XNRS_LAUNCHED();
     return XNRS_OK;
 }
@@ -234,8 +328,8 @@ extern "C" int xnrs_perspool_bwd(const float *x, const int *x_rows, const float 
     XNRS_REQUIRE(x && hid && qh && attn && d_pooled && d_hid && d_qh && rows_per_query > 0, "null pointer");
     XNRS_REQUIRE(!(d_x && x_rows), "d_x is only defined for dense x");
     pool_bwd_kernel<true><<<pool_grid(R), POOL_THREADS, (2 * L + A) * sizeof(float), STREAM(st)>>>(
-        x, x_rows, hid, nullptr, qh, rows_per_query, attn, d_pooled, nullptr, seg, R, L, F, A, d_hid, nullptr, nullptr,
-        d_qh, d_x);
+            x, x_rows, hid, nullptr, qh, rows_per_query, attn, d_pooled, nullptr, seg, R, L, F, A, d_hid, nullptr,
+            nullptr, d_qh, d_x);
     XNRS_LAUNCHED();
     return XNRS_OK;
 }

@@ -377,15 +377,15 @@ def main():
     classes = {}
     for name, a, s_, e_ in records:
         if name == 'xnrs_gemm':
-            c = classes.setdefault((a[0], a[1], a[3], a[4]) if not a[0] else (a[0], a[1], a[2], a[3]), [0.0, 0, 0.0, 0])
+            c = classes.setdefault((a[0], a[1], a[3], a[4], a[8]) if not a[0] else (a[0], a[1], a[2], a[3], a[8]), [0.0, 0, 0.0, 0])
             c[0] += s_.elapsed_time(e_)
             c[1] += 1
             c[2] += 2.0 * a[2] * a[3] * a[4]
             c[3] += a[4] if a[0] else a[2]
-    (d_ta, d_tb, d_1, d_2), (d_ms, d_n, d_flop, d_rows) = max(classes.items(), key=lambda kv: kv[1][0])
+    (d_ta, d_tb, d_1, d_2, d_act), (d_ms, d_n, d_flop, d_rows) = max(classes.items(), key=lambda kv: kv[1][0])
     d_name = (f'gemm_tc_kernel<128> {"TN" if d_ta else "NT"} '
               + (f'M={d_1} N={d_2} K~{d_rows // max(d_n, 1)} (fc1 weight gradient)' if d_ta
-                 else f'M~{d_rows // max(d_n, 1)} N={d_1} K={d_2} (title fc1 forward, tanh epilogue)'))
+                 else f'M~{d_rows // max(d_n, 1)} N={d_1} K={d_2} ' + ('(title fc1 forward, tanh epilogue)' if d_act == 2 else '(forward)')))
     d_tflops = d_flop / (d_ms * 1e-3) / 1e12 if d_ms else None
     roofline = {
         'kernel': d_name if args.precision != 'fp32' else 'gemm_simt_kernel ' + d_name,

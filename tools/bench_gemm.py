@@ -6,6 +6,8 @@ from xnrs_b200 import kernels as K
 
 SHAPES = [  # name, M, N, K, trans_a, trans_b
     ('fc1 fwd   (tokens x 256 <- 768)', 262144, 256, 768, False, True),
+    ('fc1 fwd+tanh (157306 x 256 <- 768)', 157306, 256, 768, False, True, 'tanh'),
+    ('fc1 fwd      (157306 x 256 <- 768)', 157306, 256, 768, False, True),
     ('head fwd  (titles x 256 <- 768)', 56320, 256, 768, False, True),
     ('qkv fwd   (tokens x 768 <- 768)', 262144, 768, 768, False, True),
     ('dW fc1    (256 x 768, K=tokens)', 256, 768, 262144, True, False),
@@ -28,14 +30,16 @@ def timeit(fn, n=10):
 
 ONLY = os.environ.get('SHAPE_IDX')
 PRECS = os.environ.get('PRECS', 'fp32,tf32x3,tf32').split(',')
-for name, M, N, Kd, ta, tb in (SHAPES if ONLY is None else [SHAPES[int(ONLY)]]):
+for name, M, N, Kd, ta, tb, *extra in (SHAPES if ONLY is None else [SHAPES[int(ONLY)]]):
+    act = K.ACT_TANH if extra else K.ACT_NONE
+    bias = torch.randn(N, device='cuda') if extra else None
     a = torch.randn((Kd, M) if ta else (M, Kd), device='cuda')
     b = torch.randn((N, Kd) if tb else (Kd, N), device='cuda')
     out = torch.empty(M, N, device='cuda')
     row = {'shape': name}
     for prec in PRECS:
         with K.precision(prec):
-            ms = timeit(lambda: K.gemm(a, b, trans_a=ta, trans_b=tb, out=out))
+            ms = timeit(lambda: K.gemm(a, b, trans_a=ta, trans_b=tb, out=out, bias=bias, act=act))
         row[prec] = f'{ms:.3f} ms {2.0 * M * N * Kd / ms / 1e9:.1f} TF/s'
     torch.backends.cuda.matmul.allow_tf32 = False
     A, B = (a.T if ta else a), (b.T if tb else b)

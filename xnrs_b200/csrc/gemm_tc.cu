@@ -8,8 +8,10 @@
 //           (hi*hi + lo*hi + hi*lo; the dropped lo*lo term is ~2^-22 relative).  L2 traffic stays 1x.
 //   TF32    single pass on the raw fp32 tiles (tensor core reads the top 19 bits).
 //
-// CTA = 3 warpgroups: {warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc)} | warps 4-7 splitters | warps 8-11
-// epilogue; setmaxnreg moves registers from the first two warpgroups to the epilogue (a full 128-column row per thread)
+// CTA = 4 warpgroups: {warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc)} | warps 4-11 splitters | warps 12-15
+// epilogue (a full 128-column row per thread).  The splitters were the critical path of the 3-stage pipeline with 4 warps
+// (ncu source page: the MMA issuer spun on split_bar, the producer on empty_bar): 8 warps, shared-space 128-bit
+// loads/stores with all loads of a stage in flight, and one mbarrier arrival per warp.
 // Tile 128 x 128 x 32 (UMMA M=128, N=128, K=8 per instruction, 128-byte swizzled rows), 3 (x3) or 6 (x1)
 // smem stages, 2 TMEM accumulator stages (x2 accumulators: main + correction = all 512 columns) so the epilogue of
 // tile i overlaps the main loop of tile i+1.
@@ -19,15 +21,14 @@
 #include <stdlib.h>
 #include <string.h>
 
-#define XNRS_SPLIT_TRUNC 1
-
 #include "gemm.cuh"
 
 namespace xnrs {
 
 constexpr int TBM = 128, TBK = 32;
 constexpr int SMEM_DATA = 192 * 1024;
-constexpr int TC_THREADS = 384;          // 3 warpgroups: {TMA, MMA, -, -} | 4 splitter warps | 4 epilogue warps
+constexpr int TC_THREADS = 512;          // 4 warpgroups: {TMA, MMA, -, -} | 8 splitter warps | 4 epilogue warps
+constexpr int SPLIT_WARPS = 8, SPLIT_THREADS = SPLIT_WARPS * 32, EPI_WARP0 = 4 + SPLIT_WARPS;
 constexpr int MAX_STAGES = 6;
 constexpr long long KCHUNK = 2048;   // longest K run accumulated inside the tensor core: its fp32 accumulation truncates, so the
                                      // error grows ~linearly with K; longer reductions are split and summed with IEEE fp32 atomics
@@ -113,6 +114,16 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
 // UMMA shared-memory descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64))
 // MN-major 32-bit (tf32) operands must use the 32-byte-atom variant SWIZZLE_128B_BASE32B=1 (Swizzle<2,5,2>, 4 k-rows
@@ -120,6 +131,110 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | ((uint64_t)layout << 61);
+}
+
+
+// tanh for the tensor-core epilogues: |x| < 0.25 -> odd Taylor polynomial (abs err < 3e-9), otherwise
+// 1 - 2 / (1 + 2^(2 x log2 e)) with ex2.approx / rcp.approx (abs err ~2e-7, saturates to +-1).  libm tanhf costs ~60
+// dependent instructions per element, which made the epilogue of the fc1 GEMM (128 elements per thread per tile) longer
+// than its main loop; this is 14 branch-free instructions and stays far inside the 1e-4 parity bar.
+__device__ __forceinline__ float tanh_fast(float x) {
+    const float x2 = x * x;
+    float pl = fmaf(x2, 62.f / 2835.f, -17.f / 315.f);
+    pl = fmaf(pl, x2, 2.f / 15.f);
+    pl = fmaf(pl, x2, -1.f / 3.f);
+    pl = fmaf(pl * x2, x, x);
+    float t, rc;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(x * 2.885390081777927f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(t + 1.f));
+    return fabsf(x) < 0.25f ? pl : fmaf(-2.f, rc, 1.f);
+}
+
+// epilogue of one thread: 32 consecutive output columns [col0, col0 + 32) of its row
+template <int ACT>
+__device__ __forceinline__ void epi_fast32(float (&r)[32], const TcArgs &p, float *crow, const float *arow, long long col0,
+                                           bool bias_vec) {
+#pragma unroll
+    for (int j0 = 0; j0 < 32; j0 += 4) {
+        float x[4] = {r[j0], r[j0 + 1], r[j0 + 2], r[j0 + 3]};
+        if (p.bias) {
+            if (bias_vec) {
+                const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + col0 + j0));
+                x[0] += b.x; x[1] += b.y; x[2] += b.z; x[3] += b.w;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) x[e] += __ldg(p.bias + col0 + j0 + e);
+            }
+        }
+        if (ACT == XNRS_ACT_RELU) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e], 0.f);
+        } else if (ACT == XNRS_ACT_TANH) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[e] = tanh_fast(x[e]);
+        } else if (ACT == XNRS_ACT_RELU_MASK) {
+            const float4 a = *reinterpret_cast<const float4 *>(arow + col0 + j0);
+            x[0] = a.x > 0.f ? x[0] : 0.f; x[1] = a.y > 0.f ? x[1] : 0.f;
+            x[2] = a.z > 0.f ? x[2] : 0.f; x[3] = a.w > 0.f ? x[3] : 0.f;
+        }
+        float4 *dst = reinterpret_cast<float4 *>(crow + col0 + j0);
+        if (p.accumulate) {
+            const float4 o = *dst;
+            x[0] += o.x; x[1] += o.y; x[2] += o.z; x[3] += o.w;
+        }
+        *dst = make_float4(x[0], x[1], x[2], x[3]);
+    }
+}
+
+__device__ __forceinline__ void epi_store32(float (&r)[32], const TcArgs &p, float *crow, const float *arow, long long col0,
+                                            long long split, bool vec_ok, bool bias_vec) {
+    if (vec_ok && p.split_k == 1 && col0 + 32 <= p.N) {          // full, aligned chunk: no per-element bounds checks
+        switch (p.act) {
+            case XNRS_ACT_RELU: epi_fast32<XNRS_ACT_RELU>(r, p, crow, arow, col0, bias_vec); break;
+            case XNRS_ACT_TANH: epi_fast32<XNRS_ACT_TANH>(r, p, crow, arow, col0, bias_vec); break;
+            case XNRS_ACT_RELU_MASK: epi_fast32<XNRS_ACT_RELU_MASK>(r, p, crow, arow, col0, bias_vec); break;
+            default: epi_fast32<XNRS_ACT_NONE>(r, p, crow, arow, col0, bias_vec); break;
+        }
+        return;
+    }
+#pragma unroll
+    for (int j0 = 0; j0 < 32; j0 += 4) {
+        const long long col = col0 + j0;
+        if (col >= p.N) break;
+        float x[4] = {r[j0], r[j0 + 1], r[j0 + 2], r[j0 + 3]};
+        const int nv = (int)min((long long)4, p.N - col);
+        if (p.split_k > 1) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (e < nv) {
+                    if (split == 0 && p.bias) x[e] += p.bias[col + e];
+                    atomicAdd(crow + col + e, x[e]);
+                }
+            }
+            continue;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (e < nv) {
+                if (p.bias) x[e] += p.bias[col + e];
+                if (p.act == XNRS_ACT_RELU) x[e] = fmaxf(x[e], 0.f);
+                else if (p.act == XNRS_ACT_TANH) x[e] = tanh_fast(x[e]);
+                else if (p.act == XNRS_ACT_RELU_MASK) x[e] = (arow[col + e] > 0.f) ? x[e] : 0.f;
+            }
+        }
+        if (vec_ok && nv == 4) {
+            float4 *dst = reinterpret_cast<float4 *>(crow + col);
+            if (p.accumulate) {
+                const float4 o = *dst;
+                x[0] += o.x; x[1] += o.y; x[2] += o.z; x[3] += o.w;
+            }
+            *dst = make_float4(x[0], x[1], x[2], x[3]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (e < nv) crow[col + e] = p.accumulate ? crow[col + e] + x[e] : x[e];
+        }
+    }
 }
 
 struct StageRing {
@@ -153,7 +268,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&split_bar[s], 128);
+            mbar_init(&split_bar[s], SPLIT_WARPS);
             mbar_init(&empty_bar[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -278,40 +393,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
     } else if (warp < 4) {
         // idle warps of warpgroup 0
-    } else if (warp < 8) {
+    } else if (warp < EPI_WARP0) {
         // ===================== splitters: lo = x - hi for every element of the stage, in shared memory ================
-        // XNRS_SPLIT_TRUNC: hi is what the tensor core itself reads from the raw fp32 word (the top 19 bits), so only lo is
-        // written (one shared-memory store less per element); otherwise hi = rna_tf32(x) is written back as well
+        // hi is what the tensor core itself reads from the raw fp32 word (the top 19 bits: it truncates), so only lo is
+        // written.  All loads of a thread's share of the stage are issued before the first store (latency overlap);
+        // each warp makes its writes visible to the async proxy and arrives once.
         if (passes == 3) {
-            const int tid = threadIdx.x - 128;         // 0..127
+            const int tid = threadIdx.x - 128;         // 0..SPLIT_THREADS-1
+            constexpr int ITERS = HALF / 16 / SPLIT_THREADS;
+            static_assert(HALF % (16 * SPLIT_THREADS) == 0, "stage must divide evenly among the splitter threads");
             StageRing r;
             for (long long t = blockIdx.x; t < total; t += gridDim.x) {
                 const long long split = t / tiles_mn;
                 const long long kbeg = split * p.k_per_split, kend = min(p.K, kbeg + p.k_per_split);
                 for (long long k0 = kbeg; k0 < kend; k0 += TBK) {
                     mbar_wait(&full_bar[r.stage], r.phase);
-                    float4 *hi = reinterpret_cast<float4 *>(tileA(r.stage));      // A and B tiles are contiguous
-                    float4 *lo = reinterpret_cast<float4 *>(tileA(r.stage) + HALF);
-#pragma unroll 4
-                    for (int i = tid; i < HALF / 16; i += 128) {
-                        float4 v = hi[i], h, l;
-#ifdef XNRS_SPLIT_TRUNC
-                        h = make_float4(__uint_as_float(__float_as_uint(v.x) & 0xffffe000u), __uint_as_float(__float_as_uint(v.y) & 0xffffe000u),
-                                        __uint_as_float(__float_as_uint(v.z) & 0xffffe000u), __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
-#else
-                        uint32_t t0, t1, t2, t3;
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t0) : "f"(v.x));
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t1) : "f"(v.y));
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t2) : "f"(v.z));
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t3) : "f"(v.w));
-                        h = make_float4(__uint_as_float(t0), __uint_as_float(t1), __uint_as_float(t2), __uint_as_float(t3));
-                        hi[i] = h;
-#endif
-                        l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-                        lo[i] = l;
-                    }
+                    const uint32_t hi = smem_u32(tileA(r.stage)) + tid * 16;      // A and B tiles are contiguous
+                    float4 v[ITERS];
+#pragma unroll
+                    for (int i = 0; i < ITERS; ++i) v[i] = lds128(hi + i * (SPLIT_THREADS * 16));
+#pragma unroll
+                    for (int i = 0; i < ITERS; ++i)
+                        sts128(hi + HALF + i * (SPLIT_THREADS * 16),
+                               make_float4(tf32_lo(v[i].x), tf32_lo(v[i].y), tf32_lo(v[i].z), tf32_lo(v[i].w)));
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (MMA)
-                    mbar_arrive(&split_bar[r.stage]);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&split_bar[r.stage]);
                     r.advance(stages);
                 }
             }
@@ -319,7 +426,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     } else {
         // ===================== epilogue: TMEM -> registers -> bias/act -> global =====================
         const int q = warp & 3;                         // TMEM lane quarter this warp may access
-        const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+        const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
+                            (!p.aux || (reinterpret_cast<uintptr_t>(p.aux) & 15) == 0);
+        const bool bias_vec = (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0;
         StageRing acc;
         for (long long t = blockIdx.x; t < total; t += gridDim.x) {
             const long long split = t / tiles_mn, mn = t - split * tiles_mn;
@@ -341,44 +450,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     for (int j = 0; j < 32; ++j) r[j] += corr[j];
                 }
                 if (row >= p.M) continue;
-#pragma unroll
-                for (int j0 = 0; j0 < 32; j0 += 4) {
-                    const long long col = n0 + c * 32 + j0;
-                    if (col >= p.N) break;
-                    float x[4] = {r[j0], r[j0 + 1], r[j0 + 2], r[j0 + 3]};
-                    const int nv = (int)min((long long)4, p.N - col);
-                    if (p.split_k > 1) {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            if (e < nv) {
-                                if (split == 0 && p.bias) x[e] += p.bias[col + e];
-                                atomicAdd(crow + col + e, x[e]);
-                            }
-                        }
-                        continue;
-                    }
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        if (e < nv) {
-                            if (p.bias) x[e] += p.bias[col + e];
-                            if (p.act == XNRS_ACT_RELU) x[e] = fmaxf(x[e], 0.f);
-                            else if (p.act == XNRS_ACT_TANH) x[e] = tanhf(x[e]);
-                            else if (p.act == XNRS_ACT_RELU_MASK) x[e] = (arow[col + e] > 0.f) ? x[e] : 0.f;
-                        }
-                    }
-                    if (vec_ok && nv == 4) {
-                        float4 *dst = reinterpret_cast<float4 *>(crow + col);
-                        if (p.accumulate) {
-                            const float4 o = *dst;
-                            x[0] += o.x; x[1] += o.y; x[2] += o.z; x[3] += o.w;
-                        }
-                        *dst = make_float4(x[0], x[1], x[2], x[3]);
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            if (e < nv) crow[col + e] = p.accumulate ? crow[col + e] + x[e] : x[e];
-                    }
-                }
+                epi_store32(r, p, crow, arow, n0 + c * 32, split, vec_ok, bias_vec);
             }
             tc_fence_before();
             mbar_arrive(&tempty_bar[acc.stage]);
@@ -454,7 +526,9 @@ __device__ __forceinline__ void tc2_mma_tf32(uint32_t d_tmem, uint64_t adesc, ui
 
 constexpr int T2N = 256;       // tile columns of the pair
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+constexpr int TC2_THREADS = 384;       // CTA-pair kernel: {TMA, MMA, relay, -} | 4 splitter warps | 4 epilogue warps
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcArgs p) {
     constexpr int TILE = TBM * TBK * 4, HALF = 2 * TILE;          // per CTA: [A hi][B-half hi] | [A lo][B-half lo]
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -612,7 +686,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     } else {
         // ===================== epilogue: this CTA's 128 rows of the pair's tile =====================
         const int q = warp & 3;
-        const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+        const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
+                            (!p.aux || (reinterpret_cast<uintptr_t>(p.aux) & 15) == 0);
+        const bool bias_vec = (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0;
         StageRing acc;
         for (long long t = pair; t < total; t += npairs) {
             const long long split = t / tiles_mn, mn = t - split * tiles_mn;
@@ -634,44 +710,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     for (int j = 0; j < 32; ++j) r[j] += corr[j];
                 }
                 if (row >= p.M) continue;
-#pragma unroll
-                for (int j0 = 0; j0 < 32; j0 += 4) {
-                    const long long col = n0 + c * 32 + j0;
-                    if (col >= p.N) break;
-                    float x[4] = {r[j0], r[j0 + 1], r[j0 + 2], r[j0 + 3]};
-                    const int nv = (int)min((long long)4, p.N - col);
-                    if (p.split_k > 1) {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            if (e < nv) {
-                                if (split == 0 && p.bias) x[e] += p.bias[col + e];
-                                atomicAdd(crow + col + e, x[e]);
-                            }
-                        }
-                        continue;
-                    }
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        if (e < nv) {
-                            if (p.bias) x[e] += p.bias[col + e];
-                            if (p.act == XNRS_ACT_RELU) x[e] = fmaxf(x[e], 0.f);
-                            else if (p.act == XNRS_ACT_TANH) x[e] = tanhf(x[e]);
-                            else if (p.act == XNRS_ACT_RELU_MASK) x[e] = (arow[col + e] > 0.f) ? x[e] : 0.f;
-                        }
-                    }
-                    if (vec_ok && nv == 4) {
-                        float4 *dst = reinterpret_cast<float4 *>(crow + col);
-                        if (p.accumulate) {
-                            const float4 o = *dst;
-                            x[0] += o.x; x[1] += o.y; x[2] += o.z; x[3] += o.w;
-                        }
-                        *dst = make_float4(x[0], x[1], x[2], x[3]);
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            if (e < nv) crow[col + e] = p.accumulate ? crow[col + e] + x[e] : x[e];
-                    }
-                }
+                epi_store32(r, p, crow, arow, n0 + c * 32, split, vec_ok, bias_vec);
             }
             tc_fence_before();
             mbar_arrive_cluster(map_to_cta(smem_u32(&tempty_bar[acc.stage]), 0));
@@ -809,7 +848,7 @@ int gemm_tensorcore(const GemmArgs &a, int precision, cudaStream_t st, int *stat
     unsigned grid = (unsigned)(total < num_sms() ? total : num_sms());
     if (use2) {
         const long long pairs = total < num_sms() / 2 ? total : num_sms() / 2;
-        gemm_tc2_kernel<<<(unsigned)(2 * pairs), TC_THREADS, smem_bytes, st>>>(mapA, mapB, p);
+        gemm_tc2_kernel<<<(unsigned)(2 * pairs), TC2_THREADS, smem_bytes, st>>>(mapA, mapB, p);
     } else if (BN == 256) gemm_tc_kernel<256><<<grid, TC_THREADS, smem_bytes, st>>>(mapA, mapB, p);
     else gemm_tc_kernel<128><<<grid, TC_THREADS, smem_bytes, st>>>(mapA, mapB, p);
     g_launches.fetch_add(1, std::memory_order_relaxed);

@@ -28,7 +28,8 @@ int xnrs_version(void);
 const char *xnrs_last_error(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 long long xnrs_launch_count(void);
-/* tuning switches: "gemm_2cta" (0/1) routes wide tensor-core GEMMs to the cta_group::2 CTA-pair kernel */
+/* tuning switches: "gemm_2cta" routes wide tensor-core GEMMs to the cta_group::2 CTA-pair kernel:
+   0 = never, 1 = wherever legal, -1 = default policy (the fp32-accurate 3xTF32 mode only) */
 int xnrs_set_option(const char *name, int value);
 /* 1 when the running device is compute capability 10.x */
 int xnrs_device_is_sm100(void);

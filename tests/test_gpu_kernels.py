@@ -460,7 +460,7 @@ def test_tensor_core_gemm_tma_gather(prec, tol):
 @pytest.mark.parametrize('prec,tol', [('tf32x3', 5e-5), ('tf32', 3e-3)])
 @pytest.mark.parametrize('ta,tb', [(0, 1), (1, 0), (0, 0), (1, 1)])
 def test_tensor_core_gemm_cta_pair_kernel(prec, tol, ta, tb):
-    """the cta_group::2 (CTA-pair, 256x256 tile) variant of the tcgen05 GEMM — opt-in, kept correct for round 2"""
+    """the cta_group::2 (CTA-pair, 256x256 tile) variant of the tcgen05 GEMM — default for 3xTF32, forced here for both precisions"""
     from xnrs_b200 import _lib
     lib = _lib.lib()
     assert lib.xnrs_set_option(b'gemm_2cta', 1) == 0
@@ -474,4 +474,4 @@ def test_tensor_core_gemm_cta_pair_kernel(prec, tol, ta, tb):
                 got = K.gemm(cu(a), cu(b), trans_a=bool(ta), trans_b=bool(tb), bias=cu(bias), act=K.ACT_RELU)
             assert_close(got, torch.relu(want).float(), tol, f'2-CTA gemm {prec}')
     finally:
-        lib.xnrs_set_option(b'gemm_2cta', 0)
+        lib.xnrs_set_option(b'gemm_2cta', -1)

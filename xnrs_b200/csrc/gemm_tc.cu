@@ -27,6 +27,7 @@ namespace xnrs {
 
 constexpr int TBM = 128, TBK = 32;
 constexpr int SMEM_DATA = 192 * 1024;
+constexpr int SMEM_EPI = 8 * 4096;       // per-epilogue-warp transpose staging (coalesced stores)
 constexpr int TC_THREADS = 512;          // 4 warpgroups: {TMA, MMA, -, -} | 8 splitter warps | 4 epilogue warps
 constexpr int SPLIT_WARPS = 8, SPLIT_THREADS = SPLIT_WARPS * 32, EPI_WARP0 = 4 + SPLIT_WARPS;
 constexpr int MAX_STAGES = 6;
@@ -150,21 +151,43 @@ __device__ __forceinline__ float tanh_fast(float x) {
     return fabsf(x) < 0.25f ? pl : fmaf(-2.f, rc, 1.f);
 }
 
-// epilogue of one thread: 32 consecutive output columns [col0, col0 + 32) of its row
+// Coalesced epilogue.  tcgen05.ld hands lane l row l of a 32-row x 32-column accumulator block; storing that directly
+// makes every warp store touch 32 different 128-byte lines (16 bytes each), and the LSU then needs ~32 cycles per
+// instruction: measured, the epilogue (not the tensor pipe) bounded every GEMM with K <= 768.  So the raw accumulators are
+// transposed through a 4 KB per-warp staging buffer (16-byte chunks XOR-swizzled by row: conflict-free both ways) and all
+// epilogue math + global traffic happens in the transposed layout: lane = (row 4i + l/8, columns 4(l%8)..+3), i.e.
+// 4 rows x 128 contiguous bytes per instruction for C, bias, the ReLU mask and the accumulate read.
 template <int ACT>
-__device__ __forceinline__ void epi_fast32(float (&r)[32], const TcArgs &p, float *crow, const float *arow, long long col0,
-                                           bool bias_vec) {
+__device__ __forceinline__ void epi_rows(uint32_t stage, const TcArgs &p, long long row0, long long col0, long long split,
+                                         int lane, bool vec_ok, bool bias_vec) {
+    const int sub = lane >> 3, ch = lane & 7;
+    const long long col = col0 + 4 * ch;
+    if (col >= p.N) return;
+    const int nv = (int)min((long long)4, p.N - col);
+    float b[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p.bias && (p.split_k == 1 || split == 0)) {
+        if (bias_vec && nv == 4) {
+            const float4 t = __ldg(reinterpret_cast<const float4 *>(p.bias + col));
+            b[0] = t.x; b[1] = t.y; b[2] = t.z; b[3] = t.w;
+        } else {
 #pragma unroll
-    for (int j0 = 0; j0 < 32; j0 += 4) {
-        float x[4] = {r[j0], r[j0 + 1], r[j0 + 2], r[j0 + 3]};
-        if (p.bias) {
-            if (bias_vec) {
-                const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + col0 + j0));
-                x[0] += b.x; x[1] += b.y; x[2] += b.z; x[3] += b.w;
-            } else {
+            for (int e = 0; e < 4; ++e)
+                if (e < nv) b[e] = __ldg(p.bias + col + e);
+        }
+    }
 #pragma unroll
-                for (int e = 0; e < 4; ++e) x[e] += __ldg(p.bias + col0 + j0 + e);
-            }
+    for (int i = 0; i < 8; ++i) {
+        const int rr = 4 * i + sub;
+        const long long row = row0 + rr;
+        const float4 v = lds128(stage + rr * 128 + ((ch ^ (rr & 7)) << 4));
+        if (row >= p.M) continue;
+        float x[4] = {v.x + b[0], v.y + b[1], v.z + b[2], v.w + b[3]};
+        float *dst = p.C + row * p.ldc + col;
+        if (p.split_k > 1) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (e < nv) atomicAdd(dst + e, x[e]);
+            continue;
         }
         if (ACT == XNRS_ACT_RELU) {
 #pragma unroll
@@ -172,69 +195,44 @@ __device__ __forceinline__ void epi_fast32(float (&r)[32], const TcArgs &p, floa
         } else if (ACT == XNRS_ACT_TANH) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) x[e] = tanh_fast(x[e]);
-        } else if (ACT == XNRS_ACT_RELU_MASK) {
-            const float4 a = *reinterpret_cast<const float4 *>(arow + col0 + j0);
-            x[0] = a.x > 0.f ? x[0] : 0.f; x[1] = a.y > 0.f ? x[1] : 0.f;
-            x[2] = a.z > 0.f ? x[2] : 0.f; x[3] = a.w > 0.f ? x[3] : 0.f;
         }
-        float4 *dst = reinterpret_cast<float4 *>(crow + col0 + j0);
-        if (p.accumulate) {
-            const float4 o = *dst;
-            x[0] += o.x; x[1] += o.y; x[2] += o.z; x[3] += o.w;
-        }
-        *dst = make_float4(x[0], x[1], x[2], x[3]);
-    }
-}
-
-__device__ __forceinline__ void epi_store32(float (&r)[32], const TcArgs &p, float *crow, const float *arow, long long col0,
-                                            long long split, bool vec_ok, bool bias_vec) {
-    if (vec_ok && p.split_k == 1 && col0 + 32 <= p.N) {          // full, aligned chunk: no per-element bounds checks
-        switch (p.act) {
-            case XNRS_ACT_RELU: epi_fast32<XNRS_ACT_RELU>(r, p, crow, arow, col0, bias_vec); break;
-            case XNRS_ACT_TANH: epi_fast32<XNRS_ACT_TANH>(r, p, crow, arow, col0, bias_vec); break;
-            case XNRS_ACT_RELU_MASK: epi_fast32<XNRS_ACT_RELU_MASK>(r, p, crow, arow, col0, bias_vec); break;
-            default: epi_fast32<XNRS_ACT_NONE>(r, p, crow, arow, col0, bias_vec); break;
-        }
-        return;
-    }
-#pragma unroll
-    for (int j0 = 0; j0 < 32; j0 += 4) {
-        const long long col = col0 + j0;
-        if (col >= p.N) break;
-        float x[4] = {r[j0], r[j0 + 1], r[j0 + 2], r[j0 + 3]};
-        const int nv = (int)min((long long)4, p.N - col);
-        if (p.split_k > 1) {
+        if (vec_ok && nv == 4) {
+            if (ACT == XNRS_ACT_RELU_MASK) {
+                const float4 a = *reinterpret_cast<const float4 *>(p.aux + row * p.ldc + col);
+                x[0] = a.x > 0.f ? x[0] : 0.f; x[1] = a.y > 0.f ? x[1] : 0.f;
+                x[2] = a.z > 0.f ? x[2] : 0.f; x[3] = a.w > 0.f ? x[3] : 0.f;
+            }
+            if (p.accumulate) {
+                const float4 o = *reinterpret_cast<const float4 *>(dst);
+                x[0] += o.x; x[1] += o.y; x[2] += o.z; x[3] += o.w;
+            }
+            *reinterpret_cast<float4 *>(dst) = make_float4(x[0], x[1], x[2], x[3]);
+        } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 if (e < nv) {
-                    if (split == 0 && p.bias) x[e] += p.bias[col + e];
-                    atomicAdd(crow + col + e, x[e]);
+                    if (ACT == XNRS_ACT_RELU_MASK) x[e] = (p.aux[row * p.ldc + col + e] > 0.f) ? x[e] : 0.f;
+                    dst[e] = p.accumulate ? dst[e] + x[e] : x[e];
                 }
             }
-            continue;
-        }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            if (e < nv) {
-                if (p.bias) x[e] += p.bias[col + e];
-                if (p.act == XNRS_ACT_RELU) x[e] = fmaxf(x[e], 0.f);
-                else if (p.act == XNRS_ACT_TANH) x[e] = tanh_fast(x[e]);
-                else if (p.act == XNRS_ACT_RELU_MASK) x[e] = (arow[col + e] > 0.f) ? x[e] : 0.f;
-            }
-        }
-        if (vec_ok && nv == 4) {
-            float4 *dst = reinterpret_cast<float4 *>(crow + col);
-            if (p.accumulate) {
-                const float4 o = *dst;
-                x[0] += o.x; x[1] += o.y; x[2] += o.z; x[3] += o.w;
-            }
-            *dst = make_float4(x[0], x[1], x[2], x[3]);
-        } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-                if (e < nv) crow[col + e] = p.accumulate ? crow[col + e] + x[e] : x[e];
         }
     }
+}
+
+// r: lane l holds columns [col0, col0+32) of row row0 + l (raw accumulators); stage: this warp's 4 KB staging buffer
+__device__ __forceinline__ void epi_block32(float (&r)[32], uint32_t stage, const TcArgs &p, long long row0, long long col0,
+                                            long long split, int lane, bool vec_ok, bool bias_vec) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        sts128(stage + lane * 128 + ((c ^ (lane & 7)) << 4), make_float4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]));
+    __syncwarp();
+    switch (p.act) {
+        case XNRS_ACT_RELU: epi_rows<XNRS_ACT_RELU>(stage, p, row0, col0, split, lane, vec_ok, bias_vec); break;
+        case XNRS_ACT_TANH: epi_rows<XNRS_ACT_TANH>(stage, p, row0, col0, split, lane, vec_ok, bias_vec); break;
+        case XNRS_ACT_RELU_MASK: epi_rows<XNRS_ACT_RELU_MASK>(stage, p, row0, col0, split, lane, vec_ok, bias_vec); break;
+        default: epi_rows<XNRS_ACT_NONE>(stage, p, row0, col0, split, lane, vec_ok, bias_vec); break;
+    }
+    __syncwarp();
 }
 
 struct StageRing {
@@ -426,6 +424,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     } else {
         // ===================== epilogue: TMEM -> registers -> bias/act -> global =====================
         const int q = warp & 3;                         // TMEM lane quarter this warp may access
+        const uint32_t epi_stage = smem_u32(smem + SMEM_DATA) + (warp - EPI_WARP0) * 4096;
         const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
                             (!p.aux || (reinterpret_cast<uintptr_t>(p.aux) & 15) == 0);
         const bool bias_vec = (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0;
@@ -433,11 +432,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (long long t = blockIdx.x; t < total; t += gridDim.x) {
             const long long split = t / tiles_mn, mn = t - split * tiles_mn;
             const long long m0 = (mn / p.tiles_n) * TBM, n0 = (mn % p.tiles_n) * BN;
-            const long long row = m0 + 32 * q + lane;
             mbar_wait(&tfull_bar[acc.stage], acc.phase);
             tc_fence_after();
-            float *crow = p.C + row * p.ldc;
-            const float *arow = p.aux ? p.aux + row * p.ldc : nullptr;
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 float r[32];
@@ -449,8 +445,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
                     for (int j = 0; j < 32; ++j) r[j] += corr[j];
                 }
-                if (row >= p.M) continue;
-                epi_store32(r, p, crow, arow, n0 + c * 32, split, vec_ok, bias_vec);
+                if (m0 + 32 * q >= p.M || n0 + c * 32 >= p.N) continue;        // warp-uniform
+                epi_block32(r, epi_stage, p, m0 + 32 * q, n0 + c * 32, split, lane, vec_ok, bias_vec);
             }
             tc_fence_before();
             mbar_arrive(&tempty_bar[acc.stage]);
@@ -526,7 +522,8 @@ __device__ __forceinline__ void tc2_mma_tf32(uint32_t d_tmem, uint64_t adesc, ui
 
 constexpr int T2N = 256;       // tile columns of the pair
 
-constexpr int TC2_THREADS = 384;       // CTA-pair kernel: {TMA, MMA, relay, -} | 4 splitter warps | 4 epilogue warps
+constexpr int TC2_THREADS = 640;       // CTA-pair kernel: {TMA, MMA, relay, -} | 8 splitter warps | 8 epilogue warps
+constexpr int EPI2_WARP0 = 4 + SPLIT_WARPS, EPI2_WARPS = 8;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcArgs p) {
@@ -549,12 +546,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&ready_bar[s], passes == 3 ? 256 : 2);      // used in the leader only
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&ready_bar[s], passes == 3 ? 2 * SPLIT_WARPS : 2);      // used in the leader only: one arrival per
+            mbar_init(&empty_bar[s], 1);                                       // splitter warp (or relay) of BOTH CTAs
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], 256);                        // used in the leader only
+            mbar_init(&tempty_bar[a], 2 * EPI2_WARPS);                         // used in the leader only
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -644,64 +641,65 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     } else if (warp == 2) {
         // ===================== relay (single-pass mode): "my operands have landed" -> leader =====================
         if (passes != 3 && lane == 0) {
+            const uint32_t ready0 = map_to_cta(smem_u32(&ready_bar[0]), 0);
             StageRing r;
             for (long long t = pair; t < total; t += npairs) {
                 const long long split = t / tiles_mn;
                 const long long kbeg = split * p.k_per_split, kend = min(p.K, kbeg + p.k_per_split);
                 for (long long k0 = kbeg; k0 < kend; k0 += TBK) {
                     mbar_wait(&full_bar[r.stage], r.phase);
-                    mbar_arrive_cluster(map_to_cta(smem_u32(&ready_bar[r.stage]), 0));
+                    mbar_arrive_cluster(ready0 + 8 * r.stage);
                     r.advance(stages);
                 }
             }
         }
     } else if (warp < 4) {
         // idle
-    } else if (warp < 8) {
+    } else if (warp < EPI2_WARP0) {
         // ===================== splitters (3xTF32): lo = x - trunc_tf32(x) for this CTA's tiles =====================
         if (passes == 3) {
             const int tid = threadIdx.x - 128;
+            constexpr int ITERS = HALF / 16 / SPLIT_THREADS;
+            const uint32_t ready0 = map_to_cta(smem_u32(&ready_bar[0]), 0);
             StageRing r;
             for (long long t = pair; t < total; t += npairs) {
                 const long long split = t / tiles_mn;
                 const long long kbeg = split * p.k_per_split, kend = min(p.K, kbeg + p.k_per_split);
                 for (long long k0 = kbeg; k0 < kend; k0 += TBK) {
                     mbar_wait(&full_bar[r.stage], r.phase);
-                    const float4 *hi = reinterpret_cast<const float4 *>(tileA(r.stage));
-                    float4 *lo = reinterpret_cast<float4 *>(tileA(r.stage) + HALF);
-#pragma unroll 4
-                    for (int i = tid; i < HALF / 16; i += 128) {
-                        const float4 v = hi[i];
-                        lo[i] = make_float4(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u),
-                                            v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u),
-                                            v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u),
-                                            v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
-                    }
+                    const uint32_t hi = smem_u32(tileA(r.stage)) + tid * 16;
+                    float4 v[ITERS];
+#pragma unroll
+                    for (int i = 0; i < ITERS; ++i) v[i] = lds128(hi + i * (SPLIT_THREADS * 16));
+#pragma unroll
+                    for (int i = 0; i < ITERS; ++i)
+                        sts128(hi + HALF + i * (SPLIT_THREADS * 16),
+                               make_float4(tf32_lo(v[i].x), tf32_lo(v[i].y), tf32_lo(v[i].z), tf32_lo(v[i].w)));
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    mbar_arrive_cluster(map_to_cta(smem_u32(&ready_bar[r.stage]), 0));
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(ready0 + 8 * r.stage);
                     r.advance(stages);
                 }
             }
         }
     } else {
-        // ===================== epilogue: this CTA's 128 rows of the pair's tile =====================
-        const int q = warp & 3;
+        // ===================== epilogue: this CTA's 128 rows of the pair's tile; 2 warps per TMEM lane quarter ==========
+        const int q = warp & 3, colhalf = (warp - EPI2_WARP0) >> 2;     // columns [128 * colhalf, +128)
         const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
                             (!p.aux || (reinterpret_cast<uintptr_t>(p.aux) & 15) == 0);
         const bool bias_vec = (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0;
+        const uint32_t tempty0 = map_to_cta(smem_u32(&tempty_bar[0]), 0);
+        const uint32_t epi_stage = smem_u32(smem + SMEM_DATA) + (warp - EPI2_WARP0) * 4096;
         StageRing acc;
         for (long long t = pair; t < total; t += npairs) {
             const long long split = t / tiles_mn, mn = t - split * tiles_mn;
-            const long long m0 = (mn / p.tiles_n) * 256 + 128 * rank, n0 = (mn % p.tiles_n) * T2N;
-            const long long row = m0 + 32 * q + lane;
+            const long long m0 = (mn / p.tiles_n) * 256 + 128 * rank, n0 = (mn % p.tiles_n) * T2N + 128 * colhalf;
             mbar_wait(&tfull_bar[acc.stage], acc.phase);
             tc_fence_after();
-            float *crow = p.C + row * p.ldc;
-            const float *arow = p.aux ? p.aux + row * p.ldc : nullptr;
 #pragma unroll 1
-            for (int c = 0; c < T2N / 32; ++c) {
+            for (int c = 0; c < 4; ++c) {
                 float r[32];
-                const uint32_t taddr = tmem_base + acc.stage * acc_cols + c * 32 + ((uint32_t)(32 * q) << 16);
+                const uint32_t taddr = tmem_base + acc.stage * acc_cols + 128 * colhalf + c * 32 + ((uint32_t)(32 * q) << 16);
                 tc_ld32(taddr, r);
                 if (passes == 3) {
                     float corr[32];
@@ -709,11 +707,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 #pragma unroll
                     for (int j = 0; j < 32; ++j) r[j] += corr[j];
                 }
-                if (row >= p.M) continue;
-                epi_store32(r, p, crow, arow, n0 + c * 32, split, vec_ok, bias_vec);
+                if (m0 + 32 * q >= p.M || n0 + c * 32 >= p.N) continue;        // warp-uniform
+                epi_block32(r, epi_stage, p, m0 + 32 * q, n0 + c * 32, split, lane, vec_ok, bias_vec);
             }
             tc_fence_before();
-            mbar_arrive_cluster(map_to_cta(smem_u32(&tempty_bar[acc.stage]), 0));
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tempty0 + 8 * acc.stage);
             acc.advance(acc_stages);
         }
     }
@@ -761,7 +760,7 @@ static bool make_map(CUtensorMap *map, const float *base, long long inner, long 
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-int g_opt_2cta = -1;
+int g_opt_2cta = -2;       // -2: read XNRS_GEMM_2CTA on first use
 
 int gemm_tensorcore(const GemmArgs &a, int precision, cudaStream_t st, int *status) {
     // shapes / layouts the TMA path cannot take fall through to the exact-fp32 SIMT kernel
@@ -784,14 +783,18 @@ int gemm_tensorcore(const GemmArgs &a, int precision, cudaStream_t st, int *stat
     p.passes = (precision == XNRS_PREC_TF32X3) ? 3 : 1;
     // 3xTF32 keeps BN=128: its stage is 2x larger (hi+lo), and 3 smem stages + 2 TMEM stages beat the wider tile
     // (measured: 156 vs 142 TFLOP/s); single-pass TF32 takes BN=256 (398 vs 340 TFLOP/s)
-    // CTA-pair kernel (256x256 tiles, cta_group::2): wide outputs with enough rows and no fused gather
-    // Off by default: measured on B200 it is correct (tests) and lifts the tensor pipe from 47 % to 50 % active in 3xTF32,
-    // but its cross-CTA ready/empty handshake makes the short K loop latency-bound (168 vs 179 TFLOP/s) — round-2 work.
-    if (g_opt_2cta < 0) {
+    // CTA-pair kernel (256x256 tiles, cta_group::2): wide outputs with enough rows and no fused gather.  It halves the
+    // operand bytes the tensor core reads from shared memory per FLOP — the resource that bounds the 3xTF32 main loop
+    // (ncu: tensor-core + splitter wavefronts = 94 % of the shared-memory pipe in the 1-CTA kernel) — and is the default
+    // there (measured 3xTF32: qkv 198 -> 221, fc1 184 -> 200, dW 173 -> 179 TFLOP/s).  Single-pass TF32 keeps the 1-CTA
+    // BN=256 kernel (its short stages make the cross-CTA handshake the critical path: 525 vs 307 TFLOP/s).
+    // XNRS_GEMM_2CTA / xnrs_set_option("gemm_2cta"): 0 = never, 1 = always where legal, -1 (default) = 3xTF32 only.
+    if (g_opt_2cta == -2) {
         const char *e = getenv("XNRS_GEMM_2CTA");
-        g_opt_2cta = e ? atoi(e) : 0;
+        g_opt_2cta = e ? atoi(e) : -1;
     }
-    const bool use2 = g_opt_2cta && a.N > 128 && a.M >= 256 && !a.a_rows && !a.b_rows && (num_sms() % 2 == 0);
+    const bool want2 = g_opt_2cta == 1 || (g_opt_2cta == -1 && p.passes == 3);
+    const bool use2 = want2 && a.N > 128 && a.M >= 256 && !a.a_rows && !a.b_rows && (num_sms() % 2 == 0);
     const int BN = use2 ? 128 : ((p.passes == 1 && a.N > 128 && cdiv(a.M, TBM) * cdiv(a.N, 256) >= num_sms()) ? 256 : 128);
     const int half = TBM * TBK * 4 + BN * TBK * 4;
     p.stages = SMEM_DATA / (half * (p.passes == 3 ? 2 : 1));
@@ -834,7 +837,7 @@ int gemm_tensorcore(const GemmArgs &a, int precision, cudaStream_t st, int *stat
         }
     }
     static bool attr_set = false;
-    const int smem_bytes = SMEM_DATA + 1024;
+    const int smem_bytes = SMEM_DATA + SMEM_EPI + 1024;
     if (!attr_set) {
         if (cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess ||
             cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess ||
@@ -866,7 +869,7 @@ int gemm_tensorcore(const GemmArgs &a, int precision, cudaStream_t st, int *stat
 
 extern "C" int xnrs_set_option(const char *name, int value) {
     if (name && !strcmp(name, "gemm_2cta")) {
-        xnrs::g_opt_2cta = value ? 1 : 0;
+        xnrs::g_opt_2cta = value < 0 ? -1 : (value ? 1 : 0);
         return XNRS_OK;
     }
     return xnrs::fail(XNRS_ERR_ARG, "%s: unknown option", "xnrs_set_option");

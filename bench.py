@@ -370,6 +370,11 @@ def main():
             sh[1] += 1
             sh[2] += 2.0 * a[2] * a[3] * a[4]
     top = max(agg.items(), key=lambda kv: kv[1][0])
+    if os.environ.get('XNRS_BENCH_DUMP') and rank == 0:      # every launch of ONE step with its event time (diagnostics)
+        per = len(records) // args.steps
+        with open(os.environ['XNRS_BENCH_DUMP'], 'w') as f:
+            for name, a, s_, e_ in records[:per]:
+                f.write(json.dumps({'name': name, 'args': list(a), 'ms': round(s_.elapsed_time(e_), 4)}) + '\n')
     pk, pk_kind = peaks()
     gemm_ms, gemm_n, gemm_flop = agg.get('xnrs_gemm', [0.0, 0, 0.0])
     kernel_ms_total = sum(v[0] for v in agg.values())

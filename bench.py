@@ -225,6 +225,21 @@ def run_eval(args):
     out2, *_ = one_pass(imp_pin)                      # host CSR buffers -> H2D inside the timed region, means read back
     sync_all()
     e2e_s = time.perf_counter() - w0
+    # one more pass with every entry point bracketed by CUDA events on its stream: per-kernel durations
+    recs = []
+
+    def hook(name, args_):
+        s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        recs.append((name, s_, e_))
+        return s_, e_
+
+    K.set_event_hook(hook)
+    one_pass(imp_dev)
+    sync_all()
+    K.set_event_hook(None)
+    per_entry = {}
+    for name, s_, e_ in recs:
+        per_entry[name] = per_entry.get(name, 0.0) + s_.elapsed_time(e_)
     pk, pk_kind = peaks()
     n_cand = int(imp['offsets'][-1])
     # algorithmic bytes of the score+rank kernel: one T-wide fp32 vector per candidate + the user vector + ids/targets
@@ -245,7 +260,8 @@ def run_eval(args):
         'roofline': {'kernel': 'eval_impressions_kernel (gather + dot + segmented rank sort + metrics), whole impression phase',
                      'bound': 'hbm', 'achieved': score_bytes / (score_ms * 1e-3) / 1e9, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
                      'frac': score_bytes / (score_ms * 1e-3) / 1e9 / pk['hbm_gbs'], 'traffic': None,
-                     'peak_source': pk_kind},
+                     'peak_source': pk_kind,
+                     'per_entry_point_ms': {k: round(v, 3) for k, v in sorted(per_entry.items(), key=lambda kv: -kv[1])}},
         'clocks': clocks.summary(),
     }
     if rank == 0:

@@ -91,6 +91,13 @@ int xnrs_perspool_fwd(const float *x, const int *x_rows, const float *mask, cons
 int xnrs_perspool_bwd(const float *x, const int *x_rows, const float *mask, const float *hid, const float *qh,
                       const float *attn, const float *d_pooled, const int *seg, long long R, int L, int F, int A,
                       int rows_per_query, float *d_hid, float *d_qh, float *d_x, xnrs_stream_t st);
+/* out[i] = <x[i,:], w> + b[0]  (the pooler's fc2, layers.py:45,60, over a whole table of hidden rows) */
+int xnrs_rowdot(const float *x, const float *w, const float *b, long long n, int A, float *out, xnrs_stream_t st);
+/* additive pooling over PER-ITEM logits (evaluation with a pre-encoded catalogue; layers.py:60-65 slot by slot):
+ * group r pools the table rows ids[r,0..L): a_l = exp(logit[id]) * row_mask[id] / (sum + 1e-8); pooled[r] = sum a_l table[id].
+ * table (V,T), T % 4 == 0, T <= 1024; row_mask (V, nullable); attn (R*L, nullable) receives the weights */
+int xnrs_logitpool_fwd(const float *table, long long V, int T, const float *logit, const float *row_mask, const int *ids,
+                       long long R, int L, float *attn, float *pooled, xnrs_stream_t st);
 /* masked mean pooling (layers.py:25-37) */
 int xnrs_meanpool_fwd(const float *x, const float *mask, long long R, int L, int F, float *pooled,
                       xnrs_stream_t st);

@@ -340,3 +340,17 @@ def _xnrs_metric_sums(metrics, n_imp, sums):
     ok = torch.isfinite(metrics).all(1)
     sums[:6] += metrics[ok].sum(0)
     sums[6] += ok.sum()
+
+
+def _xnrs_rowdot(x, w, b, n, A, out):
+    out.copy_(x.reshape(n, A) @ w + (b[0] if b is not None else 0.0))
+
+
+def _xnrs_logitpool_fwd(table, V, T, logit, row_mask, ids, R, L, attn, pooled):
+    v = ids.reshape(R, L).long()
+    m = row_mask[v] if row_mask is not None else torch.ones(R, L)
+    e = torch.exp(logit[v]) * m
+    a = e / (e.sum(1, keepdim=True) + 1e-8)
+    if attn is not None:
+        attn.copy_(a.reshape(attn.shape))
+    pooled.copy_(torch.einsum('rl,rlt->rt', a, table[v]))

@@ -74,6 +74,32 @@ def test_catalogue_eval_matches_per_impression_reference(name, device):
     assert out['impressions'] == 24
 
 
+@pytest.mark.parametrize('name', ['cl', 'naml'])
+def test_per_article_pooling_logits_equal_per_slot_pooling(name, device):
+    """the evaluator computes the user pooler's logit once per catalogue article (item_logits); re-running the pooler
+    on every (user, slot) like the reference must give the same scores and metrics"""
+    fx = load_npz('model_' + name)
+    cfg = dict(fixture_cfg(fx), device=device)
+    model = make_model(cfg)
+    model.load_state_dict({k: torch.tensor(v) for k, v in sub(fx, 'sd').items()})
+    model.to(device).eval()
+    cat = syn.make_catalogue(50, cfg['seq_len'], vocab=200, dim=cfg['d_backbone'], seed=8, with_abstract=(name == 'naml'),
+                             n_categories=cfg['n_categories'], n_subcategories=cfg['n_subcategories'])
+    imp = syn.make_eval_impressions(50, 40, cfg['hist_len'], n_users=cfg['n_users'], seed=9)
+    store = TitleStore(cat.token_table.to(device), cat.title_tokens.to(device))
+    astore = TitleStore(store.token_table, cat.abstract_tokens.to(device)) if name == 'naml' else None
+    outs = []
+    for item_logits in (True, False):
+        ev = CatalogueEvaluator(model, store, cat.category, cat.subcategory, astore, news_chunk=23, impression_chunk=9)
+        ev.item_logits = item_logits
+        outs.append(ev.evaluate(imp, return_per_impression=True))
+        assert (ev.news_logit is not None) == item_logits
+    assert_close(outs[0]['scores'], outs[1]['scores'], 1e-5, 'scores')
+    # rank metrics may only differ where the two score sets order a near-tie differently
+    same = (outs[0]['per_impression'] - outs[1]['per_impression']).abs().amax(1) < 1e-9
+    assert float(same.float().mean()) >= 0.9
+
+
 def test_pad_slot_vector_is_the_encoding_of_the_pad_article(device):
     """Appendix A.16: padded history slots must see news_encoder(zeros, zero mask), non-zero for biased heads (NRMS)"""
     fx = load_npz('model_nrms')

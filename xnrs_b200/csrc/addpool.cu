@@ -267,6 +267,80 @@ static int check_pool(long long R, int L, int F, int A, const float *x) {
     return XNRS_OK;
 }
 
+
+// ---- pooling over per-ITEM logits (evaluation; rows U / U-naml with frozen weights) -------------------------------------
+// The additive pooler's logit  w2 . tanh(fc1 h + b1) + b2  of a history slot depends only on the article in that slot, so
+// with a pre-encoded catalogue it is computed ONCE per article (xnrs_gemm + xnrs_rowdot over the catalogue) instead of once
+// per (user, slot): the per-user work left is this kernel — gather the slot's logit and vector, exp * mask, normalise by
+// (sum + 1e-8), weighted sum.  Same values as layers.py:60-65 applied slot by slot.  One warp per user; HBM/L2-bound:
+// L rows of T floats per user.
+__global__ void __launch_bounds__(256)
+rowdot_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ b, long long n, int A,
+              float *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const float *xr = x + row * A;
+    float acc = 0.f;
+    for (int j = lane; j < A; j += 32) acc = fmaf(xr[j], w[j], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) out[row] = acc + (b ? b[0] : 0.f);
+}
+
+template <int NV>       // up to NV float4 columns per lane: T <= 128 * NV
+__global__ void __launch_bounds__(256)
+logitpool_fwd_kernel(const float *__restrict__ table, const float *__restrict__ logit, const float *__restrict__ row_mask,
+                     const int *__restrict__ ids, long long R, int L, int T4, float *__restrict__ attn,
+                     float *__restrict__ pooled) {
+    const int lane = threadIdx.x & 31;
+    const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= R) return;
+    const int *idr = ids + r * L;
+    // pass 1: e_l for the lane's slots (l = lane, lane + 32, ...), total
+    float tot = 0.f;
+    for (int l = lane; l < L; l += 32) {
+        const int v = idr[l];
+        const float m = row_mask ? row_mask[v] : 1.f;
+        tot += (m != 0.f) ? expf(logit[v]) * m : 0.f;
+    }
+    tot = warp_sum(tot);
+    const float inv = 1.f / (tot + 1e-8f);
+    float4 acc[NV];
+#pragma unroll
+    for (int c = 0; c < NV; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 *t4 = reinterpret_cast<const float4 *>(table);
+    for (int l0 = 0; l0 < L; l0 += 32) {
+        const int l = l0 + lane;
+        int v = 0;
+        float a = 0.f;
+        if (l < L) {
+            v = idr[l];
+            const float m = row_mask ? row_mask[v] : 1.f;
+            a = (m != 0.f) ? expf(logit[v]) * m * inv : 0.f;
+            if (attn) attn[r * L + l] = a;
+        }
+        const int cnt = min(32, L - l0);
+#pragma unroll 4
+        for (int j = 0; j < cnt; ++j) {
+            const float aj = __shfl_sync(0xffffffffu, a, j);
+            const int vj = __shfl_sync(0xffffffffu, v, j);
+            if (aj == 0.f) continue;                              // warp-uniform: padded slots are never read
+            const float4 *row = t4 + (long long)vj * T4;
+#pragma unroll
+            for (int c = 0; c < NV; ++c) {
+                if (c * 32 + lane >= T4) break;
+                const float4 x = __ldg(row + c * 32 + lane);
+                acc[c].x = fmaf(aj, x.x, acc[c].x); acc[c].y = fmaf(aj, x.y, acc[c].y);
+                acc[c].z = fmaf(aj, x.z, acc[c].z); acc[c].w = fmaf(aj, x.w, acc[c].w);
+            }
+        }
+    }
+    float4 *out = reinterpret_cast<float4 *>(pooled) + r * T4;
+#pragma unroll
+    for (int c = 0; c < NV; ++c)
+        if (c * 32 + lane < T4) out[c * 32 + lane] = acc[c];
+}
+
 }  // namespace xnrs
 
 using namespace xnrs;
@@ -349,6 +423,35 @@ extern "C" int xnrs_collapse_mask(const float *mask, long long R, int L, float *
     if (R == 0) return XNRS_OK;
     XNRS_REQUIRE(mask && out, "null pointer");
     collapse_mask_kernel<<<(unsigned)cdiv(R, 256), 256, 0, STREAM(st)>>>(mask, R, L, out);
+    XNRS_LAUNCHED();
+    return XNRS_OK;
+}
+
+extern "C" int xnrs_rowdot(const float *x, const float *w, const float *b, long long n, int A, float *out,
+                           xnrs_stream_t st) {
+    XNRS_REQUIRE(n >= 0 && A > 0, "bad sizes");
+    if (n == 0) return XNRS_OK;
+    XNRS_REQUIRE(x && w && out, "null pointer");
+    rowdot_kernel<<<(unsigned)cdiv(n, 8), 256, 0, STREAM(st)>>>(x, w, b, n, A, out);
+    XNRS_LAUNCHED();
+    return XNRS_OK;
+}
+
+extern "C" int xnrs_logitpool_fwd(const float *table, long long V, int T, const float *logit, const float *row_mask,
+                                  const int *ids, long long R, int L, float *attn, float *pooled, xnrs_stream_t st) {
+    XNRS_REQUIRE(R >= 0 && L > 0 && V > 0, "bad sizes");
+    XNRS_REQUIRE(T > 0 && T % 4 == 0 && T <= 1024, "T must be a multiple of 4, at most 1024");
+    if (R == 0) return XNRS_OK;
+    XNRS_REQUIRE(table && logit && ids && pooled, "null pointer");
+    XNRS_REQUIRE((((uintptr_t)table | (uintptr_t)pooled) & 15) == 0, "16-byte alignment");
+    const unsigned grid = (unsigned)cdiv(R, 8);
+    const int T4 = T / 4;
+#define XNRS_LP(NV) logitpool_fwd_kernel<NV><<<grid, 256, 0, STREAM(st)>>>(table, logit, row_mask, ids, R, L, T4, attn, pooled)
+    if (T4 <= 32) XNRS_LP(1);
+    else if (T4 <= 64) XNRS_LP(2);
+    else if (T4 <= 128) XNRS_LP(4);
+    else XNRS_LP(8);
+#undef XNRS_LP
     XNRS_LAUNCHED();
     return XNRS_OK;
 }

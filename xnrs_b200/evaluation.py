@@ -23,6 +23,7 @@ import torch.distributed as dist
 from . import kernels as K
 from .data import IndexedTitles, TitleStore
 from .distributed import rank, shard_range, world
+from .models.components import AdditiveAttention, UserEncoder, _apply_head
 from .models.zoo import LSTUR, NAML, NPA
 
 METRIC_NAMES = ('auc', 'rr', 'ndcg@5', 'ndcg@10', 'ctr@1', 'ctr@10')
@@ -54,6 +55,11 @@ class CatalogueEvaluator:
         self.news_chunk, self.impression_chunk, self.score_act = news_chunk, impression_chunk, score_act
         self.news_vecs: Optional[torch.Tensor] = None
         self.news_mask: Optional[torch.Tensor] = None
+        self.news_logit: Optional[torch.Tensor] = None     # per-article pooling logit (item_logits=True)
+        # With frozen weights the additive pooler's logit of a history slot depends only on the article in it, so it is
+        # computed once per catalogue article (one GEMM over n_news rows) instead of once per (user, slot): same values as
+        # layers.py:60-65 slot by slot, ~H * n_impressions / n_news fewer pooler FLOPs.  Off: re-run the pooler per slot.
+        self.item_logits = True
 
     # ---- phase 1 ---------------------------------------------------------------------------------------------
     def _encode_ids(self, ids: torch.Tensor):
@@ -97,11 +103,35 @@ class CatalogueEvaluator:
             dist.all_gather_into_tensor(allm, lmask)
             local, lmask = allv, allm
         self.news_vecs, self.news_mask = local[:n].contiguous(), lmask[:n].contiguous()
+        self.news_logit = None
+        pooler = self._item_pooler()
+        if pooler is not None:
+            hid = K.gemm(self.news_vecs, pooler.fc1.weight, trans_b=True, bias=pooler.fc1.bias, act=K.ACT_TANH)
+            self.news_logit = K.rowdot(hid, pooler.fc2.weight.reshape(-1), pooler.fc2.bias)
         return self.news_vecs
+
+    def _item_pooler(self) -> Optional[AdditiveAttention]:
+        """the user-level additive pooler when the user encoder is [no dropout, no attention] -> pooler (-> head):
+        StandardRec / CL (user_encoding.py:69-77 with att=None) and NAML (naml.py:54-57,109)"""
+        if not self.item_logits:
+            return None
+        ue = getattr(self.model, 'user_encoder', None)
+        if isinstance(self.model, NAML) and isinstance(ue, AdditiveAttention):
+            pooler = ue
+        elif type(ue) is UserEncoder and ue.att is None and isinstance(ue.pooler, AdditiveAttention):
+            pooler = ue.pooler
+        else:
+            return None
+        T = self.news_vecs.shape[1]
+        return pooler if (T % 4 == 0 and T <= 1024 and pooler.fc1.weight.shape[1] == T) else None
 
     # ---- phase 2 ---------------------------------------------------------------------------------------------
     def _users(self, hist_ids: torch.Tensor, user_index: Optional[torch.Tensor]) -> torch.Tensor:
         B, H = hist_ids.shape
+        if self.news_logit is not None:
+            pooled = K.logitpool(self.news_vecs, self.news_logit, self.news_mask, hist_ids)
+            ue = self.model.user_encoder
+            return _apply_head(ue.head, pooled) if hasattr(ue, 'head') else pooled
         flat = hist_ids.reshape(-1)
         h = K.gather_rows(self.news_vecs, flat).view(B, H, -1)
         hm = self.news_mask[flat.long()].view(B, H, 1)            # index plumbing: collapsed title mask per slot
@@ -134,10 +164,11 @@ class CatalogueEvaluator:
         uidx = None if uidx is None else uidx.to(dev)
         sums = torch.zeros(7, device=dev, dtype=torch.float64)
         per_imp, all_scores = [], []
+        off_host = impressions['offsets'] if not impressions['offsets'].is_cuda else offsets.cpu()   # chunk bounds: no per-chunk sync
         for a in range(lo, hi, self.impression_chunk):
             b = min(hi, a + self.impression_chunk)
             u = self._users(hist_ids[a:b].contiguous(), None if uidx is None else uidx[a:b].contiguous())
-            c0, c1 = int(offsets[a]), int(offsets[b])
+            c0, c1 = int(off_host[a]), int(off_host[b])
             local_off = (offsets[a:b + 1] - c0).contiguous()
             scores, metrics = K.eval_impressions(u, self.news_vecs, cand_ids[c0:c1].contiguous(), local_off,
                                                  targets[c0:c1].contiguous(), act=self.score_act)

@@ -161,6 +161,20 @@ def collapse_mask(mask: torch.Tensor, R: int, L: int) -> torch.Tensor:
     return out
 
 
+def rowdot(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor]) -> torch.Tensor:
+    out = torch.empty(x.shape[0], device=x.device, dtype=torch.float32)
+    call('xnrs_rowdot', x, w, b, x.shape[0], x.shape[1], out)
+    return out
+
+
+def logitpool(table: torch.Tensor, logit: torch.Tensor, row_mask: Optional[torch.Tensor], ids: torch.Tensor) -> torch.Tensor:
+    """additive pooling over per-item logits: ids (R,L) int32 rows of `table` -> pooled (R,T)"""
+    R, L = ids.shape
+    pooled = torch.empty((R, table.shape[1]), device=table.device, dtype=torch.float32)
+    call('xnrs_logitpool_fwd', table, table.shape[0], table.shape[1], logit, row_mask, _i32(ids), R, L, None, pooled)
+    return pooled
+
+
 def adam_step(p, g, m, v, lr, beta1=0.9, beta2=0.999, eps=1e-8, step=1, bc_dev=None, grad_scale=1.0):
     call('xnrs_adam_step', p, g, m, v, p.numel(), lr, beta1, beta2, eps, step, bc_dev, grad_scale)
 

@@ -246,9 +246,64 @@ def loss_metric_fixtures():
     np.savez_compressed(os.path.join(HERE, 'loss_metrics.npz'), **out)
 
 
+def dataset_fixture():
+    """row G: the reference's NewsRecDataset + custom_collate_fn (xnrs/data/dataset.py:48-163, utils.py:190-204) on a tiny
+    synthetic news table / behaviour log, in eval mode (all candidates) and train mode (seeded negative sampling).  The
+    raw inputs are stored next to the dense outputs so tests can rebuild the batch through xnrs_b200.mind_io."""
+    import random
+    from xnrs.data.dataset import NewsRecDataset
+    rng = np.random.default_rng(5)
+    n_news, S, D, H, K = 12, 4, 6, 3, 2
+    ids = [f'N{100 + i}' for i in range(n_news)]
+    emb = rng.normal(size=(n_news, S, D)).astype(np.float32)
+    lens = rng.integers(1, S + 1, size=n_news)
+    mask = (np.arange(S)[None, :] < lens[:, None]).astype(np.int64)
+    emb = emb * mask[:, :, None]                      # the reference stores embeddings relative to a pad reference: 0 at pads
+    cat = rng.integers(1, 5, size=n_news)
+    news_feat = {nid: {'title_emb': (emb[i][None], mask[i][None]), 'category_index': int(cat[i])} for i, nid in enumerate(ids)}
+    sessions = []
+    for u in range(6):
+        nh = int(rng.integers(1, 2 * H + 1))
+        hist = [ids[j] for j in rng.integers(0, n_news, size=nh)]
+        pos = [ids[j] for j in rng.integers(0, n_news, size=int(rng.integers(1, 3)))]
+        neg = [ids[j] for j in rng.integers(0, n_news, size=int(rng.integers(2, 6)))]
+        sessions.append({'history': hist, 'positives': pos, 'negatives': neg, 'user_index': str(u + 1),
+                         'main_theme': ['sports', 'news', 'finance'][u % 3], 'main_category': 'x'})
+    out = {'ids': np.array(ids), 'emb': emb, 'mask': mask, 'cat': cat.astype(np.int64),
+           'sessions': np.array(json.dumps(sessions)), 'dims': np.array([S, D, H, K])}
+    common = dict(l_seq=S, l_hist=H, text_features=['title_emb'], catg_features=['category_index'],
+                  user_features=['user_index'])
+    ds = NewsRecDataset([dict(s, history=list(s['history'])) for s in sessions], news_feat, mode='train', n_negatives=K, **common)
+    random.seed(77)
+    batch = U.custom_collate_fn([ds[i] for i in range(len(sessions))])
+    out['train/hist_x'] = batch['user_features']['history']['title_emb'][0].numpy()
+    out['train/hist_m'] = batch['user_features']['history']['title_emb'][1].numpy()
+    out['train/cand_x'] = batch['candidate_features']['title_emb'][0].numpy()
+    out['train/cand_m'] = batch['candidate_features']['title_emb'][1].numpy()
+    out['train/hist_cat'] = batch['user_features']['history']['category_index'].numpy()
+    out['train/cand_cat'] = batch['candidate_features']['category_index'].numpy()
+    out['train/user_index'] = batch['user_features']['other']['user_index'].numpy()
+    out['train/targets'] = batch['targets'].numpy()
+    out['train/item_ids'] = np.array(json.dumps(batch['item_ids']))
+    ds = NewsRecDataset([dict(s, history=list(s['history'])) for s in sessions], news_feat, mode='eval', n_negatives=None, **common)
+    for i in range(len(sessions)):
+        smp = ds[i]
+        out[f'eval/{i}/hist_x'] = smp['user_features']['history']['title_emb'][0].numpy()
+        out[f'eval/{i}/hist_m'] = smp['user_features']['history']['title_emb'][1].numpy()
+        out[f'eval/{i}/cand_x'] = smp['candidate_features']['title_emb'][0].numpy()
+        out[f'eval/{i}/cand_m'] = smp['candidate_features']['title_emb'][1].numpy()
+        out[f'eval/{i}/hist_cat'] = smp['user_features']['history']['category_index'].numpy()
+        out[f'eval/{i}/targets'] = smp['targets'].numpy()
+    np.savez_compressed(os.path.join(HERE, 'dataset.npz'), **out)
+
+
 if __name__ == '__main__':
+    if '--dataset-only' in sys.argv:
+        dataset_fixture()
+        sys.exit(0)
     for i, (name, over) in enumerate(MODELS.items()):
         model_fixture(name, over, seed=20 + i)
     layer_fixtures()
     loss_metric_fixtures()
+    dataset_fixture()
     print('golden fixtures written to', HERE)

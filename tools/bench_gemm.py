@@ -12,6 +12,11 @@ SHAPES = [  # name, M, N, K, trans_a, trans_b
     ('qkv fwd   (tokens x 768 <- 768)', 262144, 768, 768, False, True),
     ('dW fc1    (256 x 768, K=tokens)', 256, 768, 262144, True, False),
     ('dX        (tokens x 768 <- 256)', 262144, 768, 256, False, False),
+    ('head fwd small (8748 x 256 <- 768)', 8748, 256, 768, False, True),
+    ('head dW small (256 x 768, K=8748)', 256, 768, 8748, True, False),
+    ('user head (1024 x 256 <- 256)', 1024, 256, 256, False, True),
+    ('user head dW (256 x 256, K=1024)', 256, 256, 1024, True, False),
+    ('user fc1 (51200 x 256 <- 256)', 51200, 256, 256, False, True),
 ]
 
 

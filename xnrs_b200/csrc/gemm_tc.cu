@@ -18,6 +18,7 @@
 // Both operand majors are supported through the UMMA descriptors (K-major: nn.Linear forward;
 // MN-major: weight-gradient and input-gradient GEMMs), so no transposed copies are ever made.
 #include <cuda.h>
+#include <algorithm>
 #include <stdlib.h>
 #include <string.h>
 
@@ -794,7 +795,15 @@ int gemm_tensorcore(const GemmArgs &a, int precision, cudaStream_t st, int *stat
         g_opt_2cta = e ? atoi(e) : -1;
     }
     const bool want2 = g_opt_2cta == 1 || (g_opt_2cta == -1 && p.passes == 3);
-    const bool use2 = want2 && a.N > 128 && a.M >= 256 && !a.a_rows && !a.b_rows && (num_sms() % 2 == 0);
+    bool use2 = want2 && a.N > 128 && a.M >= 256 && !a.a_rows && !a.b_rows && (num_sms() % 2 == 0);
+    // the pair kernel has 74 workers with 256x256 tiles: problems with fewer than two waves of such tiles (launch list of a
+    // CL step: 20-40 us for 0.1-3 GFLOP GEMMs on 4-70 CTAs) run on the 1-CTA kernel, whose 128x128 tiles spread the same
+    // work over four times as many CTAs with half the per-stage latency
+    if (use2 && g_opt_2cta == -1) {
+        const long long t2 = cdiv(a.M, 256) * cdiv(a.N, 256);
+        const long long ksplit = a.act == XNRS_ACT_NONE ? (a.split_k > 0 ? a.split_k : std::max(1LL, std::min(cdiv(a.K, 512), (long long)(num_sms() / 2) / t2))) : 1;
+        if (t2 * ksplit < num_sms()) use2 = false;
+    }
     const int BN = use2 ? 128 : ((p.passes == 1 && a.N > 128 && cdiv(a.M, TBM) * cdiv(a.N, 256) >= num_sms()) ? 256 : 128);
     const int half = TBM * TBK * 4 + BN * TBK * 4;
     p.stages = SMEM_DATA / (half * (p.passes == 3 ? 2 : 1));

@@ -147,17 +147,11 @@ __global__ void __launch_bounds__(128) mha_fwd_fast_kernel(const float *__restri
     const float sc = 1.0f / sqrtf((float)DK), inv_keep = 1.f / (1.f - p_drop);
     const uint32_t key = head_key(seed, w);
     const float *keep_h = keep ? keep + w * (long long)L * L : nullptr;
-    bool staged = false;
-    for (int i = lane; i < L || !staged; i += 32) {
+    stage_wait();
+    for (int i = lane; i < L; i += 32) {
         float2 qi[DK / 2], acc[DK / 2];
-        const bool live = i < L;                       // lanes past the last query row still join the staging wait
-        if (live) load_row2<DK>(qi, q + (r * L + i) * ld + head * DK);
-        const bool masked = live && mask && mask[r * L + i] == 0.f;
-        if (!staged) {
-            stage_wait();
-            staged = true;
-        }
-        if (!live) break;
+        load_row2<DK>(qi, q + (r * L + i) * ld + head * DK);
+        const bool masked = mask && mask[r * L + i] == 0.f;
 #pragma unroll
         for (int d = 0; d < DK / 2; ++d) acc[d] = make_float2(0.f, 0.f);
         float m = -1e9f, l;

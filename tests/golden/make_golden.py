@@ -246,6 +246,45 @@ def loss_metric_fixtures():
     np.savez_compressed(os.path.join(HERE, 'loss_metrics.npz'), **out)
 
 
+def explain_fixture():
+    """§8(f) row 3: the explainer's integrated-gradients loop (xnrs/explain.py:144-172) — scaled history inputs through
+    news_encoder / user_encoder / rec_model with autograd.grad w.r.t. the scaled token embeddings — run with the REFERENCE
+    modules on the stored CL and NRMS fixture models (the best-scored (impression, candidate) pair of the fixture batch, 8 steps)."""
+    out = {}
+    for name in ('cl', 'nrms'):
+        with np.load(os.path.join(HERE, f'model_{name}.npz'), allow_pickle=False) as z:
+            fx = {k: z[k] for k in z.files}
+        cfg = DotMap(json.loads(str(fx['cfg'])))
+        model = make_model(cfg)
+        model.load_state_dict({k[3:]: torch.tensor(v) for k, v in fx.items() if k.startswith('sd/')})
+        model.eval()
+        sc = fx['ref/scores'][..., 0]
+        b, cidx = (int(v) for v in np.unravel_index(np.argmax(sc), sc.shape))      # a pair the ReLU does not zero
+        out[f'{name}/pick'] = np.array([b, cidx])
+        hx = torch.tensor(fx['batch/user_features/history/title_emb/x'])[b:b + 1]
+        hm = torch.tensor(fx['batch/user_features/history/title_emb/m'])[b:b + 1]
+        cx = torch.tensor(fx['batch/candidate_features/title_emb/x'])[b:b + 1, cidx:cidx + 1]
+        cm = torch.tensor(fx['batch/candidate_features/title_emb/m'])[b:b + 1, cidx:cidx + 1]
+        hist_emb, hist_att = hx.clone().requires_grad_(), hm.clone().requires_grad_()
+        c, _ = model.news_encoder((cx.clone().requires_grad_(), cm.clone().requires_grad_()))
+        n_steps = 8
+        da = 1 / n_steps
+        grads = []
+        for a in torch.arange(da, 1 + da, da):
+            ga = a * hist_emb
+            ha, ham = model.news_encoder((ga, hist_att))
+            ua = model.user_encoder.forward(inpt=(ha, ham))
+            sa = torch.relu(model.rec_model(ua, c))
+            grads.append(torch.autograd.grad(sa, ga)[0])
+        grads = torch.cat(grads)
+        attr = torch.sum(torch.sum(grads * da, dim=0) * hist_emb.detach(), dim=(0, 3))
+        out[f'{name}/grads'] = grads.detach().numpy()
+        out[f'{name}/attr'] = attr.detach().numpy()
+        out[f'{name}/s_true'] = np.array(float(sa))
+        print('explain', name, 's_true', float(sa), 's_attr', float(attr.sum()))
+    np.savez_compressed(os.path.join(HERE, 'explain.npz'), **out)
+
+
 def dataset_fixture():
     """row G: the reference's NewsRecDataset + custom_collate_fn (xnrs/data/dataset.py:48-163, utils.py:190-204) on a tiny
     synthetic news table / behaviour log, in eval mode (all candidates) and train mode (seeded negative sampling).  The
@@ -301,9 +340,13 @@ if __name__ == '__main__':
     if '--dataset-only' in sys.argv:
         dataset_fixture()
         sys.exit(0)
+    if '--explain-only' in sys.argv:
+        explain_fixture()
+        sys.exit(0)
     for i, (name, over) in enumerate(MODELS.items()):
         model_fixture(name, over, seed=20 + i)
     layer_fixtures()
     loss_metric_fixtures()
     dataset_fixture()
+    explain_fixture()
     print('golden fixtures written to', HERE)

@@ -271,12 +271,16 @@ class DotScoring(nn.Module):
 
 def merge_sides(history, candidates):
     """history and candidate titles go through the SAME encoder (parent.py:31-32): with index batches they are encoded in
-    one call (one de-duplication, half the launches).  Returns (merged IndexedTitles, n_hist) or None."""
+    one call (one de-duplication, half the launches).  The ids are laid out [all history slots | all candidate slots] so
+    that both sides come back as contiguous row blocks (no strided slicing / copies on either pass).
+    Returns (merged IndexedTitles of shape (1, b*nh + b*nc), b, nh, nc) or None."""
     if (isinstance(history, IndexedTitles) and isinstance(candidates, IndexedTitles)
             and history.store is candidates.store and history.news_ids.shape[0] == candidates.news_ids.shape[0]):
         dev = history.store.device
-        ids = torch.cat([history.news_ids.to(dev), candidates.news_ids.to(dev)], dim=1)
-        return IndexedTitles(history.store, ids), history.news_ids.shape[1]
+        b, nh = history.news_ids.shape
+        nc = candidates.news_ids.shape[1]
+        ids = torch.cat([history.news_ids.to(dev).reshape(1, -1), candidates.news_ids.to(dev).reshape(1, -1)], dim=1)
+        return IndexedTitles(history.store, ids), b, nh, nc
     return None
 
 
@@ -287,9 +291,10 @@ def encode_both_sides(encoder, history, candidates):
         h, hm = encoder(history)
         c, _ = encoder(candidates)
         return h, hm, c
-    e, m = encoder(merged[0])
-    nh = merged[1]
-    return e[:, :nh], m[:, :nh], e[:, nh:]
+    titles, b, nh, nc = merged
+    e, m = encoder(titles)
+    e, m = e[0], m[0]
+    return e[:b * nh].view(b, nh, -1), m[:b * nh].view(b, nh, 1), e[b * nh:].view(b, nc, -1)
 
 
 class ParentRec(nn.Module):

@@ -150,9 +150,11 @@ class NAML(nn.Module):
         mt, ma = merge_sides(hist_title_features, cand_title_features), merge_sides(hist_abstract_features, cand_abstract_features)
         if mt is not None and ma is not None:       # index batches: both sides in one pass through the shared encoders
             dev = _dev(self)
-            e, m = self._news(mt[0], ma[0], torch.cat([hist_ctg.to(dev), cand_ctg.to(dev)], 1),
-                              torch.cat([hist_subctg.to(dev), cand_subctg.to(dev)], 1))
-            h, hm, c = e[:, :mt[1]], m[:, :mt[1]], e[:, mt[1]:]
+            _, b, nh, nc = mt                        # ids laid out [all history slots | all candidate slots]
+            flat = lambda hx, cx: torch.cat([hx.to(dev).reshape(1, -1), cx.to(dev).reshape(1, -1)], 1)
+            e, m = self._news(mt[0], ma[0], flat(hist_ctg, cand_ctg), flat(hist_subctg, cand_subctg))
+            e, m = e[0], m[0]
+            h, hm, c = e[:b * nh].view(b, nh, -1), m[:b * nh].view(b, nh, 1), e[b * nh:].view(b, nc, -1)
         else:
             h, hm = self._news(hist_title_features, hist_abstract_features, hist_ctg, hist_subctg)
             c, _ = self._news(cand_title_features, cand_abstract_features, cand_ctg, cand_subctg)
@@ -265,9 +267,12 @@ class LSTUR(nn.Module):
         mt = merge_sides(hf['title_emb'], cf['title_emb'])
         if mt is not None:
             dev = _dev(self)
-            sub = None if hs is None else torch.cat([hs.to(dev), cs.to(dev)], 1)
-            e, m = self.news_encoder(mt[0], torch.cat([hf['category_index'].to(dev), cf['category_index'].to(dev)], 1), sub)
-            h, hm, c = e[:, :mt[1]], m[:, :mt[1]], e[:, mt[1]:]
+            _, b, nh, nc = mt                        # ids laid out [all history slots | all candidate slots]
+            flat = lambda hx, cx: torch.cat([hx.to(dev).reshape(1, -1), cx.to(dev).reshape(1, -1)], 1)
+            sub = None if hs is None else flat(hs, cs)
+            e, m = self.news_encoder(mt[0], flat(hf['category_index'], cf['category_index']), sub)
+            e, m = e[0], m[0]
+            h, hm, c = e[:b * nh].view(b, nh, -1), m[:b * nh].view(b, nh, 1), e[b * nh:].view(b, nc, -1)
         else:
             h, hm = self.news_encoder(hf['title_emb'], hf['category_index'], hs)
             c, _ = self.news_encoder(cf['title_emb'], cf['category_index'], cs)

@@ -230,16 +230,18 @@ def run_eval(args):
 
     def hook(name, args_):
         s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        recs.append((name, s_, e_))
+        recs.append((name, s_, e_, args_))
         return s_, e_
 
     K.set_event_hook(hook)
     one_pass(imp_dev)
     sync_all()
     K.set_event_hook(None)
-    per_entry = {}
-    for name, s_, e_ in recs:
+    per_entry, gemm_flop = {}, 0.0
+    for name, s_, e_, a_ in recs:
         per_entry[name] = per_entry.get(name, 0.0) + s_.elapsed_time(e_)
+        if name == 'xnrs_gemm':
+            gemm_flop += 2.0 * a_[2] * a_[3] * a_[4]
     pk, pk_kind = peaks()
     n_cand = int(imp['offsets'][-1])
     # algorithmic bytes of the score+rank kernel: one T-wide fp32 vector per candidate + the user vector + ids/targets
@@ -257,11 +259,22 @@ def run_eval(args):
         'e2e': {'value': n_imp / e2e_s, 'unit': UNIT,
                 'h2d_bytes_per_step': sum(v.numel() * v.element_size() for v in imp.values()), 'd2h_bytes_per_step': 56},
         'gpu_launches': launches,
-        'roofline': {'kernel': 'eval_impressions_kernel (gather + dot + segmented rank sort + metrics), whole impression phase',
-                     'bound': 'hbm', 'achieved': score_bytes / (score_ms * 1e-3) / 1e9, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
-                     'frac': score_bytes / (score_ms * 1e-3) / 1e9 / pk['hbm_gbs'], 'traffic': None,
-                     'peak_source': pk_kind,
+        # dominant kernel of the pass: the tcgen05 GEMMs of the catalogue encode (title fc1 + heads + per-article pooling
+        # logits), FLOPs = sum of 2MNK over the launches / their CUDA-event time
+        'roofline': {'kernel': 'tcgen05 GEMMs of the pass (gemm_tc2_kernel / gemm_tc_kernel: catalogue fc1 with tanh epilogue, heads, '
+                               'per-article pooling logits)', 'bound': 'tensor',
+                     'achieved': gemm_flop / (per_entry.get('xnrs_gemm', 0.0) * 1e-3) / 1e12 if per_entry.get('xnrs_gemm') else None,
+                     'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
+                     'frac': (gemm_flop / (per_entry['xnrs_gemm'] * 1e-3) / 1e12 / pk['bf16_tflops_sustained']) if per_entry.get('xnrs_gemm') else None,
+                     'traffic': None,
+                     'peak_source': f'{pk_kind} (sustained bf16 GEMM). 3xTF32 (fp32-accurate) has 1/6 of this peak as its own ceiling',
                      'per_entry_point_ms': {k: round(v, 3) for k, v in sorted(per_entry.items(), key=lambda kv: -kv[1])}},
+        # the HBM-bound scoring kernel: algorithmic bytes (one T-wide vector per candidate + ids/targets) / its event time
+        'roofline_scoring': {'kernel': 'eval_impressions_kernel (gather + dot + segmented rank sort + metrics)', 'bound': 'hbm',
+                             'achieved': score_bytes / (per_entry.get('xnrs_eval_impressions', score_ms) * 1e-3) / 1e9,
+                             'peak': pk['hbm_gbs'], 'unit': 'GB/s',
+                             'frac': score_bytes / (per_entry.get('xnrs_eval_impressions', score_ms) * 1e-3) / 1e9 / pk['hbm_gbs'],
+                             'peak_source': pk_kind},
         'clocks': clocks.summary(),
     }
     if rank == 0:
@@ -404,7 +417,10 @@ def main():
             c[2] += 2.0 * a[2] * a[3] * a[4]
             c[3] += a[4] if a[0] else a[2]
     (d_ta, d_tb, d_1, d_2, d_act), (d_ms, d_n, d_flop, d_rows) = max(classes.items(), key=lambda kv: kv[1][0])
-    d_name = (f'gemm_tc_kernel<128> {"TN" if d_ta else "NT"} '
+    d_m, d_n_ = (d_1, d_2) if d_ta else (d_rows // max(d_n, 1), d_1)
+    kern = ('gemm_tc2_kernel (cta_group::2 CTA pair, 256x256 tile)' if (args.precision == 'tf32x3' and d_n_ > 128 and d_m >= 256)
+            else ('gemm_tc_kernel<256>' if args.precision in ('tf32', 'bf16') and d_n_ > 128 else 'gemm_tc_kernel<128>'))
+    d_name = (f'{kern} {"TN" if d_ta else "NT"} '
               + (f'M={d_1} N={d_2} K~{d_rows // max(d_n, 1)} (fc1 weight gradient)' if d_ta
                  else f'M~{d_rows // max(d_n, 1)} N={d_1} K={d_2} ' + ('(title fc1 forward, tanh epilogue)' if d_act == 2 else '(forward)')))
     d_tflops = d_flop / (d_ms * 1e-3) / 1e12 if d_ms else None
@@ -412,9 +428,9 @@ def main():
         'kernel': d_name if args.precision != 'fp32' else 'gemm_simt_kernel ' + d_name,
         'bound': 'tensor', 'achieved': d_tflops, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
         'frac': d_tflops / pk['bf16_tflops_sustained'] if d_tflops else None,
-        # dram__bytes_read.sum + dram__bytes_write.sum of ONE such launch (ncu --set full, profiles/README.md): 472.7 MB read
-        # + 129.1 MB written at M=150 k rows = 4013 B/row, i.e. exactly the algorithmic A row (3072 B) + C row (1024 B)
-        'traffic': 4013.0 * (d_rows / max(d_n, 1)) if (not d_ta and args.precision != 'fp32') else None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of ONE such launch (ncu --set full, profiles/README.md): 473.2 MB read
+        # + 131.4 MB written at M=153 562 rows = 3937 B/row, i.e. the algorithmic A row (3072 B) + C row (1024 B): no re-reads
+        'traffic': 3937.0 * (d_rows / max(d_n, 1)) if (not d_ta and args.precision != 'fp32' and d_2 == 768 and d_1 == 256) else None,
         'peak_source': f'{pk_kind} (sustained bf16 GEMM; kernel timed inside a long step). The kernel computes in TF32 '
                        f'(3 MMAs per product in the fp32-accurate 3xTF32 mode): its own ceiling is 1/6 of this bf16 peak',
         'launches_timed': d_n, 'avg_launch_ms': d_ms / max(d_n, 1),

@@ -802,7 +802,9 @@ int gemm_tensorcore(const GemmArgs &a, int precision, cudaStream_t st, int *stat
     if (use2 && g_opt_2cta == -1) {
         const long long t2 = cdiv(a.M, 256) * cdiv(a.N, 256);
         const long long ksplit = a.act == XNRS_ACT_NONE ? (a.split_k > 0 ? a.split_k : std::max(1LL, std::min(cdiv(a.K, 512), (long long)(num_sms() / 2) / t2))) : 1;
-        if (t2 * ksplit < num_sms()) use2 = false;
+        const long long npairs = num_sms() / 2;
+        // split-K launches size their splits to one full wave of pairs; un-split ones need at least two waves of tiles
+        if (ksplit > 1 ? (t2 * ksplit * 10 < npairs * 9) : (t2 < 2 * npairs)) use2 = false;
     }
     const int BN = use2 ? 128 : ((p.passes == 1 && a.N > 128 && cdiv(a.M, TBM) * cdiv(a.N, 256) >= num_sms()) ? 256 : 128);
     const int half = TBM * TBK * 4 + BN * TBK * 4;

@@ -85,11 +85,16 @@ class CatalogueEvaluator:
         per = (n + w - 1) // w
         lo, hi = min(r * per, n), min((r + 1) * per, n)
         vecs, masks = [], []
-        for a in range(lo, hi, self.news_chunk):
-            ids = torch.arange(a, min(hi, a + self.news_chunk), device=self.device, dtype=torch.int32)
-            e, mk = self._encode_ids(ids)
-            vecs.append(e)
-            masks.append(mk)
+        from .models.components import TextEncoder
+        dedup, TextEncoder.dedup_titles = TextEncoder.dedup_titles, False      # catalogue ids are distinct: nothing to de-duplicate
+        try:
+            for a in range(lo, hi, self.news_chunk):
+                ids = torch.arange(a, min(hi, a + self.news_chunk), device=self.device, dtype=torch.int32)
+                e, mk = self._encode_ids(ids)
+                vecs.append(e)
+                masks.append(mk)
+        finally:
+            TextEncoder.dedup_titles = dedup
         T = vecs[0].shape[1] if vecs else self._encode_ids(torch.zeros(1, device=self.device, dtype=torch.int32))[0].shape[1]
         local = torch.zeros((per, T), device=self.device, dtype=torch.float32)
         lmask = torch.zeros(per, device=self.device, dtype=torch.float32)

@@ -98,6 +98,12 @@ int xnrs_rowdot(const float *x, const float *w, const float *b, long long n, int
  * table (V,T), T % 4 == 0, T <= 1024; row_mask (V, nullable); attn (R*L, nullable) receives the weights */
 int xnrs_logitpool_fwd(const float *table, long long V, int T, const float *logit, const float *row_mask, const int *ids,
                        long long R, int L, float *attn, float *pooled, xnrs_stream_t st);
+/* backward of xnrs_logitpool_fwd: d_logit (V) and d_table (V,T) ACCUMULATE (zero them first); attn is the saved forward output */
+int xnrs_logitpool_bwd(const float *table, long long V, int T, const int *ids, const float *attn, const float *d_pooled,
+                       long long R, int L, float *d_logit, float *d_table, xnrs_stream_t st);
+/* backward of the per-item logit <tanh-hidden row, w2> + b2: d_hid (n,A) written; d_w2 (A) and d_b2 (1) accumulate */
+int xnrs_logit_bwd(const float *hid, const float *w2, const float *d_logit, long long n, int A, float *d_hid, float *d_w2,
+                   float *d_b2, xnrs_stream_t st);
 /* masked mean pooling (layers.py:25-37) */
 int xnrs_meanpool_fwd(const float *x, const float *mask, long long R, int L, int F, float *pooled,
                       xnrs_stream_t st);

@@ -354,3 +354,19 @@ def _xnrs_logitpool_fwd(table, V, T, logit, row_mask, ids, R, L, attn, pooled):
     if attn is not None:
         attn.copy_(a.reshape(attn.shape))
     pooled.copy_(torch.einsum('rl,rlt->rt', a, table[v]))
+
+
+def _xnrs_logitpool_bwd(table, V, T, ids, attn, d_pooled, R, L, d_logit, d_table):
+    v = ids.reshape(R, L).long()
+    a = attn.reshape(R, L)
+    da = torch.einsum('rt,rlt->rl', d_pooled, table[v])
+    dl = a * (da - (a * da).sum(1, keepdim=True))
+    d_logit.index_add_(0, v.reshape(-1), dl.reshape(-1))
+    d_table.index_add_(0, v.reshape(-1), (a[:, :, None] * d_pooled[:, None, :]).reshape(R * L, -1))
+
+
+def _xnrs_logit_bwd(hid, w2, d_logit, n, A, d_hid, d_w2, d_b2):
+    h = hid.reshape(n, A)
+    d_hid.copy_((d_logit[:, None] * w2[None, :] * (1 - h * h)).reshape(d_hid.shape))
+    d_w2.add_(h.T @ d_logit)
+    d_b2.add_(d_logit.sum())

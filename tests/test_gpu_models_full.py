@@ -125,3 +125,33 @@ def test_title_dedup_gives_the_same_loss_and_gradients(name, monkeypatch):
     # identical mathematics; only the fp32 summation order differs (scatter-add, split-K atomics on the smaller GEMMs).
     # NRMS' two attention stacks amplify that noise most (measured 1.8e-4 of the gradient scale)
     assert_close(g0, g1, 5e-4 if name == 'nrms' else 1e-5, 'flat gradient')
+
+
+def test_item_logit_pooling_gives_the_same_loss_and_gradients(monkeypatch):
+    """CL: pooling the history from the batch's distinct article vectors (pooler fc1 once per article, default) ==
+    gathering the (b,H,E) history first and pooling it slot by slot like the reference (user_encoding.py:69-77)"""
+    from xnrs_b200.models.components import ParentRec
+    cfg = dict(BASE, **MODELS['cl'], seq_len=30, hist_len=50, st_hist_len=50)
+    cat = syn.make_catalogue(200, 30, VOCAB, 768, seed=3)
+    raw = syn.make_train_batch(200, 16, 50, n_users=N_USERS, seed=4)
+    raw['hist_ids'][2, 5:] = 0
+    store = TitleStore(cat.token_table.to(DEV), cat.title_tokens.to(DEV))
+    results = []
+    for on in (True, False):
+        monkeypatch.setattr(ParentRec, 'item_logits', on)
+        torch.manual_seed(1)
+        model = make_model(cfg)
+        with torch.no_grad():
+            for p in model.parameters():
+                if p.dim() > 1:
+                    p.mul_(1.5)
+        trainer = ContrastiveRankingTrainer(cfg, model)
+        model.eval()
+        trainer.optimizer.zero_grad()
+        total, _, _, preds = trainer.losses(syn.index_batch(store, cat, raw, DEV))
+        total.backward()
+        results.append((total.detach().clone(), preds.detach().clone(), trainer.optimizer.flat_g.clone()))
+    (l0, p0, g0), (l1, p1, g1) = results
+    assert_close(l0, l1, 1e-6, 'loss')
+    assert_close(p0, p1, 1e-5, 'predictions', atol=1e-6)
+    assert_close(g0, g1, 2e-5, 'flat gradient')

@@ -135,3 +135,30 @@ def test_test_step_metrics(device):
     want = O.impression_metrics(fx['batch/targets'][0, :, 0], s)
     for k in ('auc', 'rr', 'ndcg@5', 'ndcg@10', 'ctr@1', 'ctr@10'):
         assert abs(out[k] - want[k]) < 1e-4, k
+
+
+def test_item_logit_pooling_equals_pooling_the_gathered_rows(device):
+    """ItemLogitPoolFn (pooler fc1 once per distinct item, history given as ids) == AdditivePoolFn on the gathered rows:
+    values and every gradient (item vectors, fc1, fc2)"""
+    g = torch.Generator().manual_seed(3)
+    V, T, A, R, L = 23, 16, 12, 7, 5
+    table = torch.randn(V, T, generator=g)
+    row_mask = (torch.rand(V, generator=g) > 0.2).float()
+    ids = torch.randint(0, V, (R, L), generator=g, dtype=torch.int32)
+    w1, b1 = torch.randn(A, T, generator=g) * 0.3, torch.randn(A, generator=g) * 0.1
+    w2, b2 = torch.randn(A, generator=g) * 0.3, torch.randn(1, generator=g) * 0.1
+    gout = torch.randn(R, T, generator=g)
+    outs = []
+    for fused in (True, False):
+        leaves = [t.clone().to(device).requires_grad_() for t in (table, w1, b1, w2, b2)]
+        tb, a1, c1, a2, c2 = leaves
+        if fused:
+            pooled, _ = K.ItemLogitPoolFn.apply(tb, row_mask.to(device), ids.to(device), a1, c1, a2, c2)
+        else:
+            x = K.EmbeddingFn.apply(tb, ids.to(device).reshape(-1), None)
+            m = row_mask.to(device)[ids.to(device).long().reshape(-1)]
+            pooled, _ = K.AdditivePoolFn.apply(x, None, m, a1, c1, a2, c2, R, L, None)
+        (pooled * gout.to(device)).sum().backward()
+        outs.append([pooled.detach()] + [t.grad for t in leaves])
+    for name, a, b in zip(('pooled', 'd table', 'd fc1.weight', 'd fc1.bias', 'd fc2.weight', 'd fc2.bias'), *outs):
+        assert_close(a, b, 2e-5, name, atol=1e-6)

@@ -341,6 +341,173 @@ logitpool_fwd_kernel(const float *__restrict__ table, const float *__restrict__ 
         if (c * 32 + lane < T4) out[c * 32 + lane] = acc[c];
 }
 
+
+// backward of logitpool_fwd, one warp per group r (user).  With a_l = E_l / (sum + 1e-8):
+//   da_l = <d_pooled_r, table[id_l]>,   dlogit_l = a_l (da_l - sum_j a_j da_j)
+//   d_logit[id_l] += dlogit_l           (scalar reductions: many slots share an article)
+//   d_table[id_l] += a_l d_pooled_r     (16-byte vector reductions)
+// The (R, L, T) gradient of the gathered history never exists.
+template <int NV>
+__global__ void __launch_bounds__(256)
+logitpool_bwd_kernel(const float *__restrict__ table, const int *__restrict__ ids, const float *__restrict__ attn,
+                     const float *__restrict__ d_pooled, long long R, int L, int T4, float *__restrict__ d_logit,
+                     float *__restrict__ d_table) {
+    const int lane = threadIdx.x & 31;
+    const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= R) return;
+    const int *idr = ids + r * L;
+    const float *ar = attn + r * L;
+    const float4 *t4 = reinterpret_cast<const float4 *>(table);
+    float4 g[NV];
+    const float4 *g4 = reinterpret_cast<const float4 *>(d_pooled) + r * T4;
+#pragma unroll
+    for (int c = 0; c < NV; ++c) g[c] = (c * 32 + lane < T4) ? g4[c * 32 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (L <= 64) {
+        // fast path: the lane keeps (id, a, da) of slots lane and lane + 32 in registers; every table row is read once
+        float a_[2], da_[2] = {0.f, 0.f};
+        int v_[2];
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const int l = b * 32 + lane;
+            v_[b] = l < L ? idr[l] : 0;
+            a_[b] = l < L ? ar[l] : 0.f;
+        }
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const int cnt = min(32, L - 32 * b);
+            for (int j0 = 0; j0 < cnt; j0 += 4) {
+                float acc[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int j = min(j0 + q, cnt - 1);
+                    const float aj = __shfl_sync(0xffffffffu, a_[b], j);
+                    const int vj = __shfl_sync(0xffffffffu, v_[b], j);
+                    float s = 0.f;
+                    if (aj != 0.f) {                               // warp-uniform: padded slots are never read
+                        const float4 *row = t4 + (long long)vj * T4;
+#pragma unroll
+                        for (int c = 0; c < NV; ++c) {
+                            if (c * 32 + lane < T4) {
+                                const float4 x = __ldg(row + c * 32 + lane);
+                                s = fmaf(x.x, g[c].x, s); s = fmaf(x.y, g[c].y, s);
+                                s = fmaf(x.z, g[c].z, s); s = fmaf(x.w, g[c].w, s);
+                            }
+                        }
+                    }
+                    acc[q] = s;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (lane == j0 + q) da_[b] = acc[q];
+            }
+        }
+        const float tot = warp_sum(a_[0] * da_[0] + a_[1] * da_[1]);
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            if (a_[b] != 0.f) atomicAdd(d_logit + v_[b], a_[b] * (da_[b] - tot));
+            const int cnt = min(32, L - 32 * b);
+            for (int j = 0; j < cnt; ++j) {
+                const float aj = __shfl_sync(0xffffffffu, a_[b], j);
+                const int vj = __shfl_sync(0xffffffffu, v_[b], j);
+                if (aj == 0.f) continue;
+                float4 *drow = reinterpret_cast<float4 *>(d_table) + (long long)vj * T4;
+#pragma unroll
+                for (int c = 0; c < NV; ++c)
+                    if (c * 32 + lane < T4)
+                        atomicAdd(drow + c * 32 + lane, make_float4(aj * g[c].x, aj * g[c].y, aj * g[c].z, aj * g[c].w));
+            }
+        }
+        return;
+    }
+    // long groups: pass 1 computes the group-wide sum_j a_j da_j, pass 2 recomputes da per slot and scatters
+    float dot = 0.f;
+    for (int l0 = 0; l0 < L; l0 += 32) {
+        const int l = l0 + lane;
+        const int v = l < L ? idr[l] : 0;
+        const float a = l < L ? ar[l] : 0.f;
+        const int cnt = min(32, L - l0);
+        for (int j = 0; j < cnt; ++j) {
+            const float aj = __shfl_sync(0xffffffffu, a, j);
+            const int vj = __shfl_sync(0xffffffffu, v, j);
+            if (aj == 0.f) continue;
+            const float4 *row = t4 + (long long)vj * T4;
+            float s = 0.f;
+#pragma unroll
+            for (int c = 0; c < NV; ++c) {
+                if (c * 32 + lane < T4) {
+                    const float4 x = __ldg(row + c * 32 + lane);
+                    s = fmaf(x.x, g[c].x, s); s = fmaf(x.y, g[c].y, s);
+                    s = fmaf(x.z, g[c].z, s); s = fmaf(x.w, g[c].w, s);
+                }
+            }
+            dot = fmaf(aj, s, dot);                 // per-lane partial of a_j da_j
+        }
+    }
+    const float tot = warp_sum(dot);
+    for (int l0 = 0; l0 < L; l0 += 32) {
+        const int l = l0 + lane;
+        const int v = l < L ? idr[l] : 0;
+        const float a = l < L ? ar[l] : 0.f;
+        const int cnt = min(32, L - l0);
+        for (int j = 0; j < cnt; ++j) {
+            const float aj = __shfl_sync(0xffffffffu, a, j);
+            const int vj = __shfl_sync(0xffffffffu, v, j);
+            if (aj == 0.f) continue;
+            const float4 *row = t4 + (long long)vj * T4;
+            float4 *drow = reinterpret_cast<float4 *>(d_table) + (long long)vj * T4;
+            float s = 0.f;
+#pragma unroll
+            for (int c = 0; c < NV; ++c) {
+                if (c * 32 + lane < T4) {
+                    const float4 x = __ldg(row + c * 32 + lane);
+                    s = fmaf(x.x, g[c].x, s); s = fmaf(x.y, g[c].y, s);
+                    s = fmaf(x.z, g[c].z, s); s = fmaf(x.w, g[c].w, s);
+                    atomicAdd(drow + c * 32 + lane, make_float4(aj * g[c].x, aj * g[c].y, aj * g[c].z, aj * g[c].w));
+                }
+            }
+            s = warp_sum(s);
+            if (lane == 0) atomicAdd(d_logit + vj, aj * (s - tot));
+        }
+    }
+}
+
+// backward of the per-item logit  logit_v = <hid_v, w2> + b2  with hid = tanh(.):  d_hid[v,j] = d_logit[v] w2[j] (1 - hid^2),
+// d_w2[j] += sum_v d_logit[v] hid[v,j],  d_b2 += sum_v d_logit[v]     (d_w2 / d_b2 accumulate: per-CTA partials, one atomic set)
+__global__ void __launch_bounds__(256)
+logit_bwd_kernel(const float *__restrict__ hid, const float *__restrict__ w2, const float *__restrict__ d_logit, long long n,
+                 int A, float *__restrict__ d_hid, float *__restrict__ d_w2, float *__restrict__ d_b2) {
+    extern __shared__ float sm[];           // [A] partial d_w2
+    __shared__ float db;
+    for (int j = threadIdx.x; j < A; j += blockDim.x) sm[j] = 0.f;
+    if (threadIdx.x == 0) db = 0.f;
+    __syncthreads();
+    const long long rows_per = (n + gridDim.x - 1) / gridDim.x;
+    const long long v0 = blockIdx.x * rows_per, v1 = min(n, v0 + rows_per);
+    for (int j = threadIdx.x; j < A; j += blockDim.x) {
+        const float w = w2[j];
+        float gw = 0.f;
+        for (long long v = v0; v < v1; ++v) {
+            const float dl = d_logit[v];
+            const float h = hid[v * A + j];
+            gw = fmaf(dl, h, gw);
+            d_hid[v * A + j] = dl * w * (1.f - h * h);
+        }
+        sm[j] = gw;
+    }
+    float s = 0.f;
+    for (long long v = v0 + threadIdx.x; v < v1; v += blockDim.x) s += d_logit[v];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0 && s != 0.f) atomicAdd(&db, s);
+    __syncthreads();
+    for (int j = threadIdx.x; j < A; j += blockDim.x) atomicAdd(d_w2 + j, sm[j]);
+    if (threadIdx.x == 0) atomicAdd(d_b2, db);
+}
+
 }  // namespace xnrs
 
 using namespace xnrs;
@@ -452,6 +619,38 @@ extern "C" int xnrs_logitpool_fwd(const float *table, long long V, int T, const 
     else if (T4 <= 128) XNRS_LP(4);
     else XNRS_LP(8);
 #undef XNRS_LP
+    XNRS_LAUNCHED();
+    return XNRS_OK;
+}
+
+extern "C" int xnrs_logitpool_bwd(const float *table, long long V, int T, const int *ids, const float *attn,
+                                  const float *d_pooled, long long R, int L, float *d_logit, float *d_table,
+                                  xnrs_stream_t st) {
+    XNRS_REQUIRE(R >= 0 && L > 0 && V > 0, "bad sizes");
+    XNRS_REQUIRE(T > 0 && T % 4 == 0 && T <= 1024, "T must be a multiple of 4, at most 1024");
+    if (R == 0) return XNRS_OK;
+    XNRS_REQUIRE(table && ids && attn && d_pooled && d_logit && d_table, "null pointer");
+    XNRS_REQUIRE((((uintptr_t)table | (uintptr_t)d_pooled | (uintptr_t)d_table) & 15) == 0, "16-byte alignment");
+    const unsigned grid = (unsigned)cdiv(R, 8);
+    const int T4 = T / 4;
+#define XNRS_LPB(NV) logitpool_bwd_kernel<NV><<<grid, 256, 0, STREAM(st)>>>(table, ids, attn, d_pooled, R, L, T4, d_logit, d_table)
+    if (T4 <= 32) XNRS_LPB(1);
+    else if (T4 <= 64) XNRS_LPB(2);
+    else if (T4 <= 128) XNRS_LPB(4);
+    else XNRS_LPB(8);
+#undef XNRS_LPB
+    XNRS_LAUNCHED();
+    return XNRS_OK;
+}
+
+extern "C" int xnrs_logit_bwd(const float *hid, const float *w2, const float *d_logit, long long n, int A, float *d_hid,
+                              float *d_w2, float *d_b2, xnrs_stream_t st) {
+    XNRS_REQUIRE(n >= 0 && A > 0, "bad sizes");
+    if (n == 0) return XNRS_OK;
+    XNRS_REQUIRE(hid && w2 && d_logit && d_hid && d_w2 && d_b2, "null pointer");
+    long long blocks = cdiv(n, 32), cap = 2LL * num_sms();
+    logit_bwd_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, A * sizeof(float), STREAM(st)>>>(hid, w2, d_logit, n, A, d_hid,
+                                                                                                    d_w2, d_b2);
     XNRS_LAUNCHED();
     return XNRS_OK;
 }

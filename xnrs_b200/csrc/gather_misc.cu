@@ -42,14 +42,20 @@ __global__ void gather_rows_kernel(const float *__restrict__ table, long long V,
 }
 
 __global__ void scatter_add_rows_kernel(float *__restrict__ dtable, long long V, int D, const int *__restrict__ rows,
-                                        long long R, const float *__restrict__ dout, long long ld, int skip_row) {
+                                        long long R, const float *__restrict__ dout, long long ld, int skip_row, bool vec) {
     int lane = threadIdx.x & 31;
     long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
     for (long long r = w; r < R; r += nw) {
         long long dst = rows[r];
         if (dst < 0 || dst >= V || dst == skip_row) continue;
-        for (int c = lane; c < D; c += 32) atomicAdd(dtable + dst * D + c, dout[r * ld + c]);
+        if (vec) {          // 16-byte vector reductions (red.global.add.v4.f32): a quarter of the atomic transactions
+            const float4 *src = reinterpret_cast<const float4 *>(dout + r * ld);
+            float4 *d4 = reinterpret_cast<float4 *>(dtable + dst * D);
+            for (int c = lane; c < (D >> 2); c += 32) atomicAdd(d4 + c, src[c]);
+        } else {
+            for (int c = lane; c < D; c += 32) atomicAdd(dtable + dst * D + c, dout[r * ld + c]);
+        }
     }
 }
 
@@ -195,7 +201,8 @@ extern "C" int xnrs_scatter_add_rows(float *dtable, long long V, int D, const in
     XNRS_REQUIRE(D > 0 && ld_dout >= D, "bad sizes");
     if (R == 0) return XNRS_OK;
     XNRS_REQUIRE(dtable && rows && dout, "null pointer");
-    scatter_add_rows_kernel<<<ew_grid(R * 32, 256), 256, 0, STREAM(st)>>>(dtable, V, D, rows, R, dout, ld_dout, skip_row);
+    const bool vec = D % 4 == 0 && ld_dout % 4 == 0 && (((uintptr_t)dtable | (uintptr_t)dout) & 15) == 0;
+    scatter_add_rows_kernel<<<ew_grid(R * 32, 256), 256, 0, STREAM(st)>>>(dtable, V, D, rows, R, dout, ld_dout, skip_row, vec);
     XNRS_LAUNCHED();
     return XNRS_OK;
 }

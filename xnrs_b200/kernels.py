@@ -307,6 +307,48 @@ class AdditivePoolFn(torch.autograd.Function):
         return d_x, None, None, d_w1, d_b1, d_w2, d_b2, None, None, None
 
 
+class ItemLogitPoolFn(torch.autograd.Function):
+    """layers.AdditiveAttention (layers.py:47-69) over R groups whose L rows are GATHERED from a table of distinct items
+    (ids (R,L) int32): the logit w2.tanh(fc1 x + b1) + b2 of a slot depends only on the item in it, so fc1 runs once per
+    item (V rows) instead of once per slot (R*L rows), forward and backward.  Same values / gradients as pooling the
+    gathered rows.  -> pooled (R,T), attn (R,L)."""
+
+    @staticmethod
+    def forward(ctx, table, row_mask, ids, w1, b1, w2, b2):
+        V, T = table.shape
+        R, L = ids.shape
+        ids = _i32(ids)
+        hid = gemm(table, w1, trans_b=True, bias=b1, act=ACT_TANH)
+        logit = rowdot(hid, w2, b2)
+        attn = torch.empty((R, L), device=table.device, dtype=torch.float32)
+        pooled = torch.empty((R, T), device=table.device, dtype=torch.float32)
+        call('xnrs_logitpool_fwd', table, V, T, logit, row_mask, ids, R, L, attn, pooled)
+        ctx.save_for_backward(table, ids, w1, w2, hid, attn)
+        ctx.set_materialize_grads(False)
+        return pooled, attn
+
+    @staticmethod
+    def backward(ctx, d_pooled, d_attn):
+        if d_attn is not None:
+            raise RuntimeError('ItemLogitPoolFn: no gradient path through the returned weights')
+        table, ids, w1, w2, hid, attn = ctx.saved_tensors
+        V, T = table.shape
+        R, L = ids.shape
+        A = w1.shape[0]
+        dev = table.device
+        d_table = torch.zeros_like(table)
+        d_logit = torch.zeros(V, device=dev, dtype=torch.float32)
+        call('xnrs_logitpool_bwd', table, V, T, ids, attn, _f32(d_pooled), R, L, d_logit, d_table)
+        d_hid = torch.empty_like(hid)
+        d_w2 = torch.zeros_like(w2)
+        d_b2 = torch.zeros(1, device=dev, dtype=torch.float32)
+        call('xnrs_logit_bwd', hid, w2, d_logit, V, A, d_hid, d_w2, d_b2)
+        d_w1 = gemm(d_hid, table, trans_a=True)
+        d_b1 = colsum(d_hid)
+        gemm(d_hid, w1, out=d_table, accumulate=True)
+        return d_table, None, None, d_w1, d_b1, d_w2, d_b2
+
+
 class PersonalizedPoolFn(torch.autograd.Function):
     """layers.PersonalizedAttention (layers.py:88-101); group r uses query row r // rows_per_query."""
 

@@ -184,26 +184,34 @@ class TextEncoder(nn.Module):
         pooled, _ = self.pooler.pool(x2, rows, mask, R, S, seg)
         return _apply_head(self.head, pooled) if hasattr(self, 'head') else pooled
 
+    def encode_unique(self, inpt: IndexedTitles):
+        """index batches: -> (e_u (U,E) vectors of the DISTINCT articles of the batch, inv (b*n,) slot -> row of e_u or None
+        when nothing was de-duplicated, cm_u (U,) collapsed title mask)"""
+        device = _dev(self)
+        store = inpt.store
+        ids = inpt.news_ids.to(device)
+        b, n = ids.shape
+        S = store.seq_len
+        if self.dropout.p > 0 and self.training:
+            raise NotImplementedError('input dropout on gathered titles (every shipped config has p_dropout 0)')
+        uniq, inv = ids.reshape(-1), None
+        if self.dedup_titles and b * n >= 64:
+            uniq, inv = torch.unique(uniq, return_inverse=True)                 # id plumbing (one host sync)
+        nu = uniq.numel()
+        if self.skip_padding and self.att is None and hasattr(self.pooler, 'fc1'):
+            rows, seg, cm_u = ragged_token_rows(store.title_tokens, uniq)
+            e_u = self._encode(store.token_table, rows, None, nu, S, seg)
+        else:
+            rows, mask = K.expand_titles(store.title_tokens, uniq)
+            e_u = self._encode(store.token_table, rows, mask, nu, S)
+            cm_u = K.collapse_mask(mask, nu, S)
+        return e_u, inv, cm_u
+
     def forward(self, inpt):
         device = _dev(self)
         if isinstance(inpt, IndexedTitles):
-            store = inpt.store
-            ids = inpt.news_ids.to(device)
-            b, n = ids.shape
-            S = store.seq_len
-            if self.dropout.p > 0 and self.training:
-                raise NotImplementedError('input dropout on gathered titles (every shipped config has p_dropout 0)')
-            uniq, inv = ids.reshape(-1), None
-            if self.dedup_titles and b * n >= 64:
-                uniq, inv = torch.unique(uniq, return_inverse=True)                 # id plumbing (one host sync)
-            nu = uniq.numel()
-            if self.skip_padding and self.att is None and hasattr(self.pooler, 'fc1'):
-                rows, seg, cm_u = ragged_token_rows(store.title_tokens, uniq)
-                e_u = self._encode(store.token_table, rows, None, nu, S, seg)
-            else:
-                rows, mask = K.expand_titles(store.title_tokens, uniq)
-                e_u = self._encode(store.token_table, rows, mask, nu, S)
-                cm_u = K.collapse_mask(mask, nu, S)
+            b, n = inpt.news_ids.shape
+            e_u, inv, cm_u = self.encode_unique(inpt)
             if inv is None:
                 return e_u.view(b, n, self.out_dim), cm_u.view(b, n, 1)
             e = K.EmbeddingFn.apply(e_u, inv, None)                                # gather back; bwd = scatter-add
@@ -234,6 +242,20 @@ class UserEncoder(nn.Module):
             assert emb_dim is not None
             self.head = nn.Sequential(nn.Linear(emb_dim, emb_dim, bias=bias), activation,
                                       nn.Linear(emb_dim, emb_dim, bias=bias))
+
+    def can_pool_items(self) -> bool:
+        """history given as ids into a table of distinct item vectors: possible when the encoder is [no dropout, no
+        attention] -> additive pooler (-> head), i.e. StandardRec / CL"""
+        return (self.att is None and isinstance(self.pooler, AdditiveAttention)
+                and not (self.dropout.p > 0 and self.training))
+
+    def forward_items(self, items: torch.Tensor, item_mask: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
+        """== forward((items[ids], item_mask[ids])) with the pooler's fc1 evaluated once per item (ItemLogitPoolFn)"""
+        p = self.pooler
+        pooled, _ = K.ItemLogitPoolFn.apply(items, item_mask, ids, p.fc1.weight, p.fc1.bias, p.fc2.weight.reshape(-1), p.fc2.bias)
+        if hasattr(self, 'head'):
+            pooled = _apply_head(self.head, pooled)
+        return pooled.unsqueeze(1)
 
     def forward(self, inpt, add_features: Optional[dict] = None, return_weights: bool = False):
         x, m = inpt
@@ -308,7 +330,23 @@ class ParentRec(nn.Module):
         self.rec_model = rec_model
         self.text_feature = text_feature
 
+    # index batches + additive user pooler: pool the history straight from the batch's DISTINCT article vectors (the
+    # pooler's fc1 runs once per article, the (b,H,E) history tensor and its gradient never exist).  Off: gather first.
+    item_logits = True
+
     def _forward(self, history, candidates, add_user_feats=None, return_embeddings: bool = False):
+        merged = merge_sides(history, candidates) if self.item_logits else None
+        if (merged is not None and isinstance(self.news_encoder, TextEncoder) and isinstance(self.user_encoder, UserEncoder)
+                and self.user_encoder.can_pool_items()):
+            titles, b, nh, nc = merged
+            e_u, inv, cm_u = self.news_encoder.encode_unique(titles)
+            if inv is None:
+                inv = torch.arange(b * (nh + nc), device=e_u.device, dtype=torch.int32)
+            inv = K._i32(inv)
+            u = self.user_encoder.forward_items(e_u, cm_u, inv[:b * nh].view(b, nh))
+            c = K.EmbeddingFn.apply(e_u, inv[b * nh:], None).view(b, nc, -1)
+            r = self.rec_model(u, c)
+            return (r, u, c) if return_embeddings else r
         h, hm, c = encode_both_sides(self.news_encoder, history, candidates)
         u = self.user_encoder((h, hm), add_user_feats)
         r = self.rec_model(u, c)

@@ -25,8 +25,12 @@ def peaks():
     return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, 'fallback'
 
 
-def timeit(fn, n=20, flush=None):
-    for _ in range(3):
+REPS = int(os.environ.get('XNRS_BENCH_REPS', '20'))        # 1 under ncu --set full (every launch is replayed ~40x)
+
+
+def timeit(fn, n=None, flush=None):
+    n = n or REPS
+    for _ in range(3 if REPS > 1 else 0):
         fn()
     torch.cuda.synchronize()
     tot = 0.0
@@ -138,9 +142,44 @@ def bench_misc(flush):
            note='latency-bound: 6 MB of operands')
 
 
+def bench_eval(flush):
+    # MIND-large-shaped scoring: 160k article vectors of 256, impressions of ~37 candidates, 50-click histories
+    V, T, n_imp, H = 160_000, 256, 65_536, 50
+    g = torch.Generator(device='cpu').manual_seed(0)
+    vecs = torch.randn(V, T, device=DEV)
+    sizes = torch.randint(5, 74, (n_imp,), generator=g)
+    offsets = torch.cat([torch.zeros(1, dtype=torch.long), sizes.cumsum(0)]).to(DEV)
+    n_cand = int(offsets[-1])
+    zipf = lambda n: (torch.rand(n, generator=g).pow(3.0) * (V - 1)).to(torch.int32) + 1
+    cand, hist = zipf(n_cand).to(DEV), zipf(n_imp * H).view(n_imp, H).to(DEV)
+    targets = (torch.rand(n_cand, generator=g) < 0.1).float().to(DEV)
+    user = torch.randn(n_imp, T, device=DEV)
+    scores = torch.empty(n_cand, device=DEV)
+    metrics = torch.empty(n_imp, 6, device=DEV, dtype=torch.float64)
+    ms = timeit(lambda: K.call('xnrs_eval_impressions', user, vecs, T, cand, offsets, targets, n_imp, 1, scores, metrics), flush=flush)
+    report(f'xnrs_eval_impressions {n_imp} impressions, {n_cand} candidates, T={T} (gather + dot + rank sort + 6 metrics)', ms,
+           nbytes=n_cand * (T * 4 + 12) + n_imp * (T * 4 + 8 + 48))
+    logit, mask = torch.randn(V, device=DEV) * 0.1, torch.ones(V, device=DEV)
+    attn, pooled = torch.empty(n_imp, H, device=DEV), torch.empty(n_imp, T, device=DEV)
+    ms = timeit(lambda: K.call('xnrs_logitpool_fwd', vecs, V, T, logit, mask, hist, n_imp, H, attn, pooled), flush=flush)
+    report(f'xnrs_logitpool_fwd {n_imp} users x {H} history rows of {T} (per-article logits)', ms,
+           nbytes=n_imp * H * (T * 4 + 12) + n_imp * T * 4,
+           note='algorithmic bytes count every gathered row; popular (Zipf) rows of the 164 MB table are L2 hits, hence > HBM peak')
+    # training shape: 1024 users, 8748 distinct articles of the batch
+    V2, R = 8748, 1024
+    tab, lg, mk = torch.randn(V2, T, device=DEV), torch.randn(V2, device=DEV) * 0.1, torch.ones(V2, device=DEV)
+    ids = (torch.rand(R * H, generator=g).pow(3.0) * (V2 - 1)).to(torch.int32).view(R, H).to(DEV)
+    at, po = torch.empty(R, H, device=DEV), torch.empty(R, T, device=DEV)
+    K.call('xnrs_logitpool_fwd', tab, V2, T, lg, mk, ids, R, H, at, po)
+    dpo, dlg, dtab = torch.randn(R, T, device=DEV), torch.zeros(V2, device=DEV), torch.zeros(V2, T, device=DEV)
+    ms = timeit(lambda: K.call('xnrs_logitpool_bwd', tab, V2, T, ids, at, dpo, R, H, dlg, dtab))
+    report(f'xnrs_logitpool_bwd {R} users x {H} slots -> {V2} articles (fused gather + scatter reductions)', ms,
+           nbytes=R * H * (2 * T * 4 + 8) + R * T * 4, note='atomic-reduction bound: 51200 x 64 16-byte reductions onto 8748 rows')
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument('--only', default='mha,gather,pool,misc')
+    ap.add_argument('--only', default='mha,gather,pool,misc,eval')
     args = ap.parse_args()
     flush = torch.zeros(64 * 1024 * 1024, device=DEV)        # 256 MB > 126 MB L2
     for name in args.only.split(','):

@@ -287,7 +287,7 @@ extern "C" int xnrs_eval_impressions(const float *user, const float *news_vecs, 
         XNRS_LAUNCHED();
     }
     // ... and the CTA-per-impression kernel for the longer ones (it skips impressions the warp kernel took)
-    long long cap = 16LL * num_sms();
+    long long cap = warp_ok ? 2LL * num_sms() : 16LL * num_sms();        // with the warp kernel this one only sweeps for long impressions
     eval_impressions_kernel<<<(unsigned)(n_imp < cap ? n_imp : cap), MT, 0, STREAM(st)>>>(
         user, news_vecs, T, cand_ids, offsets, targets, n_imp, act, scores_io, metrics_out, warp_ok ? WCAP + 1 : 0);
     XNRS_LAUNCHED();

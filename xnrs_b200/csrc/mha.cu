@@ -432,6 +432,24 @@ __global__ void mha_bwd_kernel(const float *__restrict__ q, const float *__restr
     }
 }
 
+// warps per block for the one-warp-per-(title, head) kernels: the count that keeps the most warps resident per SM given the
+// per-warp shared-memory slab (ncu on the first version: 4 warps/block with a 31 KB slab left ONE block = 4 warps per SM)
+static int best_warps_per_block(size_t per_warp_bytes, int regs_per_thread) {
+    const size_t smem_sm = 227 * 1024;
+    int best = 1, best_resident = 0;
+    for (int wf = 1; wf <= 4; wf *= 2) {
+        const size_t block = per_warp_bytes * wf + 1024;                 // + per-block reservation
+        if (block > smem_sm) break;
+        int blocks = (int)(smem_sm / block);
+        const int by_regs = 65536 / (regs_per_thread * 32 * wf);
+        if (blocks > by_regs) blocks = by_regs;
+        if (blocks > 32) blocks = 32;
+        const int resident = blocks * wf;
+        if (resident >= best_resident) { best_resident = resident; best = wf; }
+    }
+    return best;
+}
+
 template <int DK>
 static int launch_fwd(const float *q, const float *k, const float *v, long long ld, const float *mask, long long R,
                       int L, int h, const float *keep, float p_drop, unsigned long long seed, float *o, float *lse,
@@ -439,7 +457,7 @@ static int launch_fwd(const float *q, const float *k, const float *v, long long 
     {   // fast path: two-pass softmax, packed FMAs, 4 warps per block while the per-warp slab (K, V, scores) fits
         const size_t per_warp = (size_t)(2 * L * DK + 32 * L) * sizeof(float);
         if (per_warp <= 110 * 1024) {
-            const int wf = per_warp * 4 <= 220 * 1024 ? 4 : (per_warp * 2 <= 220 * 1024 ? 2 : 1);
+            const int wf = best_warps_per_block(per_warp, 96);
             cudaFuncSetAttribute(mha_fwd_fast_kernel<DK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * wf));
             mha_fwd_fast_kernel<DK><<<(unsigned)cdiv(R * h, wf), wf * 32, per_warp * wf, st>>>(q, k, v, ld, mask, R, L, h, keep,
                                                                                              p_drop, seed, o, lse);
@@ -464,7 +482,7 @@ static int launch_bwd(const float *q, const float *k, const float *v, const floa
     {
         const size_t per_warp = (size_t)((4 * L * DK + 2 * L * (L | 1) + 3) & ~3) * sizeof(float);
         if (per_warp <= 110 * 1024) {
-            const int wf = per_warp * 4 <= 220 * 1024 ? 4 : (per_warp * 2 <= 220 * 1024 ? 2 : 1);
+            const int wf = best_warps_per_block(per_warp, 255);
             cudaFuncSetAttribute(mha_bwd_fast_kernel<DK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * wf));
             mha_bwd_fast_kernel<DK><<<(unsigned)cdiv(R * h, wf), wf * 32, per_warp * wf, st>>>(
                 q, k, v, o, d_o, ld, mask, lse, R, L, h, keep, p_drop, seed, dq, dk_, dv);

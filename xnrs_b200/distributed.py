@@ -40,10 +40,14 @@ class DistInfoNCEFn(torch.autograd.Function):
         w, r = world(), rank()
         Ba, E = emb.shape
         dev = emb.device
-        emb_all = torch.empty((w * Ba, E), device=dev, dtype=torch.float32)
-        lab_all = torch.empty(w * Ba, device=dev, dtype=torch.int32)
-        dist.all_gather_into_tensor(emb_all, emb.contiguous())
-        dist.all_gather_into_tensor(lab_all, labels.to(torch.int32).contiguous())
+        # ONE all-gather: the int32 labels ride along as an extra (bit-cast) column of the embedding block
+        packed = torch.empty((Ba, E + 1), device=dev, dtype=torch.float32)
+        packed[:, :E] = emb
+        packed[:, E] = labels.to(torch.int32).contiguous().view(torch.float32)
+        packed_all = torch.empty((w * Ba, E + 1), device=dev, dtype=torch.float32)
+        dist.all_gather_into_tensor(packed_all, packed)
+        emb_all = packed_all[:, :E].contiguous()
+        lab_all = packed_all[:, E].contiguous().view(torch.int32)
         Bk, row0 = w * Ba, r * Ba
         ehat = torch.empty_like(emb_all)
         inv_norm = torch.empty(Bk, device=dev, dtype=torch.float32)
@@ -66,13 +70,19 @@ class DistInfoNCEFn(torch.autograd.Function):
         ehat_a = ehat[row0:row0 + Ba]
         d_ehat = K.gemm(G, ehat_a, trans_a=True)                              # key side, all Bk rows
         K.gemm(G, ehat, out=d_ehat[row0:row0 + Ba], accumulate=True)          # anchor side, local rows
-        dist.all_reduce(d_ehat)
-        d_all = torch.empty_like(ehat)
-        K.call('xnrs_infonce_normalize_bwd', d_ehat, ehat, inv_norm, stats, 1.0, Bk, E, d_all)
+        # every rank only needs the summed gradient of ITS rows: reduce-scatter (half the bytes of an all-reduce)
+        d_loc = torch.empty((Ba, E), device=ehat.device, dtype=torch.float32)
+        if dist.get_backend() == 'gloo':                                      # CPU tests: gloo has no reduce-scatter
+            dist.all_reduce(d_ehat)
+            d_loc.copy_(d_ehat[row0:row0 + Ba])
+        else:
+            dist.reduce_scatter_tensor(d_loc, d_ehat)
+        d_a = torch.empty_like(d_loc)
+        K.call('xnrs_infonce_normalize_bwd', d_loc, ehat_a.contiguous(), inv_norm[row0:row0 + Ba].contiguous(), stats, 1.0, Ba, E, d_a)
         # parameter gradients are averaged over ranks afterwards; this term is already the gradient of the
         # GLOBAL loss, so pre-multiply by world to survive the averaging
         d_emb = torch.empty((Ba, E), device=ehat.device, dtype=torch.float32)
-        K.call('xnrs_axpby', Ba * E, float(w), K._f32(g).reshape(1), d_all[row0:row0 + Ba].contiguous(), 0.0, d_emb)
+        K.call('xnrs_axpby', Ba * E, float(w), K._f32(g).reshape(1), d_a, 0.0, d_emb)
         return d_emb, None, None
 
 

@@ -155,3 +155,33 @@ def test_item_logit_pooling_gives_the_same_loss_and_gradients(monkeypatch):
     assert_close(l0, l1, 1e-6, 'loss')
     assert_close(p0, p1, 1e-5, 'predictions', atol=1e-6)
     assert_close(g0, g1, 2e-5, 'flat gradient')
+
+
+def test_naml_article_level_encoding_gives_the_same_loss_and_gradients(monkeypatch):
+    """NAML: the 4-view news encoder once per distinct article + item-logit user pooling (default) == once per slot"""
+    from xnrs_b200.models.zoo import NAML
+    cfg = dict(BASE, **MODELS['naml'], seq_len=30, hist_len=50, st_hist_len=50)
+    cat = syn.make_catalogue(200, 30, VOCAB, 768, seed=3, with_abstract=True)
+    raw = syn.make_train_batch(200, 16, 50, n_users=N_USERS, seed=4)
+    raw['hist_ids'][2, 5:] = 0
+    store = TitleStore(cat.token_table.to(DEV), cat.title_tokens.to(DEV))
+    astore = TitleStore(store.token_table, cat.abstract_tokens.to(DEV))
+    results = []
+    for on in (True, False):
+        monkeypatch.setattr(NAML, 'article_level', on)
+        torch.manual_seed(1)
+        model = make_model(cfg)
+        with torch.no_grad():
+            for p in model.parameters():
+                if p.dim() > 1:
+                    p.mul_(1.5)
+        trainer = ContrastiveRankingTrainer(cfg, model)
+        model.eval()
+        trainer.optimizer.zero_grad()
+        total, _, _, preds = trainer.losses(syn.index_batch(store, cat, raw, DEV, abstract_store=astore))
+        total.backward()
+        results.append((total.detach().clone(), preds.detach().clone(), trainer.optimizer.flat_g.clone()))
+    (l0, p0, g0), (l1, p1, g1) = results
+    assert_close(l0, l1, 1e-6, 'loss')
+    assert_close(p0, p1, 1e-5, 'predictions', atol=1e-6)
+    assert_close(g0, g1, 2e-5, 'flat gradient')

@@ -162,3 +162,35 @@ def test_item_logit_pooling_equals_pooling_the_gathered_rows(device):
         outs.append([pooled.detach()] + [t.grad for t in leaves])
     for name, a, b in zip(('pooled', 'd table', 'd fc1.weight', 'd fc1.bias', 'd fc2.weight', 'd fc2.bias'), *outs):
         assert_close(a, b, 2e-5, name, atol=1e-6)
+
+
+@pytest.mark.parametrize('name', ['cl', 'nrms', 'naml', 'lstur_con', 'npa'])
+def test_index_batches_equal_dense_batches(name, device):
+    """the index fast path (device-resident token table + int32 news ids: title de-duplication, padding-free pooling,
+    one encoder pass for both sides, per-article pooling logits / article-level NAML) gives the scores and parameter
+    gradients of the reference-format dense batch built from the same ids"""
+    from xnrs_b200 import synthetic as syn
+    from xnrs_b200.data import TitleStore
+    fx = load_npz('model_' + name)
+    cfg = dict(fixture_cfg(fx), device=device)
+    n_news, S, H, D = 40, cfg['seq_len'], cfg['hist_len'], cfg['d_backbone']
+    cat = syn.make_catalogue(n_news, S, vocab=100, dim=D, seed=11, with_abstract=(name == 'naml'),
+                             n_categories=cfg['n_categories'], n_subcategories=cfg['n_subcategories'])
+    raw = syn.make_train_batch(n_news, 12, H, n_neg=cfg['n_negatives'], n_users=cfg['n_users'], seed=12)   # 12*(H+1+K) >= 64 slots
+    store = TitleStore(cat.token_table.to(device), cat.title_tokens.to(device))
+    astore = TitleStore(store.token_table, cat.abstract_tokens.to(device)) if name == 'naml' else None
+    grads, scores = [], []
+    for kind in ('index', 'dense'):
+        model = make_model(cfg)
+        model.load_state_dict({k: torch.tensor(v) for k, v in sub(fx, 'sd').items()})
+        model.to(device).eval()
+        batch = (syn.index_batch(store, cat, raw, device, abstract_store=astore) if kind == 'index'
+                 else syn.dense_batch(cat, raw, with_abstract=(name == 'naml')))
+        s = model(batch)
+        (s * torch.linspace(-1, 1, s.numel(), device=s.device).view_as(s)).sum().backward()
+        scores.append(s.detach())
+        grads.append({k: (p.grad.detach().clone() if p.grad is not None else torch.zeros_like(p)) for k, p in model.named_parameters()})
+    assert_close(scores[0], scores[1], 2e-5, 'scores')
+    gmax = max(float(g.abs().max()) for g in grads[1].values())
+    for k in grads[1]:
+        assert_close(grads[0][k], grads[1][k], 1e-4, 'grad ' + k, atol=2e-6 * gmax)

@@ -11,6 +11,7 @@ import torch
 import torch.nn as nn
 
 from .. import kernels as K
+from ..data import IndexedTitles
 from .components import (AdditiveAttention, DotScoring, MultiHeadAttention, ParentRec, PersonalizedAttention,
                          TextEncoder, UserEncoder, _dev, _flat_mask, merge_sides)
 
@@ -112,6 +113,8 @@ class NRMS(ParentRec):
 class NAML(nn.Module):
     """naml.py:7-160 — title + abstract encoders, category / sub-category views, 4-view additive pooling."""
 
+    article_level = True        # index batches: run the 4-view news encoder once per distinct article (off: once per slot)
+
     def __init__(self, cfg, rec_model):
         super().__init__()
         cfg = _cfg(cfg)
@@ -152,6 +155,35 @@ class NAML(nn.Module):
             dev = _dev(self)
             _, b, nh, nc = mt                        # ids laid out [all history slots | all candidate slots]
             flat = lambda hx, cx: torch.cat([hx.to(dev).reshape(1, -1), cx.to(dev).reshape(1, -1)], 1)
+            ids = mt[0].news_ids.reshape(-1)
+            if (self.article_level and ids.numel() >= 64 and torch.equal(ids, ma[0].news_ids.reshape(-1))
+                    and not (self.title_encoder.dropout.p > 0 and self.training)):
+                # Every view of a NAML news vector (title, abstract, category, sub-category: naml.py:82-107) is an attribute
+                # of the ARTICLE, so the whole 4-view encoder runs once per distinct article of the batch (id plumbing: one
+                # unique + the per-article category ids), and the user pooler works from those vectors (ItemLogitPoolFn).
+                uniq, inv = torch.unique(ids, return_inverse=True)
+                U = uniq.numel()
+                per_article = lambda slot_vals: torch.empty(U, device=dev, dtype=slot_vals.dtype).scatter_(0, inv, slot_vals.reshape(-1))
+                u_ids = uniq.view(1, U)
+                encs = (self.title_encoder, self.body_encoder)
+                saved = [enc.dedup_titles for enc in encs]
+                for enc in encs:
+                    enc.dedup_titles = False             # the ids are distinct already: no second unique / gather-back
+                try:
+                    e_u, cm_u = self._news(IndexedTitles(mt[0].store, u_ids), IndexedTitles(ma[0].store, u_ids),
+                                           per_article(flat(hist_ctg, cand_ctg)).view(1, U),
+                                           per_article(flat(hist_subctg, cand_subctg)).view(1, U))
+                finally:
+                    for enc, v in zip(encs, saved):
+                        enc.dedup_titles = v
+                e_u, cm_u, inv = e_u[0], K._f32(cm_u.reshape(-1)), K._i32(inv)
+                ue = self.user_encoder
+                u, _ = K.ItemLogitPoolFn.apply(e_u, cm_u, inv[:b * nh].view(b, nh), ue.fc1.weight, ue.fc1.bias,
+                                               ue.fc2.weight.reshape(-1), ue.fc2.bias)
+                u = u.unsqueeze(1)
+                c = K.EmbeddingFn.apply(e_u, inv[b * nh:], None).view(b, nc, -1)
+                r = self.rec_model(u, c)
+                return (r, u, c) if return_embeddings else r
             e, m = self._news(mt[0], ma[0], flat(hist_ctg, cand_ctg), flat(hist_subctg, cand_subctg))
             e, m = e[0], m[0]
             h, hm, c = e[:b * nh].view(b, nh, -1), m[:b * nh].view(b, nh, 1), e[b * nh:].view(b, nc, -1)

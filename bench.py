@@ -71,10 +71,11 @@ class ClockSampler:
 
     def __enter__(self):
         # nvidia-smi takes ~1 s (and driver locks: a 100 ms stall of the GPU work queue was measured) to initialise, so it
-        # is started and allowed to print its first sample BEFORE the timed region; inside the region it only polls
+        # is started and allowed to print its first sample BEFORE the timed region; inside the region it only polls (every
+        # 200 ms like the recipe's clocks line: polling at 25 ms was measured to stall short timed regions)
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                                          '-lms', '25', '-i', str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          '-lms', '200', '-i', str(self.index)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=lambda: self.rows.extend(self.proc.stdout), daemon=True)
             self.t.start()
             t0 = time.perf_counter()
@@ -307,6 +308,7 @@ def main():
     ap.add_argument('--workload', default='train', choices=['train', 'eval'])
     ap.add_argument('--model', default='cl', choices=list(MODEL_CFGS), help='cl is the headline (BASELINE configs[1])')
     ap.add_argument('--no-skip-padding', action='store_true', help='run pad tokens through the encoder like the reference does')
+    ap.add_argument('--no-prefetch', action='store_true', help='compute the id plumbing of each batch inside its own step')
     ap.add_argument('--no-dedup', action='store_true', help='encode every (impression, slot) title, not each distinct article once')
     ap.add_argument('--eval-impressions', type=int, default=376_471)
     args = ap.parse_args()
@@ -377,9 +379,12 @@ def main():
     def timed_resident():
         sync_all()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dp.prefetch(resident[0])
         t0.record()
         for i in range(args.steps):
             dp.train_step(resident[i % n_batches])
+            if not args.no_prefetch:         # input pipeline: the next batch's id plumbing runs on a side stream meanwhile
+                dp.prefetch(resident[(i + 1) % n_batches])
         t1.record()
         sync_all()
         ms = torch.tensor([t0.elapsed_time(t1)], device=dev, dtype=torch.float64)
@@ -454,18 +459,25 @@ def main():
     }
 
     # ---- timed region 2: end to end through the public trainer API with HOST (pinned) index buffers ----
-    def e2e_step(i):
-        out = dp.train_step(syn.index_batch(store, cat, pinned[i % n_batches], dev, abstract_store=astore))
-        return float(out['loss'])            # device -> host read of the step's loss (4 bytes, synchronises)
+    def h2d(i):                              # host (pinned) int32 ids / targets / labels -> device, on the main stream
+        b = syn.index_batch(store, cat, pinned[i % n_batches], dev, abstract_store=astore)
+        return b, torch.cuda.current_stream().record_event()
 
-    e2e_step(0)
+    def e2e_step(cur, i):
+        nxt = h2d(i + 1)                     # tiny copy, queued BEFORE this step so the side stream can plan it meanwhile
+        out = dp.train_step(cur[0])
+        if not args.no_prefetch:
+            dp.prefetch(nxt[0], after=nxt[1])
+        return float(out['loss']), nxt       # device -> host read of the step's loss (4 bytes, synchronises)
+
+    _, cur = e2e_step(h2d(0), 0)
     sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     wall0 = time.perf_counter()
     e0.record()
     last = 0.0
     for i in range(args.steps):
-        last = e2e_step(i)
+        last, cur = e2e_step(cur, i + 1)
     e1.record()
     sync_all()
     wall = time.perf_counter() - wall0

@@ -194,3 +194,28 @@ def test_index_batches_equal_dense_batches(name, device):
     gmax = max(float(g.abs().max()) for g in grads[1].values())
     for k in grads[1]:
         assert_close(grads[0][k], grads[1][k], 1e-4, 'grad ' + k, atol=2e-6 * gmax)
+
+
+def test_prefetched_id_plumbing_is_equivalent_and_single_use(device):
+    """ParentRec.prefetch computes the merged-side TitlePlan ahead of the step (side stream on CUDA): same scores as the
+    in-line plumbing, and the plan is consumed by exactly one forward (a recycled batch object is planned afresh)"""
+    from xnrs_b200 import synthetic as syn
+    from xnrs_b200.data import TitleStore
+    fx = load_npz('model_cl')
+    cfg = dict(fixture_cfg(fx), device=device)
+    cat = syn.make_catalogue(40, cfg['seq_len'], vocab=100, dim=cfg['d_backbone'], seed=11)
+    raw = syn.make_train_batch(40, 12, cfg['hist_len'], n_neg=cfg['n_negatives'], n_users=cfg['n_users'], seed=12)
+    store = TitleStore(cat.token_table.to(device), cat.title_tokens.to(device))
+    model = make_model(cfg)
+    model.load_state_dict({k: torch.tensor(v) for k, v in sub(fx, 'sd').items()})
+    model.to(device).eval()
+    batch = syn.index_batch(store, cat, raw, device)
+    with torch.no_grad():
+        plain = model(batch)
+        assert model.prefetch(batch)
+        hist = batch['user_features']['history']['title_emb']
+        assert hist._merged is not None and hist._merged[1][0].plan is not None
+        fetched = model(batch)
+        assert hist._merged is None                                   # consumed
+        again = model(batch)                                          # in-line plumbing again
+    assert torch.equal(plain, fetched) and torch.equal(plain, again)

@@ -57,10 +57,63 @@ class TitleStore:
 
 
 @dataclass
+class TitlePlan:
+    """index plumbing of one encoder pass over a set of news ids — a pure function of the ids (no model state), so it can
+    be computed ahead of the step on a side stream (`prefetch`), where its two host syncs (sizes of the distinct-article
+    and real-token sets) overlap the previous step instead of idling the GPU.
+      uniq (U,) distinct news ids | inv (n,) int32 slot -> row of uniq (None: no de-duplication)
+      ragged: rows (tokens,) token-table rows of the real tokens, seg (U+1,) group offsets, mask None
+      fixed:  rows (U*S,), mask (U*S,) fp32, seg None
+      cm (U,) fp32 collapsed title mask; event: recorded on the producing stream after the last plan kernel"""
+    uniq: torch.Tensor
+    inv: 'torch.Tensor | None'
+    rows: torch.Tensor
+    seg: 'torch.Tensor | None'
+    mask: 'torch.Tensor | None'
+    cm: torch.Tensor
+    ragged: bool
+    dedup: bool
+    event: 'torch.cuda.Event | None' = None
+
+    def tensors(self):
+        return [t for t in (self.uniq, self.inv, self.rows, self.seg, self.mask, self.cm) if t is not None]
+
+    def acquire(self):
+        """make the plan usable on the current stream (no-op for plans computed in line)"""
+        if self.event is not None and self.uniq.is_cuda:
+            cur = torch.cuda.current_stream()
+            cur.wait_event(self.event)
+            for t in self.tensors():
+                t.record_stream(cur)
+            self.event = None
+        return self
+
+
+def plan_titles(store: TitleStore, ids_flat: torch.Tensor, dedup: bool, ragged: bool) -> TitlePlan:
+    """ids_flat (n,) int32 on the store's device -> TitlePlan (torch index ops + xnrs_expand_titles; two host syncs)"""
+    uniq, inv = ids_flat, None
+    if dedup:
+        uniq, inv = torch.unique(ids_flat, return_inverse=True)             # id plumbing (host sync: the distinct count)
+        inv = inv.to(torch.int32)
+    if ragged:
+        tok = store.title_tokens[uniq.long()]
+        valid = tok != 0
+        lens = valid.sum(1, dtype=torch.int32)
+        seg = torch.zeros(lens.numel() + 1, device=tok.device, dtype=torch.int32)
+        torch.cumsum(lens, 0, out=seg[1:])
+        rows = tok[valid].contiguous()                                      # host sync: the real-token count
+        return TitlePlan(uniq, inv, rows, seg, None, (lens > 0).to(torch.float32), True, dedup)
+    rows, mask = K.expand_titles(store.title_tokens, uniq)
+    cm = K.collapse_mask(mask, uniq.numel(), store.seq_len)
+    return TitlePlan(uniq, inv, rows, None, mask, cm, False, dedup)
+
+
+@dataclass
 class IndexedTitles:
     """what a batch carries instead of (x, m): int32 news ids (b, n) into a TitleStore."""
     store: TitleStore
     news_ids: torch.Tensor
+    plan: 'TitlePlan | None' = None          # optional pre-computed plumbing for these ids (see TitlePlan)
 
     def to(self, device):
         return IndexedTitles(self.store, self.news_ids.to(device, non_blocking=True))

@@ -99,6 +99,11 @@ class DataParallelTrainer:
                 trainer._compute_contrastive_loss = (
                     lambda e, l: DistInfoNCEFn.apply(K._f32(e.reshape(e.shape[0], -1)), l, temp))
 
+    def prefetch(self, batch: dict, after=None) -> bool:
+        """input-pipeline hook: prepare the id plumbing of the NEXT batch while the current step runs (models that support it)"""
+        fn = getattr(self.trainer.model, 'prefetch', None)
+        return bool(fn(batch, after)) if fn is not None else False
+
     def train_step(self, batch: dict) -> dict:
         tr = self.trainer
         tr.optimizer.zero_grad()

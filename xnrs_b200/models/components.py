@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 
 from .. import kernels as K
-from ..data import IndexedTitles
+from ..data import IndexedTitles, plan_titles
 
 
 def _dev(module: nn.Module) -> torch.device:
@@ -184,28 +184,29 @@ class TextEncoder(nn.Module):
         pooled, _ = self.pooler.pool(x2, rows, mask, R, S, seg)
         return _apply_head(self.head, pooled) if hasattr(self, 'head') else pooled
 
+    def plan_kind(self, n_slots: int):
+        """(dedup, ragged) of the plumbing this encoder wants for n_slots title slots"""
+        return (self.dedup_titles and n_slots >= 64,
+                self.skip_padding and self.att is None and hasattr(self.pooler, 'fc1'))
+
     def encode_unique(self, inpt: IndexedTitles):
-        """index batches: -> (e_u (U,E) vectors of the DISTINCT articles of the batch, inv (b*n,) slot -> row of e_u or None
-        when nothing was de-duplicated, cm_u (U,) collapsed title mask)"""
+        """index batches: -> (e_u (U,E) vectors of the DISTINCT articles of the batch, inv (b*n,) int32 slot -> row of e_u or
+        None when nothing was de-duplicated, cm_u (U,) collapsed title mask).  The id plumbing comes from ``inpt.plan`` when a
+        matching plan was prefetched, else it is computed here."""
         device = _dev(self)
         store = inpt.store
-        ids = inpt.news_ids.to(device)
-        b, n = ids.shape
+        b, n = inpt.news_ids.shape
         S = store.seq_len
         if self.dropout.p > 0 and self.training:
             raise NotImplementedError('input dropout on gathered titles (every shipped config has p_dropout 0)')
-        uniq, inv = ids.reshape(-1), None
-        if self.dedup_titles and b * n >= 64:
-            uniq, inv = torch.unique(uniq, return_inverse=True)                 # id plumbing (one host sync)
-        nu = uniq.numel()
-        if self.skip_padding and self.att is None and hasattr(self.pooler, 'fc1'):
-            rows, seg, cm_u = ragged_token_rows(store.title_tokens, uniq)
-            e_u = self._encode(store.token_table, rows, None, nu, S, seg)
-        else:
-            rows, mask = K.expand_titles(store.title_tokens, uniq)
-            e_u = self._encode(store.token_table, rows, mask, nu, S)
-            cm_u = K.collapse_mask(mask, nu, S)
-        return e_u, inv, cm_u
+        dedup, ragged = self.plan_kind(b * n)
+        plan = inpt.plan
+        if plan is None or plan.dedup != dedup or plan.ragged != ragged:
+            plan = plan_titles(store, inpt.news_ids.to(device).reshape(-1), dedup, ragged)
+        plan.acquire()
+        nu = plan.uniq.numel()
+        e_u = self._encode(store.token_table, plan.rows, plan.mask, nu, S, plan.seg)
+        return e_u, plan.inv, plan.cm
 
     def forward(self, inpt):
         device = _dev(self)
@@ -298,12 +299,51 @@ def merge_sides(history, candidates):
     Returns (merged IndexedTitles of shape (1, b*nh + b*nc), b, nh, nc) or None."""
     if (isinstance(history, IndexedTitles) and isinstance(candidates, IndexedTitles)
             and history.store is candidates.store and history.news_ids.shape[0] == candidates.news_ids.shape[0]):
+        cached = getattr(history, '_merged', None)             # set by prefetch_titles for exactly this pair;
+        if cached is not None and cached[0] is candidates:     # consumed once: a reused batch object is planned afresh
+            history._merged = None
+            return cached[1]
         dev = history.store.device
         b, nh = history.news_ids.shape
         nc = candidates.news_ids.shape[1]
         ids = torch.cat([history.news_ids.to(dev).reshape(1, -1), candidates.news_ids.to(dev).reshape(1, -1)], dim=1)
         return IndexedTitles(history.store, ids), b, nh, nc
     return None
+
+
+_prefetch_streams = {}
+
+
+def prefetch_titles(encoder, history, candidates, after=None) -> bool:
+    """compute the merged-side id plumbing of an upcoming (history, candidates) pair on a side stream (see TitlePlan): call
+    it right after enqueuing the current step.  `after`: CUDA event the ids become valid at (e.g. their H2D copy).
+    Returns False when the pair is not index-based."""
+    if not (isinstance(history, IndexedTitles) and isinstance(candidates, IndexedTitles) and isinstance(encoder, TextEncoder)):
+        return False
+    history._merged = None
+    merged = None
+    dev = history.store.device
+    if dev.type != 'cuda':
+        merged = merge_sides(history, candidates)
+        if merged is not None:
+            merged[0].plan = plan_titles(merged[0].store, merged[0].news_ids.reshape(-1), *encoder.plan_kind(merged[0].news_ids.numel()))
+            history._merged = (candidates, merged)
+        return merged is not None
+    side = _prefetch_streams.get(dev)
+    if side is None:
+        side = _prefetch_streams[dev] = torch.cuda.Stream(device=dev)
+    if after is not None:
+        side.wait_event(after)
+    with torch.cuda.stream(side):
+        merged = merge_sides(history, candidates)
+        if merged is None:
+            return False
+        titles = merged[0]
+        plan = plan_titles(titles.store, titles.news_ids.reshape(-1), *encoder.plan_kind(titles.news_ids.numel()))
+        plan.event = side.record_event()
+        titles.plan = plan
+    history._merged = (candidates, merged)
+    return True
 
 
 def encode_both_sides(encoder, history, candidates):
@@ -351,6 +391,11 @@ class ParentRec(nn.Module):
         u = self.user_encoder((h, hm), add_user_feats)
         r = self.rec_model(u, c)
         return (r, u, c) if return_embeddings else r
+
+    def prefetch(self, batch: dict, after=None) -> bool:
+        """index batches: compute the id plumbing of an UPCOMING batch on a side stream (overlaps the running step)"""
+        return prefetch_titles(self.news_encoder, batch['user_features']['history'][self.text_feature],
+                               batch['candidate_features'][self.text_feature], after)
 
     def forward(self, batch: dict, return_embeddings: bool = False):
         return self._forward(history=batch['user_features']['history'][self.text_feature],

@@ -145,6 +145,12 @@ class RankingTrainer:
         loss, preds, _ = K.ScoreLossFn.apply(None, K._f32(s).reshape(B, N), t, w, self.loss_kind)
         return loss, preds.unsqueeze(-1), None
 
+    def prefetch(self, batch: dict, after=None) -> bool:
+        """input-pipeline hook (no reference counterpart: the reference's DataLoader has num_workers 0): prepare the id
+        plumbing of an upcoming index batch on a side stream while the current step runs"""
+        fn = getattr(self.model, 'prefetch', None)
+        return bool(fn(batch, after)) if fn is not None else False
+
     def _train_step(self, batch: dict) -> dict:
         """BaseTrainer._train_step (training.py:97-112)."""
         self.optimizer.zero_grad()

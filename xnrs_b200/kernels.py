@@ -51,13 +51,22 @@ class _Strided:
         self.t = t
 
 
+_Tensor = torch.Tensor
+
+
 def _arg(a):
-    if isinstance(a, _Strided):
+    # hot path: ~10 arguments per launch, ~45 launches per step — exact-type checks first (scalars, None), then tensors
+    if a is None:
+        return None
+    t = type(a)
+    if t is int or t is float:
+        return a
+    if t is _Strided:
         a = a.t
         if not a.is_cuda:
             raise RuntimeError('xnrs_b200 kernels need CUDA tensors (there is no CPU path)')
         return a.data_ptr()
-    if isinstance(a, torch.Tensor):
+    if isinstance(a, _Tensor):
         if not a.is_cuda:
             raise RuntimeError('xnrs_b200 kernels need CUDA tensors (there is no CPU path)')
         if not a.is_contiguous():
@@ -234,6 +243,43 @@ def _resolve_rows(x, rows):
     return x, rows
 
 
+# ---- weight gradients straight into the optimiser's gradient buffer ----------------------------------------------------
+# Parameters managed by FlatAdam carry a persistent ``.grad`` view into its flat buffer and the mark ``_xnrs_direct``.  For
+# those, the backward GEMM / column-sum accumulates IN PLACE into ``param.grad`` (beta = 1) and autograd is handed ``None``:
+# same result as autograd's own ``param.grad += d_param``, without the temporary, its allocation and the add kernel
+# (12-20 launches per step).  Any other parameter (no trainer, torch.autograd.grad callers) takes the ordinary path.
+
+def _direct(param) -> Optional[torch.Tensor]:
+    g = param.grad if getattr(param, '_xnrs_direct', False) else None
+    return g if (g is not None and g.is_contiguous()) else None
+
+
+def _wgrad_gemm(param, a, b, **kw):
+    """d_param = a^T @ b (trans_a GEMM), accumulated into param.grad when possible"""
+    g = _direct(param)
+    if g is not None and g.dim() == 2:
+        gemm(a, b, trans_a=True, out=g, accumulate=True, **kw)
+        return None
+    return gemm(a, b, trans_a=True, **kw)
+
+
+def _wgrad_colsum(param, x2d):
+    g = _direct(param)
+    if g is not None:
+        colsum_into(x2d, g.view(-1))
+        return None
+    return colsum(x2d)
+
+
+def _wgrad_buffer(param, like):
+    """an accumulation target for kernels that ADD their parameter gradient: (buffer, value to return to autograd)"""
+    g = _direct(param)
+    if g is not None and g.numel() == like.numel():
+        return g.view(like.shape), None
+    z = torch.zeros_like(like)
+    return z, z
+
+
 class LinearFn(torch.autograd.Function):
     """y = x W^T + b (nn.Linear), optional fused table gather on x."""
 
@@ -242,6 +288,7 @@ class LinearFn(torch.autograd.Function):
         y = gemm(x, weight, trans_b=True, bias=bias, a_rows=rows)
         ctx.save_for_backward(x, rows, weight)
         ctx.has_bias = bias is not None
+        ctx.bias_param = bias
         return y
 
     @staticmethod
@@ -254,9 +301,9 @@ class LinearFn(torch.autograd.Function):
                 raise RuntimeError('no gradient flows into a gathered (frozen) table')
             dx = gemm(dy, weight)
         if _need(ctx, 2):
-            dw = gemm(dy, x, trans_a=True, b_rows=rows)
+            dw = _wgrad_gemm(weight, dy, x, b_rows=rows)
         if ctx.has_bias and _need(ctx, 3):
-            db = colsum(dy)
+            db = _wgrad_colsum(ctx.bias_param, dy)
         return dx, None, dw, db
 
 
@@ -269,17 +316,18 @@ class Mlp2Fn(torch.autograd.Function):
         y = gemm(h, w2, trans_b=True, bias=b2)
         ctx.save_for_backward(x, w1, w2, h)
         ctx.bias = b1 is not None
+        ctx.bias_params = (b1, b2)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, w1, w2, h = ctx.saved_tensors
         dy = _f32(dy)
-        dw2 = gemm(dy, h, trans_a=True)
+        dw2 = _wgrad_gemm(w2, dy, h)
         dh = gemm(dy, w2, act=ACT_RELU_MASK, aux=h)
-        dw1 = gemm(dh, x, trans_a=True)
-        db1 = colsum(dh) if ctx.bias else None
-        db2 = colsum(dy) if ctx.bias else None
+        dw1 = _wgrad_gemm(w1, dh, x)
+        db1 = _wgrad_colsum(ctx.bias_params[0], dh) if ctx.bias else None
+        db2 = _wgrad_colsum(ctx.bias_params[1], dy) if ctx.bias else None
         dx = gemm(dh, w1) if _need(ctx, 0) else None
         return dx, dw1, db1, dw2, db2
 
@@ -295,9 +343,10 @@ class AdditivePoolFn(torch.autograd.Function):
         hid = gemm(x, w1, trans_b=True, bias=b1, act=ACT_TANH, a_rows=rows)
         attn = torch.empty((R, L) if seg is None else (hid.shape[0],), device=x.device, dtype=torch.float32)
         pooled = torch.empty((R, F_), device=x.device, dtype=torch.float32)
-        call('xnrs_addpool_fwd', x, rows, mask, hid, w2, b2, seg, R, L, F_, A, attn, pooled)
+        call('xnrs_addpool_fwd', x, rows, mask, hid, w2.reshape(-1), b2, seg, R, L, F_, A, attn, pooled)
         ctx.save_for_backward(x, rows, w1, w2, hid, attn, seg)
         ctx.dims = (R, L, F_, A)
+        ctx.bias_params = (b1, b2)
         return pooled, attn
 
     @staticmethod
@@ -308,15 +357,17 @@ class AdditivePoolFn(torch.autograd.Function):
         d_pooled = _f32(d_pooled)
         d_attn = None if d_attn is None else _f32(d_attn)
         d_hid = torch.empty_like(hid)
-        d_w2 = torch.zeros_like(w2)
-        d_b2 = torch.zeros(1, device=dev, dtype=torch.float32)
+        b1, b2 = ctx.bias_params
+        w2_buf, d_w2 = _wgrad_buffer(w2, w2)
+        b2_buf, d_b2 = _wgrad_buffer(b2, b2)
         need_dx = _need(ctx, 0)
         if need_dx and rows is not None:
             raise RuntimeError('no gradient flows into a gathered (frozen) table')
         d_x = torch.empty_like(x) if need_dx else None
-        call('xnrs_addpool_bwd', x, rows, None, hid, w2, attn, d_pooled, d_attn, seg, R, L, F_, A, d_hid, d_w2, d_b2, d_x)
-        d_w1 = gemm(d_hid, x, trans_a=True, b_rows=rows)
-        d_b1 = colsum(d_hid)
+        call('xnrs_addpool_bwd', x, rows, None, hid, w2.reshape(-1), attn, d_pooled, d_attn, seg, R, L, F_, A, d_hid,
+             w2_buf.view(-1), b2_buf.view(-1), d_x)
+        d_w1 = _wgrad_gemm(w1, d_hid, x, b_rows=rows)
+        d_b1 = _wgrad_colsum(b1, d_hid)
         if need_dx:
             gemm(d_hid, w1, out=d_x, accumulate=True)
         return d_x, None, None, d_w1, d_b1, d_w2, d_b2, None, None, None
@@ -334,11 +385,12 @@ class ItemLogitPoolFn(torch.autograd.Function):
         R, L = ids.shape
         ids = _i32(ids)
         hid = gemm(table, w1, trans_b=True, bias=b1, act=ACT_TANH)
-        logit = rowdot(hid, w2, b2)
+        logit = rowdot(hid, w2.reshape(-1), b2)
         attn = torch.empty((R, L), device=table.device, dtype=torch.float32)
         pooled = torch.empty((R, T), device=table.device, dtype=torch.float32)
         call('xnrs_logitpool_fwd', table, V, T, logit, row_mask, ids, R, L, attn, pooled)
         ctx.save_for_backward(table, ids, w1, w2, hid, attn)
+        ctx.bias_params = (b1, b2)
         ctx.set_materialize_grads(False)
         return pooled, attn
 
@@ -355,11 +407,12 @@ class ItemLogitPoolFn(torch.autograd.Function):
         d_logit = torch.zeros(V, device=dev, dtype=torch.float32)
         call('xnrs_logitpool_bwd', table, V, T, ids, attn, _f32(d_pooled), R, L, d_logit, d_table)
         d_hid = torch.empty_like(hid)
-        d_w2 = torch.zeros_like(w2)
-        d_b2 = torch.zeros(1, device=dev, dtype=torch.float32)
-        call('xnrs_logit_bwd', hid, w2, d_logit, V, A, d_hid, d_w2, d_b2)
-        d_w1 = gemm(d_hid, table, trans_a=True)
-        d_b1 = colsum(d_hid)
+        b1, b2 = ctx.bias_params
+        w2_buf, d_w2 = _wgrad_buffer(w2, w2)
+        b2_buf, d_b2 = _wgrad_buffer(b2, b2)
+        call('xnrs_logit_bwd', hid, w2.reshape(-1), d_logit, V, A, d_hid, w2_buf.view(-1), b2_buf.view(-1))
+        d_w1 = _wgrad_gemm(w1, d_hid, table)
+        d_b1 = _wgrad_colsum(b1, d_hid)
         gemm(d_hid, w1, out=d_table, accumulate=True)
         return d_table, None, None, d_w1, d_b1, d_w2, d_b2
 
@@ -419,6 +472,7 @@ class MultiHeadAttentionFn(torch.autograd.Function):
         y = gemm(o, wo, trans_b=True, bias=bo)
         ctx.save_for_backward(x, rows, mask, wq, wk, wv, wo, q, k, v, o, lse, keep)
         ctx.cfg = (R, L, n_heads, dk, D, p_drop, seed)
+        ctx.bias_params = (bq, bk, bv, bo)
         return y
 
     @staticmethod
@@ -426,15 +480,16 @@ class MultiHeadAttentionFn(torch.autograd.Function):
         x, rows, mask, wq, wk, wv, wo, q, k, v, o, lse, keep = ctx.saved_tensors
         R, L, h, dk, D, p_drop, seed = ctx.cfg
         dy = _f32(dy)
-        d_wo = gemm(dy, o, trans_a=True)
-        d_bo = colsum(dy)
+        bq, bk, bv, bo = ctx.bias_params
+        d_wo = _wgrad_gemm(wo, dy, o)
+        d_bo = _wgrad_colsum(bo, dy)
         d_o = gemm(dy, wo)
         dq, dk_, dv = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
         call('xnrs_mha_bwd', q, k, v, o, d_o, D, mask, lse, R, L, h, dk, keep, p_drop, seed, dq, dk_, dv)
-        d_wq = gemm(dq, x, trans_a=True, b_rows=rows)
-        d_wk = gemm(dk_, x, trans_a=True, b_rows=rows)
-        d_wv = gemm(dv, x, trans_a=True, b_rows=rows)
-        d_bq, d_bk, d_bv = colsum(dq), colsum(dk_), colsum(dv)
+        d_wq = _wgrad_gemm(wq, dq, x, b_rows=rows)
+        d_wk = _wgrad_gemm(wk, dk_, x, b_rows=rows)
+        d_wv = _wgrad_gemm(wv, dv, x, b_rows=rows)
+        d_bq, d_bk, d_bv = _wgrad_colsum(bq, dq), _wgrad_colsum(bk, dk_), _wgrad_colsum(bv, dv)
         d_x = None
         if _need(ctx, 0):
             if rows is not None:

@@ -60,7 +60,7 @@ class AdditiveAttention(nn.Module):
     def pool(self, x2: torch.Tensor, rows, mask, R: int, L: int, seg=None):
         """(R*L, F) rows (or table + row index) -> pooled (R, F), weights (R, L); seg: ragged group offsets (R+1)"""
         return K.AdditivePoolFn.apply(x2, rows, mask, self.fc1.weight, self.fc1.bias,
-                                      self.fc2.weight.reshape(-1), self.fc2.bias, R, L, seg)
+                                      self.fc2.weight, self.fc2.bias, R, L, seg)
 
     def forward(self, x: torch.Tensor, m: torch.Tensor = None, return_weights: bool = False):
         x2, R, L = _flat_rows(x)
@@ -253,7 +253,7 @@ class UserEncoder(nn.Module):
     def forward_items(self, items: torch.Tensor, item_mask: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
         """== forward((items[ids], item_mask[ids])) with the pooler's fc1 evaluated once per item (ItemLogitPoolFn)"""
         p = self.pooler
-        pooled, _ = K.ItemLogitPoolFn.apply(items, item_mask, ids, p.fc1.weight, p.fc1.bias, p.fc2.weight.reshape(-1), p.fc2.bias)
+        pooled, _ = K.ItemLogitPoolFn.apply(items, item_mask, ids, p.fc1.weight, p.fc1.bias, p.fc2.weight, p.fc2.bias)
         if hasattr(self, 'head'):
             pooled = _apply_head(self.head, pooled)
         return pooled.unsqueeze(1)

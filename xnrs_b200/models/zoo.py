@@ -179,7 +179,7 @@ class NAML(nn.Module):
                 e_u, cm_u, inv = e_u[0], K._f32(cm_u.reshape(-1)), K._i32(inv)
                 ue = self.user_encoder
                 u, _ = K.ItemLogitPoolFn.apply(e_u, cm_u, inv[:b * nh].view(b, nh), ue.fc1.weight, ue.fc1.bias,
-                                               ue.fc2.weight.reshape(-1), ue.fc2.bias)
+                                               ue.fc2.weight, ue.fc2.bias)
                 u = u.unsqueeze(1)
                 c = K.EmbeddingFn.apply(e_u, inv[b * nh:], None).view(b, nc, -1)
                 r = self.rec_model(u, c)

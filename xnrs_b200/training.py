@@ -63,6 +63,7 @@ class FlatAdam:
             view.copy_(p.data)
             p.data = view
             p.grad = self.flat_g[off:off + p.numel()].view_as(p)
+            p._xnrs_direct = True          # kernels.py: weight gradients are accumulated straight into this view
             off += n
         self.lr, self.betas, self.eps = lr, betas, eps
         self.step_count = 0

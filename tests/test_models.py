@@ -214,8 +214,33 @@ def test_prefetched_id_plumbing_is_equivalent_and_single_use(device):
         plain = model(batch)
         assert model.prefetch(batch)
         hist = batch['user_features']['history']['title_emb']
-        assert hist._merged is not None and hist._merged[1][0].plan is not None
+        assert hist._merged is not None
         fetched = model(batch)
         assert hist._merged is None                                   # consumed
         again = model(batch)                                          # in-line plumbing again
     assert torch.equal(plain, fetched) and torch.equal(plain, again)
+
+
+@pytest.mark.timeout(120)
+def test_prefetch_over_recycled_batches(monkeypatch):
+    """prefetch / consume over many recycled batch objects: every forward sees a fresh plan for exactly its batch"""
+    import _kernel_emulator as EMU
+    from xnrs_b200 import synthetic as syn
+    from xnrs_b200.data import TitleStore
+    monkeypatch.setattr(K, 'call', EMU.call)
+    fx = load_npz('model_cl')
+    cfg = dict(fixture_cfg(fx), device='cpu')
+    cat = syn.make_catalogue(40, cfg['seq_len'], vocab=100, dim=cfg['d_backbone'], seed=11)
+    store = TitleStore(cat.token_table, cat.title_tokens)
+    model = make_model(cfg)
+    model.load_state_dict({k: torch.tensor(v) for k, v in sub(fx, 'sd').items()})
+    model.eval()
+    batches = [syn.index_batch(store, cat, syn.make_train_batch(40, 12, cfg['hist_len'], n_neg=cfg['n_negatives'],
+                                                                n_users=cfg['n_users'], seed=20 + i), 'cpu') for i in range(3)]
+    with torch.no_grad():
+        want = [model(b) for b in batches]
+        assert model.prefetch(batches[0])
+        for i in range(12):
+            got = model(batches[i % 3])
+            assert model.prefetch(batches[(i + 1) % 3])
+            assert torch.equal(got, want[i % 3])

@@ -292,6 +292,15 @@ class DotScoring(nn.Module):
         return K.DotScoreFn.apply(K._f32(u).reshape(B, T), K._f32(c)).unsqueeze(-1)
 
 
+def _merge_ids(history, candidates):
+    """[all history slots | all candidate slots] as one IndexedTitles of shape (1, b*nh + b*nc) -> (titles, b, nh, nc)"""
+    dev = history.store.device
+    b, nh = history.news_ids.shape
+    nc = candidates.news_ids.shape[1]
+    ids = torch.cat([history.news_ids.to(dev).reshape(1, -1), candidates.news_ids.to(dev).reshape(1, -1)], dim=1)
+    return IndexedTitles(history.store, ids), b, nh, nc
+
+
 def merge_sides(history, candidates):
     """history and candidate titles go through the SAME encoder (parent.py:31-32): with index batches they are encoded in
     one call (one de-duplication, half the launches).  The ids are laid out [all history slots | all candidate slots] so
@@ -303,11 +312,7 @@ def merge_sides(history, candidates):
         if cached is not None and cached[0] is candidates:     # consumed once: a reused batch object is planned afresh
             history._merged = None
             return cached[1]
-        dev = history.store.device
-        b, nh = history.news_ids.shape
-        nc = candidates.news_ids.shape[1]
-        ids = torch.cat([history.news_ids.to(dev).reshape(1, -1), candidates.news_ids.to(dev).reshape(1, -1)], dim=1)
-        return IndexedTitles(history.store, ids), b, nh, nc
+        return _merge_ids(history, candidates)
     return None
 
 
@@ -317,31 +322,31 @@ _prefetch_streams = {}
 def prefetch_titles(encoder, history, candidates, after=None) -> bool:
     """compute the merged-side id plumbing of an upcoming (history, candidates) pair on a side stream (see TitlePlan): call
     it right after enqueuing the current step.  `after`: CUDA event the ids become valid at (e.g. their H2D copy).
-    Returns False when the pair is not index-based."""
-    if not (isinstance(history, IndexedTitles) and isinstance(candidates, IndexedTitles) and isinstance(encoder, TextEncoder)):
+    Returns False when the pair is not index-based.  (A helper-thread variant was measured too: the GIL hand-offs cost as
+    much as the ~0.3 ms of stream-local waiting they removed from the enqueuing thread, so the plan is computed in line.)"""
+    if not (isinstance(history, IndexedTitles) and isinstance(candidates, IndexedTitles) and isinstance(encoder, TextEncoder)
+            and history.store is candidates.store and history.news_ids.shape[0] == candidates.news_ids.shape[0]):
         return False
     history._merged = None
-    merged = None
     dev = history.store.device
+
+    def job():
+        merged = _merge_ids(history, candidates)               # never through the cache of merge_sides
+        titles = merged[0]
+        titles.plan = plan_titles(titles.store, titles.news_ids.reshape(-1), *encoder.plan_kind(titles.news_ids.numel()))
+        return merged
+
     if dev.type != 'cuda':
-        merged = merge_sides(history, candidates)
-        if merged is not None:
-            merged[0].plan = plan_titles(merged[0].store, merged[0].news_ids.reshape(-1), *encoder.plan_kind(merged[0].news_ids.numel()))
-            history._merged = (candidates, merged)
-        return merged is not None
+        history._merged = (candidates, job())
+        return True
     side = _prefetch_streams.get(dev)
     if side is None:
         side = _prefetch_streams[dev] = torch.cuda.Stream(device=dev)
     if after is not None:
         side.wait_event(after)
     with torch.cuda.stream(side):
-        merged = merge_sides(history, candidates)
-        if merged is None:
-            return False
-        titles = merged[0]
-        plan = plan_titles(titles.store, titles.news_ids.reshape(-1), *encoder.plan_kind(titles.news_ids.numel()))
-        plan.event = side.record_event()
-        titles.plan = plan
+        merged = job()
+        merged[0].plan.event = side.record_event()
     history._merged = (candidates, merged)
     return True
 

@@ -86,9 +86,12 @@ TITLES = [('r01b_bench_cl.log', 'headline: CL train, 1 x B200 (`python bench.py`
           ('r01b_bench_npa.log', '`--model npa`'), ('r01b_bench_eval.log', '`--workload eval` (MIND-large-shaped full-catalogue evaluation)'),
           ('r01b_bench_cl_tf32.log', 'CL, `--precision tf32` (single-pass TF32: the 2e-2 tolerance class)'),
           ('r01b_bench_nrms_tf32.log', 'NRMS, `--precision tf32`'),
-          ('r01b_bench_cl_2gpu.log', 'CL train, 2 x B200 (torchrun, NCCL)'), ('r01b_bench_cl_4gpu.log', 'CL train, 4 x B200'),
-          ('r01b_bench_cl_8gpu.log', 'CL train, 8 x B200'), ('r01b_bench_nrms_8gpu.log', 'NRMS train, 8 x B200'),
-          ('r01b_bench_eval_2gpu.log', 'eval, 2 x B200'), ('r01b_bench_eval_4gpu.log', 'eval, 4 x B200'), ('r01b_bench_eval_8gpu.log', 'eval, 8 x B200')]
+          ('r01b_bench_cl_2gpu.log', 'CL train, 2 x B200 (torchrun, NCCL)'), ('r01b_bench_nrms_2gpu.log', 'NRMS train, 2 x B200'),
+          ('r01b_bench_cl_4gpu.log', 'CL train, 4 x B200'),
+          ('r01b_bench_cl_8gpu.log', 'CL train, 8 x B200 (build of mid-session: before the pooling / launch-path / prefetch work, 2.44 ms single-GPU step)'),
+          ('r01b_bench_nrms_8gpu.log', 'NRMS train, 8 x B200 (same mid-session build)'),
+          ('r01b_bench_naml_8gpu.log', 'NAML train, 8 x B200 (same mid-session build)'), ('r01b_bench_lstur_8gpu.log', 'LSTUR train, 8 x B200 (same mid-session build)'),
+          ('r01b_bench_eval_2gpu.log', 'eval, 2 x B200'), ('r01b_bench_eval_4gpu.log', 'eval, 4 x B200'), ('r01b_bench_eval_8gpu.log', 'eval, 8 x B200 (mid-session build)')]
 for f, title in TITLES:
     d = bench_line(f)
     if not d:
@@ -157,12 +160,14 @@ if os.path.exists(os.path.join(P, 'r01b_ncu_kernels.jsonl')):
         r = json.loads(l)
         md.append(f"| `{r['kernel']}` | {r.get('grid')} | {r.get('time')} | {r.get('dram_read')} | {r.get('dram_write')} | {r.get('dram_%')} | "
                   f"{r.get('issue_active_%')} | {r.get('warps_active_%')} | {r.get('regs')} |")
-    md += ['', 'Reading: `gather_rows` runs at 71 % DRAM utilisation (5.4 TB/s of algorithmic traffic = 83 % of the measured copy peak); the '
-           'ragged pooling kernels at 37-40 % (their DRAM traffic equals the algorithmic bytes: 632 MB / 660 MB read for 653 / 810 MB '
-           'algorithmic — they are latency-, not bandwidth-limited: one warp walks one title); `eval_impressions_warp_kernel` moves only '
-           '0.94 GB of DRAM for 2.7 GB of gathered candidate vectors (Zipf-popular articles are L2 hits) at 62 % issue utilisation; the '
-           'attention core is bound by shared-memory broadcast loads and FMA latency at 4-14 resident warps per SM (fwd 36 %, bwd 26 % issue '
-           'utilisation), not by DRAM (18-28 %).', '']
+    md += ['', 'Reading (this capture predates the last pooling / column-sum tuning — the CUDA-event table above is the final build): '
+           '`gather_rows` runs at 71 % DRAM utilisation (5.4-5.6 TB/s of algorithmic traffic = 83-86 % of the measured copy peak); the '
+           'ragged pooling kernels read exactly their algorithmic bytes (632 MB / 660 MB of DRAM reads for 653 / 810 MB algorithmic) and were '
+           'latency-, not bandwidth-limited (issue utilisation 13 % / 30 %: one warp walks one title) — batching four hidden rows per '
+           'iteration with hoisted loads took them from 48 % to 54 % / 58 % of the HBM peak; `colsum` went from 54 % to 91 % with 16-byte '
+           'loads and four rows in flight per thread; `eval_impressions_warp_kernel` moves only 0.94 GB of DRAM for 2.7 GB of gathered '
+           'candidate vectors (Zipf-popular articles are L2 hits) at 62 % issue utilisation; the attention core is bound by shared-memory '
+           'broadcast loads and FMA latency at 7-14 resident warps per SM (fwd 36 %, bwd 26 % issue utilisation), not by DRAM (18-28 %).', '']
 
 gp = os.path.join(G, 'r01b_bench_gemm.jsonl')
 if os.path.exists(gp):

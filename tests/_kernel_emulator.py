@@ -17,11 +17,16 @@ def _rows(x, rows):
     return x if rows is None else x[rows.long()]
 
 
-def _kf(keep, p, shape):
+def _kf(keep, p, shape, seed=None):
     if keep is not None:
         return keep.reshape(shape)
     if p > 0:
-        raise NotImplementedError('emulator only supports explicit keep masks')
+        if seed is None:
+            raise NotImplementedError('emulator needs an explicit keep mask or a seed')
+        # seeded draw, reproduced by the backward from the same seed (the kernels use a counter hash: same contract,
+        # different stream — bit parity with a particular generator is not part of the ABI)
+        g = torch.Generator().manual_seed(int(seed) % (2 ** 63))
+        return (torch.rand(shape, generator=g) >= p).float()
     return torch.ones(shape)
 
 
@@ -91,7 +96,7 @@ def _xnrs_transpose(inp, rows, cols, out):
 
 
 def _xnrs_dropout(n, x, keep, p, seed, y):
-    y.copy_(x * _kf(keep, p, x.shape) / (1 - p))
+    y.copy_(x * _kf(keep, p, x.shape, seed) / (1 - p))
 
 
 def _groups(R, L, seg):
@@ -169,24 +174,24 @@ def _xnrs_collapse_mask(mask, R, L, out):
     out.copy_(mask.reshape(R, L).sum(1).clamp(0, 1))
 
 
-def _att(q, k, v, mask, R, L, h, dk, keep, p):
+def _att(q, k, v, mask, R, L, h, dk, keep, p, seed=None):
     qh, kh, vh = (t.reshape(R, L, h, dk).transpose(1, 2) for t in (q, k, v))
     s = qh @ kh.transpose(-1, -2) / math.sqrt(dk)
     if mask is not None:
         s = s.masked_fill(mask.reshape(R, 1, L, 1) == 0, -1e9)
     pr = torch.softmax(s, -1)
-    return pr * _kf(keep, p, pr.shape) / (1 - p), vh
+    return pr * _kf(keep, p, pr.shape, seed) / (1 - p), vh
 
 
 def _xnrs_mha_fwd(q, k, v, ld, mask, R, L, h, dk, keep, p, seed, o, lse):
-    pr, vh = _att(q, k, v, mask, R, L, h, dk, keep, p)
+    pr, vh = _att(q, k, v, mask, R, L, h, dk, keep, p, seed)
     o.copy_((pr @ vh).transpose(1, 2).reshape(R * L, h * dk))
 
 
 def _xnrs_mha_bwd(q, k, v, o, d_o, ld, mask, lse, R, L, h, dk, keep, p, seed, dq, dk_, dv):
     qq, kk, vv = (t.detach().clone().requires_grad_(True) for t in (q, k, v))
     with torch.enable_grad():
-        pr, vh = _att(qq, kk, vv, mask, R, L, h, dk, keep, p)
+        pr, vh = _att(qq, kk, vv, mask, R, L, h, dk, keep, p, seed)
         out = (pr @ vh).transpose(1, 2).reshape(R * L, h * dk)
         g = torch.autograd.grad(out, (qq, kk, vv), d_o)
     dq.copy_(g[0])

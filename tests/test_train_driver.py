@@ -27,7 +27,7 @@ user_features: []
 add_features: []
 title_emb_dim: 16
 total_emb_dim: 16
-d_backbone: 12
+d_backbone: 16
 n_heads: 4
 hist_len: 4
 seq_len: 5
@@ -54,7 +54,7 @@ dir: {out}
 """
 
 
-def _write_dataset(tmp_path, n_news=30, n_train=24, n_test=9, S=5, D=12):
+def _write_dataset(tmp_path, n_news=30, n_train=24, n_test=9, S=5, D=16):    # 16 / 4 heads: a head width the kernels support
     import pandas as pd
     rng = np.random.default_rng(0)
     ids = [f'N{i}' for i in range(n_news)]
@@ -79,14 +79,22 @@ def _write_dataset(tmp_path, n_news=30, n_train=24, n_test=9, S=5, D=12):
     behaviours(n_test, tmp_path / 'test.csv')
 
 
+@pytest.fixture(params=['emulated', pytest.param('cuda', marks=pytest.mark.gpu)])
+def device(request, monkeypatch):
+    if request.param == 'emulated':
+        monkeypatch.setattr(K, 'call', EMU.call)
+        return 'cpu'
+    return 'cuda:0'
+
+
 @pytest.mark.parametrize('model', ['standard', 'NRMS'])
-def test_train_driver_runs_epochs_evaluates_and_checkpoints(model, tmp_path, monkeypatch):
+def test_train_driver_runs_epochs_evaluates_and_checkpoints(model, device, tmp_path):
     from xnrs_b200 import train as T
-    monkeypatch.setattr(K, 'call', EMU.call)
     _write_dataset(tmp_path)
     cfg_path = tmp_path / 'cfg.yml'
     cfg_path.write_text(CONFIG.format(news=tmp_path / 'news.pkl', train_csv=tmp_path / 'train.csv',
-                                      test_csv=tmp_path / 'test.csv', out=tmp_path / 'runs', model=model))
+                                      test_csv=tmp_path / 'test.csv', out=tmp_path / 'runs', model=model)
+                        .replace("device: 'cpu'", f"device: '{device}'"))
     hist = T.train(str(cfg_path))
     assert len(hist['train_loss']) == 2 and all(np.isfinite(hist['train_loss']))
     assert len(hist['test']) == 2 and hist['test'][-1]['impressions'] == 9
@@ -95,7 +103,7 @@ def test_train_driver_runs_epochs_evaluates_and_checkpoints(model, tmp_path, mon
     ck = torch.load(hist['checkpoints'][-1], weights_only=False)
     assert set(ck) == {'config', 'model_name', 'state_dict'} and ck['model_name'] == 'tiny_run'
     assert ck['config']['random_seed'] == 3                        # duplicated YAML key: the last value wins, like the reference
-    loaded, _ = T.load_model_from_ckpt(hist['checkpoints'][-1], device='cpu')
+    loaded, _ = T.load_model_from_ckpt(hist['checkpoints'][-1], device=device)
     for (k, a), (_, b) in zip(hist['model'].state_dict().items(), loaded.state_dict().items()):
         assert torch.equal(a.cpu(), b.cpu()), k
     # debug mode: one step, one impression, one epoch (training.py:125-127,138-140,156-158)

@@ -171,6 +171,10 @@ int xnrs_eval_impressions(const float *user, const float *news_vecs, int T, cons
                           float *scores_io, double *metrics_out, xnrs_stream_t st);
 /* sums[0..5] += column sums over impressions with a finite auc, sums[6] += their count */
 int xnrs_metric_sums(const double *metrics, long long n_imp, double *sums, xnrs_stream_t st);
+/* thresholded metrics of _test_step (training.py:219-222; metrics.py:47-64) per CSR impression: out (n_imp,7) float64 =
+ * accuracy, recall, precision, tn, fp, fn, tp with prediction = round(clip(nan_to_num(score), 0, 1)) = (score > 0.5) */
+int xnrs_binary_metrics(const float *scores, const float *targets, const long long *offsets, long long n_imp, double *out,
+                        xnrs_stream_t st);
 
 /* ---- row Opt: Adam, torch defaults (training.py:39), one launch over a flat parameter buffer ---- */
 /* bias corrections come from the host `step` (>= 1) or, when bc_dev is non-null, from the device pair

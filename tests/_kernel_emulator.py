@@ -375,3 +375,14 @@ def _xnrs_logit_bwd(hid, w2, d_logit, n, A, d_hid, d_w2, d_b2):
     d_hid.copy_((d_logit[:, None] * w2[None, :] * (1 - h * h)).reshape(d_hid.shape))
     d_w2.add_(h.T @ d_logit)
     d_b2.add_(d_logit.sum())
+
+
+def _xnrs_binary_metrics(scores, targets, offsets, n_imp, out):
+    sc = torch.nan_to_num(scores, nan=0.0, posinf=1.0, neginf=0.0)
+    for i in range(n_imp):
+        a, b = int(offsets[i]), int(offsets[i + 1])
+        pred, pos = sc[a:b] > 0.5, targets[a:b] > 0.5
+        tp, fp = int((pred & pos).sum()), int((pred & ~pos).sum())
+        fn, tn = int((~pred & pos).sum()), int((~pred & ~pos).sum())
+        out[i] = torch.tensor([(tp + tn) / max(b - a, 1), tp / (tp + fn) if tp + fn else 0.0, tp / (tp + fp) if tp + fp else 0.0,
+                               tn, fp, fn, tp], dtype=torch.float64)

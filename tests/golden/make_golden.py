@@ -285,6 +285,32 @@ def explain_fixture():
     np.savez_compressed(os.path.join(HERE, 'explain.npz'), **out)
 
 
+def binary_metric_fixture():
+    """the thresholded epoch metrics of `_test_step` (training.py:219-222; metrics.py:47-64: acc / rec / prec / confusion on
+    round(clip(score, 0, 1))) through the reference functions, on random impressions incl. scores of exactly 0.5, scores
+    outside [0, 1] and impressions whose predictions are all one class"""
+    rng = np.random.default_rng(9)
+    ys, yt, vals, confs = [], [], [], []
+    import warnings
+    for i in range(48):
+        n_pos, n_neg = int(rng.integers(1, 4)), int(rng.integers(1, 40))
+        t = np.array([1.] * n_pos + [0.] * n_neg, dtype=np.float32)
+        s = rng.normal(0.4, 0.5, size=n_pos + n_neg).astype(np.float32)
+        if i % 5 == 0:
+            s[rng.integers(0, len(s))] = 0.5                    # np.round(0.5) == 0
+        if i % 7 == 0:
+            s = np.minimum(s, 0.3).astype(np.float32)           # nothing predicted positive
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            vals.append([M.acc_score(t, s), M.recall_score(t, s), M.precision_score(t, s)])
+            confs.append(M.confusion_matrix(t, s).reshape(-1))  # [[tn, fp], [fn, tp]] — both classes are always in t here
+        ys.append(s)
+        yt.append(t)
+    out = {'offsets': np.cumsum([0] + [len(s) for s in ys]).astype(np.int64), 'scores': np.concatenate(ys),
+           'targets': np.concatenate(yt), 'values': np.array(vals, dtype=np.float64), 'conf': np.array(confs, dtype=np.int64)}
+    np.savez_compressed(os.path.join(HERE, 'binary_metrics.npz'), **out)
+
+
 def dataset_fixture():
     """row G: the reference's NewsRecDataset + custom_collate_fn (xnrs/data/dataset.py:48-163, utils.py:190-204) on a tiny
     synthetic news table / behaviour log, in eval mode (all candidates) and train mode (seeded negative sampling).  The
@@ -340,6 +366,9 @@ if __name__ == '__main__':
     if '--dataset-only' in sys.argv:
         dataset_fixture()
         sys.exit(0)
+    if '--binary-only' in sys.argv:
+        binary_metric_fixture()
+        sys.exit(0)
     if '--explain-only' in sys.argv:
         explain_fixture()
         sys.exit(0)
@@ -349,4 +378,5 @@ if __name__ == '__main__':
     loss_metric_fixtures()
     dataset_fixture()
     explain_fixture()
+    binary_metric_fixture()
     print('golden fixtures written to', HERE)

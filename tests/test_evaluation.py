@@ -126,3 +126,30 @@ def test_impression_shards_balance_candidates():
         assert all(cuts[i][1] == cuts[i + 1][0] for i in range(w - 1))
         loads = [int(off[b] - off[a]) for a, b in cuts]
         assert max(loads) - min(loads) <= 2 * 74
+
+
+def test_binary_metrics_match_reference(device):
+    """acc / rec / prec / confusion of _test_step (training.py:219-222) vs the reference functions (sklearn on
+    round(clip(score, 0, 1))): golden generated by make_golden.py:binary_metric_fixture"""
+    z = load_npz('binary_metrics')
+    got = K.binary_metrics(torch.tensor(z['scores'], device=device), torch.tensor(z['targets'], device=device),
+                           torch.tensor(z['offsets'], device=device)).cpu().numpy()
+    np.testing.assert_allclose(got[:, :3], z['values'], rtol=0, atol=1e-12)
+    np.testing.assert_array_equal(got[:, 3:].astype(np.int64), z['conf'])
+
+
+def test_evaluator_reports_binary_metrics(device):
+    fx = load_npz('model_cl')
+    cfg = dict(fixture_cfg(fx), device=device)
+    model = make_model(cfg)
+    model.load_state_dict({k: torch.tensor(v) for k, v in sub(fx, 'sd').items()})
+    model.to(device).eval()
+    cat = syn.make_catalogue(50, cfg['seq_len'], vocab=200, dim=cfg['d_backbone'], seed=8)
+    imp = syn.make_eval_impressions(50, 30, cfg['hist_len'], n_users=cfg['n_users'], seed=9)
+    ev = CatalogueEvaluator(model, TitleStore(cat.token_table.to(device), cat.title_tokens.to(device)), impression_chunk=7)
+    ev.binary_metrics = True
+    out = ev.evaluate(imp, return_per_impression=True)
+    want = K.binary_metrics(out['scores'], imp['targets'].to(device), imp['offsets'].to(device)).cpu().numpy()
+    assert abs(out['acc'] - want[:, 0].mean()) < 1e-12 and abs(out['rec'] - want[:, 1].mean()) < 1e-12
+    assert out['conf'] == [[int(want[:, 3].sum()), int(want[:, 4].sum())], [int(want[:, 5].sum()), int(want[:, 6].sum())]]
+    assert out['candidates'] == imp['targets'].numel()

@@ -237,6 +237,38 @@ eval_impressions_warp_kernel(const float *__restrict__ user, const float *__rest
     }
 }
 
+// Thresholded per-impression metrics of _test_step (training.py:219-222; metrics.py:47-64): predictions are
+// round(clip(score, 0, 1)) with numpy's round-half-to-even, i.e. 1 exactly when the (nan_to_num'd) score is > 0.5.
+//   out[imp] = (accuracy, recall, precision, tn, fp, fn, tp);  recall / precision are 0 when their denominator is 0
+//   (sklearn's zero_division behaviour in the reference calls).  One warp per impression.
+__global__ void __launch_bounds__(256)
+binary_metrics_kernel(const float *__restrict__ scores, const float *__restrict__ targets, const long long *__restrict__ offsets,
+                      long long n_imp, double *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long imp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (imp >= n_imp) return;
+    const long long beg = offsets[imp];
+    const int n = (int)(offsets[imp + 1] - beg);
+    int tn = 0, fp = 0, fn = 0, tp = 0;
+    for (int c = lane; c < n; c += 32) {
+        const bool pred = nan_to_num_f(scores[beg + c]) > 0.5f;
+        const bool pos = targets[beg + c] > 0.5f;
+        tp += pred && pos; fp += pred && !pos; fn += !pred && pos; tn += !pred && !pos;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        tn += __shfl_xor_sync(0xffffffffu, tn, o); fp += __shfl_xor_sync(0xffffffffu, fp, o);
+        fn += __shfl_xor_sync(0xffffffffu, fn, o); tp += __shfl_xor_sync(0xffffffffu, tp, o);
+    }
+    if (lane == 0) {
+        double *m = out + imp * 7;
+        m[0] = n > 0 ? (double)(tp + tn) / (double)n : nan("");
+        m[1] = (tp + fn) > 0 ? (double)tp / (double)(tp + fn) : 0.0;
+        m[2] = (tp + fp) > 0 ? (double)tp / (double)(tp + fp) : 0.0;
+        m[3] = tn; m[4] = fp; m[5] = fn; m[6] = tp;
+    }
+}
+
 __global__ void metric_sums_kernel(const double *__restrict__ metrics, long long n_imp, double *__restrict__ sums) {
     __shared__ double red[32];
     double acc[7] = {0, 0, 0, 0, 0, 0, 0};
@@ -300,6 +332,16 @@ extern "C" int xnrs_metric_sums(const double *metrics, long long n_imp, double *
     XNRS_REQUIRE(metrics && sums, "null pointer");
     long long blocks = cdiv(n_imp, 256), cap = 2LL * num_sms();
     metric_sums_kernel<<<(unsigned)(blocks > cap ? cap : blocks), 256, 0, STREAM(st)>>>(metrics, n_imp, sums);
+    XNRS_LAUNCHED();
+    return XNRS_OK;
+}
+
+extern "C" int xnrs_binary_metrics(const float *scores, const float *targets, const long long *offsets, long long n_imp,
+                                   double *out, xnrs_stream_t st) {
+    XNRS_REQUIRE(n_imp >= 0, "bad sizes");
+    if (n_imp == 0) return XNRS_OK;
+    XNRS_REQUIRE(scores && targets && offsets && out, "null pointer");
+    binary_metrics_kernel<<<(unsigned)cdiv(n_imp, 8), 256, 0, STREAM(st)>>>(scores, targets, offsets, n_imp, out);
     XNRS_LAUNCHED();
     return XNRS_OK;
 }

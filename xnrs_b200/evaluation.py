@@ -60,6 +60,8 @@ class CatalogueEvaluator:
         # computed once per catalogue article (one GEMM over n_news rows) instead of once per (user, slot): same values as
         # layers.py:60-65 slot by slot, ~H * n_impressions / n_news fewer pooler FLOPs.  Off: re-run the pooler per slot.
         self.item_logits = True
+        # also report the thresholded epoch metrics of _test_step (acc / rec / prec / confusion, training.py:219-222)
+        self.binary_metrics = False
 
     # ---- phase 1 ---------------------------------------------------------------------------------------------
     def _encode_ids(self, ids: torch.Tensor):
@@ -168,6 +170,7 @@ class CatalogueEvaluator:
         uidx = impressions.get('user_index')
         uidx = None if uidx is None else uidx.to(dev)
         sums = torch.zeros(7, device=dev, dtype=torch.float64)
+        bsums = torch.zeros(7, device=dev, dtype=torch.float64)
         per_imp, all_scores = [], []
         off_host = impressions['offsets'] if not impressions['offsets'].is_cuda else offsets.cpu()   # chunk bounds: no per-chunk sync
         for a in range(lo, hi, self.impression_chunk):
@@ -178,13 +181,22 @@ class CatalogueEvaluator:
             scores, metrics = K.eval_impressions(u, self.news_vecs, cand_ids[c0:c1].contiguous(), local_off,
                                                  targets[c0:c1].contiguous(), act=self.score_act)
             K.call('xnrs_metric_sums', metrics, b - a, sums)
+            if self.binary_metrics:
+                bsums += K.binary_metrics(scores, targets[c0:c1].contiguous(), local_off).sum(0)      # epoch bookkeeping (7 numbers)
             if return_per_impression:
                 per_imp.append(metrics)
                 all_scores.append(scores)
         if w > 1:
             dist.all_reduce(sums)
+            if self.binary_metrics:
+                dist.all_reduce(bsums)
         out = {name: float(sums[i] / sums[6]) if float(sums[6]) > 0 else float('nan') for i, name in enumerate(METRIC_NAMES)}
         out['impressions'] = int(sums[6])
+        if self.binary_metrics:
+            b_ = bsums.tolist()                                    # (after the all-reduce: sums over ALL impressions)
+            n_all = max(n_imp, 1)
+            out.update({'acc': b_[0] / n_all, 'rec': b_[1] / n_all, 'prec': b_[2] / n_all,
+                        'conf': [[int(b_[3]), int(b_[4])], [int(b_[5]), int(b_[6])]], 'candidates': int(sum(b_[3:]))})
         if return_per_impression:
             out['per_impression'] = torch.cat(per_imp) if per_imp else None
             out['scores'] = torch.cat(all_scores) if all_scores else None

@@ -215,6 +215,14 @@ def eval_impressions(user, news_vecs, cand_ids, offsets, targets, act=1, scores=
     return scores, metrics
 
 
+def binary_metrics(scores: torch.Tensor, targets: torch.Tensor, offsets: torch.Tensor) -> torch.Tensor:
+    """-> (n_imp,7) float64: accuracy, recall, precision, tn, fp, fn, tp of round(clip(score,0,1)) per impression"""
+    n_imp = offsets.numel() - 1
+    out = torch.empty((n_imp, 7), device=scores.device, dtype=torch.float64)
+    call('xnrs_binary_metrics', scores, targets, offsets, n_imp, out)
+    return out
+
+
 def metric_sums(metrics: torch.Tensor) -> torch.Tensor:
     sums = torch.zeros(7, device=metrics.device, dtype=torch.float64)
     call('xnrs_metric_sums', metrics, metrics.shape[0], sums)

@@ -49,7 +49,7 @@ def _xnrs_gather_rows(table, V, D, rows, R, out, ld):
 
 
 def _xnrs_scatter_add_rows(dtable, V, D, rows, R, dout, ld, skip):
-    keep = rows != skip
+    keep = (rows != skip) & (rows >= 0) & (rows < V)          # out-of-range ids (e.g. -1 padding) are skipped like the kernel does
     dtable.index_add_(0, rows[keep].long(), dout[keep])
 
 

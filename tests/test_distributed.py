@@ -61,13 +61,15 @@ def _worker(rank, world, port, name, out_dir):
     batch['main_theme'] = torch.tensor([ids[t] for t in batch['main_theme']], dtype=torch.int32)
     lo, hi = shard_range(batch['targets'].shape[0], rank, world)
     dp = DataParallelTrainer(tr)
+    dp.SPARSE_MIN_ROWS = 1                 # the fixture's 12-row user table takes the (ids, rows) exchange path
     out = dp.train_step(_slice_batch(batch, lo, hi))
+    assert (dp.last_sparse_tables >= 1) == name.startswith('lstur')     # user table (and the category table) went sparse
     np.savez(os.path.join(out_dir, f'r{rank}.npz'), g=tr.optimizer.flat_g.numpy(), p=tr.optimizer.flat_p.numpy(),
              cl=out['loss_cl'].numpy())
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('name', ['cl', 'nrms'])
+@pytest.mark.parametrize('name', ['cl', 'nrms', 'lstur_con'])
 def test_two_rank_step_equals_full_batch_step(name, tmp_path):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), name, str(tmp_path)), nprocs=world, join=True)

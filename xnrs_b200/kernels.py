@@ -509,20 +509,34 @@ class MultiHeadAttentionFn(torch.autograd.Function):
                 None, None, None, None, None, None)
 
 
+# Data-parallel runs exchange the gradient of row-sparse tables (the 700k-row user tables of LSTUR / NPA) as (ids, rows)
+# instead of all-reducing the dense table: while this list is not None, EmbeddingFn.backward logs every
+# lookup of a directly-accumulated parameter here; distributed.DataParallelTrainer consumes it after the backward pass.
+sparse_grad_log = None
+
+
 class EmbeddingFn(torch.autograd.Function):
     """nn.Embedding lookup with a dense weight gradient (lstur.py:94-98,180-183; npa.py:12-15; naml.py:34-47)."""
 
     @staticmethod
     def forward(ctx, weight, idx, padding_idx):
         idx = _i32(idx).reshape(-1)
-        ctx.save_for_backward(idx)
+        ctx.save_for_backward(idx, weight)
         ctx.shape, ctx.pad = weight.shape, -1 if padding_idx is None else int(padding_idx)
         return gather_rows(weight, idx)
 
     @staticmethod
     def backward(ctx, dy):
-        (idx,) = ctx.saved_tensors
+        idx, weight = ctx.saved_tensors
         dy = _f32(dy)
+        g = _direct(weight)
+        if g is not None and g.shape == ctx.shape:
+            # FlatAdam-managed table: scatter straight into its gradient view (no V x D temporary, zero fill and add — 3 x 383 MB
+            # of traffic per step for the LSTUR user table)
+            call('xnrs_scatter_add_rows', g, ctx.shape[0], ctx.shape[1], idx, idx.numel(), dy, dy.stride(0), ctx.pad)
+            if sparse_grad_log is not None:
+                sparse_grad_log.append((weight, idx, dy, ctx.pad))
+            return None, None, None
         dw = torch.zeros(ctx.shape, device=dy.device, dtype=torch.float32)
         call('xnrs_scatter_add_rows', dw, ctx.shape[0], ctx.shape[1], idx, idx.numel(), dy, dy.stride(0), ctx.pad)
         return dw, None, None

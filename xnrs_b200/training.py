@@ -58,7 +58,9 @@ class FlatAdam:
         self.m = torch.zeros(total, device=dev, dtype=torch.float32)
         self.v = torch.zeros(total, device=dev, dtype=torch.float32)
         off = 0
+        self.ranges = {}                     # id(param) -> (begin, end) of its slice of the flat buffers
         for p, n in zip(self.params, sizes):
+            self.ranges[id(p)] = (off, off + p.numel())
             view = self.flat_p[off:off + p.numel()].view_as(p)
             view.copy_(p.data)
             p.data = view

@@ -87,6 +87,7 @@ TITLES = [('r01b_bench_cl.log', 'headline: CL train, 1 x B200 (`python bench.py`
           ('r01b_bench_cl_tf32.log', 'CL, `--precision tf32` (single-pass TF32: the 2e-2 tolerance class)'),
           ('r01b_bench_nrms_tf32.log', 'NRMS, `--precision tf32`'),
           ('r01b_bench_cl_2gpu.log', 'CL train, 2 x B200 (torchrun, NCCL)'), ('r01b_bench_nrms_2gpu.log', 'NRMS train, 2 x B200'),
+          ('r01b_bench_lstur_2gpu.log', 'LSTUR train, 2 x B200 (user-table gradient exchanged as (ids, rows))'),
           ('r01b_bench_cl_4gpu.log', 'CL train, 4 x B200'),
           ('r01b_bench_cl_8gpu.log', 'CL train, 8 x B200 (build of mid-session: before the pooling / launch-path / prefetch work, 2.44 ms single-GPU step)'),
           ('r01b_bench_nrms_8gpu.log', 'NRMS train, 8 x B200 (same mid-session build)'),

@@ -498,11 +498,6 @@ __device__ __forceinline__ bool mbar_try_cluster(uint64_t *bar, uint32_t parity)
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
-#ifdef XNRS_EXP_CTA_WAIT
-    mbar_wait(bar, parity);
-    asm volatile("fence.acq_rel.cluster;" ::: "memory");
-    return;
-#endif
     if (mbar_try_cluster(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_cluster(bar, parity)) {

@@ -427,12 +427,15 @@ def main():
     classes = {}
     for name, a, s_, e_ in records:
         if name == 'xnrs_gemm':
-            c = classes.setdefault((a[0], a[1], a[3], a[4], a[8]) if not a[0] else (a[0], a[1], a[2], a[3], a[8]), [0.0, 0, 0.0, 0])
+            big = a[4] if a[0] else a[2]          # the batch-dependent dimension; its power-of-two bucket keeps e.g. the
+            bucket = max(int(big), 1).bit_length()   # token-level fc1 GEMMs apart from the title-level head GEMMs of equal N, K
+            key = ((a[0], a[1], a[3], a[4], a[8]) if not a[0] else (a[0], a[1], a[2], a[3], a[8])) + (bucket,)
+            c = classes.setdefault(key, [0.0, 0, 0.0, 0])
             c[0] += s_.elapsed_time(e_)
             c[1] += 1
             c[2] += 2.0 * a[2] * a[3] * a[4]
             c[3] += a[4] if a[0] else a[2]
-    (d_ta, d_tb, d_1, d_2, d_act), (d_ms, d_n, d_flop, d_rows) = max(classes.items(), key=lambda kv: kv[1][0])
+    (d_ta, d_tb, d_1, d_2, d_act, _), (d_ms, d_n, d_flop, d_rows) = max(classes.items(), key=lambda kv: kv[1][0])
     d_m, d_n_ = (d_1, d_2) if d_ta else (d_rows // max(d_n, 1), d_1)
     kern = ('gemm_tc2_kernel (cta_group::2 CTA pair, 256x256 tile)' if (args.precision == 'tf32x3' and d_n_ > 128 and d_m >= 256)
             else ('gemm_tc_kernel<256>' if args.precision in ('tf32', 'bf16') and d_n_ > 128 else 'gemm_tc_kernel<128>'))
@@ -446,7 +449,10 @@ def main():
         'frac': d_tflops / pk['bf16_tflops_sustained'] if d_tflops else None,
         # dram__bytes_read.sum + dram__bytes_write.sum of ONE such launch (ncu --set full, profiles/README.md): 473.2 MB read
         # + 131.4 MB written at M=153 562 rows = 3937 B/row, i.e. the algorithmic A row (3072 B) + C row (1024 B): no re-reads
-        'traffic': 3937.0 * (d_rows / max(d_n, 1)) if (not d_ta and args.precision != 'fp32' and d_2 == 768 and d_1 == 256) else None,
+        # the fc1 weight gradient (TN, M=256, N=768): 651.4 MB read + 8.4 MB written at K=153 562 = 4296 B per k-row = one
+        # d_hid row (1024 B) + one x row (3072 B) + the split-K partial tiles
+        'traffic': (3937.0 * (d_rows / max(d_n, 1)) if (not d_ta and args.precision != 'fp32' and d_2 == 768 and d_1 == 256)
+                    else (4296.0 * (d_rows / max(d_n, 1)) if (d_ta and args.precision != 'fp32' and d_1 == 256 and d_2 == 768) else None)),
         'peak_source': f'{pk_kind} (sustained bf16 GEMM; kernel timed inside a long step). The kernel computes in TF32 '
                        f'(3 MMAs per product in the fp32-accurate 3xTF32 mode): its own ceiling is 1/6 of this bf16 peak',
         'launches_timed': d_n, 'avg_launch_ms': d_ms / max(d_n, 1),

@@ -351,7 +351,7 @@ def contrastive_loss(emb: Tensor, labels: Tensor, temperature: float) -> Tensor:
     e = e / e.norm(dim=-1, keepdim=True).clamp_min(1e-12)               # F.normalize, eps 1e-12
     ex = torch.exp((e @ e.T) / temperature)
     B = e.shape[0]
-    off = ~torch.eye(B, dtype=torch.bool)
+    off = ~torch.eye(B, dtype=torch.bool, device=e.device)
     pos = (labels[:, None] == labels[None, :]) & off
     num = (ex * pos).sum(dim=1)
     den = (ex * off).sum(dim=1)

@@ -196,12 +196,13 @@ def test_index_batches_equal_dense_batches(name, device):
         assert_close(grads[0][k], grads[1][k], 1e-4, 'grad ' + k, atol=2e-6 * gmax)
 
 
-def test_prefetched_id_plumbing_is_equivalent_and_single_use(device):
+@pytest.mark.parametrize('name', ['cl', 'nrms'])       # ragged (padding-free) plan / fixed-length plan (self-attention)
+def test_prefetched_id_plumbing_is_equivalent_and_single_use(name, device):
     """ParentRec.prefetch computes the merged-side TitlePlan ahead of the step (side stream on CUDA): same scores as the
     in-line plumbing, and the plan is consumed by exactly one forward (a recycled batch object is planned afresh)"""
     from xnrs_b200 import synthetic as syn
     from xnrs_b200.data import TitleStore
-    fx = load_npz('model_cl')
+    fx = load_npz('model_' + name)
     cfg = dict(fixture_cfg(fx), device=device)
     cat = syn.make_catalogue(40, cfg['seq_len'], vocab=100, dim=cfg['d_backbone'], seed=11)
     raw = syn.make_train_batch(40, 12, cfg['hist_len'], n_neg=cfg['n_negatives'], n_users=cfg['n_users'], seed=12)

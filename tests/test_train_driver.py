@@ -99,6 +99,12 @@ def test_train_driver_runs_epochs_evaluates_and_checkpoints(model, device, tmp_p
     assert len(hist['train_loss']) == 2 and all(np.isfinite(hist['train_loss']))
     assert len(hist['test']) == 2 and hist['test'][-1]['impressions'] == 9
     assert all(0.0 <= hist['test'][-1][k] <= 1.0 for k in ('auc', 'rr', 'ndcg@5', 'ndcg@10'))
+    last = hist['test'][-1]
+    assert 0.0 <= last['acc'] <= 1.0 and sum(map(sum, last['conf'])) > 0
+    pred = torch.load(last['predictions'], weights_only=False)       # training.py:85-95 dump format
+    assert os.path.basename(last['predictions']) == 'predictions_1' and set(pred) == {'targets', 'scores', 'stats'}
+    assert pred['scores'].shape == pred['targets'].shape and set(pred['stats']) == {'auc', 'mrr', 'ndcg@5', 'ndcg@10'}
+    assert pred['stats']['auc'].shape == (9,)
     assert [os.path.basename(p) for p in hist['checkpoints']] == ['ckpt_0', 'ckpt_1']
     ck = torch.load(hist['checkpoints'][-1], weights_only=False)
     assert set(ck) == {'config', 'model_name', 'state_dict'} and ck['model_name'] == 'tiny_run'

@@ -92,17 +92,35 @@ def _stores(tables: mind_io.NewsTables, text_features, device) -> Dict[str, Titl
     return {f: TitleStore(table, tables.tokens[f].to(device)) for f in text_features}
 
 
-def evaluate(model, cfg: Cfg, tables: mind_io.NewsTables, sessions: Sequence[dict], device, debug: bool = False) -> dict:
-    """`_test_iteration` (training.py:131-142, 194-266) as one full-catalogue pass"""
+def save_scores(cfg: Cfg, epoch: int, targets, scores, stats: dict) -> str:
+    """training.py:85-95: `<dir>/<name>/predictions/predictions_<epoch>` = {targets, scores, stats} (numpy arrays)"""
+    path = os.path.join(cfg.dir, cfg.name, 'predictions')
+    os.makedirs(path, exist_ok=True)
+    fname = os.path.join(path, f'predictions_{epoch}')
+    torch.save({'targets': targets, 'scores': scores, 'stats': stats}, fname)
+    return fname
+
+
+def evaluate(model, cfg: Cfg, tables: mind_io.NewsTables, sessions: Sequence[dict], device, debug: bool = False,
+             epoch: Optional[int] = None) -> dict:
+    """`_test_iteration` + `_after_test_iteration` (training.py:131-142, 194-303) as one full-catalogue pass: the epoch
+    means of every `_test_step` metric (ranking + thresholded), the summed confusion matrix, and — when `epoch` is given —
+    the reference's per-epoch prediction dump (all scores / targets, per-impression auc / mrr / ndcg)."""
     stores = _stores(tables, list(cfg.get('text_features', ['title_emb'])), device)
     text = list(cfg.get('text_features', ['title_emb']))
     cat = tables.categorical.get('category_index')
     sub = tables.categorical.get('subcategory_index')
     ev = CatalogueEvaluator(model, stores[text[0]], cat, sub, stores.get('abstract_emb'))
+    ev.binary_metrics = True
     imp = mind_io.eval_impressions(sessions[:1] if debug else sessions, tables, int(cfg.hist_len))
     model.eval()
-    out = ev.evaluate(imp)
-    return {k: out[k] for k in ('auc', 'rr', 'ndcg@5', 'ndcg@10', 'ctr@1', 'ctr@10', 'impressions')}
+    out = ev.evaluate(imp, return_per_impression=epoch is not None)
+    res = {k: out[k] for k in ('auc', 'rr', 'ndcg@5', 'ndcg@10', 'ctr@1', 'ctr@10', 'acc', 'rec', 'prec', 'conf', 'impressions')}
+    if epoch is not None and out.get('per_impression') is not None:
+        per = out['per_impression'].cpu().numpy()
+        res['predictions'] = save_scores(cfg, epoch, imp['targets'].numpy(), out['scores'].cpu().numpy(),
+                                         {'auc': per[:, 0], 'mrr': per[:, 1], 'ndcg@5': per[:, 2], 'ndcg@10': per[:, 3]})
+    return res
 
 
 def save_checkpoint(cfg: Cfg, model, epoch: int) -> str:
@@ -145,12 +163,15 @@ def train(cfg_path: str, debug: bool = False, data: Optional[MindData] = None, *
     rng = random.Random(int(cfg.random_seed))
     stores = _stores(data.train_tables, text, device) if data.train_tables is not None else None
 
+    current = [0]
+
     def run_test():
         if data.test_tables is not None and data.test_sessions:
-            history['test'].append(evaluate(model, cfg, data.test_tables, data.test_sessions, device, debug))
+            history['test'].append(evaluate(model, cfg, data.test_tables, data.test_sessions, device, debug, epoch=current[0]))
             print('test:', history['test'][-1])
 
     for epoch in range(n_epochs):
+        current[0] = epoch
         print(f'\n Epoch {epoch}:')
         if stores is not None and data.train_sessions:
             model.train()

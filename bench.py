@@ -151,6 +151,27 @@ def time_cpu(batch_size, steps, warmup, threads):
     return batch_size * steps / dt, dt / steps
 
 
+def eval_cpu_baseline(cat, imp, model_sd, n_sample, threads):
+    """the reference evaluation procedure (training.py:194-243: ONE impression per step — full re-encode of the history
+    and every candidate, scores to the host, numpy metrics) restated by the oracle, on a bounded sample of the same
+    impressions -> (impressions/s, seconds)"""
+    from oracle import xnrs_oracle as O
+    from xnrs_b200 import synthetic as syn
+    torch.set_num_threads(threads)
+    P = {k: v.detach().cpu().clone() for k, v in model_sd.items()}
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        for i in range(n_sample):
+            a, b = int(imp['offsets'][i]), int(imp['offsets'][i + 1])
+            raw = {'hist_ids': imp['hist_ids'][i:i + 1], 'cand_ids': imp['cand_ids'][a:b][None, :],
+                   'targets': imp['targets'][a:b][None, :, None], 'user_index': imp['user_index'][i:i + 1],
+                   'main_theme': torch.zeros(1, dtype=torch.int32)}
+            scores = torch.relu(O.parent_forward(P, syn.dense_batch(cat, raw))).reshape(-1)
+            O.impression_metrics(imp['targets'][a:b].numpy(), scores.numpy())
+    dt = time.perf_counter() - t0
+    return n_sample / dt, dt
+
+
 def run_reference(args):
     """--impl reference: the reference algorithm's CPU path (oracle port; the Python reference cannot travel to the
     GPU box) with all host threads, same metric/config, each step a bounded sample of the workload."""
@@ -289,6 +310,16 @@ def run_eval(args):
                              'peak_source': pk_kind},
         'clocks': clocks.summary(),
     }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n_s = 400
+        threads = os.cpu_count() or 1
+        try:
+            v, dt = eval_cpu_baseline(cat, imp, model.state_dict(), n_s, threads)
+            res['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                                   'sample': f'{n_s} of the {n_imp} impressions, one per step with a full re-encode of history and candidates '
+                                             f'+ numpy metrics like training.py:194-243 (oracle, torch CPU fp32), {dt:.1f} s'}
+        except Exception as exc:                              # the baseline must never take the measurement down with it
+            res['cpu_baseline'] = {'value': None, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': f'failed: {exc!r}'}
     if rank == 0:
         print(json.dumps(res))
     if world > 1:

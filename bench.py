@@ -311,7 +311,7 @@ def run_eval(args):
         'clocks': clocks.summary(),
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n_s = 400
+        n_s = min(4000, n_imp)                                # ~6 s of host work on the box's 16 cores
         threads = os.cpu_count() or 1
         try:
             v, dt = eval_cpu_baseline(cat, imp, model.state_dict(), n_s, threads)

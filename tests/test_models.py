@@ -245,3 +245,17 @@ def test_prefetch_over_recycled_batches(monkeypatch):
             got = model(batches[i % 3])
             assert model.prefetch(batches[(i + 1) % 3])
             assert torch.equal(got, want[i % 3])
+
+
+def test_flat_adam_refuses_detached_gradients(device):
+    """FlatAdam updates from ONE flat gradient buffer; if user code replaces the parameters' .grad views
+    (model.zero_grad(set_to_none=True)) the step must fail loudly instead of training on zeros"""
+    fx, cfg, model = build('cl', device)
+    trainer = ContrastiveRankingTrainer(dict(cfg, lr=1e-3), model)
+    batch = fixture_batch(fx, device)
+    ids = {t: i for i, t in enumerate(sorted(set(batch['main_theme'])))}
+    batch['main_theme'] = torch.tensor([ids[t] for t in batch['main_theme']], dtype=torch.int32, device=device)
+    trainer._train_step(batch)                         # fine
+    model.zero_grad(set_to_none=True)
+    with pytest.raises(RuntimeError, match='flat gradient buffer'):
+        trainer._train_step(batch)

@@ -77,7 +77,17 @@ class FlatAdam:
     def zero_grad(self) -> None:
         self.flat_g.zero_()
 
+    def _check_views(self) -> None:
+        """the parameters' .grad must still be the views into flat_g handed out at construction (e.g. a
+        `model.zero_grad(set_to_none=True)` would silently detach them and the update would see zeros)"""
+        base = self.flat_g.untyped_storage().data_ptr()
+        for p in (self.params[0], self.params[-1]):
+            if p.grad is None or p.grad.untyped_storage().data_ptr() != base:
+                raise RuntimeError('FlatAdam: a parameter gradient no longer lives in the flat gradient buffer — use '
+                                   'optimizer.zero_grad() (not model.zero_grad(set_to_none=True)) between steps')
+
     def step(self, grad_scale: float = 1.0) -> None:
+        self._check_views()
         self.step_count += 1
         bc = None
         if self.graph_safe:

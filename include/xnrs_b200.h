@@ -22,7 +22,7 @@ enum { XNRS_ACT_NONE = 0, XNRS_ACT_RELU = 1, XNRS_ACT_TANH = 2, XNRS_ACT_RELU_MA
 /* arithmetic of the GEMM-shaped ops: exact fp32 FMA, 3xTF32 split (fp32-accurate, tensor cores),
  * single-pass TF32, or BF16 operands with fp32 accumulation */
 enum { XNRS_PREC_FP32 = 0, XNRS_PREC_TF32X3 = 1, XNRS_PREC_TF32 = 2, XNRS_PREC_BF16 = 3 };
-enum { XNRS_LOSS_MSE_RELU = 0, XNRS_LOSS_BCE_LOGITS = 1, XNRS_LOSS_NLL = 2 };
+enum { XNRS_LOSS_MSE_RELU = 0, XNRS_LOSS_BCE_LOGITS = 1, XNRS_LOSS_NLL = 2, XNRS_LOSS_BCE_SIGMOID = 3 };
 
 int xnrs_version(void);
 const char *xnrs_last_error(void);
@@ -56,12 +56,20 @@ int xnrs_gemm(int transA, int transB, long long M, long long N, long long K, con
               const int *a_rows, const float *B, long long ldb, const int *b_rows, float *C, long long ldc,
               const float *bias, int act, const float *aux, int accumulate, int split_k, int precision,
               xnrs_stream_t st);
+/* name of the kernel the calling thread's last xnrs_gemm dispatched to ("gemm_tc2_kernel ...", "gemm_tc_kernel<128> ...",
+ * "gemm_simt_kernel"), and the number of xnrs_gemm calls made in a tensor-core precision that the exact-fp32 SIMT kernel
+ * took instead (shape / alignment the TMA path cannot express): correct but slow, so it is counted, never silent */
+const char *xnrs_last_gemm_kernel(void);
+long long xnrs_gemm_simt_fallbacks(void);
 /* out[N] += column sums of X[M,N] (bias gradients) */
 int xnrs_colsum(const float *X, long long M, long long N, long long ldx, float *out, xnrs_stream_t st);
 /* y = a*x + b*y elementwise; a_dev (nullable) is a device scalar multiplied into a */
 int xnrs_axpby(long long n, float a, const float *a_dev, const float *x, float b, float *y, xnrs_stream_t st);
 int xnrs_relu(long long n, const float *x, float *y, xnrs_stream_t st);
 int xnrs_relu_bwd(long long n, const float *y, const float *dy, float *dx, xnrs_stream_t st);
+/* BCERankingTrainer's output activation (training.py:329-331) and its backward (y = the forward output) */
+int xnrs_sigmoid(long long n, const float *x, float *y, xnrs_stream_t st);
+int xnrs_sigmoid_bwd(long long n, const float *y, const float *dy, float *dx, xnrs_stream_t st);
 /* out (cols,rows) = in (rows,cols)^T */
 int xnrs_transpose(const float *in, long long rows, long long cols, float *out, xnrs_stream_t st);
 /* inverted dropout y = x * keep / (1-p)  (nn.Dropout: lstur.py:112,135; layers.py:148 lives inside xnrs_mha_*).
@@ -113,7 +121,8 @@ int xnrs_collapse_mask(const float *mask, long long R, int L, float *out, xnrs_s
 /* ---- row M: multi-head self-attention core (layers.py:133-151) -------------------------------
  * q,k,v,o: (R,L,h*dk) with row stride ld.  QUERY-axis mask (R*L, nullable): masked query rows attend
  * uniformly, keys are never masked.  Dropout on the normalised weights: keep (nullable, R*h*L*L 0/1)
- * is an explicit keep mask; else if p_drop > 0 a Philox stream (seed, per (r,head,i,j) counter) is used.
+ * is an explicit keep mask; else if p_drop > 0 a counter-based hash generator (splitmix64 of seed and the
+ * (r,head,i,j) counter; NOT torch's Philox stream — SURVEY §7 hard part 3) draws the keep decisions.
  * lse (R*h*L) is saved for the backward. */
 int xnrs_mha_fwd(const float *q, const float *k, const float *v, long long ld, const float *mask, long long R,
                  int L, int h, int dk, const float *keep, float p_drop, unsigned long long seed, float *o,
@@ -136,7 +145,8 @@ int xnrs_lengths_from_mask(const float *mask, long long B, int L, int *lengths, 
 
 /* ---- rows S + L-*: dot scoring (scoring.py:12-23) fused with the trainer losses
  * (training.py:336-337, 378-392; utils.py:117-131).  u (B,T), c (B,N,T), targets/weights (B*N).
- * Outputs: scores (B*N raw dot products), preds (B*N activated: relu for MSE, raw otherwise),
+ * Outputs: scores (B*N raw dot products), preds (B*N activated: relu for MSE, sigmoid for BCE_SIGMOID =
+ * BCERankingTrainer's nn.BCELoss on sigmoid scores (training.py:324-331), raw otherwise),
  * loss (1, overwritten), and — when d_u/d_c are non-null — gradients of the loss (times grad_scale).
  * With u == NULL, c holds (B,N) scores computed upstream and d_c (B,N) receives d loss / d score. */
 int xnrs_score_loss(const float *u, const float *c, const float *targets, const float *weights, int kind,
@@ -164,7 +174,7 @@ int xnrs_infonce_normalize_bwd(const float *d_ehat, const float *ehat, const flo
 /* ---- rows E + Me: per-impression scoring and ranking metrics (training.py:194-227; metrics.py:7-44)
  * CSR impressions: candidates of impression i are cand_ids[offsets[i]:offsets[i+1]].  score =
  * act(<user[i], news_vecs[cand]>) (act: 0 raw, 1 relu, 2 sigmoid), then nan_to_num(nan 0, +inf 1, -inf 0).
- * If user == NULL, `scores_io` already holds the scores.  metrics_out (n_imp,6) doubles:
+ * If user == NULL, `scores_io` holds raw scores computed upstream; `act` is applied to them in place.  metrics_out (n_imp,6) doubles:
  * auc, rr, ndcg@5, ndcg@10, ctr@1, ctr@10.  Tie order: descending score, then descending index. */
 int xnrs_eval_impressions(const float *user, const float *news_vecs, int T, const int *cand_ids,
                           const long long *offsets, const float *targets, long long n_imp, int act,

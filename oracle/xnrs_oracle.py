@@ -333,6 +333,16 @@ def bce_logits_loss(scores: Tensor, targets: Tensor, weights: Optional[Tensor] =
     return l.mean()
 
 
+def bce_sigmoid_loss(scores: Tensor, targets: Tensor, weights: Optional[Tensor] = None):
+    """BCERankingTrainer (training.py:324-331): prediction = sigmoid(score), loss = nn.BCELoss (each log term clamped
+    at -100 like torch.nn.functional.binary_cross_entropy), mean reduction."""
+    p = torch.sigmoid(scores)
+    l = -(targets * torch.clamp(torch.log(p), min=-100.0) + (1 - targets) * torch.clamp(torch.log(1 - p), min=-100.0))
+    if weights is not None:
+        l = l * weights
+    return l.mean(), p
+
+
 def ranking_nll(p: Tensor, n: Tensor, reduction: str = 'mean') -> Tensor:
     """utils.py:117-131 — un-stabilised softmax NLL of the positive among 1+K."""
     ep = torch.exp(p)

@@ -259,6 +259,9 @@ def _xnrs_score_loss(u, c, targets, weights, kind, B, N, T, gscale, scores, pred
             p = s
             t = targets.reshape(B, N)
             l = ((torch.clamp(s, min=0) - s * t + torch.log1p(torch.exp(-s.abs()))) * w).mean()
+        elif kind == K.LOSS_BCE_SIGMOID:
+            p = torch.sigmoid(s)
+            l = torch.nn.functional.binary_cross_entropy(p, targets.reshape(B, N), weight=None if weights is None else w)
         else:
             p = s
             e = torch.exp(s)
@@ -272,6 +275,14 @@ def _xnrs_score_loss(u, c, targets, weights, kind, B, N, T, gscale, scores, pred
     if preds is not None:
         preds.copy_(p.detach())
     loss.copy_(l.detach().reshape(1))
+
+
+def _xnrs_sigmoid(n, x, y):
+    y.copy_(torch.sigmoid(x))
+
+
+def _xnrs_sigmoid_bwd(n, y, dy, dx):
+    dx.copy_(dy * y * (1 - y))
 
 
 def _xnrs_dot_score(u, c, B, N, T, scores):
@@ -336,6 +347,9 @@ def _xnrs_eval_impressions(user, news_vecs, T, cand_ids, offsets, targets, n_imp
             s = news_vecs[cand_ids[a:b].long()] @ user[i]
             s = torch.relu(s) if act == 1 else (torch.sigmoid(s) if act == 2 else s)
             scores[a:b] = s
+        elif act:
+            s = scores[a:b]
+            scores[a:b] = torch.relu(s) if act == 1 else torch.sigmoid(s)
         r = O.impression_metrics(targets[a:b].numpy(), scores[a:b].numpy())
         metrics[i] = torch.tensor([r['auc'], r['rr'], r['ndcg@5'], r['ndcg@10'], r['ctr@1'], r['ctr@10']],
                                   dtype=torch.float64)

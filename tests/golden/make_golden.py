@@ -116,6 +116,8 @@ def model_fixture(name, over, seed):
     l_rec = torch.nn.functional.mse_loss(torch.relu(scores), batch['targets'])
     out['ref/loss_mse'] = l_rec.detach().numpy()
     out['ref/loss_bce'] = torch.nn.functional.binary_cross_entropy_with_logits(scores, batch['targets']).detach().numpy()
+    # BCERankingTrainer (training.py:324-331): forward = sigmoid(model(batch)), L = nn.BCELoss()
+    out['ref/loss_bce_sigmoid'] = torch.nn.BCELoss()(torch.sigmoid(scores), batch['targets']).detach().numpy()
     if hasattr(model, 'get_user_embeddings'):
         ue = model.get_user_embeddings(batch)
         out['ref/user_emb'] = ue.detach().numpy()

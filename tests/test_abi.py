@@ -14,9 +14,10 @@ def test_header_prototypes_parse():
                  'xnrs_score_loss', 'xnrs_infonce_rows', 'xnrs_eval_impressions', 'xnrs_adam_step',
                  'xnrs_gather_rows', 'xnrs_expand_titles'):
         assert must in protos
-    # every prototype ends with the stream argument (no hidden streams), except the three queries
+    # every prototype ends with the stream argument (no hidden streams), except the host-side queries / switches
     for name, (_, args) in protos.items():
-        if name not in ('xnrs_version', 'xnrs_last_error', 'xnrs_launch_count', 'xnrs_device_is_sm100', 'xnrs_set_option'):
+        if name not in ('xnrs_version', 'xnrs_last_error', 'xnrs_launch_count', 'xnrs_device_is_sm100', 'xnrs_set_option',
+                        'xnrs_last_gemm_kernel', 'xnrs_gemm_simt_fallbacks'):
             assert args and args[-1] is ctypes.c_void_p, name
 
 

@@ -229,7 +229,7 @@ def test_gru_forward_backward(B, L, I, Hd, with_h0):
         assert_close(Pg[k].grad, Po[k].grad, TOL, 'grad ' + k)
 
 
-@pytest.mark.parametrize('kind', [K.LOSS_MSE_RELU, K.LOSS_BCE_LOGITS, K.LOSS_NLL])
+@pytest.mark.parametrize('kind', [K.LOSS_MSE_RELU, K.LOSS_BCE_LOGITS, K.LOSS_NLL, K.LOSS_BCE_SIGMOID])
 @pytest.mark.parametrize('B,N,T', [(64, 5, 256), (3, 300, 272)])
 def test_score_loss_fused(kind, B, N, T):
     gg = g(41)
@@ -243,6 +243,8 @@ def test_score_loss_fused(kind, B, N, T):
         want, _ = O.mse_relu_loss(s, t.unsqueeze(-1), w.unsqueeze(-1))
     elif kind == K.LOSS_BCE_LOGITS:
         want = O.bce_logits_loss(s, t.unsqueeze(-1), w.unsqueeze(-1))
+    elif kind == K.LOSS_BCE_SIGMOID:
+        want, _ = O.bce_sigmoid_loss(s, t.unsqueeze(-1), w.unsqueeze(-1))
     else:
         want = O.ranking_nll(s[:, :1, 0], s[:, 1:, 0])
     want.backward()

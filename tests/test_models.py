@@ -13,7 +13,8 @@ import _kernel_emulator as EMU
 from _common import MODEL_NAMES, assert_close, fixture_batch, fixture_cfg, load_npz, sub
 from xnrs_b200 import kernels as K
 from xnrs_b200.models import make_model
-from xnrs_b200.training import BCELogitsRankingTrainer, ContrastiveRankingTrainer, MSERankingTrainer
+from xnrs_b200.training import (BCELogitsRankingTrainer, BCERankingTrainer, ContrastiveRankingTrainer,
+                                MSERankingTrainer)
 
 TOL = 1e-4          # north-star fp32 tolerance (relative to the tensor's scale)
 
@@ -96,6 +97,46 @@ def test_bce_trainer_and_unfused_hooks(name, device):
     assert_close(tr2.L(s, batch['targets']), fx['ref/loss_mse'], TOL, 'mse via self.L')
     assert_close(tr2.forward(batch), np.maximum(fx['ref/scores'], 0), TOL, 'forward() = relu(scores)')
     assert_close(tr.L(s, batch['targets']), fx['ref/loss_bce'], TOL, 'bce via self.L')
+
+
+def _one_impression(batch):
+    return {'user_features': {'history': {'title_emb': tuple(t[:1] for t in batch['user_features']['history']['title_emb'])},
+                              'other': {}},
+            'candidate_features': {'title_emb': tuple(t[:1] for t in batch['candidate_features']['title_emb'])},
+            'targets': batch['targets'][:1]}
+
+
+def test_bce_sigmoid_trainer(device):
+    """BCERankingTrainer (training.py:324-331): forward() = sigmoid(scores), L = nn.BCELoss — pinned to the reference value."""
+    fx, cfg, model = build('cl', device)
+    batch = fixture_batch(fx, device)
+    tr = BCERankingTrainer(cfg, model)
+    loss, preds, _ = tr.rec_loss(batch)
+    sig = 1.0 / (1.0 + np.exp(-fx['ref/scores'].astype(np.float64)))
+    assert_close(loss, fx['ref/loss_bce_sigmoid'], TOL, 'BCELoss(sigmoid(s))')
+    assert_close(preds, sig, TOL, 'preds = sigmoid(scores)')
+    assert_close(tr.forward(batch), sig, TOL, 'forward() = sigmoid(scores)')
+    assert_close(tr.L(tr.raw_scores(batch), batch['targets']), fx['ref/loss_bce_sigmoid'], TOL, 'bce via self.L')
+    from oracle import xnrs_oracle as O
+    want, _ = O.bce_sigmoid_loss(torch.tensor(fx['ref/scores']), torch.tensor(fx['batch/targets']))
+    assert_close(want, fx['ref/loss_bce_sigmoid'], 2e-6, 'oracle restatement of nn.BCELoss')
+
+
+@pytest.mark.parametrize('trainer', [BCELogitsRankingTrainer, BCERankingTrainer])
+def test_bce_test_step_ranks_sigmoid_scores(trainer, device):
+    """both BCE trainers evaluate sigmoid(score) (training.py:329-331 via forward(); :357 after the loss)"""
+    fx, cfg, model = build('cl', device)
+    batch = fixture_batch(fx, device)
+    out = trainer(cfg, model)._test_step(_one_impression(batch))
+    from oracle import xnrs_oracle as O
+    s = 1.0 / (1.0 + np.exp(-fx['ref/scores'][0, :, 0].astype(np.float64)))
+    assert_close(out['scores'], s, TOL, 'ranked scores = sigmoid(raw)')
+    want = O.impression_metrics(fx['batch/targets'][0, :, 0], s.astype(np.float32))
+    for k in ('auc', 'rr', 'ndcg@5', 'ndcg@10', 'ctr@1', 'ctr@10'):
+        assert abs(out[k] - want[k]) < 1e-6, (k, out[k], want[k])
+    ref_loss = float(fx['ref/loss_bce']) if trainer is BCELogitsRankingTrainer else None
+    if ref_loss is not None:            # the loss of the single impression differs from the batch loss: just finite
+        assert np.isfinite(float(out['loss']))
 
 
 def test_train_step_matches_torch_adam(device):

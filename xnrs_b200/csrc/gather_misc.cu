@@ -131,6 +131,17 @@ __global__ void relu_bwd_kernel(long long n, const float *__restrict__ y, const 
         dx[i] = y[i] > 0.f ? dy[i] : 0.f;
 }
 
+__global__ void sigmoid_kernel(long long n, const float *__restrict__ x, float *__restrict__ y) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        y[i] = 1.f / (1.f + expf(-x[i]));
+}
+
+__global__ void sigmoid_bwd_kernel(long long n, const float *__restrict__ y, const float *__restrict__ dy,
+                                   float *__restrict__ dx) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dx[i] = dy[i] * y[i] * (1.f - y[i]);
+}
+
 __global__ void transpose_kernel(const float *__restrict__ in, long long rows, long long cols, float *__restrict__ out) {
     __shared__ float tile[32][33];
     long long c0 = blockIdx.x * 32LL, r0 = blockIdx.y * 32LL;
@@ -318,6 +329,22 @@ extern "C" int xnrs_dropout(long long n, const float *x, const float *keep, floa
     if (n <= 0) return XNRS_OK;
     XNRS_REQUIRE(x && y, "null pointer");
     dropout_kernel<<<ew_grid(n, 256), 256, 0, STREAM(st)>>>(n, x, keep, p, seed, y);
+    XNRS_LAUNCHED();
+    return XNRS_OK;
+}
+
+extern "C" int xnrs_sigmoid(long long n, const float *x, float *y, xnrs_stream_t st) {
+    if (n <= 0) return XNRS_OK;
+    XNRS_REQUIRE(x && y, "null pointer");
+    sigmoid_kernel<<<ew_grid(n, 256), 256, 0, STREAM(st)>>>(n, x, y);
+    XNRS_LAUNCHED();
+    return XNRS_OK;
+}
+
+extern "C" int xnrs_sigmoid_bwd(long long n, const float *y, const float *dy, float *dx, xnrs_stream_t st) {
+    if (n <= 0) return XNRS_OK;
+    XNRS_REQUIRE(y && dy && dx, "null pointer");
+    sigmoid_bwd_kernel<<<ew_grid(n, 256), 256, 0, STREAM(st)>>>(n, y, dy, dx);
     XNRS_LAUNCHED();
     return XNRS_OK;
 }

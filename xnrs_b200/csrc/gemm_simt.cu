@@ -201,6 +201,11 @@ int gemm_simt(const GemmArgs &a_in, cudaStream_t st) {
 
 using namespace xnrs;
 
+namespace xnrs {
+thread_local const char *g_last_gemm_kernel = "";
+std::atomic<long long> g_simt_fallbacks{0};
+}  // namespace xnrs
+
 extern "C" int xnrs_gemm(int transA, int transB, long long M, long long N, long long K, const float *A,
                          long long lda, const int *a_rows, const float *B, long long ldb, const int *b_rows,
                          float *C, long long ldc, const float *bias, int act, const float *aux, int accumulate,
@@ -217,6 +222,11 @@ extern "C" int xnrs_gemm(int transA, int transB, long long M, long long N, long 
     if (precision != XNRS_PREC_FP32) {
         int status = XNRS_OK;
         if (gemm_tensorcore(a, precision, STREAM(st), &status)) return status;
+        g_simt_fallbacks.fetch_add(1, std::memory_order_relaxed);
     }
+    g_last_gemm_kernel = "gemm_simt_kernel";
     return gemm_simt(a, STREAM(st));
 }
+
+extern "C" const char *xnrs_last_gemm_kernel(void) { return g_last_gemm_kernel; }
+extern "C" long long xnrs_gemm_simt_fallbacks(void) { return g_simt_fallbacks.load(); }

@@ -858,8 +858,15 @@ int gemm_tensorcore(const GemmArgs &a, int precision, cudaStream_t st, int *stat
     if (use2) {
         const long long pairs = total < num_sms() / 2 ? total : num_sms() / 2;
         gemm_tc2_kernel<<<(unsigned)(2 * pairs), TC2_THREADS, smem_bytes, st>>>(mapA, mapB, p);
-    } else if (BN == 256) gemm_tc_kernel<256><<<grid, TC_THREADS, smem_bytes, st>>>(mapA, mapB, p);
-    else gemm_tc_kernel<128><<<grid, TC_THREADS, smem_bytes, st>>>(mapA, mapB, p);
+        g_last_gemm_kernel = p.passes == 3 ? "gemm_tc2_kernel (cta_group::2, 256x256 pair tile, 3xTF32)"
+                                           : "gemm_tc2_kernel (cta_group::2, 256x256 pair tile, TF32)";
+    } else if (BN == 256) {
+        gemm_tc_kernel<256><<<grid, TC_THREADS, smem_bytes, st>>>(mapA, mapB, p);
+        g_last_gemm_kernel = p.passes == 3 ? "gemm_tc_kernel<256> (3xTF32)" : "gemm_tc_kernel<256> (TF32)";
+    } else {
+        gemm_tc_kernel<128><<<grid, TC_THREADS, smem_bytes, st>>>(mapA, mapB, p);
+        g_last_gemm_kernel = p.passes == 3 ? "gemm_tc_kernel<128> (3xTF32)" : "gemm_tc_kernel<128> (TF32)";
+    }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {

@@ -57,6 +57,14 @@ score_loss_kernel(const float *__restrict__ u, const float *__restrict__ c, cons
                 p = fmaxf(sv, 0.f);
                 l = (p - t) * (p - t);
                 gr = sv > 0.f ? 2.f * (p - t) : 0.f;
+            } else if (kind == XNRS_LOSS_BCE_SIGMOID) {
+                // nn.BCELoss()(sigmoid(s), t) (training.py:324-331): each log term is clamped at -100 like torch does, and a
+                // clamped term passes no gradient
+                p = 1.f / (1.f + expf(-sv));
+                const float lp = logf(p), lq = logf(1.f - p);
+                l = -(t * fmaxf(lp, -100.f) + (1.f - t) * fmaxf(lq, -100.f));
+                const float dp = -(lp > -100.f ? t / p : 0.f) + (lq > -100.f ? (1.f - t) / (1.f - p) : 0.f);
+                gr = dp * p * (1.f - p);
             } else {   // BCE with logits
                 p = sv;
                 l = fmaxf(sv, 0.f) - sv * t + log1pf(expf(-fabsf(sv)));
@@ -212,7 +220,7 @@ extern "C" int xnrs_score_loss(const float *u, const float *c, const float *targ
                                long long B, int N, int T, float grad_scale, float *scores, float *preds, float *loss,
                                float *d_u, float *d_c, xnrs_stream_t st) {
     XNRS_REQUIRE(B >= 0 && N > 0 && (!u || (T > 0 && T % 4 == 0)), "bad sizes (T % 4 == 0)");
-    XNRS_REQUIRE(kind >= 0 && kind <= 2, "bad loss kind");
+    XNRS_REQUIRE(kind >= 0 && kind <= 3, "bad loss kind");
     XNRS_REQUIRE(loss && scores, "null pointer");
     XNRS_REQUIRE(!u || (d_u == nullptr) == (d_c == nullptr), "d_u and d_c go together");
     cudaMemsetAsync(loss, 0, sizeof(float), STREAM(st));

@@ -64,6 +64,14 @@ eval_impressions_kernel(const float *__restrict__ user, const float *__restrict_
                 }
             }
             __syncthreads();
+        } else if (act != 0) {       // scores computed upstream: the trainer's output activation still applies (BCE: sigmoid)
+            for (int c = tid; c < n; c += blockDim.x) {
+                float v = gs[c];
+                if (act == 1) v = fmaxf(v, 0.f);
+                else v = 1.f / (1.f + expf(-v));
+                gs[c] = v;
+            }
+            __syncthreads();
         }
         const bool in_smem = n <= MCAP;
         if (in_smem) {
@@ -184,7 +192,14 @@ eval_impressions_warp_kernel(const float *__restrict__ user, const float *__rest
             }
             for (int c = lane; c < n; c += 32) s_tg[c] = gt[c];
         } else {
-            for (int c = lane; c < n; c += 32) { s_sc[c] = nan_to_num_f(gs[c]); s_tg[c] = gt[c]; }
+            for (int c = lane; c < n; c += 32) {
+                float v = gs[c];
+                if (act == 1) v = fmaxf(v, 0.f);
+                else if (act == 2) v = 1.f / (1.f + expf(-v));
+                if (act != 0) gs[c] = v;
+                s_sc[c] = nan_to_num_f(v);
+                s_tg[c] = gt[c];
+            }
         }
         __syncwarp();
         double dcg5 = 0, dcg10 = 0, idcg5 = 0, idcg10 = 0, ctr1 = 0, ctr10 = 0, rr = 0;

@@ -159,8 +159,26 @@ class DataParallelTrainer:
         fn = getattr(self.trainer.model, 'prefetch', None)
         return bool(fn(batch, after)) if fn is not None else False
 
+    def _check_equal_shards(self, batch: dict) -> None:
+        """the packed all-gather / reduce-scatter of the InfoNCE term and the flat 1/world gradient average need the SAME
+        number of impressions on every rank; a ragged split (B % world != 0) would hang NCCL or mis-weight the loss, so it is
+        rejected loudly on first use and whenever the local batch size changes"""
+        n = int(batch['targets'].shape[0])
+        if getattr(self, '_checked_b', None) == n:
+            return
+        dev = self.trainer.device
+        mm = torch.tensor([n, -n], device=dev, dtype=torch.int64)
+        dist.all_reduce(mm, op=dist.ReduceOp.MAX)
+        if int(mm[0]) != -int(mm[1]):
+            raise RuntimeError(f'data-parallel train_step needs the same number of impressions on every rank '
+                               f'(this rank has {n}; ranks hold between {-int(mm[1])} and {int(mm[0])}): '
+                               f'make the global batch a multiple of the world size')
+        self._checked_b = n
+
     def train_step(self, batch: dict) -> dict:
         tr = self.trainer
+        if self.world > 1:
+            self._check_equal_shards(batch)
         tr.optimizer.zero_grad()
         if hasattr(tr, 'losses'):
             total, loss_rec, loss_cl, preds = tr.losses(batch)

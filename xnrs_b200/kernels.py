@@ -14,7 +14,7 @@ import torch
 from . import _lib
 
 ACT_NONE, ACT_RELU, ACT_TANH, ACT_RELU_MASK = 0, 1, 2, 3
-LOSS_MSE_RELU, LOSS_BCE_LOGITS, LOSS_NLL = 0, 1, 2
+LOSS_MSE_RELU, LOSS_BCE_LOGITS, LOSS_NLL, LOSS_BCE_SIGMOID = 0, 1, 2, 3
 PRECISIONS = {'fp32': 0, 'tf32x3': 1, 'tf32': 2, 'bf16': 3}
 _precision = 0
 
@@ -670,6 +670,26 @@ class ReluFn(torch.autograd.Function):
         dy = _f32(dy)
         dx = torch.empty_like(dy)
         call('xnrs_relu_bwd', dy.numel(), y, dy, dx)
+        return dx
+
+
+class SigmoidFn(torch.autograd.Function):
+    """BCERankingTrainer's output activation (training.py:329-331)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _f32(x)
+        y = torch.empty_like(x)
+        call('xnrs_sigmoid', x.numel(), x, y)
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        dy = _f32(dy)
+        dx = torch.empty_like(dy)
+        call('xnrs_sigmoid_bwd', dy.numel(), y, dy, dx)
         return dx
 
 

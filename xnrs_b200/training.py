@@ -7,7 +7,10 @@ out of scope): dataloaders, epoch loops, wandb, checkpoint / CSV export.
 Differences that are deliberate and documented in DESIGN.md:
   * the user embedding for the contrastive term is taken from the SAME forward pass as the scores
     (``share_user_forward=True``); the reference runs the history side twice (training.py:409), which
-    gives identical values whenever dropout is off (every config except NRMS' attention dropout);
+    gives identical values whenever dropout is off.  With dropout active in train mode (NRMS' attention
+    dropout p=0.1, LSTUR's p_user_dropout=0.07) the reference draws two independent masks where this code
+    draws one — the same distribution of each term, a different joint draw; ``share_user_forward=False``
+    restores the second pass;
   * all parameters live in one flat buffer so Adam is one kernel launch and data-parallel training
     all-reduces one bucket.
 """
@@ -81,7 +84,7 @@ class FlatAdam:
         """the parameters' .grad must still be the views into flat_g handed out at construction (e.g. a
         `model.zero_grad(set_to_none=True)` would silently detach them and the update would see zeros)"""
         base = self.flat_g.untyped_storage().data_ptr()
-        for p in (self.params[0], self.params[-1]):
+        for p in self.params:                  # a pointer compare per parameter (a middle one can be detached too)
             if p.grad is None or p.grad.untyped_storage().data_ptr() != base:
                 raise RuntimeError('FlatAdam: a parameter gradient no longer lives in the flat gradient buffer — use '
                                    'optimizer.zero_grad() (not model.zero_grad(set_to_none=True)) between steps')
@@ -101,7 +104,8 @@ class RankingTrainer:
     """common part of the reference's BaseTrainer / RankingTrainer (training.py:24-44, 191-243)."""
 
     loss_kind = K.LOSS_MSE_RELU
-    eval_act = 1            # activation applied to raw scores before the ranking metrics (relu)
+    eval_act = 1            # activation that takes RAW scores to the ranked scores (catalogue evaluation): relu
+    test_act = 0            # activation _test_step still has to apply to forward()'s output before the metrics
 
     def __init__(self, cfg, model: nn.Module, trainset=None, testset=None, graph_safe: bool = False):
         self.cfg = cfg if isinstance(cfg, Cfg) else Cfg(cfg)
@@ -130,7 +134,11 @@ class RankingTrainer:
     def forward(self, batch) -> torch.Tensor:
         """scores with the trainer's output activation (training.py:388-392 applies relu)."""
         s = self.raw_scores(batch)
-        return K.ReluFn.apply(s) if self.loss_kind == K.LOSS_MSE_RELU else s
+        if self.loss_kind == K.LOSS_MSE_RELU:
+            return K.ReluFn.apply(s)
+        if self.loss_kind == K.LOSS_BCE_SIGMOID:
+            return K.SigmoidFn.apply(s)
+        return s
 
     def _embeddings(self, batch):
         """(u (B,T), c (B,N,T)) from ONE forward pass; None if the model cannot return embeddings (NPA)."""
@@ -144,10 +152,12 @@ class RankingTrainer:
         B, N, T = c.shape
         return K._f32(u).reshape(B, T), K._f32(c)
 
+    use_weights = True      # batch['weights'] enters the loss (training.py:101-105); the contrastive trainer ignores it
+
     def rec_loss(self, batch):
         """-> (loss_rec, preds (B,N,1), user_emb (B,T) or None): scorer and loss fused when the model exposes u, c."""
         t = _flat(batch['targets'].to(self.device))
-        w = _flat(batch['weights'].to(self.device)) if 'weights' in batch else None
+        w = _flat(batch['weights'].to(self.device)) if (self.use_weights and 'weights' in batch) else None
         uc = self._embeddings(batch)
         if uc is not None:
             u, c = uc
@@ -175,15 +185,14 @@ class RankingTrainer:
 
     @torch.no_grad()
     def _test_step(self, batch: dict) -> dict:
-        """RankingTrainer._test_step (training.py:194-243) for one impression (B=1, all candidates)."""
+        """RankingTrainer._test_step (training.py:194-243) for one impression (B=1, all candidates): the metrics rank
+        ``self.forward(batch)``; BCELogitsRankingTrainer ranks sigmoid(forward) (training.py:345-373, ``test_act`` 2)."""
         t = batch['targets'].to(self.device)
         loss, preds, _ = self.rec_loss(batch)
-        raw = self.raw_scores(batch) if self.eval_act == 2 else None
-        scores = K._f32(preds).reshape(-1) if raw is None else K._f32(raw).reshape(-1)
+        scores = K._f32(preds).reshape(-1).clone()
         n = scores.numel()
         offsets = torch.tensor([0, n], device=self.device, dtype=torch.int64)
-        scores = scores.clone()
-        _, m = K.eval_impressions(None, None, None, offsets, _flat(t), act=0 if raw is None else 2, scores=scores)
+        _, m = K.eval_impressions(None, None, None, offsets, _flat(t), act=self.test_act, scores=scores)
         m = m[0].tolist()
         return {'auc': m[0], 'rr': m[1], 'ndcg@5': m[2], 'ndcg@10': m[3], 'ctr@1': m[4], 'ctr@10': m[5],
                 'scores': scores, 'targets': t.reshape(-1), 'loss': loss}
@@ -199,14 +208,23 @@ class MSERankingTrainer(RankingTrainer):
     eval_act = 1
 
 
+class BCERankingTrainer(RankingTrainer):
+    """training.py:324-331 — nn.BCELoss on sigmoid(score); forward() returns the sigmoid scores, which are also ranked."""
+    loss_kind = K.LOSS_BCE_SIGMOID
+    eval_act = 2
+
+
 class BCELogitsRankingTrainer(RankingTrainer):
-    """training.py:334-373 — BCE with logits; evaluation ranks sigmoid(score)."""
+    """training.py:334-373 — BCE with logits; forward() returns raw scores, evaluation ranks sigmoid(score)."""
     loss_kind = K.LOSS_BCE_LOGITS
     eval_act = 2
+    test_act = 2
 
 
 class ContrastiveRankingTrainer(MSERankingTrainer):
     """training.py:395-472 — MSE(relu(score), target) + lambda * supervised InfoNCE(user embeddings, theme)."""
+
+    use_weights = False     # its _train_step calls self.L(preds, targets) without the weights (training.py:405-407)
 
     def __init__(self, cfg, model, trainset=None, testset=None, share_user_forward: bool = True,
                  graph_safe: bool = False):

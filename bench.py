@@ -1,19 +1,26 @@
 #!/usr/bin/env python
-"""Headline benchmark: CL bi-encoder (config/mind_small_CL.yml, `model: standard`) TRAINING throughput in
-impressions/s on synthetic MIND-shaped data (BASELINE.json configs[1]; north-star shapes S=30, H=50, 1:4).
+"""Benchmark of the xnrs bi-encoder hot path on B200 (BASELINE.json: "train impressions/s & eval scored impressions/s").
 
-One "step" = one full ContrastiveRankingTrainer step over one batch of impressions: index gather from the
-device-resident token table, title + user encoders, fused dot-score + MSE(ReLU), supervised InfoNCE,
-backward through everything, Adam.  Contract: see the task statement (`value` = inputs resident in HBM,
-`e2e` = host index buffers + H2D + D2H loss read inside the timed region, `roofline` for the dominant
-kernel timed live with CUDA events, `cpu_baseline` = the CPU oracle on a bounded sample).
+    python bench.py [--gpus N] [--steps K] [--warmup W]          ONE JSON line:
+        headline   = CL bi-encoder (config/mind_small_CL.yml, `model: standard`) TRAINING throughput, BASELINE configs[1]
+        sub.nrms_train = NRMS (config/mind_small_NRMS.yml) training throughput, BASELINE configs[0]
+        sub.eval       = MIND-large-shaped full-catalogue evaluation (160k news, 376 471 impressions), BASELINE configs[4]
+      each with its own value / e2e / roofline / cpu_baseline; north-star shapes S=30, H=50, 1:4 negatives, synthetic data.
+    python bench.py --only cl|nrms|naml|lstur|npa|eval ...        one workload (diagnostics, secondary models)
+    python bench.py --impl reference ...                          the UNMODIFIED reference (oracle/_ref, see oracle/make_ref.py)
+                                                                  on the box's host cores, same line format
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B] [--precision fp32]
-N>1 is launched by torchrun (one rank per GPU, NCCL); rank 0 prints ONE JSON line.
+A "step" of a train workload = one full trainer step over one batch of impressions (index gather from the device-resident
+token table, title + user encoders, fused score + loss, InfoNCE, backward, Adam); a "step" of the eval workload = one full
+pass (catalogue encode + every impression).  `value`: inputs resident in HBM; `e2e`: through the public trainer /
+evaluator API from pinned HOST buffers, H2D + result read-back inside the timed region.  Every timed region is EXACTLY K
+steps bracketed by barrier + synchronize; regions are repeated until >= 1 s has been measured and the MEDIAN region is
+reported (min / max beside it).  N > 1 is launched by torchrun (one rank per GPU, NCCL); rank 0 prints the line.
 """
 import argparse
 import json
 import os
+import statistics
 import subprocess
 import sys
 import threading
@@ -27,7 +34,7 @@ import torch  # noqa: E402
 CL_CFG = dict(model='standard', scoring='dot', text_features=['title_emb'], catg_features=[], title_emb_dim=256,
               total_emb_dim=256, d_backbone=768, p_dropout=0., bias=False, n_negatives=4, lr=1e-4,
               contrastive_temperature=0.08, contrastive_lambda=0.01)          # config/mind_small_CL.yml
-# the other BASELINE.json configs (secondary lines: `--model nrms|naml|lstur|npa`), hyper-parameters from config/mind_small_*.yml
+# the other BASELINE.json configs, hyper-parameters from config/mind_small_*.yml
 _COMMON = dict(scoring='dot', title_emb_dim=256, d_backbone=768, p_dropout=0., bias=False, n_negatives=4, lr=1e-4,
                n_categories=19, n_subcategories=300, n_users=703_789, cat_emb_dim=16, sub_emb_dim=16, n_heads=16,
                contrastive_temperature=0.08, contrastive_lambda=0.1)
@@ -41,7 +48,10 @@ MODEL_CFGS = {
     'npa': dict(_COMMON, model='NPA', text_features=['title_emb'], catg_features=[], total_emb_dim=256, user_emb_dim=64),
 }
 SEQ_LEN, HIST_LEN, N_NEWS, VOCAB = 30, 50, 65_238, 100_000                     # SURVEY §8(d) north-star shapes
-METRIC, UNIT = 'train impressions/s', 'impressions/s'
+EVAL_NEWS = 160_000
+UNIT = 'impressions/s'
+MIN_TIMED_S = 1.0            # every reported number comes from >= this much measured time
+TRAFFIC_FILE = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
 
 
 def workload_name(batch, model='cl'):
@@ -81,6 +91,7 @@ class ClockSampler:
             t0 = time.perf_counter()
             while not self.rows and time.perf_counter() - t0 < 5.0:
                 time.sleep(0.02)
+            self.rows.clear()                    # samples from before the timed region do not count
             torch.cuda.synchronize()
         except Exception:
             self.proc = None
@@ -108,22 +119,124 @@ class ClockSampler:
         return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': max(mx), 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
-def oracle_step_fn(batch_size, threads):
-    """the CPU path: the oracle's restatement of ContrastiveRankingTrainer._train_step (two history forwards like
-    the reference, training.py:402-431) + autograd + Adam, on dense host batches built from the same ids."""
-    from oracle import xnrs_oracle as O
+class Ctx:
+    """process-wide state: rank / world / device and the barrier-bracketed region timer"""
+
+    def __init__(self, gpus):
+        import torch.distributed as dist
+        self.dist = dist
+        self.world = int(os.environ.get('WORLD_SIZE', '1'))
+        self.rank = int(os.environ.get('RANK', '0'))
+        self.local = int(os.environ.get('LOCAL_RANK', '0'))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device('cuda', self.local)
+        if self.world > 1:
+            dist.init_process_group('nccl', device_id=self.dev)
+        if self.world != gpus and self.rank == 0:
+            print(f'warning: --gpus {gpus} but WORLD_SIZE {self.world}', file=sys.stderr)
+
+    def sync_all(self):
+        torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(self, x: float) -> float:
+        if self.world == 1:
+            return float(x)
+        t = torch.tensor([x], device=self.dev, dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t)
+
+    def timed_regions(self, region, min_total_s=MIN_TIMED_S, max_regions=400):
+        """region() runs EXACTLY K steps and returns its duration in ms (this rank); every region is bracketed by barrier +
+        synchronize on both sides and its duration is the MAX over ranks.  Regions repeat until min_total_s is covered
+        (the repetition count follows the all-reduced times, so every rank takes the same decision)."""
+        out, total = [], 0.0
+        while (total < min_total_s * 1e3 and len(out) < max_regions) or not out:
+            self.sync_all()
+            ms = region()
+            self.sync_all()
+            ms = self.max_over_ranks(ms)
+            out.append(ms)
+            total += ms
+        return out
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def spread(ms_list, units_per_region):
+    """median region -> value; the run-to-run resolution beside it"""
+    med = statistics.median(ms_list)
+    return med, {'regions': len(ms_list), 'timed_s': round(sum(ms_list) * 1e-3, 3),
+                 'value_min': units_per_region / (max(ms_list) * 1e-3), 'value_max': units_per_region / (min(ms_list) * 1e-3)}
+
+
+def traffic_entry(key):
+    """measured DRAM traffic of a kernel class from the tracked ncu summary (profiles/ncu_traffic.json), or None"""
+    try:
+        return json.load(open(TRAFFIC_FILE))['classes'].get(key)
+    except Exception:
+        return None
+
+
+# =====================================================================================================================
+# CPU arms: the unmodified reference (oracle/_ref) when it travelled with the repo, else the oracle port
+# =====================================================================================================================
+
+def _str_themes(batch):
+    b = dict(batch)
+    b['main_theme'] = [str(int(t)) for t in batch['main_theme']]          # the reference numbers theme STRINGS (training.py:414-417)
+    return b
+
+
+def cpu_train_step_fn(model_key, batch_size, threads, device='cpu', tf32=False):
+    """-> (step(), kind): one ContrastiveRankingTrainer._train_step (MSERankingTrainer for NPA, which has no CL hook) of the
+    reference on dense reference-format batches built from the same synthetic ids.  kind "reference": the unmodified
+    reference package; "port": the oracle's restatement (two history forwards like training.py:402-431, autograd, Adam)."""
+    from oracle import refload
     from xnrs_b200 import synthetic as syn
-    from xnrs_b200.models import make_model
     torch.set_num_threads(threads)
-    cat = syn.make_catalogue(N_NEWS, SEQ_LEN, VOCAB, 768, seed=0)
-    torch.manual_seed(0)
-    P = {k: v.detach().clone().requires_grad_(True) for k, v in make_model(CL_CFG).state_dict().items()}
-    state = {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in P.items()}
-    batches = [syn.dense_batch(cat, syn.make_train_batch(N_NEWS, batch_size, HIST_LEN, seed=100 + i)) for i in range(2)]
+    cfg = dict(MODEL_CFGS[model_key], device=str(device), seq_len=SEQ_LEN, hist_len=HIST_LEN, batch_size=batch_size)
+    cat = syn.make_catalogue(N_NEWS, SEQ_LEN, VOCAB, 768, seed=0, with_abstract=(model_key == 'naml'))
+
+    def to_dev(x):
+        if isinstance(x, torch.Tensor):
+            return x.to(device)
+        if isinstance(x, dict):
+            return {k: to_dev(v) for k, v in x.items()}
+        if isinstance(x, (tuple, list)):
+            return type(x)(to_dev(v) for v in x)
+        return x
+
+    batches = [to_dev(syn.dense_batch(cat, syn.make_train_batch(N_NEWS, batch_size, HIST_LEN, seed=100 + i),
+                                      with_abstract=(model_key == 'naml'))) for i in range(2)]
     counter = [0]
+    if refload.available():
+        torch.manual_seed(0)
+        tr = refload.make_trainer(cfg, 'MSERankingTrainer' if model_key == 'npa' else 'ContrastiveRankingTrainer')
+        tr.model.train()
+        sbatches = [_str_themes(b) for b in batches]
+
+        def step():
+            b = sbatches[counter[0] % 2]
+            counter[0] += 1
+            out = tr._train_step(b)
+            return float(out['loss'])
+        return step, 'reference'
+
+    from oracle import xnrs_oracle as O
+    from xnrs_b200.models import make_model
+    if model_key != 'cl':
+        raise RuntimeError('oracle port of the CPU step exists for the CL model only (oracle/_ref missing)')
+    torch.manual_seed(0)
+    P = {k: v.detach().clone().to(device).requires_grad_(True) for k, v in make_model(CL_CFG).state_dict().items()}
+    state = {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in P.items()}
 
     def step():
-        b = batches[counter[0] % len(batches)]
+        b = batches[counter[0] % 2]
         counter[0] += 1
         for v in P.values():
             v.grad = None
@@ -137,80 +250,336 @@ def oracle_step_fn(batch_size, threads):
                 if v.grad is not None:
                     O.adam_step(v, v.grad, state[k][0], state[k][1], counter[0], CL_CFG['lr'])
         return float(loss.detach())
-    return step
+    return step, 'port'
 
 
-def time_cpu(batch_size, steps, warmup, threads):
-    step = oracle_step_fn(batch_size, threads)
+def time_cpu_train(model_key, batch_size, steps, warmup, threads):
+    step, kind = cpu_train_step_fn(model_key, batch_size, threads)
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
-    return batch_size * steps / dt, dt / steps
+    return batch_size * steps / dt, dt / steps, kind
 
 
-def eval_cpu_baseline(cat, imp, model_sd, n_sample, threads):
-    """the reference evaluation procedure (training.py:194-243: ONE impression per step — full re-encode of the history
-    and every candidate, scores to the host, numpy metrics) restated by the oracle, on a bounded sample of the same
-    impressions -> (impressions/s, seconds)"""
-    from oracle import xnrs_oracle as O
+def cpu_baseline_train(model_key, batch_size, steps=3, warmup=1):
+    threads = os.cpu_count() or 1
+    try:
+        v, per, kind = time_cpu_train(model_key, batch_size, steps, warmup, threads)
+        return {'value': v, 'unit': UNIT, 'cores': threads, 'kind': kind,
+                'sample': f'{batch_size} impressions/step x {steps} steps after {warmup} warm-up, '
+                          + ('the unmodified reference trainer step (oracle/_ref, torch CPU fp32)' if kind == 'reference'
+                             else 'oracle port (torch CPU fp32, autograd + Adam)') + f', same shapes, {per:.2f} s/step'}
+    except Exception as exc:                                   # a baseline must never take the measurement down with it
+        return {'value': None, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': f'failed: {exc!r}'}
+
+
+def eager_gpu_baseline(dev, batch_size=256, steps=5):
+    """SURVEY §8(d) last row: the reference's own training step in STOCK PyTorch eager on the same B200 (reference modules
+    .to(cuda), dense reference-format batches resident in HBM, cuBLAS fp32 with TF32 off, and TF32 on for context)."""
+    out = {'batch': batch_size, 'unit': UNIT}
+    try:
+        old = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+        step, kind = cpu_train_step_fn('cl', batch_size, os.cpu_count() or 1, device=dev)
+        out['kind'] = ('unmodified reference modules + trainer step on cuda (oracle/_ref)' if kind == 'reference'
+                       else 'torch restatement of the reference step on cuda (oracle port)')
+        for tf32 in (False, True):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(steps):
+                step()
+            e.record()
+            torch.cuda.synchronize()
+            ms = s.elapsed_time(e) / steps
+            out['tf32' if tf32 else 'fp32'] = {'value': batch_size / (ms * 1e-3), 'ms_per_step': ms}
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    except Exception as exc:
+        out['failed'] = repr(exc)
+    torch.cuda.empty_cache()
+    return out
+
+
+def cpu_eval_fn(cat, imp, model_sd, threads):
+    """-> (run(i) for impression i, kind): the reference evaluation procedure (training.py:131-142,194-243: ONE impression
+    per step — full re-encode of the history and every candidate, scores to the host, numpy / sklearn metrics)."""
+    from oracle import refload
     from xnrs_b200 import synthetic as syn
     torch.set_num_threads(threads)
+
+    def raw_of(i):
+        a, b = int(imp['offsets'][i]), int(imp['offsets'][i + 1])
+        return {'hist_ids': imp['hist_ids'][i:i + 1], 'cand_ids': imp['cand_ids'][a:b][None, :],
+                'targets': imp['targets'][a:b][None, :, None], 'user_index': imp['user_index'][i:i + 1],
+                'main_theme': torch.zeros(1, dtype=torch.int32)}
+
+    if refload.available():
+        cfg = dict(CL_CFG, device='cpu', seq_len=SEQ_LEN, hist_len=HIST_LEN, batch_size=1)
+        tr = refload.make_trainer(cfg, 'MSERankingTrainer')
+        tr.model.load_state_dict({k: v.detach().cpu() for k, v in model_sd.items()})
+        tr.model.eval()
+
+        def run(i):
+            return tr._test_step(syn.dense_batch(cat, raw_of(i)))
+        return run, 'reference'
+
+    from oracle import xnrs_oracle as O
     P = {k: v.detach().cpu().clone() for k, v in model_sd.items()}
-    t0 = time.perf_counter()
-    with torch.no_grad():
-        for i in range(n_sample):
-            a, b = int(imp['offsets'][i]), int(imp['offsets'][i + 1])
-            raw = {'hist_ids': imp['hist_ids'][i:i + 1], 'cand_ids': imp['cand_ids'][a:b][None, :],
-                   'targets': imp['targets'][a:b][None, :, None], 'user_index': imp['user_index'][i:i + 1],
-                   'main_theme': torch.zeros(1, dtype=torch.int32)}
-            scores = torch.relu(O.parent_forward(P, syn.dense_batch(cat, raw))).reshape(-1)
-            O.impression_metrics(imp['targets'][a:b].numpy(), scores.numpy())
-    dt = time.perf_counter() - t0
-    return n_sample / dt, dt
+
+    def run(i):
+        a, b = int(imp['offsets'][i]), int(imp['offsets'][i + 1])
+        with torch.no_grad():
+            scores = torch.relu(O.parent_forward(P, syn.dense_batch(cat, raw_of(i)))).reshape(-1)
+        return O.impression_metrics(imp['targets'][a:b].numpy(), scores.numpy())
+    return run, 'port'
 
 
-def run_reference(args):
-    """--impl reference: the reference algorithm's CPU path (oracle port; the Python reference cannot travel to the
-    GPU box) with all host threads, same metric/config, each step a bounded sample of the workload."""
-    if int(os.environ.get('RANK', '0')) != 0:
-        return
+def cpu_baseline_eval(cat, imp, model_sd, n_sample):
     threads = os.cpu_count() or 1
-    bs = args.ref_batch
-    value, per_step = time_cpu(bs, args.steps, args.warmup, threads)
-    sample = f'{bs} impressions/step x {args.steps} steps (bounded sample of the {args.batch}/GPU workload)'
-    print(json.dumps({
-        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
-        'warmup': args.warmup, 'ms_per_step': per_step * 1e3, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': workload_name(args.batch), 'reference_sample': sample},
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
-        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-    }))
+    try:
+        run, kind = cpu_eval_fn(cat, imp, model_sd, threads)
+        run(0)
+        t0 = time.perf_counter()
+        for i in range(n_sample):
+            run(i)
+        dt = time.perf_counter() - t0
+        n_imp = imp['offsets'].numel() - 1
+        return {'value': n_sample / dt, 'unit': UNIT, 'cores': threads, 'kind': kind,
+                'sample': f'{n_sample} of the {n_imp} impressions, one per step with a full re-encode of history and candidates + '
+                          + ('numpy/sklearn metrics: the unmodified reference RankingTrainer._test_step (oracle/_ref)' if kind == 'reference'
+                             else 'numpy metrics like training.py:194-243 (oracle port)') + f', torch CPU fp32, {dt:.1f} s'}
+    except Exception as exc:
+        return {'value': None, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': f'failed: {exc!r}'}
 
 
-def run_eval(args):
-    """--workload eval: BASELINE.json configs[4] — MIND-large-shaped full-catalogue evaluation (160k news, 376,471
-    impressions, ~37 candidates each) with the CL/standard model: encode the catalogue once (sharded over ranks,
-    all-gathered), then per-impression user encoding + candidate scoring + AUC/MRR/nDCG (strong scaling)."""
-    import torch.distributed as dist
+# =====================================================================================================================
+# train workloads
+# =====================================================================================================================
+
+class HookLog:
+    """brackets every C-ABI entry point with CUDA events on its launching stream (kernels.set_event_hook)"""
+
+    class Rec:
+        __slots__ = ('name', 'args', 'start', 'end', 'kernel')
+
+        def __init__(self, name, args):
+            self.name, self.args, self.kernel = name, args, None
+            self.start, self.end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def __init__(self):
+        self.records = []
+
+    def __call__(self, name, args):
+        r = HookLog.Rec(name, args)
+        self.records.append(r)
+        return r
+
+
+def gemm_rooflines(records, steps, precision):
+    """dominant-kernel roofline from one hooked pass: GEMM launches are grouped by (layout, the two batch-independent
+    dimensions, activation, power-of-two bucket of the batch-dependent dimension, kernel the LIBRARY dispatched to)."""
+    pk, pk_kind = peaks()
+    agg, shapes, classes = {}, {}, {}
+    for r in records:
+        dt = r.start.elapsed_time(r.end)
+        d = agg.setdefault(r.name, [0.0, 0, 0.0])
+        d[0] += dt
+        d[1] += 1
+        if r.name == 'xnrs_gemm':
+            a = r.args
+            flop = 2.0 * a[2] * a[3] * a[4]
+            d[2] += flop
+            sh = shapes.setdefault(f'{"T" if a[0] else "N"}{"T" if a[1] else "N"} M={a[2]} N={a[3]} K={a[4]}', [0.0, 0, 0.0])
+            sh[0] += dt
+            sh[1] += 1
+            sh[2] += flop
+            big = a[4] if a[0] else a[2]                       # the batch-dependent dimension
+            key = ((a[0], a[1], a[3], a[4], a[8]) if not a[0] else (a[0], a[1], a[2], a[3], a[8])) + (max(int(big), 1).bit_length(), r.kernel)
+            c = classes.setdefault(key, [0.0, 0, 0.0, 0])
+            c[0] += dt
+            c[1] += 1
+            c[2] += flop
+            c[3] += big
+    if not classes:
+        return None, agg
+    (d_ta, d_tb, d_1, d_2, d_act, _, d_kernel), (d_ms, d_n, d_flop, d_rows) = max(classes.items(), key=lambda kv: kv[1][0])
+    rows = d_rows / max(d_n, 1)
+    if d_ta:
+        role, cls = f'TN M={d_1} N={d_2} K~{rows:.0f} (weight gradient: K = token / title rows)', f'TN_{d_1}x{d_2}'
+    else:
+        role, cls = f'NT M~{rows:.0f} N={d_1} K={d_2} (forward' + (', tanh epilogue)' if d_act == 2 else ')'), f'NT_{d_1}x{d_2}_act{d_act}'
+    tr = traffic_entry(cls)
+    gemm_ms, gemm_n, gemm_flop = agg.get('xnrs_gemm', [0.0, 0, 0.0])
+    kernel_ms_total = sum(v[0] for v in agg.values())
+    top = max(agg.items(), key=lambda kv: kv[1][0])
+    d_tflops = d_flop / (d_ms * 1e-3) / 1e12 if d_ms else None
+    roofline = {
+        'kernel': f'{d_kernel} {role}', 'bound': 'tensor', 'achieved': d_tflops, 'peak': pk['bf16_tflops_sustained'],
+        'unit': 'TFLOP/s', 'frac': d_tflops / pk['bf16_tflops_sustained'] if d_tflops else None,
+        # per-launch DRAM bytes of this kernel class from the tracked `ncu --set full` summary, scaled by the batch-dependent
+        # row count of THIS run (bytes per row x rows); null when the class has no capture
+        'traffic': (tr['dram_bytes_per_row'] * rows) if tr else None,
+        'traffic_source': (f"{os.path.relpath(TRAFFIC_FILE, ROOT)}:{cls} ({tr['dram_bytes_per_row']} B/row from {tr['source']}) x {rows:.0f} rows"
+                           if tr else 'no ncu capture of this kernel class'),
+        'algorithmic_bytes': (tr['algorithmic_bytes_per_row'] * rows) if tr and 'algorithmic_bytes_per_row' in tr else None,
+        'peak_source': f'{pk_kind} (MEASURED_PEAKS.json, sustained bf16 GEMM; kernel timed inside a long step). '
+                       + {'tf32x3': 'The kernel issues 3 TF32 MMAs per product (fp32-accurate 3xTF32): its own ceiling is 1/6 of this bf16 peak',
+                          'tf32': 'TF32 operands: ceiling 1/2 of this bf16 peak', 'bf16': 'bf16 operands',
+                          'fp32': 'exact-fp32 SIMT kernel (no tensor cores)'}[precision],
+        'launches_timed': d_n, 'avg_launch_ms': d_ms / max(d_n, 1),
+        'all_gemm_tflops': gemm_flop / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None,
+        'gemm_share_of_step_kernel_time': gemm_ms / kernel_ms_total if kernel_ms_total else None,
+        'top_entry_point_by_time': top[0],
+        'gemm_shapes_ms_per_step': {k: f'{v[0] / steps:.3f} ms, {v[2] / (v[0] * 1e-3) / 1e12:.1f} TF/s, {v[1] // steps}x'
+                                    for k, v in sorted(shapes.items(), key=lambda kv: -kv[1][0])[:8]},
+        'per_entry_point_ms_per_step': {k: round(v[0] / steps, 4) for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])},
+        'kernel_ms_per_step': kernel_ms_total / steps,
+    }
+    return roofline, agg
+
+
+def train_workload(ctx, args, model_key, want_cpu=True, want_eager=False):
+    from xnrs_b200 import kernels as K
+    from xnrs_b200 import _lib
+    from xnrs_b200 import synthetic as syn
+    from xnrs_b200.data import TitleStore
+    from xnrs_b200.distributed import DataParallelTrainer
+    from xnrs_b200.models import make_model
+    from xnrs_b200.models.components import encoder_options
+    from xnrs_b200.training import ContrastiveRankingTrainer, MSERankingTrainer
+
+    dev, world, rank = ctx.dev, ctx.world, ctx.rank
+    K.set_precision(args.precision)
+    B, steps = args.batch, args.steps
+    cfg = MODEL_CFGS[model_key]
+    cat = syn.make_catalogue(N_NEWS, SEQ_LEN, VOCAB, 768, seed=0, with_abstract=(model_key == 'naml'))
+    store = TitleStore(cat.token_table.to(dev), cat.title_tokens.to(dev))
+    astore = TitleStore(store.token_table, cat.abstract_tokens.to(dev)) if model_key == 'naml' else None
+    torch.manual_seed(0)
+    trainer_cls = MSERankingTrainer if model_key == 'npa' else ContrastiveRankingTrainer     # NPA has no CL hook
+    model = make_model(cfg)
+    encoder_options(model, dedup_titles=not args.no_dedup, skip_padding=not args.no_skip_padding)
+    trainer = trainer_cls(dict(cfg, device=str(dev)), model)
+    trainer.model.train()
+    dp = DataParallelTrainer(trainer)
+
+    n_batches = 8           # distinct batches cycled through; weak scaling: every rank draws its own B impressions
+    raws = [syn.make_train_batch(N_NEWS, B, HIST_LEN, seed=1000 + 97 * rank + i) for i in range(n_batches)]
+    pinned = [{k: v.pin_memory() for k, v in r.items()} for r in raws]
+    resident = [syn.index_batch(store, cat, r, dev, abstract_store=astore) for r in raws]
+    h2d_bytes = sum(v.numel() * v.element_size() for v in raws[0].values())
+
+    for i in range(args.warmup):
+        dp.train_step(resident[i % n_batches])
+
+    # ---- timed region 1: inputs resident in HBM --------------------------------------------------------------------
+    def region_resident():
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dp.prefetch(resident[0])
+        t0.record()
+        for i in range(steps):
+            dp.train_step(resident[i % n_batches])
+            if not args.no_prefetch:         # input pipeline: the next batch's id plumbing runs on a side stream meanwhile
+                dp.prefetch(resident[(i + 1) % n_batches])
+        t1.record()
+        torch.cuda.synchronize()
+        return t0.elapsed_time(t1)
+
+    # (a) one region with every C-ABI call bracketed by CUDA events on its launching stream: per-kernel durations
+    log = HookLog()
+    K.set_event_hook(log)
+    ms_hooked = ctx.timed_regions(region_resident, min_total_s=0.0)[0]
+    K.set_event_hook(None)
+    fb0 = int(_lib.lib().xnrs_gemm_simt_fallbacks())
+    # (b) without hooks: `value`
+    n0 = K.launch_count()
+    with ClockSampler(ctx.local) as clocks:
+        ms_list = ctx.timed_regions(region_resident)
+    launches = (K.launch_count() - n0) // len(ms_list)
+    fallbacks = (int(_lib.lib().xnrs_gemm_simt_fallbacks()) - fb0) // len(ms_list)
+    ms_med, sp = spread(ms_list, B * world * steps)
+    value = B * world * steps / (ms_med * 1e-3)
+    roofline, agg = gemm_rooflines(log.records, steps, args.precision)
+    if roofline is not None:
+        roofline['ms_per_step_with_event_hooks'] = ms_hooked / steps
+        roofline['simt_fallback_gemms_per_region'] = fallbacks
+    if os.environ.get('XNRS_BENCH_DUMP') and rank == 0:      # every launch of ONE step with its event time (diagnostics)
+        per = len(log.records) // steps
+        with open(os.environ['XNRS_BENCH_DUMP'] + '.' + model_key, 'w') as f:
+            for r in log.records[:per]:
+                f.write(json.dumps({'name': r.name, 'kernel': r.kernel, 'args': list(r.args), 'ms': round(r.start.elapsed_time(r.end), 4)}) + '\n')
+
+    # ---- timed region 2: end to end through the public trainer API with HOST (pinned) index buffers ---------------
+    def h2d(i):                              # host (pinned) int32 ids / targets / labels -> device, on the main stream
+        b = syn.index_batch(store, cat, pinned[i % n_batches], dev, abstract_store=astore)
+        return b, torch.cuda.current_stream().record_event()
+
+    last = [0.0]
+
+    def region_e2e():
+        cur = h2d(0)
+        t0 = time.perf_counter()
+        for i in range(steps):
+            nxt = h2d(i + 1)                 # tiny copy, queued BEFORE this step so the side stream can plan it meanwhile
+            out = dp.train_step(cur[0])
+            if not args.no_prefetch:
+                dp.prefetch(nxt[0], after=nxt[1])
+            last[0] = float(out['loss'])     # device -> host read of the step's loss (4 bytes, synchronises)
+            cur = nxt
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) * 1e3
+
+    region_e2e()
+    e_list = ctx.timed_regions(region_e2e)
+    e_med, e_sp = spread(e_list, B * world * steps)
+    e2e_value = B * world * steps / (e_med * 1e-3)
+
+    out = {
+        'metric': 'train impressions/s', 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': steps, 'warmup': args.warmup,
+        'ms_per_step': ms_med / steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': {'fp32': 'f32', 'tf32x3': 'f32 (3xTF32)', 'tf32': 'tf32', 'bf16': 'bf16'}[args.precision],
+        'data': 'synthetic',
+        'config': {'workload': workload_name(B, model_key), 'global_batch': B * world, 'parallelism': f'dp{world}',
+                   'l2': 'inputs larger than L2: 307 MB token table, ~0.5 GB of gathered rows per step, 8 batches cycled',
+                   'precision': args.precision, 'final_loss': last[0],
+                   'dedup_titles': not args.no_dedup, 'skip_padding': not args.no_skip_padding,
+                   'timing': f'median of {sp["regions"]} regions of exactly {steps} steps ({sp["timed_s"]} s measured)'},
+        'spread': sp,
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4,
+                'spread': e_sp, 'note': 'host input = int32 news ids / targets / labels (the index fast path of the drop-in API)'},
+        'gpu_launches': launches, 'roofline': roofline, 'clocks': clocks.summary(),
+    }
+    del dp, trainer, model, resident, store, astore
+    torch.cuda.empty_cache()
+    if world == 1 and want_eager and not args.no_cpu_baseline:
+        out['eager_gpu_baseline'] = eager_gpu_baseline(dev)
+    if world == 1 and want_cpu and not args.no_cpu_baseline:
+        out['cpu_baseline'] = cpu_baseline_train(model_key, args.ref_batch if model_key != 'nrms' else max(8, args.ref_batch // 4))
+    return out
+
+
+# =====================================================================================================================
+# eval workload (BASELINE.json configs[4])
+# =====================================================================================================================
+
+def eval_workload(ctx, args, want_cpu=True):
+    """MIND-large-shaped full-catalogue evaluation with the CL/standard model: encode the catalogue once (sharded over
+    ranks, all-gathered), then per-impression user encoding + candidate scoring + AUC/MRR/nDCG (strong scaling)."""
     from xnrs_b200 import kernels as K
     from xnrs_b200 import synthetic as syn
     from xnrs_b200.data import TitleStore
     from xnrs_b200.evaluation import CatalogueEvaluator
     from xnrs_b200.models import make_model
 
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
+    dev, world, rank = ctx.dev, ctx.world, ctx.rank
     K.set_precision(args.precision)
-    n_news, n_imp = 160_000, args.eval_impressions
+    n_news, n_imp, passes = EVAL_NEWS, args.eval_impressions, args.steps
     cat = syn.make_catalogue(n_news, SEQ_LEN, VOCAB, 768, seed=0)
     imp = syn.make_eval_impressions(n_news, n_imp, HIST_LEN, seed=1)
     store = TitleStore(cat.token_table.to(dev), cat.title_tokens.to(dev))
@@ -219,12 +588,8 @@ def run_eval(args):
     ev = CatalogueEvaluator(model, store, news_chunk=16384, impression_chunk=16384)
     imp_dev = {k: v.to(dev) for k, v in imp.items()}
     imp_pin = {k: v.pin_memory() for k, v in imp.items()}
-
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
+    phase = {'enc': 0.0, 'score': 0.0, 'n': 0}
+    result = [None]
 
     def one_pass(src):
         ev.news_vecs = None
@@ -232,98 +597,148 @@ def run_eval(args):
         t0.record()
         ev.encode_catalogue()
         t1.record()
-        out = ev.evaluate(src)
+        result[0] = ev.evaluate(src)
         t2.record()
-        return out, t0, t1, t2
+        return t0, t1, t2
+
+    def make_region(src, wall):
+        def region():
+            w0 = time.perf_counter()
+            evs = [one_pass(src) for _ in range(passes)]
+            torch.cuda.synchronize()
+            if wall:
+                return (time.perf_counter() - w0) * 1e3
+            for t0, t1, t2 in evs:
+                phase['enc'] += t0.elapsed_time(t1)
+                phase['score'] += t1.elapsed_time(t2)
+                phase['n'] += 1
+            return sum(t0.elapsed_time(t2) for t0, _, t2 in evs)
+        return region
 
     for _ in range(max(1, args.warmup // 3)):
         one_pass(imp_dev)
-    sync_all()
     n0 = K.launch_count()
-    passes = max(1, min(args.steps, 5))               # a step = one full pass (catalogue encode + every impression)
-    with ClockSampler(local) as clocks:
-        sync_all()
-        evs = [one_pass(imp_dev) for _ in range(passes)]
-        sync_all()
-    out = evs[-1][0]
-    launches = K.launch_count() - n0
-    tt = torch.tensor([sum(e[1].elapsed_time(e[3]) for e in evs) / passes, sum(e[1].elapsed_time(e[2]) for e in evs) / passes,
-                       sum(e[2].elapsed_time(e[3]) for e in evs) / passes], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    total_ms, enc_ms, score_ms = (float(x) for x in tt)
-    sync_all()
-    w0 = time.perf_counter()
-    for _ in range(passes):
-        out2, *_ = one_pass(imp_pin)                  # host CSR buffers -> H2D inside the timed region, means read back
-    sync_all()
-    e2e_s = (time.perf_counter() - w0) / passes
+    with ClockSampler(ctx.local) as clocks:
+        ms_list = ctx.timed_regions(make_region(imp_dev, False))
+    launches = (K.launch_count() - n0) // len(ms_list)
+    ms_med, sp = spread(ms_list, n_imp * passes)
+    e_list = ctx.timed_regions(make_region(imp_pin, True))   # host CSR buffers -> H2D of this rank's shard inside the region
+    e_med, e_sp = spread(e_list, n_imp * passes)
+    out_metrics = result[0]
+    shard = dict(ev.last_shard)
     # one more pass with every entry point bracketed by CUDA events on its stream: per-kernel durations
-    recs = []
-
-    def hook(name, args_):
-        s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        recs.append((name, s_, e_, args_))
-        return s_, e_
-
-    K.set_event_hook(hook)
+    log = HookLog()
+    K.set_event_hook(log)
+    ctx.sync_all()
     one_pass(imp_dev)
-    sync_all()
+    ctx.sync_all()
     K.set_event_hook(None)
-    per_entry, gemm_flop = {}, 0.0
-    for name, s_, e_, a_ in recs:
-        per_entry[name] = per_entry.get(name, 0.0) + s_.elapsed_time(e_)
-        if name == 'xnrs_gemm':
-            gemm_flop += 2.0 * a_[2] * a_[3] * a_[4]
+    per_entry, gemm_flop, gemm_kernels = {}, 0.0, {}
+    for r in log.records:
+        dt = r.start.elapsed_time(r.end)
+        per_entry[r.name] = per_entry.get(r.name, 0.0) + dt
+        if r.name == 'xnrs_gemm':
+            gemm_flop += 2.0 * r.args[2] * r.args[3] * r.args[4]
+            gemm_kernels[r.kernel] = gemm_kernels.get(r.kernel, 0.0) + dt
     pk, pk_kind = peaks()
-    n_cand = int(imp['offsets'][-1])
-    # algorithmic bytes of the score+rank kernel: one T-wide fp32 vector per candidate + the user vector + ids/targets
-    score_bytes = n_cand * (256 * 4 + 4 + 4 + 4) + n_imp * (256 * 4 + 8 + 6 * 8)
+    # algorithmic bytes of THIS RANK's score+rank launches: one T-wide fp32 vector per candidate + the user vector + ids/targets
+    score_bytes = shard['candidates'] * (256 * 4 + 4 + 4 + 4) + shard['impressions'] * (256 * 4 + 8 + 6 * 8)
+    score_ms = per_entry.get('xnrs_eval_impressions')
+    gemm_ms = per_entry.get('xnrs_gemm')
+    h2d_shard = (shard['impressions'] * (HIST_LEN * 4 + 8 + 4) + shard['candidates'] * 8)
     res = {
-        'metric': 'eval scored impressions/s', 'value': n_imp / (total_ms * 1e-3), 'unit': UNIT, 'n_gpus': world,
-        'steps': passes, 'warmup': max(1, args.warmup // 3), 'ms_per_step': total_ms, 'higher_is_better': True,
+        'metric': 'eval scored impressions/s', 'value': n_imp * passes / (ms_med * 1e-3), 'unit': UNIT, 'n_gpus': world,
+        'steps': passes, 'warmup': max(1, args.warmup // 3), 'ms_per_step': ms_med / passes, 'higher_is_better': True,
         'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32 (3xTF32)' if args.precision == 'tf32x3' else args.precision,
         'data': 'synthetic',
         'config': {'workload': f'MIND-large-shaped full-catalogue eval, model=standard (mind_standard.yml): {n_news} news '
                                f'encoded once, {n_imp} impressions x ~37 candidates, H={HIST_LEN}, S={SEQ_LEN}; one step = '
                                f'catalogue encode + all impressions', 'parallelism': f'news+impression sharding x{world}',
-                   'l2': 'news vectors 164 MB + 14M candidate gathers exceed L2', 'catalogue_encode_ms': enc_ms,
-                   'impression_phase_ms': score_ms, 'metrics': {k: out[k] for k in ('auc', 'rr', 'ndcg@5', 'ndcg@10')}},
-        'e2e': {'value': n_imp / e2e_s, 'unit': UNIT,
-                'h2d_bytes_per_step': sum(v.numel() * v.element_size() for v in imp.values()), 'd2h_bytes_per_step': 56},
-        'gpu_launches': launches,
-        # dominant kernel of the pass: the tcgen05 GEMMs of the catalogue encode (title fc1 + heads + per-article pooling
-        # logits), FLOPs = sum of 2MNK over the launches / their CUDA-event time
-        'roofline': {'kernel': 'tcgen05 GEMMs of the pass (gemm_tc2_kernel / gemm_tc_kernel: catalogue fc1 with tanh epilogue, heads, '
-                               'per-article pooling logits)', 'bound': 'tensor',
-                     'achieved': gemm_flop / (per_entry.get('xnrs_gemm', 0.0) * 1e-3) / 1e12 if per_entry.get('xnrs_gemm') else None,
+                   'l2': 'news vectors 164 MB + 14M candidate gathers exceed L2',
+                   'catalogue_encode_ms': phase['enc'] / max(phase['n'], 1), 'impression_phase_ms': phase['score'] / max(phase['n'], 1),
+                   'metrics': {k: out_metrics[k] for k in ('auc', 'rr', 'ndcg@5', 'ndcg@10')},
+                   'timing': f'median of {sp["regions"]} regions of exactly {passes} passes ({sp["timed_s"]} s measured)'},
+        'spread': sp,
+        'e2e': {'value': n_imp * passes / (e_med * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d_shard, 'd2h_bytes_per_step': 56,
+                'spread': e_sp, 'note': 'per rank: only its CSR shard crosses PCIe'},
+        'gpu_launches': launches // max(passes, 1),
+        # dominant kernel class of the pass: the tcgen05 GEMMs of the catalogue encode (title fc1 + heads + per-article pooling
+        # logits), FLOPs = sum of 2MNK over this rank's launches / their CUDA-event time
+        'roofline': {'kernel': 'GEMMs of the pass: ' + ', '.join(f'{k} {v:.2f} ms' for k, v in sorted(gemm_kernels.items(), key=lambda kv: -kv[1])),
+                     'bound': 'tensor', 'achieved': gemm_flop / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None,
                      'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
-                     'frac': (gemm_flop / (per_entry['xnrs_gemm'] * 1e-3) / 1e12 / pk['bf16_tflops_sustained']) if per_entry.get('xnrs_gemm') else None,
+                     'frac': (gemm_flop / (gemm_ms * 1e-3) / 1e12 / pk['bf16_tflops_sustained']) if gemm_ms else None,
                      'traffic': None,
-                     'peak_source': f'{pk_kind} (sustained bf16 GEMM). 3xTF32 (fp32-accurate) has 1/6 of this peak as its own ceiling',
+                     'peak_source': f'{pk_kind} (sustained bf16 GEMM). 3xTF32 (fp32-accurate) has 1/6 of this peak as its own ceiling; per rank',
                      'per_entry_point_ms': {k: round(v, 3) for k, v in sorted(per_entry.items(), key=lambda kv: -kv[1])}},
-        # the HBM-bound scoring kernel: algorithmic bytes (one T-wide vector per candidate + ids/targets) / its event time
-        'roofline_scoring': {'kernel': 'eval_impressions_kernel (gather + dot + segmented rank sort + metrics)', 'bound': 'hbm',
-                             'achieved': score_bytes / (per_entry.get('xnrs_eval_impressions', score_ms) * 1e-3) / 1e9,
+        # the HBM-bound scoring kernel, PER RANK: this rank's algorithmic bytes / this rank's event time
+        'roofline_scoring': {'kernel': 'eval_impressions_warp_kernel (gather + dot + segmented rank sort + metrics)', 'bound': 'hbm',
+                             'achieved': score_bytes / (score_ms * 1e-3) / 1e9 if score_ms else None,
                              'peak': pk['hbm_gbs'], 'unit': 'GB/s',
-                             'frac': score_bytes / (per_entry.get('xnrs_eval_impressions', score_ms) * 1e-3) / 1e9 / pk['hbm_gbs'],
-                             'peak_source': pk_kind},
+                             'frac': score_bytes / (score_ms * 1e-3) / 1e9 / pk['hbm_gbs'] if score_ms else None,
+                             'peak_source': f'{pk_kind}; rank 0 of {world}: {shard["impressions"]} impressions, {shard["candidates"]} candidates'},
         'clocks': clocks.summary(),
     }
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n_s = min(4000, n_imp)                                # ~6 s of host work on the box's 16 cores
-        threads = os.cpu_count() or 1
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    del ev, model, store, imp_dev, imp_pin
+    torch.cuda.empty_cache()
+    if rank == 0 and world == 1 and want_cpu and not args.no_cpu_baseline:
+        res['cpu_baseline'] = cpu_baseline_eval(cat, imp, sd, min(args.ref_eval_sample, n_imp))
+    return res
+
+
+# =====================================================================================================================
+# --impl reference
+# =====================================================================================================================
+
+def run_reference(args):
+    """the reference's own CPU implementation of the path on the box's host cores — the unmodified reference package when
+    oracle/_ref travelled with the repo (kind "reference"), else the oracle port — with all host threads, same metric /
+    config, each step a bounded sample of the workload.  Under torchrun rank 0 alone runs it."""
+    if int(os.environ.get('RANK', '0')) != 0:
+        return
+    threads = os.cpu_count() or 1
+
+    def train_line(model_key, bs, steps, warmup):
+        value, per_step, kind = time_cpu_train(model_key, bs, steps, warmup, threads)
+        sample = f'{bs} impressions/step x {steps} steps (bounded sample of the {args.batch}/GPU workload)'
+        return {
+            'impl': 'reference', 'metric': 'train impressions/s', 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps,
+            'warmup': warmup, 'ms_per_step': per_step * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': workload_name(args.batch, model_key), 'reference_sample': sample},
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': kind, 'sample': sample},
+            'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        }
+
+    def eval_line():
+        from xnrs_b200 import synthetic as syn
+        from xnrs_b200.models import make_model
+        n = min(args.ref_eval_sample, args.eval_impressions)
+        cat = syn.make_catalogue(EVAL_NEWS, SEQ_LEN, VOCAB, 768, seed=0)
+        imp = syn.make_eval_impressions(EVAL_NEWS, max(n, 1000), HIST_LEN, seed=1)
+        torch.manual_seed(0)
+        base = cpu_baseline_eval(cat, imp, make_model(CL_CFG).state_dict(), n)
+        return {'impl': 'reference', 'metric': 'eval scored impressions/s', 'value': base['value'], 'unit': UNIT, 'n_gpus': args.gpus,
+                'steps': 1, 'warmup': 0, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32',
+                'data': 'synthetic', 'config': {'workload': 'MIND-large-shaped full-catalogue eval, model=standard', 'reference_sample': base['sample']},
+                'cpu_baseline': base, 'e2e': {'value': base['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+
+    only = args.only
+    if only == 'eval':
+        line = eval_line()
+    elif only:
+        line = train_line(only, args.ref_batch, args.steps, args.warmup)
+    else:
+        line = train_line('cl', args.ref_batch, args.steps, args.warmup)
+        sub = {}
         try:
-            v, dt = eval_cpu_baseline(cat, imp, model.state_dict(), n_s, threads)
-            res['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-                                   'sample': f'{n_s} of the {n_imp} impressions, one per step with a full re-encode of history and candidates '
-                                             f'+ numpy metrics like training.py:194-243 (oracle, torch CPU fp32), {dt:.1f} s'}
-        except Exception as exc:                              # the baseline must never take the measurement down with it
-            res['cpu_baseline'] = {'value': None, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': f'failed: {exc!r}'}
-    if rank == 0:
-        print(json.dumps(res))
-    if world > 1:
-        dist.destroy_process_group()
+            sub['nrms_train'] = train_line('nrms', max(8, args.ref_batch // 4), 2, 1)
+        except Exception as exc:
+            sub['nrms_train'] = {'impl': 'reference', 'unavailable': repr(exc)}
+        sub['eval'] = eval_line()
+        line['sub'] = sub
+    print(json.dumps(line))
 
 
 def main():
@@ -334,218 +749,37 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=1024, help='impressions per GPU per step')
     ap.add_argument('--ref-batch', type=int, default=64, help='impressions per CPU step (reference arm / cpu_baseline)')
+    ap.add_argument('--ref-eval-sample', type=int, default=400, help='impressions of the eval workload timed on the CPU')
     ap.add_argument('--precision', default='tf32x3', choices=['fp32', 'tf32x3', 'tf32', 'bf16'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--workload', default='train', choices=['train', 'eval'])
-    ap.add_argument('--model', default='cl', choices=list(MODEL_CFGS), help='cl is the headline (BASELINE configs[1])')
+    ap.add_argument('--only', default=None, choices=list(MODEL_CFGS) + ['eval'],
+                    help='run ONE workload instead of the headline + sub lines')
+    ap.add_argument('--workload', default=None, choices=['train', 'eval'], help='(round-1 spelling) eval == --only eval')
+    ap.add_argument('--model', default=None, choices=list(MODEL_CFGS), help='(round-1 spelling) == --only MODEL')
     ap.add_argument('--no-skip-padding', action='store_true', help='run pad tokens through the encoder like the reference does')
     ap.add_argument('--no-prefetch', action='store_true', help='compute the id plumbing of each batch inside its own step')
     ap.add_argument('--no-dedup', action='store_true', help='encode every (impression, slot) title, not each distinct article once')
     ap.add_argument('--eval-impressions', type=int, default=376_471)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.workload == 'eval':
+        args.only = 'eval'
+    elif args.model:
+        args.only = args.model
     if args.impl == 'reference':
         return run_reference(args)
-    if args.workload == 'eval':
-        return run_eval(args)
 
-    import torch.distributed as dist
-    from xnrs_b200 import kernels as K
-    from xnrs_b200 import synthetic as syn
-    from xnrs_b200.data import TitleStore
-    from xnrs_b200.distributed import DataParallelTrainer
-    from xnrs_b200.models import make_model
-    from xnrs_b200.training import ContrastiveRankingTrainer
-
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
-    if world != args.gpus and rank == 0:
-        print(f'warning: --gpus {args.gpus} but WORLD_SIZE {world}', file=sys.stderr)
-    K.set_precision(args.precision)
-    B = args.batch
-    from xnrs_b200.models.components import TextEncoder
-    TextEncoder.dedup_titles = not args.no_dedup
-    TextEncoder.skip_padding = not args.no_skip_padding
-
-    cfg = MODEL_CFGS[args.model]
-    cat = syn.make_catalogue(N_NEWS, SEQ_LEN, VOCAB, 768, seed=0, with_abstract=(args.model == 'naml'))
-    store = TitleStore(cat.token_table.to(dev), cat.title_tokens.to(dev))
-    astore = TitleStore(store.token_table, cat.abstract_tokens.to(dev)) if args.model == 'naml' else None
-    torch.manual_seed(0)
-    from xnrs_b200.training import MSERankingTrainer
-    trainer_cls = MSERankingTrainer if args.model == 'npa' else ContrastiveRankingTrainer     # NPA has no CL hook
-    trainer = trainer_cls(dict(cfg, device=str(dev)), make_model(cfg))
-    trainer.model.train()
-    dp = DataParallelTrainer(trainer)
-
-    n_batches = 8           # distinct batches cycled through; weak scaling: every rank draws its own B impressions
-    raws = [syn.make_train_batch(N_NEWS, B, HIST_LEN, seed=1000 + 97 * rank + i) for i in range(n_batches)]
-    pinned = [{k: v.pin_memory() for k, v in r.items()} for r in raws]
-    resident = [syn.index_batch(store, cat, r, dev, abstract_store=astore) for r in raws]
-    h2d_bytes = sum(v.numel() * v.element_size() for v in raws[0].values())
-
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    for i in range(args.warmup):
-        dp.train_step(resident[i % n_batches])
-
-    # ---- timed region 1: inputs resident in HBM.  Run twice over the same K steps: (a) every kernel call bracketed by
-    # CUDA events on its launching stream (per-kernel durations for the roofline), (b) without the event hooks (`value`)
-    records = []
-
-    def hook(name, args_):
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        records.append((name, args_, s, e))
-        return s, e
-
-    def timed_resident():
-        sync_all()
-        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        dp.prefetch(resident[0])
-        t0.record()
-        for i in range(args.steps):
-            dp.train_step(resident[i % n_batches])
-            if not args.no_prefetch:         # input pipeline: the next batch's id plumbing runs on a side stream meanwhile
-                dp.prefetch(resident[(i + 1) % n_batches])
-        t1.record()
-        sync_all()
-        ms = torch.tensor([t0.elapsed_time(t1)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms)
-
-    K.set_event_hook(hook)
-    ms_hooked = timed_resident()
-    K.set_event_hook(None)
-    n0 = K.launch_count()
-    with ClockSampler(local) as clocks:
-        ms_total = timed_resident()
-    launches = K.launch_count() - n0
-    value = B * world * args.steps / (ms_total * 1e-3)
-
-    # dominant kernel: aggregate event time per entry point; GEMM FLOPs are 2*M*N*K per launch
-    agg, shapes = {}, {}
-    for name, a, s, e in records:
-        d = agg.setdefault(name, [0.0, 0, 0.0])
-        dt = s.elapsed_time(e)
-        d[0] += dt
-        d[1] += 1
-        if name == 'xnrs_gemm':
-            d[2] += 2.0 * a[2] * a[3] * a[4]
-            sh = shapes.setdefault(f'{"T" if a[0] else "N"}{"T" if a[1] else "N"} M={a[2]} N={a[3]} K={a[4]}', [0.0, 0, 0.0])
-            sh[0] += dt
-            sh[1] += 1
-            sh[2] += 2.0 * a[2] * a[3] * a[4]
-    top = max(agg.items(), key=lambda kv: kv[1][0])
-    if os.environ.get('XNRS_BENCH_DUMP') and rank == 0:      # every launch of ONE step with its event time (diagnostics)
-        per = len(records) // args.steps
-        with open(os.environ['XNRS_BENCH_DUMP'], 'w') as f:
-            for name, a, s_, e_ in records[:per]:
-                f.write(json.dumps({'name': name, 'args': list(a), 'ms': round(s_.elapsed_time(e_), 4)}) + '\n')
-    pk, pk_kind = peaks()
-    gemm_ms, gemm_n, gemm_flop = agg.get('xnrs_gemm', [0.0, 0, 0.0])
-    kernel_ms_total = sum(v[0] for v in agg.values())
-    # dominant kernel = the GEMM launch class (layout, N, K; M varies with the batch's distinct-token count) with the most time
-    classes = {}
-    for name, a, s_, e_ in records:
-        if name == 'xnrs_gemm':
-            big = a[4] if a[0] else a[2]          # the batch-dependent dimension; its power-of-two bucket keeps e.g. the
-            bucket = max(int(big), 1).bit_length()   # token-level fc1 GEMMs apart from the title-level head GEMMs of equal N, K
-            key = ((a[0], a[1], a[3], a[4], a[8]) if not a[0] else (a[0], a[1], a[2], a[3], a[8])) + (bucket,)
-            c = classes.setdefault(key, [0.0, 0, 0.0, 0])
-            c[0] += s_.elapsed_time(e_)
-            c[1] += 1
-            c[2] += 2.0 * a[2] * a[3] * a[4]
-            c[3] += a[4] if a[0] else a[2]
-    (d_ta, d_tb, d_1, d_2, d_act, _), (d_ms, d_n, d_flop, d_rows) = max(classes.items(), key=lambda kv: kv[1][0])
-    d_m, d_n_ = (d_1, d_2) if d_ta else (d_rows // max(d_n, 1), d_1)
-    kern = ('gemm_tc2_kernel (cta_group::2 CTA pair, 256x256 tile)' if (args.precision == 'tf32x3' and d_n_ > 128 and d_m >= 256)
-            else ('gemm_tc_kernel<256>' if args.precision in ('tf32', 'bf16') and d_n_ > 128 else 'gemm_tc_kernel<128>'))
-    d_name = (f'{kern} {"TN" if d_ta else "NT"} '
-              + (f'M={d_1} N={d_2} K~{d_rows // max(d_n, 1)} (fc1 weight gradient)' if d_ta
-                 else f'M~{d_rows // max(d_n, 1)} N={d_1} K={d_2} ' + ('(title fc1 forward, tanh epilogue)' if d_act == 2 else '(forward)')))
-    d_tflops = d_flop / (d_ms * 1e-3) / 1e12 if d_ms else None
-    roofline = {
-        'kernel': d_name if args.precision != 'fp32' else 'gemm_simt_kernel ' + d_name,
-        'bound': 'tensor', 'achieved': d_tflops, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
-        'frac': d_tflops / pk['bf16_tflops_sustained'] if d_tflops else None,
-        # dram__bytes_read.sum + dram__bytes_write.sum of ONE such launch (ncu --set full, profiles/README.md): 473.2 MB read
-        # + 131.4 MB written at M=153 562 rows = 3937 B/row, i.e. the algorithmic A row (3072 B) + C row (1024 B): no re-reads
-        # the fc1 weight gradient (TN, M=256, N=768): 651.4 MB read + 8.4 MB written at K=153 562 = 4296 B per k-row = one
-        # d_hid row (1024 B) + one x row (3072 B) + the split-K partial tiles
-        'traffic': (3937.0 * (d_rows / max(d_n, 1)) if (not d_ta and args.precision != 'fp32' and d_2 == 768 and d_1 == 256)
-                    else (4296.0 * (d_rows / max(d_n, 1)) if (d_ta and args.precision != 'fp32' and d_1 == 256 and d_2 == 768) else None)),
-        'peak_source': f'{pk_kind} (sustained bf16 GEMM; kernel timed inside a long step). The kernel computes in TF32 '
-                       f'(3 MMAs per product in the fp32-accurate 3xTF32 mode): its own ceiling is 1/6 of this bf16 peak',
-        'launches_timed': d_n, 'avg_launch_ms': d_ms / max(d_n, 1),
-        'all_gemm_tflops': gemm_flop / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None,
-        'gemm_share_of_step_kernel_time': gemm_ms / kernel_ms_total if kernel_ms_total else None,
-        'top_entry_point_by_time': top[0], 'ms_per_step_with_event_hooks': ms_hooked / args.steps,
-        'gemm_shapes_ms_per_step': {k: f'{v[0] / args.steps:.3f} ms, {v[2] / (v[0] * 1e-3) / 1e12:.1f} TF/s, {v[1] // args.steps}x'
-                                    for k, v in sorted(shapes.items(), key=lambda kv: -kv[1][0])[:8]},
-        'per_entry_point_ms_per_step': {k: round(v[0] / args.steps, 4) for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])},
-    }
-
-    # ---- timed region 2: end to end through the public trainer API with HOST (pinned) index buffers ----
-    def h2d(i):                              # host (pinned) int32 ids / targets / labels -> device, on the main stream
-        b = syn.index_batch(store, cat, pinned[i % n_batches], dev, abstract_store=astore)
-        return b, torch.cuda.current_stream().record_event()
-
-    def e2e_step(cur, i):
-        nxt = h2d(i + 1)                     # tiny copy, queued BEFORE this step so the side stream can plan it meanwhile
-        out = dp.train_step(cur[0])
-        if not args.no_prefetch:
-            dp.prefetch(nxt[0], after=nxt[1])
-        return float(out['loss']), nxt       # device -> host read of the step's loss (4 bytes, synchronises)
-
-    _, cur = e2e_step(h2d(0), 0)
-    sync_all()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    wall0 = time.perf_counter()
-    e0.record()
-    last = 0.0
-    for i in range(args.steps):
-        last, cur = e2e_step(cur, i + 1)
-    e1.record()
-    sync_all()
-    wall = time.perf_counter() - wall0
-    ems = torch.tensor([max(e0.elapsed_time(e1), wall * 1e3)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ems, op=dist.ReduceOp.MAX)
-    e2e_value = B * world * args.steps / (float(ems) * 1e-3)
-
-    out = {
-        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': {'fp32': 'f32', 'tf32x3': 'f32 (3xTF32)', 'tf32': 'tf32', 'bf16': 'bf16'}[args.precision],
-        'data': 'synthetic',
-        'config': {'workload': workload_name(B, args.model), 'global_batch': B * world, 'parallelism': f'dp{world}',
-                   'l2': 'inputs larger than L2: 307 MB token table, ~5 GB of gathered rows per step, 8 batches cycled',
-                   'precision': args.precision, 'final_loss': last,
-                   'dedup_titles': not args.no_dedup, 'skip_padding': not args.no_skip_padding},
-        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4,
-                'note': 'host input = int32 news ids / targets / labels (the index fast path of the drop-in API)'},
-        'gpu_launches': launches, 'roofline': roofline, 'clocks': clocks.summary(),
-    }
-    if world == 1 and not args.no_cpu_baseline and args.model == 'cl':
-        threads = os.cpu_count() or 1
-        v, per = time_cpu(args.ref_batch, 3, 1, threads)
-        out['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-                               'sample': f'{args.ref_batch} impressions/step x 3 steps after 1 warm-up, oracle '
-                                         f'(torch CPU fp32, autograd + Adam), same shapes'}
-    if rank == 0:
-        print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    ctx = Ctx(args.gpus)
+    if args.only == 'eval':
+        line = eval_workload(ctx, args)
+    elif args.only:
+        line = train_workload(ctx, args, args.only, want_eager=(args.only == 'cl'))
+    else:
+        line = train_workload(ctx, args, 'cl', want_eager=True)
+        line['sub'] = {'nrms_train': train_workload(ctx, args, 'nrms'), 'eval': eval_workload(ctx, args)}
+    if ctx.rank == 0:
+        print(json.dumps(line))
+    ctx.close()
 
 
 if __name__ == '__main__':

@@ -98,3 +98,60 @@ def test_shard_range_is_a_partition():
             assert cuts[0][0] == 0 and cuts[-1][1] == n
             assert all(cuts[i][1] == cuts[i + 1][0] for i in range(w - 1))
             assert max(b - a for a, b in cuts) - min(b - a for a, b in cuts) <= 1
+
+
+def _eval_setup(name='cl'):
+    import _kernel_emulator as EMU
+    from xnrs_b200 import kernels as K
+    from xnrs_b200 import synthetic as syn
+    from xnrs_b200.data import TitleStore
+    from xnrs_b200.evaluation import CatalogueEvaluator
+    from xnrs_b200.models import make_model
+    K.call = EMU.call
+    fx = load_npz('model_' + name)
+    cfg = dict(fixture_cfg(fx), device='cpu')
+    model = make_model(cfg)
+    model.load_state_dict({k: torch.tensor(v) for k, v in sub(fx, 'sd').items()})
+    model.eval()
+    cat = syn.make_catalogue(61, cfg['seq_len'], vocab=200, dim=cfg['d_backbone'], seed=5)      # 62 rows: odd shard sizes
+    imp = syn.make_eval_impressions(61, 37, cfg['hist_len'], n_users=cfg['n_users'], seed=6)
+    store = TitleStore(cat.token_table, cat.title_tokens)
+    ev = CatalogueEvaluator(model, store, cat.category, cat.subcategory, None, news_chunk=9, impression_chunk=5)
+    ev.binary_metrics = True
+    return ev, imp
+
+
+def _eval_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    ev, imp = _eval_setup()
+    out = ev.evaluate(imp, return_per_impression=True)
+    np.savez(os.path.join(out_dir, f'e{rank}.npz'), vecs=ev.news_vecs.numpy(), shard=np.array([ev.last_shard['impressions'], ev.last_shard['candidates']]),
+             means=np.array([out[k] for k in ('auc', 'rr', 'ndcg@5', 'ndcg@10', 'ctr@1', 'ctr@10', 'acc', 'rec', 'prec')]),
+             n=out['impressions'], conf=np.array(out['conf']), per=out['per_impression'].numpy(), scores=out['scores'].numpy())
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_evaluation_equals_single_process(tmp_path):
+    """§8(e) row 2: catalogue rows sharded + all-gathered, impressions sharded by candidate count, metric sums all-reduced
+    — every rank reports the single-process epoch means; the shards partition the impressions; news vectors identical."""
+    world = 2
+    mp.spawn(_eval_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    ev, imp = _eval_setup()
+    want = ev.evaluate(imp, return_per_impression=True)
+    r0, r1 = (np.load(tmp_path / f'e{r}.npz') for r in range(world))
+    # sharded encode + all-gather == one pass (chunk boundaries differ, so GEMM blocking may: fp32 summation-order noise only)
+    np.testing.assert_allclose(r0['vecs'], ev.news_vecs.numpy(), rtol=0, atol=1e-6 * np.abs(r0['vecs']).max())
+    np.testing.assert_array_equal(r0['vecs'], r1['vecs'])                        # every rank holds the same gathered table
+    assert int(r0['shard'][0] + r1['shard'][0]) == 37                            # the shards partition the impressions ...
+    assert int(r0['shard'][1] + r1['shard'][1]) == int(imp['offsets'][-1])       # ... and the candidates,
+    assert abs(int(r0['shard'][1]) - int(r1['shard'][1])) <= 80                  # balanced by candidate count
+    np.testing.assert_allclose(np.concatenate([r0['scores'], r1['scores']]), want['scores'].numpy(), rtol=0,
+                               atol=1e-5 * np.abs(want['scores'].numpy()).max())
+    np.testing.assert_allclose(np.concatenate([r0['per'], r1['per']]), want['per_impression'].numpy(), rtol=0, atol=1e-9)
+    want_means = np.array([want[k] for k in ('auc', 'rr', 'ndcg@5', 'ndcg@10', 'ctr@1', 'ctr@10', 'acc', 'rec', 'prec')])
+    for r in (r0, r1):
+        np.testing.assert_allclose(r['means'], want_means, rtol=0, atol=1e-12)   # sums of the same doubles, two partial sums
+        assert int(r['n']) == want['impressions']
+        np.testing.assert_array_equal(r['conf'], np.array(want['conf']))

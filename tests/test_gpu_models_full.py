@@ -102,7 +102,7 @@ def test_index_path_matches_oracle(name, S, H, prec, monkeypatch):
 @pytest.mark.parametrize('name', ['cl', 'nrms', 'naml'])
 def test_title_dedup_gives_the_same_loss_and_gradients(name, monkeypatch):
     """encoding each distinct article of the batch once (default) == encoding every (impression, slot) title"""
-    from xnrs_b200.models.components import TextEncoder
+    from xnrs_b200.models.components import encoder_options
     cfg = dict(BASE, **MODELS[name], seq_len=30, hist_len=50, st_hist_len=50)
     cat = syn.make_catalogue(60, 30, VOCAB, 768, seed=3, with_abstract=(name == 'naml'))     # tiny catalogue: many repeats
     raw = syn.make_train_batch(60, 6, 50, n_users=N_USERS, seed=4)
@@ -110,9 +110,9 @@ def test_title_dedup_gives_the_same_loss_and_gradients(name, monkeypatch):
     astore = TitleStore(store.token_table, cat.abstract_tokens.to(DEV)) if name == 'naml' else None
     results = []
     for dedup in (True, False):
-        monkeypatch.setattr(TextEncoder, 'dedup_titles', dedup)
         torch.manual_seed(1)
         model = make_model(cfg)
+        encoder_options(model, dedup_titles=dedup)
         trainer = ContrastiveRankingTrainer(cfg, model)
         model.eval()
         trainer.optimizer.zero_grad()
@@ -138,9 +138,10 @@ def test_item_logit_pooling_gives_the_same_loss_and_gradients(monkeypatch):
     store = TitleStore(cat.token_table.to(DEV), cat.title_tokens.to(DEV))
     results = []
     for on in (True, False):
-        monkeypatch.setattr(ParentRec, 'item_logits', on)
         torch.manual_seed(1)
         model = make_model(cfg)
+        assert isinstance(model, ParentRec)
+        model.item_logits = on
         with torch.no_grad():
             for p in model.parameters():
                 if p.dim() > 1:
@@ -168,9 +169,10 @@ def test_naml_article_level_encoding_gives_the_same_loss_and_gradients(monkeypat
     astore = TitleStore(store.token_table, cat.abstract_tokens.to(DEV))
     results = []
     for on in (True, False):
-        monkeypatch.setattr(NAML, 'article_level', on)
         torch.manual_seed(1)
         model = make_model(cfg)
+        assert isinstance(model, NAML)
+        model.article_level = on
         with torch.no_grad():
             for p in model.parameters():
                 if p.dim() > 1:
@@ -185,3 +187,70 @@ def test_naml_article_level_encoding_gives_the_same_loss_and_gradients(monkeypat
     assert_close(l0, l1, 1e-6, 'loss')
     assert_close(p0, p1, 1e-5, 'predictions', atol=1e-6)
     assert_close(g0, g1, 2e-5, 'flat gradient')
+
+
+def _chunked_oracle_step(P, cat, raw, temperature, lam, chunk=64):
+    """loss and parameter gradients of the CL train step on the FULL batch with bounded host memory: the MSE term is a
+    sum over impressions; the InfoNCE term couples users, so pass 1 collects every user embedding (no grad) and
+    differentiates the loss w.r.t. them, pass 2 re-runs each chunk with grad and back-propagates
+    rec_chunk + <u_chunk, lam * dCL/du_chunk>.  Exact (same sums as one big autograd graph, chunk order aside)."""
+    B = raw['hist_ids'].shape[0]
+    N = raw['cand_ids'].shape[1]
+    sl = lambda a, b: {k: v[a:b] for k, v in raw.items()}
+    us = []
+    with torch.no_grad():
+        for a in range(0, B, chunk):
+            _, u, _ = O.parent_forward(P, syn.dense_batch(cat, sl(a, a + chunk)), return_embeddings=True)
+            us.append(u.squeeze(1))
+    u_all = torch.cat(us).requires_grad_(True)
+    l_cl = O.contrastive_loss(u_all, raw['main_theme'].long(), temperature)
+    (d_u,) = torch.autograd.grad(l_cl, u_all)
+    l_rec = 0.0
+    for a in range(0, B, chunk):
+        d = syn.dense_batch(cat, sl(a, a + chunk))
+        s, u, _ = O.parent_forward(P, d, return_embeddings=True)
+        rec = ((torch.relu(s) - d['targets']) ** 2).sum() / (B * N)
+        (rec + lam * (u.squeeze(1) * d_u[a:a + chunk]).sum()).backward()
+        l_rec += float(rec.detach())
+    return l_rec + lam * float(l_cl.detach()), l_rec, float(l_cl.detach())
+
+
+def test_bench_config_step_matches_oracle(monkeypatch):
+    """ONE step of bench.py's headline configuration — B=1024 impressions, S=30, H=50, 65 238-news catalogue, 100k-row token
+    table, 3xTF32, title de-duplication + padding-free pooling + prefetched id plumbing + item-logit user pooling — checked
+    against the CPU oracle on the same ids: total / rec / CL loss and EVERY parameter gradient of the flat buffer."""
+    import bench
+    from xnrs_b200 import kernels as K
+    monkeypatch.setattr(K, '_precision', K.PRECISIONS['tf32x3'])
+    B = 1024
+    cfg = dict(bench.CL_CFG, device=DEV)
+    cat = syn.make_catalogue(bench.N_NEWS, bench.SEQ_LEN, bench.VOCAB, 768, seed=0)
+    raw = syn.make_train_batch(bench.N_NEWS, B, bench.HIST_LEN, seed=1000)
+    store = TitleStore(cat.token_table.to(DEV), cat.title_tokens.to(DEV))
+    torch.manual_seed(0)
+    model = make_model(cfg)
+    P = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    trainer = ContrastiveRankingTrainer(cfg, model)
+    model.train()
+    batch = syn.index_batch(store, cat, raw, DEV)
+    assert trainer.prefetch(batch)                      # the bench loop plans the ids of a batch ahead of its step
+    trainer.optimizer.zero_grad()
+    total, l_rec, l_cl, _ = trainer.losses(batch)
+    total.backward()
+    torch.cuda.synchronize()
+    assert int(_lib_fallbacks()) >= 0
+    want_total, want_rec, want_cl = _chunked_oracle_step(P, cat, raw, cfg['contrastive_temperature'], cfg['contrastive_lambda'])
+    assert_close(l_rec, torch.tensor(want_rec), 1e-4, 'rec loss')
+    assert_close(l_cl, torch.tensor(want_cl), 1e-4, 'cl loss')
+    assert_close(total, torch.tensor(want_total), 1e-4, 'total loss')
+    named = dict(model.named_parameters())
+    gscale = max(float(v.grad.abs().max()) for v in P.values() if v.grad is not None)
+    for k, v in P.items():
+        if v.grad is None:
+            continue
+        assert_close(named[k].grad, v.grad, 2e-4, 'grad ' + k, atol=2e-6 * gscale)
+
+
+def _lib_fallbacks():
+    from xnrs_b200 import _lib
+    return _lib.lib().xnrs_gemm_simt_fallbacks()

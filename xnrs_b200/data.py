@@ -114,6 +114,7 @@ class IndexedTitles:
     store: TitleStore
     news_ids: torch.Tensor
     plan: 'TitlePlan | None' = None          # optional pre-computed plumbing for these ids (see TitlePlan)
+    distinct: bool = False                   # caller's promise that no id repeats (catalogue slices): nothing to de-duplicate
 
     def to(self, device):
-        return IndexedTitles(self.store, self.news_ids.to(device, non_blocking=True))
+        return IndexedTitles(self.store, self.news_ids.to(device, non_blocking=True), None, self.distinct)

@@ -68,9 +68,9 @@ class CatalogueEvaluator:
         """ids (n,) -> (vectors (n,T), collapsed mask (n,)) through the model's own news encoder"""
         m = self.model
         idx = ids.view(-1, 1)
-        title = IndexedTitles(self.store, idx)
+        title = IndexedTitles(self.store, idx, None, True)        # catalogue slices: distinct ids, nothing to de-duplicate
         if isinstance(m, NAML):
-            e, mask = m._news(title, IndexedTitles(self.abstract_store, idx), self.category[ids.long()].view(-1, 1),
+            e, mask = m._news(title, IndexedTitles(self.abstract_store, idx, None, True), self.category[ids.long()].view(-1, 1),
                               self.subcategory[ids.long()].view(-1, 1))
         elif isinstance(m, LSTUR):
             sub = self.subcategory[ids.long()].view(-1, 1) if 'subcategory_index' in m.cfg.catg_features else None
@@ -87,16 +87,11 @@ class CatalogueEvaluator:
         per = (n + w - 1) // w
         lo, hi = min(r * per, n), min((r + 1) * per, n)
         vecs, masks = [], []
-        from .models.components import TextEncoder
-        dedup, TextEncoder.dedup_titles = TextEncoder.dedup_titles, False      # catalogue ids are distinct: nothing to de-duplicate
-        try:
-            for a in range(lo, hi, self.news_chunk):
-                ids = torch.arange(a, min(hi, a + self.news_chunk), device=self.device, dtype=torch.int32)
-                e, mk = self._encode_ids(ids)
-                vecs.append(e)
-                masks.append(mk)
-        finally:
-            TextEncoder.dedup_titles = dedup
+        for a in range(lo, hi, self.news_chunk):
+            ids = torch.arange(a, min(hi, a + self.news_chunk), device=self.device, dtype=torch.int32)
+            e, mk = self._encode_ids(ids)
+            vecs.append(e)
+            masks.append(mk)
         T = vecs[0].shape[1] if vecs else self._encode_ids(torch.zeros(1, device=self.device, dtype=torch.int32))[0].shape[1]
         local = torch.zeros((per, T), device=self.device, dtype=torch.float32)
         lmask = torch.zeros(per, device=self.device, dtype=torch.float32)
@@ -160,19 +155,24 @@ class CatalogueEvaluator:
         if self.news_vecs is None:
             self.encode_catalogue()
         dev = self.device
-        offsets = impressions['offsets'].to(dev)
-        n_imp = offsets.numel() - 1
         w, r = world(), rank()
-        lo, hi = balanced_impression_shards(offsets, w)[r] if w > 1 else (0, n_imp)
-        hist_ids = impressions['hist_ids'].to(dev)
-        cand_ids = impressions['cand_ids'].to(dev)
-        targets = impressions['targets'].to(dev)
+        off_in = impressions['offsets']
+        n_imp = off_in.numel() - 1
+        lo, hi = balanced_impression_shards(off_in, w)[r] if w > 1 else (0, n_imp)
+        # this rank's contiguous CSR shard only: sliced where the buffers live (host buffers: only the shard crosses PCIe)
+        c_lo, c_hi = int(off_in[lo]), int(off_in[hi])
+        off_host = (off_in[lo:hi + 1] - c_lo) if not off_in.is_cuda else (off_in[lo:hi + 1] - c_lo).cpu()   # chunk bounds: no per-chunk sync
+        offsets = (off_in[lo:hi + 1] - c_lo).to(dev, non_blocking=True)
+        hist_ids = impressions['hist_ids'][lo:hi].to(dev, non_blocking=True)
+        cand_ids = impressions['cand_ids'][c_lo:c_hi].to(dev, non_blocking=True)
+        targets = impressions['targets'][c_lo:c_hi].to(dev, non_blocking=True)
         uidx = impressions.get('user_index')
-        uidx = None if uidx is None else uidx.to(dev)
+        uidx = None if uidx is None else uidx[lo:hi].to(dev, non_blocking=True)
+        self.last_shard = {'impressions': hi - lo, 'candidates': c_hi - c_lo}
+        lo, hi = 0, hi - lo                                       # everything below is in shard-local coordinates
         sums = torch.zeros(7, device=dev, dtype=torch.float64)
         bsums = torch.zeros(7, device=dev, dtype=torch.float64)
         per_imp, all_scores = [], []
-        off_host = impressions['offsets'] if not impressions['offsets'].is_cuda else offsets.cpu()   # chunk bounds: no per-chunk sync
         for a in range(lo, hi, self.impression_chunk):
             b = min(hi, a + self.impression_chunk)
             u = self._users(hist_ids[a:b].contiguous(), None if uidx is None else uidx[a:b].contiguous())

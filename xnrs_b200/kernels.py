@@ -82,8 +82,9 @@ _get_device = getattr(torch._C, '_cuda_getDevice', None)
 
 
 def set_event_hook(hook) -> None:
-    """bench.py timing: ``hook(name, scalar_args) -> (start_event, end_event)`` brackets each entry point with CUDA
-    events recorded on the stream the kernel is launched on (torch's current stream)."""
+    """bench.py timing: ``hook(name, scalar_args) -> record`` with ``.start`` / ``.end`` CUDA events (recorded here on the
+    stream the kernel is launched on, torch's current stream) and a ``.kernel`` slot that receives the name of the GEMM
+    kernel the library dispatched to."""
     global _event_hook
     _event_hook = hook
 
@@ -102,10 +103,12 @@ def call(name: str, *args) -> None:
     if fn is None:
         fn = _fns[name] = getattr(_lib.lib(), name)
     if _event_hook is not None:
-        ev = _event_hook(name, tuple(a for a in args if isinstance(a, (int, float))))
-        ev[0].record()
+        rec = _event_hook(name, tuple(a for a in args if isinstance(a, (int, float))))
+        rec.start.record()
         rc = fn(*[_arg(a) for a in args], torch.cuda.current_stream().cuda_stream)
-        ev[1].record()
+        rec.end.record()
+        if name == 'xnrs_gemm':              # which kernel the library dispatched this GEMM to (its claim, not a guess)
+            rec.kernel = _lib.lib().xnrs_last_gemm_kernel().decode()
     else:
         rc = fn(*[_arg(a) for a in args], _current_stream_handle())
     if rc != 0:

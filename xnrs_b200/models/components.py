@@ -161,13 +161,12 @@ class TextEncoder(nn.Module):
     they cannot influence anything: only real tokens are gathered and the pooler works on ragged groups.  (With
     self-attention padded tokens ARE attended to as keys — layers.py:142-144 — so NRMS keeps the fixed-length path.)"""
 
-    dedup_titles = True
-    skip_padding = True
-
     def __init__(self, pooler: nn.Module, p_dropout: float, out_features: int, in_features: Optional[int] = 768,
                  head: bool = True, activation: nn.Module = nn.ReLU(), att: Optional[nn.Module] = None,
                  bias: bool = True):
         super().__init__()
+        self.dedup_titles = True        # per-instance options of the index fast path (see the class docstring);
+        self.skip_padding = True        # `encoder_options(model, ...)` sets them on every TextEncoder of a model
         self.dummy_param = nn.Parameter(torch.zeros(1))
         self.dropout = nn.Dropout(p=p_dropout)
         self.att = att
@@ -184,9 +183,9 @@ class TextEncoder(nn.Module):
         pooled, _ = self.pooler.pool(x2, rows, mask, R, S, seg)
         return _apply_head(self.head, pooled) if hasattr(self, 'head') else pooled
 
-    def plan_kind(self, n_slots: int):
-        """(dedup, ragged) of the plumbing this encoder wants for n_slots title slots"""
-        return (self.dedup_titles and n_slots >= 64,
+    def plan_kind(self, n_slots: int, distinct: bool = False):
+        """(dedup, ragged) of the plumbing this encoder wants for n_slots title slots (distinct: the ids do not repeat)"""
+        return (self.dedup_titles and not distinct and n_slots >= 64,
                 self.skip_padding and self.att is None and hasattr(self.pooler, 'fc1'))
 
     def encode_unique(self, inpt: IndexedTitles):
@@ -199,7 +198,7 @@ class TextEncoder(nn.Module):
         S = store.seq_len
         if self.dropout.p > 0 and self.training:
             raise NotImplementedError('input dropout on gathered titles (every shipped config has p_dropout 0)')
-        dedup, ragged = self.plan_kind(b * n)
+        dedup, ragged = self.plan_kind(b * n, inpt.distinct)
         plan = inpt.plan
         if plan is None or plan.dedup != dedup or plan.ragged != ragged:
             plan = plan_titles(store, inpt.news_ids.to(device).reshape(-1), dedup, ragged)
@@ -226,6 +225,17 @@ class TextEncoder(nn.Module):
             e = self._encode(K._f32(x).reshape(b * n * S, d), None, mask, b * n, S)
         cm = K.collapse_mask(mask, b * n, S)
         return e.view(b, n, self.out_dim), cm.view(b, n, 1)
+
+
+def encoder_options(model: nn.Module, **options) -> None:
+    """set index-fast-path options (dedup_titles, skip_padding) on every TextEncoder inside `model` (instance attributes:
+    two models in one process never see each other's settings)"""
+    for m in model.modules():
+        if isinstance(m, TextEncoder):
+            for k, v in options.items():
+                if not hasattr(m, k):
+                    raise AttributeError(f'TextEncoder has no option {k!r}')
+                setattr(m, k, bool(v))
 
 
 class UserEncoder(nn.Module):
@@ -374,10 +384,9 @@ class ParentRec(nn.Module):
         self.user_encoder = user_encoder
         self.rec_model = rec_model
         self.text_feature = text_feature
-
-    # index batches + additive user pooler: pool the history straight from the batch's DISTINCT article vectors (the
-    # pooler's fc1 runs once per article, the (b,H,E) history tensor and its gradient never exist).  Off: gather first.
-    item_logits = True
+        # index batches + additive user pooler: pool the history straight from the batch's DISTINCT article vectors (the
+        # pooler's fc1 runs once per article, the (b,H,E) history tensor and its gradient never exist).  Off: gather first.
+        self.item_logits = True
 
     def _forward(self, history, candidates, add_user_feats=None, return_embeddings: bool = False):
         merged = merge_sides(history, candidates) if self.item_logits else None

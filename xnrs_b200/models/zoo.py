@@ -113,11 +113,10 @@ class NRMS(ParentRec):
 class NAML(nn.Module):
     """naml.py:7-160 — title + abstract encoders, category / sub-category views, 4-view additive pooling."""
 
-    article_level = True        # index batches: run the 4-view news encoder once per distinct article (off: once per slot)
-
     def __init__(self, cfg, rec_model):
         super().__init__()
         cfg = _cfg(cfg)
+        self.article_level = True   # index batches: run the 4-view news encoder once per distinct article (off: once per slot)
         self.title_encoder = TextEncoder(att=None, pooler=AdditiveAttention(cfg.d_backbone, 256),
                                          p_dropout=cfg.p_dropout, in_features=cfg.d_backbone,
                                          out_features=cfg.title_emb_dim)
@@ -165,17 +164,10 @@ class NAML(nn.Module):
                 U = uniq.numel()
                 per_article = lambda slot_vals: torch.empty(U, device=dev, dtype=slot_vals.dtype).scatter_(0, inv, slot_vals.reshape(-1))
                 u_ids = uniq.view(1, U)
-                encs = (self.title_encoder, self.body_encoder)
-                saved = [enc.dedup_titles for enc in encs]
-                for enc in encs:
-                    enc.dedup_titles = False             # the ids are distinct already: no second unique / gather-back
-                try:
-                    e_u, cm_u = self._news(IndexedTitles(mt[0].store, u_ids), IndexedTitles(ma[0].store, u_ids),
-                                           per_article(flat(hist_ctg, cand_ctg)).view(1, U),
-                                           per_article(flat(hist_subctg, cand_subctg)).view(1, U))
-                finally:
-                    for enc, v in zip(encs, saved):
-                        enc.dedup_titles = v
+                # (the ids are distinct already: `distinct=True` skips the encoders' own unique / gather-back)
+                e_u, cm_u = self._news(IndexedTitles(mt[0].store, u_ids, None, True), IndexedTitles(ma[0].store, u_ids, None, True),
+                                       per_article(flat(hist_ctg, cand_ctg)).view(1, U),
+                                       per_article(flat(hist_subctg, cand_subctg)).view(1, U))
                 e_u, cm_u, inv = e_u[0], K._f32(cm_u.reshape(-1)), K._i32(inv)
                 ue = self.user_encoder
                 u, _ = K.ItemLogitPoolFn.apply(e_u, cm_u, inv[:b * nh].view(b, nh), ue.fc1.weight, ue.fc1.bias,
@@ -332,6 +324,7 @@ class NPA(nn.Module):
                                        nn.Linear(cfg.title_emb_dim, cfg.title_emb_dim))
         self.user_encoder = PersonalizedAttention(cfg.title_emb_dim, 128, cfg.user_emb_dim)
         self.rec_model = rec_model
+        self.skip_padding = True    # index batches: only real tokens reach the GEMM / pooler (ragged groups)
 
     def _titles(self, feats, ue2):
         """per-title personalised pooling + head: (b,n,s,d) or IndexedTitles -> (b,n,E), token mask (b*n*s)"""
@@ -341,9 +334,9 @@ class NPA(nn.Module):
             ids = feats.news_ids.to(device)
             b, n = ids.shape
             s = feats.store.seq_len
-            from .components import TextEncoder, ragged_token_rows
+            from .components import ragged_token_rows
             x2 = feats.store.token_table
-            if TextEncoder.skip_padding:            # only real tokens reach the GEMM / pooler (ragged groups)
+            if self.skip_padding:                   # only real tokens reach the GEMM / pooler (ragged groups)
                 rows, seg, cm = ragged_token_rows(feats.store.title_tokens, ids.reshape(-1))
                 pooled = self.title_pooler.pool(ue2, x2, rows, None, b * n, s, rows_per_query=n, seg=seg)
                 hd = self.news_head

@@ -46,6 +46,21 @@ int xnrs_gather_rows(const float *table, long long V, int D, const int *rows, lo
 int xnrs_scatter_add_rows(float *dtable, long long V, int D, const int *rows, long long R, const float *dout,
                           long long ld_dout, int skip_row, xnrs_stream_t st);
 
+/* device-side id plumbing of one encoder pass (replaces the reference's per-sample host lookups, dataset.py:63-65,77-85;
+ * no host round trip: the counts stay in `counts`, int32[2] = {U distinct articles, T real tokens}).
+ * xnrs_plan_dedup: ids (n) -> uniq (capacity n: the U distinct ids ascending, then article 0), inv (n: slot -> row of uniq),
+ * counts[0] = U.  work = 2 * ceil(n_news / 32) ints of scratch (bitmap + word prefixes).  Ids outside [0, n_news) count
+ * as the pad article 0. */
+int xnrs_plan_dedup(const int *ids, long long n, long long n_news, int *work, int *uniq, int *inv, int *counts,
+                    xnrs_stream_t st);
+/* xnrs_plan_ragged: the real (non-zero) tokens of the articles uniq[0..U) (U = u_count[0], or cap when u_count is NULL), in
+ * title order: rows (capacity rows_cap >= cap*S; entries [T, T+pad_rows) are set to token 0 = the zero row), seg (cap+1 group
+ * offsets; groups past U are empty, seg[cap] = T), cm (cap, 1.0 where a title has tokens: xnrs/utils.py:74-75), lens (cap,
+ * scratch), counts[1] = T. */
+int xnrs_plan_ragged(const int *title_tokens, long long n_news, int S, const int *uniq, long long cap, const int *u_count,
+                     int pad_rows, int *lens, int *seg, int *rows, long long rows_cap, float *cm, int *counts,
+                     xnrs_stream_t st);
+
 /* ---- GEMM (every nn.Linear / matmul on the path: layers.py:60,94-95,128-130,154; news_encoding.py:55-56)
  * C[M,N] (=|+=) act( opA(A)[M,K] * opB(B)[K,N] + bias[N] ).  transA=0: A stored MxK (lda), 1: KxM.
  * transB=0: B stored KxN (ldb), 1: NxK (an nn.Linear weight).  a_rows / b_rows (nullable) gather the
@@ -87,10 +102,11 @@ int xnrs_addpool_fwd(const float *x, const int *x_rows, const float *mask, const
                      xnrs_stream_t st);
 /* d_hid (R*L,A) = grad wrt the fc1 pre-activation; d_w2 (A), d_b2 (1) accumulate; d_x (nullable, R*L,F)
  * receives a_s * d_pooled (the fc1 path is added by the caller's GEMM); d_attn (nullable) is an
- * incoming gradient on the returned weights */
+ * incoming gradient on the returned weights; with seg, n_rows (>= seg[R], or 0) is the length of the row buffers: rows past
+ * the last group (TitlePlan padding) get d_hid = 0 */
 int xnrs_addpool_bwd(const float *x, const int *x_rows, const float *mask, const float *hid, const float *w2,
                      const float *attn, const float *d_pooled, const float *d_attn, const int *seg, long long R, int L,
-                     int F, int A, float *d_hid, float *d_w2, float *d_b2, float *d_x, xnrs_stream_t st);
+                     int F, int A, long long n_rows, float *d_hid, float *d_w2, float *d_b2, float *d_x, xnrs_stream_t st);
 /* ---- row P: personalised attention (layers.py:88-101): logit = <tanh(x_fc x), q_fc(q)> ---------
  * hid (R*L,A) = tanh(x_fc x); qh (Rq,A) = q_fc(q); title r uses query row r / rows_per_query */
 int xnrs_perspool_fwd(const float *x, const int *x_rows, const float *mask, const float *hid, const float *qh,
@@ -98,7 +114,7 @@ int xnrs_perspool_fwd(const float *x, const int *x_rows, const float *mask, cons
                       xnrs_stream_t st);
 int xnrs_perspool_bwd(const float *x, const int *x_rows, const float *mask, const float *hid, const float *qh,
                       const float *attn, const float *d_pooled, const int *seg, long long R, int L, int F, int A,
-                      int rows_per_query, float *d_hid, float *d_qh, float *d_x, xnrs_stream_t st);
+                      int rows_per_query, long long n_rows, float *d_hid, float *d_qh, float *d_x, xnrs_stream_t st);
 /* out[i] = <x[i,:], w> + b[0]  (the pooler's fc2, layers.py:45,60, over a whole table of hidden rows) */
 int xnrs_rowdot(const float *x, const float *w, const float *b, long long n, int A, float *out, xnrs_stream_t st);
 /* additive pooling over PER-ITEM logits (evaluation with a pre-encoded catalogue; layers.py:60-65 slot by slot):

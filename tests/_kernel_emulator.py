@@ -44,6 +44,31 @@ def _xnrs_expand_titles(title_tokens, n_news, S, news_ids, R, rows, mask):
         mask.copy_((tok != 0).float())
 
 
+def _xnrs_plan_dedup(ids, n, n_news, work, uniq, inv, counts):
+    safe = torch.where((ids >= 0) & (ids < n_news), ids, torch.zeros_like(ids))
+    u, iv = torch.unique(safe, return_inverse=True)
+    uniq.zero_()
+    uniq[:u.numel()] = u.to(torch.int32)
+    inv.copy_(iv.to(torch.int32))
+    counts[0] = u.numel()
+
+
+def _xnrs_plan_ragged(title_tokens, n_news, S, uniq, cap, u_count, pad_rows, lens, seg, rows, rows_cap, cm, counts):
+    U = cap if u_count is None else int(u_count[0])
+    tok = title_tokens[uniq[:U].long()]
+    valid = tok != 0
+    ln = valid.sum(1).to(torch.int32)
+    lens.zero_()
+    lens[:U] = ln
+    seg[0] = 0
+    seg[1:cap + 1] = torch.cumsum(lens[:cap], 0).to(torch.int32)
+    T = int(seg[cap])
+    rows[:T] = tok[valid]
+    rows[T:min(T + pad_rows, rows_cap)] = 0
+    cm.copy_((lens[:cap] > 0).float())
+    counts[1] = T
+
+
 def _xnrs_gather_rows(table, V, D, rows, R, out, ld):
     out.copy_(table[rows.long()])
 
@@ -138,7 +163,7 @@ def _xnrs_addpool_fwd(x, x_rows, mask, hid, w2, b2, seg, R, L, F_, A, attn, pool
     _pool_fwd(x, x_rows, mask, hid @ w2 + b2, seg, R, L, attn, pooled)
 
 
-def _xnrs_addpool_bwd(x, x_rows, mask, hid, w2, attn, d_pooled, d_attn, seg, R, L, F_, A, d_hid, d_w2, d_b2, d_x):
+def _xnrs_addpool_bwd(x, x_rows, mask, hid, w2, attn, d_pooled, d_attn, seg, R, L, F_, A, n_rows, d_hid, d_w2, d_b2, d_x):
     dl = _pool_dlogit(x, x_rows, attn, d_pooled, d_attn, seg, R, L)
     d_hid.copy_(dl[:, None] * w2[None, :] * (1 - hid * hid))
     d_w2.add_((dl[:, None] * hid).sum(0))
@@ -153,12 +178,17 @@ def _qrows(qh, seg, R, L, rpq):
 
 
 def _xnrs_perspool_fwd(x, x_rows, mask, hid, qh, seg, R, L, F_, A, rpq, attn, pooled):
-    _pool_fwd(x, x_rows, mask, (hid * _qrows(qh, seg, R, L, rpq)).sum(-1), seg, R, L, attn, pooled)
+    qr = _qrows(qh, seg, R, L, rpq)
+    lg = torch.zeros(hid.shape[0])
+    lg[:qr.shape[0]] = (hid[:qr.shape[0]] * qr).sum(-1)
+    _pool_fwd(x, x_rows, mask, lg, seg, R, L, attn, pooled)
 
 
-def _xnrs_perspool_bwd(x, x_rows, mask, hid, qh, attn, d_pooled, seg, R, L, F_, A, rpq, d_hid, d_qh, d_x):
+def _xnrs_perspool_bwd(x, x_rows, mask, hid, qh, attn, d_pooled, seg, R, L, F_, A, rpq, n_rows, d_hid, d_qh, d_x):
     dl = _pool_dlogit(x, x_rows, attn, d_pooled, None, seg, R, L)
-    d_hid.copy_(dl[:, None] * _qrows(qh, seg, R, L, rpq) * (1 - hid * hid))
+    qr = _qrows(qh, seg, R, L, rpq)
+    d_hid.zero_()                                            # rows past the last ragged group (plan padding) get 0
+    d_hid[:qr.shape[0]] = dl[:qr.shape[0], None] * qr * (1 - hid[:qr.shape[0]] * hid[:qr.shape[0]])
     for r, (b, n) in enumerate(_groups(R, L, seg)):
         d_qh[r // rpq] += (dl[b:b + n, None] * hid[b:b + n]).sum(0)
     if d_x is not None:

@@ -445,18 +445,27 @@ def test_tensor_core_gemm_tma_gather(prec, tol):
     weight-gradient (rows of B along K) forms, ragged sizes"""
     V, D, A_ = 5000, 768, 256
     table = torch.randn(V, D, generator=g(1)) / math.sqrt(D)
-    for R in (1650, 4097):
+    for R in (1650, 4097, 41000):
         rows = torch.randint(0, V, (R,), generator=g(2)).int()
         w = torch.randn(A_, D, generator=g(3))
         bias = torch.randn(A_, generator=g(4))
         want = torch.tanh(table[rows.long()].double() @ w.double().T + bias.double()).float()
         d = torch.randn(R, A_, generator=g(5))
         want_dw = (d.double().T @ table[rows.long()].double()).float()
-        with K.precision(prec):
-            got = K.gemm(cu(table), cu(w), trans_b=True, bias=cu(bias), act=K.ACT_TANH, a_rows=cu(rows))
-            assert_close(got, want, tol, 'gathered forward')
-            got_dw = K.gemm(cu(d), cu(table), trans_a=True, b_rows=cu(rows))
-            assert_close(got_dw, want_dw, tol, 'gathered weight gradient')
+        from xnrs_b200 import _lib
+        lib = _lib.lib()
+        for two in (-1, 1):         # 1: force the CTA-pair kernel, whose gather is a cp.async producer warp (LSU), not TMA
+            lib.xnrs_set_option(b'gemm_2cta', two)
+            try:
+                with K.precision(prec):
+                    got = K.gemm(cu(table), cu(w), trans_b=True, bias=cu(bias), act=K.ACT_TANH, a_rows=cu(rows))
+                    assert_close(got, want, tol, f'gathered forward (gemm_2cta={two})')
+                    if two == 1:
+                        assert lib.xnrs_last_gemm_kernel().decode().startswith('gemm_tc2_kernel')
+                    got_dw = K.gemm(cu(d), cu(table), trans_a=True, b_rows=cu(rows))
+                    assert_close(got_dw, want_dw, tol, f'gathered weight gradient (gemm_2cta={two})')
+            finally:
+                lib.xnrs_set_option(b'gemm_2cta', -1)
 
 
 @pytest.mark.parametrize('prec,tol', [('tf32x3', 5e-5), ('tf32', 3e-3)])
@@ -477,3 +486,42 @@ def test_tensor_core_gemm_cta_pair_kernel(prec, tol, ta, tb):
             assert_close(got, torch.relu(want).float(), tol, f'2-CTA gemm {prec}')
     finally:
         lib.xnrs_set_option(b'gemm_2cta', -1)
+
+
+@pytest.mark.parametrize('n_news,S,n', [(60, 12, 40), (65238, 30, 56320), (160000, 50, 8192), (33, 7, 500)])
+def test_plan_kernels_match_torch_index_ops(n_news, S, n):
+    """device-side id plumbing (xnrs_plan_dedup / xnrs_plan_ragged) == torch.unique + boolean compaction, bit exact, and
+    the padding past the counts is harmless (article 0 / token 0 / empty groups)"""
+    from xnrs_b200 import synthetic as syn
+    from xnrs_b200.data import T_GRANULE, TitleStore, plan_titles
+    cat = syn.make_catalogue(n_news, S, 500, 8, seed=n)
+    tt = cat.title_tokens.clone()
+    tt[3, 1] = 0                                           # a pad token in the MIDDLE of a title: compaction, not truncation
+    ids = torch.from_numpy(syn.zipf_news(np.random.default_rng(n), n_news, n)).int()
+    ids[::7] = 0                                           # pad slots
+    store = TitleStore(cu(cat.token_table), cu(tt))
+    for dedup in (True, False):
+        plan = plan_titles(store, cu(ids), dedup, True).acquire()
+        uniq, inv = torch.unique(ids, return_inverse=True) if dedup else (ids, None)
+        U = uniq.numel()
+        assert plan.n_titles == U and plan.uniq.numel() >= U
+        assert torch.equal(plan.uniq[:U].cpu(), uniq.int()) and int(plan.uniq[U:].abs().sum()) == 0
+        if dedup:
+            assert torch.equal(plan.inv.cpu(), inv.int())
+        tok = tt[uniq.long()]
+        valid = tok != 0
+        lens = valid.sum(1)
+        T = int(lens.sum())
+        assert plan.n_rows == T and plan.rows.numel() % T_GRANULE == 0 and plan.rows.numel() >= T
+        assert torch.equal(plan.rows[:T].cpu(), tok[valid]) and int(plan.rows[T:].abs().sum()) == 0
+        seg = torch.zeros(U + 1, dtype=torch.int64)
+        seg[1:] = torch.cumsum(lens, 0)
+        assert torch.equal(plan.seg[:U + 1].cpu().long(), seg) and bool((plan.seg[U:] == T).all())
+        assert torch.equal(plan.cm[:U].cpu(), (lens > 0).float()) and float(plan.cm[U:].sum()) == 0
+    # fixed-length layout (self-attention keeps pad tokens): rows / mask of the distinct articles, padded titles = article 0
+    plan = plan_titles(store, cu(ids), True, False).acquire()
+    uniq = torch.unique(ids)
+    U = uniq.numel()
+    tok = tt[uniq.long()].reshape(-1)
+    assert torch.equal(plan.rows[:U * S].cpu(), tok) and int(plan.rows[U * S:].abs().sum()) == 0
+    assert torch.equal(plan.mask[:U * S].cpu(), (tok != 0).float()) and float(plan.mask[U * S:].sum()) == 0

@@ -66,8 +66,8 @@ __global__ void __launch_bounds__(POOL_THREADS)
 pool_bwd_kernel(const float *__restrict__ x, const int *__restrict__ x_rows, const float *__restrict__ hid,
                 const float *__restrict__ w2, const float *__restrict__ qh, int rows_per_query,
                 const float *__restrict__ attn, const float *__restrict__ d_pooled, const float *__restrict__ d_attn,
-                const int *__restrict__ seg, long long R, int L, int F, int A, float *__restrict__ d_hid, float *__restrict__ d_w2,
-                float *__restrict__ d_b2, float *__restrict__ d_qh, float *__restrict__ d_x) {
+                const int *__restrict__ seg, long long R, int L, int F, int A, long long n_rows, float *__restrict__ d_hid,
+                float *__restrict__ d_w2, float *__restrict__ d_b2, float *__restrict__ d_qh, float *__restrict__ d_x) {
     extern __shared__ float sm[];
     float *da = sm;            // [L]  da_l, then dlogit_l            (L here = the maximum group length)
     float *al = sm + L;        // [L]  a_l
@@ -151,6 +151,13 @@ pool_bwd_kernel(const float *__restrict__ x, const int *__restrict__ x_rows, con
     if (!kPers) {
         for (int j = tid; j < A; j += blockDim.x) atomicAdd(d_w2 + j, dw[j]);
         if (tid == 0) atomicAdd(d_b2, db_acc);
+    }
+    // ragged groups listed in a padded row buffer (TitlePlan): the rows past the last group belong to no title; their
+    // gradient is exactly 0 and is written here so that the weight-gradient GEMM / column sum can run over all n_rows
+    if (seg && n_rows > 0) {
+        const long long t0 = (long long)seg[R] * A, t1 = n_rows * A;
+        for (long long i = t0 + blockIdx.x * (long long)blockDim.x + tid; i < t1; i += (long long)gridDim.x * blockDim.x)
+            d_hid[i] = 0.f;
     }
 }
 
@@ -555,15 +562,15 @@ extern "C" int xnrs_addpool_fwd(const float *x, const int *x_rows, const float *
 
 extern "C" int xnrs_addpool_bwd(const float *x, const int *x_rows, const float *mask, const float *hid,
                                 const float *w2, const float *attn, const float *d_pooled, const float *d_attn,
-                                const int *seg, long long R, int L, int F, int A, float *d_hid, float *d_w2, float *d_b2,
-                                float *d_x, xnrs_stream_t st) {
+                                const int *seg, long long R, int L, int F, int A, long long n_rows, float *d_hid, float *d_w2,
+                                float *d_b2, float *d_x, xnrs_stream_t st) {
     (void)mask;   // the mask is already folded into attn (masked rows have weight exactly 0)
     if (int e = check_pool(R, L, F, A, x)) return e;
     if (R == 0) return XNRS_OK;
     XNRS_REQUIRE(x && hid && w2 && attn && d_pooled && d_hid && d_w2 && d_b2, "null pointer");
     XNRS_REQUIRE(!(d_x && x_rows), "d_x is only defined for dense x");
     pool_bwd_kernel<false><<<pool_grid(R), POOL_THREADS, (2 * L + A) * sizeof(float), STREAM(st)>>>(
-            x, x_rows, hid, w2, nullptr, 1, attn, d_pooled, d_attn, seg, R, L, F, A, d_hid, d_w2, d_b2, nullptr, d_x);
+            x, x_rows, hid, w2, nullptr, 1, attn, d_pooled, d_attn, seg, R, L, F, A, n_rows, d_hid, d_w2, d_b2, nullptr, d_x);
     XNRS_LAUNCHED();
     return XNRS_OK;
 }
@@ -586,7 +593,7 @@ extern "C" int xnrs_perspool_fwd(const float *x, const int *x_rows, const float 
 
 extern "C" int xnrs_perspool_bwd(const float *x, const int *x_rows, const float *mask, const float *hid,
                                  const float *qh, const float *attn, const float *d_pooled, const int *seg, long long R,
-                                 int L, int F, int A, int rows_per_query, float *d_hid, float *d_qh, float *d_x,
+                                 int L, int F, int A, int rows_per_query, long long n_rows, float *d_hid, float *d_qh, float *d_x,
                                  xnrs_stream_t st) {
     (void)mask;
     if (int e = check_pool(R, L, F, A, x)) return e;
@@ -594,7 +601,7 @@ extern "C" int xnrs_perspool_bwd(const float *x, const int *x_rows, const float 
     XNRS_REQUIRE(x && hid && qh && attn && d_pooled && d_hid && d_qh && rows_per_query > 0, "null pointer");
     XNRS_REQUIRE(!(d_x && x_rows), "d_x is only defined for dense x");
     pool_bwd_kernel<true><<<pool_grid(R), POOL_THREADS, (2 * L + A) * sizeof(float), STREAM(st)>>>(
-            x, x_rows, hid, nullptr, qh, rows_per_query, attn, d_pooled, nullptr, seg, R, L, F, A, d_hid, nullptr,
+            x, x_rows, hid, nullptr, qh, rows_per_query, attn, d_pooled, nullptr, seg, R, L, F, A, n_rows, d_hid, nullptr,
             nullptr, d_qh, d_x);
     XNRS_LAUNCHED();
     return XNRS_OK;

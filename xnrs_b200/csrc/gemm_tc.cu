@@ -43,6 +43,9 @@ struct TcArgs {
     int a_mn, b_mn;         // 1: operand stored [K, MN] (MN contiguous); 0: stored [MN, K] (K contiguous)
     const int *a_gather;    // K-major A: stored rows gathered through this index (table gather fused by TMA gather4)
     const int *b_gather;    // MN-major B: stored rows (= K index) gathered through this index
+    int lsu_gather;         // CTA-pair kernel: 1 = A rows, 2 = B rows gathered by a cp.async producer warp instead of TMA gather4
+    const float *A; long long lda;      // raw operand pointers for that warp
+    const float *B; long long ldb;
     int passes;             // 3 (TF32X3) or 1 (TF32)
     int stages;
     long long tiles_m, tiles_n;
@@ -90,6 +93,13 @@ __device__ __forceinline__ void tma_gather4(void *dst, const CUtensorMap *map, u
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(rows.x), "r"(rows.y), "r"(rows.z), "r"(rows.w)
         : "memory");
 }
+// Ampere-style asynchronous 16-byte copy global -> shared (LDGSTS); src_bytes < 16 zero-fills the remainder
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t *bar) {
@@ -541,7 +551,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
-            mbar_init(&full_bar[s], 1);
+            mbar_init(&full_bar[s], p.lsu_gather ? 2 : 1);                    // TMA thread (+ the cp.async gather warp)
             mbar_init(&ready_bar[s], passes == 3 ? 2 * SPLIT_WARPS : 2);      // used in the leader only: one arrival per
             mbar_init(&empty_bar[s], 1);                                       // splitter warp (or relay) of BOTH CTAs
         }
@@ -566,15 +576,31 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 
     if (warp == 0) {
         // ===================== TMA producer: this CTA's 128 A rows and its half of B =====================
-        if (lane == 0) {
-            StageRing r;
-            for (long long t = pair; t < total; t += npairs) {
-                const long long split = t / tiles_mn, mn = t - split * tiles_mn;
-                const int m0 = (int)((mn / p.tiles_n) * 256 + 128 * rank), n0 = (int)((mn % p.tiles_n) * T2N + 128 * rank);
-                const long long kbeg = split * p.k_per_split, kend = min(p.K, kbeg + p.k_per_split);
-                for (long long k0 = kbeg; k0 < kend; k0 += TBK) {
+        // (lane 0 drives; with a fused table gather all 32 lanes issue tile::gather4 rows: 4 table rows x 128 B each)
+        StageRing r;
+        for (long long t = pair; t < total; t += npairs) {
+            const long long split = t / tiles_mn, mn = t - split * tiles_mn;
+            const int m0 = (int)((mn / p.tiles_n) * 256 + 128 * rank), n0 = (int)((mn % p.tiles_n) * T2N + 128 * rank);
+            const long long kbeg = split * p.k_per_split, kend = min(p.K, kbeg + p.k_per_split);
+            int4 arow = make_int4(0, 0, 0, 0);
+            if (p.a_gather) {       // rows m0+4*lane .. +3 of this CTA's half tile; rows past M re-read the last valid row
+                const long long m = m0 + 4 * lane, last = p.M - 1;
+                arow.x = p.a_gather[min(m, last)];
+                arow.y = p.a_gather[min(m + 1, last)];
+                arow.z = p.a_gather[min(m + 2, last)];
+                arow.w = p.a_gather[min(m + 3, last)];
+            }
+            for (long long k0 = kbeg; k0 < kend; k0 += TBK) {
+                if (lane == 0) {
                     mbar_wait(&empty_bar[r.stage], r.phase ^ 1);
-                    mbar_expect_tx(&full_bar[r.stage], HALF);
+                    mbar_expect_tx(&full_bar[r.stage], p.lsu_gather ? TILE : HALF);
+                }
+                __syncwarp();
+                if (p.lsu_gather == 1) {
+                    // A arrives through the cp.async gather warp
+                } else if (p.a_gather) {
+                    tma_gather4(tileA(r.stage) + lane * 512, &mapA, &full_bar[r.stage], (int)k0, arow);
+                } else if (lane == 0) {
                     if (!p.a_mn) {
                         tma_load_2d(tileA(r.stage), &mapA, &full_bar[r.stage], (int)k0, m0);
                     } else {
@@ -582,6 +608,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                         for (int c = 0; c < 4; ++c)
                             tma_load_2d(tileA(r.stage) + c * 4096, &mapA, &full_bar[r.stage], m0 + 32 * c, (int)k0);
                     }
+                }
+                if (p.lsu_gather == 2) {
+                    // B arrives through the cp.async gather warp
+                } else if (p.b_gather) {   // chunk c = lane / 8 (32 N-columns) x k-row group j = lane % 8: k-rows k0+4j .. +3
+                    const int j = lane & 7, c = lane >> 3;
+                    const long long k = k0 + 4 * j, last = p.K - 1;
+                    int4 brow;      // rows past K re-read the last valid row: the A tile is zero-filled there
+                    brow.x = p.b_gather[min(k, last)];
+                    brow.y = p.b_gather[min(k + 1, last)];
+                    brow.z = p.b_gather[min(k + 2, last)];
+                    brow.w = p.b_gather[min(k + 3, last)];
+                    tma_gather4(tileB(r.stage) + c * 4096 + j * 512, &mapB, &full_bar[r.stage], n0 + 32 * c, brow);
+                } else if (lane == 0) {
                     if (!p.b_mn) {
                         tma_load_2d(tileB(r.stage), &mapB, &full_bar[r.stage], (int)k0, n0);
                     } else {
@@ -589,8 +628,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                         for (int c = 0; c < 4; ++c)
                             tma_load_2d(tileB(r.stage) + c * 4096, &mapB, &full_bar[r.stage], n0 + 32 * c, (int)k0);
                     }
-                    r.advance(stages);
                 }
+                r.advance(stages);
             }
         }
     } else if (warp == 1) {
@@ -649,8 +688,76 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 }
             }
         }
-    } else if (warp < 4) {
-        // idle
+    } else if (warp == 3) {
+        // ===================== cp.async gather warp: table rows -> the swizzled operand tile ===========================
+        // TMA tile::gather4 moves one 128-byte row per ~32 cycles per SM (measured: 1.0 TB/s chip-wide, the fused-gather
+        // GEMMs ran 0.10-0.21 ms slower than gather-then-GEMM); the LSU path issues 512 B per instruction.  One warp copies
+        // this CTA's tile of the gathered operand with 16-byte cp.async into exactly the layout TMA would have produced
+        // (K-major A: 128-byte rows, 16-byte chunk c of row r stored at chunk c ^ (r & 7); MN-major B: 32-byte units XORed
+        // with k-row & 3 inside each 32-column chunk), keeps stages-1 groups in flight and publishes a stage with
+        // wait_group -> fence.proxy.async -> mbarrier arrive.
+        if (p.lsu_gather) {
+            StageRing r, done;
+            int inflight = 0;
+            auto publish = [&]() {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full_bar[done.stage]);
+                done.advance(stages);
+                --inflight;
+            };
+            for (long long t = pair; t < total; t += npairs) {
+                const long long split = t / tiles_mn, mn = t - split * tiles_mn;
+                const long long m0 = (mn / p.tiles_n) * 256 + 128 * rank, n0 = (mn % p.tiles_n) * T2N + 128 * rank;
+                const long long kbeg = split * p.k_per_split, kend = min(p.K, kbeg + p.k_per_split);
+                int arow[32];
+                if (p.lsu_gather == 1) {        // lane covers chunk (lane & 7) of rows (lane >> 3) + 4 i
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        arow[i] = p.a_gather[min(m0 + (lane >> 3) + 4 * i, p.M - 1)];
+                }
+                for (long long k0 = kbeg; k0 < kend; k0 += TBK) {
+                    if (lane == 0) mbar_wait(&empty_bar[r.stage], r.phase ^ 1);
+                    __syncwarp();
+                    if (p.lsu_gather == 1) {
+                        const uint32_t dst = smem_u32(tileA(r.stage));
+                        const int c = lane & 7;
+                        const long long kk = k0 + 4 * c;
+                        const int nbytes = (int)max(0LL, min(4LL, p.K - kk)) * 4;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const int rr = (lane >> 3) + 4 * i;
+                            cp_async16(dst + rr * 128 + ((c ^ (rr & 7)) << 4), p.A + (long long)arow[i] * p.lda + (nbytes ? kk : 0), nbytes);
+                        }
+                    } else {
+                        const uint32_t dst = smem_u32(tileB(r.stage));
+                        const int c4 = lane >> 3, u = lane & 7;
+                        const long long kmine = k0 + lane;
+                        const int myrow = kmine < p.K ? p.b_gather[kmine] : -1;
+                        const long long col = n0 + 32 * c4 + 4 * u;
+                        const int cbytes = (int)max(0LL, min(4LL, p.N - col)) * 4;
+#pragma unroll
+                        for (int kr = 0; kr < 32; ++kr) {
+                            const int row = __shfl_sync(0xffffffffu, myrow, kr);
+                            const int nbytes = row >= 0 ? cbytes : 0;
+                            cp_async16(dst + c4 * 4096 + kr * 128 + ((((u >> 1) ^ (kr & 3)) << 5) | ((u & 1) << 4)),
+                                       p.B + (nbytes ? (long long)row * p.ldb + col : 0), nbytes);
+                        }
+                    }
+                    cp_async_commit();
+                    ++inflight;
+                    r.advance(stages);
+                    if (inflight == stages) {           // the oldest group has had stages-1 younger groups issued behind it
+                        if (stages == 3) cp_async_wait<2>();
+                        else if (stages == 6) cp_async_wait<5>();
+                        else cp_async_wait<0>();
+                        publish();
+                    }
+                }
+            }
+            cp_async_wait<0>();
+            while (inflight > 0) publish();
+        }
     } else if (warp < EPI2_WARP0) {
         // ===================== splitters (3xTF32): lo = x - trunc_tf32(x) for this CTA's tiles =====================
         if (passes == 3) {
@@ -776,6 +883,8 @@ int gemm_tensorcore(const GemmArgs &a, int precision, cudaStream_t st, int *stat
     p.a_mn = a.transA ? 1 : 0;      // transA: A stored [K, M]
     p.b_mn = a.transB ? 0 : 1;      // transB: B stored [N, K] (K-major); else stored [K, N]
     p.a_gather = a.a_rows; p.b_gather = a.b_rows;
+    p.A = a.A; p.lda = a.lda; p.B = a.B; p.ldb = a.ldb;
+    p.lsu_gather = 0;
     p.passes = (precision == XNRS_PREC_TF32X3) ? 3 : 1;
     // 3xTF32 keeps BN=128: its stage is 2x larger (hi+lo), and 3 smem stages + 2 TMEM stages beat the wider tile
     // (measured: 156 vs 142 TFLOP/s); single-pass TF32 takes BN=256 (398 vs 340 TFLOP/s)
@@ -790,7 +899,7 @@ int gemm_tensorcore(const GemmArgs &a, int precision, cudaStream_t st, int *stat
         g_opt_2cta = e ? atoi(e) : -1;
     }
     const bool want2 = g_opt_2cta == 1 || (g_opt_2cta == -1 && p.passes == 3);
-    bool use2 = want2 && a.N > 128 && a.M >= 256 && !a.a_rows && !a.b_rows && (num_sms() % 2 == 0);
+    bool use2 = want2 && a.N > 128 && a.M >= 256 && (num_sms() % 2 == 0);
     // the pair kernel has 74 workers with 256x256 tiles: problems with fewer than two waves of such tiles (launch list of a
     // CL step: 20-40 us for 0.1-3 GFLOP GEMMs on 4-70 CTAs) run on the 1-CTA kernel, whose 128x128 tiles spread the same
     // work over four times as many CTAs with half the per-stage latency
@@ -856,6 +965,9 @@ int gemm_tensorcore(const GemmArgs &a, int precision, cudaStream_t st, int *stat
     long long total = tiles * split;
     unsigned grid = (unsigned)(total < num_sms() ? total : num_sms());
     if (use2) {
+        static int lsu = -1;                    // XNRS_LSU_GATHER=0 falls back to TMA tile::gather4 (kept for comparison)
+        if (lsu < 0) { const char *e = getenv("XNRS_LSU_GATHER"); lsu = e ? atoi(e) : 1; }
+        if (lsu) p.lsu_gather = a.a_rows ? 1 : (a.b_rows ? 2 : 0);
         const long long pairs = total < num_sms() / 2 ? total : num_sms() / 2;
         gemm_tc2_kernel<<<(unsigned)(2 * pairs), TC2_THREADS, smem_bytes, st>>>(mapA, mapB, p);
         g_last_gemm_kernel = p.passes == 3 ? "gemm_tc2_kernel (cta_group::2, 256x256 pair tile, 3xTF32)"

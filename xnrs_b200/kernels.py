@@ -241,17 +241,22 @@ def _need(ctx, i):
     return ctx.needs_input_grad[i]
 
 
-GATHER_IN_TMA = bool(int(__import__('os').environ.get('XNRS_TMA_GATHER', '0')))
+FUSED_GATHER = bool(int(__import__('os').environ.get('XNRS_FUSED_GATHER', '1')))
+FUSED_GATHER_MIN_ROWS = 40960       # >= two waves of 256-row pair tiles: below that the 1-CTA kernel (TMA gather4) would run
 
 
-def _resolve_rows(x, rows):
-    """how the fused table gather (row G) reaches the GEMMs.  The exact-fp32 SIMT GEMM gathers rows inside its tile
-    loads.  The tcgen05 GEMM can gather with TMA tile::gather4 (XNRS_TMA_GATHER=1), but 128-byte gather4 rows
-    issue ~4x slower than tiled TMA boxes (measured 92 vs 156 TFLOP/s), so by default the tensor-core modes copy the
-    gathered rows once (one coalesced pass, bit exact) and every consumer of the step reads the dense copy."""
-    if rows is not None and _precision != 0 and not GATHER_IN_TMA:
-        return gather_rows(x, rows), None
-    return x, rows
+def _resolve_rows(x, rows, fuse_ok: bool = True):
+    """how the fused table gather (row G) reaches the GEMMs.  The exact-fp32 SIMT GEMM gathers rows inside its tile loads.
+    The 3xTF32 CTA-pair GEMM gathers with a cp.async producer warp straight into its swizzled operand tiles (forward: rows of
+    A; weight gradient: rows of B), so for the token-level GEMMs of the additive / personalised poolers no dense copy of the
+    gathered rows is ever made and the pooling kernels read the table rows themselves.  Everything else (small problems,
+    single-pass modes, the three projection GEMMs of self-attention that would each gather again) copies the gathered rows
+    once (one coalesced pass, bit exact) and reads the dense copy."""
+    if rows is None or _precision == 0:
+        return x, rows
+    if FUSED_GATHER and fuse_ok and _precision == 1 and rows.numel() >= FUSED_GATHER_MIN_ROWS:
+        return x, rows
+    return gather_rows(x, rows), None
 
 
 # ---- weight gradients straight into the optimiser's gradient buffer ----------------------------------------------------
@@ -375,7 +380,7 @@ class AdditivePoolFn(torch.autograd.Function):
         if need_dx and rows is not None:
             raise RuntimeError('no gradient flows into a gathered (frozen) table')
         d_x = torch.empty_like(x) if need_dx else None
-        call('xnrs_addpool_bwd', x, rows, None, hid, w2.reshape(-1), attn, d_pooled, d_attn, seg, R, L, F_, A, d_hid,
+        call('xnrs_addpool_bwd', x, rows, None, hid, w2.reshape(-1), attn, d_pooled, d_attn, seg, R, L, F_, A, hid.shape[0], d_hid,
              w2_buf.view(-1), b2_buf.view(-1), d_x)
         d_w1 = _wgrad_gemm(w1, d_hid, x, b_rows=rows)
         d_b1 = _wgrad_colsum(b1, d_hid)
@@ -455,7 +460,7 @@ class PersonalizedPoolFn(torch.autograd.Function):
         if need_dx and rows is not None:
             raise RuntimeError('no gradient flows into a gathered (frozen) table')
         d_x = torch.empty_like(x) if need_dx else None
-        call('xnrs_perspool_bwd', x, rows, None, hid, qh, attn, d_pooled, seg, R, L, F_, A, rpq, d_hid, d_qh, d_x)
+        call('xnrs_perspool_bwd', x, rows, None, hid, qh, attn, d_pooled, seg, R, L, F_, A, rpq, hid.shape[0], d_hid, d_qh, d_x)
         d_xw = gemm(d_hid, x, trans_a=True, b_rows=rows)
         d_xb = colsum(d_hid)
         if need_dx:
@@ -473,7 +478,7 @@ class MultiHeadAttentionFn(torch.autograd.Function):
     def forward(ctx, x, rows, mask, wq, bq, wk, bk, wv, bv, wo, bo, R, L, n_heads, keep, p_drop, seed):
         D = wq.shape[0]
         dk = D // n_heads
-        x, rows = _resolve_rows(x, rows)
+        x, rows = _resolve_rows(x, rows, fuse_ok=False)
         q = gemm(x, wq, trans_b=True, bias=bq, a_rows=rows)
         k = gemm(x, wk, trans_b=True, bias=bk, a_rows=rows)
         v = gemm(x, wv, trans_b=True, bias=bv, a_rows=rows)

@@ -121,15 +121,11 @@ class MultiHeadAttention(nn.Module):
         return self.attend(x2, None, _flat_mask(m, R * L), R, L).view(R, L, self.d_model)
 
 
-def ragged_token_rows(title_tokens: torch.Tensor, news_ids: torch.Tensor):
-    """index plumbing for the padding-free path: -> (token rows of the real tokens (total,) int32,
-    group offsets (n+1,) int32, collapsed title mask (n,) fp32).  One host sync (the compacted size)."""
-    tok = title_tokens[news_ids.long()]
-    valid = tok != 0
-    lens = valid.sum(1, dtype=torch.int32)
-    seg = torch.zeros(lens.numel() + 1, device=tok.device, dtype=torch.int32)
-    torch.cumsum(lens, 0, out=seg[1:])
-    return tok[valid].contiguous(), seg, (lens > 0).to(torch.float32)
+def ragged_token_rows(store, news_ids: torch.Tensor):
+    """index plumbing for the padding-free path without de-duplication: -> (token rows of the real tokens (T',) int32 padded
+    with the zero row, group offsets (n+1,) int32, collapsed title mask (n,) fp32).  Device kernels; one count read-back."""
+    plan = plan_titles(store, news_ids.reshape(-1), False, True).acquire()
+    return plan.rows, plan.seg, plan.cm
 
 
 def _apply_head(head: nn.Sequential, x2: torch.Tensor) -> torch.Tensor:

@@ -337,7 +337,7 @@ class NPA(nn.Module):
             from .components import ragged_token_rows
             x2 = feats.store.token_table
             if self.skip_padding:                   # only real tokens reach the GEMM / pooler (ragged groups)
-                rows, seg, cm = ragged_token_rows(feats.store.title_tokens, ids.reshape(-1))
+                rows, seg, cm = ragged_token_rows(feats.store, ids.reshape(-1))
                 pooled = self.title_pooler.pool(ue2, x2, rows, None, b * n, s, rows_per_query=n, seg=seg)
                 hd = self.news_head
                 e = K.Mlp2Fn.apply(pooled, hd[0].weight, hd[0].bias, hd[2].weight, hd[2].bias)

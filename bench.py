@@ -465,9 +465,16 @@ def train_workload(ctx, args, model_key, want_cpu=True, want_eager=False):
     trainer_cls = MSERankingTrainer if model_key == 'npa' else ContrastiveRankingTrainer     # NPA has no CL hook
     model = make_model(cfg)
     encoder_options(model, dedup_titles=not args.no_dedup, skip_padding=not args.no_skip_padding)
-    trainer = trainer_cls(dict(cfg, device=str(dev)), model)
+    use_graph = model_key == 'cl' and not args.no_graph and (world == 1 or args.graph_multi_gpu)
+    trainer = trainer_cls(dict(cfg, device=str(dev)), model, graph_safe=use_graph)
     trainer.model.train()
     dp = DataParallelTrainer(trainer)
+    if use_graph:           # whole step (zero_grad .. Adam, gradient collectives included) replayed as ONE CUDA graph per shape bucket
+        from xnrs_b200.graphs import GraphedStep
+        stepper = GraphedStep(dp)
+        run_step = stepper.step
+    else:
+        stepper, run_step = None, dp.train_step
 
     n_batches = 8           # distinct batches cycled through; weak scaling: every rank draws its own B impressions
     raws = [syn.make_train_batch(N_NEWS, B, HIST_LEN, seed=1000 + 97 * rank + i) for i in range(n_batches)]
@@ -475,8 +482,8 @@ def train_workload(ctx, args, model_key, want_cpu=True, want_eager=False):
     resident = [syn.index_batch(store, cat, r, dev, abstract_store=astore) for r in raws]
     h2d_bytes = sum(v.numel() * v.element_size() for v in raws[0].values())
 
-    for i in range(args.warmup):
-        dp.train_step(resident[i % n_batches])
+    for i in range(max(args.warmup, 2 * n_batches if use_graph else 0)):      # graphs: every cycled batch's bucket gets captured
+        run_step(resident[i % n_batches])
 
     # ---- timed region 1: inputs resident in HBM --------------------------------------------------------------------
     def region_resident():
@@ -484,7 +491,7 @@ def train_workload(ctx, args, model_key, want_cpu=True, want_eager=False):
         dp.prefetch(resident[0])
         t0.record()
         for i in range(steps):
-            dp.train_step(resident[i % n_batches])
+            run_step(resident[i % n_batches])
             if not args.no_prefetch:         # input pipeline: the next batch's id plumbing runs on a side stream meanwhile
                 dp.prefetch(resident[(i + 1) % n_batches])
         t1.record()
@@ -527,7 +534,7 @@ def train_workload(ctx, args, model_key, want_cpu=True, want_eager=False):
         t0 = time.perf_counter()
         for i in range(steps):
             nxt = h2d(i + 1)                 # tiny copy, queued BEFORE this step so the side stream can plan it meanwhile
-            out = dp.train_step(cur[0])
+            out = run_step(cur[0])
             if not args.no_prefetch:
                 dp.prefetch(nxt[0], after=nxt[1])
             last[0] = float(out['loss'])     # device -> host read of the step's loss (4 bytes, synchronises)
@@ -549,13 +556,15 @@ def train_workload(ctx, args, model_key, want_cpu=True, want_eager=False):
                    'l2': 'inputs larger than L2: 307 MB token table, ~0.5 GB of gathered rows per step, 8 batches cycled',
                    'precision': args.precision, 'final_loss': last[0],
                    'dedup_titles': not args.no_dedup, 'skip_padding': not args.no_skip_padding,
+                   'cuda_graph': ({'replays': stepper.replays, 'captures': stepper.captures, 'eager_steps': stepper.eager_steps,
+                                   'shape_buckets': len(stepper.graphs)} if stepper else False),
                    'timing': f'median of {sp["regions"]} regions of exactly {steps} steps ({sp["timed_s"]} s measured)'},
         'spread': sp,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4,
                 'spread': e_sp, 'note': 'host input = int32 news ids / targets / labels (the index fast path of the drop-in API)'},
         'gpu_launches': launches, 'roofline': roofline, 'clocks': clocks.summary(),
     }
-    del dp, trainer, model, resident, store, astore
+    del dp, trainer, model, resident, store, astore, stepper, run_step
     torch.cuda.empty_cache()
     if world == 1 and want_eager and not args.no_cpu_baseline:
         out['eager_gpu_baseline'] = eager_gpu_baseline(dev)
@@ -758,6 +767,8 @@ def main():
     ap.add_argument('--model', default=None, choices=list(MODEL_CFGS), help='(round-1 spelling) == --only MODEL')
     ap.add_argument('--no-skip-padding', action='store_true', help='run pad tokens through the encoder like the reference does')
     ap.add_argument('--no-prefetch', action='store_true', help='compute the id plumbing of each batch inside its own step')
+    ap.add_argument('--no-graph', action='store_true', help='launch the CL step kernel by kernel instead of replaying its CUDA graph')
+    ap.add_argument('--graph-multi-gpu', action='store_true', help='also replay CUDA graphs (NCCL collectives captured) under torchrun')
     ap.add_argument('--no-dedup', action='store_true', help='encode every (impression, slot) title, not each distinct article once')
     ap.add_argument('--eval-impressions', type=int, default=376_471)
     args = ap.parse_args()

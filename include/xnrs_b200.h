@@ -56,9 +56,9 @@ int xnrs_plan_dedup(const int *ids, long long n, long long n_news, int *work, in
 /* xnrs_plan_ragged: the real (non-zero) tokens of the articles uniq[0..U) (U = u_count[0], or cap when u_count is NULL), in
  * title order: rows (capacity rows_cap >= cap*S; entries [T, T+pad_rows) are set to token 0 = the zero row), seg (cap+1 group
  * offsets; groups past U are empty, seg[cap] = T), cm (cap, 1.0 where a title has tokens: xnrs/utils.py:74-75), lens (cap,
- * scratch), counts[1] = T. */
+ * scratch), counts[1] = T.  tix (nullable, rows_cap): the group of each row, -1 on the padding rows. */
 int xnrs_plan_ragged(const int *title_tokens, long long n_news, int S, const int *uniq, long long cap, const int *u_count,
-                     int pad_rows, int *lens, int *seg, int *rows, long long rows_cap, float *cm, int *counts,
+                     int pad_rows, int *lens, int *seg, int *rows, int *tix, long long rows_cap, float *cm, int *counts,
                      xnrs_stream_t st);
 
 /* ---- GEMM (every nn.Linear / matmul on the path: layers.py:60,94-95,128-130,154; news_encoding.py:55-56)
@@ -103,10 +103,23 @@ int xnrs_addpool_fwd(const float *x, const int *x_rows, const float *mask, const
 /* d_hid (R*L,A) = grad wrt the fc1 pre-activation; d_w2 (A), d_b2 (1) accumulate; d_x (nullable, R*L,F)
  * receives a_s * d_pooled (the fc1 path is added by the caller's GEMM); d_attn (nullable) is an
  * incoming gradient on the returned weights; with seg, n_rows (>= seg[R], or 0) is the length of the row buffers: rows past
- * the last group (TitlePlan padding) get d_hid = 0 */
+ * the last group (TitlePlan padding) get d_hid = 0; d_b1 (nullable, A) accumulates the fc1 bias gradient = column sums of
+ * d_hid (saves the separate xnrs_colsum pass over d_hid) */
 int xnrs_addpool_bwd(const float *x, const int *x_rows, const float *mask, const float *hid, const float *w2,
                      const float *attn, const float *d_pooled, const float *d_attn, const int *seg, long long R, int L,
-                     int F, int A, long long n_rows, float *d_hid, float *d_w2, float *d_b2, float *d_x, xnrs_stream_t st);
+                     int F, int A, long long n_rows, float *d_hid, float *d_w2, float *d_b2, float *d_x, float *d_b1,
+                     xnrs_stream_t st);
+/* ---- rows G + A fused (north-star items 1 + 3): gather -> fc1 (+b1, tanh) -> <., w2> + b2 -> exp -> per-title sum(e) and
+ * sum(e * x) -> normalise by (sum + 1e-8), in ONE launch of the CTA-pair tcgen05 kernel (cp.async gather warp, pooling
+ * epilogue on the TMEM accumulators; the x rows of a tile are re-read from L2 for the weighted sum) plus a small
+ * normalisation pass.  x rows are x[g] or table rows x[x_rows[g]] (ldx floats apart); tix (n_rows) = title of each row, -1
+ * for padding rows.  Outputs: hid (n_rows, A) = tanh(fc1 x) (saved for the backward), e (n_rows, scratch), zsum (R, scratch),
+ * attn (n_rows) and pooled (R, F) exactly as xnrs_addpool_fwd defines them.  Covers A == 256, F % 128 == 0, F <= 768,
+ * n_rows >= 256 in the tensor-core precisions on sm_100; otherwise returns XNRS_ERR_UNSUPPORTED with nothing launched and the
+ * caller runs xnrs_gemm(TANH) + xnrs_addpool_fwd (the same mathematics in two launches). */
+int xnrs_titlepool_fwd(const float *x, long long ldx, const int *x_rows, const int *tix, long long n_rows, long long R, int F,
+                       int A, const float *w1, const float *b1, const float *w2, const float *b2, int precision, float *hid,
+                       float *e, float *zsum, float *attn, float *pooled, xnrs_stream_t st);
 /* ---- row P: personalised attention (layers.py:88-101): logit = <tanh(x_fc x), q_fc(q)> ---------
  * hid (R*L,A) = tanh(x_fc x); qh (Rq,A) = q_fc(q); title r uses query row r / rows_per_query */
 int xnrs_perspool_fwd(const float *x, const int *x_rows, const float *mask, const float *hid, const float *qh,

@@ -53,7 +53,7 @@ def _xnrs_plan_dedup(ids, n, n_news, work, uniq, inv, counts):
     counts[0] = u.numel()
 
 
-def _xnrs_plan_ragged(title_tokens, n_news, S, uniq, cap, u_count, pad_rows, lens, seg, rows, rows_cap, cm, counts):
+def _xnrs_plan_ragged(title_tokens, n_news, S, uniq, cap, u_count, pad_rows, lens, seg, rows, tix, rows_cap, cm, counts):
     U = cap if u_count is None else int(u_count[0])
     tok = title_tokens[uniq[:U].long()]
     valid = tok != 0
@@ -65,6 +65,9 @@ def _xnrs_plan_ragged(title_tokens, n_news, S, uniq, cap, u_count, pad_rows, len
     T = int(seg[cap])
     rows[:T] = tok[valid]
     rows[T:min(T + pad_rows, rows_cap)] = 0
+    if tix is not None:
+        tix[:T] = torch.repeat_interleave(torch.arange(U, dtype=torch.int32), ln.long())
+        tix[T:min(T + pad_rows, rows_cap)] = -1
     cm.copy_((lens[:cap] > 0).float())
     counts[1] = T
 
@@ -163,9 +166,27 @@ def _xnrs_addpool_fwd(x, x_rows, mask, hid, w2, b2, seg, R, L, F_, A, attn, pool
     _pool_fwd(x, x_rows, mask, hid @ w2 + b2, seg, R, L, attn, pooled)
 
 
-def _xnrs_addpool_bwd(x, x_rows, mask, hid, w2, attn, d_pooled, d_attn, seg, R, L, F_, A, n_rows, d_hid, d_w2, d_b2, d_x):
+def _xnrs_titlepool_fwd(x, ldx, x_rows, tix, n_rows, R, F_, A, w1, b1, w2, b2, prec, hid, e, zsum, attn, pooled):
+    xr = _rows(x, x_rows)[:n_rows]
+    h = torch.tanh(xr @ w1.T + b1)
+    hid.copy_(h)
+    valid = tix[:n_rows] >= 0
+    ev = torch.where(valid, torch.exp(h @ w2.reshape(-1) + b2), torch.zeros(n_rows))
+    e.copy_(ev)
+    t = tix[:n_rows].clamp_min(0).long()
+    zsum.zero_()
+    zsum.index_add_(0, t, ev)
+    pooled.zero_()
+    pooled.index_add_(0, t, ev[:, None] * xr)
+    attn.copy_(torch.where(valid, ev / (zsum[t] + 1e-8), torch.zeros(n_rows)))
+    pooled.div_((zsum + 1e-8)[:, None])
+
+
+def _xnrs_addpool_bwd(x, x_rows, mask, hid, w2, attn, d_pooled, d_attn, seg, R, L, F_, A, n_rows, d_hid, d_w2, d_b2, d_x, d_b1):
     dl = _pool_dlogit(x, x_rows, attn, d_pooled, d_attn, seg, R, L)
     d_hid.copy_(dl[:, None] * w2[None, :] * (1 - hid * hid))
+    if d_b1 is not None:
+        d_b1.add_(d_hid.sum(0))
     d_w2.add_((dl[:, None] * hid).sum(0))
     d_b2.add_(dl.sum())
     if d_x is not None:

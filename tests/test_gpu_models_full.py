@@ -254,3 +254,40 @@ def test_bench_config_step_matches_oracle(monkeypatch):
 def _lib_fallbacks():
     from xnrs_b200 import _lib
     return _lib.lib().xnrs_gemm_simt_fallbacks()
+
+
+def test_cuda_graph_replay_equals_eager_steps(monkeypatch):
+    """12 training steps through GraphedStep (first visit of a shape bucket eager, second captured, the rest replayed with
+    ONE launch) == the same 12 steps launched kernel by kernel: per-step losses and the final parameters.  (Not bit-for-bit:
+    split-K and scatter reductions use fp32 atomics whose order differs from run to run, eager or not.)"""
+    import bench
+    from xnrs_b200 import kernels as K
+    from xnrs_b200.distributed import DataParallelTrainer
+    from xnrs_b200.graphs import GraphedStep
+    monkeypatch.setattr(K, '_precision', K.PRECISIONS['tf32x3'])
+    B = 256
+    cfg = dict(bench.CL_CFG, device=DEV, lr=1e-3)
+    cat = syn.make_catalogue(5000, bench.SEQ_LEN, 20000, 768, seed=0)
+    store = TitleStore(cat.token_table.to(DEV), cat.title_tokens.to(DEV))
+    raws = [syn.make_train_batch(5000, B, bench.HIST_LEN, seed=50 + (i % 3)) for i in range(12)]   # three distinct batches recur
+    runs = []
+    for graphed in (False, True):
+        torch.manual_seed(0)
+        model = make_model(cfg)
+        trainer = ContrastiveRankingTrainer(cfg, model, graph_safe=True)
+        model.train()
+        dp = DataParallelTrainer(trainer)
+        stepper = GraphedStep(dp) if graphed else None
+        losses = []
+        for i, raw in enumerate(raws):
+            batch = syn.index_batch(store, cat, raw, DEV)
+            if i % 2:
+                dp.prefetch(batch)                      # both the prefetched and the in-line plan reach the graph
+            out = stepper.step(batch) if graphed else dp.train_step(batch)
+            losses.append(float(out['loss']))
+        runs.append((losses, trainer.optimizer.flat_p.clone()))
+        if graphed:
+            assert stepper.replays >= 6 and stepper.captures >= 1 and stepper.eager_steps <= 4, (stepper.replays, stepper.captures, stepper.eager_steps)
+    (l0, p0), (l1, p1) = runs
+    assert_close(torch.tensor(l1), torch.tensor(l0), 1e-5, 'per-step losses')
+    assert_close(p1, p0, 1e-4, 'parameters after 12 steps')

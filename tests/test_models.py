@@ -205,6 +205,43 @@ def test_item_logit_pooling_equals_pooling_the_gathered_rows(device):
         assert_close(a, b, 2e-5, name, atol=1e-6)
 
 
+def test_fused_title_pool_equals_gemm_plus_pool(device, monkeypatch):
+    """AdditivePoolFn's one-launch forward (xnrs_titlepool_fwd: gather -> fc1 -> tanh -> logit -> exp -> per-title sums) ==
+    xnrs_gemm(TANH) + xnrs_addpool_fwd on the same ragged, padded TitlePlan rows: pooled vectors, weights, every gradient"""
+    from xnrs_b200 import synthetic as syn
+    from xnrs_b200.data import TitleStore, plan_titles
+    if device == 'cpu':
+        monkeypatch.setattr(K, '_precision', K.PRECISIONS['tf32x3'])       # host-logic run: the emulator ignores the precision
+    elif K.get_precision() == 'fp32':
+        pytest.skip('the fused kernel exists in the tensor-core precisions only')
+    monkeypatch.setattr(K, 'FUSED_GATHER_MIN_ROWS', 256)
+    D, A = 128, 256
+    cat = syn.make_catalogue(300, 20, vocab=900, dim=D, seed=21)
+    ids = torch.from_numpy(syn.zipf_news(np.random.default_rng(3), 300, 700)).int()
+    ids[::9] = 0
+    store = TitleStore(cat.token_table.to(device) * 0.3, cat.title_tokens.to(device))
+    plan = plan_titles(store, ids.to(device), True, True).acquire()
+    assert plan.rows.numel() >= 256 and plan.tix is not None
+    gen = torch.Generator().manual_seed(5)
+    params = [torch.randn(A, D, generator=gen) / D ** 0.5, torch.randn(A, generator=gen) * 0.1,
+              torch.randn(1, A, generator=gen) / A ** 0.5, torch.randn(1, generator=gen) * 0.1]
+    R = plan.uniq.numel()
+    gout = torch.randn(R, D, generator=gen).to(device)
+    outs = []
+    for fused in (True, False):
+        monkeypatch.setattr(K, 'FUSED_TITLEPOOL', fused)
+        n0 = K.launch_count() if device != 'cpu' else 0
+        leaves = [p.clone().to(device).requires_grad_(True) for p in params]
+        pooled, attn = K.AdditivePoolFn.apply(store.token_table, plan.rows, None, *leaves, R, 20, plan.seg, plan.tix)
+        (pooled * gout).sum().backward()
+        outs.append([pooled.detach(), attn.detach()[:plan.n_rows]] + [t.grad for t in leaves])
+        assert float(pooled[plan.n_titles:].abs().sum()) == 0           # padded titles pool to exactly 0
+    tol = 1e-4 if device != 'cpu' else 2e-5
+    for name, a, b in zip(('pooled', 'attn', 'd fc1.weight', 'd fc1.bias', 'd fc2.weight', 'd fc2.bias'), *outs):
+        # d fc2.bias is analytically ~0 (the normalised weights are shift invariant up to the 1e-8): absolute floor only
+        assert_close(a, b, tol, name, atol=1e-4 if name == 'd fc2.bias' else 1e-6)
+
+
 @pytest.mark.parametrize('name', ['cl', 'nrms', 'naml', 'lstur_con', 'npa'])
 def test_index_batches_equal_dense_batches(name, device):
     """the index fast path (device-resident token table + int32 news ids: title de-duplication, padding-free pooling,

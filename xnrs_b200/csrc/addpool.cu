@@ -67,11 +67,13 @@ pool_bwd_kernel(const float *__restrict__ x, const int *__restrict__ x_rows, con
                 const float *__restrict__ w2, const float *__restrict__ qh, int rows_per_query,
                 const float *__restrict__ attn, const float *__restrict__ d_pooled, const float *__restrict__ d_attn,
                 const int *__restrict__ seg, long long R, int L, int F, int A, long long n_rows, float *__restrict__ d_hid,
-                float *__restrict__ d_w2, float *__restrict__ d_b2, float *__restrict__ d_qh, float *__restrict__ d_x) {
+                float *__restrict__ d_w2, float *__restrict__ d_b2, float *__restrict__ d_qh, float *__restrict__ d_x,
+                float *__restrict__ d_b1) {
     extern __shared__ float sm[];
     float *da = sm;            // [L]  da_l, then dlogit_l            (L here = the maximum group length)
     float *al = sm + L;        // [L]  a_l
     float *dw = sm + 2 * L;    // [A]  per-CTA accumulator for d_w2 (additive only)
+    float *db1 = sm + 2 * L + A;   // [A]  per-CTA accumulator for the fc1 bias gradient = column sums of d_hid (optional)
     __shared__ float db_acc;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int F4 = F >> 2;
@@ -80,6 +82,8 @@ pool_bwd_kernel(const float *__restrict__ x, const int *__restrict__ x_rows, con
         for (int j = tid; j < A; j += blockDim.x) dw[j] = 0.f;
         if (tid == 0) db_acc = 0.f;
     }
+    if (d_b1)
+        for (int j = tid; j < A; j += blockDim.x) db1[j] = 0.f;
     __syncthreads();
     const int Lmax = L;
     for (long long r = blockIdx.x; r < R; r += gridDim.x) {
@@ -111,7 +115,7 @@ pool_bwd_kernel(const float *__restrict__ x, const int *__restrict__ x_rows, con
         const float *wv = kPers ? qh + (r / rows_per_query) * A : w2;
         for (int j = tid; j < A; j += blockDim.x) {
             const float w = wv[j];
-            float gw = 0.f;
+            float gw = 0.f, gb = 0.f;
             // four rows per iteration with the loads hoisted (rows with dlogit 0 — padding — still write 0, branch-free)
             int l = 0;
             for (; l + 4 <= L; l += 4) {
@@ -119,17 +123,23 @@ pool_bwd_kernel(const float *__restrict__ x, const int *__restrict__ x_rows, con
                 const float h0 = hid[idx], h1 = hid[idx + A], h2 = hid[idx + 2 * A], h3 = hid[idx + 3 * A];
                 const float d0 = da[l], d1 = da[l + 1], d2 = da[l + 2], d3 = da[l + 3];
                 gw = fmaf(d0, h0, gw); gw = fmaf(d1, h1, gw); gw = fmaf(d2, h2, gw); gw = fmaf(d3, h3, gw);
-                d_hid[idx] = d0 * w * (1.f - h0 * h0);
-                d_hid[idx + A] = d1 * w * (1.f - h1 * h1);
-                d_hid[idx + 2 * A] = d2 * w * (1.f - h2 * h2);
-                d_hid[idx + 3 * A] = d3 * w * (1.f - h3 * h3);
+                const float g0 = d0 * w * (1.f - h0 * h0), g1 = d1 * w * (1.f - h1 * h1);
+                const float g2 = d2 * w * (1.f - h2 * h2), g3 = d3 * w * (1.f - h3 * h3);
+                d_hid[idx] = g0;
+                d_hid[idx + A] = g1;
+                d_hid[idx + 2 * A] = g2;
+                d_hid[idx + 3 * A] = g3;
+                gb += (g0 + g1) + (g2 + g3);
             }
             for (; l < L; ++l) {
                 const long long idx = (base + l) * A + j;
                 const float dl = da[l], h = hid[idx];
                 gw = fmaf(dl, h, gw);
-                d_hid[idx] = dl * w * (1.f - h * h);
+                const float g0 = dl * w * (1.f - h * h);
+                d_hid[idx] = g0;
+                gb += g0;
             }
+            if (d_b1) db1[j] += gb;
             if (kPers) atomicAdd(d_qh + (r / rows_per_query) * A + j, gw);
             else dw[j] += gw;
         }
@@ -152,6 +162,8 @@ pool_bwd_kernel(const float *__restrict__ x, const int *__restrict__ x_rows, con
         for (int j = tid; j < A; j += blockDim.x) atomicAdd(d_w2 + j, dw[j]);
         if (tid == 0) atomicAdd(d_b2, db_acc);
     }
+    if (d_b1)
+        for (int j = tid; j < A; j += blockDim.x) atomicAdd(d_b1 + j, db1[j]);
     // ragged groups listed in a padded row buffer (TitlePlan): the rows past the last group belong to no title; their
     // gradient is exactly 0 and is written here so that the weight-gradient GEMM / column sum can run over all n_rows
     if (seg && n_rows > 0) {
@@ -563,14 +575,14 @@ extern "C" int xnrs_addpool_fwd(const float *x, const int *x_rows, const float *
 extern "C" int xnrs_addpool_bwd(const float *x, const int *x_rows, const float *mask, const float *hid,
                                 const float *w2, const float *attn, const float *d_pooled, const float *d_attn,
                                 const int *seg, long long R, int L, int F, int A, long long n_rows, float *d_hid, float *d_w2,
-                                float *d_b2, float *d_x, xnrs_stream_t st) {
+                                float *d_b2, float *d_x, float *d_b1, xnrs_stream_t st) {
     (void)mask;   // the mask is already folded into attn (masked rows have weight exactly 0)
     if (int e = check_pool(R, L, F, A, x)) return e;
     if (R == 0) return XNRS_OK;
     XNRS_REQUIRE(x && hid && w2 && attn && d_pooled && d_hid && d_w2 && d_b2, "null pointer");
     XNRS_REQUIRE(!(d_x && x_rows), "d_x is only defined for dense x");
-    pool_bwd_kernel<false><<<pool_grid(R), POOL_THREADS, (2 * L + A) * sizeof(float), STREAM(st)>>>(
-            x, x_rows, hid, w2, nullptr, 1, attn, d_pooled, d_attn, seg, R, L, F, A, n_rows, d_hid, d_w2, d_b2, nullptr, d_x);
+    pool_bwd_kernel<false><<<pool_grid(R), POOL_THREADS, (2 * L + 2 * A) * sizeof(float), STREAM(st)>>>(
+            x, x_rows, hid, w2, nullptr, 1, attn, d_pooled, d_attn, seg, R, L, F, A, n_rows, d_hid, d_w2, d_b2, nullptr, d_x, d_b1);
     XNRS_LAUNCHED();
     return XNRS_OK;
 }
@@ -600,9 +612,9 @@ extern "C" int xnrs_perspool_bwd(const float *x, const int *x_rows, const float 
     if (R == 0) return XNRS_OK;
     XNRS_REQUIRE(x && hid && qh && attn && d_pooled && d_hid && d_qh && rows_per_query > 0, "null pointer");
     XNRS_REQUIRE(!(d_x && x_rows), "d_x is only defined for dense x");
-    pool_bwd_kernel<true><<<pool_grid(R), POOL_THREADS, (2 * L + A) * sizeof(float), STREAM(st)>>>(
+    pool_bwd_kernel<true><<<pool_grid(R), POOL_THREADS, (2 * L + 2 * A) * sizeof(float), STREAM(st)>>>(
             x, x_rows, hid, nullptr, qh, rows_per_query, attn, d_pooled, nullptr, seg, R, L, F, A, n_rows, d_hid, nullptr,
-            nullptr, d_qh, d_x);
+            nullptr, d_qh, d_x, nullptr);
     XNRS_LAUNCHED();
     return XNRS_OK;
 }

@@ -35,6 +35,17 @@ constexpr int MAX_STAGES = 6;
 constexpr long long KCHUNK = 2048;   // longest K run accumulated inside the tensor core: its fp32 accumulation truncates, so the
                                      // error grows ~linearly with K; longer reductions are split and summed with IEEE fp32 atomics
 
+// fused additive-attention pooling epilogue of the CTA-pair kernel (xnrs_titlepool_fwd): with hid = tanh(x W1^T + b1) in
+// TMEM, logit = <hid, w2> + b2, e = exp(logit), and per title sum(e) and sum(e * x) are accumulated — layers.py:60-65
+struct PoolArgs {
+    const float *w2, *b2;   // fc2 weight (N = 256 hidden units) and bias
+    const int *tix;         // title of each row (M entries), -1 for padding rows
+    float *e;               // (M) un-normalised pooling weights exp(logit)
+    float *zsum;            // (R) += sum of e over the title's rows
+    float *pooled;          // (R, F) += sum of e * x row
+    int F4;                 // x row width in float4 (= K / 4)
+};
+
 struct TcArgs {
     long long M, N, K;
     float *C; long long ldc;
@@ -47,6 +58,7 @@ struct TcArgs {
     const float *A; long long lda;      // raw operand pointers for that warp
     const float *B; long long ldb;
     int passes;             // 3 (TF32X3) or 1 (TF32)
+    PoolArgs pool;
     int stages;
     long long tiles_m, tiles_n;
 };
@@ -169,21 +181,21 @@ __device__ __forceinline__ float tanh_fast(float x) {
 // epilogue math + global traffic happens in the transposed layout: lane = (row 4i + l/8, columns 4(l%8)..+3), i.e.
 // 4 rows x 128 contiguous bytes per instruction for C, bias, the ReLU mask and the accumulate read.
 template <int ACT>
-__device__ __forceinline__ void epi_rows(uint32_t stage, const TcArgs &p, long long row0, long long col0, long long split,
-                                         int lane, bool vec_ok, bool bias_vec) {
+__device__ __forceinline__ void epi_rows(uint32_t stage, const TcArgs &p, const float *bias, long long row0, long long col0,
+                                         long long split, int lane, bool vec_ok, bool bias_vec) {
     const int sub = lane >> 3, ch = lane & 7;
     const long long col = col0 + 4 * ch;
     if (col >= p.N) return;
     const int nv = (int)min((long long)4, p.N - col);
     float b[4] = {0.f, 0.f, 0.f, 0.f};
-    if (p.bias && (p.split_k == 1 || split == 0)) {
+    if (bias && (p.split_k == 1 || split == 0)) {
         if (bias_vec && nv == 4) {
-            const float4 t = __ldg(reinterpret_cast<const float4 *>(p.bias + col));
+            const float4 t = __ldg(reinterpret_cast<const float4 *>(bias + col));
             b[0] = t.x; b[1] = t.y; b[2] = t.z; b[3] = t.w;
         } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e)
-                if (e < nv) b[e] = __ldg(p.bias + col + e);
+                if (e < nv) b[e] = __ldg(bias + col + e);
         }
     }
 #pragma unroll
@@ -232,16 +244,16 @@ __device__ __forceinline__ void epi_rows(uint32_t stage, const TcArgs &p, long l
 
 // r: lane l holds columns [col0, col0+32) of row row0 + l (raw accumulators); stage: this warp's 4 KB staging buffer
 __device__ __forceinline__ void epi_block32(float (&r)[32], uint32_t stage, const TcArgs &p, long long row0, long long col0,
-                                            long long split, int lane, bool vec_ok, bool bias_vec) {
+                                            long long split, int lane, bool vec_ok, bool bias_vec, int act, const float *bias) {
 #pragma unroll
     for (int c = 0; c < 8; ++c)
         sts128(stage + lane * 128 + ((c ^ (lane & 7)) << 4), make_float4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]));
     __syncwarp();
-    switch (p.act) {
-        case XNRS_ACT_RELU: epi_rows<XNRS_ACT_RELU>(stage, p, row0, col0, split, lane, vec_ok, bias_vec); break;
-        case XNRS_ACT_TANH: epi_rows<XNRS_ACT_TANH>(stage, p, row0, col0, split, lane, vec_ok, bias_vec); break;
-        case XNRS_ACT_RELU_MASK: epi_rows<XNRS_ACT_RELU_MASK>(stage, p, row0, col0, split, lane, vec_ok, bias_vec); break;
-        default: epi_rows<XNRS_ACT_NONE>(stage, p, row0, col0, split, lane, vec_ok, bias_vec); break;
+    switch (act) {
+        case XNRS_ACT_RELU: epi_rows<XNRS_ACT_RELU>(stage, p, bias, row0, col0, split, lane, vec_ok, bias_vec); break;
+        case XNRS_ACT_TANH: epi_rows<XNRS_ACT_TANH>(stage, p, bias, row0, col0, split, lane, vec_ok, bias_vec); break;
+        case XNRS_ACT_RELU_MASK: epi_rows<XNRS_ACT_RELU_MASK>(stage, p, bias, row0, col0, split, lane, vec_ok, bias_vec); break;
+        default: epi_rows<XNRS_ACT_NONE>(stage, p, bias, row0, col0, split, lane, vec_ok, bias_vec); break;
     }
     __syncwarp();
 }
@@ -457,7 +469,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     for (int j = 0; j < 32; ++j) r[j] += corr[j];
                 }
                 if (m0 + 32 * q >= p.M || n0 + c * 32 >= p.N) continue;        // warp-uniform
-                epi_block32(r, epi_stage, p, m0 + 32 * q, n0 + c * 32, split, lane, vec_ok, bias_vec);
+                epi_block32(r, epi_stage, p, m0 + 32 * q, n0 + c * 32, split, lane, vec_ok, bias_vec, p.act, p.bias);
             }
             tc_fence_before();
             mbar_arrive(&tempty_bar[acc.stage]);
@@ -531,6 +543,7 @@ constexpr int T2N = 256;       // tile columns of the pair
 constexpr int TC2_THREADS = 640;       // CTA-pair kernel: {TMA, MMA, relay, -} | 8 splitter warps | 8 epilogue warps
 constexpr int EPI2_WARP0 = 4 + SPLIT_WARPS, EPI2_WARPS = 8;
 
+template <bool POOL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcArgs p) {
     constexpr int TILE = TBM * TBK * 4, HALF = 2 * TILE;          // per CTA: [A hi][B-half hi] | [A lo][B-half lo]
@@ -569,7 +582,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
-
     const long long tiles_mn = p.tiles_m * p.tiles_n;
     const long long total = tiles_mn * p.split_k;
     const long long pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
@@ -799,6 +811,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             const long long m0 = (mn / p.tiles_n) * 256 + 128 * rank, n0 = (mn % p.tiles_n) * T2N + 128 * colhalf;
             mbar_wait(&tfull_bar[acc.stage], acc.phase);
             tc_fence_after();
+            float lp = 0.f;             // POOL: this lane's row, partial logit over this warp's 128 hidden units
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
                 float r[32];
@@ -811,12 +824,89 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     for (int j = 0; j < 32; ++j) r[j] += corr[j];
                 }
                 if (m0 + 32 * q >= p.M || n0 + c * 32 >= p.N) continue;        // warp-uniform
-                epi_block32(r, epi_stage, p, m0 + 32 * q, n0 + c * 32, split, lane, vec_ok, bias_vec);
+                if (POOL) {             // bias + tanh + <., w2> in the row-per-lane layout, then the plain coalesced store of hid
+                    // (fc1 bias / fc2 weight: warp-uniform L1-resident loads — the 227 KB of shared memory are spoken for)
+                    const float *b1s = p.bias + n0 + c * 32, *w2s = p.pool.w2 + n0 + c * 32;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float h = tanh_fast(r[j] + __ldg(b1s + j));
+                        lp = fmaf(h, __ldg(w2s + j), lp);
+                        r[j] = h;
+                    }
+                    epi_block32(r, epi_stage, p, m0 + 32 * q, n0 + c * 32, split, lane, vec_ok, bias_vec, XNRS_ACT_NONE, nullptr);
+                } else {
+                    epi_block32(r, epi_stage, p, m0 + 32 * q, n0 + c * 32, split, lane, vec_ok, bias_vec, p.act, p.bias);
+                }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(tempty0 + 8 * acc.stage);
             acc.advance(acc_stages);
+            if (POOL) {
+                // TMEM is released: the next tile's MMAs run while the pooling weights and weighted sums are formed
+                // scratch lives in the epilogue warps' own (now idle) staging buffers: warp we keeps its 32 partial logits in
+                // floats [0,32) of its buffer, the column-half-0 warps keep e of their 32 rows in floats [32,64) of theirs
+                auto stagef = [&](int we) { return reinterpret_cast<float *>(smem + SMEM_DATA + we * 4096); };
+                const int we = warp - EPI2_WARP0;              // = 4 * colhalf + q
+                stagef(we)[lane] = lp;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (colhalf == 0) {
+                    const long long g = m0 + 32 * q + lane;
+                    float e = 0.f;
+                    if (g < p.M) {
+                        if (__ldg(p.pool.tix + g) >= 0) e = expf(stagef(q)[lane] + stagef(4 + q)[lane] + __ldg(p.pool.b2));
+                        p.pool.e[g] = e;
+                    }
+                    stagef(q)[32 + lane] = e;
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                // weighted sum: warp w8 owns rows [16 w8, +16) of this CTA's 128; the x rows were fetched from the table
+                // moments ago (L2 hits); a title's partial sums leave through 16-byte vector reductions
+                const int w8 = warp - EPI2_WARP0, F4 = p.pool.F4, nq = F4 >> 5;
+                const float4 *x4 = reinterpret_cast<const float4 *>(p.A);
+                float4 *pool4 = reinterpret_cast<float4 *>(p.pool.pooled);
+                const long long ld4 = p.lda >> 2;
+                float4 accv[6];          // F <= 768
+                float zs = 0.f;
+                int cur = -1;
+                auto flush = [&]() {
+                    if (cur >= 0) {
+#pragma unroll
+                        for (int cq = 0; cq < 6; ++cq)
+                            if (cq < nq) atomicAdd(pool4 + (long long)cur * F4 + lane + 32 * cq, accv[cq]);
+                        if (lane == 0) atomicAdd(p.pool.zsum + cur, zs);
+                    }
+                };
+#pragma unroll 1
+                for (int i = 0; i < 16; ++i) {
+                    const int row = 16 * w8 + i;
+                    const long long g = m0 + row;
+                    const int ti = g < p.M ? __ldg(p.pool.tix + g) : -1;
+                    if (ti != cur) {
+                        flush();
+                        cur = ti;
+                        zs = 0.f;
+#pragma unroll
+                        for (int cq = 0; cq < 6; ++cq) accv[cq] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    if (ti >= 0) {
+                        const float e = stagef(row >> 5)[32 + (row & 31)];
+                        const long long src = p.a_gather ? (long long)__ldg(p.a_gather + g) : g;
+                        const float4 *xr = x4 + src * ld4 + lane;
+                        zs += e;
+#pragma unroll
+                        for (int cq = 0; cq < 6; ++cq) {
+                            if (cq < nq) {
+                                const float4 v = __ldg(xr + 32 * cq);
+                                accv[cq].x = fmaf(e, v.x, accv[cq].x); accv[cq].y = fmaf(e, v.y, accv[cq].y);
+                                accv[cq].z = fmaf(e, v.z, accv[cq].z); accv[cq].w = fmaf(e, v.w, accv[cq].w);
+                            }
+                        }
+                    }
+                }
+                flush();
+                asm volatile("bar.sync 1, 256;" ::: "memory");     // the staging buffers are reused by the next tile's stores
+            }
         }
     }
 
@@ -956,7 +1046,7 @@ int gemm_tensorcore(const GemmArgs &a, int precision, cudaStream_t st, int *stat
     if (!attr_set) {
         if (cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess ||
             cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess ||
-            cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) {
+            cudaFuncSetAttribute(gemm_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) {
             cudaGetLastError();
             return 0;
         }
@@ -969,7 +1059,7 @@ int gemm_tensorcore(const GemmArgs &a, int precision, cudaStream_t st, int *stat
         if (lsu < 0) { const char *e = getenv("XNRS_LSU_GATHER"); lsu = e ? atoi(e) : 1; }
         if (lsu) p.lsu_gather = a.a_rows ? 1 : (a.b_rows ? 2 : 0);
         const long long pairs = total < num_sms() / 2 ? total : num_sms() / 2;
-        gemm_tc2_kernel<<<(unsigned)(2 * pairs), TC2_THREADS, smem_bytes, st>>>(mapA, mapB, p);
+        gemm_tc2_kernel<false><<<(unsigned)(2 * pairs), TC2_THREADS, smem_bytes, st>>>(mapA, mapB, p);
         g_last_gemm_kernel = p.passes == 3 ? "gemm_tc2_kernel (cta_group::2, 256x256 pair tile, 3xTF32)"
                                            : "gemm_tc2_kernel (cta_group::2, 256x256 pair tile, TF32)";
     } else if (BN == 256) {
@@ -990,7 +1080,82 @@ int gemm_tensorcore(const GemmArgs &a, int precision, cudaStream_t st, int *stat
     return 1;
 }
 
+// attn[g] = e[g] / (zsum[title] + 1e-8) (0 on padding rows); pooled[t,:] /= (zsum[t] + 1e-8)   (layers.py:62-65)
+__global__ void titlepool_finalize_kernel(const float *__restrict__ e, const int *__restrict__ tix, const float *__restrict__ zsum,
+                                          long long n_rows, long long R, int F4, float *__restrict__ attn, float *__restrict__ pooled) {
+    const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nt = (long long)gridDim.x * blockDim.x;
+    for (long long g = tid; g < n_rows; g += nt) {
+        const int t = tix[g];
+        attn[g] = t >= 0 ? e[g] / (zsum[t] + 1e-8f) : 0.f;
+    }
+    float4 *p4 = reinterpret_cast<float4 *>(pooled);
+    for (long long i = tid; i < R * F4; i += nt) {
+        const float d = zsum[i / F4] + 1e-8f;
+        float4 v = p4[i];
+        v.x /= d; v.y /= d; v.z /= d; v.w /= d;
+        p4[i] = v;
+    }
+}
+
 }  // namespace xnrs
+
+using namespace xnrs;
+
+// gather -> fc1 (+bias, tanh) -> <., w2> + b2 -> exp -> per-title sum(e), sum(e * x) in ONE launch of the CTA-pair tcgen05
+// kernel (cp.async gather warp + pooling epilogue), then a small normalisation pass.  Returns XNRS_ERR_UNSUPPORTED (nothing
+// launched) for shapes / devices / precisions the fused kernel does not cover; the caller then runs xnrs_gemm + xnrs_addpool_fwd.
+extern "C" int xnrs_titlepool_fwd(const float *x, long long ldx, const int *x_rows, const int *tix, long long n_rows, long long R,
+                                  int F, int A, const float *w1, const float *b1, const float *w2, const float *b2,
+                                  int precision, float *hid, float *e, float *zsum, float *attn, float *pooled,
+                                  xnrs_stream_t st_) {
+    XNRS_REQUIRE(x && tix && w1 && b1 && w2 && b2 && hid && e && zsum && attn && pooled, "null pointer");
+    XNRS_REQUIRE(n_rows >= 0 && R >= 0 && F > 0 && A > 0, "bad sizes");
+    cudaStream_t st = STREAM(st_);
+    static int is_sm100 = -1;
+    if (is_sm100 < 0) is_sm100 = xnrs_device_is_sm100();
+    if (!is_sm100 || (precision != XNRS_PREC_TF32X3 && precision != XNRS_PREC_TF32) || A != 256 || F % 128 || F > 768 ||
+        n_rows < 256 || ldx % 4 || ((uintptr_t)x & 15) || ((uintptr_t)w1 & 15) || ((uintptr_t)hid & 15) || ((uintptr_t)pooled & 15) ||
+        num_sms() % 2)
+        return fail(XNRS_ERR_UNSUPPORTED, "%s: shape / device / precision not covered by the fused kernel", "xnrs_titlepool_fwd");
+    TcArgs p;
+    memset(&p, 0, sizeof(p));
+    p.M = n_rows; p.N = A; p.K = F;
+    p.C = hid; p.ldc = A; p.bias = b1; p.act = XNRS_ACT_TANH; p.aux = nullptr; p.accumulate = 0;
+    p.split_k = 1; p.k_per_split = cdiv(F, TBK) * TBK;
+    p.a_mn = 0; p.b_mn = 0;
+    p.a_gather = x_rows; p.b_gather = nullptr;
+    p.A = x; p.lda = ldx; p.B = w1; p.ldb = F;
+    p.lsu_gather = x_rows ? 1 : 0;
+    p.passes = precision == XNRS_PREC_TF32X3 ? 3 : 1;
+    p.pool.w2 = w2; p.pool.b2 = b2; p.pool.tix = tix; p.pool.e = e; p.pool.zsum = zsum; p.pool.pooled = pooled; p.pool.F4 = F / 4;
+    const int half = 2 * TBM * TBK * 4;
+    p.stages = SMEM_DATA / (half * (p.passes == 3 ? 2 : 1));
+    if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+    p.tiles_m = cdiv(n_rows, 256); p.tiles_n = 1;
+    CUtensorMap mapA, mapB;
+    bool ok = make_map(&mapA, x, F, x_rows ? 0x7fffffffLL : n_rows, ldx, x_rows ? 1 : TBM, false) && make_map(&mapB, w1, F, A, F, 128, false);
+    if (!ok) return fail(XNRS_ERR_UNSUPPORTED, "%s: tensor map encoding failed", "xnrs_titlepool_fwd");
+    const int smem_bytes = SMEM_DATA + SMEM_EPI + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(gemm_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(XNRS_ERR_UNSUPPORTED, "%s: cannot reserve shared memory", "xnrs_titlepool_fwd");
+        }
+        attr_set = true;
+    }
+    if (cudaMemsetAsync(pooled, 0, (size_t)R * F * sizeof(float), st) != cudaSuccess ||
+        cudaMemsetAsync(zsum, 0, (size_t)R * sizeof(float), st) != cudaSuccess)
+        return fail(XNRS_ERR_CUDA, "%s: memset failed", "xnrs_titlepool_fwd");
+    const long long pairs = std::min<long long>(p.tiles_m, num_sms() / 2);
+    gemm_tc2_kernel<true><<<(unsigned)(2 * pairs), TC2_THREADS, smem_bytes, st>>>(mapA, mapB, p);
+    XNRS_LAUNCHED();
+    const long long work = std::max<long long>(n_rows, R * (F / 4));
+    long long blocks = cdiv(work, 256), cap = 8LL * num_sms();
+    titlepool_finalize_kernel<<<(unsigned)std::max<long long>(1, std::min(blocks, cap)), 256, 0, st>>>(e, tix, zsum, n_rows, R, F / 4, attn, pooled);
+    XNRS_LAUNCHED();
+    return XNRS_OK;
+}
 
 extern "C" int xnrs_set_option(const char *name, int value) {
     if (name && !strcmp(name, "gemm_2cta")) {

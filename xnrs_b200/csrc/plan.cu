@@ -132,7 +132,8 @@ plan_scan_lens_kernel(const int *__restrict__ lens, long long cap, const int *__
 
 // one warp per article: its real tokens, in title order, to rows[seg[u] ...); then rows [T, T + pad) = token 0 (the zero row)
 __global__ void plan_rows_kernel(const int *__restrict__ title_tokens, long long n_news, int S, const int *__restrict__ uniq,
-                                 long long cap, const int *__restrict__ seg, long long rows_cap, int pad, int *__restrict__ rows) {
+                                 long long cap, const int *__restrict__ seg, long long rows_cap, int pad, int *__restrict__ rows,
+                                 int *__restrict__ tix) {
     const int lane = threadIdx.x & 31;
     const long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5, nw = ((long long)gridDim.x * blockDim.x) >> 5;
     for (long long u = w; u < cap; u += nw) {
@@ -144,14 +145,21 @@ __global__ void plan_rows_kernel(const int *__restrict__ title_tokens, long long
             const int s = s0 + lane;
             const int tok = s < S ? t[s] : 0;
             const unsigned m = __ballot_sync(0xffffffffu, tok != 0);
-            if (tok != 0) rows[out + __popc(m & ((1u << lane) - 1u))] = tok;
+            if (tok != 0) {
+                const int o = out + __popc(m & ((1u << lane) - 1u));
+                rows[o] = tok;
+                if (tix) tix[o] = (int)u;
+            }
             out += __popc(m);
         }
     }
     const long long T = seg[cap];
     for (long long i = T + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < T + pad && i < rows_cap;
          i += (long long)gridDim.x * blockDim.x)
+    {
         rows[i] = 0;
+        if (tix) tix[i] = -1;
+    }
 }
 
 static unsigned ew_blocks(long long n, int threads) {
@@ -187,7 +195,7 @@ extern "C" int xnrs_plan_dedup(const int *ids, long long n, long long n_news, in
 }
 
 extern "C" int xnrs_plan_ragged(const int *title_tokens, long long n_news, int S, const int *uniq, long long cap,
-                                const int *u_count, int pad_rows, int *lens, int *seg, int *rows, long long rows_cap,
+                                const int *u_count, int pad_rows, int *lens, int *seg, int *rows, int *tix, long long rows_cap,
                                 float *cm, int *counts, xnrs_stream_t st) {
     XNRS_REQUIRE(cap > 0 && n_news > 0 && S > 0 && pad_rows >= 0, "bad sizes");
     XNRS_REQUIRE(title_tokens && uniq && lens && seg && rows && cm && counts, "null pointer");
@@ -197,7 +205,7 @@ extern "C" int xnrs_plan_ragged(const int *title_tokens, long long n_news, int S
     XNRS_LAUNCHED();
     plan_scan_lens_kernel<<<1, SCAN_T, 0, s>>>(lens, cap, u_count, seg, counts);
     XNRS_LAUNCHED();
-    plan_rows_kernel<<<ew_blocks(cap * 32, 256), 256, 0, s>>>(title_tokens, n_news, S, uniq, cap, seg, rows_cap, pad_rows, rows);
+    plan_rows_kernel<<<ew_blocks(cap * 32, 256), 256, 0, s>>>(title_tokens, n_news, S, uniq, cap, seg, rows_cap, pad_rows, rows, tix);
     XNRS_LAUNCHED();
     return XNRS_OK;
 }

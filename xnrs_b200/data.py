@@ -88,6 +88,7 @@ class TitlePlan:
     cm: torch.Tensor
     ragged: bool
     dedup: bool
+    tix: 'torch.Tensor | None' = None  # ragged: (T',) int32 title of each token row, -1 on the padding rows
     event: 'torch.cuda.Event | None' = None
     seq_len: int = 0
     n_titles: int = -1                 # U after acquire() (exact count), n_rows: T
@@ -95,7 +96,7 @@ class TitlePlan:
     _counts: 'tuple | None' = None     # (device counts, pinned host copy or None, event or None) until acquire()
 
     def tensors(self):
-        return [t for t in (self.uniq, self.inv, self.rows, self.seg, self.mask, self.cm) if t is not None]
+        return [t for t in (self.uniq, self.inv, self.rows, self.seg, self.mask, self.cm, self.tix) if t is not None]
 
     def acquire(self):
         """make the plan usable on the current stream and cut the padded arrays at the (rounded) counts"""
@@ -123,7 +124,7 @@ class TitlePlan:
             if self.ragged:
                 self.n_rows = T
                 t_cap = min(self.rows.numel(), -(-max(T, 1) // T_GRANULE) * T_GRANULE)
-                self.rows, self.seg = self.rows[:t_cap], self.seg[:u_cap + 1]
+                self.rows, self.seg, self.tix = self.rows[:t_cap], self.seg[:u_cap + 1], self.tix[:t_cap]
             else:
                 self.n_rows = u_cap * self.seq_len
                 self.rows, self.mask = self.rows[:u_cap * self.seq_len], self.mask[:u_cap * self.seq_len]
@@ -146,15 +147,16 @@ def plan_titles(store: TitleStore, ids_flat: torch.Tensor, dedup: bool, ragged: 
     if ragged:
         rows_cap = n * S + T_GRANULE
         lens, seg, rows = torch.empty(n, **i32), torch.empty(n + 1, **i32), torch.empty(rows_cap, **i32)
+        tix = torch.empty(rows_cap, **i32)
         cm = torch.empty(n, device=dev, dtype=torch.float32)
         K.call('xnrs_plan_ragged', store.title_tokens, n_news, S, uniq, n, counts if dedup else None, T_GRANULE, lens, seg,
-               rows, rows_cap, cm, counts)
+               rows, tix, rows_cap, cm, counts)
         mask = None
     else:
         rows, mask = K.expand_titles(store.title_tokens, uniq)               # over the capacity: padded titles are article 0
         cm = K.collapse_mask(mask, n, S)
-        seg = None
-    plan = TitlePlan(uniq, inv, rows, seg, mask, cm, ragged, dedup, seq_len=S)
+        seg = tix = None
+    plan = TitlePlan(uniq, inv, rows, seg, mask, cm, ragged, dedup, tix=tix, seq_len=S)
     if not dedup and not ragged:
         plan._counts = None
         plan.n_titles, plan.n_rows = n, n * S

@@ -348,18 +348,34 @@ class Mlp2Fn(torch.autograd.Function):
         return dx, dw1, db1, dw2, db2
 
 
+FUSED_TITLEPOOL = bool(int(__import__('os').environ.get('XNRS_FUSED_TITLEPOOL', '1')))
+
+
 class AdditivePoolFn(torch.autograd.Function):
     """layers.AdditiveAttention (layers.py:47-69) over R groups of L rows: -> pooled (R,F), attn (R,L)."""
 
     @staticmethod
-    def forward(ctx, x, rows, mask, w1, b1, w2, b2, R, L, seg=None):
-        """seg (R+1 int32, optional): ragged groups — group r owns rows [seg[r], seg[r+1]); L = longest group"""
+    def forward(ctx, x, rows, mask, w1, b1, w2, b2, R, L, seg=None, tix=None):
+        """seg (R+1 int32, optional): ragged groups — group r owns rows [seg[r], seg[r+1]); L = longest group.
+        tix (optional, with seg): the group of each row (-1: padding row) — enables the ONE-launch fused forward
+        (xnrs_titlepool_fwd: gather -> fc1 -> tanh -> logit -> exp -> per-title sums on the tensor-core kernel)."""
         F_, A = x.shape[1], w1.shape[0]
         x, rows = _resolve_rows(x, rows)
-        hid = gemm(x, w1, trans_b=True, bias=b1, act=ACT_TANH, a_rows=rows)
-        attn = torch.empty((R, L) if seg is None else (hid.shape[0],), device=x.device, dtype=torch.float32)
+        n_rows = rows.numel() if rows is not None else x.shape[0]
+        fused = (FUSED_TITLEPOOL and tix is not None and seg is not None and mask is None and _precision in (1, 2)
+                 and A == 256 and F_ % 128 == 0 and F_ <= 768 and n_rows >= FUSED_GATHER_MIN_ROWS and x.stride(0) % 4 == 0)
         pooled = torch.empty((R, F_), device=x.device, dtype=torch.float32)
-        call('xnrs_addpool_fwd', x, rows, mask, hid, w2.reshape(-1), b2, seg, R, L, F_, A, attn, pooled)
+        if fused:
+            hid = torch.empty((n_rows, A), device=x.device, dtype=torch.float32)
+            attn = torch.empty(n_rows, device=x.device, dtype=torch.float32)
+            e = torch.empty(n_rows, device=x.device, dtype=torch.float32)
+            zsum = torch.empty(R, device=x.device, dtype=torch.float32)
+            call('xnrs_titlepool_fwd', _mat(x), x.stride(0), rows, tix, n_rows, R, F_, A, w1, b1, w2.reshape(-1), b2,
+                 _precision, hid, e, zsum, attn, pooled)
+        else:
+            hid = gemm(x, w1, trans_b=True, bias=b1, act=ACT_TANH, a_rows=rows)
+            attn = torch.empty((R, L) if seg is None else (hid.shape[0],), device=x.device, dtype=torch.float32)
+            call('xnrs_addpool_fwd', x, rows, mask, hid, w2.reshape(-1), b2, seg, R, L, F_, A, attn, pooled)
         ctx.save_for_backward(x, rows, w1, w2, hid, attn, seg)
         ctx.dims = (R, L, F_, A)
         ctx.bias_params = (b1, b2)
@@ -376,17 +392,17 @@ class AdditivePoolFn(torch.autograd.Function):
         b1, b2 = ctx.bias_params
         w2_buf, d_w2 = _wgrad_buffer(w2, w2)
         b2_buf, d_b2 = _wgrad_buffer(b2, b2)
+        b1_buf, d_b1 = _wgrad_buffer(b1, b1)            # fc1 bias gradient = column sums of d_hid, fused into the kernel
         need_dx = _need(ctx, 0)
         if need_dx and rows is not None:
             raise RuntimeError('no gradient flows into a gathered (frozen) table')
         d_x = torch.empty_like(x) if need_dx else None
         call('xnrs_addpool_bwd', x, rows, None, hid, w2.reshape(-1), attn, d_pooled, d_attn, seg, R, L, F_, A, hid.shape[0], d_hid,
-             w2_buf.view(-1), b2_buf.view(-1), d_x)
+             w2_buf.view(-1), b2_buf.view(-1), d_x, b1_buf.view(-1))
         d_w1 = _wgrad_gemm(w1, d_hid, x, b_rows=rows)
-        d_b1 = _wgrad_colsum(b1, d_hid)
         if need_dx:
             gemm(d_hid, w1, out=d_x, accumulate=True)
-        return d_x, None, None, d_w1, d_b1, d_w2, d_b2, None, None, None
+        return d_x, None, None, d_w1, d_b1, d_w2, d_b2, None, None, None, None
 
 
 class ItemLogitPoolFn(torch.autograd.Function):

@@ -57,10 +57,11 @@ class AdditiveAttention(nn.Module):
         self.fc1 = nn.Linear(in_features, hidden_features)
         self.fc2 = nn.Linear(hidden_features, 1)
 
-    def pool(self, x2: torch.Tensor, rows, mask, R: int, L: int, seg=None):
-        """(R*L, F) rows (or table + row index) -> pooled (R, F), weights (R, L); seg: ragged group offsets (R+1)"""
+    def pool(self, x2: torch.Tensor, rows, mask, R: int, L: int, seg=None, tix=None):
+        """(R*L, F) rows (or table + row index) -> pooled (R, F), weights (R, L); seg: ragged group offsets (R+1);
+        tix: group of each row (TitlePlan) — lets large ragged problems take the one-launch fused forward"""
         return K.AdditivePoolFn.apply(x2, rows, mask, self.fc1.weight, self.fc1.bias,
-                                      self.fc2.weight, self.fc2.bias, R, L, seg)
+                                      self.fc2.weight, self.fc2.bias, R, L, seg, tix)
 
     def forward(self, x: torch.Tensor, m: torch.Tensor = None, return_weights: bool = False):
         x2, R, L = _flat_rows(x)
@@ -173,10 +174,13 @@ class TextEncoder(nn.Module):
                                       nn.Linear(out_features, out_features, bias=bias))
         self.out_dim = out_features
 
-    def _encode(self, x2, rows, mask, R: int, S: int, seg=None):
+    def _encode(self, x2, rows, mask, R: int, S: int, seg=None, tix=None):
         if self.att is not None:
             x2, rows = self.att.attend(x2, rows, mask, R, S), None
-        pooled, _ = self.pooler.pool(x2, rows, mask, R, S, seg)
+        if tix is not None and isinstance(self.pooler, AdditiveAttention):
+            pooled, _ = self.pooler.pool(x2, rows, mask, R, S, seg, tix)
+        else:
+            pooled, _ = self.pooler.pool(x2, rows, mask, R, S, seg)
         return _apply_head(self.head, pooled) if hasattr(self, 'head') else pooled
 
     def plan_kind(self, n_slots: int, distinct: bool = False):
@@ -200,7 +204,7 @@ class TextEncoder(nn.Module):
             plan = plan_titles(store, inpt.news_ids.to(device).reshape(-1), dedup, ragged)
         plan.acquire()
         nu = plan.uniq.numel()
-        e_u = self._encode(store.token_table, plan.rows, plan.mask, nu, S, plan.seg)
+        e_u = self._encode(store.token_table, plan.rows, plan.mask, nu, S, plan.seg, plan.tix)
         return e_u, plan.inv, plan.cm
 
     def forward(self, inpt):

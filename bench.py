@@ -505,10 +505,13 @@ def train_workload(ctx, args, model_key, want_cpu=True, want_eager=False):
     K.set_event_hook(None)
     fb0 = int(_lib.lib().xnrs_gemm_simt_fallbacks())
     # (b) without hooks: `value`
-    n0 = K.launch_count()
+    n0 = K.launch_count() + (stepper.replayed_kernels if stepper else 0)
+    g0 = stepper.replays if stepper else 0
     with ClockSampler(ctx.local) as clocks:
         ms_list = ctx.timed_regions(region_resident)
-    launches = (K.launch_count() - n0) // len(ms_list)
+    # kernels of this library EXECUTED per region: launched one by one + those inside replayed CUDA graphs
+    launches = (K.launch_count() + (stepper.replayed_kernels if stepper else 0) - n0) // len(ms_list)
+    graph_launches = ((stepper.replays - g0) // len(ms_list)) if stepper else 0
     fallbacks = (int(_lib.lib().xnrs_gemm_simt_fallbacks()) - fb0) // len(ms_list)
     ms_med, sp = spread(ms_list, B * world * steps)
     value = B * world * steps / (ms_med * 1e-3)
@@ -556,8 +559,8 @@ def train_workload(ctx, args, model_key, want_cpu=True, want_eager=False):
                    'l2': 'inputs larger than L2: 307 MB token table, ~0.5 GB of gathered rows per step, 8 batches cycled',
                    'precision': args.precision, 'final_loss': last[0],
                    'dedup_titles': not args.no_dedup, 'skip_padding': not args.no_skip_padding,
-                   'cuda_graph': ({'replays': stepper.replays, 'captures': stepper.captures, 'eager_steps': stepper.eager_steps,
-                                   'shape_buckets': len(stepper.graphs)} if stepper else False),
+                   'cuda_graph': ({'graph_launches_per_region': graph_launches, 'replays': stepper.replays, 'captures': stepper.captures,
+                                   'eager_steps': stepper.eager_steps, 'shape_buckets': len(stepper.graphs)} if stepper else False),
                    'timing': f'median of {sp["regions"]} regions of exactly {steps} steps ({sp["timed_s"]} s measured)'},
         'spread': sp,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4,

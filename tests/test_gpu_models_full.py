@@ -285,7 +285,14 @@ def test_cuda_graph_replay_equals_eager_steps(monkeypatch):
                 dp.prefetch(batch)                      # both the prefetched and the in-line plan reach the graph
             out = stepper.step(batch) if graphed else dp.train_step(batch)
             losses.append(float(out['loss']))
-        runs.append((losses, trainer.optimizer.flat_p.clone()))
+        # Adam turns the rounding noise of analytically-zero gradients (a pooler's fc2.bias: the normalised weights are shift
+        # invariant) into +-lr steps: those scalars are left out of the parameter comparison
+        keep = torch.ones_like(trainer.optimizer.flat_p, dtype=torch.bool)
+        for name, p in model.named_parameters():
+            if name.endswith('pooler.fc2.bias') or name.endswith('dummy_param'):
+                a, b = trainer.optimizer.ranges[id(p)]
+                keep[a:b] = False
+        runs.append((losses, trainer.optimizer.flat_p[keep].clone()))
         if graphed:
             assert stepper.replays >= 6 and stepper.captures >= 1 and stepper.eager_steps <= 4, (stepper.replays, stepper.captures, stepper.eager_steps)
     (l0, p0), (l1, p1) = runs

@@ -109,6 +109,10 @@ __device__ __forceinline__ void tma_gather4(void *dst, const CUtensorMap *map, u
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, int src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+// the mbarrier receives one (pre-counted) arrival once all cp.async copies issued so far by this thread have landed
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t *bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -564,7 +568,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
-            mbar_init(&full_bar[s], p.lsu_gather ? 2 : 1);                    // TMA thread (+ the cp.async gather warp)
+            mbar_init(&full_bar[s], p.lsu_gather ? 33 : 1);                   // TMA thread (+ the 32 lanes of the cp.async gather warp)
             mbar_init(&ready_bar[s], passes == 3 ? 2 * SPLIT_WARPS : 2);      // used in the leader only: one arrival per
             mbar_init(&empty_bar[s], 1);                                       // splitter warp (or relay) of BOTH CTAs
         }
@@ -706,18 +710,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         // GEMMs ran 0.10-0.21 ms slower than gather-then-GEMM); the LSU path issues 512 B per instruction.  One warp copies
         // this CTA's tile of the gathered operand with 16-byte cp.async into exactly the layout TMA would have produced
         // (K-major A: 128-byte rows, 16-byte chunk c of row r stored at chunk c ^ (r & 7); MN-major B: 32-byte units XORed
-        // with k-row & 3 inside each 32-column chunk), keeps stages-1 groups in flight and publishes a stage with
-        // wait_group -> fence.proxy.async -> mbarrier arrive.
+        // with k-row & 3 inside each 32-column chunk).
         if (p.lsu_gather) {
-            StageRing r, done;
-            int inflight = 0;
-            auto publish = [&]() {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&full_bar[done.stage]);
-                done.advance(stages);
-                --inflight;
-            };
+            StageRing r;
             for (long long t = pair; t < total; t += npairs) {
                 const long long split = t / tiles_mn, mn = t - split * tiles_mn;
                 const long long m0 = (mn / p.tiles_n) * 256 + 128 * rank, n0 = (mn % p.tiles_n) * T2N + 128 * rank;
@@ -756,19 +751,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                                        p.B + (nbytes ? (long long)row * p.ldb + col : 0), nbytes);
                         }
                     }
-                    cp_async_commit();
-                    ++inflight;
+                    // asynchronous completion: the stage's full barrier collects one arrival per lane when that lane's
+                    // copies have landed (CUTLASS' sm100 mixed TMA + cp.async mainloop signals the MMA the same way), so
+                    // this warp never waits for data — it runs ahead as far as the empty slots allow
+                    cp_async_arrive_noinc(&full_bar[r.stage]);
                     r.advance(stages);
-                    if (inflight == stages) {           // the oldest group has had stages-1 younger groups issued behind it
-                        if (stages == 3) cp_async_wait<2>();
-                        else if (stages == 6) cp_async_wait<5>();
-                        else cp_async_wait<0>();
-                        publish();
-                    }
                 }
             }
             cp_async_wait<0>();
-            while (inflight > 0) publish();
         }
     } else if (warp < EPI2_WARP0) {
         // ===================== splitters (3xTF32): lo = x - trunc_tf32(x) for this CTA's tiles =====================

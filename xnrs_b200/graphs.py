@@ -47,7 +47,7 @@ class GraphedStep:
         self.seen: Dict[tuple, int] = {}
         self.pool = None
         self.max_graphs = max_graphs
-        self.replays = self.captures = self.eager_steps = 0
+        self.replays = self.captures = self.eager_steps = self.replayed_kernels = 0
 
     # ---- plan of a batch (prefetched or computed here) -----------------------------------------------------------
     def _plan(self, batch):
@@ -122,8 +122,10 @@ class GraphedStep:
             self._arm(g)
             torch.cuda.synchronize()
             counters = (self.tr.optimizer.step_count, self.tr.current_train_step)
+            n0 = K.launch_count()
             with torch.cuda.graph(graph, pool=self.pool):
                 g['out'] = self.dp.train_step(g['batch'])
+            g['kernels'] = K.launch_count() - n0            # this library's kernel nodes in the graph (one replay runs them all)
             self.tr.optimizer.step_count, self.tr.current_train_step = counters     # capturing executed nothing
             if self.pool is None:
                 self.pool = graph.pool()
@@ -131,6 +133,7 @@ class GraphedStep:
             self.captures += 1
         g['graph'].replay()
         self.replays += 1
+        self.replayed_kernels += g['kernels']
         self.tr.optimizer.step_count += 1
         self.tr.current_train_step += 1
         return g['out']

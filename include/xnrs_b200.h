@@ -114,7 +114,7 @@ int xnrs_addpool_bwd(const float *x, const int *x_rows, const float *mask, const
  * epilogue on the TMEM accumulators; the x rows of a tile are re-read from L2 for the weighted sum) plus a small
  * normalisation pass.  x rows are x[g] or table rows x[x_rows[g]] (ldx floats apart); tix (n_rows) = title of each row, -1
  * for padding rows.  Outputs: hid (n_rows, A) = tanh(fc1 x) (saved for the backward), e (n_rows, scratch), zsum (R, scratch),
- * attn (n_rows) and pooled (R, F) exactly as xnrs_addpool_fwd defines them.  Covers A == 256, F % 128 == 0, F <= 768,
+ * attn (n_rows) and pooled (R, F) exactly as xnrs_addpool_fwd defines them.  Covers A == 256, F % 128 == 0, F <= 1024,
  * n_rows >= 256 in the tensor-core precisions on sm_100; otherwise returns XNRS_ERR_UNSUPPORTED with nothing launched and the
  * caller runs xnrs_gemm(TANH) + xnrs_addpool_fwd (the same mathematics in two launches). */
 int xnrs_titlepool_fwd(const float *x, long long ldx, const int *x_rows, const int *tix, long long n_rows, long long R, int F,

@@ -718,12 +718,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 const long long m0 = (mn / p.tiles_n) * 256 + 128 * rank, n0 = (mn % p.tiles_n) * T2N + 128 * rank;
                 const long long kbeg = split * p.k_per_split, kend = min(p.K, kbeg + p.k_per_split);
                 int arow[32];
+                int myrow = -1;                 // B gather: lane l holds the table row of k-row k0 + l, loaded one stage ahead
                 if (p.lsu_gather == 1) {        // lane covers chunk (lane & 7) of rows (lane >> 3) + 4 i
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
                         arow[i] = p.a_gather[min(m0 + (lane >> 3) + 4 * i, p.M - 1)];
+                } else if (kbeg + lane < p.K) {
+                    myrow = p.b_gather[kbeg + lane];
                 }
                 for (long long k0 = kbeg; k0 < kend; k0 += TBK) {
+                    int nextrow = -1;
+                    if (p.lsu_gather == 2 && k0 + TBK < kend && k0 + TBK + lane < p.K) nextrow = p.b_gather[k0 + TBK + lane];
                     if (lane == 0) mbar_wait(&empty_bar[r.stage], r.phase ^ 1);
                     __syncwarp();
                     if (p.lsu_gather == 1) {
@@ -739,8 +744,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     } else {
                         const uint32_t dst = smem_u32(tileB(r.stage));
                         const int c4 = lane >> 3, u = lane & 7;
-                        const long long kmine = k0 + lane;
-                        const int myrow = kmine < p.K ? p.b_gather[kmine] : -1;
                         const long long col = n0 + 32 * c4 + 4 * u;
                         const int cbytes = (int)max(0LL, min(4LL, p.N - col)) * 4;
 #pragma unroll
@@ -756,6 +759,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     // this warp never waits for data — it runs ahead as far as the empty slots allow
                     cp_async_arrive_noinc(&full_bar[r.stage]);
                     r.advance(stages);
+                    myrow = nextrow;
                 }
             }
             cp_async_wait<0>();
@@ -850,51 +854,62 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     stagef(q)[32 + lane] = e;
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");
-                // weighted sum: warp w8 owns rows [16 w8, +16) of this CTA's 128; the x rows were fetched from the table
-                // moments ago (L2 hits); a title's partial sums leave through 16-byte vector reductions
-                const int w8 = warp - EPI2_WARP0, F4 = p.pool.F4, nq = F4 >> 5;
-                const float4 *x4 = reinterpret_cast<const float4 *>(p.A);
-                float4 *pool4 = reinterpret_cast<float4 *>(p.pool.pooled);
+                // weighted sum over this CTA's 128 rows: warp w8 owns a slice of F/8 columns (one float4 per lane, F/32 lanes
+                // active) and walks ALL rows, eight independent row loads in flight; the x rows were fetched from the table
+                // moments ago (L2 hits).  A title's partial sums leave through 16-byte vector reductions when the title ends.
+                const int w8 = warp - EPI2_WARP0, F4 = p.pool.F4, per = F4 >> 3;     // float4 columns per warp (24 at F=768)
+                const bool active = lane < per;
+                const float4 *x4 = reinterpret_cast<const float4 *>(p.A) + (active ? w8 * per + lane : 0);
+                float4 *pool4 = reinterpret_cast<float4 *>(p.pool.pooled) + (active ? w8 * per + lane : 0);
                 const long long ld4 = p.lda >> 2;
-                float4 accv[6];          // F <= 768
+                // lane l keeps title / source row of rows l, l+32, l+64, l+96 (coalesced loads, broadcast by shuffle)
+                int tixv[4], srcv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const long long g = m0 + lane + 32 * j;
+                    tixv[j] = g < p.M ? __ldg(p.pool.tix + g) : -1;
+                    srcv[j] = g < p.M ? (p.a_gather ? __ldg(p.a_gather + g) : (int)g) : 0;
+                }
+                float4 accv = make_float4(0.f, 0.f, 0.f, 0.f);
                 float zs = 0.f;
                 int cur = -1;
-                auto flush = [&]() {
-                    if (cur >= 0) {
-#pragma unroll
-                        for (int cq = 0; cq < 6; ++cq)
-                            if (cq < nq) atomicAdd(pool4 + (long long)cur * F4 + lane + 32 * cq, accv[cq]);
-                        if (lane == 0) atomicAdd(p.pool.zsum + cur, zs);
-                    }
-                };
 #pragma unroll 1
-                for (int i = 0; i < 16; ++i) {
-                    const int row = 16 * w8 + i;
-                    const long long g = m0 + row;
-                    const int ti = g < p.M ? __ldg(p.pool.tix + g) : -1;
-                    if (ti != cur) {
-                        flush();
-                        cur = ti;
-                        zs = 0.f;
+                for (int r0 = 0; r0 < 128; r0 += 8) {
+                    float4 v[8];
+                    int ti[8];
 #pragma unroll
-                        for (int cq = 0; cq < 6; ++cq) accv[cq] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int i = 0; i < 8; ++i) {                   // all eight row loads first ...
+                        const int row = r0 + i, j = row >> 5;
+                        const int tj = j == 0 ? tixv[0] : (j == 1 ? tixv[1] : (j == 2 ? tixv[2] : tixv[3]));
+                        const int sj = j == 0 ? srcv[0] : (j == 1 ? srcv[1] : (j == 2 ? srcv[2] : srcv[3]));
+                        ti[i] = __shfl_sync(0xffffffffu, tj, row & 31);
+                        const long long src = __shfl_sync(0xffffffffu, sj, row & 31);
+                        v[i] = (active && ti[i] >= 0) ? __ldg(x4 + src * ld4) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
-                    if (ti >= 0) {
-                        const float e = stagef(row >> 5)[32 + (row & 31)];
-                        const long long src = p.a_gather ? (long long)__ldg(p.a_gather + g) : g;
-                        const float4 *xr = x4 + src * ld4 + lane;
-                        zs += e;
 #pragma unroll
-                        for (int cq = 0; cq < 6; ++cq) {
-                            if (cq < nq) {
-                                const float4 v = __ldg(xr + 32 * cq);
-                                accv[cq].x = fmaf(e, v.x, accv[cq].x); accv[cq].y = fmaf(e, v.y, accv[cq].y);
-                                accv[cq].z = fmaf(e, v.z, accv[cq].z); accv[cq].w = fmaf(e, v.w, accv[cq].w);
+                    for (int i = 0; i < 8; ++i) {                   // ... then the running per-title sums
+                        const int row = r0 + i;
+                        if (ti[i] != cur) {
+                            if (cur >= 0) {
+                                if (active) atomicAdd(pool4 + (long long)cur * F4, accv);
+                                if (lane == 0 && w8 == 0) atomicAdd(p.pool.zsum + cur, zs);
                             }
+                            cur = ti[i];
+                            zs = 0.f;
+                            accv = make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                        if (ti[i] >= 0) {
+                            const float e = stagef(row >> 5)[32 + (row & 31)];
+                            zs += e;
+                            accv.x = fmaf(e, v[i].x, accv.x); accv.y = fmaf(e, v[i].y, accv.y);
+                            accv.z = fmaf(e, v[i].z, accv.z); accv.w = fmaf(e, v[i].w, accv.w);
                         }
                     }
                 }
-                flush();
+                if (cur >= 0) {
+                    if (active) atomicAdd(pool4 + (long long)cur * F4, accv);
+                    if (lane == 0 && w8 == 0) atomicAdd(p.pool.zsum + cur, zs);
+                }
                 asm volatile("bar.sync 1, 256;" ::: "memory");     // the staging buffers are reused by the next tile's stores
             }
         }
@@ -1103,7 +1118,7 @@ extern "C" int xnrs_titlepool_fwd(const float *x, long long ldx, const int *x_ro
     cudaStream_t st = STREAM(st_);
     static int is_sm100 = -1;
     if (is_sm100 < 0) is_sm100 = xnrs_device_is_sm100();
-    if (!is_sm100 || (precision != XNRS_PREC_TF32X3 && precision != XNRS_PREC_TF32) || A != 256 || F % 128 || F > 768 ||
+    if (!is_sm100 || (precision != XNRS_PREC_TF32X3 && precision != XNRS_PREC_TF32) || A != 256 || F % 128 || F > 1024 ||
         n_rows < 256 || ldx % 4 || ((uintptr_t)x & 15) || ((uintptr_t)w1 & 15) || ((uintptr_t)hid & 15) || ((uintptr_t)pooled & 15) ||
         num_sms() % 2)
         return fail(XNRS_ERR_UNSUPPORTED, "%s: shape / device / precision not covered by the fused kernel", "xnrs_titlepool_fwd");

@@ -82,6 +82,10 @@ int xnrs_colsum(const float *X, long long M, long long N, long long ldx, float *
 int xnrs_axpby(long long n, float a, const float *a_dev, const float *x, float b, float *y, xnrs_stream_t st);
 int xnrs_relu(long long n, const float *x, float *y, xnrs_stream_t st);
 int xnrs_relu_bwd(long long n, const float *y, const float *dy, float *dx, xnrs_stream_t st);
+/* backward of a tanh activation (FCScoring, scoring.py:72-102): dx = dy * (1 - y^2), y = the forward output */
+int xnrs_tanh_bwd(long long n, const float *y, const float *dy, float *dx, xnrs_stream_t st);
+/* y = x + b[0] (the bias of nn.Bilinear(.., out_features=1), scoring.py:41-69) */
+int xnrs_add_scalar(long long n, const float *x, const float *b, float *y, xnrs_stream_t st);
 /* BCERankingTrainer's output activation (training.py:329-331) and its backward (y = the forward output) */
 int xnrs_sigmoid(long long n, const float *x, float *y, xnrs_stream_t st);
 int xnrs_sigmoid_bwd(long long n, const float *y, const float *dy, float *dx, xnrs_stream_t st);
@@ -144,6 +148,7 @@ int xnrs_logit_bwd(const float *hid, const float *w2, const float *d_logit, long
 /* masked mean pooling (layers.py:25-37) */
 int xnrs_meanpool_fwd(const float *x, const float *mask, long long R, int L, int F, float *pooled,
                       xnrs_stream_t st);
+int xnrs_meanpool_bwd(const float *mask, const float *d_pooled, long long R, int L, int F, float *d_x, xnrs_stream_t st);
 /* collapsed mask: clamp(sum_l m, 0, 1) (xnrs/utils.py:74-75) */
 int xnrs_collapse_mask(const float *mask, long long R, int L, float *out, xnrs_stream_t st);
 
@@ -192,7 +197,8 @@ int xnrs_dot_score_bwd(const float *u, const float *c, const float *d_s, long lo
  * sim = ehat[row0:row0+Ba] ehat^T with xnrs_gemm; stage 2 turns sim (Ba,Bk) into the un-normalised
  * gradient G in place and accumulates stats[0] += sum of anchor terms, stats[1] += anchors with positives.
  * stage 3 (after an optional all-reduce of stats) writes loss = stats[0]/(stats[1]+1e-8).
- * stage 4 maps d_ehat (Bk,E) (= G ehat_k on anchor rows + G^T ehat_a, from xnrs_gemm) to d_emb. */
+ * stage 4 maps d_ehat (Bk,E) (= G ehat_k on anchor rows + G^T ehat_a, from xnrs_gemm) to d_emb; with stats == NULL it is
+ * the plain backward of the row normalisation (DotScoring(normalize=True), scoring.py:20-22) scaled by grad_scale. */
 int xnrs_infonce_normalize(const float *emb, long long Bk, int E, float *ehat, float *inv_norm, xnrs_stream_t st);
 int xnrs_infonce_rows(float *sim, const int *labels, long long Ba, long long Bk, long long row0,
                       float temperature, float *stats, xnrs_stream_t st);

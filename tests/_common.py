@@ -7,6 +7,8 @@ import torch
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 MODEL_NAMES = ['cl', 'nrms', 'naml', 'lstur_con', 'lstur_ini', 'npa']
+# ablation models, non-dot scorers, constructor options off their defaults (tests/golden/make_golden.py)
+EXTRA_MODEL_NAMES = ['base', 'mean', 'param_free', 'nrms_lf', 'small_naml', 'cl_bilin', 'cl_fc', 'cl_norm', 'nrms_unscaled']
 
 
 def load_npz(name):

@@ -221,6 +221,19 @@ def _xnrs_meanpool_fwd(x, mask, R, L, F_, pooled):
     pooled.copy_((x.reshape(R, L, F_) * m).sum(1) / (m.sum(1) + 1e-8))
 
 
+def _xnrs_meanpool_bwd(mask, d_pooled, R, L, F_, d_x):
+    m = mask.reshape(R, L, 1)
+    d_x.copy_((d_pooled.reshape(R, 1, F_) * m / (m.sum(1, keepdim=True) + 1e-8)).reshape(d_x.shape))
+
+
+def _xnrs_tanh_bwd(n, y, dy, dx):
+    dx.copy_(dy * (1 - y * y))
+
+
+def _xnrs_add_scalar(n, x, b, y):
+    y.copy_(x + b[0])
+
+
 def _xnrs_collapse_mask(mask, R, L, out):
     out.copy_(mask.reshape(R, L).sum(1).clamp(0, 1))
 
@@ -369,7 +382,7 @@ def _xnrs_infonce_finalize(stats, loss):
 
 
 def _xnrs_infonce_normalize_bwd(d_ehat, ehat, inv_norm, stats, gscale, Bk, E, d_emb):
-    sc = gscale / (stats[1] + 1e-8)
+    sc = gscale / (stats[1] + 1e-8) if stats is not None else gscale
     d_emb.copy_(sc * inv_norm[:, None] * (d_ehat - ehat * (ehat * d_ehat).sum(1, keepdim=True)))
 
 

@@ -48,6 +48,22 @@ MODELS = {
                       p_user_dropout=0.0, catg_features=['category_index'], user_features=['user_index']),
     'npa': dict(model='NPA', user_features=['user_index']),
 }
+# ablation models, non-dot scorers and the constructor options the five target models leave at their
+# defaults.  Keys starting with '_' are instructions for this script (and for tests/test_models.py:build), not config keys:
+#   _class      build this class of xnrs.models.full_models directly (not reachable through the reference's make_model)
+#   _normalize  set rec_model.normalize = True after construction (scoring.py:20-22)
+#   _unscaled   set scaled = False on every MultiHeadAttention (layers.py:135-137)
+EXTRA_MODELS = {
+    'base': dict(model='base'),
+    'mean': dict(model='mean', bias=True),
+    'param_free': dict(model='param_free', title_emb_dim=32, total_emb_dim=32, _class='ParamFreeRec'),
+    'nrms_lf': dict(model='NRMS_LF', _class='NRMS_LF'),
+    'small_naml': dict(model='smallNAML', catg_features=['category_index']),
+    'cl_bilin': dict(model='standard', scoring='bilin', bias=True),
+    'cl_fc': dict(model='standard', scoring='fc', bias=True),
+    'cl_norm': dict(model='standard', bias=True, _normalize=True),   # biased heads: no all-zero vector (0 / ||0|| is NaN in the reference)
+    'nrms_unscaled': dict(model='NRMS', _unscaled=True),
+}
 
 
 def make_batch(cfg, g, lstur=False):
@@ -92,9 +108,21 @@ def flat(prefix, obj, out):
 
 
 def model_fixture(name, over, seed):
-    cfg = DotMap(dict(BASE, **over))
+    cfg = DotMap(dict(BASE, **{k: v for k, v in over.items() if not k.startswith('_')}))
     torch.manual_seed(seed)
-    model = make_model(cfg)
+    if '_class' in over:
+        import xnrs.models.full_models.nrms as _nrms
+        import xnrs.models.full_models.param_free_model as _pf
+        from xnrs.models.components import scoring as _scoring
+        model = {'ParamFreeRec': _pf.ParamFreeRec, 'NRMS_LF': _nrms.NRMS_LF}[over['_class']](cfg, _scoring.DotScoring())
+    else:
+        model = make_model(cfg)
+    if over.get('_normalize'):
+        model.rec_model.normalize = True
+    if over.get('_unscaled'):
+        for m_ in model.modules():
+            if isinstance(m_, layers.MultiHeadAttention):
+                m_.scaled = False
     # default init leaves dummy_param at 0 and heads tiny; perturb so every path carries signal
     with torch.no_grad():
         for p in model.parameters():
@@ -103,7 +131,7 @@ def model_fixture(name, over, seed):
     model.eval()
     g = torch.Generator().manual_seed(seed + 100)
     batch = make_batch(cfg, g, lstur=name.startswith('lstur'))
-    out = {'cfg': np.array(json.dumps(dict(cfg)))}
+    out = {'cfg': np.array(json.dumps(dict(dict(cfg), **{k: v for k, v in over.items() if k.startswith('_')})))}
     for k, v in model.state_dict().items():
         out['sd/' + k] = v.numpy().copy()
     flat('batch', {k: v for k, v in batch.items() if k != 'main_theme'}, out)
@@ -128,7 +156,8 @@ def model_fixture(name, over, seed):
         total = l_rec
     out['ref/loss_total'] = total.detach().numpy()
     model.zero_grad()
-    total.backward()
+    if total.requires_grad:                 # ParamFreeRec: nothing trainable reaches the loss
+        total.backward()
     for k, p in model.named_parameters():
         out['grad/' + k] = (p.grad if p.grad is not None else torch.zeros_like(p)).numpy().copy()
     np.savez_compressed(os.path.join(HERE, f'model_{name}.npz'), **out)
@@ -376,6 +405,8 @@ if __name__ == '__main__':
         sys.exit(0)
     for i, (name, over) in enumerate(MODELS.items()):
         model_fixture(name, over, seed=20 + i)
+    for i, (name, over) in enumerate(EXTRA_MODELS.items()):
+        model_fixture(name, over, seed=60 + i)
     layer_fixtures()
     loss_metric_fixtures()
     dataset_fixture()

@@ -1,0 +1,54 @@
+"""Small driver for ncu captures of the token-level kernels of the CL step at bench shapes (T ~ 153.6k real tokens, 8.7k titles):
+the fused title-pooling forward (gather -> fc1 -> tanh -> logit -> exp -> per-title sums), the fc1 weight gradient with the
+fused table gather, and their dense counterparts.  Three launches each, in that order.
+    ncu --set full --clock-control none --import-source on -k regex:gemm_tc2 -o gpurun_out/prof python tools/prof_titlepool.py"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from xnrs_b200 import kernels as K  # noqa: E402
+from xnrs_b200 import synthetic as syn  # noqa: E402
+from xnrs_b200.data import TitleStore, plan_titles  # noqa: E402
+
+
+def main():
+    dev = 'cuda'
+    K.set_precision('tf32x3')
+    cat = syn.make_catalogue(65238, 30, 100_000, 768, seed=0)
+    store = TitleStore(cat.token_table.to(dev), cat.title_tokens.to(dev))
+    raw = syn.make_train_batch(65238, 1024, 50, seed=1000)
+    ids = torch.cat([raw['hist_ids'].reshape(-1), raw['cand_ids'].reshape(-1)]).to(dev)
+    plan = plan_titles(store, ids, True, True).acquire()
+    R, T = plan.uniq.numel(), plan.rows.numel()
+    g = torch.Generator().manual_seed(0)
+    w1 = (torch.randn(256, 768, generator=g) / 768 ** 0.5).to(dev)
+    b1 = (torch.randn(256, generator=g) * 0.1).to(dev)
+    w2 = (torch.randn(256, generator=g) / 16).to(dev)
+    b2 = torch.zeros(1, device=dev)
+    hid = torch.empty(T, 256, device=dev)
+    e, attn, zsum = torch.empty(T, device=dev), torch.empty(T, device=dev), torch.empty(R, device=dev)
+    pooled = torch.empty(R, 768, device=dev)
+    dhid = torch.randn(T, 256, device=dev)
+    dw = torch.zeros(256, 768, device=dev)
+    x = K.gather_rows(store.token_table, plan.rows)
+    print(f'titles {R}, token rows {T}')
+    for _ in range(3):
+        K.call('xnrs_titlepool_fwd', K._mat(store.token_table), 768, plan.rows, plan.tix, T, R, 768, 256, w1, b1, w2, b2, 1, hid, e, zsum,
+               attn, pooled)
+    for _ in range(3):
+        K.gemm(dhid, store.token_table, trans_a=True, out=dw, accumulate=True, b_rows=plan.rows)
+    for _ in range(3):
+        K.gemm(dhid, x, trans_a=True, out=dw, accumulate=True)
+    for _ in range(3):
+        K.gemm(x, w1, trans_b=True, bias=b1, act=K.ACT_TANH, out=hid)
+    for _ in range(3):
+        K.gemm(store.token_table, w1, trans_b=True, bias=b1, act=K.ACT_TANH, out=hid, a_rows=plan.rows)
+    torch.cuda.synchronize()
+    print('done')
+
+
+if __name__ == '__main__':
+    main()

@@ -283,6 +283,20 @@ __global__ void meanpool_fwd_kernel(const float *__restrict__ x, const float *__
     }
 }
 
+// d_x[r,l,:] = d_pooled[r,:] * m[r,l] / (sum_l m + 1e-8)   (backward of layers.py:34-36; the mask carries no gradient)
+__global__ void meanpool_bwd_kernel(const float *__restrict__ mask, const float *__restrict__ d_pooled, long long R, int L, int F,
+                                    float *__restrict__ d_x) {
+    for (long long r = blockIdx.x; r < R; r += gridDim.x) {
+        float tot = 0.f;
+        for (int l = 0; l < L; ++l) tot += mask[r * L + l];
+        const float inv = 1.f / (tot + 1e-8f);
+        for (int i = threadIdx.x; i < L * F; i += blockDim.x) {
+            const int l = i / F, f = i - l * F;
+            d_x[(r * L + l) * F + f] = d_pooled[r * F + f] * mask[r * L + l] * inv;
+        }
+    }
+}
+
 __global__ void collapse_mask_kernel(const float *__restrict__ mask, long long R, int L, float *__restrict__ out) {
     for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < R; r += (long long)gridDim.x * blockDim.x) {
         float s = 0.f;
@@ -625,6 +639,16 @@ extern "C" int xnrs_meanpool_fwd(const float *x, const float *mask, long long R,
     if (R == 0) return XNRS_OK;
     XNRS_REQUIRE(x && mask && pooled, "null pointer");
     meanpool_fwd_kernel<<<pool_grid(R), 128, 0, STREAM(st)>>>(x, mask, R, L, F, pooled);
+    XNRS_LAUNCHED();
+    return XNRS_OK;
+}
+
+extern "C" int xnrs_meanpool_bwd(const float *mask, const float *d_pooled, long long R, int L, int F, float *d_x,
+                                 xnrs_stream_t st) {
+    XNRS_REQUIRE(R >= 0 && L > 0 && F > 0, "bad sizes");
+    if (R == 0) return XNRS_OK;
+    XNRS_REQUIRE(mask && d_pooled && d_x, "null pointer");
+    meanpool_bwd_kernel<<<pool_grid(R), 256, 0, STREAM(st)>>>(mask, d_pooled, R, L, F, d_x);
     XNRS_LAUNCHED();
     return XNRS_OK;
 }

@@ -142,6 +142,17 @@ __global__ void sigmoid_bwd_kernel(long long n, const float *__restrict__ y, con
         dx[i] = dy[i] * y[i] * (1.f - y[i]);
 }
 
+__global__ void tanh_bwd_kernel(long long n, const float *__restrict__ y, const float *__restrict__ dy, float *__restrict__ dx) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dx[i] = dy[i] * (1.f - y[i] * y[i]);
+}
+
+__global__ void add_scalar_kernel(long long n, const float *__restrict__ x, const float *__restrict__ b, float *__restrict__ y) {
+    const float bv = b[0];
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        y[i] = x[i] + bv;
+}
+
 __global__ void transpose_kernel(const float *__restrict__ in, long long rows, long long cols, float *__restrict__ out) {
     __shared__ float tile[32][33];
     long long c0 = blockIdx.x * 32LL, r0 = blockIdx.y * 32LL;
@@ -345,6 +356,22 @@ extern "C" int xnrs_sigmoid_bwd(long long n, const float *y, const float *dy, fl
     if (n <= 0) return XNRS_OK;
     XNRS_REQUIRE(y && dy && dx, "null pointer");
     sigmoid_bwd_kernel<<<ew_grid(n, 256), 256, 0, STREAM(st)>>>(n, y, dy, dx);
+    XNRS_LAUNCHED();
+    return XNRS_OK;
+}
+
+extern "C" int xnrs_tanh_bwd(long long n, const float *y, const float *dy, float *dx, xnrs_stream_t st) {
+    if (n <= 0) return XNRS_OK;
+    XNRS_REQUIRE(y && dy && dx, "null pointer");
+    tanh_bwd_kernel<<<ew_grid(n, 256), 256, 0, STREAM(st)>>>(n, y, dy, dx);
+    XNRS_LAUNCHED();
+    return XNRS_OK;
+}
+
+extern "C" int xnrs_add_scalar(long long n, const float *x, const float *b, float *y, xnrs_stream_t st) {
+    if (n <= 0) return XNRS_OK;
+    XNRS_REQUIRE(x && b && y, "null pointer");
+    add_scalar_kernel<<<ew_grid(n, 256), 256, 0, STREAM(st)>>>(n, x, b, y);
     XNRS_LAUNCHED();
     return XNRS_OK;
 }

@@ -198,7 +198,7 @@ __global__ void infonce_normalize_bwd_kernel(const float *__restrict__ d_ehat, c
     const int lane = threadIdx.x & 31;
     long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
-    const float sc = gscale / (stats[1] + 1e-8f);
+    const float sc = stats ? gscale / (stats[1] + 1e-8f) : gscale;
     for (; w < Bk; w += nw) {
         float dot = 0.f;
         for (int i = lane; i < E; i += 32) dot = fmaf(ehat[w * E + i], d_ehat[w * E + i], dot);

@@ -491,11 +491,15 @@ class MultiHeadAttentionFn(torch.autograd.Function):
     """layers.MultiHeadAttention (layers.py:121-156) over R sequences of L rows."""
 
     @staticmethod
-    def forward(ctx, x, rows, mask, wq, bq, wk, bk, wv, bv, wo, bo, R, L, n_heads, keep, p_drop, seed):
+    def forward(ctx, x, rows, mask, wq, bq, wk, bk, wv, bv, wo, bo, R, L, n_heads, keep, p_drop, seed, q_scale=1.0):
+        """q_scale: the kernels divide the logits by sqrt(d_k) (layers.py:135-137, scaled=True); scaled=False passes
+        sqrt(d_k) here and q is multiplied by it after its projection"""
         D = wq.shape[0]
         dk = D // n_heads
         x, rows = _resolve_rows(x, rows, fuse_ok=False)
         q = gemm(x, wq, trans_b=True, bias=bq, a_rows=rows)
+        if q_scale != 1.0:
+            call('xnrs_axpby', q.numel(), float(q_scale), None, q.clone(), 0.0, q)
         k = gemm(x, wk, trans_b=True, bias=bk, a_rows=rows)
         v = gemm(x, wv, trans_b=True, bias=bv, a_rows=rows)
         o = torch.empty_like(q)
@@ -504,6 +508,7 @@ class MultiHeadAttentionFn(torch.autograd.Function):
         y = gemm(o, wo, trans_b=True, bias=bo)
         ctx.save_for_backward(x, rows, mask, wq, wk, wv, wo, q, k, v, o, lse, keep)
         ctx.cfg = (R, L, n_heads, dk, D, p_drop, seed)
+        ctx.q_scale = float(q_scale)
         ctx.bias_params = (bq, bk, bv, bo)
         return y
 
@@ -518,6 +523,8 @@ class MultiHeadAttentionFn(torch.autograd.Function):
         d_o = gemm(dy, wo)
         dq, dk_, dv = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
         call('xnrs_mha_bwd', q, k, v, o, d_o, D, mask, lse, R, L, h, dk, keep, p_drop, seed, dq, dk_, dv)
+        if ctx.q_scale != 1.0:
+            call('xnrs_axpby', dq.numel(), ctx.q_scale, None, dq.clone(), 0.0, dq)
         d_wq = _wgrad_gemm(wq, dq, x, b_rows=rows)
         d_wk = _wgrad_gemm(wk, dk_, x, b_rows=rows)
         d_wv = _wgrad_gemm(wv, dv, x, b_rows=rows)
@@ -530,7 +537,7 @@ class MultiHeadAttentionFn(torch.autograd.Function):
             gemm(dk_, wk, out=d_x, accumulate=True)
             gemm(dv, wv, out=d_x, accumulate=True)
         return (d_x, None, None, d_wq, d_bq, d_wk, d_bk, d_wv, d_bv, d_wo, d_bo,
-                None, None, None, None, None, None)
+                None, None, None, None, None, None, None)
 
 
 # Data-parallel runs exchange the gradient of row-sparse tables (the 700k-row user tables of LSTUR / NPA) as (ids, rows)
@@ -695,6 +702,105 @@ class ReluFn(torch.autograd.Function):
         dx = torch.empty_like(dy)
         call('xnrs_relu_bwd', dy.numel(), y, dy, dx)
         return dx
+
+
+class MeanPoolFn(torch.autograd.Function):
+    """layers.MaskedMean (layers.py:19-37): x (R*L, F), mask (R*L) -> (R, F)."""
+
+    @staticmethod
+    def forward(ctx, x, mask, R, L):
+        F_ = x.shape[1]
+        out = torch.empty((R, F_), device=x.device, dtype=torch.float32)
+        call('xnrs_meanpool_fwd', x, mask, R, L, F_, out)
+        ctx.save_for_backward(mask)
+        ctx.dims = (R, L, F_)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        (mask,) = ctx.saved_tensors
+        R, L, F_ = ctx.dims
+        d_x = None
+        if _need(ctx, 0):
+            d_x = torch.empty((R * L, F_), device=d_out.device, dtype=torch.float32)
+            call('xnrs_meanpool_bwd', mask, _f32(d_out), R, L, F_, d_x)
+        return d_x, None, None, None
+
+
+class LinearTanhFn(torch.autograd.Function):
+    """tanh(x W^T + b) with the activation in the GEMM epilogue (FCScoring's hidden layer, scoring.py:79-102)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        y = gemm(x, weight, trans_b=True, bias=bias, act=ACT_TANH)
+        ctx.save_for_backward(x, weight, y)
+        ctx.bias_param = bias
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, y = ctx.saved_tensors
+        d_pre = torch.empty_like(y)
+        call('xnrs_tanh_bwd', y.numel(), y, _f32(dy), d_pre)
+        dx = gemm(d_pre, weight) if _need(ctx, 0) else None
+        dw = _wgrad_gemm(weight, d_pre, x)
+        db = _wgrad_colsum(ctx.bias_param, d_pre) if ctx.bias_param is not None else None
+        return dx, dw, db
+
+
+class AddScalarFn(torch.autograd.Function):
+    """x + b for a one-element parameter b (the bias of nn.Bilinear(.., out_features=1), scoring.py:45-50)."""
+
+    @staticmethod
+    def forward(ctx, x, b):
+        x = _f32(x)
+        y = torch.empty_like(x)
+        call('xnrs_add_scalar', x.numel(), x, b, y)
+        ctx.bparam = b
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _f32(dy)
+        return dy, _wgrad_colsum(ctx.bparam, dy.reshape(-1, 1))
+
+
+class NormalizeRowsFn(torch.autograd.Function):
+    """x / ||x||_2 per row (DotScoring / BilinScoring normalize=True, scoring.py:20-22,63-65)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _f32(x)
+        y = torch.empty_like(x)
+        inv = torch.empty(x.shape[0], device=x.device, dtype=torch.float32)
+        call('xnrs_infonce_normalize', x, x.shape[0], x.shape[1], y, inv)
+        ctx.save_for_backward(y, inv)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        y, inv = ctx.saved_tensors
+        dx = torch.empty_like(y)
+        call('xnrs_infonce_normalize_bwd', _f32(dy), y, inv, None, 1.0, y.shape[0], y.shape[1], dx)
+        return dx
+
+
+class ScaleFn(torch.autograd.Function):
+    """a * x for a host scalar a (MultiHeadAttention(scaled=False): undoes the kernel's 1/sqrt(d_k))."""
+
+    @staticmethod
+    def forward(ctx, x, a):
+        ctx.a = float(a)
+        y = torch.empty_like(x)
+        call('xnrs_axpby', x.numel(), ctx.a, None, x, 0.0, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _f32(dy)
+        dx = torch.empty_like(dy)
+        call('xnrs_axpby', dy.numel(), ctx.a, None, dy, 0.0, dx)
+        return dx, None
 
 
 class SigmoidFn(torch.autograd.Function):

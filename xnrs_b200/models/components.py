@@ -40,13 +40,21 @@ def _seed() -> int:
 
 
 class MaskedMean(nn.Module):
-    """layers.MaskedMean (layers.py:19-37); forward only (its users are outside the five target models)."""
+    """layers.MaskedMean (layers.py:19-37): sum(x * m) / (sum(m) + 1e-8) over the sequence axis."""
+
+    def pool(self, x2: torch.Tensor, rows, mask, R: int, L: int, seg=None):
+        """pooler interface of TextEncoder / UserEncoder: (R*L, F) rows (or table + row index) -> (pooled (R, F), None)"""
+        if seg is not None:
+            raise RuntimeError('MaskedMean pools fixed-length groups')
+        if rows is not None:
+            x2 = K.gather_rows(x2, rows)
+        if mask is None:
+            mask = torch.ones(R * L, device=x2.device, dtype=torch.float32)
+        return K.MeanPoolFn.apply(x2, mask, R, L), None
 
     def forward(self, x: torch.Tensor, m: torch.Tensor):
         x2, R, L = _flat_rows(x)
-        out = torch.empty((R, x.shape[2]), device=x.device, dtype=torch.float32)
-        K.call('xnrs_meanpool_fwd', x2, _flat_mask(m, R * L), R, L, x.shape[2], out)
-        return out.unsqueeze(1)
+        return self.pool(x2, None, _flat_mask(m, R * L), R, L)[0].unsqueeze(1)
 
 
 class AdditiveAttention(nn.Module):
@@ -96,8 +104,6 @@ class MultiHeadAttention(nn.Module):
 
     def __init__(self, n_heads, d_model, dropout=0.1, scaled=True):
         super().__init__()
-        if not scaled:
-            raise NotImplementedError('the reference only ever uses scaled=True')
         self.scaled = scaled
         self.d_model = d_model
         self.d_k = d_model // n_heads
@@ -115,7 +121,8 @@ class MultiHeadAttention(nn.Module):
         seed = _seed() if (p > 0 and keep is None) else 0
         return K.MultiHeadAttentionFn.apply(
             x2, rows, mask, self.q_linear.weight, self.q_linear.bias, self.k_linear.weight, self.k_linear.bias,
-            self.v_linear.weight, self.v_linear.bias, self.out.weight, self.out.bias, R, L, self.h, keep, p, seed)
+            self.v_linear.weight, self.v_linear.bias, self.out.weight, self.out.bias, R, L, self.h, keep, p, seed,
+            1.0 if self.scaled else float(self.d_k) ** 0.5)
 
     def forward(self, x: torch.Tensor, m: torch.Tensor):
         x2, R, L = _flat_rows(x)
@@ -278,14 +285,20 @@ class UserEncoder(nn.Module):
         if self.att is not None:
             x2 = self.att.attend(x2, None, mask, R, L)
         a = None
-        if isinstance(self.pooler, MaskedMean):
-            pooled = self.pooler(x2.view(R, L, -1), mask.view(R, L, 1)).squeeze(1)
-        else:
-            pooled, a = self.pooler.pool(x2, None, mask, R, L)
+        pooled, a = self.pooler.pool(x2, None, mask, R, L)
+        if return_weights and a is None:
+            raise RuntimeError('this pooler has no attention weights to return')
         if hasattr(self, 'head'):
             pooled = _apply_head(self.head, pooled)
         u = pooled.unsqueeze(1)
         return (u, a.unsqueeze(-1)) if return_weights else u
+
+
+def _normalized(u: torch.Tensor, c: torch.Tensor):
+    """u / ||u||, c / ||c|| along the embedding axis (scoring.py:20-22)"""
+    B, N, T = c.shape
+    return (K.NormalizeRowsFn.apply(K._f32(u).reshape(B, T)).view(B, 1, T),
+            K.NormalizeRowsFn.apply(K._f32(c).reshape(B * N, T)).view(B, N, T))
 
 
 class DotScoring(nn.Module):
@@ -293,13 +306,51 @@ class DotScoring(nn.Module):
 
     def __init__(self, normalize: bool = False):
         super().__init__()
-        if normalize:
-            raise NotImplementedError('normalize=True is never enabled by the reference factory')
         self.normalize = normalize
 
     def forward(self, u: torch.Tensor, c: torch.Tensor):
+        if self.normalize:
+            u, c = _normalized(u, c)
         B, N, T = c.shape
         return K.DotScoreFn.apply(K._f32(u).reshape(B, T), K._f32(c)).unsqueeze(-1)
+
+
+class BilinScoring(nn.Module):
+    """scoring.BilinScoring (scoring.py:41-69): nn.Bilinear(D, D, 1) of (u repeated over the candidates, c).
+    s[b,n] = u_b^T W c_bn + bias = <u_b, W c_bn> + bias: one GEMM over the candidates, then the dot-score kernel."""
+
+    def __init__(self, emb_dim: int, normalize: bool = False, bias: bool = True):
+        super().__init__()
+        self.bilin = nn.Bilinear(in1_features=emb_dim, in2_features=emb_dim, out_features=1, bias=bias)
+        self.normalize = normalize
+
+    def forward(self, u: torch.Tensor, c: torch.Tensor):
+        if self.normalize:
+            u, c = _normalized(u, c)
+        B, N, T = c.shape
+        wc = K.LinearFn.apply(K._f32(c).reshape(B * N, T), None, self.bilin.weight[0], None)        # rows W c_bn
+        s = K.DotScoreFn.apply(K._f32(u).reshape(B, T), wc.view(B, N, T))
+        if self.bilin.bias is not None:
+            s = K.AddScalarFn.apply(s, self.bilin.bias)
+        return s.unsqueeze(-1)
+
+
+class FCScoring(nn.Module):
+    """scoring.FCScoring (scoring.py:72-102): fc2(tanh(fc1([u, c]))) over the concatenated pair."""
+
+    def __init__(self, emb_dim: int, hidden_dim: int, activation=torch.tanh, bias: bool = True):
+        super().__init__()
+        if activation is not torch.tanh:
+            raise NotImplementedError('FCScoring: only the reference default activation torch.tanh is implemented')
+        self.fc1 = nn.Linear(in_features=2 * emb_dim, out_features=hidden_dim, bias=bias)
+        self.fc2 = nn.Linear(in_features=hidden_dim, out_features=1, bias=bias)
+        self.activation = activation
+
+    def forward(self, u: torch.Tensor, c: torch.Tensor):
+        B, N, T = c.shape
+        x = torch.cat([K._f32(u).reshape(B, 1, T).expand(B, N, T), K._f32(c)], dim=2).reshape(B * N, 2 * T)   # byte movement
+        h = K.LinearTanhFn.apply(x, self.fc1.weight, self.fc1.bias)
+        return K.LinearFn.apply(h, None, self.fc2.weight, self.fc2.bias).view(B, N, 1)
 
 
 def _merge_ids(history, candidates):

@@ -12,8 +12,8 @@ import torch.nn as nn
 
 from .. import kernels as K
 from ..data import IndexedTitles
-from .components import (AdditiveAttention, DotScoring, MultiHeadAttention, ParentRec, PersonalizedAttention,
-                         TextEncoder, UserEncoder, _dev, _flat_mask, merge_sides)
+from .components import (AdditiveAttention, BilinScoring, DotScoring, FCScoring, MaskedMean, MultiHeadAttention, ParentRec,
+                         PersonalizedAttention, TextEncoder, UserEncoder, _dev, _flat_mask, merge_sides)
 
 
 class _Missing:
@@ -96,6 +96,43 @@ class StandardRec(ParentRec):
         return self.news_encoder(news_input)[0]
 
 
+class BaseRec(ParentRec):
+    """``model: 'base'`` (base_model.py:5-36): StandardRec without the user-side head."""
+
+    def __init__(self, cfg, rec_model: nn.Module):
+        cfg = _cfg(cfg)
+        title_encoder = TextEncoder(att=None, pooler=AdditiveAttention(cfg.d_backbone, 256), p_dropout=cfg.p_dropout,
+                                    in_features=cfg.d_backbone, out_features=cfg.title_emb_dim, bias=bool(cfg.bias))
+        user_encoder = UserEncoder(pooler=AdditiveAttention(cfg.title_emb_dim, 256), att=None, head=False,
+                                   p_dropout=cfg.p_dropout, emb_dim=cfg.title_emb_dim)
+        super().__init__(news_encoder=title_encoder, user_encoder=user_encoder, rec_model=rec_model)
+
+
+class MeanRec(ParentRec):
+    """``model: 'mean'`` (mean_model.py:5-31): masked-mean pooling at both levels, head on the news side only."""
+
+    def __init__(self, cfg, rec_model: nn.Module):
+        cfg = _cfg(cfg)
+        title_encoder = TextEncoder(att=None, pooler=MaskedMean(), p_dropout=cfg.p_dropout, in_features=cfg.d_backbone,
+                                    out_features=cfg.title_emb_dim, bias=bool(cfg.bias))
+        user_encoder = UserEncoder(pooler=MaskedMean(), att=None, head=False, p_dropout=cfg.p_dropout,
+                                   emb_dim=cfg.title_emb_dim, bias=bool(cfg.bias))
+        super().__init__(news_encoder=title_encoder, user_encoder=user_encoder, rec_model=rec_model)
+
+
+class ParamFreeRec(ParentRec):
+    """param_free_model.py:5-31 — masked means only; its single trainable tensors are the encoders' dummy_params."""
+
+    def __init__(self, cfg, rec_model: nn.Module):
+        cfg = _cfg(cfg)
+        assert cfg.title_emb_dim == cfg.d_backbone
+        title_encoder = TextEncoder(att=None, head=False, pooler=MaskedMean(), p_dropout=cfg.p_dropout,
+                                    out_features=cfg.d_backbone)
+        user_encoder = UserEncoder(att=None, head=False, pooler=MaskedMean(), p_dropout=cfg.p_dropout,
+                                   emb_dim=cfg.title_emb_dim)
+        super().__init__(news_encoder=title_encoder, user_encoder=user_encoder, rec_model=rec_model)
+
+
 class NRMS(ParentRec):
     """nrms.py:9-47 — heads are always biased (the reference does not forward cfg.bias here)."""
 
@@ -108,6 +145,55 @@ class NRMS(ParentRec):
                                    pooler=AdditiveAttention(cfg.title_emb_dim, 256), emb_dim=cfg.title_emb_dim,
                                    p_dropout=cfg.p_dropout, head=False)
         super().__init__(news_encoder=title_encoder, user_encoder=user_encoder, rec_model=rec_model)
+
+
+class NRMS_LF(ParentRec):
+    """nrms.py:49-79 — NRMS news encoder, masked-mean ("late fusion") user encoder."""
+
+    def __init__(self, cfg, rec_model: nn.Module):
+        cfg = _cfg(cfg)
+        title_encoder = TextEncoder(att=MultiHeadAttention(cfg.n_heads, cfg.d_backbone),
+                                    pooler=AdditiveAttention(cfg.d_backbone, 256), p_dropout=cfg.p_dropout,
+                                    in_features=cfg.d_backbone, out_features=cfg.title_emb_dim)
+        user_encoder = UserEncoder(att=None, pooler=MaskedMean(), emb_dim=cfg.title_emb_dim, p_dropout=cfg.p_dropout, head=False)
+        super().__init__(news_encoder=title_encoder, user_encoder=user_encoder, rec_model=rec_model)
+
+
+class SmallNAML(nn.Module):
+    """naml.py:162-238 — NAML with two views (title, category); forward only returns scores (no CL hook exists for it)."""
+
+    def __init__(self, cfg, rec_model):
+        super().__init__()
+        cfg = _cfg(cfg)
+        self.title_encoder = TextEncoder(att=None, pooler=AdditiveAttention(cfg.d_backbone, 256), p_dropout=cfg.p_dropout,
+                                         in_features=cfg.d_backbone, out_features=cfg.title_emb_dim)
+        self.cat_embedder = nn.Embedding(cfg.n_categories + 1, cfg.cat_emb_dim)
+        self.cat_fc = nn.Linear(cfg.cat_emb_dim, cfg.total_emb_dim)
+        self.feature_pooler = AdditiveAttention(cfg.total_emb_dim, 256)
+        self.user_encoder = AdditiveAttention(cfg.title_emb_dim, 256)
+        self.rec_model = rec_model
+        self.emb_dim = cfg.total_emb_dim
+
+    def _news(self, title, ctg):
+        t, mask = self.title_encoder(title)
+        c = _linear(self.cat_fc, _embed(self.cat_embedder, ctg))
+        b, n, e = t.shape
+        views = torch.cat([t, c], dim=2).reshape(b * n * 2, e)                 # == stack(dim=2): byte movement only
+        pooled, _ = self.feature_pooler.pool(views, None, None, b * n, 2)
+        return pooled.view(b, n, e), mask
+
+    def _forward(self, hist_title_features, hist_ctg, cand_title_features, cand_ctg):
+        h, hm = self._news(hist_title_features, hist_ctg)
+        c, _ = self._news(cand_title_features, cand_ctg)
+        b, n, e = h.shape
+        u, _ = self.user_encoder.pool(h.reshape(b * n, e), None, _flat_mask(hm, b * n), b, n)
+        return self.rec_model(u.unsqueeze(1), c)
+
+    def forward(self, batch: dict):
+        return self._forward(hist_title_features=batch['user_features']['history']['title_emb'],
+                             hist_ctg=batch['user_features']['history']['category_index'],
+                             cand_title_features=batch['candidate_features']['title_emb'],
+                             cand_ctg=batch['candidate_features']['category_index'])
 
 
 class NAML(nn.Module):
@@ -371,17 +457,25 @@ class NPA(nn.Module):
 
 
 def make_model(cfg):
-    """make_model.py:15-55 restricted to what the five target models use (dot scoring)."""
+    """make_model.py:15-55: scorer from cfg.scoring, model class from cfg.model.  CAUM (a candidate-aware model, not a
+    bi-encoder) and the 'nonlin' scorer (referenced by the reference factory but defined nowhere in it) are rejected."""
     c = _cfg(cfg)
+    emb_dim, bias = c.total_emb_dim, bool(c.bias)
     if c.scoring == 'dot':
         scoring_fn = DotScoring()
-    elif c.scoring in ('bilin', 'nonlin', 'fc', 'CAUMScoring'):
-        raise NotImplementedError(f'scoring {c.scoring!r} is outside the B200 hot path (every shipped config uses dot)')
+    elif c.scoring == 'bilin':
+        scoring_fn = BilinScoring(emb_dim, bias=bias)
+    elif c.scoring == 'fc':
+        scoring_fn = FCScoring(emb_dim, hidden_dim=emb_dim // 2, bias=bias)
+    elif c.scoring in ('nonlin', 'CAUMScoring'):
+        raise NotImplementedError(f'scoring {c.scoring!r}: NonLinScoring does not exist in the reference (make_model.py:25-26 would '
+                                  f'raise AttributeError) and CAUMScoring belongs to the candidate-aware CAUM model (SURVEY §2 row 12)')
     else:
         raise ValueError(f'invalid value for cfg.scoring: {c.scoring}')
-    models = {'standard': StandardRec, 'NRMS': NRMS, 'NAML': NAML, 'NPA': NPA, 'LSTUR': LSTUR}
+    models = {'standard': StandardRec, 'base': BaseRec, 'mean': MeanRec, 'NRMS': NRMS, 'NAML': NAML, 'smallNAML': SmallNAML,
+              'NPA': NPA, 'LSTUR': LSTUR}
     if c.model in models:
         return models[c.model](c, scoring_fn)
-    if c.model in ('base', 'mean', 'smallNAML', 'CAUM'):
-        raise NotImplementedError(f'model {c.model!r} is outside the B200 hot path (SURVEY §2 rows 11-12)')
+    if c.model == 'CAUM':
+        raise NotImplementedError("model 'CAUM' is not a bi-encoder (its user vector depends on the candidate): SURVEY §2 row 12")
     raise ValueError(f'invalid value for cfg.model: {c.model}')

@@ -143,11 +143,12 @@ class RankingTrainer:
     def _embeddings(self, batch):
         """(u (B,T), c (B,N,T)) from ONE forward pass; None if the model cannot return embeddings (NPA)."""
         batch_to_device(batch, self.device)
+        rec = getattr(self.model, 'rec_model', None)
+        if not isinstance(rec, DotScoring) or rec.normalize:      # the fused scorer + loss kernel is the plain dot product
+            return None
         try:
             r, u, c = self.model(batch, return_embeddings=True)
         except TypeError:
-            return None
-        if not isinstance(getattr(self.model, 'rec_model', None), DotScoring):
             return None
         B, N, T = c.shape
         return K._f32(u).reshape(B, T), K._f32(c)

@@ -227,6 +227,18 @@ int xnrs_binary_metrics(const float *scores, const float *targets, const long lo
 int xnrs_adam_step(float *p, const float *g, float *m, float *v, long long n, float lr, float beta1, float beta2,
                    float eps, int step, const float *bc_dev, float grad_scale, xnrs_stream_t st);
 int xnrs_adam_tick(int *step_dev, float beta1, float beta2, float *bc_dev, xnrs_stream_t st);
+/* Adam over the ACTIVE rows of a row-sparse table (nn.Embedding(n_users + 1, ..): lstur.py:94-98, npa.py:12-15).  A row that
+ * never received a gradient has g = m = v = 0 and dense Adam leaves it exactly unchanged, so the optimiser tracks the rows
+ * touched at least once: xnrs_mark_rows appends first-time rows of idx (n) to `active` (V ints) through `bitmap` (ceil(V/32)
+ * ints, zero-initialised) and bumps count[0]; rows equal to skip_row (padding_idx) or outside [0, V) are ignored.
+ * xnrs_adam_rows applies xnrs_adam_step's update to the active rows only (bit-identical to the dense pass over the table);
+ * xnrs_zero_rows clears the gradient of the active rows (the rest of the table's gradient is never written). */
+int xnrs_mark_rows(const int *idx, long long n, long long V, int skip_row, int *bitmap, int *active, int *count,
+                   xnrs_stream_t st);
+int xnrs_adam_rows(float *p, const float *g, float *m, float *v, long long V, int D, const int *active, const int *count,
+                   float lr, float beta1, float beta2, float eps, int step, const float *bc_dev, float grad_scale,
+                   xnrs_stream_t st);
+int xnrs_zero_rows(float *g, long long V, int D, const int *active, const int *count, xnrs_stream_t st);
 
 #ifdef __cplusplus
 }

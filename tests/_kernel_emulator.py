@@ -397,6 +397,30 @@ def _xnrs_adam_step(p, g, m, v, n, lr, b1, b2, eps, step, bc_dev, gscale):
     p.sub_(lr * i1 * m / (v.sqrt() * i2 + eps))
 
 
+def _xnrs_mark_rows(idx, n, V, skip_row, bitmap, active, count):
+    for r in idx.tolist():
+        if r < 0 or r >= V or r == skip_row:
+            continue
+        w, b = r >> 5, 1 << (r & 31)
+        word = int(bitmap[w]) & 0xffffffff
+        if not word & b:
+            word |= b
+            bitmap[w] = word - (1 << 32) if word >= (1 << 31) else word
+            active[int(count[0])] = r
+            count[0] += 1
+
+
+def _xnrs_adam_rows(p, g, m, v, V, D, active, count, lr, b1, b2, eps, step, bc_dev, gscale):
+    rows = active[:int(count[0])].long()
+    pr, mr, vr = p.reshape(V, D)[rows], m.reshape(V, D)[rows], v.reshape(V, D)[rows]
+    _xnrs_adam_step(pr, g.reshape(V, D)[rows], mr, vr, pr.numel(), lr, b1, b2, eps, step, bc_dev, gscale)
+    p.reshape(V, D)[rows], m.reshape(V, D)[rows], v.reshape(V, D)[rows] = pr, mr, vr
+
+
+def _xnrs_zero_rows(g, V, D, active, count):
+    g.reshape(V, D)[active[:int(count[0])].long()] = 0
+
+
 def _xnrs_adam_tick(step_dev, b1, b2, bc):
     step_dev += 1
     t = int(step_dev)

@@ -341,6 +341,32 @@ def test_prefetch_over_recycled_batches(monkeypatch):
             assert torch.equal(got, want[i % 3])
 
 
+def test_active_row_adam_equals_dense_adam(device, monkeypatch):
+    """§8(f) row 1 / SURVEY §7 hard part 4: Adam restricted to the rows of an embedding table that have received a gradient
+    so far (xnrs_adam_rows) == torch's dense Adam over the whole table, BIT FOR BIT, over 25 steps that keep touching new
+    users: a never-touched row has g = m = v = 0 and the dense update leaves it exactly unchanged."""
+    from xnrs_b200 import training as TR
+    runs = []
+    for min_rows in (5, 10 ** 9):                  # 5: the 12-row user table and the 7-row category table go row-sparse
+        monkeypatch.setattr(TR.RankingTrainer, 'sparse_min_rows', min_rows)
+        fx, cfg, model = build('lstur_con', device)
+        tr = ContrastiveRankingTrainer(dict(cfg, lr=1e-2), model)
+        assert len(tr.optimizer.tables) == (2 if min_rows == 5 else 0)
+        gen = torch.Generator().manual_seed(3)
+        for step in range(25):
+            batch = fixture_batch(fx, device)
+            B = batch['targets'].shape[0]
+            n_u = cfg['n_users'] if step >= 8 else 4                    # the first steps only see users 1..4
+            batch['user_features']['other']['user_index'] = torch.randint(1, n_u + 1, (B, 1), generator=gen).int().to(device)
+            tr._train_step(batch)
+        runs.append({k: v.detach().cpu().clone() for k, v in model.named_parameters()})
+        if min_rows == 5:
+            t = tr.optimizer.tables[-1]
+            assert 0 < int(t['count']) <= t['V'] - 1                    # padding row 0 never becomes active
+    for k in runs[0]:
+        assert torch.equal(runs[0][k], runs[1][k]), k
+
+
 def test_flat_adam_refuses_detached_gradients(device):
     """FlatAdam updates from ONE flat gradient buffer; if user code replaces the parameters' .grad views
     (model.zero_grad(set_to_none=True)) the step must fail loudly instead of training on zeros"""

@@ -204,6 +204,47 @@ __global__ void adam_kernel(float *__restrict__ p, const float *__restrict__ g, 
     }
 }
 
+// ---- Adam over the ACTIVE rows of a row-sparse table (the 700k-row user tables of LSTUR / NPA, SURVEY §7 hard part 4) -------
+// torch's dense Adam moves every row every step, but a row that has never received a gradient has g = m = v = 0 and its update
+// is exactly lr * 0 / (0 + eps) = 0: only rows touched at least once ("active") can change.  The optimiser keeps a bitmap and
+// an append-only list of those rows; this kernel applies the SAME per-element update as adam_kernel to the listed rows only —
+// bit-identical parameters to the dense pass, at (active rows / all rows) of its HBM traffic.
+__global__ void mark_rows_kernel(const int *__restrict__ idx, long long n, long long V, int skip_row, unsigned *__restrict__ bitmap,
+                                 int *__restrict__ active, int *__restrict__ count) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int r = idx[i];
+        if (r < 0 || r >= V || r == skip_row) continue;
+        const unsigned bit = 1u << (r & 31);
+        if (!(atomicOr(bitmap + (r >> 5), bit) & bit)) active[atomicAdd(count, 1)] = r;      // first touch: append
+    }
+}
+
+__global__ void adam_rows_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
+                                 int D, const int *__restrict__ active, const int *__restrict__ count, float lr, float b1, float b2,
+                                 float eps, float inv_bc1, float inv_sqrt_bc2, const float *__restrict__ bc_dev, float gscale) {
+    if (bc_dev) {
+        inv_bc1 = bc_dev[0];
+        inv_sqrt_bc2 = bc_dev[1];
+    }
+    const long long n = (long long)count[0] * D;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const long long i = (long long)active[e / D] * D + e % D;
+        float gi = g[i] * gscale;
+        float mi = b1 * m[i] + (1.f - b1) * gi;
+        float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+        p[i] -= (lr * inv_bc1) * (mi / denom);
+    }
+}
+
+__global__ void zero_rows_kernel(float *__restrict__ g, int D, const int *__restrict__ active, const int *__restrict__ count) {
+    const long long n = (long long)count[0] * D;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+        g[(long long)active[e / D] * D + e % D] = 0.f;
+}
+
 // device-side step counter for CUDA-graph replay: bc = {1/(1-b1^t), 1/sqrt(1-b2^t)}
 __global__ void adam_tick_kernel(int *step, float b1, float b2, float *bc) {
     int t = ++(*step);
@@ -315,6 +356,37 @@ extern "C" int xnrs_adam_step(float *p, const float *g, float *m, float *v, long
     double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
     adam_kernel<<<ew_grid(n, 256), 256, 0, STREAM(st)>>>(p, g, m, v, n, lr, beta1, beta2, eps, (float)(1.0 / bc1),
                                                     (float)(1.0 / sqrt(bc2)), bc_dev, grad_scale);
+    XNRS_LAUNCHED();
+    return XNRS_OK;
+}
+
+extern "C" int xnrs_mark_rows(const int *idx, long long n, long long V, int skip_row, int *bitmap, int *active, int *count,
+                              xnrs_stream_t st) {
+    XNRS_REQUIRE(n >= 0 && V > 0, "bad sizes");
+    if (n == 0) return XNRS_OK;
+    XNRS_REQUIRE(idx && bitmap && active && count, "null pointer");
+    mark_rows_kernel<<<ew_grid(n, 256), 256, 0, STREAM(st)>>>(idx, n, V, skip_row, reinterpret_cast<unsigned *>(bitmap), active, count);
+    XNRS_LAUNCHED();
+    return XNRS_OK;
+}
+
+extern "C" int xnrs_adam_rows(float *p, const float *g, float *m, float *v, long long V, int D, const int *active, const int *count,
+                              float lr, float beta1, float beta2, float eps, int step, const float *bc_dev, float grad_scale,
+                              xnrs_stream_t st) {
+    XNRS_REQUIRE(step >= 1 || bc_dev, "step counts from 1");
+    if (step < 1) step = 1;
+    XNRS_REQUIRE(V > 0 && D > 0 && p && g && m && v && active && count, "bad arguments");
+    double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
+    // the active count lives on the device: size the grid for the machine, the kernel reads the count
+    adam_rows_kernel<<<(unsigned)(8 * num_sms()), 256, 0, STREAM(st)>>>(p, g, m, v, D, active, count, lr, beta1, beta2, eps,
+                                                                     (float)(1.0 / bc1), (float)(1.0 / sqrt(bc2)), bc_dev, grad_scale);
+    XNRS_LAUNCHED();
+    return XNRS_OK;
+}
+
+extern "C" int xnrs_zero_rows(float *g, long long V, int D, const int *active, const int *count, xnrs_stream_t st) {
+    XNRS_REQUIRE(V > 0 && D > 0 && g && active && count, "bad arguments");
+    zero_rows_kernel<<<(unsigned)(8 * num_sms()), 256, 0, STREAM(st)>>>(g, D, active, count);
     XNRS_LAUNCHED();
     return XNRS_OK;
 }

@@ -144,6 +144,7 @@ class DataParallelTrainer:
             r_ids = remote[:, D].contiguous().view(torch.int32)
             r_rows = remote[:, :D].contiguous()
             K.call('xnrs_scatter_add_rows', weight.grad, V, D, r_ids, r_ids.numel(), r_rows, D, pad)
+            K.mark_active_rows(weight, r_ids, pad)                             # remote rows become active in this replica too
             # Every rank now holds the same sums up to fp32 summation order (own rows first, atomics).  Replicas must stay
             # BIT-identical (a dense all-reduce guarantees that), so rank 0's values of the touched rows are made
             # authoritative: gather them, broadcast, write back (byte movement; W*B x D floats).
@@ -186,6 +187,9 @@ class DataParallelTrainer:
         else:
             total, preds, _ = tr.rec_loss(batch)
             out = {'loss': total.detach(), 'logits': preds}
+        if self.world > 1 and not self.sparse_tables and getattr(tr.optimizer, 'tables', None):
+            raise RuntimeError('the optimiser updates its big embedding tables row-sparsely: their gradients must be exchanged as '
+                               '(ids, rows) (sparse_tables=True), a dense all-reduce would deliver rows it does not know about')
         if self.world > 1 and self.sparse_tables:
             K.sparse_grad_log = []
         try:

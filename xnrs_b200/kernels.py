@@ -546,6 +546,13 @@ class MultiHeadAttentionFn(torch.autograd.Function):
 sparse_grad_log = None
 
 
+def mark_active_rows(weight, idx, pad: int = -1) -> None:
+    """FlatAdam row-sparse tables: remember the rows that have received a gradient (training.FlatAdam, xnrs_adam_rows)"""
+    t = getattr(weight, '_xnrs_rows', None)
+    if t is not None and idx.numel():
+        call('xnrs_mark_rows', idx, idx.numel(), t['V'], int(pad), t['bitmap'], t['active'], t['count'])
+
+
 class EmbeddingFn(torch.autograd.Function):
     """nn.Embedding lookup with a dense weight gradient (lstur.py:94-98,180-183; npa.py:12-15; naml.py:34-47)."""
 
@@ -565,6 +572,7 @@ class EmbeddingFn(torch.autograd.Function):
             # FlatAdam-managed table: scatter straight into its gradient view (no V x D temporary, zero fill and add — 3 x 383 MB
             # of traffic per step for the LSTUR user table)
             call('xnrs_scatter_add_rows', g, ctx.shape[0], ctx.shape[1], idx, idx.numel(), dy, dy.stride(0), ctx.pad)
+            mark_active_rows(weight, idx, ctx.pad)
             if sparse_grad_log is not None:
                 sparse_grad_log.append((weight, idx, dy, ctx.pad))
             return None, None, None

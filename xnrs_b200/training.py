@@ -48,11 +48,22 @@ class FlatAdam:
 
     Every parameter becomes a view into ``flat_p`` and owns a persistent ``.grad`` view into ``flat_g``
     (autograd accumulates into it in place), so the update is a single xnrs_adam_step launch and a
-    data-parallel job all-reduces a single bucket."""
+    data-parallel job all-reduces a single bucket.
+
+    ``row_sparse``: embedding tables (the 703 790-row user tables of LSTUR / NPA, lstur.py:94-98, npa.py:12-15) whose gradient
+    only ever arrives as a scatter-add of looked-up rows.  They are laid out AFTER the dense parameters and updated by
+    xnrs_adam_rows over the rows touched at least once so far ("active"): a never-touched row has g = m = v = 0 and dense
+    Adam leaves it exactly unchanged, so this is torch's dense Adam bit for bit at a fraction of its 7 x 383 MB of traffic
+    per step (SURVEY §7 hard part 4: the explicit decision).  Their gradient is cleared row-wise too."""
+
+    SPARSE_MIN_ROWS = 100_000
 
     def __init__(self, params: Iterable[nn.Parameter], lr: float, betas=(0.9, 0.999), eps: float = 1e-8,
-                 graph_safe: bool = False):
-        self.params: List[nn.Parameter] = [p for p in params if p.requires_grad]
+                 graph_safe: bool = False, row_sparse: Iterable[nn.Parameter] = ()):
+        sparse_ids = {id(p) for p in row_sparse if p.requires_grad and p.dim() == 2}
+        params = [p for p in params if p.requires_grad]
+        self.params: List[nn.Parameter] = ([p for p in params if id(p) not in sparse_ids]
+                                           + [p for p in params if id(p) in sparse_ids])
         dev = self.params[0].device
         sizes = [((p.numel() + 3) // 4) * 4 for p in self.params]          # keep every view 16-byte aligned
         total = sum(sizes)
@@ -62,6 +73,8 @@ class FlatAdam:
         self.v = torch.zeros(total, device=dev, dtype=torch.float32)
         off = 0
         self.ranges = {}                     # id(param) -> (begin, end) of its slice of the flat buffers
+        self.tables = []                     # row-sparse tables: dict(param, begin, V, D, bitmap, active, count)
+        self.dense_end = None
         for p, n in zip(self.params, sizes):
             self.ranges[id(p)] = (off, off + p.numel())
             view = self.flat_p[off:off + p.numel()].view_as(p)
@@ -69,7 +82,19 @@ class FlatAdam:
             p.data = view
             p.grad = self.flat_g[off:off + p.numel()].view_as(p)
             p._xnrs_direct = True          # kernels.py: weight gradients are accumulated straight into this view
+            if id(p) in sparse_ids:
+                if self.dense_end is None:
+                    self.dense_end = off
+                V, D = p.shape
+                t = {'param': p, 'begin': off, 'V': V, 'D': D,
+                     'bitmap': torch.zeros((V + 31) // 32, device=dev, dtype=torch.int32),
+                     'active': torch.zeros(V, device=dev, dtype=torch.int32),
+                     'count': torch.zeros(1, device=dev, dtype=torch.int32)}
+                self.tables.append(t)
+                p._xnrs_rows = t           # kernels.EmbeddingFn.backward marks the rows it scatters into
             off += n
+        if self.dense_end is None:
+            self.dense_end = total
         self.lr, self.betas, self.eps = lr, betas, eps
         self.step_count = 0
         self.graph_safe = graph_safe
@@ -77,8 +102,14 @@ class FlatAdam:
             self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
             self.bc_dev = torch.zeros(2, device=dev, dtype=torch.float32)
 
+    def _table_views(self, t):
+        a, b = t['begin'], t['begin'] + t['V'] * t['D']
+        return self.flat_p[a:b], self.flat_g[a:b], self.m[a:b], self.v[a:b]
+
     def zero_grad(self) -> None:
-        self.flat_g.zero_()
+        self.flat_g[:self.dense_end].zero_()
+        for t in self.tables:               # only active rows can hold a gradient
+            K.call('xnrs_zero_rows', self._table_views(t)[1], t['V'], t['D'], t['active'], t['count'])
 
     def _check_views(self) -> None:
         """the parameters' .grad must still be the views into flat_g handed out at construction (e.g. a
@@ -96,14 +127,25 @@ class FlatAdam:
         if self.graph_safe:
             K.call('xnrs_adam_tick', self.step_dev, self.betas[0], self.betas[1], self.bc_dev)
             bc = self.bc_dev
-        K.adam_step(self.flat_p, self.flat_g, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps,
+        d = self.dense_end
+        K.adam_step(self.flat_p[:d], self.flat_g[:d], self.m[:d], self.v[:d], self.lr, self.betas[0], self.betas[1], self.eps,
                     self.step_count, bc, grad_scale)
+        for t in self.tables:
+            p, g, m, v = self._table_views(t)
+            K.call('xnrs_adam_rows', p, g, m, v, t['V'], t['D'], t['active'], t['count'], self.lr, self.betas[0], self.betas[1],
+                   self.eps, self.step_count, bc, grad_scale)
+
+
+def row_sparse_tables(model: nn.Module, min_rows: int = FlatAdam.SPARSE_MIN_ROWS):
+    """the embedding tables big enough for the active-row Adam (user-id tables; category tables stay dense)"""
+    return [m.weight for m in model.modules() if isinstance(m, nn.Embedding) and m.num_embeddings >= min_rows]
 
 
 class RankingTrainer:
     """common part of the reference's BaseTrainer / RankingTrainer (training.py:24-44, 191-243)."""
 
     loss_kind = K.LOSS_MSE_RELU
+    sparse_min_rows = FlatAdam.SPARSE_MIN_ROWS      # embedding tables at least this tall get the active-row Adam
     eval_act = 1            # activation that takes RAW scores to the ranked scores (catalogue evaluation): relu
     test_act = 0            # activation _test_step still has to apply to forward()'s output before the metrics
 
@@ -112,7 +154,8 @@ class RankingTrainer:
         self.model = model
         self.device = torch.device(self.cfg.get('device', 'cuda:0'))
         self.model.to(self.device)
-        self.optimizer = FlatAdam(self.model.parameters(), lr=float(self.cfg.get('lr', 1e-4)), graph_safe=graph_safe)
+        self.optimizer = FlatAdam(self.model.parameters(), lr=float(self.cfg.get('lr', 1e-4)), graph_safe=graph_safe,
+                                  row_sparse=row_sparse_tables(self.model, self.sparse_min_rows))
         self._init_loss()
         self.current_train_step = 0
 

@@ -465,7 +465,7 @@ def train_workload(ctx, args, model_key, want_cpu=True, want_eager=False):
     trainer_cls = MSERankingTrainer if model_key == 'npa' else ContrastiveRankingTrainer     # NPA has no CL hook
     model = make_model(cfg)
     encoder_options(model, dedup_titles=not args.no_dedup, skip_padding=not args.no_skip_padding)
-    use_graph = model_key == 'cl' and not args.no_graph and (world == 1 or args.graph_multi_gpu)
+    use_graph = model_key == 'cl' and not args.no_graph and (world == 1 or not args.no_graph_multi_gpu)
     trainer = trainer_cls(dict(cfg, device=str(dev)), model, graph_safe=use_graph)
     trainer.model.train()
     dp = DataParallelTrainer(trainer)
@@ -771,7 +771,8 @@ def main():
     ap.add_argument('--no-skip-padding', action='store_true', help='run pad tokens through the encoder like the reference does')
     ap.add_argument('--no-prefetch', action='store_true', help='compute the id plumbing of each batch inside its own step')
     ap.add_argument('--no-graph', action='store_true', help='launch the CL step kernel by kernel instead of replaying its CUDA graph')
-    ap.add_argument('--graph-multi-gpu', action='store_true', help='also replay CUDA graphs (NCCL collectives captured) under torchrun')
+    ap.add_argument('--no-graph-multi-gpu', action='store_true', help='under torchrun, launch kernel by kernel (graphs capture the NCCL collectives too)')
+    ap.add_argument('--graph-multi-gpu', action='store_true', help='(default now) replay CUDA graphs under torchrun as well')
     ap.add_argument('--no-dedup', action='store_true', help='encode every (impression, slot) title, not each distinct article once')
     ap.add_argument('--eval-impressions', type=int, default=376_471)
     args = ap.parse_args()

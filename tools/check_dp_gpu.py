@@ -77,7 +77,9 @@ def main():
         finals.append((losses, t2.optimizer.flat_p.clone(), st))
     dl = max(abs(a - b) / max(abs(a), 1e-9) for a, b in zip(finals[0][0], finals[1][0]))
     dp_ = float((finals[0][1] - finals[1][1]).abs().max())
-    ok2 = dl < 1e-4 and dp_ < 1e-4 and finals[1][2].replays >= 2
+    # parameters: Adam turns the sign of a ~0 gradient component (fp32 atomic order) into a whole +-lr step, so two runs of
+    # the SAME eager code differ by a few lr as well; a wrong replay would show up in the losses and as O(1) differences
+    ok2 = dl < 1e-4 and dp_ < 3 * cfg['lr'] and finals[1][2].replays >= 2
     print(f'rank {rank}/{world}: graph-vs-eager loss diff {dl:.2e}, param diff {dp_:.2e}, replays {finals[1][2].replays} -> '
           f'{"OK" if ok2 else "FAIL"}', flush=True)
 
@@ -101,6 +103,12 @@ def main():
     print(f'rank {rank}/{world}: sharded-vs-single evaluation metric diff {de:.2e} over {single["impressions"]} impressions -> '
           f'{"OK" if ok3 else "FAIL"}', flush=True)
     ok = ok and ok2 and ok3
+    replays = finals[1][2].replays
+    finals.clear()                      # the captured graphs hold NCCL work: release them before the communicator goes away
+    del st, d2, t2
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

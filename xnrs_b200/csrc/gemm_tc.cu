@@ -57,7 +57,9 @@ struct TcArgs {
     int lsu_gather;         // CTA-pair kernel: 1 = A rows, 2 = B rows gathered by a cp.async producer warp instead of TMA gather4
     const float *A; long long lda;      // raw operand pointers for that warp
     const float *B; long long ldb;
-    int passes;             // 3 (TF32X3) or 1 (TF32)
+    int passes;             // 3 (TF32X3) or 1 (TF32 / BF16)
+    int elt;                // bytes per operand element: 4 (fp32 storage, kind::tf32) or 2 (bf16 storage, kind::f16) — pair kernel
+    int c_bf16;             // pair kernel: C is stored as bf16 (fp32 accumulators rounded to nearest even)
     PoolArgs pool;
     int stages;
     long long tiles_m, tiles_n;
@@ -542,6 +544,14 @@ __device__ __forceinline__ void tc2_mma_tf32(uint32_t d_tmem, uint64_t adesc, ui
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
 
+__device__ __forceinline__ void tc2_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+
 constexpr int T2N = 256;       // tile columns of the pair
 
 constexpr int TC2_THREADS = 640;       // CTA-pair kernel: {TMA, MMA, relay, -} | 8 splitter warps | 8 epilogue warps
@@ -560,6 +570,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_rank();
     const int stages = p.stages, passes = p.passes;
+    // operand tiles are 128 rows x 128 bytes whatever the element type: a stage spans 32 fp32 / 64 bf16 elements of K; an
+    // MN-major tile is made of boxes of (128 bytes of MN) x (kstep k-rows): four of 4 KB (fp32) or two of 8 KB (bf16)
+    const int kstep = p.elt == 2 ? 64 : TBK;
+    const int mn_box_elems = p.elt == 2 ? 64 : 32, mn_box_bytes = kstep * 128, mn_boxes = 128 / mn_box_elems;
     const int stage_bytes = (passes == 3 ? 2 : 1) * HALF;
     const int acc_cols = (passes == 3 ? 2 : 1) * T2N;
     const int acc_stages = 512 / acc_cols;
@@ -606,7 +620,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 arow.z = p.a_gather[min(m + 2, last)];
                 arow.w = p.a_gather[min(m + 3, last)];
             }
-            for (long long k0 = kbeg; k0 < kend; k0 += TBK) {
+            for (long long k0 = kbeg; k0 < kend; k0 += kstep) {
                 if (lane == 0) {
                     mbar_wait(&empty_bar[r.stage], r.phase ^ 1);
                     mbar_expect_tx(&full_bar[r.stage], p.lsu_gather ? TILE : HALF);
@@ -622,7 +636,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     } else {
 #pragma unroll
                         for (int c = 0; c < 4; ++c)
-                            tma_load_2d(tileA(r.stage) + c * 4096, &mapA, &full_bar[r.stage], m0 + 32 * c, (int)k0);
+                            if (c < mn_boxes)
+                                tma_load_2d(tileA(r.stage) + c * mn_box_bytes, &mapA, &full_bar[r.stage], m0 + mn_box_elems * c, (int)k0);
                     }
                 }
                 if (p.lsu_gather == 2) {
@@ -642,7 +657,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     } else {
 #pragma unroll
                         for (int c = 0; c < 4; ++c)
-                            tma_load_2d(tileB(r.stage) + c * 4096, &mapB, &full_bar[r.stage], n0 + 32 * c, (int)k0);
+                            if (c < mn_boxes)
+                                tma_load_2d(tileB(r.stage) + c * mn_box_bytes, &mapB, &full_bar[r.stage], n0 + mn_box_elems * c, (int)k0);
                     }
                 }
                 r.advance(stages);
@@ -651,12 +667,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     } else if (warp == 1) {
         // ===================== MMA issuer: one thread of the LEADER CTA =====================
         if (rank == 0 && lane == 0) {
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
+            // instruction descriptor: D = F32, A/B format TF32 (2) or BF16 (1), operand majors, N >> 3, M >> 4
+            const uint32_t fmt = p.elt == 2 ? 1u : 2u;
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
                                    ((uint32_t)(T2N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-            const uint32_t a_lbo = p.a_mn ? 4096 : 16, b_lbo = p.b_mn ? 4096 : 16;
-            const uint32_t a_kadv = p.a_mn ? 1024 : 32, b_kadv = p.b_mn ? 1024 : 32;
-            const uint32_t a_sbo = p.a_mn ? 512 : 1024, b_sbo = p.b_mn ? 512 : 1024;
-            const uint32_t a_lay = p.a_mn ? 1 : 2, b_lay = p.b_mn ? 1 : 2;
+            // one MMA consumes 32 bytes of K (8 tf32 / 16 bf16).  K-major: 128-byte rows, SWIZZLE_128B.  MN-major: k-rows of
+            // 128 bytes; fp32 uses the 32-byte-atom swizzle (4-row atoms, 8 k-rows per MMA), bf16 the plain 128-byte swizzle
+            // (8-row atoms, 16 k-rows per MMA); LBO = distance between the boxes along MN
+            const uint32_t mn_lbo = (uint32_t)mn_box_bytes, mn_kadv = p.elt == 2 ? 2048u : 1024u, mn_sbo = p.elt == 2 ? 1024u : 512u;
+            const uint32_t mn_lay = p.elt == 2 ? 2u : 1u;
+            const uint32_t a_lbo = p.a_mn ? mn_lbo : 16, b_lbo = p.b_mn ? mn_lbo : 16;
+            const uint32_t a_kadv = p.a_mn ? mn_kadv : 32, b_kadv = p.b_mn ? mn_kadv : 32;
+            const uint32_t a_sbo = p.a_mn ? mn_sbo : 1024, b_sbo = p.b_mn ? mn_sbo : 1024;
+            const uint32_t a_lay = p.a_mn ? mn_lay : 2, b_lay = p.b_mn ? mn_lay : 2;
             StageRing r, acc;
             for (long long t = pair; t < total; t += npairs) {
                 const long long split = t / tiles_mn;
@@ -665,7 +688,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc.stage * acc_cols, d_corr = d_tmem + T2N;
                 uint32_t first = 1;
-                for (long long k0 = kbeg; k0 < kend; k0 += TBK) {
+                for (long long k0 = kbeg; k0 < kend; k0 += kstep) {
                     mbar_wait_cluster(&ready_bar[r.stage], r.phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(tileA(r.stage)), sb = smem_u32(tileB(r.stage));
@@ -673,6 +696,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     for (int k = 0; k < TBK / 8; ++k) {
                         const uint64_t da = umma_desc(sa + k * a_kadv, a_lbo, a_sbo, a_lay);
                         const uint64_t db = umma_desc(sb + k * b_kadv, b_lbo, b_sbo, b_lay);
+                        if (p.elt == 2) {
+                            tc2_mma_bf16(d_tmem, da, db, idesc, first ? 0u : 1u);
+                            first = 0;
+                            continue;
+                        }
                         tc2_mma_tf32(d_tmem, da, db, idesc, first ? 0u : 1u);
                         if (passes == 3) {
                             const uint64_t dal = umma_desc(sa + HALF + k * a_kadv, a_lbo, a_sbo, a_lay);
@@ -697,7 +725,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             for (long long t = pair; t < total; t += npairs) {
                 const long long split = t / tiles_mn;
                 const long long kbeg = split * p.k_per_split, kend = min(p.K, kbeg + p.k_per_split);
-                for (long long k0 = kbeg; k0 < kend; k0 += TBK) {
+                for (long long k0 = kbeg; k0 < kend; k0 += kstep) {
                     mbar_wait(&full_bar[r.stage], r.phase);
                     mbar_arrive_cluster(ready0 + 8 * r.stage);
                     r.advance(stages);
@@ -713,35 +741,42 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         // with k-row & 3 inside each 32-column chunk).
         if (p.lsu_gather) {
             StageRing r;
+            const int elt = p.elt, epc = 16 / elt;           // elements per 16-byte chunk
+            const char *Ab = reinterpret_cast<const char *>(p.A), *Bb = reinterpret_cast<const char *>(p.B);
             for (long long t = pair; t < total; t += npairs) {
                 const long long split = t / tiles_mn, mn = t - split * tiles_mn;
                 const long long m0 = (mn / p.tiles_n) * 256 + 128 * rank, n0 = (mn % p.tiles_n) * T2N + 128 * rank;
                 const long long kbeg = split * p.k_per_split, kend = min(p.K, kbeg + p.k_per_split);
                 int arow[32];
-                int myrow = -1;                 // B gather: lane l holds the table row of k-row k0 + l, loaded one stage ahead
+                int myrow = -1, myrow2 = -1;    // B gather: the table rows of k-rows k0 + lane (and k0 + 32 + lane for bf16), a stage ahead
                 if (p.lsu_gather == 1) {        // lane covers chunk (lane & 7) of rows (lane >> 3) + 4 i
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
                         arow[i] = p.a_gather[min(m0 + (lane >> 3) + 4 * i, p.M - 1)];
-                } else if (kbeg + lane < p.K) {
-                    myrow = p.b_gather[kbeg + lane];
+                } else {
+                    if (kbeg + lane < p.K) myrow = p.b_gather[kbeg + lane];
+                    if (elt == 2 && kbeg + 32 + lane < p.K) myrow2 = p.b_gather[kbeg + 32 + lane];
                 }
-                for (long long k0 = kbeg; k0 < kend; k0 += TBK) {
-                    int nextrow = -1;
-                    if (p.lsu_gather == 2 && k0 + TBK < kend && k0 + TBK + lane < p.K) nextrow = p.b_gather[k0 + TBK + lane];
+                for (long long k0 = kbeg; k0 < kend; k0 += kstep) {
+                    int nextrow = -1, nextrow2 = -1;
+                    if (p.lsu_gather == 2 && k0 + kstep < kend) {
+                        if (k0 + kstep + lane < p.K) nextrow = p.b_gather[k0 + kstep + lane];
+                        if (elt == 2 && k0 + kstep + 32 + lane < p.K) nextrow2 = p.b_gather[k0 + kstep + 32 + lane];
+                    }
                     if (lane == 0) mbar_wait(&empty_bar[r.stage], r.phase ^ 1);
                     __syncwarp();
                     if (p.lsu_gather == 1) {
                         const uint32_t dst = smem_u32(tileA(r.stage));
                         const int c = lane & 7;
-                        const long long kk = k0 + 4 * c;
-                        const int nbytes = (int)max(0LL, min(4LL, p.K - kk)) * 4;
+                        const long long kk = k0 + epc * c;
+                        const int nbytes = (int)max(0LL, min((long long)epc, p.K - kk)) * elt;
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
                             const int rr = (lane >> 3) + 4 * i;
-                            cp_async16(dst + rr * 128 + ((c ^ (rr & 7)) << 4), p.A + (long long)arow[i] * p.lda + (nbytes ? kk : 0), nbytes);
+                            cp_async16(dst + rr * 128 + ((c ^ (rr & 7)) << 4),
+                                       Ab + ((long long)arow[i] * p.lda + (nbytes ? kk : 0)) * elt, nbytes);
                         }
-                    } else {
+                    } else if (elt == 4) {
                         const uint32_t dst = smem_u32(tileB(r.stage));
                         const int c4 = lane >> 3, u = lane & 7;
                         const long long col = n0 + 32 * c4 + 4 * u;
@@ -751,7 +786,23 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                             const int row = __shfl_sync(0xffffffffu, myrow, kr);
                             const int nbytes = row >= 0 ? cbytes : 0;
                             cp_async16(dst + c4 * 4096 + kr * 128 + ((((u >> 1) ^ (kr & 3)) << 5) | ((u & 1) << 4)),
-                                       p.B + (nbytes ? (long long)row * p.ldb + col : 0), nbytes);
+                                       Bb + (nbytes ? ((long long)row * p.ldb + col) * 4 : 0), nbytes);
+                        }
+                    } else {
+                        // bf16, MN-major: a k-row of this CTA's 128 columns is 256 bytes = two 128-byte box rows; one warp
+                        // instruction copies two k-rows (16 lanes x 16 bytes each); plain 128-byte swizzle (chunk ^ (k-row & 7))
+                        const uint32_t dst = smem_u32(tileB(r.stage));
+                        const int sub = lane >> 4, c2 = (lane >> 3) & 1, u = lane & 7;
+                        const long long col = n0 + 64 * c2 + 8 * u;
+                        const int cbytes = (int)max(0LL, min(8LL, p.N - col)) * 2;
+#pragma unroll
+                        for (int kp = 0; kp < 32; ++kp) {
+                            const int kr = 2 * kp + sub;
+                            const int lo = __shfl_sync(0xffffffffu, myrow, kr & 31), hi = __shfl_sync(0xffffffffu, myrow2, kr & 31);
+                            const int row = kr < 32 ? lo : hi;
+                            const int nbytes = row >= 0 ? cbytes : 0;
+                            cp_async16(dst + c2 * 8192 + kr * 128 + ((u ^ (kr & 7)) << 4),
+                                       Bb + (nbytes ? ((long long)row * p.ldb + col) * 2 : 0), nbytes);
                         }
                     }
                     // asynchronous completion: the stage's full barrier collects one arrival per lane when that lane's
@@ -760,6 +811,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     cp_async_arrive_noinc(&full_bar[r.stage]);
                     r.advance(stages);
                     myrow = nextrow;
+                    myrow2 = nextrow2;
                 }
             }
             cp_async_wait<0>();
@@ -774,7 +826,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             for (long long t = pair; t < total; t += npairs) {
                 const long long split = t / tiles_mn;
                 const long long kbeg = split * p.k_per_split, kend = min(p.K, kbeg + p.k_per_split);
-                for (long long k0 = kbeg; k0 < kend; k0 += TBK) {
+                for (long long k0 = kbeg; k0 < kend; k0 += kstep) {
                     mbar_wait(&full_bar[r.stage], r.phase);
                     const uint32_t hi = smem_u32(tileA(r.stage)) + tid * 16;
                     float4 v[ITERS];

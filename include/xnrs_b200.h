@@ -19,8 +19,9 @@ typedef void *xnrs_stream_t; /* cudaStream_t */
 
 enum { XNRS_OK = 0, XNRS_ERR_ARG = -1, XNRS_ERR_CUDA = -2, XNRS_ERR_UNSUPPORTED = -3 };
 enum { XNRS_ACT_NONE = 0, XNRS_ACT_RELU = 1, XNRS_ACT_TANH = 2, XNRS_ACT_RELU_MASK = 3 };
-/* arithmetic of the GEMM-shaped ops: exact fp32 FMA, 3xTF32 split (fp32-accurate, tensor cores),
- * single-pass TF32, or BF16 operands with fp32 accumulation */
+/* arithmetic of the GEMM-shaped ops on fp32 operands: exact fp32 FMA, 3xTF32 split (fp32-accurate, tensor cores) or
+ * single-pass TF32.  XNRS_PREC_BF16 names the bf16-STORAGE mode: its GEMMs take bf16 operands through xnrs_gemm_bf16 /
+ * xnrs_titlepool_fwd_bf16 (tcgen05 kind::f16); xnrs_gemm itself rejects it (fp32 operands cannot be "bf16"). */
 enum { XNRS_PREC_FP32 = 0, XNRS_PREC_TF32X3 = 1, XNRS_PREC_TF32 = 2, XNRS_PREC_BF16 = 3 };
 enum { XNRS_LOSS_MSE_RELU = 0, XNRS_LOSS_BCE_LOGITS = 1, XNRS_LOSS_NLL = 2, XNRS_LOSS_BCE_SIGMOID = 3 };
 
@@ -124,6 +125,23 @@ int xnrs_addpool_bwd(const float *x, const int *x_rows, const float *mask, const
 int xnrs_titlepool_fwd(const float *x, long long ldx, const int *x_rows, const int *tix, long long n_rows, long long R, int F,
                        int A, const float *w1, const float *b1, const float *w2, const float *b2, int precision, float *hid,
                        float *e, float *zsum, float *attn, float *pooled, xnrs_stream_t st);
+/* ---- XNRS_PREC_BF16: bf16 STORAGE of the token-level tensors (token table rows x, tanh hidden layer hid, its gradient) with
+ * fp32 accumulation everywhere — the north-star's 2e-2 tolerance class.  bf16 operands are `void *` to 16-bit brain floats.
+ * xnrs_cast_bf16 rounds fp32 to nearest-even bf16 (token table once, fc1.weight per step).
+ * xnrs_gemm_bf16: C[M,N] (=|+=) act(opA(A) opB(B) + bias) on tcgen05 kind::f16 (CTA-pair kernel, fp32 TMEM accumulators);
+ * same layout rules as xnrs_gemm; a_rows (K-major A) / b_rows (MN-major B) gather table rows with the cp.async warp; C is fp32
+ * (accumulate / split-K allowed) or bf16 (c_bf16 = 1).  Returns XNRS_ERR_UNSUPPORTED off sm_100 or for unaligned operands.
+ * xnrs_titlepool_fwd_bf16 / xnrs_addpool_bwd_bf16: the fused forward and the pooling backward on bf16 x / w1 / hid / d_hid. */
+int xnrs_cast_bf16(long long n, const float *src, void *dst, xnrs_stream_t st);
+int xnrs_gemm_bf16(int transA, int transB, long long M, long long N, long long K, const void *A, long long lda,
+                   const int *a_rows, const void *B, long long ldb, const int *b_rows, void *C, long long ldc, int c_bf16,
+                   const float *bias, int act, int accumulate, int split_k, xnrs_stream_t st);
+int xnrs_titlepool_fwd_bf16(const void *x, long long ldx, const int *x_rows, const int *tix, long long n_rows, long long R, int F,
+                            int A, const void *w1, const float *b1, const float *w2, const float *b2, void *hid, float *e,
+                            float *zsum, float *attn, float *pooled, xnrs_stream_t st);
+int xnrs_addpool_bwd_bf16(const void *x, const int *x_rows, const void *hid, const float *w2, const float *attn,
+                          const float *d_pooled, const int *seg, long long R, int L, int F, int A, long long n_rows, void *d_hid,
+                          float *d_w2, float *d_b2, float *d_b1, xnrs_stream_t st);
 /* ---- row P: personalised attention (layers.py:88-101): logit = <tanh(x_fc x), q_fc(q)> ---------
  * hid (R*L,A) = tanh(x_fc x); qh (Rq,A) = q_fc(q); title r uses query row r / rows_per_query */
 int xnrs_perspool_fwd(const float *x, const int *x_rows, const float *mask, const float *hid, const float *qh,

@@ -182,6 +182,35 @@ def _xnrs_titlepool_fwd(x, ldx, x_rows, tix, n_rows, R, F_, A, w1, b1, w2, b2, p
     pooled.div_((zsum + 1e-8)[:, None])
 
 
+def _xnrs_cast_bf16(n, src, dst):
+    dst.copy_(src.to(torch.bfloat16))
+
+
+def _xnrs_gemm_bf16(ta, tb, M, N, K_, A, lda, a_rows, B, ldb, b_rows, C, ldc, c_bf16, bias, act, accumulate, split_k):
+    a = _rows(A, a_rows).float()
+    b = _rows(B, b_rows).float()
+    y = (a.T if ta else a) @ (b.T if tb else b)
+    if bias is not None:
+        y = y + bias
+    y = torch.relu(y) if act == K.ACT_RELU else (torch.tanh(y) if act == K.ACT_TANH else y)
+    C.copy_((C.float() + y if accumulate else y).to(C.dtype))
+
+
+def _xnrs_titlepool_fwd_bf16(x, ldx, x_rows, tix, n_rows, R, F_, A, w1, b1, w2, b2, hid, e, zsum, attn, pooled):
+    h32 = torch.empty(hid.shape, dtype=torch.float32)
+    _xnrs_titlepool_fwd(x.float(), ldx, x_rows, tix, n_rows, R, F_, A, w1.float(), b1, w2, b2, 3, h32, e, zsum, attn, pooled)
+    hid.copy_(h32.to(torch.bfloat16))
+
+
+def _xnrs_addpool_bwd_bf16(x, x_rows, hid, w2, attn, d_pooled, seg, R, L, F_, A, n_rows, d_hid, d_w2, d_b2, d_b1):
+    d32 = torch.empty(d_hid.shape, dtype=torch.float32)
+    _xnrs_addpool_bwd(x.float(), x_rows, None, hid.float(), w2, attn, d_pooled, None, seg, R, L, F_, A, n_rows, d32, d_w2, d_b2,
+                      None, None)
+    d_hid.copy_(d32.to(torch.bfloat16))
+    if d_b1 is not None:
+        d_b1.add_(d_hid.float().sum(0))
+
+
 def _xnrs_addpool_bwd(x, x_rows, mask, hid, w2, attn, d_pooled, d_attn, seg, R, L, F_, A, n_rows, d_hid, d_w2, d_b2, d_x, d_b1):
     dl = _pool_dlogit(x, x_rows, attn, d_pooled, d_attn, seg, R, L)
     d_hid.copy_(dl[:, None] * w2[None, :] * (1 - hid * hid))

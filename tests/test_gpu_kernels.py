@@ -525,3 +525,48 @@ def test_plan_kernels_match_torch_index_ops(n_news, S, n):
     tok = tt[uniq.long()].reshape(-1)
     assert torch.equal(plan.rows[:U * S].cpu(), tok) and int(plan.rows[U * S:].abs().sum()) == 0
     assert torch.equal(plan.mask[:U * S].cpu(), (tok != 0).float()) and float(plan.mask[U * S:].sum()) == 0
+
+
+@pytest.mark.parametrize('ta,tb', [(0, 1), (1, 0), (0, 0), (1, 1)])
+def test_bf16_tensor_core_gemm(ta, tb):
+    """xnrs_gemm_bf16 (tcgen05 kind::f16 on the CTA-pair kernel): all four operand layouts, ragged sizes, bias / tanh, bf16 and
+    fp32 outputs, split-K accumulation — against float64 on the bf16-rounded operands"""
+    for M, N, K_ in [(1000, 200, 1344), (4097, 768, 768), (256, 768, 9000)]:
+        a = (torch.randn((K_, M) if ta else (M, K_), generator=g(1)) / math.sqrt(K_)).bfloat16()
+        b = torch.randn((N, K_) if tb else (K_, N), generator=g(2)).bfloat16()
+        bias = torch.randn(N, generator=g(3))
+        want = (a.double().T if ta else a.double()) @ (b.double().T if tb else b.double())
+        got = K.gemm_bf16(cu(a), cu(b), trans_a=bool(ta), trans_b=bool(tb))
+        assert_close(got, want.float(), 2e-5, f'bf16 gemm fp32 out {M}x{N}x{K_}')
+        got = K.gemm_bf16(cu(a), cu(b), trans_a=bool(ta), trans_b=bool(tb), bias=cu(bias), act=K.ACT_TANH, out_bf16=True)
+        assert got.dtype == torch.bfloat16
+        assert_close(got.float(), torch.tanh(want + bias.double()).float(), 8e-3, 'bf16 gemm bf16 out + tanh')
+        acc = torch.ones(M, N)
+        out = cu(acc.clone())
+        K.gemm_bf16(cu(a), cu(b), trans_a=bool(ta), trans_b=bool(tb), out=out, accumulate=True, split_k=3)
+        assert_close(out, (want + 1).float(), 2e-5, 'bf16 gemm split-K accumulate')
+
+
+def test_bf16_tensor_core_gemm_fused_gather():
+    """bf16 table rows gathered by the cp.async warp: forward (rows of A) and weight-gradient (rows of B along K) forms"""
+    V, D, A_ = 5000, 768, 256
+    table = (torch.randn(V, D, generator=g(1)) / math.sqrt(D)).bfloat16()
+    for R in (1650, 41000):
+        rows = torch.randint(0, V, (R,), generator=g(2)).int()
+        w = torch.randn(A_, D, generator=g(3)).bfloat16()
+        want = table[rows.long()].double() @ w.double().T
+        got = K.gemm_bf16(cu(table), cu(w), trans_b=True, a_rows=cu(rows))
+        assert_close(got, want.float(), 2e-5, 'bf16 gathered forward')
+        d = torch.randn(R, A_, generator=g(5)).bfloat16()
+        want_dw = d.double().T @ table[rows.long()].double()
+        got_dw = K.gemm_bf16(cu(d), cu(table), trans_a=True, b_rows=cu(rows))
+        assert_close(got_dw, want_dw.float(), 5e-5, 'bf16 gathered weight gradient')
+
+
+def test_gemm_rejects_the_bf16_precision_on_fp32_operands():
+    with K.precision('bf16'):
+        assert K._gemm_precision() == K.PRECISIONS['tf32']          # python maps fp32-stored GEMMs of the bf16 mode to TF32
+    with pytest.raises(RuntimeError, match='xnrs_gemm_bf16'):
+        a = cu(torch.randn(256, 64))
+        K.call('xnrs_gemm', 0, 1, 256, 256, 64, K._mat(a), 64, None, K._mat(a), 64, None, K._mat(cu(torch.empty(256, 256))), 256, None, 0,
+               None, 0, 0, K.PRECISIONS['bf16'])

@@ -215,13 +215,14 @@ def _chunked_oracle_step(P, cat, raw, temperature, lam, chunk=64):
     return l_rec + lam * float(l_cl.detach()), l_rec, float(l_cl.detach())
 
 
-def test_bench_config_step_matches_oracle(monkeypatch):
+@pytest.mark.parametrize('prec,tol', [('tf32x3', 1e-4), ('bf16', 2e-2)])
+def test_bench_config_step_matches_oracle(prec, tol, monkeypatch):
     """ONE step of bench.py's headline configuration — B=1024 impressions, S=30, H=50, 65 238-news catalogue, 100k-row token
     table, 3xTF32, title de-duplication + padding-free pooling + prefetched id plumbing + item-logit user pooling — checked
     against the CPU oracle on the same ids: total / rec / CL loss and EVERY parameter gradient of the flat buffer."""
     import bench
     from xnrs_b200 import kernels as K
-    monkeypatch.setattr(K, '_precision', K.PRECISIONS['tf32x3'])
+    monkeypatch.setattr(K, '_precision', K.PRECISIONS[prec])
     B = 1024
     cfg = dict(bench.CL_CFG, device=DEV)
     cat = syn.make_catalogue(bench.N_NEWS, bench.SEQ_LEN, bench.VOCAB, 768, seed=0)
@@ -240,15 +241,15 @@ def test_bench_config_step_matches_oracle(monkeypatch):
     torch.cuda.synchronize()
     assert int(_lib_fallbacks()) >= 0
     want_total, want_rec, want_cl = _chunked_oracle_step(P, cat, raw, cfg['contrastive_temperature'], cfg['contrastive_lambda'])
-    assert_close(l_rec, torch.tensor(want_rec), 1e-4, 'rec loss')
-    assert_close(l_cl, torch.tensor(want_cl), 1e-4, 'cl loss')
-    assert_close(total, torch.tensor(want_total), 1e-4, 'total loss')
+    assert_close(l_rec, torch.tensor(want_rec), tol, 'rec loss')
+    assert_close(l_cl, torch.tensor(want_cl), tol, 'cl loss')
+    assert_close(total, torch.tensor(want_total), tol, 'total loss')
     named = dict(model.named_parameters())
     gscale = max(float(v.grad.abs().max()) for v in P.values() if v.grad is not None)
     for k, v in P.items():
         if v.grad is None:
             continue
-        assert_close(named[k].grad, v.grad, 2e-4, 'grad ' + k, atol=2e-6 * gscale)
+        assert_close(named[k].grad, v.grad, 2 * tol, 'grad ' + k, atol=(2e-6 if prec == 'tf32x3' else 2e-3) * gscale)
 
 
 def _lib_fallbacks():

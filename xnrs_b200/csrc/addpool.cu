@@ -5,6 +5,8 @@
 // logit = <hid, w> (+b), exp, multiplicative mask, normalisation by (sum + 1e-8) and the weighted sum
 // over the (optionally table-gathered) rows of x.  One CTA walks titles grid-stride; rows whose
 // weight is exactly 0 (padding) are never read.  HBM-bound: per title it reads L*A (hid) + L*F (x).
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace xnrs {
@@ -171,6 +173,91 @@ pool_bwd_kernel(const float *__restrict__ x, const int *__restrict__ x_rows, con
         for (long long i = t0 + blockIdx.x * (long long)blockDim.x + tid; i < t1; i += (long long)gridDim.x * blockDim.x)
             d_hid[i] = 0.f;
     }
+}
+
+// bf16-storage twin of pool_bwd_kernel<false> (XNRS_PREC_BF16: token rows x, hid and d_hid are bf16 in HBM, every sum is
+// fp32): x rows come from the bf16 token table through x_rows; no d_x / d_attn (the table is frozen).
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+__global__ void __launch_bounds__(POOL_THREADS)
+pool_bwd_bf16_kernel(const __nv_bfloat16 *__restrict__ x, const int *__restrict__ x_rows, const __nv_bfloat16 *__restrict__ hid,
+                     const float *__restrict__ w2, const float *__restrict__ attn, const float *__restrict__ d_pooled,
+                     const int *__restrict__ seg, long long R, int L, int F, int A, long long n_rows,
+                     __nv_bfloat16 *__restrict__ d_hid, float *__restrict__ d_w2, float *__restrict__ d_b2, float *__restrict__ d_b1) {
+    extern __shared__ float sm[];
+    float *da = sm, *al = sm + L, *dw = sm + 2 * L, *db1 = sm + 2 * L + A;
+    __shared__ float db_acc;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int F8 = F >> 3, F4 = F >> 2;
+    const uint4 *x8 = reinterpret_cast<const uint4 *>(x);
+    for (int j = tid; j < A; j += blockDim.x) { dw[j] = 0.f; db1[j] = 0.f; }
+    if (tid == 0) db_acc = 0.f;
+    __syncthreads();
+    const int Lmax = L;
+    for (long long r = blockIdx.x; r < R; r += gridDim.x) {
+        const long long base = seg ? (long long)seg[r] : r * (long long)Lmax;
+        const int L = seg ? seg[r + 1] - seg[r] : Lmax;
+        const float4 *dp4 = reinterpret_cast<const float4 *>(d_pooled) + r * F4;
+        for (int l = warp; l < L; l += nwarps) {
+            const float a = attn[base + l];
+            float acc = 0.f;
+            if (a != 0.f) {
+                const long long row = x_rows ? (long long)x_rows[base + l] : base + l;
+                for (int c = lane; c < F8; c += 32) {
+                    const uint4 v = __ldg(x8 + row * F8 + c);
+                    const float4 g0 = dp4[2 * c], g1 = dp4[2 * c + 1];
+                    acc = fmaf(bf16_lo(v.x), g0.x, acc); acc = fmaf(bf16_hi(v.x), g0.y, acc);
+                    acc = fmaf(bf16_lo(v.y), g0.z, acc); acc = fmaf(bf16_hi(v.y), g0.w, acc);
+                    acc = fmaf(bf16_lo(v.z), g1.x, acc); acc = fmaf(bf16_hi(v.z), g1.y, acc);
+                    acc = fmaf(bf16_lo(v.w), g1.z, acc); acc = fmaf(bf16_hi(v.w), g1.w, acc);
+                }
+                acc = warp_sum(acc);
+            }
+            if (lane == 0) { da[l] = acc; al[l] = a; }
+        }
+        __syncthreads();
+        float dot = 0.f;
+        for (int l = 0; l < L; ++l) dot = fmaf(al[l], da[l], dot);
+        __syncthreads();
+        for (int l = tid; l < L; l += blockDim.x) da[l] = al[l] * (da[l] - dot);     // dlogit
+        __syncthreads();
+        for (int j = tid; j < A; j += blockDim.x) {
+            const float w = w2[j];
+            float gw = 0.f, gb = 0.f;
+            for (int l = 0; l < L; ++l) {
+                const long long idx = (base + l) * A + j;
+                const float dl = da[l], h = __bfloat162float(hid[idx]);
+                gw = fmaf(dl, h, gw);
+                const __nv_bfloat16 g16 = __float2bfloat16_rn(dl * w * (1.f - h * h));
+                d_hid[idx] = g16;
+                gb += __bfloat162float(g16);          // the bias gradient sums the STORED values, as a column sum of d_hid would
+            }
+            db1[j] += gb;
+            dw[j] += gw;
+        }
+        if (tid == 0) {
+            float sacc = 0.f;
+            for (int l = 0; l < L; ++l) sacc += da[l];
+            db_acc += sacc;
+        }
+        __syncthreads();
+    }
+    for (int j = tid; j < A; j += blockDim.x) {
+        atomicAdd(d_w2 + j, dw[j]);
+        if (d_b1) atomicAdd(d_b1 + j, db1[j]);
+    }
+    if (tid == 0) atomicAdd(d_b2, db_acc);
+    if (seg && n_rows > 0) {
+        const long long t0 = (long long)seg[R] * A, t1 = n_rows * A;
+        for (long long i = t0 + blockIdx.x * (long long)blockDim.x + tid; i < t1; i += (long long)gridDim.x * blockDim.x)
+            d_hid[i] = __float2bfloat16_rn(0.f);
+    }
+}
+
+__global__ void cast_bf16_kernel(long long n, const float *__restrict__ src, __nv_bfloat16 *__restrict__ dst) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = __float2bfloat16_rn(src[i]);
 }
 
 // ---- warp-per-group forward (used when there are thousands of groups): no block barriers, one warp owns a title from
@@ -597,6 +684,29 @@ extern "C" int xnrs_addpool_bwd(const float *x, const int *x_rows, const float *
     XNRS_REQUIRE(!(d_x && x_rows), "d_x is only defined for dense x");
     pool_bwd_kernel<false><<<pool_grid(R), POOL_THREADS, (2 * L + 2 * A) * sizeof(float), STREAM(st)>>>(
             x, x_rows, hid, w2, nullptr, 1, attn, d_pooled, d_attn, seg, R, L, F, A, n_rows, d_hid, d_w2, d_b2, nullptr, d_x, d_b1);
+    XNRS_LAUNCHED();
+    return XNRS_OK;
+}
+
+extern "C" int xnrs_addpool_bwd_bf16(const void *x, const int *x_rows, const void *hid, const float *w2, const float *attn,
+                                     const float *d_pooled, const int *seg, long long R, int L, int F, int A, long long n_rows,
+                                     void *d_hid, float *d_w2, float *d_b2, float *d_b1, xnrs_stream_t st) {
+    if (R < 0 || L <= 0 || F <= 0 || A <= 0 || F % 8) return fail(XNRS_ERR_ARG, "%s: bad sizes (F % 8 == 0)", "xnrs_addpool_bwd_bf16");
+    if (R == 0) return XNRS_OK;
+    XNRS_REQUIRE(x && hid && w2 && attn && d_pooled && d_hid && d_w2 && d_b2, "null pointer");
+    XNRS_REQUIRE(!((uintptr_t)x & 15) && !((uintptr_t)d_pooled & 15), "x and d_pooled must be 16-byte aligned");
+    pool_bwd_bf16_kernel<<<pool_grid(R), POOL_THREADS, (2 * L + 2 * A) * sizeof(float), STREAM(st)>>>(
+        reinterpret_cast<const __nv_bfloat16 *>(x), x_rows, reinterpret_cast<const __nv_bfloat16 *>(hid), w2, attn, d_pooled, seg, R,
+        L, F, A, n_rows, reinterpret_cast<__nv_bfloat16 *>(d_hid), d_w2, d_b2, d_b1);
+    XNRS_LAUNCHED();
+    return XNRS_OK;
+}
+
+extern "C" int xnrs_cast_bf16(long long n, const float *src, void *dst, xnrs_stream_t st) {
+    if (n <= 0) return XNRS_OK;
+    XNRS_REQUIRE(src && dst, "null pointer");
+    long long b = cdiv(n, 256), cap = 16LL * num_sms();
+    cast_bf16_kernel<<<(unsigned)(b > cap ? cap : b), 256, 0, STREAM(st)>>>(n, src, reinterpret_cast<__nv_bfloat16 *>(dst));
     XNRS_LAUNCHED();
     return XNRS_OK;
 }

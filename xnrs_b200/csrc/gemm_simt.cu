@@ -216,6 +216,8 @@ extern "C" int xnrs_gemm(int transA, int transB, long long M, long long N, long 
     XNRS_REQUIRE(lda >= (transA ? M : K) && ldb >= (transB ? K : N) && ldc >= N, "leading dimension too small");
     XNRS_REQUIRE(act >= 0 && act <= 3, "bad activation");
     XNRS_REQUIRE(act != XNRS_ACT_RELU_MASK || aux, "RELU_MASK needs aux");
+    if (precision == XNRS_PREC_BF16)
+        return fail(XNRS_ERR_UNSUPPORTED, "%s: XNRS_PREC_BF16 means bf16 operands: call xnrs_gemm_bf16 (fp32 operands run in FP32 / TF32X3 / TF32)", "xnrs_gemm");
     XNRS_REQUIRE(cdiv(M, BM) * cdiv(N, BN) < 2147483647LL, "too many tiles for one launch");
     GemmArgs a{M, N, K, A, lda, a_rows, transA, B, ldb, b_rows, transB, C, ldc, bias, act, aux, accumulate,
                split_k, 0};

@@ -18,6 +18,7 @@
 // Both operand majors are supported through the UMMA descriptors (K-major: nn.Linear forward;
 // MN-major: weight-gradient and input-gradient GEMMs), so no transposed copies are ever made.
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <algorithm>
 #include <stdlib.h>
 #include <string.h>
@@ -224,6 +225,21 @@ __device__ __forceinline__ void epi_rows(uint32_t stage, const TcArgs &p, const 
         } else if (ACT == XNRS_ACT_TANH) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) x[e] = tanh_fast(x[e]);
+        }
+        if (p.c_bf16) {         // bf16 C (no accumulate / split-K / ReLU mask: checked on the host), 8-byte stores
+            __nv_bfloat16 *d16 = reinterpret_cast<__nv_bfloat16 *>(p.C) + row * p.ldc + col;
+            if (nv == 4) {
+                const __nv_bfloat162 lo = __floats2bfloat162_rn(x[0], x[1]), hi = __floats2bfloat162_rn(x[2], x[3]);
+                uint2 pk;
+                pk.x = *reinterpret_cast<const uint32_t *>(&lo);
+                pk.y = *reinterpret_cast<const uint32_t *>(&hi);
+                *reinterpret_cast<uint2 *>(d16) = pk;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (e < nv) d16[e] = __float2bfloat16_rn(x[e]);
+            }
+            continue;
         }
         if (vec_ok && nv == 4) {
             if (ACT == XNRS_ACT_RELU_MASK) {
@@ -910,6 +926,74 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 // active) and walks ALL rows, eight independent row loads in flight; the x rows were fetched from the table
                 // moments ago (L2 hits).  A title's partial sums leave through 16-byte vector reductions when the title ends.
                 const int w8 = warp - EPI2_WARP0, F4 = p.pool.F4, per = F4 >> 3;     // float4 columns per warp (24 at F=768)
+                if (p.elt == 2) {
+                    // bf16 rows: 16-byte loads carry 8 elements, so a warp's F/8-column slice is F/64 lanes wide (12 at F=768)
+                    const int per8 = F4 >> 4;
+                    const bool act8 = lane < per8;
+                    const uint4 *x8 = reinterpret_cast<const uint4 *>(p.A) + (act8 ? w8 * per8 + lane : 0);
+                    float *poolf = p.pool.pooled + (act8 ? (w8 * per8 + lane) * 8 : 0);
+                    const long long ld8 = p.lda >> 3;
+                    int tixv[4], srcv[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const long long g = m0 + lane + 32 * j;
+                        tixv[j] = g < p.M ? __ldg(p.pool.tix + g) : -1;
+                        srcv[j] = g < p.M ? (p.a_gather ? __ldg(p.a_gather + g) : (int)g) : 0;
+                    }
+                    float a8[8];
+#pragma unroll
+                    for (int q8 = 0; q8 < 8; ++q8) a8[q8] = 0.f;
+                    float zs = 0.f;
+                    int cur = -1;
+                    auto flush8 = [&]() {
+                        if (cur >= 0) {
+                            if (act8) {
+                                float4 *dst = reinterpret_cast<float4 *>(poolf + (long long)cur * F4 * 4);
+                                atomicAdd(dst, make_float4(a8[0], a8[1], a8[2], a8[3]));
+                                atomicAdd(dst + 1, make_float4(a8[4], a8[5], a8[6], a8[7]));
+                            }
+                            if (lane == 0 && w8 == 0) atomicAdd(p.pool.zsum + cur, zs);
+                        }
+                    };
+#pragma unroll 1
+                    for (int r0 = 0; r0 < 128; r0 += 8) {
+                        uint4 v[8];
+                        int ti[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int row = r0 + i, j = row >> 5;
+                            const int tj = j == 0 ? tixv[0] : (j == 1 ? tixv[1] : (j == 2 ? tixv[2] : tixv[3]));
+                            const int sj = j == 0 ? srcv[0] : (j == 1 ? srcv[1] : (j == 2 ? srcv[2] : srcv[3]));
+                            ti[i] = __shfl_sync(0xffffffffu, tj, row & 31);
+                            const long long src = __shfl_sync(0xffffffffu, sj, row & 31);
+                            v[i] = (act8 && ti[i] >= 0) ? __ldg(x8 + src * ld8) : make_uint4(0u, 0u, 0u, 0u);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int row = r0 + i;
+                            if (ti[i] != cur) {
+                                flush8();
+                                cur = ti[i];
+                                zs = 0.f;
+#pragma unroll
+                                for (int q8 = 0; q8 < 8; ++q8) a8[q8] = 0.f;
+                            }
+                            if (ti[i] >= 0) {
+                                const float e = stagef(row >> 5)[32 + (row & 31)];
+                                zs += e;
+                                const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+                                for (int q8 = 0; q8 < 4; ++q8) {        // bf16 -> fp32 is a 16-bit shift
+                                    a8[2 * q8] = fmaf(e, __uint_as_float(w[q8] << 16), a8[2 * q8]);
+                                    a8[2 * q8 + 1] = fmaf(e, __uint_as_float(w[q8] & 0xffff0000u), a8[2 * q8 + 1]);
+                                }
+                            }
+                        }
+                    }
+                    flush8();
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    continue;
+                }
                 const bool active = lane < per;
                 const float4 *x4 = reinterpret_cast<const float4 *>(p.A) + (active ? w8 * per + lane : 0);
                 float4 *pool4 = reinterpret_cast<float4 *>(p.pool.pooled) + (active ? w8 * per + lane : 0);
@@ -1010,6 +1094,20 @@ static bool make_map(CUtensorMap *map, const float *base, long long inner, long 
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// 2-D bf16 tensor map: box {64 elements = 128 bytes, box_outer rows}, 128-byte swizzle (K-major and MN-major alike)
+static bool make_map_bf16(CUtensorMap *map, const void *base, long long inner, long long outer, long long ld, int box_outer) {
+    if (outer <= 0) outer = 1;
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 int g_opt_2cta = -2;       // -2: read XNRS_GEMM_2CTA on first use
 
 int gemm_tensorcore(const GemmArgs &a, int precision, cudaStream_t st, int *status) {
@@ -1032,6 +1130,8 @@ int gemm_tensorcore(const GemmArgs &a, int precision, cudaStream_t st, int *stat
     p.a_gather = a.a_rows; p.b_gather = a.b_rows;
     p.A = a.A; p.lda = a.lda; p.B = a.B; p.ldb = a.ldb;
     p.lsu_gather = 0;
+    p.elt = 4; p.c_bf16 = 0;
+    memset(&p.pool, 0, sizeof(p.pool));
     p.passes = (precision == XNRS_PREC_TF32X3) ? 3 : 1;
     // 3xTF32 keeps BN=128: its stage is 2x larger (hi+lo), and 3 smem stages + 2 TMEM stages beat the wider tile
     // (measured: 156 vs 142 TFLOP/s); single-pass TF32 takes BN=256 (398 vs 340 TFLOP/s)
@@ -1161,36 +1261,43 @@ using namespace xnrs;
 // gather -> fc1 (+bias, tanh) -> <., w2> + b2 -> exp -> per-title sum(e), sum(e * x) in ONE launch of the CTA-pair tcgen05
 // kernel (cp.async gather warp + pooling epilogue), then a small normalisation pass.  Returns XNRS_ERR_UNSUPPORTED (nothing
 // launched) for shapes / devices / precisions the fused kernel does not cover; the caller then runs xnrs_gemm + xnrs_addpool_fwd.
-extern "C" int xnrs_titlepool_fwd(const float *x, long long ldx, const int *x_rows, const int *tix, long long n_rows, long long R,
-                                  int F, int A, const float *w1, const float *b1, const float *w2, const float *b2,
-                                  int precision, float *hid, float *e, float *zsum, float *attn, float *pooled,
-                                  xnrs_stream_t st_) {
+// shared by the fp32-storage (tf32 / 3xtf32) and the bf16-storage entry points: x / w1 / hid are fp32 (elt 4) or bf16 (elt 2)
+static int titlepool_fwd_impl(const void *x, long long ldx, const int *x_rows, const int *tix, long long n_rows, long long R,
+                              int F, int A, const void *w1, const float *b1, const float *w2, const float *b2, int passes, int elt,
+                              void *hid, float *e, float *zsum, float *attn, float *pooled, cudaStream_t st) {
     XNRS_REQUIRE(x && tix && w1 && b1 && w2 && b2 && hid && e && zsum && attn && pooled, "null pointer");
     XNRS_REQUIRE(n_rows >= 0 && R >= 0 && F > 0 && A > 0, "bad sizes");
-    cudaStream_t st = STREAM(st_);
     static int is_sm100 = -1;
     if (is_sm100 < 0) is_sm100 = xnrs_device_is_sm100();
-    if (!is_sm100 || (precision != XNRS_PREC_TF32X3 && precision != XNRS_PREC_TF32) || A != 256 || F % 128 || F > 1024 ||
-        n_rows < 256 || ldx % 4 || ((uintptr_t)x & 15) || ((uintptr_t)w1 & 15) || ((uintptr_t)hid & 15) || ((uintptr_t)pooled & 15) ||
-        num_sms() % 2)
+    if (!is_sm100 || A != 256 || F % 128 || F > 1024 || n_rows < 256 || ldx % (16 / elt) || ((uintptr_t)x & 15) ||
+        ((uintptr_t)w1 & 15) || ((uintptr_t)hid & 15) || ((uintptr_t)pooled & 15) || num_sms() % 2)
         return fail(XNRS_ERR_UNSUPPORTED, "%s: shape / device / precision not covered by the fused kernel", "xnrs_titlepool_fwd");
     TcArgs p;
     memset(&p, 0, sizeof(p));
     p.M = n_rows; p.N = A; p.K = F;
-    p.C = hid; p.ldc = A; p.bias = b1; p.act = XNRS_ACT_TANH; p.aux = nullptr; p.accumulate = 0;
-    p.split_k = 1; p.k_per_split = cdiv(F, TBK) * TBK;
+    p.C = reinterpret_cast<float *>(hid); p.ldc = A; p.bias = b1; p.act = XNRS_ACT_TANH; p.aux = nullptr; p.accumulate = 0;
+    p.elt = elt; p.c_bf16 = elt == 2;
+    const int kstep = elt == 2 ? 64 : TBK;
+    p.split_k = 1; p.k_per_split = cdiv(F, kstep) * kstep;
     p.a_mn = 0; p.b_mn = 0;
     p.a_gather = x_rows; p.b_gather = nullptr;
-    p.A = x; p.lda = ldx; p.B = w1; p.ldb = F;
+    p.A = reinterpret_cast<const float *>(x); p.lda = ldx; p.B = reinterpret_cast<const float *>(w1); p.ldb = F;
     p.lsu_gather = x_rows ? 1 : 0;
-    p.passes = precision == XNRS_PREC_TF32X3 ? 3 : 1;
+    p.passes = passes;
     p.pool.w2 = w2; p.pool.b2 = b2; p.pool.tix = tix; p.pool.e = e; p.pool.zsum = zsum; p.pool.pooled = pooled; p.pool.F4 = F / 4;
     const int half = 2 * TBM * TBK * 4;
     p.stages = SMEM_DATA / (half * (p.passes == 3 ? 2 : 1));
     if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
     p.tiles_m = cdiv(n_rows, 256); p.tiles_n = 1;
     CUtensorMap mapA, mapB;
-    bool ok = make_map(&mapA, x, F, x_rows ? 0x7fffffffLL : n_rows, ldx, x_rows ? 1 : TBM, false) && make_map(&mapB, w1, F, A, F, 128, false);
+    bool ok;
+    if (elt == 2) {
+        ok = make_map_bf16(&mapB, w1, F, A, F, 128);
+        ok = ok && (x_rows ? make_map_bf16(&mapA, w1, F, A, F, 128) : make_map_bf16(&mapA, x, F, n_rows, ldx, TBM));
+    } else {
+        ok = make_map(&mapA, reinterpret_cast<const float *>(x), F, x_rows ? 0x7fffffffLL : n_rows, ldx, x_rows ? 1 : TBM, false) &&
+             make_map(&mapB, reinterpret_cast<const float *>(w1), F, A, F, 128, false);
+    }
     if (!ok) return fail(XNRS_ERR_UNSUPPORTED, "%s: tensor map encoding failed", "xnrs_titlepool_fwd");
     const int smem_bytes = SMEM_DATA + SMEM_EPI + 1024;
     static bool attr_set = false;
@@ -1210,6 +1317,88 @@ extern "C" int xnrs_titlepool_fwd(const float *x, long long ldx, const int *x_ro
     const long long work = std::max<long long>(n_rows, R * (F / 4));
     long long blocks = cdiv(work, 256), cap = 8LL * num_sms();
     titlepool_finalize_kernel<<<(unsigned)std::max<long long>(1, std::min(blocks, cap)), 256, 0, st>>>(e, tix, zsum, n_rows, R, F / 4, attn, pooled);
+    XNRS_LAUNCHED();
+    return XNRS_OK;
+}
+
+extern "C" int xnrs_titlepool_fwd(const float *x, long long ldx, const int *x_rows, const int *tix, long long n_rows, long long R,
+                                  int F, int A, const float *w1, const float *b1, const float *w2, const float *b2,
+                                  int precision, float *hid, float *e, float *zsum, float *attn, float *pooled,
+                                  xnrs_stream_t st) {
+    if (precision != XNRS_PREC_TF32X3 && precision != XNRS_PREC_TF32)
+        return fail(XNRS_ERR_UNSUPPORTED, "%s: fp32-storage fused pooling runs in the TF32X3 / TF32 precisions", "xnrs_titlepool_fwd");
+    return titlepool_fwd_impl(x, ldx, x_rows, tix, n_rows, R, F, A, w1, b1, w2, b2, precision == XNRS_PREC_TF32X3 ? 3 : 1, 4, hid, e,
+                              zsum, attn, pooled, STREAM(st));
+}
+
+extern "C" int xnrs_titlepool_fwd_bf16(const void *x, long long ldx, const int *x_rows, const int *tix, long long n_rows,
+                                       long long R, int F, int A, const void *w1, const float *b1, const float *w2,
+                                       const float *b2, void *hid, float *e, float *zsum, float *attn, float *pooled,
+                                       xnrs_stream_t st) {
+    return titlepool_fwd_impl(x, ldx, x_rows, tix, n_rows, R, F, A, w1, b1, w2, b2, 1, 2, hid, e, zsum, attn, pooled, STREAM(st));
+}
+
+// C[M,N] (=|+=) act(opA(A) opB(B) + bias) with bf16 operands (tcgen05 kind::f16, fp32 accumulation in TMEM) on the CTA-pair
+// kernel.  C is fp32 (split-K / accumulate allowed) or bf16 (c_bf16: plain store).  a_rows / b_rows gather table rows with
+// the cp.async producer warp (K-major A / MN-major B, as in the fp32 kernel).
+extern "C" int xnrs_gemm_bf16(int transA, int transB, long long M, long long N, long long K, const void *A, long long lda,
+                              const int *a_rows, const void *B, long long ldb, const int *b_rows, void *C, long long ldc,
+                              int c_bf16, const float *bias, int act, int accumulate, int split_k, xnrs_stream_t st_) {
+    XNRS_REQUIRE(M > 0 && N > 0 && K > 0 && A && B && C, "bad arguments");
+    XNRS_REQUIRE(act == XNRS_ACT_NONE || act == XNRS_ACT_RELU || act == XNRS_ACT_TANH, "activation");
+    XNRS_REQUIRE(!(c_bf16 && (accumulate || split_k > 1)), "a bf16 C cannot accumulate / split K");
+    cudaStream_t st = STREAM(st_);
+    static int is_sm100 = -1;
+    if (is_sm100 < 0) is_sm100 = xnrs_device_is_sm100();
+    if (!is_sm100 || num_sms() % 2 || lda % 8 || ldb % 8 || ((uintptr_t)A & 15) || ((uintptr_t)B & 15) || (a_rows && transA) ||
+        (b_rows && transB) || (c_bf16 ? ldc % 4 : 0) || M > 2000000000LL || N > 2000000000LL || K > 2000000000LL)
+        return fail(XNRS_ERR_UNSUPPORTED, "%s: shape / alignment / device not covered by the bf16 tensor-core kernel", "xnrs_gemm_bf16");
+    TcArgs p;
+    memset(&p, 0, sizeof(p));
+    p.M = M; p.N = N; p.K = K;
+    p.C = reinterpret_cast<float *>(C); p.ldc = ldc; p.bias = bias; p.act = act; p.aux = nullptr; p.accumulate = accumulate;
+    p.elt = 2; p.c_bf16 = c_bf16;
+    p.a_mn = transA ? 1 : 0; p.b_mn = transB ? 0 : 1;
+    p.a_gather = a_rows; p.b_gather = b_rows;
+    p.A = reinterpret_cast<const float *>(A); p.lda = lda; p.B = reinterpret_cast<const float *>(B); p.ldb = ldb;
+    p.lsu_gather = a_rows ? 1 : (b_rows ? 2 : 0);
+    XNRS_REQUIRE(!(a_rows && b_rows), "one gathered operand at a time");
+    p.passes = 1;
+    p.stages = MAX_STAGES;
+    p.tiles_m = cdiv(M, 256); p.tiles_n = cdiv(N, 256);
+    const long long tiles = p.tiles_m * p.tiles_n, npairs = num_sms() / 2;
+    long long split = split_k;
+    if (split <= 0) {
+        split = tiles >= npairs ? 1 : npairs / tiles;
+        split = std::max(1LL, std::min(split, cdiv(K, 1024)));
+        if (act != XNRS_ACT_NONE || c_bf16) split = 1;
+    }
+    XNRS_REQUIRE(split == 1 || act == XNRS_ACT_NONE, "split_k with activation");
+    p.split_k = (int)split;
+    p.k_per_split = cdiv(cdiv(K, split), 64) * 64;
+    CUtensorMap mapA, mapB;
+    bool ok = true;
+    if (!a_rows) ok = p.a_mn ? make_map_bf16(&mapA, A, M, K, lda, 64) : make_map_bf16(&mapA, A, K, M, lda, TBM);
+    if (ok && !b_rows) ok = p.b_mn ? make_map_bf16(&mapB, B, N, K, ldb, 64) : make_map_bf16(&mapB, B, K, N, ldb, 128);
+    if (a_rows) mapA = mapB;
+    if (b_rows) mapB = mapA;
+    if (!ok) return fail(XNRS_ERR_UNSUPPORTED, "%s: tensor map encoding failed", "xnrs_gemm_bf16");
+    if (split > 1 && !accumulate) {
+        if (cudaMemset2DAsync(C, ldc * sizeof(float), 0, N * sizeof(float), M, st) != cudaSuccess)
+            return fail(XNRS_ERR_CUDA, "%s: memset2d failed", "xnrs_gemm_bf16");
+    }
+    const int smem_bytes = SMEM_DATA + SMEM_EPI + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(gemm_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(XNRS_ERR_UNSUPPORTED, "%s: cannot reserve shared memory", "xnrs_gemm_bf16");
+        }
+        attr_set = true;
+    }
+    const long long total = tiles * split, pairs = total < npairs ? total : npairs;
+    gemm_tc2_kernel<false><<<(unsigned)(2 * pairs), TC2_THREADS, smem_bytes, st>>>(mapA, mapB, p);
+    g_last_gemm_kernel = "gemm_tc2_kernel (cta_group::2, 256x256 pair tile, BF16 kind::f16)";
     XNRS_LAUNCHED();
     return XNRS_OK;
 }

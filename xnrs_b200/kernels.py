@@ -20,10 +20,17 @@ _precision = 0
 
 
 def set_precision(name: str) -> None:
-    """arithmetic of the GEMM-shaped ops: 'fp32' (exact FMA), 'tf32x3' (fp32-accurate tensor cores),
-    'tf32' or 'bf16' (2e-2 tolerance class)."""
+    """arithmetic of the GEMM-shaped ops: 'fp32' (exact FMA), 'tf32x3' (fp32-accurate tensor cores), 'tf32' (single pass) or
+    'bf16' (2e-2 tolerance class): the token-level tensors of the additive-pooling title encoder — token-table rows, the
+    tanh hidden layer and its gradient, i.e. ~99 % of the step's bytes and FLOPs — are STORED in bf16 and multiplied by
+    tcgen05 kind::f16 with fp32 accumulation; the small title / user level GEMMs on fp32 tensors run single-pass TF32."""
     global _precision
     _precision = PRECISIONS[name]
+
+
+def _gemm_precision() -> int:
+    """precision code handed to xnrs_gemm (fp32 operands): the bf16-storage mode multiplies them in single-pass TF32"""
+    return 2 if _precision == 3 else _precision
 
 
 def get_precision() -> str:
@@ -151,7 +158,43 @@ def gemm(a, b, *, trans_a=False, trans_b=False, bias=None, act=ACT_NONE, aux=Non
         out = torch.empty((M, N), device=a.device, dtype=torch.float32)
         accumulate = False
     call('xnrs_gemm', int(trans_a), int(trans_b), M, N, K, _mat(a), a.stride(0), a_rows, _mat(b), b.stride(0), b_rows,
-         _mat(out), out.stride(0), bias, act, aux, int(accumulate), split_k, _precision)
+         _mat(out), out.stride(0), bias, act, aux, int(accumulate), split_k, _gemm_precision())
+    return out
+
+
+def cast_bf16(t: torch.Tensor) -> torch.Tensor:
+    """fp32 -> bf16 (round to nearest even), same shape"""
+    t = _f32(t)
+    out = torch.empty(t.shape, device=t.device, dtype=torch.bfloat16)
+    call('xnrs_cast_bf16', t.numel(), t, out)
+    return out
+
+
+def bf16_twin(t: torch.Tensor) -> torch.Tensor:
+    """the bf16 copy of a FROZEN fp32 table (the token table), made once and cached on the tensor object"""
+    twin = getattr(t, '_xnrs_bf16', None)
+    if twin is None or twin.shape != t.shape or twin.device != t.device:
+        twin = cast_bf16(t)
+        t._xnrs_bf16 = twin
+    return twin
+
+
+def gemm_bf16(a, b, *, trans_a=False, trans_b=False, bias=None, act=ACT_NONE, out=None, out_bf16=False, accumulate=False,
+              a_rows=None, b_rows=None, split_k=0):
+    """xnrs_gemm_bf16: bf16 operands (2-D, unit column stride), fp32 accumulation; out fp32 (default) or bf16"""
+    rows_a = a_rows.numel() if a_rows is not None else a.shape[0]
+    rows_b = b_rows.numel() if b_rows is not None else b.shape[0]
+    M, K = (a.shape[1], rows_a) if trans_a else (rows_a, a.shape[1])
+    N, Kb = (rows_b, b.shape[1]) if trans_b else (b.shape[1], rows_b)
+    if K != Kb:
+        raise RuntimeError(f'gemm_bf16: inner dimensions differ ({K} vs {Kb})')
+    if a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16 or a.stride(1) != 1 or b.stride(1) != 1:
+        raise RuntimeError('gemm_bf16 operands must be bf16 2-D with unit column stride')
+    if out is None:
+        out = torch.empty((M, N), device=a.device, dtype=torch.bfloat16 if out_bf16 else torch.float32)
+        accumulate = False
+    call('xnrs_gemm_bf16', int(trans_a), int(trans_b), M, N, K, a, a.stride(0), a_rows, b, b.stride(0), b_rows, out, out.stride(0),
+         int(out.dtype == torch.bfloat16), bias, act, int(accumulate), split_k)
     return out
 
 
@@ -360,10 +403,28 @@ class AdditivePoolFn(torch.autograd.Function):
         tix (optional, with seg): the group of each row (-1: padding row) — enables the ONE-launch fused forward
         (xnrs_titlepool_fwd: gather -> fc1 -> tanh -> logit -> exp -> per-title sums on the tensor-core kernel)."""
         F_, A = x.shape[1], w1.shape[0]
+        ctx.set_materialize_grads(False)            # an unused `attn` output arrives as None in backward, not as zeros
+        shape_ok = (tix is not None and seg is not None and mask is None and A == 256 and F_ % 128 == 0 and F_ <= 1024
+                    and (rows.numel() if rows is not None else x.shape[0]) >= FUSED_GATHER_MIN_ROWS)
+        ctx.bf16 = bool(_precision == 3 and FUSED_TITLEPOOL and rows is not None and shape_ok)
+        if ctx.bf16:
+            # bf16-storage mode: the rows are gathered from the bf16 twin of the frozen table, fc1.weight is rounded to bf16 for
+            # this step, the hidden layer is kept in bf16 for the backward pass; logits / weights / pooled sums are fp32
+            xb, n_rows = bf16_twin(x), rows.numel()
+            hid = torch.empty((n_rows, A), device=x.device, dtype=torch.bfloat16)
+            attn = torch.empty(n_rows, device=x.device, dtype=torch.float32)
+            e = torch.empty(n_rows, device=x.device, dtype=torch.float32)
+            zsum = torch.empty(R, device=x.device, dtype=torch.float32)
+            pooled = torch.empty((R, F_), device=x.device, dtype=torch.float32)
+            call('xnrs_titlepool_fwd_bf16', xb, F_, rows, tix, n_rows, R, F_, A, cast_bf16(w1), b1, w2.reshape(-1), b2, hid, e, zsum,
+                 attn, pooled)
+            ctx.save_for_backward(xb, rows, w1, w2, hid, attn, seg)
+            ctx.dims = (R, L, F_, A)
+            ctx.bias_params = (b1, b2)
+            return pooled, attn
         x, rows = _resolve_rows(x, rows)
         n_rows = rows.numel() if rows is not None else x.shape[0]
-        fused = (FUSED_TITLEPOOL and tix is not None and seg is not None and mask is None and _precision in (1, 2)
-                 and A == 256 and F_ % 128 == 0 and F_ <= 768 and n_rows >= FUSED_GATHER_MIN_ROWS and x.stride(0) % 4 == 0)
+        fused = (FUSED_TITLEPOOL and shape_ok and _precision in (1, 2, 3) and x.stride(0) % 4 == 0)
         pooled = torch.empty((R, F_), device=x.device, dtype=torch.float32)
         if fused:
             hid = torch.empty((n_rows, A), device=x.device, dtype=torch.float32)
@@ -371,7 +432,7 @@ class AdditivePoolFn(torch.autograd.Function):
             e = torch.empty(n_rows, device=x.device, dtype=torch.float32)
             zsum = torch.empty(R, device=x.device, dtype=torch.float32)
             call('xnrs_titlepool_fwd', _mat(x), x.stride(0), rows, tix, n_rows, R, F_, A, w1, b1, w2.reshape(-1), b2,
-                 _precision, hid, e, zsum, attn, pooled)
+                 _gemm_precision(), hid, e, zsum, attn, pooled)
         else:
             hid = gemm(x, w1, trans_b=True, bias=b1, act=ACT_TANH, a_rows=rows)
             attn = torch.empty((R, L) if seg is None else (hid.shape[0],), device=x.device, dtype=torch.float32)
@@ -386,13 +447,25 @@ class AdditivePoolFn(torch.autograd.Function):
         x, rows, w1, w2, hid, attn, seg = ctx.saved_tensors
         R, L, F_, A = ctx.dims
         dev = x.device
-        d_pooled = _f32(d_pooled)
+        d_pooled = torch.zeros((R, F_), device=dev, dtype=torch.float32) if d_pooled is None else _f32(d_pooled)
         d_attn = None if d_attn is None else _f32(d_attn)
         d_hid = torch.empty_like(hid)
         b1, b2 = ctx.bias_params
         w2_buf, d_w2 = _wgrad_buffer(w2, w2)
         b2_buf, d_b2 = _wgrad_buffer(b2, b2)
         b1_buf, d_b1 = _wgrad_buffer(b1, b1)            # fc1 bias gradient = column sums of d_hid, fused into the kernel
+        if ctx.bf16:                                    # x = the bf16 table twin, hid / d_hid bf16; gradients accumulate in fp32
+            if d_attn is not None:
+                raise RuntimeError('bf16 pooling: no gradient path through the returned weights')
+            call('xnrs_addpool_bwd_bf16', x, rows, hid, w2.reshape(-1), attn, d_pooled, seg, R, L, F_, A, hid.shape[0], d_hid,
+                 w2_buf.view(-1), b2_buf.view(-1), b1_buf.view(-1))
+            g = _direct(w1)
+            if g is not None and g.dim() == 2:
+                gemm_bf16(d_hid, x, trans_a=True, b_rows=rows, out=g, accumulate=True)
+                d_w1 = None
+            else:
+                d_w1 = gemm_bf16(d_hid, x, trans_a=True, b_rows=rows)
+            return None, None, None, d_w1, d_b1, d_w2, d_b2, None, None, None, None
         need_dx = _need(ctx, 0)
         if need_dx and rows is not None:
             raise RuntimeError('no gradient flows into a gathered (frozen) table')

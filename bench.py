@@ -519,6 +519,26 @@ def train_workload(ctx, args, model_key, want_cpu=True, want_eager=False):
     if roofline is not None:
         roofline['ms_per_step_with_event_hooks'] = ms_hooked / steps
         roofline['simt_fallback_gemms_per_region'] = fallbacks
+        # the fused title-pooling forward (gather -> fc1 -> tanh -> logit -> exp -> per-title sums: ONE tcgen05 launch + a small
+        # normalisation pass) is its own entry point: FLOPs = 2 * rows * A * F of the fc1 product inside it
+        tp = [r for r in log.records if r.name.startswith('xnrs_titlepool_fwd')]
+        if tp:
+            bf = tp[0].name.endswith('bf16')
+            ms_tp = sum(r.start.elapsed_time(r.end) for r in tp)
+            rows_tp = sum(r.args[1] for r in tp)
+            flop_tp = sum(2.0 * r.args[1] * r.args[3] * r.args[4] for r in tp)
+            pk_, _ = peaks()
+            cls = 'titlepool_bf16' if bf else 'titlepool_fp32'
+            tr = traffic_entry(cls)
+            roofline['fused_title_pool'] = {
+                'kernel': 'gemm_tc2_kernel<POOL> (cta_group::2 pair tile, cp.async table gather, pooling epilogue on TMEM; '
+                          + ('bf16 storage, kind::f16)' if bf else 'fp32 storage, 3xTF32)') + ' + titlepool_finalize_kernel',
+                'launches_timed': len(tp), 'avg_launch_ms': ms_tp / len(tp), 'rows_per_launch': rows_tp / len(tp),
+                'achieved': flop_tp / (ms_tp * 1e-3) / 1e12, 'unit': 'TFLOP/s', 'peak': pk_['bf16_tflops_sustained'],
+                'frac': flop_tp / (ms_tp * 1e-3) / 1e12 / pk_['bf16_tflops_sustained'],
+                'traffic': tr['dram_bytes_per_row'] * rows_tp / len(tp) if tr else None,
+                'algorithmic_bytes': tr['algorithmic_bytes_per_row'] * rows_tp / len(tp) if tr else None,
+                'traffic_source': f"{os.path.relpath(TRAFFIC_FILE, ROOT)}:{cls}" if tr else 'no ncu capture of this kernel class'}
     if os.environ.get('XNRS_BENCH_DUMP') and rank == 0:      # every launch of ONE step with its event time (diagnostics)
         per = len(log.records) // steps
         with open(os.environ['XNRS_BENCH_DUMP'] + '.' + model_key, 'w') as f:

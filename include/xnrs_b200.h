@@ -118,13 +118,14 @@ int xnrs_addpool_bwd(const float *x, const int *x_rows, const float *mask, const
  * sum(e * x) -> normalise by (sum + 1e-8), in ONE launch of the CTA-pair tcgen05 kernel (cp.async gather warp, pooling
  * epilogue on the TMEM accumulators; the x rows of a tile are re-read from L2 for the weighted sum) plus a small
  * normalisation pass.  x rows are x[g] or table rows x[x_rows[g]] (ldx floats apart); tix (n_rows) = title of each row, -1
- * for padding rows.  Outputs: hid (n_rows, A) = tanh(fc1 x) (saved for the backward), e (n_rows, scratch), zsum (R, scratch),
+ * for padding rows; seg (R+1, nullable) = the same grouping as offsets: with it the per-title sums may be formed by a second,
+ * warp-per-title kernel instead of the GEMM epilogue (chosen by measurement, XNRS_TITLEPOOL_SPLIT).  Outputs: hid (n_rows, A) = tanh(fc1 x) (saved for the backward), e (n_rows, scratch), zsum (R, scratch),
  * attn (n_rows) and pooled (R, F) exactly as xnrs_addpool_fwd defines them.  Covers A == 256, F % 128 == 0, F <= 1024,
  * n_rows >= 256 in the tensor-core precisions on sm_100; otherwise returns XNRS_ERR_UNSUPPORTED with nothing launched and the
  * caller runs xnrs_gemm(TANH) + xnrs_addpool_fwd (the same mathematics in two launches). */
-int xnrs_titlepool_fwd(const float *x, long long ldx, const int *x_rows, const int *tix, long long n_rows, long long R, int F,
-                       int A, const float *w1, const float *b1, const float *w2, const float *b2, int precision, float *hid,
-                       float *e, float *zsum, float *attn, float *pooled, xnrs_stream_t st);
+int xnrs_titlepool_fwd(const float *x, long long ldx, const int *x_rows, const int *tix, const int *seg, long long n_rows,
+                       long long R, int F, int A, const float *w1, const float *b1, const float *w2, const float *b2, int precision,
+                       float *hid, float *e, float *zsum, float *attn, float *pooled, xnrs_stream_t st);
 /* ---- XNRS_PREC_BF16: bf16 STORAGE of the token-level tensors (token table rows x, tanh hidden layer hid, its gradient) with
  * fp32 accumulation everywhere — the north-star's 2e-2 tolerance class.  bf16 operands are `void *` to 16-bit brain floats.
  * xnrs_cast_bf16 rounds fp32 to nearest-even bf16 (token table once, fc1.weight per step).
@@ -136,9 +137,9 @@ int xnrs_cast_bf16(long long n, const float *src, void *dst, xnrs_stream_t st);
 int xnrs_gemm_bf16(int transA, int transB, long long M, long long N, long long K, const void *A, long long lda,
                    const int *a_rows, const void *B, long long ldb, const int *b_rows, void *C, long long ldc, int c_bf16,
                    const float *bias, int act, int accumulate, int split_k, xnrs_stream_t st);
-int xnrs_titlepool_fwd_bf16(const void *x, long long ldx, const int *x_rows, const int *tix, long long n_rows, long long R, int F,
-                            int A, const void *w1, const float *b1, const float *w2, const float *b2, void *hid, float *e,
-                            float *zsum, float *attn, float *pooled, xnrs_stream_t st);
+int xnrs_titlepool_fwd_bf16(const void *x, long long ldx, const int *x_rows, const int *tix, const int *seg, long long n_rows,
+                            long long R, int F, int A, const void *w1, const float *b1, const float *w2, const float *b2, void *hid,
+                            float *e, float *zsum, float *attn, float *pooled, xnrs_stream_t st);
 int xnrs_addpool_bwd_bf16(const void *x, const int *x_rows, const void *hid, const float *w2, const float *attn,
                           const float *d_pooled, const int *seg, long long R, int L, int F, int A, long long n_rows, void *d_hid,
                           float *d_w2, float *d_b2, float *d_b1, xnrs_stream_t st);

@@ -166,7 +166,7 @@ def _xnrs_addpool_fwd(x, x_rows, mask, hid, w2, b2, seg, R, L, F_, A, attn, pool
     _pool_fwd(x, x_rows, mask, hid @ w2 + b2, seg, R, L, attn, pooled)
 
 
-def _xnrs_titlepool_fwd(x, ldx, x_rows, tix, n_rows, R, F_, A, w1, b1, w2, b2, prec, hid, e, zsum, attn, pooled):
+def _xnrs_titlepool_fwd(x, ldx, x_rows, tix, seg, n_rows, R, F_, A, w1, b1, w2, b2, prec, hid, e, zsum, attn, pooled):
     xr = _rows(x, x_rows)[:n_rows]
     h = torch.tanh(xr @ w1.T + b1)
     hid.copy_(h)
@@ -196,9 +196,9 @@ def _xnrs_gemm_bf16(ta, tb, M, N, K_, A, lda, a_rows, B, ldb, b_rows, C, ldc, c_
     C.copy_((C.float() + y if accumulate else y).to(C.dtype))
 
 
-def _xnrs_titlepool_fwd_bf16(x, ldx, x_rows, tix, n_rows, R, F_, A, w1, b1, w2, b2, hid, e, zsum, attn, pooled):
+def _xnrs_titlepool_fwd_bf16(x, ldx, x_rows, tix, seg, n_rows, R, F_, A, w1, b1, w2, b2, hid, e, zsum, attn, pooled):
     h32 = torch.empty(hid.shape, dtype=torch.float32)
-    _xnrs_titlepool_fwd(x.float(), ldx, x_rows, tix, n_rows, R, F_, A, w1.float(), b1, w2, b2, 3, h32, e, zsum, attn, pooled)
+    _xnrs_titlepool_fwd(x.float(), ldx, x_rows, tix, seg, n_rows, R, F_, A, w1.float(), b1, w2, b2, 3, h32, e, zsum, attn, pooled)
     hid.copy_(h32.to(torch.bfloat16))
 
 

@@ -531,7 +531,7 @@ def test_plan_kernels_match_torch_index_ops(n_news, S, n):
 def test_bf16_tensor_core_gemm(ta, tb):
     """xnrs_gemm_bf16 (tcgen05 kind::f16 on the CTA-pair kernel): all four operand layouts, ragged sizes, bias / tanh, bf16 and
     fp32 outputs, split-K accumulation — against float64 on the bf16-rounded operands"""
-    for M, N, K_ in [(1000, 200, 1344), (4097, 768, 768), (256, 768, 9000)]:
+    for M, N, K_ in [(1000, 200, 1344), (4104, 768, 768), (256, 768, 9000)]:          # row strides multiples of 8 (16 bytes)
         a = (torch.randn((K_, M) if ta else (M, K_), generator=g(1)) / math.sqrt(K_)).bfloat16()
         b = torch.randn((N, K_) if tb else (K_, N), generator=g(2)).bfloat16()
         bias = torch.randn(N, generator=g(3))
@@ -570,3 +570,32 @@ def test_gemm_rejects_the_bf16_precision_on_fp32_operands():
         a = cu(torch.randn(256, 64))
         K.call('xnrs_gemm', 0, 1, 256, 256, 64, K._mat(a), 64, None, K._mat(a), 64, None, K._mat(cu(torch.empty(256, 256))), 256, None, 0,
                None, 0, 0, K.PRECISIONS['bf16'])
+
+
+def test_active_row_adam_kernel_is_bit_identical_to_the_dense_pass():
+    """xnrs_mark_rows + xnrs_adam_rows over the rows touched so far == xnrs_adam_step over the whole table, bit for bit, for 30
+    steps in which new rows keep appearing (never-touched rows have g = m = v = 0: the dense update leaves them unchanged)"""
+    V, D = 5000, 136
+    gen = g(9)
+    p0 = torch.randn(V, D, generator=gen)
+    dense = [cu(p0.clone()), cu(torch.zeros(V, D)), cu(torch.zeros(V, D)), cu(torch.zeros(V, D))]       # p, g, m, v
+    rows_ = [cu(p0.clone()), cu(torch.zeros(V, D)), cu(torch.zeros(V, D)), cu(torch.zeros(V, D))]
+    bitmap, active = cu(torch.zeros((V + 31) // 32, dtype=torch.int32)), cu(torch.zeros(V, dtype=torch.int32))
+    count = cu(torch.zeros(1, dtype=torch.int32))
+    for step in range(1, 31):
+        idx = torch.randint(0, 200 + 150 * step, (64,), generator=gen).clamp(max=V - 1).int()
+        idx[0] = 0                                                     # the padding row: never marked, never updated
+        gr = torch.randn(64, D, generator=gen)
+        for buf in (dense, rows_):
+            buf[1].zero_()
+            K.call('xnrs_scatter_add_rows', buf[1], V, D, cu(idx), 64, cu(gr), D, 0)
+        K.call('xnrs_mark_rows', cu(idx), 64, V, 0, bitmap, active, count)
+        K.adam_step(dense[0].view(-1), dense[1].view(-1), dense[2].view(-1), dense[3].view(-1), 1e-2, step=step, grad_scale=0.5)
+        K.call('xnrs_adam_rows', rows_[0], rows_[1], rows_[2], rows_[3], V, D, active, count, 1e-2, 0.9, 0.999, 1e-8, step, None, 0.5)
+    n_active = int(count)
+    assert 0 < n_active < V and 0 not in active[:n_active].tolist()
+    assert len(set(active[:n_active].tolist())) == n_active                 # each row appended once
+    for a, b in zip(dense, rows_):
+        assert torch.equal(a, b)
+    K.call('xnrs_zero_rows', rows_[1], V, D, active, count)
+    assert float(rows_[1].abs().sum()) == 0

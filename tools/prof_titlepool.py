@@ -36,7 +36,7 @@ def main():
     x = K.gather_rows(store.token_table, plan.rows)
     print(f'titles {R}, token rows {T}')
     for _ in range(3):
-        K.call('xnrs_titlepool_fwd', K._mat(store.token_table), 768, plan.rows, plan.tix, T, R, 768, 256, w1, b1, w2, b2, 1, hid, e, zsum,
+        K.call('xnrs_titlepool_fwd', K._mat(store.token_table), 768, plan.rows, plan.tix, plan.seg, T, R, 768, 256, w1, b1, w2, b2, 1, hid, e, zsum,
                attn, pooled)
     for _ in range(3):
         K.gemm(dhid, store.token_table, trans_a=True, out=dw, accumulate=True, b_rows=plan.rows)

@@ -922,6 +922,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     stagef(q)[32 + lane] = e;
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (!p.pool.pooled) continue;       // the per-title sums are formed by titlepool_wsum_kernel from e (see host side)
                 // weighted sum over this CTA's 128 rows: warp w8 owns a slice of F/8 columns (one float4 per lane, F/32 lanes
                 // active) and walks ALL rows, eight independent row loads in flight; the x rows were fetched from the table
                 // moments ago (L2 hits).  A title's partial sums leave through 16-byte vector reductions when the title ends.
@@ -1237,6 +1238,78 @@ int gemm_tensorcore(const GemmArgs &a, int precision, cudaStream_t st, int *stat
     return 1;
 }
 
+// Second half of the fused pooling when the weighted sum is NOT done in the GEMM epilogue: one warp per title turns the
+// un-normalised weights e into attn = e / (sum e + 1e-8) and pooled = sum attn * x (layers.py:62-65), reading the title's
+// rows straight from the (fp32 or bf16) table with four rows of loads in flight; padding rows get attn = 0.
+template <bool BF>
+__global__ void __launch_bounds__(256)
+titlepool_wsum_kernel(const void *__restrict__ x, long long ldx, const int *__restrict__ x_rows, const int *__restrict__ seg,
+                      const float *__restrict__ e, long long R, long long n_rows, int F, float *__restrict__ attn,
+                      float *__restrict__ pooled) {
+    const int lane = threadIdx.x & 31;
+    const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5, nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    constexpr int EPC = BF ? 8 : 4;                 // elements per 16-byte chunk
+    const int nchunk = F / EPC;                     // 16-byte chunks per row (192 fp32 / 96 bf16 at F = 768)
+    for (long long r = wid; r < R; r += nw) {
+        const long long base = seg[r];
+        const int L = seg[r + 1] - seg[r];
+        float z = 0.f;
+        for (int l = lane; l < L; l += 32) z += e[base + l];
+        z = warp_sum(z);
+        const float denom = z + 1e-8f;
+        for (int l = lane; l < L; l += 32) attn[base + l] = e[base + l] / denom;
+        float acc[6][EPC];
+#pragma unroll
+        for (int c = 0; c < 6; ++c)
+#pragma unroll
+            for (int q = 0; q < EPC; ++q) acc[c][q] = 0.f;
+        for (int l0 = 0; l0 < L; l0 += 2) {
+            uint4 v[2][6];
+            float a[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {           // every load of both rows first ...
+                const int l = min(l0 + i, L - 1);
+                a[i] = (l0 + i < L) ? e[base + l] / denom : 0.f;
+                const long long row = x_rows ? (long long)x_rows[base + l] : base + l;
+                const uint4 *src = reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(x) + row * ldx * (BF ? 2 : 4));
+#pragma unroll
+                for (int c = 0; c < 6; ++c)
+                    v[i][c] = (lane + 32 * c < nchunk) ? __ldg(src + lane + 32 * c) : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {           // ... then the arithmetic
+#pragma unroll
+                for (int c = 0; c < 6; ++c) {
+                    const uint32_t w[4] = {v[i][c].x, v[i][c].y, v[i][c].z, v[i][c].w};
+                    if (BF) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            acc[c][2 * q] = fmaf(a[i], __uint_as_float(w[q] << 16), acc[c][2 * q]);
+                            acc[c][2 * q + 1] = fmaf(a[i], __uint_as_float(w[q] & 0xffff0000u), acc[c][2 * q + 1]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) acc[c][q] = fmaf(a[i], __uint_as_float(w[q]), acc[c][q]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            const int ch = lane + 32 * c;
+            if (ch < nchunk) {
+                float4 *dst = reinterpret_cast<float4 *>(pooled + r * F + (long long)ch * EPC);
+                dst[0] = make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
+                if (BF) dst[1] = make_float4(acc[c][4 % EPC], acc[c][5 % EPC], acc[c][6 % EPC], acc[c][7 % EPC]);
+            }
+        }
+    }
+    // rows past the last title (TitlePlan padding) carry no weight
+    const long long t0 = seg[R];
+    for (long long g = t0 + blockIdx.x * (long long)blockDim.x + threadIdx.x; g < n_rows; g += (long long)gridDim.x * blockDim.x)
+        attn[g] = 0.f;
+}
+
 // attn[g] = e[g] / (zsum[title] + 1e-8) (0 on padding rows); pooled[t,:] /= (zsum[t] + 1e-8)   (layers.py:62-65)
 __global__ void titlepool_finalize_kernel(const float *__restrict__ e, const int *__restrict__ tix, const float *__restrict__ zsum,
                                           long long n_rows, long long R, int F4, float *__restrict__ attn, float *__restrict__ pooled) {
@@ -1262,9 +1335,9 @@ using namespace xnrs;
 // kernel (cp.async gather warp + pooling epilogue), then a small normalisation pass.  Returns XNRS_ERR_UNSUPPORTED (nothing
 // launched) for shapes / devices / precisions the fused kernel does not cover; the caller then runs xnrs_gemm + xnrs_addpool_fwd.
 // shared by the fp32-storage (tf32 / 3xtf32) and the bf16-storage entry points: x / w1 / hid are fp32 (elt 4) or bf16 (elt 2)
-static int titlepool_fwd_impl(const void *x, long long ldx, const int *x_rows, const int *tix, long long n_rows, long long R,
-                              int F, int A, const void *w1, const float *b1, const float *w2, const float *b2, int passes, int elt,
-                              void *hid, float *e, float *zsum, float *attn, float *pooled, cudaStream_t st) {
+static int titlepool_fwd_impl(const void *x, long long ldx, const int *x_rows, const int *tix, const int *seg, long long n_rows,
+                              long long R, int F, int A, const void *w1, const float *b1, const float *w2, const float *b2,
+                              int passes, int elt, void *hid, float *e, float *zsum, float *attn, float *pooled, cudaStream_t st) {
     XNRS_REQUIRE(x && tix && w1 && b1 && w2 && b2 && hid && e && zsum && attn && pooled, "null pointer");
     XNRS_REQUIRE(n_rows >= 0 && R >= 0 && F > 0 && A > 0, "bad sizes");
     static int is_sm100 = -1;
@@ -1308,10 +1381,28 @@ static int titlepool_fwd_impl(const void *x, long long ldx, const int *x_rows, c
         }
         attr_set = true;
     }
+    // where the per-title weighted sums are formed.  In the GEMM epilogue (x rows re-read from L2 while the next tile's MMAs
+    // run): fewer HBM bytes, but the epilogue warps then sit on L2 latency; or by titlepool_wsum_kernel afterwards (a warp per
+    // title, rows re-read from HBM / L2 at stream speed).  Measured: the split wins whenever the GEMM itself is short
+    // (bf16 storage); XNRS_TITLEPOOL_SPLIT = 0 / 1 forces either.
+    static int split_opt = -2;
+    if (split_opt == -2) { const char *ev = getenv("XNRS_TITLEPOOL_SPLIT"); split_opt = ev ? atoi(ev) : -1; }
+    const bool split = seg && F <= 768 && (split_opt == 1 || (split_opt == -1 && elt == 2));
+    const long long pairs = std::min<long long>(p.tiles_m, num_sms() / 2);
+    if (split) {
+        p.pool.pooled = nullptr;
+        p.pool.zsum = nullptr;
+        gemm_tc2_kernel<true><<<(unsigned)(2 * pairs), TC2_THREADS, smem_bytes, st>>>(mapA, mapB, p);
+        XNRS_LAUNCHED();
+        const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(cdiv(R, 8), 16LL * num_sms()));
+        if (elt == 2) titlepool_wsum_kernel<true><<<grid, 256, 0, st>>>(x, ldx, x_rows, seg, e, R, n_rows, F, attn, pooled);
+        else titlepool_wsum_kernel<false><<<grid, 256, 0, st>>>(x, ldx, x_rows, seg, e, R, n_rows, F, attn, pooled);
+        XNRS_LAUNCHED();
+        return XNRS_OK;
+    }
     if (cudaMemsetAsync(pooled, 0, (size_t)R * F * sizeof(float), st) != cudaSuccess ||
         cudaMemsetAsync(zsum, 0, (size_t)R * sizeof(float), st) != cudaSuccess)
         return fail(XNRS_ERR_CUDA, "%s: memset failed", "xnrs_titlepool_fwd");
-    const long long pairs = std::min<long long>(p.tiles_m, num_sms() / 2);
     gemm_tc2_kernel<true><<<(unsigned)(2 * pairs), TC2_THREADS, smem_bytes, st>>>(mapA, mapB, p);
     XNRS_LAUNCHED();
     const long long work = std::max<long long>(n_rows, R * (F / 4));
@@ -1321,21 +1412,21 @@ static int titlepool_fwd_impl(const void *x, long long ldx, const int *x_rows, c
     return XNRS_OK;
 }
 
-extern "C" int xnrs_titlepool_fwd(const float *x, long long ldx, const int *x_rows, const int *tix, long long n_rows, long long R,
-                                  int F, int A, const float *w1, const float *b1, const float *w2, const float *b2,
+extern "C" int xnrs_titlepool_fwd(const float *x, long long ldx, const int *x_rows, const int *tix, const int *seg, long long n_rows,
+                                  long long R, int F, int A, const float *w1, const float *b1, const float *w2, const float *b2,
                                   int precision, float *hid, float *e, float *zsum, float *attn, float *pooled,
                                   xnrs_stream_t st) {
     if (precision != XNRS_PREC_TF32X3 && precision != XNRS_PREC_TF32)
         return fail(XNRS_ERR_UNSUPPORTED, "%s: fp32-storage fused pooling runs in the TF32X3 / TF32 precisions", "xnrs_titlepool_fwd");
-    return titlepool_fwd_impl(x, ldx, x_rows, tix, n_rows, R, F, A, w1, b1, w2, b2, precision == XNRS_PREC_TF32X3 ? 3 : 1, 4, hid, e,
-                              zsum, attn, pooled, STREAM(st));
+    return titlepool_fwd_impl(x, ldx, x_rows, tix, seg, n_rows, R, F, A, w1, b1, w2, b2, precision == XNRS_PREC_TF32X3 ? 3 : 1, 4,
+                              hid, e, zsum, attn, pooled, STREAM(st));
 }
 
-extern "C" int xnrs_titlepool_fwd_bf16(const void *x, long long ldx, const int *x_rows, const int *tix, long long n_rows,
-                                       long long R, int F, int A, const void *w1, const float *b1, const float *w2,
-                                       const float *b2, void *hid, float *e, float *zsum, float *attn, float *pooled,
-                                       xnrs_stream_t st) {
-    return titlepool_fwd_impl(x, ldx, x_rows, tix, n_rows, R, F, A, w1, b1, w2, b2, 1, 2, hid, e, zsum, attn, pooled, STREAM(st));
+extern "C" int xnrs_titlepool_fwd_bf16(const void *x, long long ldx, const int *x_rows, const int *tix, const int *seg,
+                                       long long n_rows, long long R, int F, int A, const void *w1, const float *b1,
+                                       const float *w2, const float *b2, void *hid, float *e, float *zsum, float *attn,
+                                       float *pooled, xnrs_stream_t st) {
+    return titlepool_fwd_impl(x, ldx, x_rows, tix, seg, n_rows, R, F, A, w1, b1, w2, b2, 1, 2, hid, e, zsum, attn, pooled, STREAM(st));
 }
 
 // C[M,N] (=|+=) act(opA(A) opB(B) + bias) with bf16 operands (tcgen05 kind::f16, fp32 accumulation in TMEM) on the CTA-pair

@@ -289,7 +289,7 @@ extern "C" int xnrs_infonce_normalize_bwd(const float *d_ehat, const float *ehat
                                           xnrs_stream_t st) {
     XNRS_REQUIRE(Bk >= 0 && E > 0, "bad sizes");
     if (Bk == 0) return XNRS_OK;
-    XNRS_REQUIRE(d_ehat && ehat && inv_norm && stats && d_emb, "null pointer");
+    XNRS_REQUIRE(d_ehat && ehat && inv_norm && d_emb, "null pointer");          // stats may be NULL: plain normalisation backward
     infonce_normalize_bwd_kernel<<<(unsigned)cdiv(Bk, 8), 256, 0, STREAM(st)>>>(d_ehat, ehat, inv_norm, stats, grad_scale,
                                                                            Bk, E, d_emb);
     XNRS_LAUNCHED();

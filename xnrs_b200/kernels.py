@@ -416,7 +416,7 @@ class AdditivePoolFn(torch.autograd.Function):
             e = torch.empty(n_rows, device=x.device, dtype=torch.float32)
             zsum = torch.empty(R, device=x.device, dtype=torch.float32)
             pooled = torch.empty((R, F_), device=x.device, dtype=torch.float32)
-            call('xnrs_titlepool_fwd_bf16', xb, F_, rows, tix, n_rows, R, F_, A, cast_bf16(w1), b1, w2.reshape(-1), b2, hid, e, zsum,
+            call('xnrs_titlepool_fwd_bf16', xb, F_, rows, tix, seg, n_rows, R, F_, A, cast_bf16(w1), b1, w2.reshape(-1), b2, hid, e, zsum,
                  attn, pooled)
             ctx.save_for_backward(xb, rows, w1, w2, hid, attn, seg)
             ctx.dims = (R, L, F_, A)
@@ -431,7 +431,7 @@ class AdditivePoolFn(torch.autograd.Function):
             attn = torch.empty(n_rows, device=x.device, dtype=torch.float32)
             e = torch.empty(n_rows, device=x.device, dtype=torch.float32)
             zsum = torch.empty(R, device=x.device, dtype=torch.float32)
-            call('xnrs_titlepool_fwd', _mat(x), x.stride(0), rows, tix, n_rows, R, F_, A, w1, b1, w2.reshape(-1), b2,
+            call('xnrs_titlepool_fwd', _mat(x), x.stride(0), rows, tix, seg, n_rows, R, F_, A, w1, b1, w2.reshape(-1), b2,
                  _gemm_precision(), hid, e, zsum, attn, pooled)
         else:
             hid = gemm(x, w1, trans_b=True, bias=b1, act=ACT_TANH, a_rows=rows)

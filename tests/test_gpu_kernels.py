@@ -602,8 +602,10 @@ def test_active_row_adam_kernel_is_bit_identical_to_the_dense_pass():
 
 
 @pytest.mark.parametrize('bf', [False, True])
-def test_warp_per_title_pool_backward_matches_the_cta_kernel(bf):
-    """the warp-per-title pooling backward (R >= 4096 ragged groups gathered from a table, fp32 or bf16 storage) against the
+def test_warp_per_title_pool_backward_matches_the_cta_kernel(bf, monkeypatch):
+    """(XNRS_POOL_BWD_WARP=1 must be in the environment before the library first dispatches this entry point for the warp
+    kernel to be the one under test; otherwise both runs take the CTA kernel and the test checks it against float64.)
+    the warp-per-title pooling backward (R >= 4096 ragged groups gathered from a table, fp32 or bf16 storage) against the
     CTA-per-title kernel on a slice of the same problem (R < 4096 takes the CTA kernel): d_hid rows, d_w2, d_b2, d_b1"""
     V, F_, A, R = 3000, 768, 256, 5000
     gen = g(13)

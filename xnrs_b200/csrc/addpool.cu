@@ -818,8 +818,11 @@ extern "C" int xnrs_addpool_bwd(const float *x, const int *x_rows, const float *
     if (R == 0) return XNRS_OK;
     XNRS_REQUIRE(x && hid && w2 && attn && d_pooled && d_hid && d_w2 && d_b2, "null pointer");
     XNRS_REQUIRE(!(d_x && x_rows), "d_x is only defined for dense x");
-    static int warp_bwd = -1;       // XNRS_POOL_BWD_WARP=0 keeps the CTA-per-title kernel (comparison)
-    if (warp_bwd < 0) { const char *ev = getenv("XNRS_POOL_BWD_WARP"); warp_bwd = ev ? atoi(ev) : 1; }
+    // XNRS_POOL_BWD_WARP=1 selects the warp-per-title kernel.  Measured on the CL step (8.7k ragged titles, 153k rows): it is
+    // SLOWER than the CTA-per-title kernel (0.315 vs 0.231 ms fp32, 0.260 vs 0.227 ms bf16): phase 2 walks a title's rows one
+    // by one per warp, where the CTA kernel spreads them over 256 threads — so the CTA kernel stays the default
+    static int warp_bwd = -1;
+    if (warp_bwd < 0) { const char *ev = getenv("XNRS_POOL_BWD_WARP"); warp_bwd = ev ? atoi(ev) : 0; }
     if (warp_bwd && !d_x && !d_attn && R >= 4096 && F % 4 == 0 && F <= 768 && A <= 32 * AQ && L <= 1024) {
         pool_bwd_warp_kernel<false><<<warp_grid(R), WPB * 32, WPB * L * sizeof(float), STREAM(st)>>>(
             x, x_rows, hid, w2, attn, d_pooled, seg, R, L, F, A, n_rows, d_hid, d_w2, d_b2, d_b1);
@@ -839,8 +842,8 @@ extern "C" int xnrs_addpool_bwd_bf16(const void *x, const int *x_rows, const voi
     if (R == 0) return XNRS_OK;
     XNRS_REQUIRE(x && hid && w2 && attn && d_pooled && d_hid && d_w2 && d_b2, "null pointer");
     XNRS_REQUIRE(!((uintptr_t)x & 15) && !((uintptr_t)d_pooled & 15), "x and d_pooled must be 16-byte aligned");
-    static int warp_bwd = -1;
-    if (warp_bwd < 0) { const char *ev = getenv("XNRS_POOL_BWD_WARP"); warp_bwd = ev ? atoi(ev) : 1; }
+    static int warp_bwd = -1;       // see xnrs_addpool_bwd: measured slower, off by default
+    if (warp_bwd < 0) { const char *ev = getenv("XNRS_POOL_BWD_WARP"); warp_bwd = ev ? atoi(ev) : 0; }
     if (warp_bwd && R >= 4096 && F <= 768 && A <= 32 * AQ && L <= 1024) {
         pool_bwd_warp_kernel<true><<<warp_grid(R), WPB * 32, WPB * L * sizeof(float), STREAM(st)>>>(
             x, x_rows, hid, w2, attn, d_pooled, seg, R, L, F, A, n_rows, d_hid, d_w2, d_b2, d_b1);

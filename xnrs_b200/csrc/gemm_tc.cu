@@ -598,7 +598,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
-            mbar_init(&full_bar[s], p.lsu_gather ? 33 : 1);                   // TMA thread (+ the 32 lanes of the cp.async gather warp)
+            // TMA thread (+ every lane of the cp.async gather warps: 2 warps in 3xTF32 mode, 8 in the single-pass modes)
+            mbar_init(&full_bar[s], p.lsu_gather ? 1 + 32 * (passes == 3 ? 2 : SPLIT_WARPS) : 1);
             mbar_init(&ready_bar[s], passes == 3 ? 2 * SPLIT_WARPS : 2);      // used in the leader only: one arrival per
             mbar_init(&empty_bar[s], 1);                                       // splitter warp (or relay) of BOTH CTAs
         }
@@ -619,6 +620,98 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     const long long tiles_mn = p.tiles_m * p.tiles_n;
     const long long total = tiles_mn * p.split_k;
     const long long pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+    // ===================== cp.async gather role: table rows -> the swizzled operand tile ======================================
+    // TMA tile::gather4 moves one 128-byte row per ~32 cycles per SM (measured: 1.0 TB/s chip-wide: the fused-gather GEMMs ran
+    // 0.10-0.21 ms slower than gather-then-GEMM); the LSU path issues 512 B per instruction.  G warps (the two spare warps of
+    // warpgroup 0 in 3xTF32 mode, the eight idle splitter warps in the single-pass modes) copy this CTA's tile of the gathered
+    // operand with 16-byte cp.async into exactly the layout TMA would have produced (K-major A: 128-byte rows, 16-byte chunk c
+    // of row r stored at chunk c ^ (r & 7); MN-major B: fp32 32-byte units XORed with k-row & 3 inside each 32-column chunk,
+    // bf16 the plain 128-byte swizzle), warp gw taking every G-th instruction of the tile.  Completion is asynchronous: the
+    // stage's full barrier collects one arrival per lane when that lane's copies have landed (CUTLASS' sm100 mixed
+    // TMA + cp.async mainloop signals the MMA the same way), so these warps never wait for data.
+    auto gather_role = [&](const int gw, const int G) {
+        StageRing r;
+        const int elt = p.elt, epc = 16 / elt;           // elements per 16-byte chunk
+        const char *Ab = reinterpret_cast<const char *>(p.A), *Bb = reinterpret_cast<const char *>(p.B);
+        for (long long t = pair; t < total; t += npairs) {
+            const long long split = t / tiles_mn, mn = t - split * tiles_mn;
+            const long long m0 = (mn / p.tiles_n) * 256 + 128 * rank, n0 = (mn % p.tiles_n) * T2N + 128 * rank;
+            const long long kbeg = split * p.k_per_split, kend = min(p.K, kbeg + p.k_per_split);
+            int arow[16];                   // A gather: this warp's rows (lane >> 3) + 4 (gw + G i), i < 32 / G  (G >= 2)
+            int myrow = -1, myrow2 = -1;    // B gather: the table rows of k-rows k0 + lane (and k0 + 32 + lane for bf16), a stage ahead
+            if (p.lsu_gather == 1) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if (gw + G * i < 32) arow[i] = p.a_gather[min(m0 + (lane >> 3) + 4 * (gw + G * i), p.M - 1)];
+            } else {
+                if (kbeg + lane < p.K) myrow = p.b_gather[kbeg + lane];
+                if (elt == 2 && kbeg + 32 + lane < p.K) myrow2 = p.b_gather[kbeg + 32 + lane];
+            }
+            for (long long k0 = kbeg; k0 < kend; k0 += kstep) {
+                int nextrow = -1, nextrow2 = -1;
+                if (p.lsu_gather == 2 && k0 + kstep < kend) {
+                    if (k0 + kstep + lane < p.K) nextrow = p.b_gather[k0 + kstep + lane];
+                    if (elt == 2 && k0 + kstep + 32 + lane < p.K) nextrow2 = p.b_gather[k0 + kstep + 32 + lane];
+                }
+                if (lane == 0) mbar_wait(&empty_bar[r.stage], r.phase ^ 1);
+                __syncwarp();
+                if (p.lsu_gather == 1) {
+                    const uint32_t dst = smem_u32(tileA(r.stage));
+                    const int c = lane & 7;
+                    const long long kk = k0 + epc * c;
+                    const int nbytes = (int)max(0LL, min((long long)epc, p.K - kk)) * elt;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        if (gw + G * i < 32) {
+                            const int rr = (lane >> 3) + 4 * (gw + G * i);
+                            cp_async16(dst + rr * 128 + ((c ^ (rr & 7)) << 4),
+                                       Ab + ((long long)arow[i] * p.lda + (nbytes ? kk : 0)) * elt, nbytes);
+                        }
+                    }
+                } else if (elt == 4) {
+                    const uint32_t dst = smem_u32(tileB(r.stage));
+                    const int c4 = lane >> 3, u = lane & 7;
+                    const long long col = n0 + 32 * c4 + 4 * u;
+                    const int cbytes = (int)max(0LL, min(4LL, p.N - col)) * 4;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int kr = gw + G * i;
+                        if (kr < 32) {
+                            const int row = __shfl_sync(0xffffffffu, myrow, kr);
+                            const int nbytes = row >= 0 ? cbytes : 0;
+                            cp_async16(dst + c4 * 4096 + kr * 128 + ((((u >> 1) ^ (kr & 3)) << 5) | ((u & 1) << 4)),
+                                       Bb + (nbytes ? ((long long)row * p.ldb + col) * 4 : 0), nbytes);
+                        }
+                    }
+                } else {
+                    // bf16, MN-major: a k-row of this CTA's 128 columns is 256 bytes = two 128-byte box rows; one warp
+                    // instruction copies two k-rows (16 lanes x 16 bytes each)
+                    const uint32_t dst = smem_u32(tileB(r.stage));
+                    const int sub = lane >> 4, c2 = (lane >> 3) & 1, u = lane & 7;
+                    const long long col = n0 + 64 * c2 + 8 * u;
+                    const int cbytes = (int)max(0LL, min(8LL, p.N - col)) * 2;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int kp = gw + G * i;
+                        if (kp < 32) {
+                            const int kr = 2 * kp + sub;
+                            const int lo = __shfl_sync(0xffffffffu, myrow, kr & 31), hi = __shfl_sync(0xffffffffu, myrow2, kr & 31);
+                            const int row = kr < 32 ? lo : hi;
+                            const int nbytes = row >= 0 ? cbytes : 0;
+                            cp_async16(dst + c2 * 8192 + kr * 128 + ((u ^ (kr & 7)) << 4),
+                                       Bb + (nbytes ? ((long long)row * p.ldb + col) * 2 : 0), nbytes);
+                        }
+                    }
+                }
+                cp_async_arrive_noinc(&full_bar[r.stage]);
+                r.advance(stages);
+                myrow = nextrow;
+                myrow2 = nextrow2;
+            }
+        }
+        cp_async_wait<0>();
+    };
 
     if (warp == 0) {
         // ===================== TMA producer: this CTA's 128 A rows and its half of B =====================
@@ -734,6 +827,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             }
         }
     } else if (warp == 2) {
+        if (passes == 3 && p.lsu_gather) gather_role(0, 2);
         // ===================== relay (single-pass mode): "my operands have landed" -> leader =====================
         if (passes != 3 && lane == 0) {
             const uint32_t ready0 = map_to_cta(smem_u32(&ready_bar[0]), 0);
@@ -749,90 +843,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             }
         }
     } else if (warp == 3) {
-        // ===================== cp.async gather warp: table rows -> the swizzled operand tile ===========================
-        // TMA tile::gather4 moves one 128-byte row per ~32 cycles per SM (measured: 1.0 TB/s chip-wide, the fused-gather
-        // GEMMs ran 0.10-0.21 ms slower than gather-then-GEMM); the LSU path issues 512 B per instruction.  One warp copies
-        // this CTA's tile of the gathered operand with 16-byte cp.async into exactly the layout TMA would have produced
-        // (K-major A: 128-byte rows, 16-byte chunk c of row r stored at chunk c ^ (r & 7); MN-major B: 32-byte units XORed
-        // with k-row & 3 inside each 32-column chunk).
-        if (p.lsu_gather) {
-            StageRing r;
-            const int elt = p.elt, epc = 16 / elt;           // elements per 16-byte chunk
-            const char *Ab = reinterpret_cast<const char *>(p.A), *Bb = reinterpret_cast<const char *>(p.B);
-            for (long long t = pair; t < total; t += npairs) {
-                const long long split = t / tiles_mn, mn = t - split * tiles_mn;
-                const long long m0 = (mn / p.tiles_n) * 256 + 128 * rank, n0 = (mn % p.tiles_n) * T2N + 128 * rank;
-                const long long kbeg = split * p.k_per_split, kend = min(p.K, kbeg + p.k_per_split);
-                int arow[32];
-                int myrow = -1, myrow2 = -1;    // B gather: the table rows of k-rows k0 + lane (and k0 + 32 + lane for bf16), a stage ahead
-                if (p.lsu_gather == 1) {        // lane covers chunk (lane & 7) of rows (lane >> 3) + 4 i
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        arow[i] = p.a_gather[min(m0 + (lane >> 3) + 4 * i, p.M - 1)];
-                } else {
-                    if (kbeg + lane < p.K) myrow = p.b_gather[kbeg + lane];
-                    if (elt == 2 && kbeg + 32 + lane < p.K) myrow2 = p.b_gather[kbeg + 32 + lane];
-                }
-                for (long long k0 = kbeg; k0 < kend; k0 += kstep) {
-                    int nextrow = -1, nextrow2 = -1;
-                    if (p.lsu_gather == 2 && k0 + kstep < kend) {
-                        if (k0 + kstep + lane < p.K) nextrow = p.b_gather[k0 + kstep + lane];
-                        if (elt == 2 && k0 + kstep + 32 + lane < p.K) nextrow2 = p.b_gather[k0 + kstep + 32 + lane];
-                    }
-                    if (lane == 0) mbar_wait(&empty_bar[r.stage], r.phase ^ 1);
-                    __syncwarp();
-                    if (p.lsu_gather == 1) {
-                        const uint32_t dst = smem_u32(tileA(r.stage));
-                        const int c = lane & 7;
-                        const long long kk = k0 + epc * c;
-                        const int nbytes = (int)max(0LL, min((long long)epc, p.K - kk)) * elt;
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const int rr = (lane >> 3) + 4 * i;
-                            cp_async16(dst + rr * 128 + ((c ^ (rr & 7)) << 4),
-                                       Ab + ((long long)arow[i] * p.lda + (nbytes ? kk : 0)) * elt, nbytes);
-                        }
-                    } else if (elt == 4) {
-                        const uint32_t dst = smem_u32(tileB(r.stage));
-                        const int c4 = lane >> 3, u = lane & 7;
-                        const long long col = n0 + 32 * c4 + 4 * u;
-                        const int cbytes = (int)max(0LL, min(4LL, p.N - col)) * 4;
-#pragma unroll
-                        for (int kr = 0; kr < 32; ++kr) {
-                            const int row = __shfl_sync(0xffffffffu, myrow, kr);
-                            const int nbytes = row >= 0 ? cbytes : 0;
-                            cp_async16(dst + c4 * 4096 + kr * 128 + ((((u >> 1) ^ (kr & 3)) << 5) | ((u & 1) << 4)),
-                                       Bb + (nbytes ? ((long long)row * p.ldb + col) * 4 : 0), nbytes);
-                        }
-                    } else {
-                        // bf16, MN-major: a k-row of this CTA's 128 columns is 256 bytes = two 128-byte box rows; one warp
-                        // instruction copies two k-rows (16 lanes x 16 bytes each); plain 128-byte swizzle (chunk ^ (k-row & 7))
-                        const uint32_t dst = smem_u32(tileB(r.stage));
-                        const int sub = lane >> 4, c2 = (lane >> 3) & 1, u = lane & 7;
-                        const long long col = n0 + 64 * c2 + 8 * u;
-                        const int cbytes = (int)max(0LL, min(8LL, p.N - col)) * 2;
-#pragma unroll
-                        for (int kp = 0; kp < 32; ++kp) {
-                            const int kr = 2 * kp + sub;
-                            const int lo = __shfl_sync(0xffffffffu, myrow, kr & 31), hi = __shfl_sync(0xffffffffu, myrow2, kr & 31);
-                            const int row = kr < 32 ? lo : hi;
-                            const int nbytes = row >= 0 ? cbytes : 0;
-                            cp_async16(dst + c2 * 8192 + kr * 128 + ((u ^ (kr & 7)) << 4),
-                                       Bb + (nbytes ? ((long long)row * p.ldb + col) * 2 : 0), nbytes);
-                        }
-                    }
-                    // asynchronous completion: the stage's full barrier collects one arrival per lane when that lane's
-                    // copies have landed (CUTLASS' sm100 mixed TMA + cp.async mainloop signals the MMA the same way), so
-                    // this warp never waits for data — it runs ahead as far as the empty slots allow
-                    cp_async_arrive_noinc(&full_bar[r.stage]);
-                    r.advance(stages);
-                    myrow = nextrow;
-                    myrow2 = nextrow2;
-                }
-            }
-            cp_async_wait<0>();
-        }
+        if (passes == 3 && p.lsu_gather) gather_role(1, 2);
     } else if (warp < EPI2_WARP0) {
+        if (passes != 3 && p.lsu_gather) gather_role(warp - 4, SPLIT_WARPS);      // single pass: nothing to split, these warps gather
         // ===================== splitters (3xTF32): lo = x - trunc_tf32(x) for this CTA's tiles =====================
         if (passes == 3) {
             const int tid = threadIdx.x - 128;

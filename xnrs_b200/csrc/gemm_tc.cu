@@ -649,10 +649,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 if (elt == 2 && kbeg + 32 + lane < p.K) myrow2 = p.b_gather[kbeg + 32 + lane];
             }
             for (long long k0 = kbeg; k0 < kend; k0 += kstep) {
-                int nextrow = -1, nextrow2 = -1;
+                int nextrow = -1, nextrow2 = -1, pfrow = -1;
                 if (p.lsu_gather == 2 && k0 + kstep < kend) {
                     if (k0 + kstep + lane < p.K) nextrow = p.b_gather[k0 + kstep + lane];
                     if (elt == 2 && k0 + kstep + 32 + lane < p.K) nextrow2 = p.b_gather[k0 + kstep + 32 + lane];
+                }
+                // weight-gradient form: every stage touches 32 / 64 NEW random table rows (DRAM page misses) and only 3 / 6
+                // stages are in flight, so the rows of the stage PF steps ahead are pulled into L2 now (warp gw's share)
+                constexpr int PF = 4;
+                if (p.lsu_gather == 2) {
+                    const long long kp = k0 + (long long)PF * kstep + lane + 32 * gw;
+                    if (gw < kstep / 32 && kp < kend && kp < p.K) pfrow = p.b_gather[kp];
                 }
                 if (lane == 0) mbar_wait(&empty_bar[r.stage], r.phase ^ 1);
                 __syncwarp();
@@ -708,6 +715,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 r.advance(stages);
                 myrow = nextrow;
                 myrow2 = nextrow2;
+                if (pfrow >= 0) {           // this CTA's 128 columns of that row: 512 B (fp32) / 256 B (bf16) = 4 / 2 lines
+                    const char *a = Bb + ((long long)pfrow * p.ldb + n0) * elt;
+                    for (int o = 0; o < 128 * elt; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + o));
+                }
             }
         }
         cp_async_wait<0>();

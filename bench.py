@@ -5,6 +5,7 @@
         headline   = CL bi-encoder (config/mind_small_CL.yml, `model: standard`) TRAINING throughput, BASELINE configs[1]
         sub.nrms_train = NRMS (config/mind_small_NRMS.yml) training throughput, BASELINE configs[0]
         sub.eval       = MIND-large-shaped full-catalogue evaluation (160k news, 376 471 impressions), BASELINE configs[4]
+        sub.cl_train_bf16 / sub.eval_bf16 = the same two in the bf16 storage mode (2e-2 tolerance class), as second lines
       each with its own value / e2e / roofline / cpu_baseline; north-star shapes S=30, H=50, 1:4 negatives, synthetic data.
     python bench.py --only cl|nrms|naml|lstur|npa|eval ...        one workload (diagnostics, secondary models)
     python bench.py --impl reference ...                          the UNMODIFIED reference (oracle/_ref, see oracle/make_ref.py)
@@ -50,7 +51,7 @@ MODEL_CFGS = {
 SEQ_LEN, HIST_LEN, N_NEWS, VOCAB = 30, 50, 65_238, 100_000                     # SURVEY §8(d) north-star shapes
 EVAL_NEWS = 160_000
 UNIT = 'impressions/s'
-MIN_TIMED_S = 1.0            # every reported number comes from >= this much measured time
+MIN_TIMED_S = float(os.environ.get('XNRS_BENCH_MIN_S', '1.0'))   # every reported number comes from >= this much measured time (profiler runs: 0)
 TRAFFIC_FILE = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
 
 
@@ -521,6 +522,15 @@ def train_workload(ctx, args, model_key, want_cpu=True, want_eager=False):
         roofline['simt_fallback_gemms_per_region'] = fallbacks
         # the fused title-pooling forward (gather -> fc1 -> tanh -> logit -> exp -> per-title sums: ONE tcgen05 launch + a small
         # normalisation pass) is its own entry point: FLOPs = 2 * rows * A * F of the fc1 product inside it
+        gb = [r for r in log.records if r.name == 'xnrs_gemm_bf16']
+        if gb:      # bf16 storage mode: the token-level weight gradient runs in xnrs_gemm_bf16 (args: transA, transB, M, N, K, ...)
+            ms_gb = sum(r.start.elapsed_time(r.end) for r in gb)
+            flop_gb = sum(2.0 * r.args[2] * r.args[3] * r.args[4] for r in gb)
+            pk_, _ = peaks()
+            roofline['bf16_weight_gradient'] = {
+                'kernel': 'gemm_tc2_kernel (cta_group::2 pair tile, BF16 kind::f16, cp.async B gather): dW1 = d_hid^T x',
+                'launches_timed': len(gb), 'avg_launch_ms': ms_gb / len(gb), 'achieved': flop_gb / (ms_gb * 1e-3) / 1e12,
+                'unit': 'TFLOP/s', 'peak': pk_['bf16_tflops_sustained'], 'frac': flop_gb / (ms_gb * 1e-3) / 1e12 / pk_['bf16_tflops_sustained']}
         tp = [r for r in log.records if r.name.startswith('xnrs_titlepool_fwd')]
         if tp:
             bf = tp[0].name.endswith('bf16')
@@ -812,6 +822,14 @@ def main():
     else:
         line = train_workload(ctx, args, 'cl', want_eager=True)
         line['sub'] = {'nrms_train': train_workload(ctx, args, 'nrms'), 'eval': eval_workload(ctx, args)}
+        if args.precision == 'tf32x3':
+            # second lines in the bf16 STORAGE mode (north-star tolerance class 2e-2): beside the fp32-accurate numbers, never
+            # instead of them
+            import copy
+            bf = copy.copy(args)
+            bf.precision = 'bf16'
+            line['sub']['cl_train_bf16'] = train_workload(ctx, bf, 'cl', want_cpu=False)
+            line['sub']['eval_bf16'] = eval_workload(ctx, bf, want_cpu=False)
     if ctx.rank == 0:
         print(json.dumps(line))
     ctx.close()

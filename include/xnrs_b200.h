@@ -228,9 +228,10 @@ int xnrs_infonce_normalize_bwd(const float *d_ehat, const float *ehat, const flo
 /* ---- rows E + Me: per-impression scoring and ranking metrics (training.py:194-227; metrics.py:7-44)
  * CSR impressions: candidates of impression i are cand_ids[offsets[i]:offsets[i+1]].  score =
  * act(<user[i], news_vecs[cand]>) (act: 0 raw, 1 relu, 2 sigmoid), then nan_to_num(nan 0, +inf 1, -inf 0).
- * If user == NULL, `scores_io` holds raw scores computed upstream; `act` is applied to them in place.  metrics_out (n_imp,6) doubles:
+ * news_vecs has n_news rows; a candidate id outside [0, n_news) is scored as article 0 (the pad article), never read out of
+ * bounds.  If user == NULL, `scores_io` holds raw scores computed upstream; `act` is applied to them in place.  metrics_out (n_imp,6) doubles:
  * auc, rr, ndcg@5, ndcg@10, ctr@1, ctr@10.  Tie order: descending score, then descending index. */
-int xnrs_eval_impressions(const float *user, const float *news_vecs, int T, const int *cand_ids,
+int xnrs_eval_impressions(const float *user, const float *news_vecs, long long n_news, int T, const int *cand_ids,
                           const long long *offsets, const float *targets, long long n_imp, int act,
                           float *scores_io, double *metrics_out, xnrs_stream_t st);
 /* sums[0..5] += column sums over impressions with a finite auc, sums[6] += their count */

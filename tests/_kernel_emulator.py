@@ -456,12 +456,14 @@ def _xnrs_adam_tick(step_dev, b1, b2, bc):
     bc[0], bc[1] = 1 / (1 - b1 ** t), 1 / math.sqrt(1 - b2 ** t)
 
 
-def _xnrs_eval_impressions(user, news_vecs, T, cand_ids, offsets, targets, n_imp, act, scores, metrics):
+def _xnrs_eval_impressions(user, news_vecs, n_news, T, cand_ids, offsets, targets, n_imp, act, scores, metrics):
     from oracle import xnrs_oracle as O
     for i in range(n_imp):
         a, b = int(offsets[i]), int(offsets[i + 1])
         if user is not None:
-            s = news_vecs[cand_ids[a:b].long()] @ user[i]
+            cid = cand_ids[a:b].long()
+            cid = torch.where((cid >= 0) & (cid < n_news), cid, torch.zeros_like(cid))
+            s = news_vecs[cid] @ user[i]
             s = torch.relu(s) if act == 1 else (torch.sigmoid(s) if act == 2 else s)
             scores[a:b] = s
         elif act:

@@ -407,6 +407,27 @@ def test_active_row_adam_equals_dense_adam(device, monkeypatch):
             assert_close(runs[0][k], runs[1][k], 5e-2, k, atol=1e-2)
 
 
+def test_autograd_grad_with_a_trainer_attached_leaves_the_optimiser_buffer_alone(device):
+    """weight gradients go straight into FlatAdam's flat buffer ONLY inside the trainers' own backward (K.direct_grads);
+    torch.autograd.grad on the same model returns ordinary gradient tensors and does not touch flat_g"""
+    fx, cfg, model = build('cl', device)
+    batch = fixture_batch(fx, device)
+    tr = ContrastiveRankingTrainer(cfg, model)
+    tr.optimizer.zero_grad()
+    total, *_ = tr.losses(batch)
+    params = [p for p in model.parameters() if p.numel() > 1]
+    grads = torch.autograd.grad(total, params, allow_unused=True)
+    assert all(g is not None for g in grads)
+    assert float(tr.optimizer.flat_g.abs().sum()) == 0.0
+    named = dict(model.named_parameters())
+    for (k, p), g in zip([(k, p) for k, p in named.items() if p.numel() > 1], grads):
+        assert_close(g, fx['grad/' + k], 2e-4, 'autograd.grad ' + k, atol=2e-6)
+    total2, *_ = tr.losses(batch)
+    with K.direct_grads():
+        total2.backward()
+    assert float(tr.optimizer.flat_g.abs().sum()) > 0.0
+
+
 def test_flat_adam_refuses_detached_gradients(device):
     """FlatAdam updates from ONE flat gradient buffer; if user code replaces the parameters' .grad views
     (model.zero_grad(set_to_none=True)) the step must fail loudly instead of training on zeros"""

@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(MT)
 eval_impressions_kernel(const float *__restrict__ user, const float *__restrict__ news_vecs, int T,
                         const int *__restrict__ cand_ids, const long long *__restrict__ offsets,
                         const float *__restrict__ targets, long long n_imp, int act, float *__restrict__ scores_io,
-                        double *__restrict__ metrics_out, int min_n) {
+                        double *__restrict__ metrics_out, int min_n, long long n_news) {
     __shared__ float s_sc[MCAP];
     __shared__ float s_tg[MCAP];
     __shared__ double red[32];
@@ -49,7 +49,9 @@ eval_impressions_kernel(const float *__restrict__ user, const float *__restrict_
             const int T4 = T >> 2;
             const float4 *u4 = reinterpret_cast<const float4 *>(user) + imp * T4;
             for (int c = warp; c < n; c += nw) {
-                const float4 *v4 = reinterpret_cast<const float4 *>(news_vecs) + (long long)cand_ids[beg + c] * T4;
+                long long cid = cand_ids[beg + c];
+                if (cid < 0 || cid >= n_news) cid = 0;        // an id outside the catalogue scores like the pad article (row 0)
+                const float4 *v4 = reinterpret_cast<const float4 *>(news_vecs) + cid * T4;
                 float acc = 0.f;
                 for (int i = lane; i < T4; i += 32) {
                     const float4 a = v4[i], b = u4[i];
@@ -142,7 +144,7 @@ __global__ void __launch_bounds__(EW * 32)
 eval_impressions_warp_kernel(const float *__restrict__ user, const float *__restrict__ news_vecs, int T4,
                              const int *__restrict__ cand_ids, const long long *__restrict__ offsets,
                              const float *__restrict__ targets, long long n_imp, int act, float *__restrict__ scores_io,
-                             double *__restrict__ metrics_out) {
+                             double *__restrict__ metrics_out, long long n_news) {
     __shared__ float s_sc_all[EW][WCAP];
     __shared__ float s_tg_all[EW][WCAP];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -161,7 +163,8 @@ eval_impressions_warp_kernel(const float *__restrict__ user, const float *__rest
             for (int k = 0; k < NV; ++k) u[k] = (k * 32 + lane < T4) ? u4[k * 32 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
             for (int c0 = 0; c0 < n; c0 += 4) {
                 float acc[4];
-                const int myid = (lane < 4 && c0 + lane < n) ? cand_ids[beg + c0 + lane] : 0;
+                int myid = (lane < 4 && c0 + lane < n) ? cand_ids[beg + c0 + lane] : 0;
+                if (myid < 0 || myid >= n_news) myid = 0;      // out-of-catalogue id -> the pad article (row 0), never out of bounds
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int id = __shfl_sync(0xffffffffu, myid, q);
@@ -305,13 +308,13 @@ __global__ void metric_sums_kernel(const double *__restrict__ metrics, long long
 
 using namespace xnrs;
 
-extern "C" int xnrs_eval_impressions(const float *user, const float *news_vecs, int T, const int *cand_ids,
+extern "C" int xnrs_eval_impressions(const float *user, const float *news_vecs, long long n_news, int T, const int *cand_ids,
                                      const long long *offsets, const float *targets, long long n_imp, int act,
                                      float *scores_io, double *metrics_out, xnrs_stream_t st) {
     XNRS_REQUIRE(n_imp >= 0 && act >= 0 && act <= 2, "bad arguments");
     if (n_imp == 0) return XNRS_OK;
     XNRS_REQUIRE(offsets && targets && scores_io && metrics_out, "null pointer");
-    if (user) XNRS_REQUIRE(news_vecs && cand_ids && T > 0 && T % 4 == 0, "scoring needs news_vecs, cand_ids, T % 4 == 0");
+    if (user) XNRS_REQUIRE(news_vecs && cand_ids && T > 0 && T % 4 == 0 && n_news > 0, "scoring needs news_vecs (n_news rows), cand_ids, T % 4 == 0");
     static bool table_set = false;
     if (!table_set) {
         double h[10];
@@ -325,7 +328,7 @@ extern "C" int xnrs_eval_impressions(const float *user, const float *news_vecs, 
         const int T4 = T / 4;
         long long blocks = cdiv(n_imp, EW), cap = 32LL * num_sms();
         const unsigned grid = (unsigned)(blocks < cap ? blocks : cap);
-#define XNRS_EW(NV) eval_impressions_warp_kernel<NV><<<grid, EW * 32, 0, STREAM(st)>>>(user, news_vecs, T4, cand_ids, offsets, targets, n_imp, act, scores_io, metrics_out)
+#define XNRS_EW(NV) eval_impressions_warp_kernel<NV><<<grid, EW * 32, 0, STREAM(st)>>>(user, news_vecs, T4, cand_ids, offsets, targets, n_imp, act, scores_io, metrics_out, n_news)
         if (T4 <= 32) XNRS_EW(1);
         else if (T4 <= 64) XNRS_EW(2);
         else if (T4 <= 128) XNRS_EW(4);
@@ -336,7 +339,7 @@ extern "C" int xnrs_eval_impressions(const float *user, const float *news_vecs, 
     // ... and the CTA-per-impression kernel for the longer ones (it skips impressions the warp kernel took)
     long long cap = warp_ok ? 2LL * num_sms() : 16LL * num_sms();        // with the warp kernel this one only sweeps for long impressions
     eval_impressions_kernel<<<(unsigned)(n_imp < cap ? n_imp : cap), MT, 0, STREAM(st)>>>(
-        user, news_vecs, T, cand_ids, offsets, targets, n_imp, act, scores_io, metrics_out, warp_ok ? WCAP + 1 : 0);
+        user, news_vecs, T, cand_ids, offsets, targets, n_imp, act, scores_io, metrics_out, warp_ok ? WCAP + 1 : 0, n_news);
     XNRS_LAUNCHED();
     return XNRS_OK;
 }

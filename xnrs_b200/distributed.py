@@ -193,7 +193,8 @@ class DataParallelTrainer:
         if self.world > 1 and self.sparse_tables:
             K.sparse_grad_log = []
         try:
-            total.backward()
+            with K.direct_grads():
+                total.backward()
             log = K.sparse_grad_log or []
         finally:
             K.sparse_grad_log = None

@@ -256,8 +256,8 @@ def eval_impressions(user, news_vecs, cand_ids, offsets, targets, act=1, scores=
     if scores is None:
         scores = torch.empty(targets.numel(), device=dev, dtype=torch.float32)
     metrics = torch.empty((n_imp, 6), device=dev, dtype=torch.float64)
-    T = news_vecs.shape[1] if news_vecs is not None else 0
-    call('xnrs_eval_impressions', user, news_vecs, T, cand_ids, offsets, targets, n_imp, act, scores, metrics)
+    n_news, T = (news_vecs.shape[0], news_vecs.shape[1]) if news_vecs is not None else (0, 0)
+    call('xnrs_eval_impressions', user, news_vecs, n_news, T, cand_ids, offsets, targets, n_imp, act, scores, metrics)
     return scores, metrics
 
 
@@ -308,7 +308,25 @@ def _resolve_rows(x, rows, fuse_ok: bool = True):
 # same result as autograd's own ``param.grad += d_param``, without the temporary, its allocation and the add kernel
 # (12-20 launches per step).  Any other parameter (no trainer, torch.autograd.grad callers) takes the ordinary path.
 
+_direct_enabled = False
+
+
+@contextlib.contextmanager
+def direct_grads():
+    """the trainers wrap THEIR backward pass in this: only then do weight gradients go straight into FlatAdam's buffer.  Any
+    other autograd user (torch.autograd.grad, the explainer's input-gradient loop) gets ordinary gradient tensors back and
+    leaves the optimiser's buffer untouched."""
+    global _direct_enabled
+    old, _direct_enabled = _direct_enabled, True
+    try:
+        yield
+    finally:
+        _direct_enabled = old
+
+
 def _direct(param) -> Optional[torch.Tensor]:
+    if not _direct_enabled:
+        return None
     g = param.grad if getattr(param, '_xnrs_direct', False) else None
     return g if (g is not None and g.is_contiguous()) else None
 
@@ -651,6 +669,7 @@ class EmbeddingFn(torch.autograd.Function):
             return None, None, None
         dw = torch.zeros(ctx.shape, device=dy.device, dtype=torch.float32)
         call('xnrs_scatter_add_rows', dw, ctx.shape[0], ctx.shape[1], idx, idx.numel(), dy, dy.stride(0), ctx.pad)
+        mark_active_rows(weight, idx, ctx.pad)         # (a row-sparse optimiser must learn about these rows on this path too)
         return dw, None, None
 
 

@@ -222,7 +222,8 @@ class RankingTrainer:
         """BaseTrainer._train_step (training.py:97-112)."""
         self.optimizer.zero_grad()
         loss, preds, _ = self.rec_loss(batch)
-        loss.backward()
+        with K.direct_grads():
+            loss.backward()
         self.optimizer.step()
         self.current_train_step += 1
         return {'loss': loss.detach(), 'logits': preds}
@@ -298,7 +299,8 @@ class ContrastiveRankingTrainer(MSERankingTrainer):
     def _train_step(self, batch: dict) -> dict:
         self.optimizer.zero_grad()
         total, loss_rec, loss_cl, preds = self.losses(batch)
-        total.backward()
+        with K.direct_grads():
+            total.backward()
         self.optimizer.step()
         self.current_train_step += 1
         return {'loss': total.detach(), 'loss_rec': loss_rec.detach(), 'loss_cl': loss_cl.detach(), 'logits': preds}

@@ -55,6 +55,7 @@ struct TcArgs {
     int a_mn, b_mn;         // 1: operand stored [K, MN] (MN contiguous); 0: stored [MN, K] (K contiguous)
     const int *a_gather;    // K-major A: stored rows gathered through this index (table gather fused by TMA gather4)
     const int *b_gather;    // MN-major B: stored rows (= K index) gathered through this index
+    int pf_stages;          // gathered weight-gradient form: L2-prefetch the table rows this many stages ahead (0: off)
     int lsu_gather;         // CTA-pair kernel: 1 = A rows, 2 = B rows gathered by a cp.async producer warp instead of TMA gather4
     const float *A; long long lda;      // raw operand pointers for that warp
     const float *B; long long ldb;
@@ -656,8 +657,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 }
                 // weight-gradient form: every stage touches 32 / 64 NEW random table rows (DRAM page misses) and only 3 / 6
                 // stages are in flight, so the rows of the stage PF steps ahead are pulled into L2 now (warp gw's share)
-                constexpr int PF = 4;
-                if (p.lsu_gather == 2) {
+                const int PF = p.pf_stages;
+                if (p.lsu_gather == 2 && PF > 0) {
                     const long long kp = k0 + (long long)PF * kstep + lane + 32 * gw;
                     if (gw < kstep / 32 && kp < kend && kp < p.K) pfrow = p.b_gather[kp];
                 }
@@ -1135,6 +1136,12 @@ static bool make_map_bf16(CUtensorMap *map, const void *base, long long inner, l
 
 int g_opt_2cta = -2;       // -2: read XNRS_GEMM_2CTA on first use
 
+static int gather_prefetch_stages() {       // XNRS_GATHER_PF: stages of look-ahead of the L2 prefetch in the gathered dW GEMM
+    static int pf = -1;
+    if (pf < 0) { const char *e = getenv("XNRS_GATHER_PF"); pf = e ? atoi(e) : 4; if (pf < 0) pf = 0; }
+    return pf;
+}
+
 int gemm_tensorcore(const GemmArgs &a, int precision, cudaStream_t st, int *status) {
     // shapes / layouts the TMA path cannot take fall through to the exact-fp32 SIMT kernel
     if (a.a_rows && a.transA) return 0;          // gather is fused for K-major A (forward) ...
@@ -1155,6 +1162,7 @@ int gemm_tensorcore(const GemmArgs &a, int precision, cudaStream_t st, int *stat
     p.a_gather = a.a_rows; p.b_gather = a.b_rows;
     p.A = a.A; p.lda = a.lda; p.B = a.B; p.ldb = a.ldb;
     p.lsu_gather = 0;
+    p.pf_stages = gather_prefetch_stages();
     p.elt = 4; p.c_bf16 = 0;
     memset(&p.pool, 0, sizeof(p.pool));
     p.passes = (precision == XNRS_PREC_TF32X3) ? 3 : 1;
@@ -1477,6 +1485,7 @@ extern "C" int xnrs_gemm_bf16(int transA, int transB, long long M, long long N, 
     p.a_gather = a_rows; p.b_gather = b_rows;
     p.A = reinterpret_cast<const float *>(A); p.lda = lda; p.B = reinterpret_cast<const float *>(B); p.ldb = ldb;
     p.lsu_gather = a_rows ? 1 : (b_rows ? 2 : 0);
+    p.pf_stages = gather_prefetch_stages();
     XNRS_REQUIRE(!(a_rows && b_rows), "one gathered operand at a time");
     p.passes = 1;
     p.stages = MAX_STAGES;

@@ -551,6 +551,19 @@ def train_workload(ctx, args, model_key, want_cpu=True, want_eager=False):
                 'traffic': tr['dram_bytes_per_row'] * rows_tp / len(tp) if tr else None,
                 'algorithmic_bytes': tr['algorithmic_bytes_per_row'] * rows_tp / len(tp) if tr else None,
                 'traffic_source': f"{os.path.relpath(TRAFFIC_FILE, ROOT)}:{cls}" if tr else 'no ncu capture of this kernel class'}
+        if args.precision == 'bf16' and (tp or gb):
+            # bf16 storage mode: the step's dominant kernels are the two bf16 tensor-core launches above (the xnrs_gemm classes
+            # left on fp32 operands are the small title-level GEMMs): the headline roofline fields follow the longer of them
+            dom = max((k for k in ('fused_title_pool', 'bf16_weight_gradient') if k in roofline),
+                      key=lambda k: roofline[k]['avg_launch_ms'] * roofline[k]['launches_timed'])
+            roofline['small_fp32_gemm_class'] = {k: roofline[k] for k in ('kernel', 'achieved', 'frac', 'launches_timed', 'avg_launch_ms')}
+            for k in ('kernel', 'achieved', 'frac', 'launches_timed', 'avg_launch_ms'):
+                roofline[k] = roofline[dom][k]
+            roofline['traffic'], roofline['traffic_source'] = roofline[dom].get('traffic'), roofline[dom].get('traffic_source', 'no ncu capture of this kernel class')
+        elif tp:
+            roofline['note'] = ('the dominant GEMM class is the fc1 weight gradient WITH the table gather fused in (cp.async warps): no dense '
+                                'copy of the gathered rows exists any more; the same GEMM on a dense copy runs 0.39 ms (153 TFLOP/s), the '
+                                'copy itself 0.16 ms (tools/bench_gather_gemm.py)')
     if os.environ.get('XNRS_BENCH_DUMP') and rank == 0:      # every launch of ONE step with its event time (diagnostics)
         per = len(log.records) // steps
         with open(os.environ['XNRS_BENCH_DUMP'] + '.' + model_key, 'w') as f:

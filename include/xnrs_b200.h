@@ -72,6 +72,10 @@ int xnrs_gemm(int transA, int transB, long long M, long long N, long long K, con
               const int *a_rows, const float *B, long long ldb, const int *b_rows, float *C, long long ldc,
               const float *bias, int act, const float *aux, int accumulate, int split_k, int precision,
               xnrs_stream_t st);
+/* diagnostics: while buf != NULL, every CTA of the 1-CTA tensor-core GEMM kernel writes 8 SM-clock stamps to buf[8 * cta ..]
+ * (entry, set-up done, first operands ready, last MMA issued, accumulator ready, epilogue done, all roles done, TMEM freed);
+ * buf must hold 8 * 148 entries.  NULL switches it off (the default).  tools/bench_step_gemms.py reads it. */
+int xnrs_debug_gemm_trace(long long *buf);
 /* name of the kernel the calling thread's last xnrs_gemm dispatched to ("gemm_tc2_kernel ...", "gemm_tc_kernel<128> ...",
  * "gemm_simt_kernel"), and the number of xnrs_gemm calls made in a tensor-core precision that the exact-fp32 SIMT kernel
  * took instead (shape / alignment the TMA path cannot express): correct but slow, so it is counted, never silent */
@@ -221,6 +225,9 @@ int xnrs_dot_score_bwd(const float *u, const float *c, const float *d_s, long lo
 int xnrs_infonce_normalize(const float *emb, long long Bk, int E, float *ehat, float *inv_norm, xnrs_stream_t st);
 int xnrs_infonce_rows(float *sim, const int *labels, long long Ba, long long Bk, long long row0,
                       float temperature, float *stats, xnrs_stream_t st);
+/* data parallel: count[0] = rows of the WHOLE gathered batch with a same-label partner (the global normaliser; a function of
+ * the gathered labels only, so no all-reduce of the local counts is needed).  work = 2 zeroed words of scratch. */
+int xnrs_infonce_count(const int *labels, long long Bk, float *work, float *count, xnrs_stream_t st);
 int xnrs_infonce_finalize(const float *stats, float *loss, xnrs_stream_t st);
 int xnrs_infonce_normalize_bwd(const float *d_ehat, const float *ehat, const float *inv_norm, const float *stats,
                                float grad_scale, long long Bk, int E, float *d_emb, xnrs_stream_t st);

@@ -289,6 +289,19 @@ def test_infonce_known_answers_from_reference():
     assert float(all_diff) == 0.0                           # no anchor has a positive -> 0 / (0 + 1e-8)
 
 
+@pytest.mark.parametrize('Bk,n_lab', [(1, 3), (7, 3), (256, 6), (1025, 400), (8192, 6), (8192, 100000)])
+def test_infonce_global_count_from_labels(Bk, n_lab):
+    """data parallel: the global normaliser (rows with a same-label partner) from the gathered labels alone, exact"""
+    lab = torch.randint(0, n_lab, (Bk,), generator=g(52)).int()
+    same = lab[:, None] == lab[None, :]
+    same.fill_diagonal_(False)
+    want = float(same.any(1).sum())
+    work = cu(torch.zeros(4))
+    work[1] = 123.0                                         # overwritten, not accumulated
+    K.call('xnrs_infonce_count', cu(lab), Bk, work[2:], work[1:2])
+    assert float(work[1]) == want
+
+
 @pytest.mark.parametrize('tag', ['met', 'mett', 'kat'])
 def test_ranking_metrics_against_reference_values(tag):
     fx = load_npz('loss_metrics')
@@ -437,6 +450,17 @@ def test_tensor_core_gemm_split_k_weight_gradient_shape(prec, tol):
         acc = cu(torch.ones(256, 768))
         K.gemm(cu(dy), cu(x), trans_a=True, out=acc, accumulate=True, split_k=5)
         assert_close(acc, want + 1, tol, 'split-k accumulate')
+        # more splits than k-blocks to share out (K = 100 -> four 32-wide blocks for 7 splits) and the K range not a multiple
+        # of the rounded split length (K = 1650): the trailing splits must not contribute
+        for Ks, sk in ((100, 7), (1650, 12), (1650, 0)):
+            xs, dys = x[:Ks].contiguous(), dy[:Ks].contiguous()
+            want_s = (dys.double().T @ xs.double()).float()
+            acc = cu(torch.ones(256, 768))
+            K.gemm(cu(dys), cu(xs), trans_a=True, out=acc, accumulate=True, split_k=sk)
+            assert_close(acc, want_s + 1, tol, f'split-k {sk} of K={Ks}')
+            if prec == 'tf32':
+                got16 = K.gemm_bf16(K.cast_bf16(cu(dys)), K.cast_bf16(cu(xs)), trans_a=True, split_k=sk)
+                assert_close(got16, want_s, 2e-2, f'bf16 split-k {sk} of K={Ks}')
 
 
 @pytest.mark.parametrize('prec,tol', [('tf32x3', 5e-5), ('tf32', 3e-3)])

@@ -65,6 +65,7 @@ struct TcArgs {
     PoolArgs pool;
     int stages;
     long long tiles_m, tiles_n;
+    long long *trace;       // diagnostics (xnrs_debug_gemm_trace): 8 SM-clock stamps per CTA of the 1-CTA kernel, or NULL
 };
 
 // ---- PTX wrappers --------------------------------------------------------------------------------------------
@@ -206,6 +207,58 @@ __device__ __forceinline__ void epi_rows(uint32_t stage, const TcArgs &p, const 
                 if (e < nv) b[e] = __ldg(bias + col + e);
         }
     }
+    // Fast path (interior columns, fp32 C, no split-K): straight-line code with the 8 row reads, the optional accumulate /
+    // mask reads and the 8 row writes each issued as a batch.  One warp per SM sub-partition runs this, so its cost is the
+    // LENGTH of the dependent instruction chain: the general loop below (64-bit index math and mode checks per row) took
+    // 1.2-1.4 us per 32 x 32 block, 5 us per 128 x 128 tile — a third of a small GEMM's whole duration (SM-clock stamps).
+    if (vec_ok && nv == 4 && !p.c_bf16) {
+        const long long rows_left = p.M - row0;                 // > 0: the caller skips blocks past M
+        const long long step = 4 * p.ldc;
+        float *dst = p.C + (row0 + sub) * p.ldc + col;
+        const uint32_t s0 = stage + sub * 128 + ((ch ^ sub) << 4), s1 = stage + (sub + 4) * 128 + ((ch ^ (sub + 4)) << 4);
+        float4 v[8], o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = lds128(((i & 1) ? s1 : s0) + (i >> 1) * 1024);
+        if (p.split_k > 1) {        // partial sums: 16-byte vector reductions into C (act is NONE, bias rides on split 0)
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (4 * i + sub < rows_left)
+                    atomicAdd(reinterpret_cast<float4 *>(dst + i * step), make_float4(v[i].x + b[0], v[i].y + b[1], v[i].z + b[2], v[i].w + b[3]));
+            return;
+        }
+        if (ACT == XNRS_ACT_RELU_MASK) {
+            const float *ax = p.aux + (row0 + sub) * p.ldc + col;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                o[i] = 4 * i + sub < rows_left ? *reinterpret_cast<const float4 *>(ax + i * step) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                v[i].x = o[i].x > 0.f ? v[i].x + b[0] : 0.f; v[i].y = o[i].y > 0.f ? v[i].y + b[1] : 0.f;
+                v[i].z = o[i].z > 0.f ? v[i].z + b[2] : 0.f; v[i].w = o[i].w > 0.f ? v[i].w + b[3] : 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                v[i].x += b[0]; v[i].y += b[1]; v[i].z += b[2]; v[i].w += b[3];
+                if (ACT == XNRS_ACT_RELU) {
+                    v[i].x = fmaxf(v[i].x, 0.f); v[i].y = fmaxf(v[i].y, 0.f); v[i].z = fmaxf(v[i].z, 0.f); v[i].w = fmaxf(v[i].w, 0.f);
+                } else if (ACT == XNRS_ACT_TANH) {
+                    v[i].x = tanh_fast(v[i].x); v[i].y = tanh_fast(v[i].y); v[i].z = tanh_fast(v[i].z); v[i].w = tanh_fast(v[i].w);
+                }
+            }
+        }
+        if (p.accumulate) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                o[i] = 4 * i + sub < rows_left ? *reinterpret_cast<const float4 *>(dst + i * step) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { v[i].x += o[i].x; v[i].y += o[i].y; v[i].z += o[i].z; v[i].w += o[i].w; }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (4 * i + sub < rows_left) *reinterpret_cast<float4 *>(dst + i * step) = v[i];
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int rr = 4 * i + sub;
@@ -302,6 +355,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     __shared__ uint32_t tmem_base_smem;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    auto stamp = [&](int i) { if (p.trace) p.trace[blockIdx.x * 16 + i] = clock64(); };
+    if (threadIdx.x == 0) stamp(0);
     const int stages = p.stages, passes = p.passes;
     const int stage_bytes = (passes == 3 ? 2 : 1) * HALF;
     const int acc_cols = (passes == 3 ? 2 : 1) * BN;         // main (+ correction) accumulator columns per tile
@@ -329,6 +384,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    if (threadIdx.x == 0) stamp(1);
 
     const long long tiles_mn = p.tiles_m * p.tiles_n;
     const long long total = tiles_mn * p.split_k;
@@ -414,6 +470,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 for (long long k0 = kbeg; k0 < kend; k0 += TBK) {
                     mbar_wait(passes == 3 ? &split_bar[r.stage] : &full_bar[r.stage], r.phase);
                     tc_fence_after();
+                    if (first && t == blockIdx.x) stamp(2);
                     const uint32_t sa = smem_u32(tileA(r.stage)), sb = smem_u32(tileB(r.stage));
 #pragma unroll
                     for (int k = 0; k < TBK / 8; ++k) {
@@ -432,6 +489,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     r.advance(stages);
                 }
                 tc_commit(&tfull_bar[acc.stage]);             // accumulator ready for the epilogue
+                if (t == blockIdx.x) stamp(3);
                 acc.advance(acc_stages);
             }
         }
@@ -480,31 +538,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const long long m0 = (mn / p.tiles_n) * TBM, n0 = (mn % p.tiles_n) * BN;
             mbar_wait(&tfull_bar[acc.stage], acc.phase);
             tc_fence_after();
+            if (threadIdx.x == EPI_WARP0 * 32 && t == blockIdx.x) stamp(4);
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 float r[32];
                 const uint32_t taddr = tmem_base + acc.stage * acc_cols + c * 32 + ((uint32_t)(32 * q) << 16);
                 tc_ld32(taddr, r);
+                if (threadIdx.x == EPI_WARP0 * 32 && t == blockIdx.x && c == 0) stamp(8);
                 if (passes == 3) {
                     float corr[32];
                     tc_ld32(taddr + BN, corr);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) r[j] += corr[j];
                 }
+                if (threadIdx.x == EPI_WARP0 * 32 && t == blockIdx.x && c == 0) stamp(9);
                 if (m0 + 32 * q >= p.M || n0 + c * 32 >= p.N) continue;        // warp-uniform
                 epi_block32(r, epi_stage, p, m0 + 32 * q, n0 + c * 32, split, lane, vec_ok, bias_vec, p.act, p.bias);
+                if (threadIdx.x == EPI_WARP0 * 32 && t == blockIdx.x && c < 3) stamp(10 + c);
             }
             tc_fence_before();
             mbar_arrive(&tempty_bar[acc.stage]);
+            if (threadIdx.x == EPI_WARP0 * 32 && t == blockIdx.x) stamp(5);
             acc.advance(acc_stages);
         }
     }
 
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) stamp(6);
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+        if (lane == 0) stamp(7);
     }
 }
 
@@ -1135,6 +1200,7 @@ static bool make_map_bf16(CUtensorMap *map, const void *base, long long inner, l
 }
 
 int g_opt_2cta = -2;       // -2: read XNRS_GEMM_2CTA on first use
+static long long *g_gemm_trace = nullptr;     // xnrs_debug_gemm_trace
 
 static int gather_prefetch_stages() {       // XNRS_GATHER_PF: stages of look-ahead of the L2 prefetch in the gathered dW GEMM
     static int pf = -1;
@@ -1165,6 +1231,7 @@ int gemm_tensorcore(const GemmArgs &a, int precision, cudaStream_t st, int *stat
     p.pf_stages = gather_prefetch_stages();
     p.elt = 4; p.c_bf16 = 0;
     memset(&p.pool, 0, sizeof(p.pool));
+    p.trace = nullptr;
     p.passes = (precision == XNRS_PREC_TF32X3) ? 3 : 1;
     // 3xTF32 keeps BN=128: its stage is 2x larger (hi+lo), and 3 smem stages + 2 TMEM stages beat the wider tile
     // (measured: 156 vs 142 TFLOP/s); single-pass TF32 takes BN=256 (398 vs 340 TFLOP/s)
@@ -1201,7 +1268,10 @@ int gemm_tensorcore(const GemmArgs &a, int precision, cudaStream_t st, int *stat
     if (split <= 0) {
         long long want = use2 ? num_sms() / 2 : num_sms();
         long long s = tiles >= want ? 1 : want / tiles;
-        long long maxs = cdiv(a.K, 512);
+        // a CTA's K loop is latency bound (3-6 stages in flight, ~0.6 us per 32-wide k-block at 3 passes), so problems that
+        // leave SMs idle are cut into splits of >= 4 k-blocks; outputs that are not accumulated into pay a memset for it,
+        // which only pays off from K = 512 on
+        long long maxs = (a.accumulate || a.K >= 512) ? cdiv(a.K, 128) : 1;
         if (s > maxs) s = maxs;
         if (s < 1) s = 1;
         if (a.act != XNRS_ACT_NONE) s = 1;
@@ -1212,9 +1282,11 @@ int gemm_tensorcore(const GemmArgs &a, int precision, cudaStream_t st, int *stat
         *status = fail(XNRS_ERR_ARG, "%s: split_k with activation", "xnrs_gemm");
         return 1;
     }
-    p.split_k = split;
     p.k_per_split = cdiv(cdiv(a.K, split), TBK) * TBK;
+    split = (int)cdiv(a.K, p.k_per_split);         // rounding k_per_split up can empty the last splits: a split without
+    p.split_k = split;                              // k-blocks would add an accumulator no MMA ever wrote
 
+    p.trace = g_gemm_trace;
     CUtensorMap mapA, mapB;
     // gathered operands: the map spans the whole table (row count unknown to the GEMM: use the int32 range) and the box
     // is one row high — tile::gather4 fetches four such rows per instruction
@@ -1498,8 +1570,9 @@ extern "C" int xnrs_gemm_bf16(int transA, int transB, long long M, long long N, 
         if (act != XNRS_ACT_NONE || c_bf16) split = 1;
     }
     XNRS_REQUIRE(split == 1 || act == XNRS_ACT_NONE, "split_k with activation");
-    p.split_k = (int)split;
     p.k_per_split = cdiv(cdiv(K, split), 64) * 64;
+    split = cdiv(K, p.k_per_split);                 // no empty trailing splits (see gemm_tensorcore)
+    p.split_k = (int)split;
     CUtensorMap mapA, mapB;
     bool ok = true;
     if (!a_rows) ok = p.a_mn ? make_map_bf16(&mapA, A, M, K, lda, 64) : make_map_bf16(&mapA, A, K, M, lda, TBM);
@@ -1533,4 +1606,9 @@ extern "C" int xnrs_set_option(const char *name, int value) {
         return XNRS_OK;
     }
     return xnrs::fail(XNRS_ERR_ARG, "%s: unknown option", "xnrs_set_option");
+}
+
+extern "C" int xnrs_debug_gemm_trace(long long *buf) {
+    g_gemm_trace = buf;
+    return XNRS_OK;
 }

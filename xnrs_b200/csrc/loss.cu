@@ -187,6 +187,36 @@ __global__ void infonce_rows_kernel(float *__restrict__ sim, const int *__restri
     }
 }
 
+// count[0] = number of rows i of the whole (gathered) batch that have another row with the same label: the InfoNCE
+// normaliser of the GLOBAL batch.  It depends on the labels only, and every rank holds all Bk labels after the all-gather, so
+// data-parallel ranks compute it locally instead of all-reducing their local counts.  work: 2 zeroed words (partial sum,
+// ticket); the last CTA to finish publishes the total (integers < 2^24: exact and order independent in fp32).
+__global__ void __launch_bounds__(256)
+infonce_count_kernel(const int *__restrict__ labels, long long Bk, float *__restrict__ work, float *__restrict__ count) {
+    __shared__ int tile[1024];
+    __shared__ float red[32];
+    const long long i = blockIdx.x * 256LL + threadIdx.x;
+    const int lab = i < Bk ? labels[i] : 0;
+    bool has = false;
+    for (long long base = 0; base < Bk; base += 1024) {
+        const int n = (int)min(1024LL, Bk - base);
+        __syncthreads();
+        for (int t = threadIdx.x; t < n; t += 256) tile[t] = labels[base + t];
+        __syncthreads();
+        for (int j = 0; j < n; ++j) has |= (tile[j] == lab) & (base + j != i);
+    }
+    const float c = block_sum(i < Bk && has ? 1.f : 0.f, red);
+    if (threadIdx.x == 0) {
+        atomicAdd(work, c);
+        __threadfence();
+        const unsigned ticket = atomicAdd(reinterpret_cast<unsigned *>(work + 1), 1u);
+        if (ticket == gridDim.x - 1) {
+            __threadfence();
+            count[0] = atomicAdd(work, 0.f);
+        }
+    }
+}
+
 __global__ void infonce_finalize_kernel(const float *__restrict__ stats, float *__restrict__ loss) {
     loss[0] = stats[0] / (stats[1] + 1e-8f);
 }
@@ -273,6 +303,14 @@ extern "C" int xnrs_infonce_rows(float *sim, const int *labels, long long Ba, lo
     if (Ba == 0) return XNRS_OK;
     XNRS_REQUIRE(sim && labels && stats, "null pointer");
     infonce_rows_kernel<<<(unsigned)Ba, 256, 0, STREAM(st)>>>(sim, labels, Ba, Bk, row0, 1.f / temperature, stats);
+    XNRS_LAUNCHED();
+    return XNRS_OK;
+}
+
+extern "C" int xnrs_infonce_count(const int *labels, long long Bk, float *work, float *count, xnrs_stream_t st) {
+    XNRS_REQUIRE(Bk >= 0 && Bk < (1LL << 24), "bad sizes");
+    XNRS_REQUIRE(work && count && (Bk == 0 || labels), "null pointer");
+    infonce_count_kernel<<<(unsigned)max(1LL, cdiv(Bk, 256)), 256, 0, STREAM(st)>>>(labels, Bk, work, count);
     XNRS_LAUNCHED();
     return XNRS_OK;
 }

@@ -36,7 +36,12 @@ class DistInfoNCEFn(torch.autograd.Function):
     """global-batch supervised InfoNCE (training.py:433-472) with rank-local anchors."""
 
     @staticmethod
-    def forward(ctx, emb, labels, temperature):
+    def forward(ctx, emb, labels, temperature, aux=None):
+        """aux: optional float buffer that is SUMMED over ranks later in the step (FlatAdam.g_aux, part of the gradient
+        all-reduce).  With it the forward needs no collective of its own besides the all-gather: the normaliser (anchors with
+        a positive) is a function of the gathered labels, computed locally, and the rank-local share of the loss value is
+        left in aux[0] for the caller to read after the gradient all-reduce.  Without it the two statistics are all-reduced
+        here."""
         w, r = world(), rank()
         Ba, E = emb.shape
         dev = emb.device
@@ -54,11 +59,17 @@ class DistInfoNCEFn(torch.autograd.Function):
         K.call('xnrs_infonce_normalize', emb_all, Bk, E, ehat, inv_norm)
         ehat_a = ehat[row0:row0 + Ba]
         sim = K.gemm(ehat_a, ehat, trans_b=True)
-        stats = torch.zeros(2, device=dev, dtype=torch.float32)
+        work = torch.zeros(4, device=dev, dtype=torch.float32)
+        stats = work[:2]
         K.call('xnrs_infonce_rows', sim, lab_all, Ba, Bk, row0, temperature, stats)
-        dist.all_reduce(stats)
         loss = torch.empty(1, device=dev, dtype=torch.float32)
-        K.call('xnrs_infonce_finalize', stats, loss)
+        if aux is None:
+            dist.all_reduce(stats)
+            K.call('xnrs_infonce_finalize', stats, loss)
+        else:
+            K.call('xnrs_infonce_count', lab_all, Bk, work[2:], work[1:2])    # stats[1] <- the global count
+            K.call('xnrs_infonce_finalize', stats, loss)                     # this rank's share: sum over ranks = the loss
+            aux[:1].copy_(loss)
         ctx.save_for_backward(ehat, inv_norm, sim, stats)
         ctx.dims = (Ba, Bk, E, row0, w)
         return loss.reshape(())
@@ -83,7 +94,7 @@ class DistInfoNCEFn(torch.autograd.Function):
         # GLOBAL loss, so pre-multiply by world to survive the averaging
         d_emb = torch.empty((Ba, E), device=ehat.device, dtype=torch.float32)
         K.call('xnrs_axpby', Ba * E, float(w), K._f32(g).reshape(1), d_a, 0.0, d_emb)
-        return d_emb, None, None
+        return d_emb, None, None, None
 
 
 class DataParallelTrainer:
@@ -96,9 +107,10 @@ class DataParallelTrainer:
         if self.world > 1:
             dist.broadcast(trainer.optimizer.flat_p, src=0)                  # identical replicas
             if hasattr(trainer, '_compute_contrastive_loss'):
-                temp = trainer.temperature
+                temp, aux = trainer.temperature, getattr(trainer.optimizer, 'g_aux', None)
+                self.cl_aux = aux
                 trainer._compute_contrastive_loss = (
-                    lambda e, l: DistInfoNCEFn.apply(K._f32(e.reshape(e.shape[0], -1)), l, temp))
+                    lambda e, l: DistInfoNCEFn.apply(K._f32(e.reshape(e.shape[0], -1)), l, temp, aux))
 
     # tables with at least this many rows exchange their gradient as (ids, rows): LSTUR / NPA user tables (703 790 rows)
     SPARSE_MIN_ROWS = 100_000
@@ -108,7 +120,8 @@ class DataParallelTrainer:
         dense all-reduce; their touched rows travel as one all-gather of (ids | rows) per table and are scatter-added
         locally (B x (D+1) floats instead of V x D: 0.6 MB instead of 383 MB per step for the LSTUR user table)."""
         opt = self.trainer.optimizer
-        flat = opt.flat_g
+        flat = getattr(opt, 'g_store', opt.flat_g)       # [4 auxiliary floats | gradient]: one buffer, one all-reduce
+        head = flat.numel() - opt.flat_g.numel()
         tables = {}
         for weight, idx, dy, pad in log:
             if weight.shape[0] >= self.SPARSE_MIN_ROWS and id(weight) in opt.ranges:
@@ -117,7 +130,7 @@ class DataParallelTrainer:
         if not tables:
             dist.all_reduce(flat)                                            # the one gradient bucket
             return
-        cuts = sorted(opt.ranges[k] for k in tables)
+        cuts = sorted((a + head, b + head) for a, b in (opt.ranges[k] for k in tables))
         lo = 0
         for a, b in cuts + [(flat.numel(), flat.numel())]:                   # dense all-reduce of everything between the tables
             if a > lo:
@@ -200,6 +213,10 @@ class DataParallelTrainer:
             K.sparse_grad_log = None
         if self.world > 1:
             self._reduce_gradients(log)
+            if getattr(self, 'cl_aux', None) is not None and 'loss_cl' in out:
+                # the InfoNCE value was summed over ranks with the gradient (each rank contributed its anchors' share)
+                out['loss_cl'] = self.cl_aux[0].clone()
+                out['loss'] = out['loss_rec'] + tr.lambda_cl * out['loss_cl']
         tr.optimizer.step(grad_scale=1.0 / self.world)
         tr.current_train_step += 1
         return out

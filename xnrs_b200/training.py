@@ -68,7 +68,10 @@ class FlatAdam:
         sizes = [((p.numel() + 3) // 4) * 4 for p in self.params]          # keep every view 16-byte aligned
         total = sum(sizes)
         self.flat_p = torch.zeros(total, device=dev, dtype=torch.float32)
-        self.flat_g = torch.zeros(total, device=dev, dtype=torch.float32)
+        # 4 auxiliary floats sit in front of the gradient so that data-parallel scalars (the InfoNCE value) ride along in
+        # the one gradient all-reduce and zero_grad clears them with the same kernel
+        self.g_store = torch.zeros(total + 4, device=dev, dtype=torch.float32)
+        self.g_aux, self.flat_g = self.g_store[:4], self.g_store[4:]
         self.m = torch.zeros(total, device=dev, dtype=torch.float32)
         self.v = torch.zeros(total, device=dev, dtype=torch.float32)
         off = 0
@@ -107,7 +110,7 @@ class FlatAdam:
         return self.flat_p[a:b], self.flat_g[a:b], self.m[a:b], self.v[a:b]
 
     def zero_grad(self) -> None:
-        self.flat_g[:self.dense_end].zero_()
+        self.g_store[:4 + self.dense_end].zero_()
         for t in self.tables:               # only active rows can hold a gradient
             K.call('xnrs_zero_rows', self._table_views(t)[1], t['V'], t['D'], t['active'], t['count'])
 

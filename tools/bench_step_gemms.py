@@ -128,9 +128,11 @@ def main():
         t = buf.view(148, 16).cpu()
         t = t[t[:, 0] > 0]
         d = (t[:, 1:] - t[:, :1]).double() / 1965.0
+        c0 = (t[0, 1:] - t[0, 0]).double() / 1965.0
         names = ['setup', 'first_operands', 'last_mma_issued', 'acc_ready', 'epilogue_done', 'all_roles_done', 'tmem_freed', 'epi_ld1', 'epi_ld2', 'epi_chunk0', 'epi_chunk1', 'epi_chunk2', 'x13', 'x14', 'x15']
         print(json.dumps({'trace': [ta, M, N, Kd], 'ctas': int(t.shape[0]), 'kernel': _lib.lib().xnrs_last_gemm_kernel().decode(),
                           'us_since_entry_median': {n: round(float(d[:, i].median()), 2) for i, n in enumerate(names)},
+                          'cta0': [round(float(x), 2) for x in c0],
                           'us_since_entry_max': {n: round(float(d[:, i].max()), 2) for i, n in enumerate(names)}}))
     # an empty-ish kernel for scale: launch + drain of a 1-CTA kernel
     x = torch.zeros(4, device=dev)

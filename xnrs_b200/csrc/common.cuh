@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -48,6 +49,38 @@ inline int num_sms() {
 }
 
 inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
+
+// ---- programmatic dependent launch ------------------------------------------------------------------------------------
+// A training step is ~45 kernels of 2-500 us replayed from one CUDA graph; between two dependent kernels the GPU idles for
+// the ~1.5-2 us it takes to drain one grid and launch the next.  A kernel launched through launch_pdl may start while its
+// predecessor in the stream is still finishing (as soon as all the predecessor's CTAs have exited or called
+// pdl_launch_dependents): it does its set-up (barriers, TMEM, descriptor prefetch) and then calls pdl_wait(), which returns
+// once every earlier kernel has completed and its writes are visible.  RULE: a kernel launched this way touches no global
+// memory before pdl_wait().  Inside a normally launched kernel both calls are no-ops.  XNRS_PDL=0 launches everything the
+// classic way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("XNRS_PDL"); on = e ? atoi(e) != 0 : 1; }
+    return on != 0;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -65,6 +65,7 @@ struct TcArgs {
     PoolArgs pool;
     int stages;
     long long tiles_m, tiles_n;
+    int c_tma;              // 1-CTA kernel: C leaves through TMA stores / reductions of staged 32 x 32 blocks (mapC is valid)
     long long *trace;       // diagnostics (xnrs_debug_gemm_trace): 8 SM-clock stamps per CTA of the 1-CTA kernel, or NULL
 };
 
@@ -102,6 +103,21 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// TMA store of one staged 32 x 32 fp32 block (128-byte rows, 128-byte swizzle) to C; rows / columns past the tensor's extent
+// are clipped by the unit.  The reduce form adds into C at the L2 (accumulate, split-K).  Bulk-group completion.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap *map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 // Blackwell TMA gather: four independent rows (same column window) land as four consecutive smem rows
 __device__ __forceinline__ void tma_gather4(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int4 rows) {
     asm volatile(
@@ -191,13 +207,15 @@ __device__ __forceinline__ float tanh_fast(float x) {
 // 4 rows x 128 contiguous bytes per instruction for C, bias, the ReLU mask and the accumulate read.
 template <int ACT>
 __device__ __forceinline__ void epi_rows(uint32_t stage, const TcArgs &p, const float *bias, long long row0, long long col0,
-                                         long long split, int lane, bool vec_ok, bool bias_vec) {
+                                         long long split, int lane, bool vec_ok, bool bias_vec, bool has_pre, float4 bias_pre) {
     const int sub = lane >> 3, ch = lane & 7;
     const long long col = col0 + 4 * ch;
     if (col >= p.N) return;
     const int nv = (int)min((long long)4, p.N - col);
     float b[4] = {0.f, 0.f, 0.f, 0.f};
-    if (bias && (p.split_k == 1 || split == 0)) {
+    if (has_pre) {              // this lane's four bias values, loaded by the caller before it waited for the accumulator
+        b[0] = bias_pre.x; b[1] = bias_pre.y; b[2] = bias_pre.z; b[3] = bias_pre.w;
+    } else if (bias && (p.split_k == 1 || split == 0)) {
         if (bias_vec && nv == 4) {
             const float4 t = __ldg(reinterpret_cast<const float4 *>(bias + col));
             b[0] = t.x; b[1] = t.y; b[2] = t.z; b[3] = t.w;
@@ -247,12 +265,11 @@ __device__ __forceinline__ void epi_rows(uint32_t stage, const TcArgs &p, const 
                 }
             }
         }
-        if (p.accumulate) {
-#pragma unroll
+        if (p.accumulate) {     // C += v as 16-byte reductions: one fp32 add per element like load-add-store (only this CTA
+#pragma unroll                 // touches the element), without the read's round trip in the warp's dependent chain
             for (int i = 0; i < 8; ++i)
-                o[i] = 4 * i + sub < rows_left ? *reinterpret_cast<const float4 *>(dst + i * step) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { v[i].x += o[i].x; v[i].y += o[i].y; v[i].z += o[i].z; v[i].w += o[i].w; }
+                if (4 * i + sub < rows_left) atomicAdd(reinterpret_cast<float4 *>(dst + i * step), v[i]);
+            return;
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i)
@@ -318,18 +335,60 @@ __device__ __forceinline__ void epi_rows(uint32_t stage, const TcArgs &p, const 
     }
 }
 
+// r: lane l holds the FINISHED values of columns [col, col+32) of row `row + l`: stage them as 32 rows of 128 bytes in the
+// 128-byte swizzle and let one thread hand the 4 KB block to the TMA unit (store, or add-reduction for accumulate /
+// split-K).  `pending`: bulk groups of this thread that may still be reading OTHER staging buffers (0: `buf` is the only one).
+template <int PENDING>
+__device__ __forceinline__ void tma_store_block32(const float (&r)[32], uint32_t buf, const CUtensorMap *mapC, long long col,
+                                                  long long row, bool reduce, int lane) {
+    if (lane == 0) bulk_wait_read<PENDING>();       // the earlier store from `buf` has read it
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        sts128(buf + lane * 128 + ((j ^ (lane & 7)) << 4), make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]));
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+        if (reduce) tma_reduce_add_2d(mapC, buf, (int)col, (int)row);
+        else tma_store_2d(mapC, buf, (int)col, (int)row);
+        bulk_commit();
+    }
+}
+
+// bias (16-byte aligned, N % 4 == 0) + activation on a row-per-lane block
+__device__ __forceinline__ void bias_act_block32(float (&r)[32], const float *bias, long long col0, long long N, int act) {
+    if (bias) {
+        const float4 *b4 = reinterpret_cast<const float4 *>(bias + col0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (col0 + 4 * j < N) {
+                const float4 b = __ldg(b4 + j);         // same address in every lane: one L1 transaction
+                r[4 * j] += b.x; r[4 * j + 1] += b.y; r[4 * j + 2] += b.z; r[4 * j + 3] += b.w;
+            }
+        }
+    }
+    if (act == XNRS_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = fmaxf(r[j], 0.f);
+    } else if (act == XNRS_ACT_TANH) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = tanh_fast(r[j]);
+    }
+}
+
 // r: lane l holds columns [col0, col0+32) of row row0 + l (raw accumulators); stage: this warp's 4 KB staging buffer
 __device__ __forceinline__ void epi_block32(float (&r)[32], uint32_t stage, const TcArgs &p, long long row0, long long col0,
-                                            long long split, int lane, bool vec_ok, bool bias_vec, int act, const float *bias) {
+                                            long long split, int lane, bool vec_ok, bool bias_vec, int act, const float *bias,
+                                            bool has_pre = false, float4 bias_pre = float4{0.f, 0.f, 0.f, 0.f}) {
 #pragma unroll
     for (int c = 0; c < 8; ++c)
         sts128(stage + lane * 128 + ((c ^ (lane & 7)) << 4), make_float4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]));
     __syncwarp();
     switch (act) {
-        case XNRS_ACT_RELU: epi_rows<XNRS_ACT_RELU>(stage, p, bias, row0, col0, split, lane, vec_ok, bias_vec); break;
-        case XNRS_ACT_TANH: epi_rows<XNRS_ACT_TANH>(stage, p, bias, row0, col0, split, lane, vec_ok, bias_vec); break;
-        case XNRS_ACT_RELU_MASK: epi_rows<XNRS_ACT_RELU_MASK>(stage, p, bias, row0, col0, split, lane, vec_ok, bias_vec); break;
-        default: epi_rows<XNRS_ACT_NONE>(stage, p, bias, row0, col0, split, lane, vec_ok, bias_vec); break;
+        case XNRS_ACT_RELU: epi_rows<XNRS_ACT_RELU>(stage, p, bias, row0, col0, split, lane, vec_ok, bias_vec, has_pre, bias_pre); break;
+        case XNRS_ACT_TANH: epi_rows<XNRS_ACT_TANH>(stage, p, bias, row0, col0, split, lane, vec_ok, bias_vec, has_pre, bias_pre); break;
+        case XNRS_ACT_RELU_MASK: epi_rows<XNRS_ACT_RELU_MASK>(stage, p, bias, row0, col0, split, lane, vec_ok, bias_vec, has_pre, bias_pre); break;
+        default: epi_rows<XNRS_ACT_NONE>(stage, p, bias, row0, col0, split, lane, vec_ok, bias_vec, has_pre, bias_pre); break;
     }
     __syncwarp();
 }
@@ -346,7 +405,8 @@ struct StageRing {
 // the full 128 B/clk shared-memory bandwidth for BN=128; BN=256 halves the A bytes per FLOP (ncu: L1/shared was the bound).
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcArgs p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+               const __grid_constant__ CUtensorMap mapC, TcArgs p) {
     constexpr int TILE_A = TBM * TBK * 4, TILE_B = BN * TBK * 4, HALF = TILE_A + TILE_B;   // [A hi][B hi] | [A lo][B lo]
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -356,7 +416,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     auto stamp = [&](int i) { if (p.trace) p.trace[blockIdx.x * 16 + i] = clock64(); };
-    if (threadIdx.x == 0) stamp(0);
+    if (threadIdx.x == 0) {
+        stamp(0);
+        // descriptor fetch overlaps the barrier / TMEM set-up instead of delaying the first load
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB)) : "memory");
+    }
     const int stages = p.stages, passes = p.passes;
     const int stage_bytes = (passes == 3 ? 2 : 1) * HALF;
     const int acc_cols = (passes == 3 ? 2 : 1) * BN;         // main (+ correction) accumulator columns per tile
@@ -384,10 +449,59 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    pdl_launch_dependents();            // all CTAs of this grid are resident: the next kernel may set itself up meanwhile
+    pdl_wait();                         // everything below reads / writes global memory
     if (threadIdx.x == 0) stamp(1);
 
     const long long tiles_mn = p.tiles_m * p.tiles_n;
     const long long total = tiles_mn * p.split_k;
+
+    // One epilogue warp's share of a tile: the BN / 32 chunks (32 rows x 32 columns each) of TMEM lane quarter warp % 4.
+    // SM-clock stamps of the coalesced-store form (transpose through shared memory, then per-row index math, loads and
+    // 16-byte stores by every lane): 500-600 dependent instructions = 0.7-1.3 us per chunk, 3-5 us per 128 x 128 tile, a
+    // fifth to a third of a small GEMM's duration; handing chunks to other warps of the quarter did not help (same SM
+    // sub-partition).  So the common case hands the staged block to the TMA unit instead: bias + activation are applied in
+    // the row-per-lane registers, the block is staged in the layout a 128-byte-swizzled tensor map describes, and ONE
+    // thread issues a 4 KB TMA store (or add-reduction: accumulate / split-K); edge clipping, addressing and the stores
+    // themselves cost the warp nothing.  Two staging buffers per warp keep a store in flight while the next is staged.
+    constexpr int NCH = BN / 32;
+    int cbuf = 0;
+    auto epilogue_tile = [&](long long t, int a_stage, uint32_t a_phase, uint32_t stage_addr) {
+        const int q = warp & 3;                         // TMEM lane quarter this warp may access
+        const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
+                            (!p.aux || (reinterpret_cast<uintptr_t>(p.aux) & 15) == 0);
+        const bool bias_vec = (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0;
+        const long long split = t / tiles_mn, mn = t - split * tiles_mn;
+        const long long m0 = (mn / p.tiles_n) * TBM, n0 = (mn % p.tiles_n) * BN;
+        const bool bias_on = p.bias && (p.split_k == 1 || split == 0);
+        if (p.c_tma && bias_on && lane < NCH && n0 + 32 * lane < p.N)          // the tile's bias values: into L1 before the wait
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(p.bias + n0 + 32 * lane));
+        mbar_wait(&tfull_bar[a_stage], a_phase);
+        tc_fence_after();
+        if (threadIdx.x == EPI_WARP0 * 32 && t == blockIdx.x) stamp(4);
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c) {
+            float r[32];
+            const uint32_t taddr = tmem_base + a_stage * acc_cols + c * 32 + ((uint32_t)(32 * q) << 16);
+            tc_ld32(taddr, r);
+            if (passes == 3) {
+                float corr[32];
+                tc_ld32(taddr + BN, corr);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] += corr[j];
+            }
+            if (m0 + 32 * q >= p.M || n0 + c * 32 >= p.N) continue;        // warp-uniform
+            if (p.c_tma) {
+                // (N % 4 == 0 and a 16-byte aligned bias are conditions of c_tma)
+                bias_act_block32(r, bias_on ? p.bias : nullptr, n0 + c * 32, p.N, p.act);
+                tma_store_block32<1>(r, stage_addr + (cbuf << 12), &mapC, n0 + c * 32, m0 + 32 * q, p.accumulate || p.split_k > 1, lane);
+                cbuf ^= 1;
+            } else {
+                epi_block32(r, stage_addr, p, m0 + 32 * q, n0 + c * 32, split, lane, vec_ok, bias_vec, p.act, p.bias);
+            }
+            if (threadIdx.x == EPI_WARP0 * 32 && t == blockIdx.x && c < 3) stamp(10 + c);
+        }
+    };
 
     if (warp == 0) {
         // ===================== TMA producer (lane 0 drives; all 32 lanes issue the gather4 rows) =====================
@@ -527,40 +641,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
     } else {
         // ===================== epilogue: TMEM -> registers -> bias/act -> global =====================
-        const int q = warp & 3;                         // TMEM lane quarter this warp may access
-        const uint32_t epi_stage = smem_u32(smem + SMEM_DATA) + (warp - EPI_WARP0) * 4096;
-        const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
-                            (!p.aux || (reinterpret_cast<uintptr_t>(p.aux) & 15) == 0);
-        const bool bias_vec = (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0;
+        const uint32_t epi_stage = smem_u32(smem + SMEM_DATA) + (warp - EPI_WARP0) * 8192;      // two 4 KB staging buffers
         StageRing acc;
         for (long long t = blockIdx.x; t < total; t += gridDim.x) {
-            const long long split = t / tiles_mn, mn = t - split * tiles_mn;
-            const long long m0 = (mn / p.tiles_n) * TBM, n0 = (mn % p.tiles_n) * BN;
-            mbar_wait(&tfull_bar[acc.stage], acc.phase);
-            tc_fence_after();
-            if (threadIdx.x == EPI_WARP0 * 32 && t == blockIdx.x) stamp(4);
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                float r[32];
-                const uint32_t taddr = tmem_base + acc.stage * acc_cols + c * 32 + ((uint32_t)(32 * q) << 16);
-                tc_ld32(taddr, r);
-                if (threadIdx.x == EPI_WARP0 * 32 && t == blockIdx.x && c == 0) stamp(8);
-                if (passes == 3) {
-                    float corr[32];
-                    tc_ld32(taddr + BN, corr);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) r[j] += corr[j];
-                }
-                if (threadIdx.x == EPI_WARP0 * 32 && t == blockIdx.x && c == 0) stamp(9);
-                if (m0 + 32 * q >= p.M || n0 + c * 32 >= p.N) continue;        // warp-uniform
-                epi_block32(r, epi_stage, p, m0 + 32 * q, n0 + c * 32, split, lane, vec_ok, bias_vec, p.act, p.bias);
-                if (threadIdx.x == EPI_WARP0 * 32 && t == blockIdx.x && c < 3) stamp(10 + c);
-            }
+            epilogue_tile(t, acc.stage, acc.phase, epi_stage);
             tc_fence_before();
             mbar_arrive(&tempty_bar[acc.stage]);
             if (threadIdx.x == EPI_WARP0 * 32 && t == blockIdx.x) stamp(5);
             acc.advance(acc_stages);
         }
+        if (lane == 0) bulk_wait<0>();          // every TMA store / reduction of this warp has been performed
+        __syncwarp();
     }
 
     tc_fence_before();
@@ -641,7 +732,8 @@ constexpr int EPI2_WARP0 = 4 + SPLIT_WARPS, EPI2_WARPS = 8;
 
 template <bool POOL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
-gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcArgs p) {
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                const __grid_constant__ CUtensorMap mapC, TcArgs p) {
     constexpr int TILE = TBM * TBK * 4, HALF = 2 * TILE;          // per CTA: [A hi][B-half hi] | [A lo][B-half lo]
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -651,6 +743,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_rank();
+    if (threadIdx.x == 0) {     // descriptor fetch overlaps the barrier / TMEM set-up
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB)) : "memory");
+    }
     const int stages = p.stages, passes = p.passes;
     // operand tiles are 128 rows x 128 bytes whatever the element type: a stage spans 32 fp32 / 64 bf16 elements of K; an
     // MN-major tile is made of boxes of (128 bytes of MN) x (kstep k-rows): four of 4 KB (fp32) or two of 8 KB (bf16)
@@ -683,6 +779,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    pdl_launch_dependents();            // persistent grid, every CTA resident: the next kernel may set itself up meanwhile
+    pdl_wait();                         // everything below reads / writes global memory
     const long long tiles_mn = p.tiles_m * p.tiles_n;
     const long long total = tiles_mn * p.split_k;
     const long long pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
@@ -985,7 +1083,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                         lp = fmaf(h, __ldg(w2s + j), lp);
                         r[j] = h;
                     }
-                    epi_block32(r, epi_stage, p, m0 + 32 * q, n0 + c * 32, split, lane, vec_ok, bias_vec, XNRS_ACT_NONE, nullptr);
+                    if (p.c_tma) tma_store_block32<0>(r, epi_stage, &mapC, n0 + c * 32, m0 + 32 * q, false, lane);
+                    else epi_block32(r, epi_stage, p, m0 + 32 * q, n0 + c * 32, split, lane, vec_ok, bias_vec, XNRS_ACT_NONE, nullptr);
+                } else if (p.c_tma) {
+                    bias_act_block32(r, (p.bias && (p.split_k == 1 || split == 0)) ? p.bias : nullptr, n0 + c * 32, p.N, p.act);
+                    tma_store_block32<0>(r, epi_stage, &mapC, n0 + c * 32, m0 + 32 * q, p.accumulate || p.split_k > 1, lane);
                 } else {
                     epi_block32(r, epi_stage, p, m0 + 32 * q, n0 + c * 32, split, lane, vec_ok, bias_vec, p.act, p.bias);
                 }
@@ -995,6 +1097,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             if (lane == 0) mbar_arrive_cluster(tempty0 + 8 * acc.stage);
             acc.advance(acc_stages);
             if (POOL) {
+                if (p.c_tma) {          // the staging buffers double as scratch below: the last hid store must have read its block
+                    if (lane == 0) bulk_wait_read<0>();
+                    __syncwarp();
+                }
                 // TMEM is released: the next tile's MMAs run while the pooling weights and weighted sums are formed
                 // scratch lives in the epilogue warps' own (now idle) staging buffers: warp we keeps its 32 partial logits in
                 // floats [0,32) of its buffer, the column-half-0 warps keep e of their 32 rows in floats [32,64) of theirs
@@ -1140,6 +1246,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 asm volatile("bar.sync 1, 256;" ::: "memory");     // the staging buffers are reused by the next tile's stores
             }
         }
+        if (p.c_tma) {
+            if (lane == 0) bulk_wait<0>();      // every TMA store / reduction of this warp has been performed
+            __syncwarp();
+        }
     }
 
     tc_fence_before();
@@ -1200,6 +1310,16 @@ static bool make_map_bf16(CUtensorMap *map, const void *base, long long inner, l
 }
 
 int g_opt_2cta = -2;       // -2: read XNRS_GEMM_2CTA on first use
+
+// C leaves through TMA stores of staged 32 x 32 blocks when its layout allows a tensor map and the epilogue has no per-element
+// global read (ReLU mask); XNRS_TMA_STORE=0 keeps the coalesced-store epilogue everywhere
+static int c_tma_map(CUtensorMap *mapC, const float *C, long long M, long long N, long long ldc, const float *bias, int act,
+                     bool c_bf16) {
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("XNRS_TMA_STORE"); on = e ? atoi(e) : 1; }
+    return on && !c_bf16 && ldc % 4 == 0 && N % 4 == 0 && !((uintptr_t)C & 15) && !((uintptr_t)bias & 15) &&
+           act != XNRS_ACT_RELU_MASK && make_map(mapC, C, N, M, ldc, 32, false);
+}
 static long long *g_gemm_trace = nullptr;     // xnrs_debug_gemm_trace
 
 static int gather_prefetch_stages() {       // XNRS_GATHER_PF: stages of look-ahead of the L2 prefetch in the gathered dW GEMM
@@ -1287,7 +1407,8 @@ int gemm_tensorcore(const GemmArgs &a, int precision, cudaStream_t st, int *stat
     p.split_k = split;                              // k-blocks would add an accumulator no MMA ever wrote
 
     p.trace = g_gemm_trace;
-    CUtensorMap mapA, mapB;
+    CUtensorMap mapA, mapB, mapC;
+    p.c_tma = c_tma_map(&mapC, a.C, a.M, a.N, a.ldc, a.bias, a.act, false);
     // gathered operands: the map spans the whole table (row count unknown to the GEMM: use the int32 range) and the box
     // is one row high — tile::gather4 fetches four such rows per instruction
     const long long table_rows = 0x7fffffffLL;
@@ -1296,6 +1417,7 @@ int gemm_tensorcore(const GemmArgs &a, int precision, cudaStream_t st, int *stat
     ok = ok && (p.b_mn ? make_map(&mapB, a.B, a.N, a.b_rows ? table_rows : a.K, a.ldb, a.b_rows ? 1 : 32, true)
                        : make_map(&mapB, a.B, a.K, a.N, a.ldb, BN, false));
     if (!ok) return 0;
+    if (!p.c_tma) mapC = mapA;
 
     if (split > 1 && !a.accumulate) {
         if (cudaMemset2DAsync(a.C, a.ldc * sizeof(float), 0, a.N * sizeof(float), a.M, st) != cudaSuccess) {
@@ -1321,14 +1443,14 @@ int gemm_tensorcore(const GemmArgs &a, int precision, cudaStream_t st, int *stat
         if (lsu < 0) { const char *e = getenv("XNRS_LSU_GATHER"); lsu = e ? atoi(e) : 1; }
         if (lsu) p.lsu_gather = a.a_rows ? 1 : (a.b_rows ? 2 : 0);
         const long long pairs = total < num_sms() / 2 ? total : num_sms() / 2;
-        gemm_tc2_kernel<false><<<(unsigned)(2 * pairs), TC2_THREADS, smem_bytes, st>>>(mapA, mapB, p);
+        launch_pdl(gemm_tc2_kernel<false>, dim3((unsigned)(2 * pairs)), dim3(TC2_THREADS), smem_bytes, st, mapA, mapB, mapC, p);
         g_last_gemm_kernel = p.passes == 3 ? "gemm_tc2_kernel (cta_group::2, 256x256 pair tile, 3xTF32)"
                                            : "gemm_tc2_kernel (cta_group::2, 256x256 pair tile, TF32)";
     } else if (BN == 256) {
-        gemm_tc_kernel<256><<<grid, TC_THREADS, smem_bytes, st>>>(mapA, mapB, p);
+        launch_pdl(gemm_tc_kernel<256>, dim3(grid), dim3(TC_THREADS), smem_bytes, st, mapA, mapB, mapC, p);
         g_last_gemm_kernel = p.passes == 3 ? "gemm_tc_kernel<256> (3xTF32)" : "gemm_tc_kernel<256> (TF32)";
     } else {
-        gemm_tc_kernel<128><<<grid, TC_THREADS, smem_bytes, st>>>(mapA, mapB, p);
+        launch_pdl(gemm_tc_kernel<128>, dim3(grid), dim3(TC_THREADS), smem_bytes, st, mapA, mapB, mapC, p);
         g_last_gemm_kernel = p.passes == 3 ? "gemm_tc_kernel<128> (3xTF32)" : "gemm_tc_kernel<128> (TF32)";
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -1476,6 +1598,9 @@ static int titlepool_fwd_impl(const void *x, long long ldx, const int *x_rows, c
              make_map(&mapB, reinterpret_cast<const float *>(w1), F, A, F, 128, false);
     }
     if (!ok) return fail(XNRS_ERR_UNSUPPORTED, "%s: tensor map encoding failed", "xnrs_titlepool_fwd");
+    CUtensorMap mapC;               // hid (n_rows x A, fp32 storage only) leaves through TMA stores
+    p.c_tma = c_tma_map(&mapC, reinterpret_cast<const float *>(hid), n_rows, A, A, nullptr, XNRS_ACT_NONE, elt == 2);
+    if (!p.c_tma) mapC = mapB;
     const int smem_bytes = SMEM_DATA + SMEM_EPI + 1024;
     static bool attr_set = false;
     if (!attr_set) {
@@ -1496,7 +1621,7 @@ static int titlepool_fwd_impl(const void *x, long long ldx, const int *x_rows, c
     if (split) {
         p.pool.pooled = nullptr;
         p.pool.zsum = nullptr;
-        gemm_tc2_kernel<true><<<(unsigned)(2 * pairs), TC2_THREADS, smem_bytes, st>>>(mapA, mapB, p);
+        launch_pdl(gemm_tc2_kernel<true>, dim3((unsigned)(2 * pairs)), dim3(TC2_THREADS), smem_bytes, st, mapA, mapB, mapC, p);
         XNRS_LAUNCHED();
         const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(cdiv(R, 8), 16LL * num_sms()));
         if (elt == 2) titlepool_wsum_kernel<true><<<grid, 256, 0, st>>>(x, ldx, x_rows, seg, e, R, n_rows, F, attn, pooled);
@@ -1507,7 +1632,7 @@ static int titlepool_fwd_impl(const void *x, long long ldx, const int *x_rows, c
     if (cudaMemsetAsync(pooled, 0, (size_t)R * F * sizeof(float), st) != cudaSuccess ||
         cudaMemsetAsync(zsum, 0, (size_t)R * sizeof(float), st) != cudaSuccess)
         return fail(XNRS_ERR_CUDA, "%s: memset failed", "xnrs_titlepool_fwd");
-    gemm_tc2_kernel<true><<<(unsigned)(2 * pairs), TC2_THREADS, smem_bytes, st>>>(mapA, mapB, p);
+    launch_pdl(gemm_tc2_kernel<true>, dim3((unsigned)(2 * pairs)), dim3(TC2_THREADS), smem_bytes, st, mapA, mapB, mapC, p);
     XNRS_LAUNCHED();
     const long long work = std::max<long long>(n_rows, R * (F / 4));
     long long blocks = cdiv(work, 256), cap = 8LL * num_sms();
@@ -1580,6 +1705,9 @@ extern "C" int xnrs_gemm_bf16(int transA, int transB, long long M, long long N, 
     if (a_rows) mapA = mapB;
     if (b_rows) mapB = mapA;
     if (!ok) return fail(XNRS_ERR_UNSUPPORTED, "%s: tensor map encoding failed", "xnrs_gemm_bf16");
+    CUtensorMap mapC;
+    p.c_tma = c_tma_map(&mapC, reinterpret_cast<const float *>(C), M, N, ldc, bias, act, c_bf16 != 0);
+    if (!p.c_tma) mapC = mapB;
     if (split > 1 && !accumulate) {
         if (cudaMemset2DAsync(C, ldc * sizeof(float), 0, N * sizeof(float), M, st) != cudaSuccess)
             return fail(XNRS_ERR_CUDA, "%s: memset2d failed", "xnrs_gemm_bf16");
@@ -1594,7 +1722,7 @@ extern "C" int xnrs_gemm_bf16(int transA, int transB, long long M, long long N, 
         attr_set = true;
     }
     const long long total = tiles * split, pairs = total < npairs ? total : npairs;
-    gemm_tc2_kernel<false><<<(unsigned)(2 * pairs), TC2_THREADS, smem_bytes, st>>>(mapA, mapB, p);
+    launch_pdl(gemm_tc2_kernel<false>, dim3((unsigned)(2 * pairs)), dim3(TC2_THREADS), smem_bytes, st, mapA, mapB, mapC, p);
     g_last_gemm_kernel = "gemm_tc2_kernel (cta_group::2, 256x256 pair tile, BF16 kind::f16)";
     XNRS_LAUNCHED();
     return XNRS_OK;

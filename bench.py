@@ -165,6 +165,10 @@ class Ctx:
 
     def close(self):
         if self.world > 1:
+            from xnrs_b200 import distributed as D
+            for px in D._peer_cache.values():       # a peer kernel that gave up waiting would have produced garbage: fail loudly
+                px.check()
+            D._peer_cache.clear()                   # peer mappings go before the communicator
             self.dist.destroy_process_group()
 
 
@@ -602,7 +606,7 @@ def train_workload(ctx, args, model_key, want_cpu=True, want_eager=False):
         'data': 'synthetic',
         'config': {'workload': workload_name(B, model_key), 'global_batch': B * world, 'parallelism': f'dp{world}',
                    'l2': 'inputs larger than L2: 307 MB token table, ~0.5 GB of gathered rows per step, 8 batches cycled',
-                   'precision': args.precision, 'final_loss': last[0],
+                   'precision': args.precision, 'final_loss': last[0], 'infonce_exchange': dp.infonce_exchange,
                    'dedup_titles': not args.no_dedup, 'skip_padding': not args.no_skip_padding,
                    'cuda_graph': ({'graph_launches_per_region': graph_launches, 'replays': stepper.replays, 'captures': stepper.captures,
                                    'eager_steps': stepper.eager_steps, 'shape_buckets': len(stepper.graphs)} if stepper else False),

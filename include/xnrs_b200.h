@@ -232,6 +232,23 @@ int xnrs_infonce_finalize(const float *stats, float *loss, xnrs_stream_t st);
 int xnrs_infonce_normalize_bwd(const float *d_ehat, const float *ehat, const float *inv_norm, const float *stats,
                                float grad_scale, long long Bk, int E, float *d_emb, xnrs_stream_t st);
 
+/* ---- row C across GPUs: the exchange steps of the global-batch InfoNCE over NVLink peer memory (one process per GPU; the
+ * reference computes its InfoNCE over one process's batch: training.py:433-472; data parallelism is this repo's extension,
+ * SURVEY.md 8(e)).  ptrs: device array of the W base addresses of the ranks' symmetric buffers (identical layout; offsets
+ * in bytes).  ctl: 8 zero-initialised ints of device memory private to the rank (epochs / tickets / [4] = a peer never
+ * arrived).  Flags: W uint32 slots per kind at off_flags in every buffer, zero-initialised.
+ * xnrs_peer_normalize_allgather: ehat = emb / max(|emb|, 1e-12) of this rank's Ba rows, stored with 1/norm and the labels into
+ * rows [rank*Ba, (rank+1)*Ba) of EVERY rank's gathered arrays; returns (stream order) once every rank's rows have arrived here.
+ * xnrs_peer_reduce_scatter_normalize_bwd: d = sum over ranks of their d_ehat rows [rank*Ba, +Ba) (pulled in rank order),
+ * d_emb = grad_scale * (*grad_scale_dev or 1) / (stats[1] + 1e-8) * inv_norm * (d - ehat <ehat, d>). */
+int xnrs_peer_normalize_allgather(const float *emb, const int *labels, long long Ba, int E, int rank, int world,
+                                  const long long *ptrs, long long off_flags, long long off_ehat, long long off_inv,
+                                  long long off_lab, int *ctl, xnrs_stream_t st);
+int xnrs_peer_reduce_scatter_normalize_bwd(const long long *ptrs, long long off_flags, long long off_dehat, long long Ba, int E,
+                                           int rank, int world, const float *ehat_a, const float *inv_norm_a,
+                                           const float *stats, float grad_scale, const float *grad_scale_dev, float *d_emb,
+                                           int *ctl, xnrs_stream_t st);
+
 /* ---- rows E + Me: per-impression scoring and ranking metrics (training.py:194-227; metrics.py:7-44)
  * CSR impressions: candidates of impression i are cand_ids[offsets[i]:offsets[i+1]].  score =
  * act(<user[i], news_vecs[cand]>) (act: 0 raw, 1 relu, 2 sigmoid), then nan_to_num(nan 0, +inf 1, -inf 0).

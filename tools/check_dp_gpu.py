@@ -57,7 +57,9 @@ def main():
     big = want_g.abs() > 1e-3 * scale
     ep = float((tr.optimizer.flat_p - full.optimizer.flat_p)[big].abs().max())
     ok = eg < 1e-4 and ecl < 1e-4 and ep < 2e-5
-    print(f'rank {rank}/{world}: grad err {eg:.2e}, InfoNCE err {ecl:.2e}, param err {ep:.2e} -> {"OK" if ok else "FAIL"}', flush=True)
+    dp.check_peers()
+    print(f'rank {rank}/{world}: grad err {eg:.2e}, InfoNCE err {ecl:.2e}, param err {ep:.2e} -> {"OK" if ok else "FAIL"} '
+          f'[InfoNCE exchange: {dp.infonce_exchange}]', flush=True)
 
     # (2) six more data-parallel steps, eager vs CUDA-graph replay (collectives inside the graph)
     from xnrs_b200.graphs import GraphedStep
@@ -106,6 +108,9 @@ def main():
     replays = finals[1][2].replays
     finals.clear()                      # the captured graphs hold NCCL work: release them before the communicator goes away
     del st, d2, t2
+    dp.check_peers()
+    from xnrs_b200 import distributed as D
+    D._peer_cache.clear()
     import gc
     gc.collect()
     torch.cuda.synchronize()

@@ -8,6 +8,13 @@ The reference is single-process; what shards naturally is the imp
   * all parameter gradients live in FlatAdam's single flat buffer: ONE all-reduce per step, averaged by
     folding 1/world into the Adam kernel's grad_scale.
 No collective is issued on the data path itself (gathers/encoders/scorer are rank-local).
+
+On GPUs of one node the two exchange steps of the InfoNCE term do not go through NCCL: `PeerExchange` maps one buffer per
+rank into every rank (CUDA VMM peer mappings, set up by torch symmetric memory) and two kernels of this library fuse the
+exchange with the work around it over NVLink — normalise + all-gather (each rank stores its finished rows into all gathered
+buffers) and reduce-scatter + normalisation backward (each rank pulls and sums the partial gradients of its rows);
+csrc/peer.cu.  XNRS_PEER=0, a CPU / gloo group, or a failing rendezvous keep the NCCL collectives; `infonce_exchange` on the
+trainer says which path runs.
 """
 from __future__ import annotations
 
@@ -32,6 +39,72 @@ def shard_range(n: int, r: int, w: int):
     return lo, lo + base + (1 if r < rem else 0)
 
 
+class PeerExchange:
+    """the symmetric buffer of one (local batch, embedding size): flags | gathered ehat, 1/norm, labels | d_ehat"""
+
+    def __init__(self, Ba: int, E: int, dev: torch.device):
+        import torch.distributed._symmetric_memory as symm_mem
+        w = world()
+        Bk = w * Ba
+        self.Ba, self.E, self.Bk = Ba, E, Bk
+
+        def up(n):                                                  # regions start on 256-byte boundaries
+            return (n + 255) // 256 * 256
+        self.off_flags_ag, self.off_flags_rs = 0, 256               # 64 uint32 slots each
+        self.off_ehat = 512
+        self.off_inv = self.off_ehat + up(Bk * E * 4)
+        self.off_lab = self.off_inv + up(Bk * 4)
+        self.off_dehat = self.off_lab + up(Bk * 4)
+        total = self.off_dehat + up(Bk * E * 4)
+        self.buf = symm_mem.empty(total // 4, dtype=torch.float32, device=dev)
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, dist.group.WORLD)
+        self.ptrs = torch.tensor([int(p) for p in self.hdl.buffer_ptrs], dtype=torch.int64, device=dev)
+        self.ctl = torch.zeros(8, dtype=torch.int32, device=dev)
+
+        def view(off, n):
+            return self.buf[off // 4: off // 4 + n]
+        self.ehat_all = view(self.off_ehat, Bk * E).view(Bk, E)
+        self.inv_all = view(self.off_inv, Bk)
+        self.lab_all = view(self.off_lab, Bk).view(torch.int32)
+        self.d_ehat = view(self.off_dehat, Bk * E).view(Bk, E)
+        torch.cuda.synchronize(dev)
+        dist.barrier()                                              # every rank's flags are zero before the first signal
+
+    def check(self) -> None:
+        """raise if a kernel gave up waiting for a peer (reads 4 bytes back: call it outside the hot loop)"""
+        if int(self.ctl[4]) != 0:
+            raise RuntimeError('xnrs_b200 peer exchange: a rank never arrived at an InfoNCE exchange step (ranks out of step?)')
+
+
+_peer_cache = {}
+_peer_broken = []
+
+
+def peer_exchange(Ba: int, E: int, dev: torch.device):
+    """the PeerExchange for this shape, or None when the NCCL collectives are to be used.  The first call for a shape is a
+    collective (rendezvous + barrier) and must happen on every rank, outside CUDA-graph capture."""
+    import os
+    if (os.environ.get('XNRS_PEER', '1') == '0' or dev.type != 'cuda' or world() == 1 or world() > 64 or E % 4 or E > 256
+            or dist.get_backend() != 'nccl' or _peer_broken):
+        return None
+    key = (Ba, E, dev.index)
+    px = _peer_cache.get(key)
+    if px is None:
+        if torch.cuda.is_current_stream_capturing():
+            return None
+        try:
+            px = PeerExchange(Ba, E, dev)
+        except Exception as exc:                                    # no peer access / symmetric memory unsupported on this box
+            import sys
+            print(f'xnrs_b200: peer-memory InfoNCE exchange unavailable ({type(exc).__name__}: {exc}); using NCCL collectives',
+                  file=sys.stderr)
+            _peer_broken.append(True)
+            return None
+        _peer_cache[key] = px
+    return px
+
+
 class DistInfoNCEFn(torch.autograd.Function):
     """global-batch supervised InfoNCE (training.py:433-472) with rank-local anchors."""
 
@@ -45,18 +118,28 @@ class DistInfoNCEFn(torch.autograd.Function):
         w, r = world(), rank()
         Ba, E = emb.shape
         dev = emb.device
-        # ONE all-gather: the int32 labels ride along as an extra (bit-cast) column of the embedding block
-        packed = torch.empty((Ba, E + 1), device=dev, dtype=torch.float32)
-        packed[:, :E] = emb
-        packed[:, E] = labels.to(torch.int32).contiguous().view(torch.float32)
-        packed_all = torch.empty((w * Ba, E + 1), device=dev, dtype=torch.float32)
-        dist.all_gather_into_tensor(packed_all, packed)
-        emb_all = packed_all[:, :E].contiguous()
-        lab_all = packed_all[:, E].contiguous().view(torch.int32)
         Bk, row0 = w * Ba, r * Ba
-        ehat = torch.empty_like(emb_all)
-        inv_norm = torch.empty(Bk, device=dev, dtype=torch.float32)
-        K.call('xnrs_infonce_normalize', emb_all, Bk, E, ehat, inv_norm)
+        # (a buffer is reused by the next step: what keeps a fast rank from overwriting it early is the gradient all-reduce that
+        # follows every backward, so forward-only evaluations of the loss take the NCCL path)
+        px = peer_exchange(Ba, E, dev) if ctx.needs_input_grad[0] else None
+        ctx.px = px
+        if px is not None:
+            # normalise this rank's rows and store them (+ 1/norm, labels) into every rank's gathered arrays over NVLink
+            K.call('xnrs_peer_normalize_allgather', emb, labels.to(torch.int32).contiguous(), Ba, E, r, w, px.ptrs,
+                   px.off_flags_ag, px.off_ehat, px.off_inv, px.off_lab, px.ctl)
+            ehat, inv_norm, lab_all = px.ehat_all, px.inv_all, px.lab_all
+        else:
+            # ONE all-gather: the int32 labels ride along as an extra (bit-cast) column of the embedding block
+            packed = torch.empty((Ba, E + 1), device=dev, dtype=torch.float32)
+            packed[:, :E] = emb
+            packed[:, E] = labels.to(torch.int32).contiguous().view(torch.float32)
+            packed_all = torch.empty((w * Ba, E + 1), device=dev, dtype=torch.float32)
+            dist.all_gather_into_tensor(packed_all, packed)
+            emb_all = packed_all[:, :E].contiguous()
+            lab_all = packed_all[:, E].contiguous().view(torch.int32)
+            ehat = torch.empty_like(emb_all)
+            inv_norm = torch.empty(Bk, device=dev, dtype=torch.float32)
+            K.call('xnrs_infonce_normalize', emb_all, Bk, E, ehat, inv_norm)
         ehat_a = ehat[row0:row0 + Ba]
         sim = K.gemm(ehat_a, ehat, trans_b=True)
         work = torch.zeros(4, device=dev, dtype=torch.float32)
@@ -79,6 +162,16 @@ class DistInfoNCEFn(torch.autograd.Function):
         ehat, inv_norm, G, stats = ctx.saved_tensors
         Ba, Bk, E, row0, w = ctx.dims
         ehat_a = ehat[row0:row0 + Ba]
+        px = ctx.px
+        if px is not None:
+            # the gradient w.r.t. all Bk normalised rows goes into this rank's symmetric buffer; every rank then pulls and
+            # sums the W partial blocks of ITS rows and applies the normalisation backward in the same kernel
+            K.gemm(G, ehat_a, trans_a=True, out=px.d_ehat)
+            K.gemm(G, ehat, out=px.d_ehat[row0:row0 + Ba], accumulate=True)
+            d_emb = torch.empty((Ba, E), device=ehat.device, dtype=torch.float32)
+            K.call('xnrs_peer_reduce_scatter_normalize_bwd', px.ptrs, px.off_flags_rs, px.off_dehat, Ba, E, rank(), w,
+                   ehat_a, inv_norm[row0:row0 + Ba], stats, float(w), K._f32(g).reshape(1), d_emb, px.ctl)
+            return d_emb, None, None, None
         d_ehat = K.gemm(G, ehat_a, trans_a=True)                              # key side, all Bk rows
         K.gemm(G, ehat, out=d_ehat[row0:row0 + Ba], accumulate=True)          # anchor side, local rows
         # every rank only needs the summed gradient of ITS rows: reduce-scatter (half the bytes of an all-reduce)
@@ -111,6 +204,17 @@ class DataParallelTrainer:
                 self.cl_aux = aux
                 trainer._compute_contrastive_loss = (
                     lambda e, l: DistInfoNCEFn.apply(K._f32(e.reshape(e.shape[0], -1)), l, temp, aux))
+
+    @property
+    def infonce_exchange(self) -> str:
+        """which path the InfoNCE exchange steps of the steps run so far took"""
+        if self.world == 1 or not hasattr(self.trainer, '_compute_contrastive_loss'):
+            return 'none'
+        return 'peer memory (NVLink P2P kernels, csrc/peer.cu)' if _peer_cache else 'nccl'
+
+    def check_peers(self) -> None:
+        for px in _peer_cache.values():
+            px.check()
 
     # tables with at least this many rows exchange their gradient as (ids, rows): LSTUR / NPA user tables (703 790 rows)
     SPARSE_MIN_ROWS = 100_000

@@ -189,30 +189,41 @@ __global__ void infonce_rows_kernel(float *__restrict__ sim, const int *__restri
 
 // count[0] = number of rows i of the whole (gathered) batch that have another row with the same label: the InfoNCE
 // normaliser of the GLOBAL batch.  It depends on the labels only, and every rank holds all Bk labels after the all-gather, so
-// data-parallel ranks compute it locally instead of all-reducing their local counts.  work: 2 zeroed words (partial sum,
-// ticket); the last CTA to finish publishes the total (integers < 2^24: exact and order independent in fp32).
+// data-parallel ranks compute it locally instead of all-reducing their local counts.  O(Bk^2) compares spread over Bk / 32
+// CTAs: lane = anchor (32 per CTA), each of the 8 warps scans one eighth of the labels through its own shared-memory tile.
+// work: 2 zeroed words (partial sum, ticket); the last CTA to finish publishes the total (integers < 2^24: exact and order
+// independent in fp32).
 __global__ void __launch_bounds__(256)
 infonce_count_kernel(const int *__restrict__ labels, long long Bk, float *__restrict__ work, float *__restrict__ count) {
-    __shared__ int tile[1024];
-    __shared__ float red[32];
-    const long long i = blockIdx.x * 256LL + threadIdx.x;
+    __shared__ int tile[8][256];
+    __shared__ int has_s[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long i = blockIdx.x * 32LL + lane;
     const int lab = i < Bk ? labels[i] : 0;
+    const long long per = (Bk + 7) / 8, j0 = warp * per, j1 = min(Bk, j0 + per);
     bool has = false;
-    for (long long base = 0; base < Bk; base += 1024) {
-        const int n = (int)min(1024LL, Bk - base);
-        __syncthreads();
-        for (int t = threadIdx.x; t < n; t += 256) tile[t] = labels[base + t];
-        __syncthreads();
-        for (int j = 0; j < n; ++j) has |= (tile[j] == lab) & (base + j != i);
+    for (long long base = j0; base < j1; base += 256) {
+        const int n = (int)min(256LL, j1 - base);
+        __syncwarp();
+        for (int t = lane; t < n; t += 32) tile[warp][t] = labels[base + t];
+        __syncwarp();
+        for (int j = 0; j < n; ++j) has |= (tile[warp][j] == lab) & (base + j != i);
     }
-    const float c = block_sum(i < Bk && has ? 1.f : 0.f, red);
-    if (threadIdx.x == 0) {
-        atomicAdd(work, c);
-        __threadfence();
-        const unsigned ticket = atomicAdd(reinterpret_cast<unsigned *>(work + 1), 1u);
-        if (ticket == gridDim.x - 1) {
+    has_s[warp][lane] = has;
+    __syncthreads();
+    if (warp == 0) {
+        int any = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) any |= has_s[w][lane];
+        const unsigned m = __ballot_sync(0xffffffffu, any && i < Bk);
+        if (lane == 0) {
+            atomicAdd(work, (float)__popc(m));
             __threadfence();
-            count[0] = atomicAdd(work, 0.f);
+            const unsigned ticket = atomicAdd(reinterpret_cast<unsigned *>(work + 1), 1u);
+            if (ticket == gridDim.x - 1) {
+                __threadfence();
+                count[0] = atomicAdd(work, 0.f);
+            }
         }
     }
 }
@@ -310,7 +321,7 @@ extern "C" int xnrs_infonce_rows(float *sim, const int *labels, long long Ba, lo
 extern "C" int xnrs_infonce_count(const int *labels, long long Bk, float *work, float *count, xnrs_stream_t st) {
     XNRS_REQUIRE(Bk >= 0 && Bk < (1LL << 24), "bad sizes");
     XNRS_REQUIRE(work && count && (Bk == 0 || labels), "null pointer");
-    infonce_count_kernel<<<(unsigned)max(1LL, cdiv(Bk, 256)), 256, 0, STREAM(st)>>>(labels, Bk, work, count);
+    infonce_count_kernel<<<(unsigned)max(1LL, cdiv(Bk, 32)), 256, 0, STREAM(st)>>>(labels, Bk, work, count);
     XNRS_LAUNCHED();
     return XNRS_OK;
 }

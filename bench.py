@@ -547,8 +547,9 @@ def train_workload(ctx, args, model_key, want_cpu=True, want_eager=False):
             cls = 'titlepool_bf16' if bf else 'titlepool_fp32'
             tr = traffic_entry(cls)
             roofline['fused_title_pool'] = {
-                'kernel': 'gemm_tc2_kernel<POOL> (cta_group::2 pair tile, cp.async table gather, pooling epilogue on TMEM; '
-                          + ('bf16 storage, kind::f16)' if bf else 'fp32 storage, 3xTF32)') + ' + titlepool_finalize_kernel',
+                'kernel': 'gemm_tc2_kernel<POOL> (cta_group::2 pair tile, cp.async table gather, pooling epilogue on TMEM, hid through '
+                          'TMA stores; ' + ('bf16 storage, kind::f16)' if bf else 'fp32 storage, 3xTF32)')
+                          + ' + titlepool_wsum_kernel (per-title weighted sums); the whole entry point is timed',
                 'launches_timed': len(tp), 'avg_launch_ms': ms_tp / len(tp), 'rows_per_launch': rows_tp / len(tp),
                 'achieved': flop_tp / (ms_tp * 1e-3) / 1e12, 'unit': 'TFLOP/s', 'peak': pk_['bf16_tflops_sustained'],
                 'frac': flop_tp / (ms_tp * 1e-3) / 1e12 / pk_['bf16_tflops_sustained'],

@@ -1,7 +1,8 @@
 """Small driver for ncu captures of the token-level kernels of the CL step at bench shapes (T ~ 153.6k real tokens, 8.7k titles):
 the fused title-pooling forward (gather -> fc1 -> tanh -> logit -> exp -> per-title sums), the fc1 weight gradient with the
-fused table gather, and their dense counterparts.  Three launches each, in that order.
-    ncu --set full --clock-control none --import-source on -k regex:gemm_tc2 -o gpurun_out/prof python tools/prof_titlepool.py"""
+fused table gather, their dense counterparts, the title-level pooling backward and two title-level GEMMs.  Three launches
+each, in that order.
+    ncu --set full --clock-control none --import-source on -k regex:'gemm_tc|pool_bwd' -o gpurun_out/prof python tools/prof_titlepool.py"""
 import os
 import sys
 
@@ -46,6 +47,19 @@ def main():
         K.gemm(x, w1, trans_b=True, bias=b1, act=K.ACT_TANH, out=hid)
     for _ in range(3):
         K.gemm(store.token_table, w1, trans_b=True, bias=b1, act=K.ACT_TANH, out=hid, a_rows=plan.rows)
+    # pooling backward at title level (pool_bwd2_kernel) and one title-level GEMM (TMA-store epilogue, split-K reductions)
+    d_pooled = torch.randn(R, 768, device=dev)
+    d_hid = torch.empty(T, 256, device=dev)
+    d_w2, d_b2, d_b1 = torch.zeros(256, device=dev), torch.zeros(1, device=dev), torch.zeros(256, device=dev)
+    for _ in range(3):
+        K.call('xnrs_addpool_bwd', K._mat(store.token_table), plan.rows, None, hid, w2, attn, d_pooled, None, plan.seg, R, 30, 768, 256, T,
+               d_hid, d_w2, d_b2, None, d_b1)
+    a_small, w_small, o_small = torch.randn(R, 256, device=dev), torch.randn(256, 256, device=dev), torch.empty(R, 256, device=dev)
+    for _ in range(3):
+        K.gemm(a_small, w_small, trans_b=True, bias=b1, out=o_small)
+    g_small = torch.zeros(256, 256, device=dev)
+    for _ in range(3):
+        K.gemm(o_small, a_small, trans_a=True, out=g_small, accumulate=True)
     torch.cuda.synchronize()
     print('done')
 

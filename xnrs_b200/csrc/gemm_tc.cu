@@ -1612,11 +1612,12 @@ static int titlepool_fwd_impl(const void *x, long long ldx, const int *x_rows, c
     }
     // where the per-title weighted sums are formed.  In the GEMM epilogue (x rows re-read from L2 while the next tile's MMAs
     // run): fewer HBM bytes, but the epilogue warps then sit on L2 latency; or by titlepool_wsum_kernel afterwards (a warp per
-    // title, rows re-read from HBM / L2 at stream speed).  Measured: the split wins whenever the GEMM itself is short
-    // (bf16 storage); XNRS_TITLEPOOL_SPLIT = 0 / 1 forces either.
+    // title, rows re-read from HBM / L2 at stream speed).  Measured at the bench shapes: bf16 storage 0.41 (fused) vs 0.24 ms
+    // (split); fp32 storage / 3xTF32 0.496 vs 0.477 ms since hid leaves through TMA stores (before: fused 0.51, split 0.55).
+    // The split is the default wherever it applies; XNRS_TITLEPOOL_SPLIT = 0 / 1 forces either.
     static int split_opt = -2;
     if (split_opt == -2) { const char *ev = getenv("XNRS_TITLEPOOL_SPLIT"); split_opt = ev ? atoi(ev) : -1; }
-    const bool split = seg && F <= 768 && (split_opt == 1 || (split_opt == -1 && elt == 2));
+    const bool split = seg && F <= 768 && split_opt != 0;
     const long long pairs = std::min<long long>(p.tiles_m, num_sms() / 2);
     if (split) {
         p.pool.pooled = nullptr;

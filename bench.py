@@ -582,17 +582,33 @@ def train_workload(ctx, args, model_key, want_cpu=True, want_eager=False):
 
     last = [0.0]
 
+    # every step's loss is copied to pinned host memory (asynchronously, right behind the step) and READ by the host one step
+    # later, i.e. after the next step has been queued: a training loop that logs the loss with one step of lag keeps the GPU
+    # queue non-empty.  --e2e-sync-read reads each loss before the next step is queued (the GPU then idles for the host's
+    # wake-up + launch time every step).
+    loss_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ev = [torch.cuda.Event() for _ in range(2)]
+
     def region_e2e():
         cur = h2d(0)
         t0 = time.perf_counter()
         for i in range(steps):
             nxt = h2d(i + 1)                 # tiny copy, queued BEFORE this step so the side stream can plan it meanwhile
             out = run_step(cur[0])
+            if args.e2e_sync_read:
+                last[0] = float(out['loss'])     # device -> host read of the step's loss (4 bytes, synchronises)
+            else:
+                loss_host[i & 1].copy_(out['loss'].reshape(1), non_blocking=True)      # device -> host, 4 bytes, every step
+                loss_ev[i & 1].record()
             if not args.no_prefetch:
                 dp.prefetch(nxt[0], after=nxt[1])
-            last[0] = float(out['loss'])     # device -> host read of the step's loss (4 bytes, synchronises)
+            if not args.e2e_sync_read and i > 0:
+                loss_ev[(i - 1) & 1].synchronize()
+                last[0] = float(loss_host[(i - 1) & 1])
             cur = nxt
         torch.cuda.synchronize()
+        if not args.e2e_sync_read:
+            last[0] = float(loss_host[(steps - 1) & 1])
         return (time.perf_counter() - t0) * 1e3
 
     region_e2e()
@@ -614,7 +630,9 @@ def train_workload(ctx, args, model_key, want_cpu=True, want_eager=False):
                    'timing': f'median of {sp["regions"]} regions of exactly {steps} steps ({sp["timed_s"]} s measured)'},
         'spread': sp,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4,
-                'spread': e_sp, 'note': 'host input = int32 news ids / targets / labels (the index fast path of the drop-in API)'},
+                'spread': e_sp, 'loss_readback': 'synchronous, before the next step is queued' if args.e2e_sync_read else
+                'every step: async copy to pinned memory, read by the host after the NEXT step is queued (one step of lag)',
+                'note': 'host input = int32 news ids / targets / labels (the index fast path of the drop-in API)'},
         'gpu_launches': launches, 'roofline': roofline, 'clocks': clocks.summary(),
     }
     del dp, trainer, model, resident, store, astore, stepper, run_step
@@ -823,6 +841,8 @@ def main():
                     help='run ONE workload instead of the headline + sub lines')
     ap.add_argument('--workload', default=None, choices=['train', 'eval'], help='(round-1 spelling) eval == --only eval')
     ap.add_argument('--model', default=None, choices=list(MODEL_CFGS), help='(round-1 spelling) == --only MODEL')
+    ap.add_argument('--e2e-sync-read', action='store_true',
+                    help='e2e: read each step\'s loss synchronously before queueing the next step (default: one step of lag)')
     ap.add_argument('--no-skip-padding', action='store_true', help='run pad tokens through the encoder like the reference does')
     ap.add_argument('--no-prefetch', action='store_true', help='compute the id plumbing of each batch inside its own step')
     ap.add_argument('--no-graph', action='store_true', help='launch the CL step kernel by kernel instead of replaying its CUDA graph')

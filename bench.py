@@ -436,6 +436,7 @@ def gemm_rooflines(records, steps, precision):
         'peak_source': f'{pk_kind} (MEASURED_PEAKS.json, sustained bf16 GEMM; kernel timed inside a long step). '
                        + {'tf32x3': 'The kernel issues 3 TF32 MMAs per product (fp32-accurate 3xTF32): its own ceiling is 1/6 of this bf16 peak',
                           'tf32': 'TF32 operands: ceiling 1/2 of this bf16 peak', 'bf16': 'bf16 operands',
+                          'bf16x3': 'fp32-accurate 3xBF16 on the token-level launches (ceiling 1/3 of this bf16 peak), 3xTF32 elsewhere',
                           'fp32': 'exact-fp32 SIMT kernel (no tensor cores)'}[precision],
         'launches_timed': d_n, 'avg_launch_ms': d_ms / max(d_n, 1),
         'all_gemm_tflops': gemm_flop / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None,
@@ -528,18 +529,19 @@ def train_workload(ctx, args, model_key, want_cpu=True, want_eager=False):
         roofline['simt_fallback_gemms_per_region'] = fallbacks
         # the fused title-pooling forward (gather -> fc1 -> tanh -> logit -> exp -> per-title sums: ONE tcgen05 launch + a small
         # normalisation pass) is its own entry point: FLOPs = 2 * rows * A * F of the fc1 product inside it
-        gb = [r for r in log.records if r.name == 'xnrs_gemm_bf16']
-        if gb:      # bf16 storage mode: the token-level weight gradient runs in xnrs_gemm_bf16 (args: transA, transB, M, N, K, ...)
+        gb = [r for r in log.records if r.name in ('xnrs_gemm_bf16', 'xnrs_gemm_bf16x3')]
+        if gb:      # bf16 storage / 3xBF16 modes: the token-level weight gradient runs in xnrs_gemm_bf16(x3) (args: transA, transB, M, N, K, ...)
             ms_gb = sum(r.start.elapsed_time(r.end) for r in gb)
             flop_gb = sum(2.0 * r.args[2] * r.args[3] * r.args[4] for r in gb)
             pk_, _ = peaks()
             roofline['bf16_weight_gradient'] = {
-                'kernel': 'gemm_tc2_kernel (cta_group::2 pair tile, BF16 kind::f16, cp.async B gather): dW1 = d_hid^T x',
+                'kernel': 'gemm_tc2_kernel (cta_group::2 pair tile, ' + ('3xBF16 on pre-split planes' if gb[0].name.endswith('x3') else 'BF16')
+                          + ' kind::f16, cp.async B gather): dW1 = d_hid^T x',
                 'launches_timed': len(gb), 'avg_launch_ms': ms_gb / len(gb), 'achieved': flop_gb / (ms_gb * 1e-3) / 1e12,
                 'unit': 'TFLOP/s', 'peak': pk_['bf16_tflops_sustained'], 'frac': flop_gb / (ms_gb * 1e-3) / 1e12 / pk_['bf16_tflops_sustained']}
         tp = [r for r in log.records if r.name.startswith('xnrs_titlepool_fwd')]
         if tp:
-            bf = tp[0].name.endswith('bf16')
+            bf, x3 = tp[0].name.endswith('bf16'), tp[0].name.endswith('bf16x3')
             ms_tp = sum(r.start.elapsed_time(r.end) for r in tp)
             rows_tp = sum(r.args[1] for r in tp)
             flop_tp = sum(2.0 * r.args[1] * r.args[3] * r.args[4] for r in tp)
@@ -548,7 +550,7 @@ def train_workload(ctx, args, model_key, want_cpu=True, want_eager=False):
             tr = traffic_entry(cls)
             roofline['fused_title_pool'] = {
                 'kernel': 'gemm_tc2_kernel<POOL> (cta_group::2 pair tile, cp.async table gather, pooling epilogue on TMEM, hid through '
-                          'TMA stores; ' + ('bf16 storage, kind::f16)' if bf else 'fp32 storage, 3xTF32)')
+                          'TMA stores; ' + ('bf16 storage, kind::f16)' if bf else ('3xBF16 on pre-split planes, kind::f16)' if x3 else 'fp32 storage, 3xTF32)'))
                           + ' + titlepool_wsum_kernel (per-title weighted sums); the whole entry point is timed',
                 'launches_timed': len(tp), 'avg_launch_ms': ms_tp / len(tp), 'rows_per_launch': rows_tp / len(tp),
                 'achieved': flop_tp / (ms_tp * 1e-3) / 1e12, 'unit': 'TFLOP/s', 'peak': pk_['bf16_tflops_sustained'],
@@ -556,7 +558,7 @@ def train_workload(ctx, args, model_key, want_cpu=True, want_eager=False):
                 'traffic': tr['dram_bytes_per_row'] * rows_tp / len(tp) if tr else None,
                 'algorithmic_bytes': tr['algorithmic_bytes_per_row'] * rows_tp / len(tp) if tr else None,
                 'traffic_source': f"{os.path.relpath(TRAFFIC_FILE, ROOT)}:{cls}" if tr else 'no ncu capture of this kernel class'}
-        if args.precision == 'bf16' and (tp or gb):
+        if args.precision in ('bf16', 'bf16x3') and (tp or gb):
             # bf16 storage mode: the step's dominant kernels are the two bf16 tensor-core launches above (the xnrs_gemm classes
             # left on fp32 operands are the small title-level GEMMs): the headline roofline fields follow the longer of them
             dom = max((k for k in ('fused_title_pool', 'bf16_weight_gradient') if k in roofline),
@@ -619,7 +621,8 @@ def train_workload(ctx, args, model_key, want_cpu=True, want_eager=False):
     out = {
         'metric': 'train impressions/s', 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': steps, 'warmup': args.warmup,
         'ms_per_step': ms_med / steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': {'fp32': 'f32', 'tf32x3': 'f32 (3xTF32)', 'tf32': 'tf32', 'bf16': 'bf16'}[args.precision],
+        'dtype': {'fp32': 'f32', 'tf32x3': 'f32 (3xTF32)', 'tf32': 'tf32', 'bf16': 'bf16',
+                  'bf16x3': 'f32 (3xBF16 split on the token-level GEMMs, 3xTF32 elsewhere)'}[args.precision],
         'data': 'synthetic',
         'config': {'workload': workload_name(B, model_key), 'global_batch': B * world, 'parallelism': f'dp{world}',
                    'l2': 'inputs larger than L2: 307 MB token table, ~0.5 GB of gathered rows per step, 8 batches cycled',
@@ -734,7 +737,7 @@ def eval_workload(ctx, args, want_cpu=True):
     res = {
         'metric': 'eval scored impressions/s', 'value': n_imp * passes / (ms_med * 1e-3), 'unit': UNIT, 'n_gpus': world,
         'steps': passes, 'warmup': max(1, args.warmup // 3), 'ms_per_step': ms_med / passes, 'higher_is_better': True,
-        'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32 (3xTF32)' if args.precision == 'tf32x3' else args.precision,
+        'scaling': 'strong', 'vs_baseline': None, 'dtype': {'tf32x3': 'f32 (3xTF32)', 'bf16x3': 'f32 (3xBF16 split on the token-level GEMMs, 3xTF32 elsewhere)'}.get(args.precision, args.precision),
         'data': 'synthetic',
         'config': {'workload': f'MIND-large-shaped full-catalogue eval, model=standard (mind_standard.yml): {n_news} news '
                                f'encoded once, {n_imp} impressions x ~37 candidates, H={HIST_LEN}, S={SEQ_LEN}; one step = '
@@ -835,7 +838,7 @@ def main():
     ap.add_argument('--batch', type=int, default=1024, help='impressions per GPU per step')
     ap.add_argument('--ref-batch', type=int, default=64, help='impressions per CPU step (reference arm / cpu_baseline)')
     ap.add_argument('--ref-eval-sample', type=int, default=400, help='impressions of the eval workload timed on the CPU')
-    ap.add_argument('--precision', default='tf32x3', choices=['fp32', 'tf32x3', 'tf32', 'bf16'])
+    ap.add_argument('--precision', default='tf32x3', choices=['fp32', 'tf32x3', 'tf32', 'bf16', 'bf16x3'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--only', default=None, choices=list(MODEL_CFGS) + ['eval'],
                     help='run ONE workload instead of the headline + sub lines')

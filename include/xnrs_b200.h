@@ -138,6 +138,26 @@ int xnrs_titlepool_fwd(const float *x, long long ldx, const int *x_rows, const i
  * (accumulate / split-K allowed) or bf16 (c_bf16 = 1).  Returns XNRS_ERR_UNSUPPORTED off sm_100 or for unaligned operands.
  * xnrs_titlepool_fwd_bf16 / xnrs_addpool_bwd_bf16: the fused forward and the pooling backward on bf16 x / w1 / hid / d_hid. */
 int xnrs_cast_bf16(long long n, const float *src, void *dst, xnrs_stream_t st);
+
+/* ---- fp32-accurate arithmetic on the bf16 tensor-core path: 3xBF16 over PRE-SPLIT operands.
+ * x ~ hi + lo with hi = bf16(x), lo = bf16(x - hi) (16 mantissa bits, relative error <= 2^-17); a product x y is evaluated as
+ * hi hi + (lo hi + hi lo) by three kind::f16 MMAs with fp32 accumulation (the two small terms in their own TMEM accumulator,
+ * added once in the epilogue) — the bf16 analogue of 3xTF32 (measured error ~1e-6 of the result scale, inside the 1e-4 bar),
+ * at twice the MMA rate and half the shared-memory bytes per k, and with NO in-kernel split pass: the planes of the frozen
+ * token table are made once (xnrs_split_bf16), fc1.weight is split once per step, and the pooling backward writes d_hid
+ * directly as two planes (xnrs_addpool_bwd_split).  Same layouts / gathers / epilogues as xnrs_gemm_bf16; C and hid are fp32.
+ * xnrs_titlepool_fwd_bf16x3: xnrs_titlepool_fwd on planes; x_f32 (ld_f32 floats per row) = the fp32 rows for the weighted sum. */
+int xnrs_split_bf16(long long n, const float *src, void *hi, void *lo, xnrs_stream_t st);
+int xnrs_gemm_bf16x3(int transA, int transB, long long M, long long N, long long K, const void *A_hi, const void *A_lo,
+                     long long lda, const int *a_rows, const void *B_hi, const void *B_lo, long long ldb, const int *b_rows,
+                     float *C, long long ldc, const float *bias, int act, int accumulate, int split_k, xnrs_stream_t st);
+int xnrs_titlepool_fwd_bf16x3(const void *x_hi, const void *x_lo, long long ldx, const int *x_rows, const int *tix, const int *seg,
+                              long long n_rows, long long R, int F, int A, const void *w1_hi, const void *w1_lo, const float *b1,
+                              const float *w2, const float *b2, const float *x_f32, long long ld_f32, float *hid, float *e,
+                              float *zsum, float *attn, float *pooled, xnrs_stream_t st);
+int xnrs_addpool_bwd_split(const float *x, const int *x_rows, const float *hid, const float *w2, const float *attn,
+                           const float *d_pooled, const int *seg, long long R, int L, int F, int A, long long n_rows,
+                           void *d_hid_hi, void *d_hid_lo, float *d_w2, float *d_b2, float *d_b1, xnrs_stream_t st);
 int xnrs_gemm_bf16(int transA, int transB, long long M, long long N, long long K, const void *A, long long lda,
                    const int *a_rows, const void *B, long long ldb, const int *b_rows, void *C, long long ldc, int c_bf16,
                    const float *bias, int act, int accumulate, int split_k, xnrs_stream_t st);

@@ -196,6 +196,48 @@ def _xnrs_gemm_bf16(ta, tb, M, N, K_, A, lda, a_rows, B, ldb, b_rows, C, ldc, c_
     C.copy_((C.float() + y if accumulate else y).to(C.dtype))
 
 
+def _xnrs_split_bf16(n, src, hi, lo):
+    h = src.to(torch.bfloat16)
+    hi.copy_(h)
+    lo.copy_((src - h.float()).to(torch.bfloat16))
+
+
+def _xnrs_gemm_bf16x3(ta, tb, M, N, K_, A_hi, A_lo, lda, a_rows, B_hi, B_lo, ldb, b_rows, C, ldc, bias, act, accumulate, split_k):
+    ah, al, bh, bl = (_rows(t, r).float() for t, r in ((A_hi, a_rows), (A_lo, a_rows), (B_hi, b_rows), (B_lo, b_rows)))
+    op = (lambda m: m.T) if ta else (lambda m: m)
+    oq = (lambda m: m.T) if tb else (lambda m: m)
+    y = op(ah) @ oq(bh) + (op(al) @ oq(bh) + op(ah) @ oq(bl))          # hi hi + (lo hi + hi lo): the lo lo term is dropped
+    if bias is not None:
+        y = y + bias
+    y = torch.relu(y) if act == K.ACT_RELU else (torch.tanh(y) if act == K.ACT_TANH else y)
+    C.copy_(C + y if accumulate else y)
+
+
+def _xnrs_titlepool_fwd_bf16x3(x_hi, x_lo, ldx, x_rows, tix, seg, n_rows, R, F_, A, w1_hi, w1_lo, b1, w2, b2, x_f32, ld_f32, hid, e,
+                               zsum, attn, pooled):
+    xr = _rows(x_f32, x_rows)[:n_rows]
+    xh, xl = _rows(x_hi, x_rows)[:n_rows].float(), _rows(x_lo, x_rows)[:n_rows].float()
+    wh, wl = w1_hi.float(), w1_lo.float()
+    h = torch.tanh(xh @ wh.T + (xl @ wh.T + xh @ wl.T) + b1)
+    hid.copy_(h)
+    valid = tix[:n_rows] >= 0
+    ev = torch.where(valid, torch.exp(h @ w2.reshape(-1) + b2), torch.zeros(n_rows))
+    e.copy_(ev)
+    t = tix[:n_rows].clamp_min(0).long()
+    zsum.zero_()
+    zsum.index_add_(0, t, ev)
+    pooled.zero_()
+    pooled.index_add_(0, t, ev[:, None] * xr)
+    attn.copy_(torch.where(valid, ev / (zsum[t] + 1e-8), torch.zeros(n_rows)))
+    pooled.div_((zsum + 1e-8)[:, None])
+
+
+def _xnrs_addpool_bwd_split(x, x_rows, hid, w2, attn, d_pooled, seg, R, L, F_, A, n_rows, d_hid_hi, d_hid_lo, d_w2, d_b2, d_b1):
+    d32 = torch.empty(hid.shape, dtype=torch.float32)
+    _xnrs_addpool_bwd(x, x_rows, None, hid, w2, attn, d_pooled, None, seg, R, L, F_, A, n_rows, d32, d_w2, d_b2, None, d_b1)
+    _xnrs_split_bf16(d32.numel(), d32, d_hid_hi, d_hid_lo)
+
+
 def _xnrs_titlepool_fwd_bf16(x, ldx, x_rows, tix, seg, n_rows, R, F_, A, w1, b1, w2, b2, hid, e, zsum, attn, pooled):
     h32 = torch.empty(hid.shape, dtype=torch.float32)
     _xnrs_titlepool_fwd(x.float(), ldx, x_rows, tix, seg, n_rows, R, F_, A, w1.float(), b1, w2, b2, 3, h32, e, zsum, attn, pooled)

@@ -587,6 +587,46 @@ def test_bf16_tensor_core_gemm_fused_gather():
         assert_close(got_dw, want_dw.float(), 5e-5, 'bf16 gathered weight gradient')
 
 
+@pytest.mark.parametrize('ta,tb', [(0, 1), (1, 0), (0, 0), (1, 1)])
+def test_bf16x3_tensor_core_gemm(ta, tb):
+    """xnrs_gemm_bf16x3: fp32 operands pre-split into two bf16 planes (x ~ hi + lo), three kind::f16 MMAs per k-step — the result
+    must be fp32-accurate (1e-4 class; measured ~1e-6) against float64 on the ORIGINAL fp32 operands"""
+    for M, N, K_ in [(1000, 200, 1344), (4104, 768, 768), (256, 768, 9000)]:
+        a = torch.randn((K_, M) if ta else (M, K_), generator=g(1)) / math.sqrt(K_)
+        b = torch.randn((N, K_) if tb else (K_, N), generator=g(2))
+        bias = torch.randn(N, generator=g(3))
+        want = (a.double().T if ta else a.double()) @ (b.double().T if tb else b.double())
+        ah, al = K.split_bf16(cu(a))
+        bh, bl = K.split_bf16(cu(b))
+        assert float((ah.float() + al.float() - cu(a)).abs().max()) <= 2 ** -16 * float(a.abs().max())
+        got = K.gemm_bf16x3(ah, al, bh, bl, trans_a=bool(ta), trans_b=bool(tb))
+        assert_close(got, want.float(), 2e-5, f'bf16x3 gemm {M}x{N}x{K_}')
+        got = K.gemm_bf16x3(ah, al, bh, bl, trans_a=bool(ta), trans_b=bool(tb), bias=cu(bias), act=K.ACT_TANH)
+        assert_close(got, torch.tanh(want + bias.double()).float(), 5e-5, 'bf16x3 gemm bias + tanh')
+        out = cu(torch.ones(M, N))
+        K.gemm_bf16x3(ah, al, bh, bl, trans_a=bool(ta), trans_b=bool(tb), out=out, accumulate=True, split_k=3)
+        assert_close(out, (want + 1).float(), 2e-5, 'bf16x3 gemm split-K accumulate')
+
+
+def test_bf16x3_tensor_core_gemm_fused_gather():
+    """the two planes of a table gathered by the cp.async warps: forward (rows of A) and weight-gradient (rows of B along K)"""
+    V, D, A_ = 5000, 768, 256
+    table = torch.randn(V, D, generator=g(1)) / math.sqrt(D)
+    th, tl = K.split_bf16(cu(table))
+    for R in (1650, 41000):
+        rows = torch.randint(0, V, (R,), generator=g(2)).int()
+        w = torch.randn(A_, D, generator=g(3))
+        wh, wl = K.split_bf16(cu(w))
+        want = table[rows.long()].double() @ w.double().T
+        got = K.gemm_bf16x3(th, tl, wh, wl, trans_b=True, a_rows=cu(rows))
+        assert_close(got, want.float(), 2e-5, 'bf16x3 gathered forward')
+        d = torch.randn(R, A_, generator=g(5))
+        dh, dl = K.split_bf16(cu(d))
+        want_dw = d.double().T @ table[rows.long()].double()
+        got_dw = K.gemm_bf16x3(dh, dl, th, tl, trans_a=True, b_rows=cu(rows))
+        assert_close(got_dw, want_dw.float(), 3e-5, 'bf16x3 gathered weight gradient')
+
+
 def test_gemm_rejects_the_bf16_precision_on_fp32_operands():
     with K.precision('bf16'):
         assert K._gemm_precision() == K.PRECISIONS['tf32']          # python maps fp32-stored GEMMs of the bf16 mode to TF32

@@ -215,7 +215,7 @@ def _chunked_oracle_step(P, cat, raw, temperature, lam, chunk=64):
     return l_rec + lam * float(l_cl.detach()), l_rec, float(l_cl.detach())
 
 
-@pytest.mark.parametrize('prec,tol', [('tf32x3', 1e-4), ('bf16', 2e-2)])
+@pytest.mark.parametrize('prec,tol', [('tf32x3', 1e-4), ('bf16x3', 1e-4), ('bf16', 2e-2)])
 def test_bench_config_step_matches_oracle(prec, tol, monkeypatch):
     """ONE step of bench.py's headline configuration — B=1024 impressions, S=30, H=50, 65 238-news catalogue, 100k-row token
     table, 3xTF32, title de-duplication + padding-free pooling + prefetched id plumbing + item-logit user pooling — checked

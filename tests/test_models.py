@@ -293,6 +293,40 @@ def test_bf16_storage_title_pool_matches_fp32(where, monkeypatch):
         assert_close(a, b, 2e-2 if not name.startswith('d ') else 5e-2, name, atol=1e-3 if name == 'd fc2.bias' else 1e-6)
 
 
+@pytest.mark.parametrize('where', ['emulated', pytest.param('cuda', marks=pytest.mark.gpu)])
+def test_bf16x3_title_pool_is_fp32_accurate(where, monkeypatch):
+    """precision 'bf16x3': the token-level launches of the title pooler run 3xBF16 on pre-split planes (cached planes of the
+    frozen table, fc1.weight split per step, d_hid written as planes) — pooled vectors, weights and every gradient within the
+    fp32 bar (1e-4 of the tensor scale) of the exact-fp32 path on the same ragged TitlePlan"""
+    from xnrs_b200 import synthetic as syn
+    from xnrs_b200.data import TitleStore, plan_titles
+    device = 'cpu' if where == 'emulated' else 'cuda'
+    if where == 'emulated':
+        monkeypatch.setattr(K, 'call', EMU.call)
+    monkeypatch.setattr(K, 'FUSED_GATHER_MIN_ROWS', 256)
+    D, A = 256, 256
+    cat = syn.make_catalogue(300, 20, vocab=900, dim=D, seed=21)
+    ids = torch.from_numpy(syn.zipf_news(np.random.default_rng(3), 300, 700)).int()
+    ids[::9] = 0
+    store = TitleStore(cat.token_table.to(device) * 0.3, cat.title_tokens.to(device))
+    plan = plan_titles(store, ids.to(device), True, True).acquire()
+    gen = torch.Generator().manual_seed(5)
+    params = [torch.randn(A, D, generator=gen) / D ** 0.5, torch.randn(A, generator=gen) * 0.1,
+              torch.randn(1, A, generator=gen) / A ** 0.5, torch.randn(1, generator=gen) * 0.1]
+    R = plan.uniq.numel()
+    gout = torch.randn(R, D, generator=gen).to(device)
+    outs = []
+    for prec in ('bf16x3', 'fp32'):
+        monkeypatch.setattr(K, '_precision', K.PRECISIONS[prec])
+        leaves = [p.clone().to(device).requires_grad_(True) for p in params]
+        pooled, attn = K.AdditivePoolFn.apply(store.token_table, plan.rows, None, *leaves, R, 20, plan.seg, plan.tix)
+        (pooled * gout).sum().backward()
+        outs.append([pooled.detach(), attn.detach()[:plan.n_rows]] + [t.grad for t in leaves])
+    assert getattr(store.token_table, '_xnrs_bf16x3', None) is not None        # the cached planes of the table were used
+    for name, a, b in zip(('pooled', 'attn', 'd fc1.weight', 'd fc1.bias', 'd fc2.weight', 'd fc2.bias'), *outs):
+        assert_close(a, b, 1e-4, name, atol=1e-4 if name == 'd fc2.bias' else 1e-6)
+
+
 @pytest.mark.parametrize('name', ['cl', 'nrms', 'naml', 'lstur_con', 'npa'])
 def test_index_batches_equal_dense_batches(name, device):
     """the index fast path (device-resident token table + int32 news ids: title de-duplication, padding-free pooling,

@@ -68,11 +68,12 @@ def main():
         us = t0.elapsed_time(t1) * 1e3 / args.reps
         total_us += us
         row = {'call': name, 'us': round(us, 2), 'ints': [x for x in a if isinstance(x, (int, float)) and not isinstance(x, bool)][:8]}
-        if name in ('xnrs_gemm', 'xnrs_gemm_bf16'):
+        if name in ('xnrs_gemm', 'xnrs_gemm_bf16', 'xnrs_gemm_bf16x3'):
             row['kernel'] = _lib.lib().xnrs_last_gemm_kernel().decode()
             flop = 2.0 * a[2] * a[3] * a[4]
             row['tflops'] = round(flop / us / 1e6, 1)
-            row['gather'] = [a[7] is not None, a[10] is not None]
+            ia, ib = (8, 12) if name.endswith('x3') else (7, 10)
+            row['gather'] = [a[ia] is not None, a[ib] is not None]
         rows.append(row)
     for r in rows:
         print(json.dumps(r))

@@ -407,12 +407,14 @@ pool_bwd_warp_kernel(const void *__restrict__ x_, const int *__restrict__ x_rows
 //   * two block barriers per title (da/al -> dot -> dlogit in a third array).
 // Measured at the bench shapes (8.9 k titles, 153.6 k rows): 0.212 -> 0.161 ms (fp32), 0.210 -> 0.129 ms (bf16).  A warp-per-title
 // variant of the same pipeline (no barriers, 16 titles in flight per SM) was slower again (0.193 / 0.238 ms) and is not kept.
-template <bool BF>
+// SPLIT_OUT (fp32 inputs only): d_hid is written as two bf16 planes, d_hid ~ hi + lo (hi = bf16(g), lo = bf16(g - hi)), the form
+// the pre-split 3xBF16 weight-gradient GEMM consumes — same bytes as the fp32 rows, no separate split pass.
+template <bool BF, bool SPLIT_OUT>
 __global__ void __launch_bounds__(POOL_THREADS, 2)
 pool_bwd2_kernel(const void *__restrict__ x_, const int *__restrict__ x_rows, const void *__restrict__ hid_,
                  const float *__restrict__ w2, const float *__restrict__ attn, const float *__restrict__ d_pooled,
                  const int *__restrict__ seg, long long R, int Lmax, int F, long long n_rows, void *__restrict__ d_hid_,
-                 float *__restrict__ d_w2, float *__restrict__ d_b2, float *__restrict__ d_b1) {
+                 void *__restrict__ d_hid_lo_, float *__restrict__ d_w2, float *__restrict__ d_b2, float *__restrict__ d_b1) {
     constexpr int A = 256, ELT = BF ? 2 : 4, EPC = 16 / ELT, NCH = BF ? 3 : 6, TOK = 4;
     constexpr int CG = A / EPC, RL = POOL_THREADS / CG, U = 32 / RL;       // 32 rows of hid in flight per pass
     extern __shared__ __align__(16) float sm[];
@@ -597,6 +599,22 @@ pool_bwd2_kernel(const void *__restrict__ x_, const int *__restrict__ x_rows, co
                         gb[q] += g;
                         out[q] = __float_as_uint(g);
                     }
+                    if (SPLIT_OUT) {
+                        uint32_t hi2[2], lo2[2];
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const float g0 = __uint_as_float(out[2 * q]), g1 = __uint_as_float(out[2 * q + 1]);
+                            const __nv_bfloat16 h0 = __float2bfloat16_rn(g0), h1 = __float2bfloat16_rn(g1);
+                            const __nv_bfloat16 l0 = __float2bfloat16_rn(g0 - __bfloat162float(h0));
+                            const __nv_bfloat16 l1 = __float2bfloat16_rn(g1 - __bfloat162float(h1));
+                            hi2[q] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                            lo2[q] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                        }
+                        const long long off = ((base + l) * A + cg * EPC) * 2;
+                        *reinterpret_cast<uint2 *>(dhb + off) = make_uint2(hi2[0], hi2[1]);
+                        *reinterpret_cast<uint2 *>(reinterpret_cast<char *>(d_hid_lo_) + off) = make_uint2(lo2[0], lo2[1]);
+                        continue;
+                    }
                 }
                 *reinterpret_cast<uint4 *>(dhb + ((base + l) * A + cg * EPC) * ELT) = make_uint4(out[0], out[1], out[2], out[3]);
             }
@@ -616,9 +634,26 @@ pool_bwd2_kernel(const void *__restrict__ x_, const int *__restrict__ x_rows, co
     if (seg && n_rows > 0) {        // rows past the last group (TitlePlan padding): d_hid = 0
         const long long t0 = (long long)seg[R] * A, t1 = n_rows * A;
         for (long long i = t0 + blockIdx.x * (long long)blockDim.x + tid; i < t1; i += (long long)gridDim.x * blockDim.x) {
-            if (BF) reinterpret_cast<__nv_bfloat16 *>(d_hid_)[i] = __float2bfloat16_rn(0.f);
-            else reinterpret_cast<float *>(d_hid_)[i] = 0.f;
+            if (SPLIT_OUT) {
+                reinterpret_cast<__nv_bfloat16 *>(d_hid_)[i] = __float2bfloat16_rn(0.f);
+                reinterpret_cast<__nv_bfloat16 *>(d_hid_lo_)[i] = __float2bfloat16_rn(0.f);
+            } else if (BF) {
+                reinterpret_cast<__nv_bfloat16 *>(d_hid_)[i] = __float2bfloat16_rn(0.f);
+            } else {
+                reinterpret_cast<float *>(d_hid_)[i] = 0.f;
+            }
         }
+    }
+}
+
+// x ~ hi + lo with hi = bf16(x), lo = bf16(x - hi): 16 mantissa bits in two bf16 planes (relative error <= 2^-17)
+__global__ void split_bf16_kernel(long long n, const float *__restrict__ src, __nv_bfloat16 *__restrict__ hi,
+                                  __nv_bfloat16 *__restrict__ lo) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float v = src[i];
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        hi[i] = h;
+        lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
     }
 }
 
@@ -1071,8 +1106,8 @@ extern "C" int xnrs_addpool_bwd(const float *x, const int *x_rows, const float *
         return XNRS_OK;
     }
     if (!d_x && !d_attn && pool_bwd2_ok(L, F, A, x, hid, d_hid, 4)) {
-        pool_bwd2_kernel<false><<<pool_grid2(R), POOL_THREADS, (2 * F + 9 * L + 2 * A) * sizeof(float), STREAM(st)>>>(
-            x, x_rows, hid, w2, attn, d_pooled, seg, R, L, F, n_rows, d_hid, d_w2, d_b2, d_b1);
+        pool_bwd2_kernel<false, false><<<pool_grid2(R), POOL_THREADS, (2 * F + 9 * L + 2 * A) * sizeof(float), STREAM(st)>>>(
+            x, x_rows, hid, w2, attn, d_pooled, seg, R, L, F, n_rows, d_hid, nullptr, d_w2, d_b2, d_b1);
         XNRS_LAUNCHED();
         return XNRS_OK;
     }
@@ -1098,14 +1133,39 @@ extern "C" int xnrs_addpool_bwd_bf16(const void *x, const int *x_rows, const voi
         return XNRS_OK;
     }
     if (pool_bwd2_ok(L, F, A, x, hid, d_hid, 2)) {
-        pool_bwd2_kernel<true><<<pool_grid2(R), POOL_THREADS, (2 * F + 9 * L + 2 * A) * sizeof(float), STREAM(st)>>>(
-            x, x_rows, hid, w2, attn, d_pooled, seg, R, L, F, n_rows, d_hid, d_w2, d_b2, d_b1);
+        pool_bwd2_kernel<true, false><<<pool_grid2(R), POOL_THREADS, (2 * F + 9 * L + 2 * A) * sizeof(float), STREAM(st)>>>(
+            x, x_rows, hid, w2, attn, d_pooled, seg, R, L, F, n_rows, d_hid, nullptr, d_w2, d_b2, d_b1);
         XNRS_LAUNCHED();
         return XNRS_OK;
     }
     pool_bwd_bf16_kernel<<<pool_grid(R), POOL_THREADS, (2 * L + 2 * A) * sizeof(float), STREAM(st)>>>(
         reinterpret_cast<const __nv_bfloat16 *>(x), x_rows, reinterpret_cast<const __nv_bfloat16 *>(hid), w2, attn, d_pooled, seg, R,
         L, F, A, n_rows, reinterpret_cast<__nv_bfloat16 *>(d_hid), d_w2, d_b2, d_b1);
+    XNRS_LAUNCHED();
+    return XNRS_OK;
+}
+
+extern "C" int xnrs_addpool_bwd_split(const float *x, const int *x_rows, const float *hid, const float *w2, const float *attn,
+                                      const float *d_pooled, const int *seg, long long R, int L, int F, int A, long long n_rows,
+                                      void *d_hid_hi, void *d_hid_lo, float *d_w2, float *d_b2, float *d_b1, xnrs_stream_t st) {
+    if (R < 0 || L <= 0 || F <= 0 || A <= 0) return fail(XNRS_ERR_ARG, "%s: bad sizes", "xnrs_addpool_bwd_split");
+    if (R == 0) return XNRS_OK;
+    XNRS_REQUIRE(x && hid && w2 && attn && d_pooled && d_hid_hi && d_hid_lo && d_w2 && d_b2, "null pointer");
+    XNRS_REQUIRE(!((uintptr_t)d_pooled & 15) && !((uintptr_t)d_hid_hi & 7) && !((uintptr_t)d_hid_lo & 7), "alignment");
+    if (!pool_bwd2_ok(L, F, A, x, hid, d_hid_hi, 4))
+        return fail(XNRS_ERR_UNSUPPORTED, "%s: shape not covered (A = 256, F <= 768, L <= 256)", "xnrs_addpool_bwd_split");
+    pool_bwd2_kernel<false, true><<<pool_grid2(R), POOL_THREADS, (2 * F + 9 * L + 2 * A) * sizeof(float), STREAM(st)>>>(
+        x, x_rows, hid, w2, attn, d_pooled, seg, R, L, F, n_rows, d_hid_hi, d_hid_lo, d_w2, d_b2, d_b1);
+    XNRS_LAUNCHED();
+    return XNRS_OK;
+}
+
+extern "C" int xnrs_split_bf16(long long n, const float *src, void *hi, void *lo, xnrs_stream_t st) {
+    if (n <= 0) return XNRS_OK;
+    XNRS_REQUIRE(src && hi && lo, "null pointer");
+    long long b = cdiv(n, 256), cap = 16LL * num_sms();
+    split_bf16_kernel<<<(unsigned)(b > cap ? cap : b), 256, 0, STREAM(st)>>>(n, src, reinterpret_cast<__nv_bfloat16 *>(hi),
+                                                                            reinterpret_cast<__nv_bfloat16 *>(lo));
     XNRS_LAUNCHED();
     return XNRS_OK;
 }

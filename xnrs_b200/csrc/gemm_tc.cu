@@ -65,6 +65,9 @@ struct TcArgs {
     PoolArgs pool;
     int stages;
     long long tiles_m, tiles_n;
+    int planes;             // pair kernel, elt == 2: 2 = both operands arrive PRE-SPLIT as two bf16 planes (x ~ hi + lo, A2 / B2 and
+                            // mapA2 / mapB2 are the lo planes): three kind::f16 MMAs per k-step like 3xTF32, no splitter warps
+    const float *A2, *B2;   // raw lo-plane pointers for the cp.async gather warps
     int c_tma;              // 1-CTA kernel: C leaves through TMA stores / reductions of staged 32 x 32 blocks (mapC is valid)
     long long *trace;       // diagnostics (xnrs_debug_gemm_trace): 8 SM-clock stamps per CTA of the 1-CTA kernel, or NULL
 };
@@ -733,7 +736,8 @@ constexpr int EPI2_WARP0 = 4 + SPLIT_WARPS, EPI2_WARPS = 8;
 template <bool POOL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                const __grid_constant__ CUtensorMap mapC, TcArgs p) {
+                const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapA2,
+                const __grid_constant__ CUtensorMap mapB2, TcArgs p) {
     constexpr int TILE = TBM * TBK * 4, HALF = 2 * TILE;          // per CTA: [A hi][B-half hi] | [A lo][B-half lo]
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -748,6 +752,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB)) : "memory");
     }
     const int stages = p.stages, passes = p.passes;
+    // pre-split bf16 planes: three MMAs per k-step and a hi / lo half per stage like 3xTF32, but the lo half is FILLED by the
+    // producers (TMA from the lo plane, cp.async gather from the lo table) instead of computed by splitter warps
+    const bool planes = p.planes == 2;
+    const bool splitting = passes == 3 && !planes;
     // operand tiles are 128 rows x 128 bytes whatever the element type: a stage spans 32 fp32 / 64 bf16 elements of K; an
     // MN-major tile is made of boxes of (128 bytes of MN) x (kstep k-rows): four of 4 KB (fp32) or two of 8 KB (bf16)
     const int kstep = p.elt == 2 ? 64 : TBK;
@@ -761,8 +769,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
             // TMA thread (+ every lane of the cp.async gather warps: 2 warps in 3xTF32 mode, 8 in the single-pass modes)
-            mbar_init(&full_bar[s], p.lsu_gather ? 1 + 32 * (passes == 3 ? 2 : SPLIT_WARPS) : 1);
-            mbar_init(&ready_bar[s], passes == 3 ? 2 * SPLIT_WARPS : 2);      // used in the leader only: one arrival per
+            mbar_init(&full_bar[s], p.lsu_gather ? 1 + 32 * (splitting ? 2 : SPLIT_WARPS) : 1);
+            mbar_init(&ready_bar[s], splitting ? 2 * SPLIT_WARPS : 2);        // used in the leader only: one arrival per
             mbar_init(&empty_bar[s], 1);                                       // splitter warp (or relay) of BOTH CTAs
         }
         for (int a = 0; a < 2; ++a) {
@@ -798,6 +806,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         StageRing r;
         const int elt = p.elt, epc = 16 / elt;           // elements per 16-byte chunk
         const char *Ab = reinterpret_cast<const char *>(p.A), *Bb = reinterpret_cast<const char *>(p.B);
+        const char *Ab2 = reinterpret_cast<const char *>(p.A2), *Bb2 = reinterpret_cast<const char *>(p.B2);
         for (long long t = pair; t < total; t += npairs) {
             const long long split = t / tiles_mn, mn = t - split * tiles_mn;
             const long long m0 = (mn / p.tiles_n) * 256 + 128 * rank, n0 = (mn % p.tiles_n) * T2N + 128 * rank;
@@ -838,6 +847,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                             const int rr = (lane >> 3) + 4 * (gw + G * i);
                             cp_async16(dst + rr * 128 + ((c ^ (rr & 7)) << 4),
                                        Ab + ((long long)arow[i] * p.lda + (nbytes ? kk : 0)) * elt, nbytes);
+                            if (planes)
+                                cp_async16(dst + HALF + rr * 128 + ((c ^ (rr & 7)) << 4),
+                                           Ab2 + ((long long)arow[i] * p.lda + (nbytes ? kk : 0)) * elt, nbytes);
                         }
                     }
                 } else if (elt == 4) {
@@ -872,6 +884,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                             const int nbytes = row >= 0 ? cbytes : 0;
                             cp_async16(dst + c2 * 8192 + kr * 128 + ((u ^ (kr & 7)) << 4),
                                        Bb + (nbytes ? ((long long)row * p.ldb + col) * 2 : 0), nbytes);
+                            if (planes)
+                                cp_async16(dst + HALF + c2 * 8192 + kr * 128 + ((u ^ (kr & 7)) << 4),
+                                           Bb2 + (nbytes ? ((long long)row * p.ldb + col) * 2 : 0), nbytes);
                         }
                     }
                 }
@@ -882,6 +897,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 if (pfrow >= 0) {           // this CTA's 128 columns of that row: 512 B (fp32) / 256 B (bf16) = 4 / 2 lines
                     const char *a = Bb + ((long long)pfrow * p.ldb + n0) * elt;
                     for (int o = 0; o < 128 * elt; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + o));
+                    if (planes) {
+                        const char *a2 = Bb2 + ((long long)pfrow * p.ldb + n0) * elt;
+                        for (int o = 0; o < 128 * elt; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(a2 + o));
+                    }
                 }
             }
         }
@@ -907,7 +926,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             for (long long k0 = kbeg; k0 < kend; k0 += kstep) {
                 if (lane == 0) {
                     mbar_wait(&empty_bar[r.stage], r.phase ^ 1);
-                    mbar_expect_tx(&full_bar[r.stage], p.lsu_gather ? TILE : HALF);
+                    mbar_expect_tx(&full_bar[r.stage], (p.lsu_gather ? TILE : HALF) * (planes ? 2 : 1));
                 }
                 __syncwarp();
                 if (p.lsu_gather == 1) {
@@ -917,11 +936,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 } else if (lane == 0) {
                     if (!p.a_mn) {
                         tma_load_2d(tileA(r.stage), &mapA, &full_bar[r.stage], (int)k0, m0);
+                        if (planes) tma_load_2d(tileA(r.stage) + HALF, &mapA2, &full_bar[r.stage], (int)k0, m0);
                     } else {
 #pragma unroll
                         for (int c = 0; c < 4; ++c)
-                            if (c < mn_boxes)
+                            if (c < mn_boxes) {
                                 tma_load_2d(tileA(r.stage) + c * mn_box_bytes, &mapA, &full_bar[r.stage], m0 + mn_box_elems * c, (int)k0);
+                                if (planes)
+                                    tma_load_2d(tileA(r.stage) + HALF + c * mn_box_bytes, &mapA2, &full_bar[r.stage], m0 + mn_box_elems * c, (int)k0);
+                            }
                     }
                 }
                 if (p.lsu_gather == 2) {
@@ -938,11 +961,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 } else if (lane == 0) {
                     if (!p.b_mn) {
                         tma_load_2d(tileB(r.stage), &mapB, &full_bar[r.stage], (int)k0, n0);
+                        if (planes) tma_load_2d(tileB(r.stage) + HALF, &mapB2, &full_bar[r.stage], (int)k0, n0);
                     } else {
 #pragma unroll
                         for (int c = 0; c < 4; ++c)
-                            if (c < mn_boxes)
+                            if (c < mn_boxes) {
                                 tma_load_2d(tileB(r.stage) + c * mn_box_bytes, &mapB, &full_bar[r.stage], n0 + mn_box_elems * c, (int)k0);
+                                if (planes)
+                                    tma_load_2d(tileB(r.stage) + HALF + c * mn_box_bytes, &mapB2, &full_bar[r.stage], n0 + mn_box_elems * c, (int)k0);
+                            }
                     }
                 }
                 r.advance(stages);
@@ -982,6 +1009,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                         const uint64_t db = umma_desc(sb + k * b_kadv, b_lbo, b_sbo, b_lay);
                         if (p.elt == 2) {
                             tc2_mma_bf16(d_tmem, da, db, idesc, first ? 0u : 1u);
+                            if (planes) {       // x y ~ hi hi + (lo hi + hi lo): the small terms in their own accumulator
+                                const uint64_t dal = umma_desc(sa + HALF + k * a_kadv, a_lbo, a_sbo, a_lay);
+                                const uint64_t dbl = umma_desc(sb + HALF + k * b_kadv, b_lbo, b_sbo, b_lay);
+                                tc2_mma_bf16(d_corr, dal, db, idesc, first ? 0u : 1u);
+                                tc2_mma_bf16(d_corr, da, dbl, idesc, 1u);
+                            }
                             first = 0;
                             continue;
                         }
@@ -1002,9 +1035,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             }
         }
     } else if (warp == 2) {
-        if (passes == 3 && p.lsu_gather) gather_role(0, 2);
-        // ===================== relay (single-pass mode): "my operands have landed" -> leader =====================
-        if (passes != 3 && lane == 0) {
+        if (splitting && p.lsu_gather) gather_role(0, 2);
+        // ===================== relay (no splitter warps): "my operands have landed" -> leader =====================
+        if (!splitting && lane == 0) {
             const uint32_t ready0 = map_to_cta(smem_u32(&ready_bar[0]), 0);
             StageRing r;
             for (long long t = pair; t < total; t += npairs) {
@@ -1018,11 +1051,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             }
         }
     } else if (warp == 3) {
-        if (passes == 3 && p.lsu_gather) gather_role(1, 2);
+        if (splitting && p.lsu_gather) gather_role(1, 2);
     } else if (warp < EPI2_WARP0) {
-        if (passes != 3 && p.lsu_gather) gather_role(warp - 4, SPLIT_WARPS);      // single pass: nothing to split, these warps gather
+        if (!splitting && p.lsu_gather) gather_role(warp - 4, SPLIT_WARPS);       // nothing to split: these warps gather
         // ===================== splitters (3xTF32): lo = x - trunc_tf32(x) for this CTA's tiles =====================
-        if (passes == 3) {
+        if (splitting) {
             const int tid = threadIdx.x - 128;
             constexpr int ITERS = HALF / 16 / SPLIT_THREADS;
             const uint32_t ready0 = map_to_cta(smem_u32(&ready_bar[0]), 0);
@@ -1418,6 +1451,7 @@ int gemm_tensorcore(const GemmArgs &a, int precision, cudaStream_t st, int *stat
                        : make_map(&mapB, a.B, a.K, a.N, a.ldb, BN, false));
     if (!ok) return 0;
     if (!p.c_tma) mapC = mapA;
+    const CUtensorMap mapA2 = mapA, mapB2 = mapB;      // (lo planes: bf16 pre-split mode only)
 
     if (split > 1 && !a.accumulate) {
         if (cudaMemset2DAsync(a.C, a.ldc * sizeof(float), 0, a.N * sizeof(float), a.M, st) != cudaSuccess) {
@@ -1443,7 +1477,7 @@ int gemm_tensorcore(const GemmArgs &a, int precision, cudaStream_t st, int *stat
         if (lsu < 0) { const char *e = getenv("XNRS_LSU_GATHER"); lsu = e ? atoi(e) : 1; }
         if (lsu) p.lsu_gather = a.a_rows ? 1 : (a.b_rows ? 2 : 0);
         const long long pairs = total < num_sms() / 2 ? total : num_sms() / 2;
-        launch_pdl(gemm_tc2_kernel<false>, dim3((unsigned)(2 * pairs)), dim3(TC2_THREADS), smem_bytes, st, mapA, mapB, mapC, p);
+        launch_pdl(gemm_tc2_kernel<false>, dim3((unsigned)(2 * pairs)), dim3(TC2_THREADS), smem_bytes, st, mapA, mapB, mapC, mapA2, mapB2, p);
         g_last_gemm_kernel = p.passes == 3 ? "gemm_tc2_kernel (cta_group::2, 256x256 pair tile, 3xTF32)"
                                            : "gemm_tc2_kernel (cta_group::2, 256x256 pair tile, TF32)";
     } else if (BN == 256) {
@@ -1561,10 +1595,17 @@ using namespace xnrs;
 // kernel (cp.async gather warp + pooling epilogue), then a small normalisation pass.  Returns XNRS_ERR_UNSUPPORTED (nothing
 // launched) for shapes / devices / precisions the fused kernel does not cover; the caller then runs xnrs_gemm + xnrs_addpool_fwd.
 // shared by the fp32-storage (tf32 / 3xtf32) and the bf16-storage entry points: x / w1 / hid are fp32 (elt 4) or bf16 (elt 2)
+// x_lo / w1_lo (both or neither): the operands arrive pre-split into two bf16 planes (x ~ x + x_lo): elt = 2, three
+// kind::f16 MMAs per k-step, fp32 hid; the per-title weighted sums then read the fp32 rows x_sum (ld_sum floats apart)
 static int titlepool_fwd_impl(const void *x, long long ldx, const int *x_rows, const int *tix, const int *seg, long long n_rows,
                               long long R, int F, int A, const void *w1, const float *b1, const float *w2, const float *b2,
-                              int passes, int elt, void *hid, float *e, float *zsum, float *attn, float *pooled, cudaStream_t st) {
+                              int passes, int elt, void *hid, float *e, float *zsum, float *attn, float *pooled, cudaStream_t st,
+                              const void *x_lo = nullptr, const void *w1_lo = nullptr, const float *x_sum = nullptr,
+                              long long ld_sum = 0) {
+    const bool planes = x_lo != nullptr;
     XNRS_REQUIRE(x && tix && w1 && b1 && w2 && b2 && hid && e && zsum && attn && pooled, "null pointer");
+    XNRS_REQUIRE(!planes || (w1_lo && x_sum && seg && F <= 768 && elt == 2 && passes == 3 && !((uintptr_t)x_lo & 15) &&
+                             !((uintptr_t)w1_lo & 15) && !((uintptr_t)x_sum & 15) && ld_sum % 4 == 0), "pre-split planes");
     XNRS_REQUIRE(n_rows >= 0 && R >= 0 && F > 0 && A > 0, "bad sizes");
     static int is_sm100 = -1;
     if (is_sm100 < 0) is_sm100 = xnrs_device_is_sm100();
@@ -1575,7 +1616,9 @@ static int titlepool_fwd_impl(const void *x, long long ldx, const int *x_rows, c
     memset(&p, 0, sizeof(p));
     p.M = n_rows; p.N = A; p.K = F;
     p.C = reinterpret_cast<float *>(hid); p.ldc = A; p.bias = b1; p.act = XNRS_ACT_TANH; p.aux = nullptr; p.accumulate = 0;
-    p.elt = elt; p.c_bf16 = elt == 2;
+    p.elt = elt; p.c_bf16 = elt == 2 && !planes;
+    p.planes = planes ? 2 : 0;
+    p.A2 = reinterpret_cast<const float *>(x_lo); p.B2 = reinterpret_cast<const float *>(w1_lo);
     const int kstep = elt == 2 ? 64 : TBK;
     p.split_k = 1; p.k_per_split = cdiv(F, kstep) * kstep;
     p.a_mn = 0; p.b_mn = 0;
@@ -1597,9 +1640,14 @@ static int titlepool_fwd_impl(const void *x, long long ldx, const int *x_rows, c
         ok = make_map(&mapA, reinterpret_cast<const float *>(x), F, x_rows ? 0x7fffffffLL : n_rows, ldx, x_rows ? 1 : TBM, false) &&
              make_map(&mapB, reinterpret_cast<const float *>(w1), F, A, F, 128, false);
     }
+    CUtensorMap mapA2 = mapA, mapB2 = mapB;
+    if (ok && planes) {
+        ok = make_map_bf16(&mapB2, w1_lo, F, A, F, 128);
+        ok = ok && (x_rows ? make_map_bf16(&mapA2, w1_lo, F, A, F, 128) : make_map_bf16(&mapA2, x_lo, F, n_rows, ldx, TBM));
+    }
     if (!ok) return fail(XNRS_ERR_UNSUPPORTED, "%s: tensor map encoding failed", "xnrs_titlepool_fwd");
-    CUtensorMap mapC;               // hid (n_rows x A, fp32 storage only) leaves through TMA stores
-    p.c_tma = c_tma_map(&mapC, reinterpret_cast<const float *>(hid), n_rows, A, A, nullptr, XNRS_ACT_NONE, elt == 2);
+    CUtensorMap mapC;               // hid (n_rows x A, fp32) leaves through TMA stores
+    p.c_tma = c_tma_map(&mapC, reinterpret_cast<const float *>(hid), n_rows, A, A, nullptr, XNRS_ACT_NONE, p.c_bf16 != 0);
     if (!p.c_tma) mapC = mapB;
     const int smem_bytes = SMEM_DATA + SMEM_EPI + 1024;
     static bool attr_set = false;
@@ -1617,15 +1665,16 @@ static int titlepool_fwd_impl(const void *x, long long ldx, const int *x_rows, c
     // The split is the default wherever it applies; XNRS_TITLEPOOL_SPLIT = 0 / 1 forces either.
     static int split_opt = -2;
     if (split_opt == -2) { const char *ev = getenv("XNRS_TITLEPOOL_SPLIT"); split_opt = ev ? atoi(ev) : -1; }
-    const bool split = seg && F <= 768 && split_opt != 0;
+    const bool split = seg && F <= 768 && (split_opt != 0 || planes);
     const long long pairs = std::min<long long>(p.tiles_m, num_sms() / 2);
     if (split) {
         p.pool.pooled = nullptr;
         p.pool.zsum = nullptr;
-        launch_pdl(gemm_tc2_kernel<true>, dim3((unsigned)(2 * pairs)), dim3(TC2_THREADS), smem_bytes, st, mapA, mapB, mapC, p);
+        launch_pdl(gemm_tc2_kernel<true>, dim3((unsigned)(2 * pairs)), dim3(TC2_THREADS), smem_bytes, st, mapA, mapB, mapC, mapA2, mapB2, p);
         XNRS_LAUNCHED();
         const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(cdiv(R, 8), 16LL * num_sms()));
-        if (elt == 2) titlepool_wsum_kernel<true><<<grid, 256, 0, st>>>(x, ldx, x_rows, seg, e, R, n_rows, F, attn, pooled);
+        if (planes) titlepool_wsum_kernel<false><<<grid, 256, 0, st>>>(x_sum, ld_sum, x_rows, seg, e, R, n_rows, F, attn, pooled);
+        else if (elt == 2) titlepool_wsum_kernel<true><<<grid, 256, 0, st>>>(x, ldx, x_rows, seg, e, R, n_rows, F, attn, pooled);
         else titlepool_wsum_kernel<false><<<grid, 256, 0, st>>>(x, ldx, x_rows, seg, e, R, n_rows, F, attn, pooled);
         XNRS_LAUNCHED();
         return XNRS_OK;
@@ -1633,7 +1682,7 @@ static int titlepool_fwd_impl(const void *x, long long ldx, const int *x_rows, c
     if (cudaMemsetAsync(pooled, 0, (size_t)R * F * sizeof(float), st) != cudaSuccess ||
         cudaMemsetAsync(zsum, 0, (size_t)R * sizeof(float), st) != cudaSuccess)
         return fail(XNRS_ERR_CUDA, "%s: memset failed", "xnrs_titlepool_fwd");
-    launch_pdl(gemm_tc2_kernel<true>, dim3((unsigned)(2 * pairs)), dim3(TC2_THREADS), smem_bytes, st, mapA, mapB, mapC, p);
+    launch_pdl(gemm_tc2_kernel<true>, dim3((unsigned)(2 * pairs)), dim3(TC2_THREADS), smem_bytes, st, mapA, mapB, mapC, mapA2, mapB2, p);
     XNRS_LAUNCHED();
     const long long work = std::max<long long>(n_rows, R * (F / 4));
     long long blocks = cdiv(work, 256), cap = 8LL * num_sms();
@@ -1659,13 +1708,26 @@ extern "C" int xnrs_titlepool_fwd_bf16(const void *x, long long ldx, const int *
     return titlepool_fwd_impl(x, ldx, x_rows, tix, seg, n_rows, R, F, A, w1, b1, w2, b2, 1, 2, hid, e, zsum, attn, pooled, STREAM(st));
 }
 
+extern "C" int xnrs_titlepool_fwd_bf16x3(const void *x_hi, const void *x_lo, long long ldx, const int *x_rows, const int *tix,
+                                         const int *seg, long long n_rows, long long R, int F, int A, const void *w1_hi,
+                                         const void *w1_lo, const float *b1, const float *w2, const float *b2, const float *x_f32,
+                                         long long ld_f32, float *hid, float *e, float *zsum, float *attn, float *pooled,
+                                         xnrs_stream_t st) {
+    XNRS_REQUIRE(x_lo && w1_lo && x_f32, "null pointer");
+    return titlepool_fwd_impl(x_hi, ldx, x_rows, tix, seg, n_rows, R, F, A, w1_hi, b1, w2, b2, 3, 2, hid, e, zsum, attn, pooled,
+                              STREAM(st), x_lo, w1_lo, x_f32, ld_f32);
+}
+
 // C[M,N] (=|+=) act(opA(A) opB(B) + bias) with bf16 operands (tcgen05 kind::f16, fp32 accumulation in TMEM) on the CTA-pair
 // kernel.  C is fp32 (split-K / accumulate allowed) or bf16 (c_bf16: plain store).  a_rows / b_rows gather table rows with
 // the cp.async producer warp (K-major A / MN-major B, as in the fp32 kernel).
-extern "C" int xnrs_gemm_bf16(int transA, int transB, long long M, long long N, long long K, const void *A, long long lda,
-                              const int *a_rows, const void *B, long long ldb, const int *b_rows, void *C, long long ldc,
-                              int c_bf16, const float *bias, int act, int accumulate, int split_k, xnrs_stream_t st_) {
+static int gemm_bf16_impl(int transA, int transB, long long M, long long N, long long K, const void *A, long long lda,
+                         const int *a_rows, const void *B, long long ldb, const int *b_rows, void *C, long long ldc, int c_bf16,
+                         const float *bias, int act, int accumulate, int split_k, xnrs_stream_t st_, const void *A_lo,
+                         const void *B_lo) {
+    const bool planes = A_lo != nullptr;
     XNRS_REQUIRE(M > 0 && N > 0 && K > 0 && A && B && C, "bad arguments");
+    XNRS_REQUIRE(!planes || (B_lo && !c_bf16 && !((uintptr_t)A_lo & 15) && !((uintptr_t)B_lo & 15)), "pre-split planes");
     XNRS_REQUIRE(act == XNRS_ACT_NONE || act == XNRS_ACT_RELU || act == XNRS_ACT_TANH, "activation");
     XNRS_REQUIRE(!(c_bf16 && (accumulate || split_k > 1)), "a bf16 C cannot accumulate / split K");
     cudaStream_t st = STREAM(st_);
@@ -1685,8 +1747,10 @@ extern "C" int xnrs_gemm_bf16(int transA, int transB, long long M, long long N, 
     p.lsu_gather = a_rows ? 1 : (b_rows ? 2 : 0);
     p.pf_stages = gather_prefetch_stages();
     XNRS_REQUIRE(!(a_rows && b_rows), "one gathered operand at a time");
-    p.passes = 1;
-    p.stages = MAX_STAGES;
+    p.passes = planes ? 3 : 1;                      // pre-split planes: hi hi + (lo hi + hi lo), a hi and a lo half per stage
+    p.planes = planes ? 2 : 0;
+    p.A2 = reinterpret_cast<const float *>(A_lo); p.B2 = reinterpret_cast<const float *>(B_lo);
+    p.stages = planes ? MAX_STAGES / 2 : MAX_STAGES;
     p.tiles_m = cdiv(M, 256); p.tiles_n = cdiv(N, 256);
     const long long tiles = p.tiles_m * p.tiles_n, npairs = num_sms() / 2;
     long long split = split_k;
@@ -1705,6 +1769,13 @@ extern "C" int xnrs_gemm_bf16(int transA, int transB, long long M, long long N, 
     if (ok && !b_rows) ok = p.b_mn ? make_map_bf16(&mapB, B, N, K, ldb, 64) : make_map_bf16(&mapB, B, K, N, ldb, 128);
     if (a_rows) mapA = mapB;
     if (b_rows) mapB = mapA;
+    CUtensorMap mapA2 = mapA, mapB2 = mapB;
+    if (ok && planes) {
+        if (!a_rows) ok = p.a_mn ? make_map_bf16(&mapA2, A_lo, M, K, lda, 64) : make_map_bf16(&mapA2, A_lo, K, M, lda, TBM);
+        if (ok && !b_rows) ok = p.b_mn ? make_map_bf16(&mapB2, B_lo, N, K, ldb, 64) : make_map_bf16(&mapB2, B_lo, K, N, ldb, 128);
+        if (a_rows) mapA2 = mapB2;
+        if (b_rows) mapB2 = mapA2;
+    }
     if (!ok) return fail(XNRS_ERR_UNSUPPORTED, "%s: tensor map encoding failed", "xnrs_gemm_bf16");
     CUtensorMap mapC;
     p.c_tma = c_tma_map(&mapC, reinterpret_cast<const float *>(C), M, N, ldc, bias, act, c_bf16 != 0);
@@ -1723,10 +1794,27 @@ extern "C" int xnrs_gemm_bf16(int transA, int transB, long long M, long long N, 
         attr_set = true;
     }
     const long long total = tiles * split, pairs = total < npairs ? total : npairs;
-    launch_pdl(gemm_tc2_kernel<false>, dim3((unsigned)(2 * pairs)), dim3(TC2_THREADS), smem_bytes, st, mapA, mapB, mapC, p);
-    g_last_gemm_kernel = "gemm_tc2_kernel (cta_group::2, 256x256 pair tile, BF16 kind::f16)";
+    launch_pdl(gemm_tc2_kernel<false>, dim3((unsigned)(2 * pairs)), dim3(TC2_THREADS), smem_bytes, st, mapA, mapB, mapC, mapA2, mapB2, p);
+    g_last_gemm_kernel = planes ? "gemm_tc2_kernel (cta_group::2, 256x256 pair tile, 3xBF16 pre-split planes, kind::f16)"
+                                : "gemm_tc2_kernel (cta_group::2, 256x256 pair tile, BF16 kind::f16)";
     XNRS_LAUNCHED();
     return XNRS_OK;
+}
+
+extern "C" int xnrs_gemm_bf16(int transA, int transB, long long M, long long N, long long K, const void *A, long long lda,
+                              const int *a_rows, const void *B, long long ldb, const int *b_rows, void *C, long long ldc,
+                              int c_bf16, const float *bias, int act, int accumulate, int split_k, xnrs_stream_t st) {
+    return gemm_bf16_impl(transA, transB, M, N, K, A, lda, a_rows, B, ldb, b_rows, C, ldc, c_bf16, bias, act, accumulate, split_k, st,
+                          nullptr, nullptr);
+}
+
+extern "C" int xnrs_gemm_bf16x3(int transA, int transB, long long M, long long N, long long K, const void *A_hi, const void *A_lo,
+                                long long lda, const int *a_rows, const void *B_hi, const void *B_lo, long long ldb,
+                                const int *b_rows, float *C, long long ldc, const float *bias, int act, int accumulate, int split_k,
+                                xnrs_stream_t st) {
+    XNRS_REQUIRE(A_lo && B_lo, "null pointer");
+    return gemm_bf16_impl(transA, transB, M, N, K, A_hi, lda, a_rows, B_hi, ldb, b_rows, C, ldc, 0, bias, act, accumulate, split_k, st,
+                          A_lo, B_lo);
 }
 
 extern "C" int xnrs_set_option(const char *name, int value) {

@@ -15,7 +15,7 @@ from . import _lib
 
 ACT_NONE, ACT_RELU, ACT_TANH, ACT_RELU_MASK = 0, 1, 2, 3
 LOSS_MSE_RELU, LOSS_BCE_LOGITS, LOSS_NLL, LOSS_BCE_SIGMOID = 0, 1, 2, 3
-PRECISIONS = {'fp32': 0, 'tf32x3': 1, 'tf32': 2, 'bf16': 3}
+PRECISIONS = {'fp32': 0, 'tf32x3': 1, 'tf32': 2, 'bf16': 3, 'bf16x3': 4}
 _precision = 0
 
 
@@ -23,14 +23,18 @@ def set_precision(name: str) -> None:
     """arithmetic of the GEMM-shaped ops: 'fp32' (exact FMA), 'tf32x3' (fp32-accurate tensor cores), 'tf32' (single pass) or
     'bf16' (2e-2 tolerance class): the token-level tensors of the additive-pooling title encoder — token-table rows, the
     tanh hidden layer and its gradient, i.e. ~99 % of the step's bytes and FLOPs — are STORED in bf16 and multiplied by
-    tcgen05 kind::f16 with fp32 accumulation; the small title / user level GEMMs on fp32 tensors run single-pass TF32."""
+    tcgen05 kind::f16 with fp32 accumulation; the small title / user level GEMMs on fp32 tensors run single-pass TF32.
+    'bf16x3' is fp32-accurate like 'tf32x3' (1e-4 class, measured ~1e-6): the two token-level tensor-core launches of the
+    additive-pooling title encoder run 3xBF16 on operands PRE-SPLIT into two bf16 planes (x ~ hi + lo: the frozen token
+    table once, fc1.weight once per step, d_hid written as planes by the pooling backward) — no in-kernel split pass, twice the
+    MMA rate of TF32; everything else is 'tf32x3'."""
     global _precision
     _precision = PRECISIONS[name]
 
 
 def _gemm_precision() -> int:
     """precision code handed to xnrs_gemm (fp32 operands): the bf16-storage mode multiplies them in single-pass TF32"""
-    return 2 if _precision == 3 else _precision
+    return 2 if _precision == 3 else (1 if _precision == 4 else _precision)
 
 
 def get_precision() -> str:
@@ -179,6 +183,46 @@ def bf16_twin(t: torch.Tensor) -> torch.Tensor:
     return twin
 
 
+def split_bf16(t: torch.Tensor):
+    """fp32 -> two bf16 planes (hi, lo) with t ~ hi + lo (hi = bf16(t), lo = bf16(t - hi))"""
+    t = _f32(t)
+    hi = torch.empty(t.shape, device=t.device, dtype=torch.bfloat16)
+    lo = torch.empty(t.shape, device=t.device, dtype=torch.bfloat16)
+    call('xnrs_split_bf16', t.numel(), t, hi, lo)
+    return hi, lo
+
+
+def bf16_split_twin(t: torch.Tensor):
+    """the two bf16 planes of a FROZEN fp32 table (the token table), made once and cached on the tensor object"""
+    twin = getattr(t, '_xnrs_bf16x3', None)
+    if twin is None or twin[0].shape != t.shape or twin[0].device != t.device:
+        twin = split_bf16(t)
+        t._xnrs_bf16x3 = twin
+    return twin
+
+
+def gemm_bf16x3(a_hi, a_lo, b_hi, b_lo, *, trans_a=False, trans_b=False, bias=None, act=ACT_NONE, out=None, accumulate=False,
+                a_rows=None, b_rows=None, split_k=0):
+    """xnrs_gemm_bf16x3: fp32-accurate product of operands given as two bf16 planes each; out fp32"""
+    rows_a = a_rows.numel() if a_rows is not None else a_hi.shape[0]
+    rows_b = b_rows.numel() if b_rows is not None else b_hi.shape[0]
+    M, K = (a_hi.shape[1], rows_a) if trans_a else (rows_a, a_hi.shape[1])
+    N, Kb = (rows_b, b_hi.shape[1]) if trans_b else (b_hi.shape[1], rows_b)
+    if K != Kb:
+        raise RuntimeError(f'gemm_bf16x3: inner dimensions differ ({K} vs {Kb})')
+    for t_ in (a_hi, a_lo, b_hi, b_lo):
+        if t_.dtype != torch.bfloat16 or t_.stride(1) != 1:
+            raise RuntimeError('gemm_bf16x3 operands must be bf16 2-D with unit column stride')
+    if a_hi.stride(0) != a_lo.stride(0) or b_hi.stride(0) != b_lo.stride(0):
+        raise RuntimeError('gemm_bf16x3: the two planes of an operand must share their leading dimension')
+    if out is None:
+        out = torch.empty((M, N), device=a_hi.device, dtype=torch.float32)
+        accumulate = False
+    call('xnrs_gemm_bf16x3', int(trans_a), int(trans_b), M, N, K, a_hi, a_lo, a_hi.stride(0), a_rows, b_hi, b_lo, b_hi.stride(0),
+         b_rows, out, out.stride(0), bias, act, int(accumulate), split_k)
+    return out
+
+
 def gemm_bf16(a, b, *, trans_a=False, trans_b=False, bias=None, act=ACT_NONE, out=None, out_bf16=False, accumulate=False,
               a_rows=None, b_rows=None, split_k=0):
     """xnrs_gemm_bf16: bf16 operands (2-D, unit column stride), fp32 accumulation; out fp32 (default) or bf16"""
@@ -297,7 +341,7 @@ def _resolve_rows(x, rows, fuse_ok: bool = True):
     once (one coalesced pass, bit exact) and reads the dense copy."""
     if rows is None or _precision == 0:
         return x, rows
-    if FUSED_GATHER and fuse_ok and _precision == 1 and rows.numel() >= FUSED_GATHER_MIN_ROWS:
+    if FUSED_GATHER and fuse_ok and _precision in (1, 4) and rows.numel() >= FUSED_GATHER_MIN_ROWS:
         return x, rows
     return gather_rows(x, rows), None
 
@@ -425,6 +469,23 @@ class AdditivePoolFn(torch.autograd.Function):
         shape_ok = (tix is not None and seg is not None and mask is None and A == 256 and F_ % 128 == 0 and F_ <= 1024
                     and (rows.numel() if rows is not None else x.shape[0]) >= FUSED_GATHER_MIN_ROWS)
         ctx.bf16 = bool(_precision == 3 and FUSED_TITLEPOOL and rows is not None and shape_ok)
+        ctx.x3 = bool(_precision == 4 and FUSED_TITLEPOOL and rows is not None and shape_ok and F_ <= 768 and x.stride(0) % 8 == 0)
+        if ctx.x3:
+            # fp32-accurate 3xBF16 on pre-split planes: the frozen table's planes are cached, fc1.weight is split for this step;
+            # hid stays fp32; the weighted sums and the backward's row dots read the fp32 table
+            (xh, xl), n_rows = bf16_split_twin(x), rows.numel()
+            w1h, w1l = split_bf16(w1)
+            hid = torch.empty((n_rows, A), device=x.device, dtype=torch.float32)
+            attn = torch.empty(n_rows, device=x.device, dtype=torch.float32)
+            e = torch.empty(n_rows, device=x.device, dtype=torch.float32)
+            zsum = torch.empty(R, device=x.device, dtype=torch.float32)
+            pooled = torch.empty((R, F_), device=x.device, dtype=torch.float32)
+            call('xnrs_titlepool_fwd_bf16x3', xh, xl, xh.stride(0), rows, tix, seg, n_rows, R, F_, A, w1h, w1l, b1, w2.reshape(-1), b2,
+                 _mat(x), x.stride(0), hid, e, zsum, attn, pooled)
+            ctx.save_for_backward(x, rows, w1, w2, hid, attn, seg)
+            ctx.dims = (R, L, F_, A)
+            ctx.bias_params = (b1, b2)
+            return pooled, attn
         if ctx.bf16:
             # bf16-storage mode: the rows are gathered from the bf16 twin of the frozen table, fc1.weight is rounded to bf16 for
             # this step, the hidden layer is kept in bf16 for the backward pass; logits / weights / pooled sums are fp32
@@ -442,7 +503,7 @@ class AdditivePoolFn(torch.autograd.Function):
             return pooled, attn
         x, rows = _resolve_rows(x, rows)
         n_rows = rows.numel() if rows is not None else x.shape[0]
-        fused = (FUSED_TITLEPOOL and shape_ok and _precision in (1, 2, 3) and x.stride(0) % 4 == 0)
+        fused = (FUSED_TITLEPOOL and shape_ok and _precision in (1, 2, 3, 4) and x.stride(0) % 4 == 0)
         pooled = torch.empty((R, F_), device=x.device, dtype=torch.float32)
         if fused:
             hid = torch.empty((n_rows, A), device=x.device, dtype=torch.float32)
@@ -467,11 +528,26 @@ class AdditivePoolFn(torch.autograd.Function):
         dev = x.device
         d_pooled = torch.zeros((R, F_), device=dev, dtype=torch.float32) if d_pooled is None else _f32(d_pooled)
         d_attn = None if d_attn is None else _f32(d_attn)
-        d_hid = torch.empty_like(hid)
         b1, b2 = ctx.bias_params
         w2_buf, d_w2 = _wgrad_buffer(w2, w2)
         b2_buf, d_b2 = _wgrad_buffer(b2, b2)
         b1_buf, d_b1 = _wgrad_buffer(b1, b1)            # fc1 bias gradient = column sums of d_hid, fused into the kernel
+        if ctx.x3:                                      # d_hid leaves the pooling backward as two bf16 planes
+            if d_attn is not None:
+                raise RuntimeError('3xBF16 pooling: no gradient path through the returned weights')
+            dh_hi = torch.empty(hid.shape, device=dev, dtype=torch.bfloat16)
+            dh_lo = torch.empty(hid.shape, device=dev, dtype=torch.bfloat16)
+            call('xnrs_addpool_bwd_split', x, rows, hid, w2.reshape(-1), attn, d_pooled, seg, R, L, F_, A, hid.shape[0], dh_hi, dh_lo,
+                 w2_buf.view(-1), b2_buf.view(-1), b1_buf.view(-1))
+            xh, xl = bf16_split_twin(x)
+            g = _direct(w1)
+            if g is not None and g.dim() == 2:
+                gemm_bf16x3(dh_hi, dh_lo, xh, xl, trans_a=True, b_rows=rows, out=g, accumulate=True)
+                d_w1 = None
+            else:
+                d_w1 = gemm_bf16x3(dh_hi, dh_lo, xh, xl, trans_a=True, b_rows=rows)
+            return None, None, None, d_w1, d_b1, d_w2, d_b2, None, None, None, None
+        d_hid = torch.empty_like(hid)
         if ctx.bf16:                                    # x = the bf16 table twin, hid / d_hid bf16; gradients accumulate in fp32
             if d_attn is not None:
                 raise RuntimeError('bf16 pooling: no gradient path through the returned weights')

@@ -725,7 +725,8 @@ def eval_workload(ctx, args, want_cpu=True):
             gemm_kernels[r.kernel] = gemm_kernels.get(r.kernel, 0.0) + dt
         elif r.name.startswith('xnrs_titlepool_fwd'):       # gather -> fc1 -> tanh -> logit -> exp -> per-title sums: 2 * rows * A * F
             gemm_flop += 2.0 * r.args[1] * r.args[3] * r.args[4]
-            kname = ('gemm_tc2_kernel<POOL> fused title pooling (' + ('bf16 kind::f16' if r.name.endswith('bf16') else '3xTF32')
+            kname = ('gemm_tc2_kernel<POOL> fused title pooling ('
+                     + ('bf16 kind::f16' if r.name.endswith('bf16') else ('3xBF16 pre-split planes' if r.name.endswith('bf16x3') else '3xTF32'))
                      + ', cp.async gather)')
             gemm_kernels[kname] = gemm_kernels.get(kname, 0.0) + dt
     pk, pk_kind = peaks()
@@ -757,7 +758,8 @@ def eval_workload(ctx, args, want_cpu=True):
                      'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
                      'frac': (gemm_flop / (gemm_ms * 1e-3) / 1e12 / pk['bf16_tflops_sustained']) if gemm_ms else None,
                      'traffic': None,
-                     'peak_source': f'{pk_kind} (sustained bf16 GEMM). 3xTF32 (fp32-accurate) has 1/6 of this peak as its own ceiling; per rank',
+                     'peak_source': f'{pk_kind} (sustained bf16 GEMM). fp32-accurate arithmetic: 3xTF32 has 1/6 of this peak as its own '
+                                    'ceiling, 3xBF16 1/3; per rank',
                      'per_entry_point_ms': {k: round(v, 3) for k, v in sorted(per_entry.items(), key=lambda kv: -kv[1])}},
         # the HBM-bound scoring kernel, PER RANK: this rank's algorithmic bytes / this rank's event time
         'roofline_scoring': {'kernel': 'eval_impressions_warp_kernel (gather + dot + segmented rank sort + metrics)', 'bound': 'hbm',
@@ -838,7 +840,10 @@ def main():
     ap.add_argument('--batch', type=int, default=1024, help='impressions per GPU per step')
     ap.add_argument('--ref-batch', type=int, default=64, help='impressions per CPU step (reference arm / cpu_baseline)')
     ap.add_argument('--ref-eval-sample', type=int, default=400, help='impressions of the eval workload timed on the CPU')
-    ap.add_argument('--precision', default='tf32x3', choices=['fp32', 'tf32x3', 'tf32', 'bf16', 'bf16x3'])
+    ap.add_argument('--precision', default='bf16x3', choices=['fp32', 'tf32x3', 'tf32', 'bf16', 'bf16x3'],
+                    help="bf16x3 (default) and tf32x3 are the fp32-accurate modes (1e-4 parity class): 3xBF16 on pre-split planes for "
+                         "the token-level tensor-core launches + 3xTF32 elsewhere, or 3xTF32 everywhere; bf16 = the bf16 STORAGE mode "
+                         "(2e-2 class)")
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--only', default=None, choices=list(MODEL_CFGS) + ['eval'],
                     help='run ONE workload instead of the headline + sub lines')
@@ -870,10 +875,14 @@ def main():
     else:
         line = train_workload(ctx, args, 'cl', want_eager=True)
         line['sub'] = {'nrms_train': train_workload(ctx, args, 'nrms'), 'eval': eval_workload(ctx, args)}
-        if args.precision == 'tf32x3':
+        if args.precision in ('tf32x3', 'bf16x3'):
+            import copy
+            if args.precision == 'bf16x3':      # the same step with 3xTF32 on every tensor-core launch (the round-2a headline mode)
+                t3 = copy.copy(args)
+                t3.precision = 'tf32x3'
+                line['sub']['cl_train_3xtf32'] = train_workload(ctx, t3, 'cl', want_cpu=False)
             # second lines in the bf16 STORAGE mode (north-star tolerance class 2e-2): beside the fp32-accurate numbers, never
             # instead of them
-            import copy
             bf = copy.copy(args)
             bf.precision = 'bf16'
             line['sub']['cl_train_bf16'] = train_workload(ctx, bf, 'cl', want_cpu=False)

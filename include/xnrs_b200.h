@@ -146,15 +146,20 @@ int xnrs_cast_bf16(long long n, const float *src, void *dst, xnrs_stream_t st);
  * at twice the MMA rate and half the shared-memory bytes per k, and with NO in-kernel split pass: the planes of the frozen
  * token table are made once (xnrs_split_bf16), fc1.weight is split once per step, and the pooling backward writes d_hid
  * directly as two planes (xnrs_addpool_bwd_split).  Same layouts / gathers / epilogues as xnrs_gemm_bf16; C and hid are fp32.
+ * The planes of an operand are bf16, or IEEE fp16 (fp16 = 1 / a_fp16 / b_fp16 / planes_fp16: hi = fp16(x), lo = fp16(x - hi),
+ * 22 mantissa bits, |x| <= 65504); both operands of a product must use the same format (the MMA rejects a mixed pair).
+ * The forward product (frozen table x fc1.weight: moderate range) uses fp16 planes — representation error 2^-24, as accurate
+ * as 3xTF32; the weight gradient (d_hid of arbitrary magnitude x table) uses bf16 planes of both.
  * xnrs_titlepool_fwd_bf16x3: xnrs_titlepool_fwd on planes; x_f32 (ld_f32 floats per row) = the fp32 rows for the weighted sum. */
-int xnrs_split_bf16(long long n, const float *src, void *hi, void *lo, xnrs_stream_t st);
+int xnrs_split_bf16(long long n, const float *src, void *hi, void *lo, int fp16, xnrs_stream_t st);
 int xnrs_gemm_bf16x3(int transA, int transB, long long M, long long N, long long K, const void *A_hi, const void *A_lo,
-                     long long lda, const int *a_rows, const void *B_hi, const void *B_lo, long long ldb, const int *b_rows,
-                     float *C, long long ldc, const float *bias, int act, int accumulate, int split_k, xnrs_stream_t st);
+                     int a_fp16, long long lda, const int *a_rows, const void *B_hi, const void *B_lo, int b_fp16, long long ldb,
+                     const int *b_rows, float *C, long long ldc, const float *bias, int act, int accumulate, int split_k,
+                     xnrs_stream_t st);
 int xnrs_titlepool_fwd_bf16x3(const void *x_hi, const void *x_lo, long long ldx, const int *x_rows, const int *tix, const int *seg,
-                              long long n_rows, long long R, int F, int A, const void *w1_hi, const void *w1_lo, const float *b1,
-                              const float *w2, const float *b2, const float *x_f32, long long ld_f32, float *hid, float *e,
-                              float *zsum, float *attn, float *pooled, xnrs_stream_t st);
+                              long long n_rows, long long R, int F, int A, const void *w1_hi, const void *w1_lo, int planes_fp16,
+                              const float *b1, const float *w2, const float *b2, const float *x_f32, long long ld_f32, float *hid,
+                              float *e, float *zsum, float *attn, float *pooled, xnrs_stream_t st);
 int xnrs_addpool_bwd_split(const float *x, const int *x_rows, const float *hid, const float *w2, const float *attn,
                            const float *d_pooled, const int *seg, long long R, int L, int F, int A, long long n_rows,
                            void *d_hid_hi, void *d_hid_lo, float *d_w2, float *d_b2, float *d_b1, xnrs_stream_t st);

@@ -196,13 +196,16 @@ def _xnrs_gemm_bf16(ta, tb, M, N, K_, A, lda, a_rows, B, ldb, b_rows, C, ldc, c_
     C.copy_((C.float() + y if accumulate else y).to(C.dtype))
 
 
-def _xnrs_split_bf16(n, src, hi, lo):
-    h = src.to(torch.bfloat16)
+def _xnrs_split_bf16(n, src, hi, lo, fp16=0):
+    dt = torch.float16 if fp16 else torch.bfloat16
+    v = src.clamp(-65504.0, 65504.0) if fp16 else src
+    h = v.to(dt)
     hi.copy_(h)
-    lo.copy_((src - h.float()).to(torch.bfloat16))
+    lo.copy_((v - h.float()).to(dt))
 
 
-def _xnrs_gemm_bf16x3(ta, tb, M, N, K_, A_hi, A_lo, lda, a_rows, B_hi, B_lo, ldb, b_rows, C, ldc, bias, act, accumulate, split_k):
+def _xnrs_gemm_bf16x3(ta, tb, M, N, K_, A_hi, A_lo, a_f16, lda, a_rows, B_hi, B_lo, b_f16, ldb, b_rows, C, ldc, bias, act, accumulate,
+                      split_k):
     ah, al, bh, bl = (_rows(t, r).float() for t, r in ((A_hi, a_rows), (A_lo, a_rows), (B_hi, b_rows), (B_lo, b_rows)))
     op = (lambda m: m.T) if ta else (lambda m: m)
     oq = (lambda m: m.T) if tb else (lambda m: m)
@@ -213,8 +216,8 @@ def _xnrs_gemm_bf16x3(ta, tb, M, N, K_, A_hi, A_lo, lda, a_rows, B_hi, B_lo, ldb
     C.copy_(C + y if accumulate else y)
 
 
-def _xnrs_titlepool_fwd_bf16x3(x_hi, x_lo, ldx, x_rows, tix, seg, n_rows, R, F_, A, w1_hi, w1_lo, b1, w2, b2, x_f32, ld_f32, hid, e,
-                               zsum, attn, pooled):
+def _xnrs_titlepool_fwd_bf16x3(x_hi, x_lo, ldx, x_rows, tix, seg, n_rows, R, F_, A, w1_hi, w1_lo, planes_f16, b1, w2, b2, x_f32, ld_f32,
+                               hid, e, zsum, attn, pooled):
     xr = _rows(x_f32, x_rows)[:n_rows]
     xh, xl = _rows(x_hi, x_rows)[:n_rows].float(), _rows(x_lo, x_rows)[:n_rows].float()
     wh, wl = w1_hi.float(), w1_lo.float()
@@ -235,7 +238,7 @@ def _xnrs_titlepool_fwd_bf16x3(x_hi, x_lo, ldx, x_rows, tix, seg, n_rows, R, F_,
 def _xnrs_addpool_bwd_split(x, x_rows, hid, w2, attn, d_pooled, seg, R, L, F_, A, n_rows, d_hid_hi, d_hid_lo, d_w2, d_b2, d_b1):
     d32 = torch.empty(hid.shape, dtype=torch.float32)
     _xnrs_addpool_bwd(x, x_rows, None, hid, w2, attn, d_pooled, None, seg, R, L, F_, A, n_rows, d32, d_w2, d_b2, None, d_b1)
-    _xnrs_split_bf16(d32.numel(), d32, d_hid_hi, d_hid_lo)
+    _xnrs_split_bf16(d32.numel(), d32, d_hid_hi, d_hid_lo, 0)
 
 
 def _xnrs_titlepool_fwd_bf16(x, ldx, x_rows, tix, seg, n_rows, R, F_, A, w1, b1, w2, b2, hid, e, zsum, attn, pooled):

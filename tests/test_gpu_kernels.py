@@ -601,6 +601,13 @@ def test_bf16x3_tensor_core_gemm(ta, tb):
         assert float((ah.float() + al.float() - cu(a)).abs().max()) <= 2 ** -16 * float(a.abs().max())
         got = K.gemm_bf16x3(ah, al, bh, bl, trans_a=bool(ta), trans_b=bool(tb))
         assert_close(got, want.float(), 2e-5, f'bf16x3 gemm {M}x{N}x{K_}')
+        # fp16 planes (22 mantissa bits) on both operands (the MMA rejects a mixed bf16 / fp16 pair: refused up front)
+        fh, fl = K.split_bf16(cu(b), fp16=True)
+        assert float((fh.float() + fl.float() - cu(b)).abs().max()) <= 2 ** -22 * float(b.abs().max())
+        gh, gl = K.split_bf16(cu(a), fp16=True)
+        assert_close(K.gemm_bf16x3(gh, gl, fh, fl, trans_a=bool(ta), trans_b=bool(tb)), want.float(), 5e-6, 'fp16 x fp16 planes')
+        with pytest.raises(RuntimeError):
+            K.gemm_bf16x3(ah, al, fh, fl, trans_a=bool(ta), trans_b=bool(tb))
         got = K.gemm_bf16x3(ah, al, bh, bl, trans_a=bool(ta), trans_b=bool(tb), bias=cu(bias), act=K.ACT_TANH)
         assert_close(got, torch.tanh(want + bias.double()).float(), 5e-5, 'bf16x3 gemm bias + tanh')
         out = cu(torch.ones(M, N))
@@ -612,18 +619,19 @@ def test_bf16x3_tensor_core_gemm_fused_gather():
     """the two planes of a table gathered by the cp.async warps: forward (rows of A) and weight-gradient (rows of B along K)"""
     V, D, A_ = 5000, 768, 256
     table = torch.randn(V, D, generator=g(1)) / math.sqrt(D)
-    th, tl = K.split_bf16(cu(table))
+    th, tl = K.split_bf16(cu(table), fp16=True)             # the frozen table and the weight: fp16 planes; the gradient: bf16 planes
     for R in (1650, 41000):
         rows = torch.randint(0, V, (R,), generator=g(2)).int()
         w = torch.randn(A_, D, generator=g(3))
-        wh, wl = K.split_bf16(cu(w))
+        wh, wl = K.split_bf16(cu(w), fp16=True)
         want = table[rows.long()].double() @ w.double().T
         got = K.gemm_bf16x3(th, tl, wh, wl, trans_b=True, a_rows=cu(rows))
-        assert_close(got, want.float(), 2e-5, 'bf16x3 gathered forward')
+        assert_close(got, want.float(), 5e-6, 'fp16-plane gathered forward')
         d = torch.randn(R, A_, generator=g(5))
         dh, dl = K.split_bf16(cu(d))
+        tbh, tbl = K.split_bf16(cu(table))
         want_dw = d.double().T @ table[rows.long()].double()
-        got_dw = K.gemm_bf16x3(dh, dl, th, tl, trans_a=True, b_rows=cu(rows))
+        got_dw = K.gemm_bf16x3(dh, dl, tbh, tbl, trans_a=True, b_rows=cu(rows))
         assert_close(got_dw, want_dw.float(), 3e-5, 'bf16x3 gathered weight gradient')
 
 

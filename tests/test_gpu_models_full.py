@@ -249,7 +249,10 @@ def test_bench_config_step_matches_oracle(prec, tol, monkeypatch):
     for k, v in P.items():
         if v.grad is None:
             continue
-        assert_close(named[k].grad, v.grad, 2 * tol, 'grad ' + k, atol=(2e-6 if prec == 'tf32x3' else 2e-3) * gscale)
+        # absolute floor relative to the largest gradient of the model: column sums with heavy cancellation (the poolers' fc1.bias
+        # gradient = sum over rows of d_hid, whose rows sum to ~0 per group) carry fp32 summation-order noise of 2e-5 ... 1.7e-4 of
+        # their own scale from run to run (atomics), in the oracle's fp32 as well
+        assert_close(named[k].grad, v.grad, 2 * tol, 'grad ' + k, atol=(1e-5 if prec in ('tf32x3', 'bf16x3') else 2e-3) * gscale)
 
 
 def _lib_fallbacks():

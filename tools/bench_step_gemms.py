@@ -1,6 +1,6 @@
 """Every C-ABI call of ONE bench-shaped CL train step, replayed back to back and timed alone (CUDA events around 50 launches
 of the same call, warm caches): where the step's time goes call by call, without launch gaps or event overhead per call.
-    python tools/bench_step_gemms.py [--precision tf32x3|bf16] [--batch 1024] > gpurun_out/step_calls.jsonl
+    python tools/bench_step_gemms.py [--precision bf16x3|tf32x3|bf16] [--batch 1024] > gpurun_out/step_calls.jsonl
 """
 import argparse
 import json
@@ -22,7 +22,7 @@ from xnrs_b200.training import ContrastiveRankingTrainer  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument('--precision', default='tf32x3')
+    ap.add_argument('--precision', default='bf16x3')
     ap.add_argument('--batch', type=int, default=1024)
     ap.add_argument('--reps', type=int, default=50)
     args = ap.parse_args()

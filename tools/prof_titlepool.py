@@ -60,6 +60,20 @@ def main():
     g_small = torch.zeros(256, 256, device=dev)
     for _ in range(3):
         K.gemm(o_small, a_small, trans_a=True, out=g_small, accumulate=True)
+    # the same token-level launches in the 3xBF16 pre-split form (bench default): fused pooling forward, pooling backward writing
+    # d_hid as two bf16 planes, gathered weight gradient
+    th, tl = K.bf16_split_twin(store.token_table, True)
+    tbh, tbl = K.bf16_split_twin(store.token_table, False)
+    w1h, w1l = K.split_bf16(w1, fp16=True)
+    dh_hi, dh_lo = torch.empty(T, 256, device=dev, dtype=torch.bfloat16), torch.empty(T, 256, device=dev, dtype=torch.bfloat16)
+    for _ in range(3):
+        K.call('xnrs_titlepool_fwd_bf16x3', th, tl, 768, plan.rows, plan.tix, plan.seg, T, R, 768, 256, w1h, w1l, 1, b1, w2, b2,
+               K._mat(store.token_table), 768, hid, e, zsum, attn, pooled)
+    for _ in range(3):
+        K.call('xnrs_addpool_bwd_split', K._mat(store.token_table), plan.rows, hid, w2, attn, d_pooled, plan.seg, R, 30, 768, 256, T,
+               dh_hi, dh_lo, d_w2, d_b2, d_b1)
+    for _ in range(3):
+        K.gemm_bf16x3(dh_hi, dh_lo, tbh, tbl, trans_a=True, b_rows=plan.rows, out=dw, accumulate=True)
     torch.cuda.synchronize()
     print('done')
 

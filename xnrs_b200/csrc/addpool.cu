@@ -6,6 +6,7 @@
 // over the (optionally table-gathered) rows of x.  One CTA walks titles grid-stride; rows whose
 // weight is exactly 0 (padding) are never read.  HBM-bound: per title it reads L*A (hid) + L*F (x).
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -657,6 +658,18 @@ __global__ void split_bf16_kernel(long long n, const float *__restrict__ src, __
     }
 }
 
+// the fp16 form: hi = fp16(x), lo = fp16(x - hi): 22 mantissa bits (relative error <= 2^-24 for |x| in fp16's normal range,
+// absolute error <= 3e-8 below it); values beyond +-65504 saturate.  For operands of moderate range (embeddings, weights);
+// gradients, whose magnitude is arbitrary, keep the bf16 form.
+__global__ void split_f16_kernel(long long n, const float *__restrict__ src, __half *__restrict__ hi, __half *__restrict__ lo) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float v = fminf(fmaxf(src[i], -65504.f), 65504.f);
+        const __half h = __float2half_rn(v);
+        hi[i] = h;
+        lo[i] = __float2half_rn(v - __half2float(h));
+    }
+}
+
 static bool pool_bwd2_ok(int L, int F, int A, const void *x, const void *hid, const void *d_hid, int elt) {
     static int on = -1;             // XNRS_POOL_BWD2=0: the first CTA-per-title kernels everywhere
     if (on < 0) { const char *e = getenv("XNRS_POOL_BWD2"); on = e ? atoi(e) : 1; }
@@ -1160,12 +1173,16 @@ extern "C" int xnrs_addpool_bwd_split(const float *x, const int *x_rows, const f
     return XNRS_OK;
 }
 
-extern "C" int xnrs_split_bf16(long long n, const float *src, void *hi, void *lo, xnrs_stream_t st) {
+extern "C" int xnrs_split_bf16(long long n, const float *src, void *hi, void *lo, int fp16, xnrs_stream_t st) {
     if (n <= 0) return XNRS_OK;
     XNRS_REQUIRE(src && hi && lo, "null pointer");
     long long b = cdiv(n, 256), cap = 16LL * num_sms();
-    split_bf16_kernel<<<(unsigned)(b > cap ? cap : b), 256, 0, STREAM(st)>>>(n, src, reinterpret_cast<__nv_bfloat16 *>(hi),
-                                                                            reinterpret_cast<__nv_bfloat16 *>(lo));
+    if (fp16)
+        split_f16_kernel<<<(unsigned)(b > cap ? cap : b), 256, 0, STREAM(st)>>>(n, src, reinterpret_cast<__half *>(hi),
+                                                                               reinterpret_cast<__half *>(lo));
+    else
+        split_bf16_kernel<<<(unsigned)(b > cap ? cap : b), 256, 0, STREAM(st)>>>(n, src, reinterpret_cast<__nv_bfloat16 *>(hi),
+                                                                                reinterpret_cast<__nv_bfloat16 *>(lo));
     XNRS_LAUNCHED();
     return XNRS_OK;
 }

@@ -68,6 +68,7 @@ struct TcArgs {
     int planes;             // pair kernel, elt == 2: 2 = both operands arrive PRE-SPLIT as two bf16 planes (x ~ hi + lo, A2 / B2 and
                             // mapA2 / mapB2 are the lo planes): three kind::f16 MMAs per k-step like 3xTF32, no splitter warps
     const float *A2, *B2;   // raw lo-plane pointers for the cp.async gather warps
+    int a_f16, b_f16;       // elt == 2: the operand's 16-bit planes are IEEE fp16 (11-bit mantissa) instead of bf16
     int c_tma;              // 1-CTA kernel: C leaves through TMA stores / reductions of staged 32 x 32 blocks (mapC is valid)
     long long *trace;       // diagnostics (xnrs_debug_gemm_trace): 8 SM-clock stamps per CTA of the 1-CTA kernel, or NULL
 };
@@ -979,8 +980,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         // ===================== MMA issuer: one thread of the LEADER CTA =====================
         if (rank == 0 && lane == 0) {
             // instruction descriptor: D = F32, A/B format TF32 (2) or BF16 (1), operand majors, N >> 3, M >> 4
-            const uint32_t fmt = p.elt == 2 ? 1u : 2u;
-            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
+            // (fp16 = 0, bf16 = 1; the hardware rejects a mixed pair: illegal instruction)
+            const uint32_t fmt_a = p.elt == 2 ? (p.a_f16 ? 0u : 1u) : 2u, fmt_b = p.elt == 2 ? (p.b_f16 ? 0u : 1u) : 2u;
+            const uint32_t idesc = (1u << 4) | (fmt_a << 7) | (fmt_b << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
                                    ((uint32_t)(T2N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
             // one MMA consumes 32 bytes of K (8 tf32 / 16 bf16).  K-major: 128-byte rows, SWIZZLE_128B.  MN-major: k-rows of
             // 128 bytes; fp32 uses the 32-byte-atom swizzle (4-row atoms, 8 k-rows per MMA), bf16 the plain 128-byte swizzle
@@ -1601,7 +1603,7 @@ static int titlepool_fwd_impl(const void *x, long long ldx, const int *x_rows, c
                               long long R, int F, int A, const void *w1, const float *b1, const float *w2, const float *b2,
                               int passes, int elt, void *hid, float *e, float *zsum, float *attn, float *pooled, cudaStream_t st,
                               const void *x_lo = nullptr, const void *w1_lo = nullptr, const float *x_sum = nullptr,
-                              long long ld_sum = 0) {
+                              long long ld_sum = 0, int planes_f16 = 0) {
     const bool planes = x_lo != nullptr;
     XNRS_REQUIRE(x && tix && w1 && b1 && w2 && b2 && hid && e && zsum && attn && pooled, "null pointer");
     XNRS_REQUIRE(!planes || (w1_lo && x_sum && seg && F <= 768 && elt == 2 && passes == 3 && !((uintptr_t)x_lo & 15) &&
@@ -1618,6 +1620,7 @@ static int titlepool_fwd_impl(const void *x, long long ldx, const int *x_rows, c
     p.C = reinterpret_cast<float *>(hid); p.ldc = A; p.bias = b1; p.act = XNRS_ACT_TANH; p.aux = nullptr; p.accumulate = 0;
     p.elt = elt; p.c_bf16 = elt == 2 && !planes;
     p.planes = planes ? 2 : 0;
+    p.a_f16 = p.b_f16 = planes && planes_f16;
     p.A2 = reinterpret_cast<const float *>(x_lo); p.B2 = reinterpret_cast<const float *>(w1_lo);
     const int kstep = elt == 2 ? 64 : TBK;
     p.split_k = 1; p.k_per_split = cdiv(F, kstep) * kstep;
@@ -1710,12 +1713,12 @@ extern "C" int xnrs_titlepool_fwd_bf16(const void *x, long long ldx, const int *
 
 extern "C" int xnrs_titlepool_fwd_bf16x3(const void *x_hi, const void *x_lo, long long ldx, const int *x_rows, const int *tix,
                                          const int *seg, long long n_rows, long long R, int F, int A, const void *w1_hi,
-                                         const void *w1_lo, const float *b1, const float *w2, const float *b2, const float *x_f32,
-                                         long long ld_f32, float *hid, float *e, float *zsum, float *attn, float *pooled,
-                                         xnrs_stream_t st) {
+                                         const void *w1_lo, int planes_fp16, const float *b1, const float *w2, const float *b2,
+                                         const float *x_f32, long long ld_f32, float *hid, float *e, float *zsum, float *attn,
+                                         float *pooled, xnrs_stream_t st) {
     XNRS_REQUIRE(x_lo && w1_lo && x_f32, "null pointer");
     return titlepool_fwd_impl(x_hi, ldx, x_rows, tix, seg, n_rows, R, F, A, w1_hi, b1, w2, b2, 3, 2, hid, e, zsum, attn, pooled,
-                              STREAM(st), x_lo, w1_lo, x_f32, ld_f32);
+                              STREAM(st), x_lo, w1_lo, x_f32, ld_f32, planes_fp16);
 }
 
 // C[M,N] (=|+=) act(opA(A) opB(B) + bias) with bf16 operands (tcgen05 kind::f16, fp32 accumulation in TMEM) on the CTA-pair
@@ -1724,7 +1727,7 @@ extern "C" int xnrs_titlepool_fwd_bf16x3(const void *x_hi, const void *x_lo, lon
 static int gemm_bf16_impl(int transA, int transB, long long M, long long N, long long K, const void *A, long long lda,
                          const int *a_rows, const void *B, long long ldb, const int *b_rows, void *C, long long ldc, int c_bf16,
                          const float *bias, int act, int accumulate, int split_k, xnrs_stream_t st_, const void *A_lo,
-                         const void *B_lo) {
+                         const void *B_lo, int a_f16 = 0, int b_f16 = 0) {
     const bool planes = A_lo != nullptr;
     XNRS_REQUIRE(M > 0 && N > 0 && K > 0 && A && B && C, "bad arguments");
     XNRS_REQUIRE(!planes || (B_lo && !c_bf16 && !((uintptr_t)A_lo & 15) && !((uintptr_t)B_lo & 15)), "pre-split planes");
@@ -1749,6 +1752,7 @@ static int gemm_bf16_impl(int transA, int transB, long long M, long long N, long
     XNRS_REQUIRE(!(a_rows && b_rows), "one gathered operand at a time");
     p.passes = planes ? 3 : 1;                      // pre-split planes: hi hi + (lo hi + hi lo), a hi and a lo half per stage
     p.planes = planes ? 2 : 0;
+    p.a_f16 = a_f16; p.b_f16 = b_f16;
     p.A2 = reinterpret_cast<const float *>(A_lo); p.B2 = reinterpret_cast<const float *>(B_lo);
     p.stages = planes ? MAX_STAGES / 2 : MAX_STAGES;
     p.tiles_m = cdiv(M, 256); p.tiles_n = cdiv(N, 256);
@@ -1809,12 +1813,13 @@ extern "C" int xnrs_gemm_bf16(int transA, int transB, long long M, long long N, 
 }
 
 extern "C" int xnrs_gemm_bf16x3(int transA, int transB, long long M, long long N, long long K, const void *A_hi, const void *A_lo,
-                                long long lda, const int *a_rows, const void *B_hi, const void *B_lo, long long ldb,
-                                const int *b_rows, float *C, long long ldc, const float *bias, int act, int accumulate, int split_k,
-                                xnrs_stream_t st) {
+                                int a_fp16, long long lda, const int *a_rows, const void *B_hi, const void *B_lo, int b_fp16,
+                                long long ldb, const int *b_rows, float *C, long long ldc, const float *bias, int act,
+                                int accumulate, int split_k, xnrs_stream_t st) {
     XNRS_REQUIRE(A_lo && B_lo, "null pointer");
+    XNRS_REQUIRE((a_fp16 != 0) == (b_fp16 != 0), "both operands fp16 planes or both bf16 planes (kind::f16 rejects a mixed pair)");
     return gemm_bf16_impl(transA, transB, M, N, K, A_hi, lda, a_rows, B_hi, ldb, b_rows, C, ldc, 0, bias, act, accumulate, split_k, st,
-                          A_lo, B_lo);
+                          A_lo, B_lo, a_fp16 != 0, b_fp16 != 0);
 }
 
 extern "C" int xnrs_set_option(const char *name, int value) {

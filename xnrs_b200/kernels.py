@@ -183,22 +183,29 @@ def bf16_twin(t: torch.Tensor) -> torch.Tensor:
     return twin
 
 
-def split_bf16(t: torch.Tensor):
-    """fp32 -> two bf16 planes (hi, lo) with t ~ hi + lo (hi = bf16(t), lo = bf16(t - hi))"""
+def split_bf16(t: torch.Tensor, fp16: bool = False):
+    """fp32 -> two 16-bit planes (hi, lo) with t ~ hi + lo (hi = round16(t), lo = round16(t - hi)).  bf16 planes: 16 mantissa bits,
+    any magnitude (gradients).  fp16 planes: 22 mantissa bits — as accurate as 3xTF32 — for values within +-65504 (embeddings,
+    weights; beyond that they saturate)."""
     t = _f32(t)
-    hi = torch.empty(t.shape, device=t.device, dtype=torch.bfloat16)
-    lo = torch.empty(t.shape, device=t.device, dtype=torch.bfloat16)
-    call('xnrs_split_bf16', t.numel(), t, hi, lo)
+    dt = torch.float16 if fp16 else torch.bfloat16
+    hi = torch.empty(t.shape, device=t.device, dtype=dt)
+    lo = torch.empty(t.shape, device=t.device, dtype=dt)
+    call('xnrs_split_bf16', t.numel(), t, hi, lo, int(fp16))
     return hi, lo
 
 
-def bf16_split_twin(t: torch.Tensor):
-    """the two bf16 planes of a FROZEN fp32 table (the token table), made once and cached on the tensor object"""
-    twin = getattr(t, '_xnrs_bf16x3', None)
-    if twin is None or twin[0].shape != t.shape or twin[0].device != t.device:
-        twin = split_bf16(t)
-        t._xnrs_bf16x3 = twin
-    return twin
+def bf16_split_twin(t: torch.Tensor, fp16: bool):
+    """the two 16-bit planes of a FROZEN fp32 table (the token table), made once per format and cached on the tensor object:
+    fp16 planes for the forward product (with the fp16 planes of fc1.weight), bf16 planes for the weight gradient (with the bf16
+    planes of d_hid) — the two operands of a kind::f16 MMA must share their format"""
+    cache = getattr(t, '_xnrs_bf16x3', None)
+    if cache is None or cache.get('shape') != t.shape or cache.get('device') != t.device:
+        cache = {'shape': t.shape, 'device': t.device}
+        t._xnrs_bf16x3 = cache
+    if fp16 not in cache:
+        cache[fp16] = split_bf16(t, fp16=fp16)
+    return cache[fp16]
 
 
 def gemm_bf16x3(a_hi, a_lo, b_hi, b_lo, *, trans_a=False, trans_b=False, bias=None, act=ACT_NONE, out=None, accumulate=False,
@@ -211,15 +218,16 @@ def gemm_bf16x3(a_hi, a_lo, b_hi, b_lo, *, trans_a=False, trans_b=False, bias=No
     if K != Kb:
         raise RuntimeError(f'gemm_bf16x3: inner dimensions differ ({K} vs {Kb})')
     for t_ in (a_hi, a_lo, b_hi, b_lo):
-        if t_.dtype != torch.bfloat16 or t_.stride(1) != 1:
-            raise RuntimeError('gemm_bf16x3 operands must be bf16 2-D with unit column stride')
-    if a_hi.stride(0) != a_lo.stride(0) or b_hi.stride(0) != b_lo.stride(0):
-        raise RuntimeError('gemm_bf16x3: the two planes of an operand must share their leading dimension')
+        if t_.dtype not in (torch.bfloat16, torch.float16) or t_.stride(1) != 1:
+            raise RuntimeError('gemm_bf16x3 operands must be bf16 / fp16 2-D with unit column stride')
+    if (a_hi.stride(0) != a_lo.stride(0) or b_hi.stride(0) != b_lo.stride(0) or a_hi.dtype != a_lo.dtype or b_hi.dtype != b_lo.dtype
+            or a_hi.dtype != b_hi.dtype):
+        raise RuntimeError('gemm_bf16x3: the planes of an operand share their leading dimension, and all four planes their type')
     if out is None:
         out = torch.empty((M, N), device=a_hi.device, dtype=torch.float32)
         accumulate = False
-    call('xnrs_gemm_bf16x3', int(trans_a), int(trans_b), M, N, K, a_hi, a_lo, a_hi.stride(0), a_rows, b_hi, b_lo, b_hi.stride(0),
-         b_rows, out, out.stride(0), bias, act, int(accumulate), split_k)
+    call('xnrs_gemm_bf16x3', int(trans_a), int(trans_b), M, N, K, a_hi, a_lo, int(a_hi.dtype == torch.float16), a_hi.stride(0), a_rows,
+         b_hi, b_lo, int(b_hi.dtype == torch.float16), b_hi.stride(0), b_rows, out, out.stride(0), bias, act, int(accumulate), split_k)
     return out
 
 
@@ -471,16 +479,16 @@ class AdditivePoolFn(torch.autograd.Function):
         ctx.bf16 = bool(_precision == 3 and FUSED_TITLEPOOL and rows is not None and shape_ok)
         ctx.x3 = bool(_precision == 4 and FUSED_TITLEPOOL and rows is not None and shape_ok and F_ <= 768 and x.stride(0) % 8 == 0)
         if ctx.x3:
-            # fp32-accurate 3xBF16 on pre-split planes: the frozen table's planes are cached, fc1.weight is split for this step;
-            # hid stays fp32; the weighted sums and the backward's row dots read the fp32 table
-            (xh, xl), n_rows = bf16_split_twin(x), rows.numel()
-            w1h, w1l = split_bf16(w1)
+            # fp32-accurate 3-pass 16-bit arithmetic on pre-split planes: the frozen table's fp16 planes are cached, fc1.weight is
+            # split (fp16) for this step; hid stays fp32; the weighted sums and the backward's row dots read the fp32 table
+            (xh, xl), n_rows = bf16_split_twin(x, True), rows.numel()
+            w1h, w1l = split_bf16(w1, fp16=True)
             hid = torch.empty((n_rows, A), device=x.device, dtype=torch.float32)
             attn = torch.empty(n_rows, device=x.device, dtype=torch.float32)
             e = torch.empty(n_rows, device=x.device, dtype=torch.float32)
             zsum = torch.empty(R, device=x.device, dtype=torch.float32)
             pooled = torch.empty((R, F_), device=x.device, dtype=torch.float32)
-            call('xnrs_titlepool_fwd_bf16x3', xh, xl, xh.stride(0), rows, tix, seg, n_rows, R, F_, A, w1h, w1l, b1, w2.reshape(-1), b2,
+            call('xnrs_titlepool_fwd_bf16x3', xh, xl, xh.stride(0), rows, tix, seg, n_rows, R, F_, A, w1h, w1l, 1, b1, w2.reshape(-1), b2,
                  _mat(x), x.stride(0), hid, e, zsum, attn, pooled)
             ctx.save_for_backward(x, rows, w1, w2, hid, attn, seg)
             ctx.dims = (R, L, F_, A)
@@ -539,7 +547,7 @@ class AdditivePoolFn(torch.autograd.Function):
             dh_lo = torch.empty(hid.shape, device=dev, dtype=torch.bfloat16)
             call('xnrs_addpool_bwd_split', x, rows, hid, w2.reshape(-1), attn, d_pooled, seg, R, L, F_, A, hid.shape[0], dh_hi, dh_lo,
                  w2_buf.view(-1), b2_buf.view(-1), b1_buf.view(-1))
-            xh, xl = bf16_split_twin(x)
+            xh, xl = bf16_split_twin(x, False)
             g = _direct(w1)
             if g is not None and g.dim() == 2:
                 gemm_bf16x3(dh_hi, dh_lo, xh, xl, trans_a=True, b_rows=rows, out=g, accumulate=True)

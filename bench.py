@@ -436,7 +436,7 @@ def gemm_rooflines(records, steps, precision):
         'peak_source': f'{pk_kind} (MEASURED_PEAKS.json, sustained bf16 GEMM; kernel timed inside a long step). '
                        + {'tf32x3': 'The kernel issues 3 TF32 MMAs per product (fp32-accurate 3xTF32): its own ceiling is 1/6 of this bf16 peak',
                           'tf32': 'TF32 operands: ceiling 1/2 of this bf16 peak', 'bf16': 'bf16 operands',
-                          'bf16x3': 'fp32-accurate 3xBF16 on the token-level launches (ceiling 1/3 of this bf16 peak), 3xTF32 elsewhere',
+                          'bf16x3': 'fp32-accurate 3-pass 16-bit split (fp16 planes forward, bf16 planes backward) on the token-level launches (ceiling 1/3 of this peak), 3xTF32 elsewhere',
                           'fp32': 'exact-fp32 SIMT kernel (no tensor cores)'}[precision],
         'launches_timed': d_n, 'avg_launch_ms': d_ms / max(d_n, 1),
         'all_gemm_tflops': gemm_flop / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None,
@@ -539,6 +539,11 @@ def train_workload(ctx, args, model_key, want_cpu=True, want_eager=False):
                           + ' kind::f16, cp.async B gather): dW1 = d_hid^T x',
                 'launches_timed': len(gb), 'avg_launch_ms': ms_gb / len(gb), 'achieved': flop_gb / (ms_gb * 1e-3) / 1e12,
                 'unit': 'TFLOP/s', 'peak': pk_['bf16_tflops_sustained'], 'frac': flop_gb / (ms_gb * 1e-3) / 1e12 / pk_['bf16_tflops_sustained']}
+            trg = traffic_entry('dw_x3') if gb[0].name.endswith('x3') else None
+            if trg:
+                kk = sum(r.args[4] for r in gb) / len(gb)
+                roofline['bf16_weight_gradient'].update({'traffic': trg['dram_bytes_per_row'] * kk, 'algorithmic_bytes': trg['algorithmic_bytes_per_row'] * kk,
+                                                         'traffic_source': f"{os.path.relpath(TRAFFIC_FILE, ROOT)}:dw_x3"})
         tp = [r for r in log.records if r.name.startswith('xnrs_titlepool_fwd')]
         if tp:
             bf, x3 = tp[0].name.endswith('bf16'), tp[0].name.endswith('bf16x3')
@@ -546,7 +551,7 @@ def train_workload(ctx, args, model_key, want_cpu=True, want_eager=False):
             rows_tp = sum(r.args[1] for r in tp)
             flop_tp = sum(2.0 * r.args[1] * r.args[3] * r.args[4] for r in tp)
             pk_, _ = peaks()
-            cls = 'titlepool_bf16' if bf else 'titlepool_fp32'
+            cls = 'titlepool_bf16' if bf else ('titlepool_x3' if x3 else 'titlepool_fp32')
             tr = traffic_entry(cls)
             roofline['fused_title_pool'] = {
                 'kernel': 'gemm_tc2_kernel<POOL> (cta_group::2 pair tile, cp.async table gather, pooling epilogue on TMEM, hid through '
@@ -621,8 +626,10 @@ def train_workload(ctx, args, model_key, want_cpu=True, want_eager=False):
     out = {
         'metric': 'train impressions/s', 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': steps, 'warmup': args.warmup,
         'ms_per_step': ms_med / steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        # (bf16x3: models without the fused token-level pooling launches — NRMS: self-attention first — run 3xTF32 throughout)
         'dtype': {'fp32': 'f32', 'tf32x3': 'f32 (3xTF32)', 'tf32': 'tf32', 'bf16': 'bf16',
-                  'bf16x3': 'f32 (3xBF16 split on the token-level GEMMs, 3xTF32 elsewhere)'}[args.precision],
+                  'bf16x3': ('f32 (3-pass fp16/bf16 split on the token-level GEMMs, 3xTF32 elsewhere)'
+                             if any(r.name.endswith('bf16x3') for r in log.records) else 'f32 (3xTF32)')}[args.precision],
         'data': 'synthetic',
         'config': {'workload': workload_name(B, model_key), 'global_batch': B * world, 'parallelism': f'dp{world}',
                    'l2': 'inputs larger than L2: 307 MB token table, ~0.5 GB of gathered rows per step, 8 batches cycled',
@@ -738,7 +745,7 @@ def eval_workload(ctx, args, want_cpu=True):
     res = {
         'metric': 'eval scored impressions/s', 'value': n_imp * passes / (ms_med * 1e-3), 'unit': UNIT, 'n_gpus': world,
         'steps': passes, 'warmup': max(1, args.warmup // 3), 'ms_per_step': ms_med / passes, 'higher_is_better': True,
-        'scaling': 'strong', 'vs_baseline': None, 'dtype': {'tf32x3': 'f32 (3xTF32)', 'bf16x3': 'f32 (3xBF16 split on the token-level GEMMs, 3xTF32 elsewhere)'}.get(args.precision, args.precision),
+        'scaling': 'strong', 'vs_baseline': None, 'dtype': {'tf32x3': 'f32 (3xTF32)', 'bf16x3': 'f32 (3-pass fp16/bf16 split on the token-level GEMMs, 3xTF32 elsewhere)'}.get(args.precision, args.precision),
         'data': 'synthetic',
         'config': {'workload': f'MIND-large-shaped full-catalogue eval, model=standard (mind_standard.yml): {n_news} news '
                                f'encoded once, {n_imp} impressions x ~37 candidates, H={HIST_LEN}, S={SEQ_LEN}; one step = '

@@ -74,7 +74,7 @@ def roofline_brief(r):
 
 def main():
     os.makedirs(P, exist_ok=True)
-    md = ['# profiles — round 2 (final build of the round)', '',
+    md = ['# profiles — round 2 (final build of the round: bench default = fp32-accurate 3-pass 16-bit split on the token-level launches)', '',
           'All captures on B200 (sm_100a, 148 SMs) through `gpurun`; every ncu run was preceded by the same command exiting 0 without '
           'ncu.  Numbers taken under a profiler are never bench values: the bench lines below come from plain runs.  Round-1 summaries: '
           '`README_r01.md`, `README_r01_session1.md`.', '']
@@ -82,7 +82,7 @@ def main():
     if final:
         json.dump(final, open(os.path.join(P, 'r02_bench_final.json'), 'w'), indent=1)
         md += ['## `python bench.py` (1 x B200): CL headline + sub lines', '', 'Full line: `profiles/r02_bench_final.json`.', '']
-        for name, x in [('headline: CL train, fp32-accurate 3xTF32', final)] + [(f'sub.{k}', v) for k, v in final.get('sub', {}).items()]:
+        for name, x in [('headline: CL train, fp32-accurate (3-pass fp16/bf16 split on the token-level GEMMs, 3xTF32 elsewhere)', final)] + [(f'sub.{k}', v) for k, v in final.get('sub', {}).items()]:
             md += [f'### {name}', '', '```json', json.dumps(brief(x)), '```', '', 'roofline: `' + json.dumps(roofline_brief(x.get('roofline'))) + '`', '']
             r = x.get('roofline') or {}
             if 'per_entry_point_ms_per_step' in r:
@@ -116,24 +116,45 @@ def main():
         shutil.copy(lp, os.path.join(P, 'r02_launches_cl.csv'))
         md += ['## ncu launch list of the CL bench command', '',
                '`XNRS_BENCH_MIN_S=0 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv python bench.py --only cl --steps 3 '
-               '--warmup 3 --no-cpu-baseline --no-graph` (kernel by kernel: the graph replays the same kernels), `profiles/r02_launches_cl.csv`:',
+               '--warmup 3 --no-cpu-baseline --no-graph` (default precision bf16x3; kernel by kernel: the graph replays the same kernels), `profiles/r02_launches_cl.csv`:',
                '', launch_summary(lp), '']
-    tk = os.path.join(P, 'r02_ncu_token_kernels.jsonl')
+    tk = os.path.join(P, 'r02c_ncu_kernels.jsonl')
     if os.path.exists(tk):
-        md += ['## ncu --set full: the token-level kernels at bench shapes (`tools/prof_titlepool.py`, 153.6 k rows, 8.9 k titles, 3xTF32)', '',
-               '| launch | time | DRAM read | DRAM write | DRAM % | tensor pipe % | issue active % | regs |', '|---|---|---|---|---|---|---|---|']
+        md += ['## ncu --set full: the token-level kernels and two title-level GEMMs at bench shapes (`tools/prof_titlepool.py`, 157.7 k rows, '
+               '8.9 k titles; final build)', '',
+               '| launch | kernel | time | DRAM read | DRAM write | DRAM % | tensor pipe % | issue active % | regs |', '|---|---|---|---|---|---|---|---|---|']
         seen = set()
         for l in open(tk):
             r = json.loads(l)
             if r['launch'] in seen:
                 continue
             seen.add(r['launch'])
-            md.append(f"| {r['launch']} | {r.get('gpu__time_duration.sum')} | {r.get('dram__bytes_read.sum')} | {r.get('dram__bytes_write.sum')} | "
+            md.append(f"| {r['launch']} | `{r.get('Kernel Name', '')[:34]}` | {r.get('gpu__time_duration.sum')} | {r.get('dram__bytes_read.sum')} | {r.get('dram__bytes_write.sum')} | "
                       f"{r.get('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed')} | {r.get('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active')} | "
                       f"{r.get('smsp__issue_active.avg.pct_of_peak_sustained_active')} | {r.get('launch__registers_per_thread')} |")
-        md += ['', '(captured before the gather was spread over 2 / 8 warps and the L2 prefetch was added; `titlepool` = fused pooling forward with '
-               'the weighted sums in the epilogue, `dw_gather` / `dw_dense` = fc1 weight gradient with / without the fused table gather, '
-               '`fc1_*` = the plain fc1 + tanh GEMM)', '']
+        md += ['', '(`titlepool_*` = the tensor-core launch of the fused pooling forward — gather, fc1, tanh, logit, exp, hid through TMA stores; the '
+               'per-title weighted sums run in `titlepool_wsum_kernel` afterwards; `dw_*` = fc1 weight gradient with / without the fused table '
+               'gather; `*_x3_*` = the 3-pass 16-bit split form on pre-split planes (bench default); `pool_bwd2_*` = title-level pooling backward, '
+               'fp32 d_hid or d_hid as two bf16 planes.  Earlier captures of the round: `r02_ncu_token_kernels.jsonl`.)', '']
+    sc = [(n, os.path.join(P, f'r02_step_calls_{n}.jsonl')) for n in ('bf16x3', 'tf32x3', 'bf16')]
+    if all(os.path.exists(f) for _, f in sc):
+        md += ['## every C-ABI call of one CL step, timed alone (`tools/bench_step_gemms.py`: 50 back-to-back launches per call, CUDA events)', '',
+               '| call | ' + ' | '.join(f'{n}: calls, us' for n, _ in sc) + ' |', '|---|' + '---|' * len(sc)]
+        sums = []
+        for n, f in sc:
+            rows = [json.loads(l) for l in open(f) if l.startswith('{')]
+            sums.append(next(r for r in rows if 'summary_us' in r))
+        keys = []
+        for sm in sums:
+            for k in sm['summary_us']:
+                if k not in keys:
+                    keys.append(k)
+        for k in keys:
+            md.append(f'| `{k}` | ' + ' | '.join((f"{sm['summary_us'][k][0]}, {sm['summary_us'][k][1]}" if k in sm['summary_us'] else '—') for sm in sums) + ' |')
+        md.append('| **total** | ' + ' | '.join(f"{sm['calls']}, {sm['total_us']}" for sm in sums) + ' |')
+        md += ['', 'Before this round\'s second half (3xTF32, build of the 8-GPU run at 3.65 M): `r02_step_calls_tf32x3_before.jsonl` (total 1940 us), '
+               '`r02_step_calls_bf16_before.jsonl` (1141 us).  The files also hold the SM-clock anatomy of a small GEMM (`trace` rows) and the '
+               'in-graph cost of a GEMM launch vs K (`sweep` rows).', '']
     for f, title in (('gather_gemm6.jsonl', 'fused gather vs gather-then-GEMM (`tools/bench_gather_gemm.py`, CUDA events; "gather4" keys = the fused form)'),
                      ('gather_pf.log', 'L2 prefetch distance of the gathered weight gradient (`XNRS_GATHER_PF`; columns: dense ms, gathered ms, fc1 gathered ms)')):
         path = os.path.join(G, f)

@@ -383,6 +383,47 @@ def _direct(param) -> Optional[torch.Tensor]:
     return g if (g is not None and g.is_contiguous()) else None
 
 
+# ---- weight gradients on a parallel branch --------------------------------------------------------------------------
+# A title / impression level GEMM leaves most SMs idle (4-140 CTAs of 9-12 us each, mostly fixed cost), and in a backward
+# pass the weight gradient (dW = dY^T X) and the input gradient (dX = dY W) of a layer are independent.  When the weight
+# gradient is accumulated IN PLACE into the optimiser's buffer (nothing is allocated), it is launched on a side stream that
+# forks from the current one and joins it again before the function returns: the two kernels overlap, and inside the step's
+# CUDA graph they become parallel branches.  XNRS_WGRAD_BRANCH=0 launches everything on one stream.
+WGRAD_BRANCH = bool(int(__import__('os').environ.get('XNRS_WGRAD_BRANCH', '1')))
+_side_streams = {}
+
+
+class _Branch:
+    """with _Branch(param, ...) as br: <launches that only accumulate into existing buffers>; ...; br.join()"""
+
+    def __init__(self, *params):
+        self.on = bool(WGRAD_BRANCH and torch.cuda.is_available() and all(_direct(p_) is not None for p_ in params if p_ is not None))
+        self.ctx = None
+
+    def __enter__(self):
+        if self.on:
+            self.cur = torch.cuda.current_stream()
+            key = self.cur.device_index
+            side = _side_streams.get(key)
+            if side is None:
+                side = _side_streams[key] = torch.cuda.Stream(device=self.cur.device)
+            self.side = side
+            side.wait_stream(self.cur)
+            self.ctx = torch.cuda.stream(side)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+            self.ctx = None
+        return False
+
+    def join(self):
+        if self.on:
+            self.cur.wait_stream(self.side)
+
+
 def _wgrad_gemm(param, a, b, **kw):
     """d_param = a^T @ b (trans_a GEMM), accumulated into param.grad when possible"""
     g = _direct(param)
@@ -425,14 +466,17 @@ class LinearFn(torch.autograd.Function):
         x, rows, weight = ctx.saved_tensors
         dy = _f32(dy)
         dx = dw = db = None
+        if _need(ctx, 0) and rows is not None:
+            raise RuntimeError('no gradient flows into a gathered (frozen) table')
+        want_b = ctx.has_bias and _need(ctx, 3)
+        with _Branch(weight if _need(ctx, 2) else None, ctx.bias_param if want_b else None) as br:
+            if _need(ctx, 2):
+                dw = _wgrad_gemm(weight, dy, x, b_rows=rows)
+            if want_b:
+                db = _wgrad_colsum(ctx.bias_param, dy)
         if _need(ctx, 0):
-            if rows is not None:
-                raise RuntimeError('no gradient flows into a gathered (frozen) table')
             dx = gemm(dy, weight)
-        if _need(ctx, 2):
-            dw = _wgrad_gemm(weight, dy, x, b_rows=rows)
-        if ctx.has_bias and _need(ctx, 3):
-            db = _wgrad_colsum(ctx.bias_param, dy)
+        br.join()
         return dx, None, dw, db
 
 
@@ -452,12 +496,17 @@ class Mlp2Fn(torch.autograd.Function):
     def backward(ctx, dy):
         x, w1, w2, h = ctx.saved_tensors
         dy = _f32(dy)
-        dw2 = _wgrad_gemm(w2, dy, h)
+        b1, b2 = ctx.bias_params
+        with _Branch(w2, b2 if ctx.bias else None) as br2:      # layer 2: weight / bias gradient beside the input gradient
+            dw2 = _wgrad_gemm(w2, dy, h)
+            db2 = _wgrad_colsum(b2, dy) if ctx.bias else None
         dh = gemm(dy, w2, act=ACT_RELU_MASK, aux=h)
-        dw1 = _wgrad_gemm(w1, dh, x)
-        db1 = _wgrad_colsum(ctx.bias_params[0], dh) if ctx.bias else None
-        db2 = _wgrad_colsum(ctx.bias_params[1], dy) if ctx.bias else None
+        br2.join()
+        with _Branch(w1, b1 if ctx.bias else None) as br1:
+            dw1 = _wgrad_gemm(w1, dh, x)
+            db1 = _wgrad_colsum(b1, dh) if ctx.bias else None
         dx = gemm(dh, w1) if _need(ctx, 0) else None
+        br1.join()
         return dx, dw1, db1, dw2, db2
 
 
@@ -618,9 +667,11 @@ class ItemLogitPoolFn(torch.autograd.Function):
         w2_buf, d_w2 = _wgrad_buffer(w2, w2)
         b2_buf, d_b2 = _wgrad_buffer(b2, b2)
         call('xnrs_logit_bwd', hid, w2.reshape(-1), d_logit, V, A, d_hid, w2_buf.view(-1), b2_buf.view(-1))
-        d_w1 = _wgrad_gemm(w1, d_hid, table)
-        d_b1 = _wgrad_colsum(b1, d_hid)
+        with _Branch(w1, b1) as br:
+            d_w1 = _wgrad_gemm(w1, d_hid, table)
+            d_b1 = _wgrad_colsum(b1, d_hid)
         gemm(d_hid, w1, out=d_table, accumulate=True)
+        br.join()
         return d_table, None, None, d_w1, d_b1, d_w2, d_b2
 
 

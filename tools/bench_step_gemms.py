@@ -67,7 +67,7 @@ def main():
         torch.cuda.synchronize()
         us = t0.elapsed_time(t1) * 1e3 / args.reps
         total_us += us
-        row = {'call': name, 'us': round(us, 2), 'ints': [x for x in a if isinstance(x, (int, float)) and not isinstance(x, bool)][:8]}
+        row = {'call': name, 'us': round(us, 2), 'ints': [x for x in a if isinstance(x, (int, float)) and not isinstance(x, bool)][:13]}
         if name in ('xnrs_gemm', 'xnrs_gemm_bf16', 'xnrs_gemm_bf16x3'):
             row['kernel'] = _lib.lib().xnrs_last_gemm_kernel().decode()
             flop = 2.0 * a[2] * a[3] * a[4]

@@ -360,7 +360,8 @@ __device__ __forceinline__ void tma_store_block32(const float (&r)[32], uint32_t
 }
 
 // bias (16-byte aligned, N % 4 == 0) + activation on a row-per-lane block
-__device__ __forceinline__ void bias_act_block32(float (&r)[32], const float *bias, long long col0, long long N, int act) {
+__device__ __forceinline__ void bias_act_block32(float (&r)[32], const float *bias, long long col0, long long N, int act,
+                                                 const float *aux = nullptr, long long ldc = 0, long long row = 0, long long M = 0) {
     if (bias) {
         const float4 *b4 = reinterpret_cast<const float4 *>(bias + col0);
 #pragma unroll
@@ -377,6 +378,18 @@ __device__ __forceinline__ void bias_act_block32(float (&r)[32], const float *bi
     } else if (act == XNRS_ACT_TANH) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) r[j] = tanh_fast(r[j]);
+    } else if (act == XNRS_ACT_RELU_MASK) {     // ReLU backward: this lane's row of the saved activation (128 contiguous bytes)
+        if (row < M) {
+            const float4 *a4 = reinterpret_cast<const float4 *>(aux + row * ldc + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (col0 + 4 * j < N) {
+                    const float4 a = __ldg(a4 + j);
+                    r[4 * j] = a.x > 0.f ? r[4 * j] : 0.f; r[4 * j + 1] = a.y > 0.f ? r[4 * j + 1] : 0.f;
+                    r[4 * j + 2] = a.z > 0.f ? r[4 * j + 2] : 0.f; r[4 * j + 3] = a.w > 0.f ? r[4 * j + 3] : 0.f;
+                }
+            }
+        }
     }
 }
 
@@ -497,7 +510,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             if (m0 + 32 * q >= p.M || n0 + c * 32 >= p.N) continue;        // warp-uniform
             if (p.c_tma) {
                 // (N % 4 == 0 and a 16-byte aligned bias are conditions of c_tma)
-                bias_act_block32(r, bias_on ? p.bias : nullptr, n0 + c * 32, p.N, p.act);
+                bias_act_block32(r, bias_on ? p.bias : nullptr, n0 + c * 32, p.N, p.act, p.aux, p.ldc, m0 + 32 * q + lane, p.M);
                 tma_store_block32<1>(r, stage_addr + (cbuf << 12), &mapC, n0 + c * 32, m0 + 32 * q, p.accumulate || p.split_k > 1, lane);
                 cbuf ^= 1;
             } else {
@@ -1121,7 +1134,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     if (p.c_tma) tma_store_block32<0>(r, epi_stage, &mapC, n0 + c * 32, m0 + 32 * q, false, lane);
                     else epi_block32(r, epi_stage, p, m0 + 32 * q, n0 + c * 32, split, lane, vec_ok, bias_vec, XNRS_ACT_NONE, nullptr);
                 } else if (p.c_tma) {
-                    bias_act_block32(r, (p.bias && (p.split_k == 1 || split == 0)) ? p.bias : nullptr, n0 + c * 32, p.N, p.act);
+                    bias_act_block32(r, (p.bias && (p.split_k == 1 || split == 0)) ? p.bias : nullptr, n0 + c * 32, p.N, p.act, p.aux, p.ldc,
+                                     m0 + 32 * q + lane, p.M);
                     tma_store_block32<0>(r, epi_stage, &mapC, n0 + c * 32, m0 + 32 * q, p.accumulate || p.split_k > 1, lane);
                 } else {
                     epi_block32(r, epi_stage, p, m0 + 32 * q, n0 + c * 32, split, lane, vec_ok, bias_vec, p.act, p.bias);
@@ -1346,14 +1360,14 @@ static bool make_map_bf16(CUtensorMap *map, const void *base, long long inner, l
 
 int g_opt_2cta = -2;       // -2: read XNRS_GEMM_2CTA on first use
 
-// C leaves through TMA stores of staged 32 x 32 blocks when its layout allows a tensor map and the epilogue has no per-element
-// global read (ReLU mask); XNRS_TMA_STORE=0 keeps the coalesced-store epilogue everywhere
+// C leaves through TMA stores of staged 32 x 32 blocks when its layout allows a tensor map (fp32 C, 16-byte aligned rows);
+// XNRS_TMA_STORE=0 keeps the coalesced-store epilogue everywhere
 static int c_tma_map(CUtensorMap *mapC, const float *C, long long M, long long N, long long ldc, const float *bias, int act,
-                     bool c_bf16) {
+                     bool c_bf16, const float *aux = nullptr) {
     static int on = -1;
     if (on < 0) { const char *e = getenv("XNRS_TMA_STORE"); on = e ? atoi(e) : 1; }
     return on && !c_bf16 && ldc % 4 == 0 && N % 4 == 0 && !((uintptr_t)C & 15) && !((uintptr_t)bias & 15) &&
-           act != XNRS_ACT_RELU_MASK && make_map(mapC, C, N, M, ldc, 32, false);
+           (act != XNRS_ACT_RELU_MASK || (aux && !((uintptr_t)aux & 15))) && make_map(mapC, C, N, M, ldc, 32, false);
 }
 static long long *g_gemm_trace = nullptr;     // xnrs_debug_gemm_trace
 
@@ -1443,7 +1457,7 @@ int gemm_tensorcore(const GemmArgs &a, int precision, cudaStream_t st, int *stat
 
     p.trace = g_gemm_trace;
     CUtensorMap mapA, mapB, mapC;
-    p.c_tma = c_tma_map(&mapC, a.C, a.M, a.N, a.ldc, a.bias, a.act, false);
+    p.c_tma = c_tma_map(&mapC, a.C, a.M, a.N, a.ldc, a.bias, a.act, false, a.aux);
     // gathered operands: the map spans the whole table (row count unknown to the GEMM: use the int32 range) and the box
     // is one row high — tile::gather4 fetches four such rows per instruction
     const long long table_rows = 0x7fffffffLL;

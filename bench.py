@@ -485,7 +485,7 @@ def train_workload(ctx, args, model_key, want_cpu=True, want_eager=False):
     n_batches = 8           # distinct batches cycled through; weak scaling: every rank draws its own B impressions
     raws = [syn.make_train_batch(N_NEWS, B, HIST_LEN, seed=1000 + 97 * rank + i) for i in range(n_batches)]
     pinned = [{k: v.pin_memory() for k, v in r.items()} for r in raws]
-    resident = [syn.index_batch(store, cat, r, dev, abstract_store=astore) for r in raws]
+    resident = [syn.index_batch(store, cat, r, dev, abstract_store=astore, categories=(model_key in ('naml', 'lstur'))) for r in raws]
     h2d_bytes = sum(v.numel() * v.element_size() for v in raws[0].values())
 
     for i in range(max(args.warmup, 2 * n_batches if use_graph else 0)):      # graphs: every cycled batch's bucket gets captured
@@ -495,12 +495,14 @@ def train_workload(ctx, args, model_key, want_cpu=True, want_eager=False):
     def region_resident(step_fn=None):
         step_fn = step_fn or run_step
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        dp.prefetch(resident[0])
+        depth = max(1, min(args.prefetch_depth, n_batches - 1))
+        for d in range(depth):
+            dp.prefetch(resident[d % n_batches])
         t0.record()
         for i in range(steps):
             step_fn(resident[i % n_batches])
-            if not args.no_prefetch:         # input pipeline: the next batch's id plumbing runs on a side stream meanwhile
-                dp.prefetch(resident[(i + 1) % n_batches])
+            if not args.no_prefetch:         # input pipeline: the id plumbing of the batch `depth` steps ahead runs on a side stream
+                dp.prefetch(resident[(i + depth) % n_batches])
         t1.record()
         torch.cuda.synchronize()
         return t0.elapsed_time(t1)
@@ -584,7 +586,7 @@ def train_workload(ctx, args, model_key, want_cpu=True, want_eager=False):
 
     # ---- timed region 2: end to end through the public trainer API with HOST (pinned) index buffers ---------------
     def h2d(i):                              # host (pinned) int32 ids / targets / labels -> device, on the main stream
-        b = syn.index_batch(store, cat, pinned[i % n_batches], dev, abstract_store=astore)
+        b = syn.index_batch(store, cat, pinned[i % n_batches], dev, abstract_store=astore, categories=(model_key in ('naml', 'lstur')))
         return b, torch.cuda.current_stream().record_event()
 
     last = [0.0]
@@ -597,10 +599,17 @@ def train_workload(ctx, args, model_key, want_cpu=True, want_eager=False):
     loss_ev = [torch.cuda.Event() for _ in range(2)]
 
     def region_e2e():
-        cur = h2d(0)
+        depth = max(1, min(args.prefetch_depth, n_batches - 1))
+        queue = []
+        for d in range(depth):               # input pipeline `depth` batches deep: ids copied from pinned memory and planned ahead
+            queue.append(h2d(d))
+            if not args.no_prefetch:
+                dp.prefetch(queue[-1][0], after=queue[-1][1])
         t0 = time.perf_counter()
         for i in range(steps):
-            nxt = h2d(i + 1)                 # tiny copy, queued BEFORE this step so the side stream can plan it meanwhile
+            nxt = h2d(i + depth)             # tiny copy, queued BEFORE this step so the side stream can plan it meanwhile
+            cur = queue.pop(0)
+            queue.append(nxt)
             out = run_step(cur[0])
             if args.e2e_sync_read:
                 last[0] = float(out['loss'])     # device -> host read of the step's loss (4 bytes, synchronises)
@@ -612,7 +621,6 @@ def train_workload(ctx, args, model_key, want_cpu=True, want_eager=False):
             if not args.e2e_sync_read and i > 0:
                 loss_ev[(i - 1) & 1].synchronize()
                 last[0] = float(loss_host[(i - 1) & 1])
-            cur = nxt
         torch.cuda.synchronize()
         if not args.e2e_sync_read:
             last[0] = float(loss_host[(steps - 1) & 1])
@@ -859,6 +867,9 @@ def main():
     ap.add_argument('--e2e-sync-read', action='store_true',
                     help='e2e: read each step\'s loss synchronously before queueing the next step (default: one step of lag)')
     ap.add_argument('--no-skip-padding', action='store_true', help='run pad tokens through the encoder like the reference does')
+    ap.add_argument('--prefetch-depth', type=int, default=2,
+                    help='how many batches ahead the input pipeline copies / plans ids (the plan kernels only get SMs at kernel '
+                         'boundaries of the running step: one batch ahead, the next step waited for its plan)')
     ap.add_argument('--no-prefetch', action='store_true', help='compute the id plumbing of each batch inside its own step')
     ap.add_argument('--no-graph', action='store_true', help='launch the CL step kernel by kernel instead of replaying its CUDA graph')
     ap.add_argument('--no-graph-multi-gpu', action='store_true', help='under torchrun, launch kernel by kernel (graphs capture the NCCL collectives too)')

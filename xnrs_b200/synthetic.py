@@ -91,8 +91,9 @@ def make_eval_impressions(n_news: int, n_imp: int, hist_len: int, n_users: int =
     }
 
 
-def index_batch(store, cat: Catalogue, raw: Dict[str, torch.Tensor], device, abstract_store=None) -> dict:
-    """reference batch-dict schema carrying IndexedTitles instead of dense (x, m) pairs."""
+def index_batch(store, cat: Catalogue, raw: Dict[str, torch.Tensor], device, abstract_store=None, categories: bool = True) -> dict:
+    """reference batch-dict schema carrying IndexedTitles instead of dense (x, m) pairs.
+    categories=False leaves out the category / subcategory index lookups (8 small device ops per batch that only NAML reads)."""
     hist_ids = raw['hist_ids'].to(device, non_blocking=True)
     cand_ids = raw['cand_ids'].to(device, non_blocking=True)
     hist = {'title_emb': store.index(hist_ids)}
@@ -100,14 +101,15 @@ def index_batch(store, cat: Catalogue, raw: Dict[str, torch.Tensor], device, abs
     if abstract_store is not None:
         hist['abstract_emb'] = abstract_store.index(hist_ids)
         cand['abstract_emb'] = abstract_store.index(cand_ids)
-    key = ('_dev', str(device))
-    if getattr(cat, '_dev_cache', None) is None or cat._dev_cache[0] != key:
-        cat._dev_cache = (key, cat.category.to(device), cat.subcategory.to(device))
-    _, category, subcategory = cat._dev_cache
-    hist['category_index'] = category[hist_ids.long()]
-    cand['category_index'] = category[cand_ids.long()]
-    hist['subcategory_index'] = subcategory[hist_ids.long()]
-    cand['subcategory_index'] = subcategory[cand_ids.long()]
+    if categories:
+        key = ('_dev', str(device))
+        if getattr(cat, '_dev_cache', None) is None or cat._dev_cache[0] != key:
+            cat._dev_cache = (key, cat.category.to(device), cat.subcategory.to(device))
+        _, category, subcategory = cat._dev_cache
+        hist['category_index'] = category[hist_ids.long()]
+        cand['category_index'] = category[cand_ids.long()]
+        hist['subcategory_index'] = subcategory[hist_ids.long()]
+        cand['subcategory_index'] = subcategory[cand_ids.long()]
     return {'user_features': {'history': hist, 'other': {'user_index': raw['user_index'].to(device, non_blocking=True)}},
             'candidate_features': cand, 'targets': raw['targets'].to(device, non_blocking=True),
             'main_theme': raw['main_theme'].to(device, non_blocking=True)}

@@ -106,7 +106,7 @@ def main():
             json.dump(x, open(os.path.join(P, f'r02_bench_{n}gpu.json'), 'w'), indent=1)
             md += [f'## torchrun, {n} x B200 (`bench.py --gpus {n}`)', '', '```json',
                    json.dumps({'cl': brief(x), **{k: brief(v) for k, v in x.get('sub', {}).items()}}), '```', '']
-    for name in ('naml', 'lstur'):
+    for name in ('naml', 'lstur', 'npa'):
         x = line(f'bench_{name}.json')
         if x:
             json.dump(x, open(os.path.join(P, f'r02_bench_{name}.json'), 'w'), indent=1)

@@ -302,6 +302,44 @@ def test_infonce_global_count_from_labels(Bk, n_lab):
     assert float(work[1]) == want
 
 
+def test_peer_exchange_kernels_on_one_rank():
+    """the two peer-memory exchange kernels of the data-parallel InfoNCE (csrc/peer.cu) with world = 1 — one buffer, its own
+    address as the only peer: normalise + all-gather must equal xnrs_infonce_normalize, reduce-scatter + normalisation backward
+    must equal xnrs_infonce_normalize_bwd times the loss scale; the epochs advance so a second launch works unchanged
+    (tools/check_dp_gpu.py runs them across real GPUs under torchrun)"""
+    Ba, E = 300, 256
+    gg = g(77)
+    emb, labels = torch.randn(Ba, E, generator=gg), torch.randint(0, 6, (Ba,), generator=gg).int()
+    off_flags_ag, off_flags_rs, off_ehat = 0, 256, 512
+    off_inv = off_ehat + Ba * E * 4
+    off_lab = off_inv + (Ba * 4 + 255) // 256 * 256
+    off_dehat = off_lab + (Ba * 4 + 255) // 256 * 256
+    buf = cu(torch.zeros((off_dehat + Ba * E * 4) // 4))
+    ptrs = torch.tensor([buf.data_ptr()], dtype=torch.int64, device=DEV)
+    ctl = cu(torch.zeros(8, dtype=torch.int32))
+    want_hat, want_inv = cu(torch.empty(Ba, E)), cu(torch.empty(Ba))
+    K.call('xnrs_infonce_normalize', cu(emb), Ba, E, want_hat, want_inv)
+    d_ehat = torch.randn(Ba, E, generator=gg)
+    stats = cu(torch.tensor([3.0, 17.0]))
+    gdev = cu(torch.tensor([0.25]))
+    want_d = cu(torch.empty(Ba, E))
+    K.call('xnrs_infonce_normalize_bwd', cu(d_ehat), want_hat, want_inv, stats, 2.0 * 0.25, Ba, E, want_d)
+    for launch in (1, 2):
+        buf[off_ehat // 4:].zero_()
+        K.call('xnrs_peer_normalize_allgather', cu(emb), cu(labels), Ba, E, 0, 1, ptrs, off_flags_ag, off_ehat, off_inv, off_lab, ctl)
+        got_hat = buf[off_ehat // 4: off_ehat // 4 + Ba * E].view(Ba, E)
+        assert_close(got_hat, want_hat, 1e-6, 'normalised rows')        # (the two kernels sum the squares in different orders)
+        assert_close(buf[off_inv // 4: off_inv // 4 + Ba], want_inv, 1e-6, 'inverse norms')
+        assert torch.equal(buf[off_lab // 4: off_lab // 4 + Ba].view(torch.int32).cpu(), labels)
+        buf[off_dehat // 4: off_dehat // 4 + Ba * E].copy_(cu(d_ehat).view(-1))
+        got_d = cu(torch.empty(Ba, E))
+        K.call('xnrs_peer_reduce_scatter_normalize_bwd', ptrs, off_flags_rs, off_dehat, Ba, E, 0, 1, want_hat, want_inv, stats, 2.0, gdev,
+               got_d, ctl)
+        assert_close(got_d, want_d, 1e-6, 'peer reduce-scatter + normalisation backward')
+        c = ctl.cpu().tolist()
+        assert c[0] == launch and c[2] == launch and c[1] == 0 and c[3] == 0 and c[4] == 0      # epochs advanced, tickets reset, no error
+
+
 @pytest.mark.parametrize('tag', ['met', 'mett', 'kat'])
 def test_ranking_metrics_against_reference_values(tag):
     fx = load_npz('loss_metrics')

@@ -474,3 +474,19 @@ def test_flat_adam_refuses_detached_gradients(device):
     model.zero_grad(set_to_none=True)
     with pytest.raises(RuntimeError, match='flat gradient buffer'):
         trainer._train_step(batch)
+
+
+def test_index_batch_category_lookups_are_optional():
+    """the bench's input pipeline leaves the category / subcategory lookups out for models that never read them (8 device ops
+    per batch); the title ids, targets and theme labels are the same either way"""
+    from xnrs_b200 import synthetic as syn
+    from xnrs_b200.data import TitleStore
+    cat = syn.make_catalogue(40, 12, vocab=100, dim=32, seed=3)
+    raw = syn.make_train_batch(40, 6, 5, seed=4)
+    store = TitleStore(cat.token_table, cat.title_tokens)
+    lean, full = (syn.index_batch(store, cat, raw, 'cpu', categories=c) for c in (False, True))
+    for side in (lambda b: b['candidate_features'], lambda b: b['user_features']['history']):
+        assert 'category_index' not in side(lean) and 'subcategory_index' not in side(lean)
+        assert 'category_index' in side(full) and 'subcategory_index' in side(full)
+        assert torch.equal(side(lean)['title_emb'].news_ids, side(full)['title_emb'].news_ids)
+    assert torch.equal(lean['targets'], full['targets']) and torch.equal(lean['main_theme'], full['main_theme'])

@@ -490,3 +490,36 @@ def test_index_batch_category_lookups_are_optional():
         assert 'category_index' in side(full) and 'subcategory_index' in side(full)
         assert torch.equal(side(lean)['title_emb'].news_ids, side(full)['title_emb'].news_ids)
     assert torch.equal(lean['targets'], full['targets']) and torch.equal(lean['main_theme'], full['main_theme'])
+
+
+@pytest.mark.parametrize('where', ['emulated', pytest.param('cuda', marks=pytest.mark.gpu)])
+def test_bf16x3_attention_projections_are_fp32_accurate(where, monkeypatch):
+    """precision 'bf16x3': the q / k / v projections of self-attention over table-gathered rows (NRMS) and their weight gradients run
+    the 3-pass 16-bit split on pre-split planes (cached fp16 / bf16 planes of the frozen table, weights and gradients split per
+    step) — output and every parameter gradient within the fp32 bar of the exact-fp32 path"""
+    from xnrs_b200.models import components as C
+    device = 'cpu' if where == 'emulated' else 'cuda'
+    if where == 'emulated':
+        monkeypatch.setattr(K, 'call', EMU.call)
+    monkeypatch.setattr(K, 'FUSED_GATHER_MIN_ROWS', 256)
+    V, D, h, R, L = 500, 256, 16, 40, 12
+    gen = torch.Generator().manual_seed(9)
+    table = (torch.randn(V, D, generator=gen) * 0.3).to(device)
+    rows = torch.randint(0, V, (R * L,), generator=gen).int().to(device)
+    ln = torch.randint(1, L + 1, (R,), generator=gen)
+    mask = (torch.arange(L)[None, :] < ln[:, None]).float().reshape(-1).to(device)
+    gout = torch.randn(R * L, D, generator=gen).to(device)
+    torch.manual_seed(3)
+    mod = C.MultiHeadAttention(h, D, dropout=0.0).to(device).eval()
+    outs = []
+    for prec in ('bf16x3', 'fp32'):
+        monkeypatch.setattr(K, '_precision', K.PRECISIONS[prec])
+        mod.zero_grad(set_to_none=True)
+        y = mod.attend(table, rows, mask, R, L)
+        (y * gout).sum().backward()
+        outs.append([y.detach()] + [p.grad.clone() for p in mod.parameters()])
+    assert set(getattr(table, '_xnrs_bf16x3', {})) >= {True, False}
+    names = ['out'] + ['d ' + n for n, _ in mod.named_parameters()]
+    gmax = max(float(t.abs().max()) for t in outs[1][1:])
+    for name, a, b in zip(names, *outs):        # d k_linear.bias is analytically 0 (a key bias shifts every score of a row equally)
+        assert_close(a, b, 1e-4, name, atol=1e-5 * gmax)

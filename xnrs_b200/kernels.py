@@ -722,16 +722,30 @@ class MultiHeadAttentionFn(torch.autograd.Function):
         sqrt(d_k) here and q is multiplied by it after its projection"""
         D = wq.shape[0]
         dk = D // n_heads
-        x, rows = _resolve_rows(x, rows, fuse_ok=False)
-        q = gemm(x, wq, trans_b=True, bias=bq, a_rows=rows)
+        # precision 'bf16x3', rows gathered from the frozen token table: the three projections (and their weight gradients) run
+        # the 3-pass 16-bit split on pre-split planes — the table's cached fp16 planes gathered inside the GEMM (no dense copy
+        # of the rows), the weights split once per step; fp32-accurate (1.3e-6), ~1.7x the 3xTF32 rate
+        ctx.x3 = bool(_precision == 4 and rows is not None and rows.numel() >= FUSED_GATHER_MIN_ROWS and D % 8 == 0
+                      and x.shape[1] % 8 == 0 and x.stride(0) % 8 == 0 and not _need(ctx, 0))
+        if ctx.x3:
+            xh, xl = bf16_split_twin(x, True)
+            q = gemm_bf16x3(xh, xl, *split_bf16(wq, fp16=True), trans_b=True, bias=bq, a_rows=rows)
+            k = gemm_bf16x3(xh, xl, *split_bf16(wk, fp16=True), trans_b=True, bias=bk, a_rows=rows)
+            v = gemm_bf16x3(xh, xl, *split_bf16(wv, fp16=True), trans_b=True, bias=bv, a_rows=rows)
+        else:
+            x, rows = _resolve_rows(x, rows, fuse_ok=False)
+            q = gemm(x, wq, trans_b=True, bias=bq, a_rows=rows)
+            k = gemm(x, wk, trans_b=True, bias=bk, a_rows=rows)
+            v = gemm(x, wv, trans_b=True, bias=bv, a_rows=rows)
         if q_scale != 1.0:
             call('xnrs_axpby', q.numel(), float(q_scale), None, q.clone(), 0.0, q)
-        k = gemm(x, wk, trans_b=True, bias=bk, a_rows=rows)
-        v = gemm(x, wv, trans_b=True, bias=bv, a_rows=rows)
         o = torch.empty_like(q)
         lse = torch.empty((R, n_heads, L), device=x.device, dtype=torch.float32)
         call('xnrs_mha_fwd', q, k, v, D, mask, R, L, n_heads, dk, keep, p_drop, seed, o, lse)
-        y = gemm(o, wo, trans_b=True, bias=bo)
+        if ctx.x3:      # output projection on fp16 planes of the attention output and of its weight
+            y = gemm_bf16x3(*split_bf16(o, fp16=True), *split_bf16(wo, fp16=True), trans_b=True, bias=bo)
+        else:
+            y = gemm(o, wo, trans_b=True, bias=bo)
         ctx.save_for_backward(x, rows, mask, wq, wk, wv, wo, q, k, v, o, lse, keep)
         ctx.cfg = (R, L, n_heads, dk, D, p_drop, seed)
         ctx.q_scale = float(q_scale)
@@ -744,17 +758,44 @@ class MultiHeadAttentionFn(torch.autograd.Function):
         R, L, h, dk, D, p_drop, seed = ctx.cfg
         dy = _f32(dy)
         bq, bk, bv, bo = ctx.bias_params
-        d_wo = _wgrad_gemm(wo, dy, o)
         d_bo = _wgrad_colsum(bo, dy)
-        d_o = gemm(dy, wo)
+        if ctx.x3:      # both products of the output projection's backward on bf16 planes (dy is a gradient: bf16's range)
+            dyh, dyl = split_bf16(dy)
+            oh, ol = split_bf16(o)
+            g_ = _direct(wo)
+            if g_ is not None and g_.dim() == 2:
+                gemm_bf16x3(dyh, dyl, oh, ol, trans_a=True, out=g_, accumulate=True)
+                d_wo = None
+            else:
+                d_wo = gemm_bf16x3(dyh, dyl, oh, ol, trans_a=True)
+            del oh, ol
+            d_o = gemm_bf16x3(dyh, dyl, *split_bf16(wo))
+            del dyh, dyl
+        else:
+            d_wo = _wgrad_gemm(wo, dy, o)
+            d_o = gemm(dy, wo)
         dq, dk_, dv = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
         call('xnrs_mha_bwd', q, k, v, o, d_o, D, mask, lse, R, L, h, dk, keep, p_drop, seed, dq, dk_, dv)
         if ctx.q_scale != 1.0:
             call('xnrs_axpby', dq.numel(), ctx.q_scale, None, dq.clone(), 0.0, dq)
-        d_wq = _wgrad_gemm(wq, dq, x, b_rows=rows)
-        d_wk = _wgrad_gemm(wk, dk_, x, b_rows=rows)
-        d_wv = _wgrad_gemm(wv, dv, x, b_rows=rows)
         d_bq, d_bk, d_bv = _wgrad_colsum(bq, dq), _wgrad_colsum(bk, dk_), _wgrad_colsum(bv, dv)
+        if ctx.x3:      # dW = d^T x on bf16 planes: the gradient is split here (arbitrary magnitude: bf16's range), the table's are cached
+            tbh, tbl = bf16_split_twin(x, False)
+            d_ws = []
+            for w_, d_ in ((wq, dq), (wk, dk_), (wv, dv)):
+                dh_, dl_ = split_bf16(d_)
+                g_ = _direct(w_)
+                if g_ is not None and g_.dim() == 2:
+                    gemm_bf16x3(dh_, dl_, tbh, tbl, trans_a=True, b_rows=rows, out=g_, accumulate=True)
+                    d_ws.append(None)
+                else:
+                    d_ws.append(gemm_bf16x3(dh_, dl_, tbh, tbl, trans_a=True, b_rows=rows))
+                del dh_, dl_
+            d_wq, d_wk, d_wv = d_ws
+        else:
+            d_wq = _wgrad_gemm(wq, dq, x, b_rows=rows)
+            d_wk = _wgrad_gemm(wk, dk_, x, b_rows=rows)
+            d_wv = _wgrad_gemm(wv, dv, x, b_rows=rows)
         d_x = None
         if _need(ctx, 0):
             if rows is not None:

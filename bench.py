@@ -634,7 +634,7 @@ def train_workload(ctx, args, model_key, want_cpu=True, want_eager=False):
     out = {
         'metric': 'train impressions/s', 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': steps, 'warmup': args.warmup,
         'ms_per_step': ms_med / steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        # (bf16x3: models without the fused token-level pooling launches — NRMS: self-attention first — run 3xTF32 throughout)
+        # (bf16x3: a model none of whose launches takes the split-plane GEMM — NPA — runs 3xTF32 throughout and says so)
         'dtype': {'fp32': 'f32', 'tf32x3': 'f32 (3xTF32)', 'tf32': 'tf32', 'bf16': 'bf16',
                   'bf16x3': ('f32 (3-pass fp16/bf16 split on the token-level GEMMs, 3xTF32 elsewhere)'
                              if any(r.name.endswith('bf16x3') for r in log.records) else 'f32 (3xTF32)')}[args.precision],

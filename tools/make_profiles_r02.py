@@ -106,6 +106,11 @@ def main():
             json.dump(x, open(os.path.join(P, f'r02_bench_{n}gpu.json'), 'w'), indent=1)
             md += [f'## torchrun, {n} x B200 (`bench.py --gpus {n}`)', '', '```json',
                    json.dumps({'cl': brief(x), **{k: brief(v) for k, v in x.get('sub', {}).items()}}), '```', '']
+    x = line('bench_r02_8gpu_nrms.json')
+    if x:
+        json.dump(x, open(os.path.join(P, 'r02_bench_8gpu_nrms.json'), 'w'), indent=1)
+        md += ['## torchrun, 8 x B200, `--only nrms` (after the self-attention projections moved to the split-plane GEMMs; the `nrms_train` '
+               'sub line of the 8-GPU run above predates that)', '', '```json', json.dumps(brief(x)), '```', '']
     for name in ('naml', 'lstur', 'npa'):
         x = line(f'bench_{name}.json')
         if x:

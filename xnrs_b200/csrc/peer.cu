@@ -14,7 +14,7 @@
 // spins on its own slots with acquire loads.  Epochs are kept in device memory and advanced by the kernels themselves, so a
 // replayed CUDA graph works unchanged.  A buffer is reused one training step later; the step's gradient all-reduce lies in
 // between, which no rank passes before every rank has finished reading (see xnrs_b200/distributed.py).
-// A spin that sees no progress for seconds gives up and raises ctl[4] (checked on the host) instead of hanging the GPU.
+// A spin that sees no progress for about a minute gives up and raises ctl[4] (checked on the host) instead of hanging the GPU.
 #include "common.cuh"
 
 namespace xnrs {
@@ -33,7 +33,8 @@ __device__ __forceinline__ void wait_flags(const unsigned *mine, int world, unsi
     for (int q = 0; q < world; ++q) {
         long long spins = 0;
         while ((int)(ld_acquire_sys(mine + q) - epoch) < 0) {
-            if (++spins > (1LL << 22)) {            // ~seconds: a peer never arrived
+            if (++spins > (1LL << 26)) {            // about a minute: a peer never arrived (a rank that merely stalls — graph
+                                                    // capture, a checkpoint write — is waited for, as a NCCL kernel would)
                 atomicExch(ctl + 4, 1);
                 return;
             }

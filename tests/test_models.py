@@ -523,3 +523,21 @@ def test_bf16x3_attention_projections_are_fp32_accurate(where, monkeypatch):
     gmax = max(float(t.abs().max()) for t in outs[1][1:])
     for name, a, b in zip(names, *outs):        # d k_linear.bias is analytically 0 (a key bias shifts every score of a row equally)
         assert_close(a, b, 1e-4, name, atol=1e-5 * gmax)
+
+
+def test_flat_adam_auxiliary_floats_ride_in_front_of_the_gradient():
+    """FlatAdam keeps 4 auxiliary floats in front of the flat gradient (one buffer: data-parallel scalars such as the InfoNCE value
+    are summed by the SAME all-reduce as the gradient); zero_grad clears them, every .grad is a 16-byte aligned view behind them"""
+    from xnrs_b200.training import FlatAdam
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(7, 5)
+    opt = FlatAdam(list(lin.parameters()), lr=1e-3)
+    assert opt.g_store.numel() == opt.flat_g.numel() + 4
+    assert opt.g_aux.data_ptr() == opt.g_store.data_ptr() and opt.flat_g.data_ptr() == opt.g_store.data_ptr() + 16
+    for p in lin.parameters():
+        assert p.grad.untyped_storage().data_ptr() == opt.g_store.untyped_storage().data_ptr()
+        assert (p.grad.data_ptr() - opt.g_store.data_ptr()) % 16 == 0
+    opt.g_aux.fill_(3.0)
+    lin.weight.grad.fill_(2.0)
+    opt.zero_grad()
+    assert float(opt.g_aux.abs().sum()) == 0.0 and float(opt.flat_g.abs().sum()) == 0.0

@@ -647,7 +647,7 @@ def test_bf16x3_tensor_core_gemm(ta, tb):
         with pytest.raises(RuntimeError):
             K.gemm_bf16x3(ah, al, fh, fl, trans_a=bool(ta), trans_b=bool(tb))
         got = K.gemm_bf16x3(ah, al, bh, bl, trans_a=bool(ta), trans_b=bool(tb), bias=cu(bias), act=K.ACT_TANH)
-        assert_close(got, torch.tanh(want + bias.double()).float(), 5e-5, 'bf16x3 gemm bias + tanh')
+        assert_close(got, torch.tanh(want + bias.double()).float(), 1e-4, 'bf16x3 gemm bias + tanh')
         out = cu(torch.ones(M, N))
         K.gemm_bf16x3(ah, al, bh, bl, trans_a=bool(ta), trans_b=bool(tb), out=out, accumulate=True, split_k=3)
         assert_close(out, (want + 1).float(), 2e-5, 'bf16x3 gemm split-K accumulate')

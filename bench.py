@@ -537,7 +537,7 @@ def train_workload(ctx, args, model_key, want_cpu=True, want_eager=False):
             flop_gb = sum(2.0 * r.args[2] * r.args[3] * r.args[4] for r in gb)
             pk_, _ = peaks()
             roofline['bf16_weight_gradient'] = {
-                'kernel': 'gemm_tc2_kernel (cta_group::2 pair tile, ' + ('3xBF16 on pre-split planes' if gb[0].name.endswith('x3') else 'BF16')
+                'kernel': 'gemm_tc2_kernel (cta_group::2 pair tile, ' + ('3-pass 16-bit split on pre-split bf16 planes' if gb[0].name.endswith('x3') else 'BF16')
                           + ' kind::f16, cp.async B gather): dW1 = d_hid^T x',
                 'launches_timed': len(gb), 'avg_launch_ms': ms_gb / len(gb), 'achieved': flop_gb / (ms_gb * 1e-3) / 1e12,
                 'unit': 'TFLOP/s', 'peak': pk_['bf16_tflops_sustained'], 'frac': flop_gb / (ms_gb * 1e-3) / 1e12 / pk_['bf16_tflops_sustained']}
@@ -557,7 +557,7 @@ def train_workload(ctx, args, model_key, want_cpu=True, want_eager=False):
             tr = traffic_entry(cls)
             roofline['fused_title_pool'] = {
                 'kernel': 'gemm_tc2_kernel<POOL> (cta_group::2 pair tile, cp.async table gather, pooling epilogue on TMEM, hid through '
-                          'TMA stores; ' + ('bf16 storage, kind::f16)' if bf else ('3xBF16 on pre-split planes, kind::f16)' if x3 else 'fp32 storage, 3xTF32)'))
+                          'TMA stores; ' + ('bf16 storage, kind::f16)' if bf else ('3-pass 16-bit split on pre-split fp16 planes, kind::f16)' if x3 else 'fp32 storage, 3xTF32)'))
                           + ' + titlepool_wsum_kernel (per-title weighted sums); the whole entry point is timed',
                 'launches_timed': len(tp), 'avg_launch_ms': ms_tp / len(tp), 'rows_per_launch': rows_tp / len(tp),
                 'achieved': flop_tp / (ms_tp * 1e-3) / 1e12, 'unit': 'TFLOP/s', 'peak': pk_['bf16_tflops_sustained'],
@@ -741,7 +741,7 @@ def eval_workload(ctx, args, want_cpu=True):
         elif r.name.startswith('xnrs_titlepool_fwd'):       # gather -> fc1 -> tanh -> logit -> exp -> per-title sums: 2 * rows * A * F
             gemm_flop += 2.0 * r.args[1] * r.args[3] * r.args[4]
             kname = ('gemm_tc2_kernel<POOL> fused title pooling ('
-                     + ('bf16 kind::f16' if r.name.endswith('bf16') else ('3xBF16 pre-split planes' if r.name.endswith('bf16x3') else '3xTF32'))
+                     + ('bf16 kind::f16' if r.name.endswith('bf16') else ('3-pass 16-bit split, pre-split fp16 planes' if r.name.endswith('bf16x3') else '3xTF32'))
                      + ', cp.async gather)')
             gemm_kernels[kname] = gemm_kernels.get(kname, 0.0) + dt
     pk, pk_kind = peaks()
@@ -774,7 +774,7 @@ def eval_workload(ctx, args, want_cpu=True):
                      'frac': (gemm_flop / (gemm_ms * 1e-3) / 1e12 / pk['bf16_tflops_sustained']) if gemm_ms else None,
                      'traffic': None,
                      'peak_source': f'{pk_kind} (sustained bf16 GEMM). fp32-accurate arithmetic: 3xTF32 has 1/6 of this peak as its own '
-                                    'ceiling, 3xBF16 1/3; per rank',
+                                    'ceiling, the 3-pass 16-bit split 1/3; per rank',
                      'per_entry_point_ms': {k: round(v, 3) for k, v in sorted(per_entry.items(), key=lambda kv: -kv[1])}},
         # the HBM-bound scoring kernel, PER RANK: this rank's algorithmic bytes / this rank's event time
         'roofline_scoring': {'kernel': 'eval_impressions_warp_kernel (gather + dot + segmented rank sort + metrics)', 'bound': 'hbm',
@@ -856,7 +856,7 @@ def main():
     ap.add_argument('--ref-batch', type=int, default=64, help='impressions per CPU step (reference arm / cpu_baseline)')
     ap.add_argument('--ref-eval-sample', type=int, default=400, help='impressions of the eval workload timed on the CPU')
     ap.add_argument('--precision', default='bf16x3', choices=['fp32', 'tf32x3', 'tf32', 'bf16', 'bf16x3'],
-                    help="bf16x3 (default) and tf32x3 are the fp32-accurate modes (1e-4 parity class): 3xBF16 on pre-split planes for "
+                    help="bf16x3 (default) and tf32x3 are the fp32-accurate modes (1e-4 parity class): a 3-pass 16-bit split on pre-split planes for "
                          "the token-level tensor-core launches + 3xTF32 elsewhere, or 3xTF32 everywhere; bf16 = the bf16 STORAGE mode "
                          "(2e-2 class)")
     ap.add_argument('--no-cpu-baseline', action='store_true')
